@@ -1,0 +1,143 @@
+"""ctypes binding of the C ABI (include/deepmimic_b200.h).  Device buffers are torch CUDA tensors; torch is only
+the allocator / stream plumbing here.  Raises if the CUDA library is missing -- there is no CPU fallback."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB_PATH = os.path.join(_REPO, "deepmimic_b200", "libdeepmimic_b200.so")
+_lib = None
+
+
+class DmDims(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("num_envs", "num_joints", "pose_dim", "num_dofs", "state_size", "goal_size", "action_size", "snapshot_size",
+                                        "updates_per_action", "num_update_substeps")] + [("motion_duration", C.c_double)]
+
+
+DM_STATE_OFFSET, DM_STATE_SCALE, DM_ACTION_OFFSET, DM_ACTION_SCALE, DM_ACTION_BOUND_MIN, DM_ACTION_BOUND_MAX, DM_STATE_NORM_GROUPS = range(7)
+
+EXPORTS = ["dm_create", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_stream", "dm_sync", "dm_set_mode", "dm_reset", "dm_set_action",
+           "dm_update", "dm_record_state", "dm_record_goal", "dm_calc_reward", "dm_observe", "dm_get_flags", "dm_step_host", "dm_get_snapshot",
+           "dm_set_snapshot", "dm_get_counters"]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError("deepmimic_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                               "There is no CPU fallback." % _LIB_PATH)
+        L = C.CDLL(_LIB_PATH)
+        vp, dp, fp, ip = C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p
+        L.dm_create.restype = vp
+        L.dm_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_uint64, C.c_uint64]
+        L.dm_destroy.argtypes = [vp]
+        L.dm_last_error.restype = C.c_char_p
+        L.dm_get_dims.argtypes = [vp, C.POINTER(DmDims)]
+        L.dm_get_static.argtypes = [vp, C.c_int, dp]
+        L.dm_stream.restype = vp
+        L.dm_stream.argtypes = [vp]
+        L.dm_sync.argtypes = [vp]
+        L.dm_set_mode.argtypes = [vp, C.c_int]
+        L.dm_reset.argtypes = [vp, C.c_int, dp, dp, dp]
+        L.dm_set_action.argtypes = [vp, fp]
+        L.dm_update.argtypes = [vp, C.c_double, C.c_int]
+        L.dm_record_state.argtypes = [vp, fp]
+        L.dm_record_goal.argtypes = [vp, fp]
+        L.dm_calc_reward.argtypes = [vp, fp]
+        L.dm_observe.argtypes = [vp, fp, fp]
+        L.dm_get_flags.argtypes = [vp, ip]
+        L.dm_step_host.argtypes = [vp, fp, C.c_double, C.c_int, fp, fp, ip]
+        L.dm_get_snapshot.argtypes = [vp, C.c_int, dp]
+        L.dm_set_snapshot.argtypes = [vp, C.c_int, dp]
+        L.dm_get_counters.argtypes = [vp, C.POINTER(C.c_int64)]
+        _lib = L
+    return _lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+class BatchedCore:
+    """Thin object wrapper over a dm_handle."""
+
+    def __init__(self, args, num_envs, asset_root, device=0, seed=0, global_env_offset=0):
+        L = lib()
+        enc = [a.encode() for a in args]
+        arr = (C.c_char_p * len(enc))(*enc)
+        self.h = L.dm_create(asset_root.encode(), len(enc), arr, num_envs, device, seed, global_env_offset)
+        if not self.h:
+            raise RuntimeError("dm_create failed: %s" % L.dm_last_error().decode())
+        self.h = C.c_void_p(self.h)
+        d = DmDims()
+        L.dm_get_dims(self.h, C.byref(d))
+        self.dims = d
+        self.num_envs = d.num_envs
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError("deepmimic_b200: %s" % lib().dm_last_error().decode())
+
+    def close(self):
+        if self.h:
+            lib().dm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def static(self, kind):
+        n = self.dims.state_size if kind in (DM_STATE_OFFSET, DM_STATE_SCALE, DM_STATE_NORM_GROUPS) else self.dims.action_size
+        out = np.zeros(n, dtype=np.float64)
+        self._chk(lib().dm_get_static(self.h, kind, _dptr(out)))
+        return out
+
+    def reset(self, force_all=True, kin_time=None, max_time=None, rot_theta=None):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        kt, mt, th = f(kin_time), f(max_time), f(rot_theta)
+        self._chk(lib().dm_reset(self.h, 1 if force_all else 0, _dptr(kt), _dptr(mt), _dptr(th)))
+
+    def set_action(self, actions):  # torch float32 cuda tensor [N, A]
+        self._chk(lib().dm_set_action(self.h, C.c_void_p(actions.data_ptr())))
+
+    def update(self, dt, n_updates=1):
+        self._chk(lib().dm_update(self.h, dt, n_updates))
+
+    def observe(self, state=None, reward=None):
+        self._chk(lib().dm_observe(self.h, C.c_void_p(state.data_ptr()) if state is not None else None,
+                                   C.c_void_p(reward.data_ptr()) if reward is not None else None))
+
+    def flags(self, out):  # torch int32 cuda tensor [N, 4]
+        self._chk(lib().dm_get_flags(self.h, C.c_void_p(out.data_ptr())))
+
+    def sync(self):
+        self._chk(lib().dm_sync(self.h))
+
+    def set_mode(self, mode):
+        self._chk(lib().dm_set_mode(self.h, mode))
+
+    def step_host(self, actions, dt, n_updates, state, reward, flags):  # numpy host arrays
+        p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+        self._chk(lib().dm_step_host(self.h, p(actions), dt, n_updates, p(state), p(reward), p(flags)))
+
+    def get_snapshot(self, env):
+        out = np.zeros(self.dims.snapshot_size, dtype=np.float64)
+        self._chk(lib().dm_get_snapshot(self.h, env, _dptr(out)))
+        return out
+
+    def set_snapshot(self, env, snap):
+        s = np.ascontiguousarray(snap, dtype=np.float64)
+        self._chk(lib().dm_set_snapshot(self.h, env, _dptr(s)))
+
+    def counters(self):
+        out = (C.c_int64 * 2)()
+        self._chk(lib().dm_get_counters(self.h, out))
+        return int(out[0]), int(out[1])
+
+    def stream(self):
+        return lib().dm_stream(self.h)

@@ -1,0 +1,515 @@
+// C-ABI implementation (include/deepmimic_b200.h): host-side scene construction from the reference's asset
+// formats, device model blob, launches of the sm_100a kernels.  No CPU fallback: every compute entry point
+// launches CUDA work and fails loudly if the device / kernels are unavailable.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/deepmimic_b200.h"
+#include "host/assets.hpp"
+#include "kernels/dm_model.cuh"
+
+namespace dmk {
+template <int W, int BLOCK>
+__global__ void dm_update_kernel(const DevModel*, DevState, const double*, const float*, double, int, int, int);
+template <int W, int BLOCK>
+__global__ void dm_observe_kernel(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
+template <int W, int BLOCK>
+__global__ void dm_reset_kernel(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*,
+                                unsigned long long, unsigned long long, int);
+__global__ void dm_set_action_kernel(const DevModel*, DevState, const float*, int);
+int dm_update_smem_bytes(int nl, int n, int cs, int maxrows, int tiles);
+
+__global__ void dm_flags_kernel(DevState st, int32_t* out, int num_real_envs) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= num_real_envs) return;
+    const int* f = st.flags + static_cast<size_t>(e) * kFlagInts;
+    out[e * 4 + 0] = f[kFNeedAction]; out[e * 4 + 1] = f[kFDone]; out[e * 4 + 2] = f[kFTerminate]; out[e * 4 + 3] = f[kFValid];
+}
+}  // namespace dmk
+
+static thread_local std::string g_err;
+#define DM_CUDA(call)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return fail(); } \
+    } while (0)
+
+struct dm_handle {
+    dmh::SceneAssets sa;
+    dmk::DevModel hm;        // host copy of the model blob
+    dmk::DevModel* d_model = nullptr;
+    dmk::DevState st{};
+    double* d_frame_times = nullptr;
+    float* d_frames = nullptr;
+    float* d_frame_vel = nullptr;
+    double* d_inj[3] = {nullptr, nullptr, nullptr};
+    int32_t* d_flags4 = nullptr;
+    float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;            // staging for dm_step_host
+    float *p_act = nullptr, *p_obs = nullptr, *p_rew = nullptr; int32_t* p_flags = nullptr;  // pinned host staging
+    cudaStream_t stream = nullptr;
+    int device = 0, num_envs = 0, padded_envs = 0, W = 32, tiles = 2, maxrows = 36, smem_bytes = 0, mode = 0;
+    uint64_t seed = 0, env_offset = 0;
+    int64_t launches = 0;
+    std::vector<double> st_off, st_scale, act_off, act_scale, act_min, act_max, st_groups;
+};
+
+namespace {
+
+int fail() { std::fprintf(stderr, "[deepmimic_b200] %s\n", g_err.c_str()); return 1; }
+
+using dmh::Quat; using dmh::V3;
+inline void put3(float* o, const V3& v, double s = 1.0) { o[0] = static_cast<float>(s * v.x); o[1] = static_cast<float>(s * v.y); o[2] = static_cast<float>(s * v.z); }
+inline void putq(float* o, const Quat& q) { o[0] = static_cast<float>(q.x); o[1] = static_cast<float>(q.y); o[2] = static_cast<float>(q.z); o[3] = static_cast<float>(q.w); }
+
+// Frame velocities of the clip, like cMotion::BuildFrameVel with cKinCharacter::CalcFrameVel -> cKinTree::CalcVel
+// (R/DeepMimicCore/anim/Motion.cpp:170-191, anim/KinTree.cpp:1281-1316): world-frame rotation vector for the root,
+// joint-local rotation vector for spherical joints, finite differences elsewhere.
+std::vector<double> build_frame_vel(const dmh::CharModel& cm, const dmh::MotionClip& mc) {
+    const int D = cm.pose_dim;
+    std::vector<double> fv(static_cast<size_t>(mc.num_frames) * D, 0.0);
+    for (int f = 0; f + 1 < mc.num_frames; ++f) {
+        const double* a = mc.frame(f); const double* b = mc.frame(f + 1);
+        const double dt = mc.frame_times[f + 1] - mc.frame_times[f];
+        double* o = &fv[static_cast<size_t>(f) * D];
+        for (int k = 0; k < 3; ++k) o[k] = (b[k] - a[k]) / dt;
+        Quat q0(a[3], a[4], a[5], a[6]), q1(b[3], b[4], b[5], b[6]);
+        V3 w = dmh::quat_to_rotvec(q1 * dmh::conj(q0));
+        o[3] = w.x / dt; o[4] = w.y / dt; o[5] = w.z / dt; o[6] = 0;
+        for (int j = 1; j < cm.num_joints(); ++j) {
+            const auto& jd = cm.joints[j];
+            const int p = jd.param_offset;
+            if (jd.type == dmh::kSpherical) {
+                Quat r0(a[p], a[p + 1], a[p + 2], a[p + 3]), r1(b[p], b[p + 1], b[p + 2], b[p + 3]);
+                V3 wl = dmh::quat_to_rotvec(dmh::conj(r0) * r1);
+                o[p] = wl.x / dt; o[p + 1] = wl.y / dt; o[p + 2] = wl.z / dt; o[p + 3] = 0;
+            } else for (int k = 0; k < jd.param_size; ++k) o[p + k] = (b[p + k] - a[p + k]) / dt;
+        }
+    }
+    if (mc.num_frames > 1) std::copy(fv.begin() + static_cast<size_t>(mc.num_frames - 2) * D, fv.begin() + static_cast<size_t>(mc.num_frames - 1) * D,
+                                     fv.begin() + static_cast<size_t>(mc.num_frames - 1) * D);
+    return fv;
+}
+
+// Digest the assets into the flat device model.  Frames follow cSimCharacter::BuildMultiBody
+// (R/DeepMimicCore/sim/SimCharacter.cpp:789-946): every link frame sits at the body's COM with the body's orientation.
+bool build_device_model(dm_handle& H) {
+    const dmh::SceneAssets& sa = H.sa;
+    const dmh::CharModel& cm = sa.character;
+    dmk::DevModel& M = H.hm;
+    std::memset(&M, 0, sizeof(M));
+    const int nl = cm.num_joints();
+    if (nl > dmk::kMaxLinks) { g_err = "character has more links than lanes (32)"; return false; }
+    if (cm.joints[0].type != dmh::kNone) { g_err = "only floating-base characters (root joint type 'none') are supported"; return false; }
+    if (sa.cfg.sync_char_root_rot) { g_err = "--sync_char_root_rot true is not supported by the batched path"; return false; }
+    const double sc = sa.cfg.world_scale;
+    M.nl = nl; M.scale = static_cast<float>(sc);
+    M.gravity[0] = static_cast<float>(sa.cfg.gravity.x * sc); M.gravity[1] = static_cast<float>(sa.cfg.gravity.y * sc); M.gravity[2] = static_cast<float>(sa.cfg.gravity.z * sc);
+    M.friction = static_cast<float>(0.9 * 0.9);   // link 0.9 (sim/SimCharacter.cpp:26) x ground 0.9 (sim/Ground.cpp:17), Bullet multiplies them
+    M.pose_dim = cm.pose_dim;
+    M.phase_input = sa.ctrl.enable_phase_input; M.rec_world_root_pos = sa.ctrl.record_world_root_pos; M.rec_world_root_rot = sa.ctrl.record_world_root_rot;
+    M.state_size = (M.phase_input ? 1 : 0) + 1 + nl * 9 + nl * 6;
+    M.num_frames = sa.motion.num_frames; M.loop_motion = sa.motion.loop;
+    M.enable_fall_end = sa.cfg.enable_fall_end; M.enable_contact_fall = sa.cfg.enable_char_contact_fall; M.sync_root_pos = sa.cfg.sync_char_root_pos;
+    M.sync_root_rot = sa.cfg.sync_char_root_rot; M.rand_rot_reset = sa.cfg.enable_rand_rot_reset;
+    M.motion_dur = sa.motion.duration(); M.cycle_period = sa.motion.duration(); M.query_dt = 1.0 / sa.ctrl.query_rate;
+    M.time_lim_min = sa.cfg.time_lim_min; M.time_lim_max = sa.cfg.time_lim_max; M.time_end_lim_max = sa.cfg.time_end_lim_max;
+    M.total_mass = static_cast<float>(cm.total_mass());
+    {
+        const double* fb = sa.motion.frame(0); const double* fe = sa.motion.frame(sa.motion.num_frames - 1);
+        M.cycle_delta[0] = static_cast<float>(fe[0] - fb[0]); M.cycle_delta[1] = 0.f; M.cycle_delta[2] = static_cast<float>(fe[2] - fb[2]);
+    }
+    double wsum = 0;
+    for (const auto& j : cm.joints) wsum += std::fabs(j.diff_weight);
+    int dof = 6, act_off = 0, maxlevel = 0, maxdepth = 5;
+    std::vector<int> last_depth(nl, 5);
+    for (int j = 0; j < nl; ++j) {
+        const auto& jd = cm.joints[j]; const auto& bd = cm.bodies[j];
+        dmk::DevLink& L = M.link[j];
+        L.parent = jd.parent;
+        const bool root = jd.parent < 0;
+        if (root || jd.type == dmh::kFixed) { L.jtype = dmk::kJFixed; L.ndof = 0; }
+        else if (jd.type == dmh::kRevolute) { L.jtype = dmk::kJRevolute; L.ndof = 1; }
+        else if (jd.type == dmh::kSpherical) { L.jtype = dmk::kJSpherical; L.ndof = 3; }
+        else { g_err = "unsupported joint type in character (planar / prismatic joints are outside the hot path)"; return false; }
+        L.dof0 = dof; dof += L.ndof;
+        L.level = root ? 0 : M.link[jd.parent].level + 1;
+        maxlevel = std::max(maxlevel, L.level);
+        L.nchild = 0;
+        if (!root) {
+            dmk::DevLink& P = M.link[jd.parent];
+            if (P.nchild >= dmk::kMaxChildren) { g_err = "a link has more than 4 children"; return false; }
+            P.child[P.nchild++] = j;
+        }
+        const int pd = root ? 5 : last_depth[jd.parent];
+        L.depth0 = pd + 1;
+        last_depth[j] = pd + L.ndof;
+        L.last_depth = last_depth[j];
+        maxdepth = std::max(maxdepth, last_depth[j]);
+        if (last_depth[j] >= dmk::kMaxChain) { g_err = "dof chain too long"; return false; }
+        if (root) for (int d = 0; d < 6; ++d) M.chain_dof[j][d] = static_cast<uint8_t>(d);
+        else for (int d = 0; d <= pd; ++d) M.chain_dof[j][d] = M.chain_dof[jd.parent][d];
+        for (int d = 0; d < L.ndof; ++d) { M.chain_dof[j][L.depth0 + d] = static_cast<uint8_t>(L.dof0 + d); M.dof_depth[L.dof0 + d] = static_cast<uint8_t>(L.depth0 + d); M.dof_link[L.dof0 + d] = static_cast<uint8_t>(j); }
+        L.anc_mask = (root ? 0u : M.link[jd.parent].anc_mask) | (1u << j);
+        // ---- frames
+        Quat this_to_parent = dmh::euler_to_quat(jd.attach_theta), body_to_this = dmh::euler_to_quat(bd.attach_theta);
+        Quat pb_to_parent; V3 pb_attach;
+        if (!root) { pb_to_parent = dmh::euler_to_quat(cm.bodies[jd.parent].attach_theta); pb_attach = cm.bodies[jd.parent].attach_pt; }
+        Quat parent_to_pb = dmh::conj(pb_to_parent);
+        Quat body_to_pb = parent_to_pb * this_to_parent * body_to_this;
+        putq(L.zrot, dmh::conj(body_to_pb));
+        V3 e = dmh::rotate(parent_to_pb, jd.attach_pt) - dmh::rotate(parent_to_pb, pb_attach);
+        V3 d = dmh::rotate(dmh::conj(body_to_this), bd.attach_pt);
+        put3(L.evec, e, sc); put3(L.dvec, d, sc);
+        put3(L.axis, dmh::rotate(dmh::conj(body_to_this), V3(0, 0, 1)));
+        putq(L.child_rot, dmh::conj(body_to_this));
+        put3(L.child_pos, -1.0 * dmh::rotate(dmh::conj(body_to_this), bd.attach_pt));
+        put3(L.att_pt, jd.attach_pt); putq(L.att_rot, this_to_parent); put3(L.body_att, bd.attach_pt);
+        // ---- mass properties at scaled size
+        L.mass = static_cast<float>(bd.mass);
+        const double m = bd.mass;
+        if (bd.shape == dmh::kShapeBox) {
+            L.shape = dmk::kSBox;
+            const double hx = 0.5 * sc * bd.param[0], hy = 0.5 * sc * bd.param[1], hz = 0.5 * sc * bd.param[2];
+            L.he[0] = static_cast<float>(hx); L.he[1] = static_cast<float>(hy); L.he[2] = static_cast<float>(hz);
+            const double ix = m / 12.0 * (4 * hy * hy + 4 * hz * hz), iy = m / 12.0 * (4 * hx * hx + 4 * hz * hz), iz = m / 12.0 * (4 * hx * hx + 4 * hy * hy);
+            L.inertiaB[0] = L.inertiaD[0] = static_cast<float>(ix); L.inertiaB[1] = L.inertiaD[1] = static_cast<float>(iy); L.inertiaB[2] = L.inertiaD[2] = static_cast<float>(iz);
+            L.break_thr = static_cast<float>(0.02 * std::sqrt(hx * hx + hy * hy + hz * hz));
+        } else if (bd.shape == dmh::kShapeCapsule) {
+            L.shape = dmk::kSCapsule;
+            const double r = 0.5 * sc * bd.param[0], hgt = sc * bd.param[1], hh = 0.5 * hgt;
+            L.he[0] = static_cast<float>(r); L.he[1] = static_cast<float>(hh); L.he[2] = 0.f;
+            // Bullet: inertia of the capsule's bounding box (btCapsuleShape::calculateLocalInertia)
+            const double lx = 2 * r, ly = 2 * (r + hh), lz = 2 * r, sm = m * 0.08333333;
+            L.inertiaB[0] = static_cast<float>(sm * (ly * ly + lz * lz)); L.inertiaB[1] = static_cast<float>(sm * (lx * lx + lz * lz)); L.inertiaB[2] = static_cast<float>(sm * (lx * lx + ly * ly));
+            // DeepMimic SPD model: exact capsule (cRBDUtil::BuildMomentInertiaCapsule, RBDUtil.cpp:667-694)
+            const double c_vol = M_PI * r * r * hgt, hs_vol = M_PI * 2.0 / 3.0 * r * r * r, dens = m / (c_vol + 2 * hs_vol), cmass = c_vol * dens, hsm = hs_vol * dens;
+            const double x = cmass * (0.25 * r * r + hgt * hgt / 12.0) + 2 * hsm * (0.4 * r * r + 0.375 * r * hgt + 0.25 * hgt * hgt), y = (0.5 * cmass + 0.8 * hsm) * r * r;
+            L.inertiaD[0] = static_cast<float>(x); L.inertiaD[1] = static_cast<float>(y); L.inertiaD[2] = static_cast<float>(x);
+            L.break_thr = static_cast<float>(0.02 * std::sqrt(2 * r * r + (r + hh) * (r + hh)));
+        } else if (bd.shape == dmh::kShapeSphere) {
+            L.shape = dmk::kSSphere;
+            const double r = 0.5 * sc * bd.param[0];
+            L.he[0] = static_cast<float>(r);
+            const double i = 0.4 * m * r * r;
+            for (int k = 0; k < 3; ++k) L.inertiaB[k] = L.inertiaD[k] = static_cast<float>(i);
+            L.break_thr = static_cast<float>(0.02 * std::sqrt(3.0) * r);
+        } else { g_err = "unsupported body shape (box / capsule / sphere only)"; return false; }
+        L.fall_contact = bd.fall_contact; L.end_eff = jd.is_end_eff;
+        L.kp = static_cast<float>(sc * sc * (root ? 0.0 : sa.ctrl.pd[j].kp)); L.kd = static_cast<float>(sc * sc * (root ? 0.0 : sa.ctrl.pd[j].kd));
+        L.tlim = std::isfinite(jd.torque_lim) ? static_cast<float>(sc * sc * jd.torque_lim) : 3.0e38f;
+        L.has_limit = (L.jtype == dmk::kJRevolute && jd.lim_low[0] <= jd.lim_high[1]) ? 1 : 0;   // sic: sim/SimCharacter.cpp:958
+        L.lim_lo = static_cast<float>(jd.lim_low[0]); L.lim_hi = static_cast<float>(jd.lim_high[0]);
+        L.joint_w = static_cast<float>(jd.diff_weight / wsum);
+        L.pose_off = jd.param_offset; L.pose_size = jd.param_size;
+        L.act_off = act_off; L.act_size = root ? 0 : (jd.type == dmh::kSpherical ? 3 : jd.param_size);
+        act_off += L.act_size;
+    }
+    M.n = dof; M.maxlevel = maxlevel; M.action_size = act_off;
+    M.cs = ((maxdepth + 1 + 7) / 8) * 8;
+    if (M.n > dmk::kMaxDofs) { g_err = "too many dofs"; return false; }
+    return true;
+}
+
+// static tables the agent reads once (cCtController / cCtCtrlUtil)
+void build_statics(dm_handle& H) {
+    const auto& cm = H.sa.character; const auto& M = H.hm;
+    H.st_off.assign(M.state_size, 0.0); H.st_scale.assign(M.state_size, 1.0); H.st_groups.assign(M.state_size, 0.0);
+    if (M.phase_input) { H.st_off[0] = -0.5; H.st_scale[0] = 2.0; H.st_groups[0] = -1.0; }   // CtController.cpp:54-69,268-279,364-371
+    H.act_off.assign(M.action_size, 0.0); H.act_scale.assign(M.action_size, 1.0); H.act_min.assign(M.action_size, 0.0); H.act_max.assign(M.action_size, 0.0);
+    for (int j = 1; j < M.nl; ++j) {
+        const auto& jd = cm.joints[j]; const auto& L = M.link[j];
+        if (jd.type == dmh::kSpherical) {
+            for (int k = 0; k < 3; ++k) { H.act_off[L.act_off + k] = 0; H.act_scale[L.act_off + k] = 2.0 / (2.0 * M_PI); H.act_min[L.act_off + k] = -2.0 * M_PI; H.act_max[L.act_off + k] = 2.0 * M_PI; }
+        } else if (jd.type == dmh::kRevolute) {
+            double lo = jd.lim_low[0], hi = jd.lim_high[0];
+            if (!(hi >= lo)) { lo = -M_PI; hi = M_PI; }
+            H.act_off[L.act_off] = -0.5 * (hi + lo); H.act_scale[L.act_off] = 0.5 / (hi - lo);
+            const double mean = 0.5 * (hi + lo), delta = hi - lo;
+            H.act_min[L.act_off] = mean - 2 * delta; H.act_max[L.act_off] = mean + 2 * delta;
+        }
+    }
+}
+
+template <int W>
+int launch_update(dm_handle* h, double dt, int n_updates) {
+    constexpr int BLOCK = 64;
+    auto kern = dmk::dm_update_kernel<W, BLOCK>;
+    static thread_local const void* configured = nullptr;
+    if (configured != reinterpret_cast<const void*>(kern)) {
+        DM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+        DM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = reinterpret_cast<const void*>(kern);
+    }
+    const int grid = h->padded_envs / (BLOCK / W);
+    kern<<<grid, BLOCK, h->smem_bytes, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, dt, n_updates, h->sa.cfg.num_sim_substeps, h->maxrows);
+    DM_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+template <int W>
+int launch_observe(dm_handle* h, float* d_state, float* d_reward) {
+    constexpr int BLOCK = 64;
+    const int grid = h->padded_envs / (BLOCK / W);
+    dmk::dm_observe_kernel<W, BLOCK><<<grid, BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, d_state, d_reward, h->num_envs);
+    DM_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+template <int W>
+int launch_reset(dm_handle* h, int force, const double* kt, const double* mt, const double* th) {
+    constexpr int BLOCK = 64;
+    const int grid = h->padded_envs / (BLOCK / W);
+    dmk::dm_reset_kernel<W, BLOCK><<<grid, BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, force, kt, mt, th, h->seed, h->env_offset, h->mode);
+    DM_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dm_last_error(void) { return g_err.c_str(); }
+
+dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int num_envs, int device, uint64_t seed, uint64_t global_env_offset) {
+    std::unique_ptr<dm_handle> h(new dm_handle());
+    try {
+        std::vector<std::string> args(argv, argv + argc);
+        dmh::ArgParser ap;
+        ap.LoadArgs(args);
+        std::string root = asset_root ? asset_root : "", arg_file;
+        if (ap.ParseString("arg_file", arg_file) && !ap.LoadFile(dmh::resolve_path(root, arg_file))) throw std::runtime_error("Failed to load args from: " + arg_file);
+        h->sa = dmh::load_scene_assets(ap, root);
+    } catch (const std::exception& e) { g_err = e.what(); fail(); return nullptr; }
+    if (num_envs <= 0) { g_err = "num_envs must be positive"; fail(); return nullptr; }
+    if (!build_device_model(*h)) { fail(); return nullptr; }
+    build_statics(*h);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device available: deepmimic_b200 has no CPU fallback"; fail(); return nullptr; }
+    auto chk = [&](cudaError_t e, const char* what) { if (e != cudaSuccess) { g_err = std::string(what) + ": " + cudaGetErrorString(e); return false; } return true; };
+    if (!chk(cudaSetDevice(device), "cudaSetDevice")) { fail(); return nullptr; }
+    h->device = device; h->seed = seed; h->env_offset = global_env_offset; h->num_envs = num_envs;
+    const auto& M = h->hm;
+    h->W = (M.nl <= 16 && M.cs <= 16) ? 16 : 32;
+    if (const char* w = std::getenv("DM_TILE_WIDTH")) { int v = std::atoi(w); if (v == 32 || (v == 16 && M.nl <= 16 && M.cs <= 16)) h->W = v; }
+    h->tiles = 64 / h->W;
+    h->padded_envs = ((num_envs + h->tiles - 1) / h->tiles) * h->tiles;
+    h->maxrows = (h->W == 16) ? 36 : 60;
+    if (const char* r = std::getenv("DM_MAX_ROWS")) { int v = std::atoi(r); if (v >= 12 && v <= 96) h->maxrows = (v / 3) * 3; }
+    h->smem_bytes = dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, h->tiles);
+    const size_t N = static_cast<size_t>(h->padded_envs);
+    const int ss = dmk::sim_stride(M.nl);
+    bool ok = chk(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
+              chk(cudaMalloc(&h->d_model, sizeof(dmk::DevModel)), "cudaMalloc model") &&
+              chk(cudaMalloc(&h->st.sim, N * ss * sizeof(float)), "cudaMalloc sim") &&
+              chk(cudaMalloc(&h->st.time, N * dmk::kTimeDoubles * sizeof(double)), "cudaMalloc time") &&
+              chk(cudaMalloc(&h->st.flags, N * dmk::kFlagInts * sizeof(int)), "cudaMalloc flags") &&
+              chk(cudaMalloc(&h->st.manifold, N * M.nl * dmk::kManifoldFloats * sizeof(float)), "cudaMalloc manifold") &&
+              chk(cudaMalloc(&h->d_frame_times, sizeof(double) * M.num_frames), "cudaMalloc frame_times") &&
+              chk(cudaMalloc(&h->d_frames, sizeof(float) * M.num_frames * M.pose_dim), "cudaMalloc frames") &&
+              chk(cudaMalloc(&h->d_frame_vel, sizeof(float) * M.num_frames * M.pose_dim), "cudaMalloc frame_vel") &&
+              chk(cudaMalloc(&h->d_flags4, N * 4 * sizeof(int32_t)), "cudaMalloc flags4") &&
+              chk(cudaMalloc(&h->d_act, N * std::max(1, M.action_size) * sizeof(float)), "cudaMalloc act") &&
+              chk(cudaMalloc(&h->d_obs, N * M.state_size * sizeof(float)), "cudaMalloc obs") && chk(cudaMalloc(&h->d_rew, N * sizeof(float)), "cudaMalloc rew") &&
+              chk(cudaMallocHost(&h->p_act, N * std::max(1, M.action_size) * sizeof(float)), "cudaMallocHost") &&
+              chk(cudaMallocHost(&h->p_obs, N * M.state_size * sizeof(float)), "cudaMallocHost") && chk(cudaMallocHost(&h->p_rew, N * sizeof(float)), "cudaMallocHost") &&
+              chk(cudaMallocHost(&h->p_flags, N * 4 * sizeof(int32_t)), "cudaMallocHost");
+    for (int k = 0; k < 3 && ok; ++k) ok = chk(cudaMalloc(&h->d_inj[k], N * sizeof(double)), "cudaMalloc inject");
+    if (!ok) { fail(); dm_destroy(h.release()); return nullptr; }
+    h->st.pdbg = nullptr; h->st.num_envs = h->padded_envs;
+    std::vector<float> frames(static_cast<size_t>(M.num_frames) * M.pose_dim), fvel(frames.size());
+    std::vector<double> fv = build_frame_vel(h->sa.character, h->sa.motion);
+    for (size_t i = 0; i < frames.size(); ++i) { frames[i] = static_cast<float>(h->sa.motion.frames[i]); fvel[i] = static_cast<float>(fv[i]); }
+    ok = chk(cudaMemcpy(h->d_model, &h->hm, sizeof(dmk::DevModel), cudaMemcpyHostToDevice), "memcpy model") &&
+         chk(cudaMemcpy(h->d_frame_times, h->sa.motion.frame_times.data(), sizeof(double) * M.num_frames, cudaMemcpyHostToDevice), "memcpy ft") &&
+         chk(cudaMemcpy(h->d_frames, frames.data(), sizeof(float) * frames.size(), cudaMemcpyHostToDevice), "memcpy frames") &&
+         chk(cudaMemcpy(h->d_frame_vel, fvel.data(), sizeof(float) * fvel.size(), cudaMemcpyHostToDevice), "memcpy fvel") &&
+         chk(cudaMemset(h->st.sim, 0, N * ss * sizeof(float)), "memset") && chk(cudaMemset(h->st.time, 0, N * dmk::kTimeDoubles * sizeof(double)), "memset") &&
+         chk(cudaMemset(h->st.flags, 0, N * dmk::kFlagInts * sizeof(int)), "memset") && chk(cudaMemset(h->st.manifold, 0, N * M.nl * dmk::kManifoldFloats * sizeof(float)), "memset");
+    if (ok) {
+        // initial PD targets: identity / TargetTheta0 (cPDController::Init, PDController.cpp:99-112)
+        std::vector<float> sim(N * ss, 0.f);
+        for (size_t e = 0; e < N; ++e) for (int j = 0; j < M.nl; ++j) {
+            float* t = &sim[e * ss + 16 + 8 * M.nl + 4 * j];
+            if (M.link[j].jtype == dmk::kJSpherical) { t[0] = t[1] = t[2] = 0.f; t[3] = 1.f; }
+            else t[0] = static_cast<float>(h->sa.ctrl.pd[j].target_theta[0]);
+        }
+        ok = chk(cudaMemcpy(h->st.sim, sim.data(), sim.size() * sizeof(float), cudaMemcpyHostToDevice), "memcpy sim");
+    }
+    if (!ok) { fail(); dm_destroy(h.release()); return nullptr; }
+    if (dm_reset(h.get(), 1, nullptr, nullptr, nullptr) != 0 || dm_sync(h.get()) != 0) { dm_destroy(h.release()); return nullptr; }
+    return h.release();
+}
+
+void dm_destroy(dm_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_model); cudaFree(h->st.sim); cudaFree(h->st.time); cudaFree(h->st.flags); cudaFree(h->st.manifold);
+    cudaFree(h->d_frame_times); cudaFree(h->d_frames); cudaFree(h->d_frame_vel); cudaFree(h->d_flags4); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew);
+    for (auto& p : h->d_inj) cudaFree(p);
+    cudaFreeHost(h->p_act); cudaFreeHost(h->p_obs); cudaFreeHost(h->p_rew); cudaFreeHost(h->p_flags);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int dm_get_dims(dm_handle* h, dm_dims* o) {
+    const auto& M = h->hm;
+    o->num_envs = h->num_envs; o->num_joints = M.nl; o->pose_dim = M.pose_dim; o->num_dofs = M.n; o->state_size = M.state_size; o->goal_size = 0;
+    o->action_size = M.action_size; o->snapshot_size = 29 + 59 * M.nl;
+    o->num_update_substeps = h->sa.cfg.num_update_substeps;
+    o->updates_per_action = 20;
+    o->motion_duration = M.motion_dur;
+    return 0;
+}
+int dm_get_static(dm_handle* h, int kind, double* out) {
+    const std::vector<double>* v = nullptr;
+    switch (kind) {
+        case DM_STATE_OFFSET: v = &h->st_off; break; case DM_STATE_SCALE: v = &h->st_scale; break; case DM_ACTION_OFFSET: v = &h->act_off; break;
+        case DM_ACTION_SCALE: v = &h->act_scale; break; case DM_ACTION_BOUND_MIN: v = &h->act_min; break; case DM_ACTION_BOUND_MAX: v = &h->act_max; break;
+        case DM_STATE_NORM_GROUPS: v = &h->st_groups; break; default: g_err = "dm_get_static: bad kind"; return fail();
+    }
+    std::copy(v->begin(), v->end(), out);
+    return 0;
+}
+void* dm_stream(dm_handle* h) { return h->stream; }
+int dm_sync(dm_handle* h) { DM_CUDA(cudaStreamSynchronize(h->stream)); return 0; }
+int dm_set_mode(dm_handle* h, int mode) { h->mode = mode; return 0; }
+
+int dm_reset(dm_handle* h, int force_all, const double* kt, const double* mt, const double* th) {
+    DM_CUDA(cudaSetDevice(h->device));
+    const double* src[3] = {kt, mt, th}; const double* dev[3] = {nullptr, nullptr, nullptr};
+    std::vector<double> tmp(h->padded_envs);
+    for (int k = 0; k < 3; ++k) if (src[k]) {
+        for (int e = 0; e < h->padded_envs; ++e) tmp[e] = src[k][e < h->num_envs ? e : h->num_envs - 1];
+        DM_CUDA(cudaMemcpyAsync(h->d_inj[k], tmp.data(), sizeof(double) * h->padded_envs, cudaMemcpyHostToDevice, h->stream));
+        DM_CUDA(cudaStreamSynchronize(h->stream));
+        dev[k] = h->d_inj[k];
+    }
+    return h->W == 16 ? launch_reset<16>(h, force_all, dev[0], dev[1], dev[2]) : launch_reset<32>(h, force_all, dev[0], dev[1], dev[2]);
+}
+int dm_set_action(dm_handle* h, const float* d_actions) {
+    DM_CUDA(cudaSetDevice(h->device));
+    const int total = h->num_envs * h->hm.nl;
+    dmk::dm_set_action_kernel<<<(total + 127) / 128, 128, 0, h->stream>>>(h->d_model, h->st, d_actions, h->num_envs);
+    DM_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+int dm_update(dm_handle* h, double dt, int n_updates) {
+    DM_CUDA(cudaSetDevice(h->device));
+    return h->W == 16 ? launch_update<16>(h, dt, n_updates) : launch_update<32>(h, dt, n_updates);
+}
+int dm_observe(dm_handle* h, float* d_state, float* d_reward) {
+    DM_CUDA(cudaSetDevice(h->device));
+    return h->W == 16 ? launch_observe<16>(h, d_state, d_reward) : launch_observe<32>(h, d_state, d_reward);
+}
+int dm_record_state(dm_handle* h, float* d_out) { return dm_observe(h, d_out, nullptr); }
+int dm_record_goal(dm_handle*, float*) { return 0; }
+int dm_calc_reward(dm_handle* h, float* d_out) { return dm_observe(h, nullptr, d_out); }
+int dm_get_flags(dm_handle* h, int32_t* d_flags) {
+    DM_CUDA(cudaSetDevice(h->device));
+    dmk::dm_flags_kernel<<<(h->num_envs + 127) / 128, 128, 0, h->stream>>>(h->st, d_flags, h->num_envs);
+    DM_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+int dm_step_host(dm_handle* h, const float* h_actions, double dt, int n_updates, float* h_state, float* h_reward, int32_t* h_flags) {
+    DM_CUDA(cudaSetDevice(h->device));
+    const size_t N = h->num_envs, A = h->hm.action_size, S = h->hm.state_size;
+    if (h_actions) {
+        std::memcpy(h->p_act, h_actions, N * A * sizeof(float));
+        DM_CUDA(cudaMemcpyAsync(h->d_act, h->p_act, N * A * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        if (dm_set_action(h, h->d_act)) return 1;
+    }
+    if (n_updates > 0 && dm_update(h, dt, n_updates)) return 1;
+    if (dm_observe(h, h_state ? h->d_obs : nullptr, h_reward ? h->d_rew : nullptr)) return 1;
+    if (h_flags && dm_get_flags(h, h->d_flags4)) return 1;
+    if (h_state) DM_CUDA(cudaMemcpyAsync(h->p_obs, h->d_obs, N * S * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (h_reward) DM_CUDA(cudaMemcpyAsync(h->p_rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (h_flags) DM_CUDA(cudaMemcpyAsync(h->p_flags, h->d_flags4, N * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    DM_CUDA(cudaStreamSynchronize(h->stream));
+    if (h_state) std::memcpy(h_state, h->p_obs, N * S * sizeof(float));
+    if (h_reward) std::memcpy(h_reward, h->p_rew, N * sizeof(float));
+    if (h_flags) std::memcpy(h_flags, h->p_flags, N * 4 * sizeof(int32_t));
+    return 0;
+}
+
+int dm_get_snapshot(dm_handle* h, int env, double* s) {
+    DM_CUDA(cudaSetDevice(h->device));
+    const auto& M = h->hm; const int nl = M.nl, ss = dmk::sim_stride(nl);
+    std::vector<float> sim(ss), man(nl * dmk::kManifoldFloats); double tm[dmk::kTimeDoubles]; int fl[dmk::kFlagInts];
+    DM_CUDA(cudaStreamSynchronize(h->stream));
+    DM_CUDA(cudaMemcpy(sim.data(), h->st.sim + static_cast<size_t>(env) * ss, ss * sizeof(float), cudaMemcpyDeviceToHost));
+    DM_CUDA(cudaMemcpy(man.data(), h->st.manifold + static_cast<size_t>(env) * nl * dmk::kManifoldFloats, man.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    DM_CUDA(cudaMemcpy(tm, h->st.time + static_cast<size_t>(env) * dmk::kTimeDoubles, sizeof(tm), cudaMemcpyDeviceToHost));
+    DM_CUDA(cudaMemcpy(fl, h->st.flags + static_cast<size_t>(env) * dmk::kFlagInts, sizeof(fl), cudaMemcpyDeviceToHost));
+    std::fill(s, s + 29 + 59 * nl, 0.0);
+    for (int k = 0; k < 3; ++k) { s[k] = sim[k]; s[7 + k] = sim[8 + k]; s[10 + k] = sim[12 + k]; }
+    for (int k = 0; k < 4; ++k) s[3 + k] = sim[4 + k];
+    for (int j = 0; j < nl; ++j) {
+        if (M.link[j].ndof > 0) for (int k = 0; k < 4; ++k) s[13 + 4 * j + k] = sim[16 + 4 * j + k];
+        else s[13 + 4 * j + 3] = 1.0;
+        for (int k = 0; k < M.link[j].ndof; ++k) s[13 + 4 * nl + 3 * j + k] = sim[16 + 4 * nl + 4 * j + k];
+        for (int c = 0; c < 4; ++c) for (int k = 0; k < 12; ++k) s[13 + 7 * nl + (j * 4 + c) * 12 + k] = man[j * dmk::kManifoldFloats + c * 12 + k];
+        // PD target back to the joint-frame (w,x,y,z) convention
+        const float* t = &sim[16 + 8 * nl + 4 * j]; double* o = s + 29 + 55 * nl + 4 * j;
+        if (M.link[j].jtype == dmk::kJSpherical) {
+            Quat cr(M.link[j].child_rot[3], M.link[j].child_rot[0], M.link[j].child_rot[1], M.link[j].child_rot[2]);
+            Quat q = dmh::conj(cr) * Quat(t[3], t[0], t[1], t[2]) * cr;
+            o[0] = q.w; o[1] = q.x; o[2] = q.y; o[3] = q.z;
+        } else if (M.link[j].jtype == dmk::kJRevolute) o[0] = t[0];
+    }
+    double* q = s + 13 + 55 * nl;
+    q[0] = tm[dmk::kTKin]; q[1] = tm[dmk::kTOrigin]; q[2] = tm[dmk::kTOrigin + 1]; q[3] = tm[dmk::kTOrigin + 2];
+    for (int k = 0; k < 4; ++k) q[4 + k] = tm[dmk::kTOriginRot + k];
+    q[8] = tm[dmk::kTCtrl]; q[9] = tm[dmk::kTInitOff]; q[10] = tm[dmk::kTPrevAct]; q[11] = fl[dmk::kFNeedAction]; q[12] = tm[dmk::kTTimer]; q[13] = tm[dmk::kTTimerMax];
+    return 0;
+}
+int dm_set_snapshot(dm_handle* h, int env, const double* s) {
+    DM_CUDA(cudaSetDevice(h->device));
+    const auto& M = h->hm; const int nl = M.nl, ss = dmk::sim_stride(nl);
+    std::vector<float> sim(ss, 0.f), man(nl * dmk::kManifoldFloats, 0.f); double tm[dmk::kTimeDoubles] = {0}; int fl[dmk::kFlagInts] = {0};
+    DM_CUDA(cudaStreamSynchronize(h->stream));
+    DM_CUDA(cudaMemcpy(fl, h->st.flags + static_cast<size_t>(env) * dmk::kFlagInts, sizeof(fl), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; ++k) { sim[k] = static_cast<float>(s[k]); sim[8 + k] = static_cast<float>(s[7 + k]); sim[12 + k] = static_cast<float>(s[10 + k]); }
+    for (int k = 0; k < 4; ++k) sim[4 + k] = static_cast<float>(s[3 + k]);
+    for (int j = 0; j < nl; ++j) {
+        for (int k = 0; k < 4; ++k) sim[16 + 4 * j + k] = static_cast<float>(s[13 + 4 * j + k]);
+        for (int k = 0; k < M.link[j].ndof; ++k) sim[16 + 4 * nl + 4 * j + k] = static_cast<float>(s[13 + 4 * nl + 3 * j + k]);
+        for (int c = 0; c < 4; ++c) for (int k = 0; k < 12; ++k) man[j * dmk::kManifoldFloats + c * 12 + k] = static_cast<float>(s[13 + 7 * nl + (j * 4 + c) * 12 + k]);
+        const double* o = s + 29 + 55 * nl + 4 * j; float* t = &sim[16 + 8 * nl + 4 * j];
+        if (M.link[j].jtype == dmk::kJSpherical) {
+            Quat cr(M.link[j].child_rot[3], M.link[j].child_rot[0], M.link[j].child_rot[1], M.link[j].child_rot[2]);
+            Quat q = cr * Quat(o[0], o[1], o[2], o[3]) * dmh::conj(cr);
+            t[0] = static_cast<float>(q.x); t[1] = static_cast<float>(q.y); t[2] = static_cast<float>(q.z); t[3] = static_cast<float>(q.w);
+        } else if (M.link[j].jtype == dmk::kJRevolute) t[0] = static_cast<float>(o[0]);
+    }
+    const double* q = s + 13 + 55 * nl;
+    tm[dmk::kTKin] = q[0]; tm[dmk::kTOrigin] = q[1]; tm[dmk::kTOrigin + 1] = q[2]; tm[dmk::kTOrigin + 2] = q[3];
+    for (int k = 0; k < 4; ++k) tm[dmk::kTOriginRot + k] = q[4 + k];
+    tm[dmk::kTCtrl] = q[8]; tm[dmk::kTInitOff] = q[9]; tm[dmk::kTPrevAct] = q[10]; tm[dmk::kTTimer] = q[12]; tm[dmk::kTTimerMax] = q[13];
+    fl[dmk::kFNeedAction] = q[11] != 0; fl[dmk::kFDone] = 0; fl[dmk::kFTerminate] = 0; fl[dmk::kFValid] = 1; fl[dmk::kFFallen] = 0;
+    DM_CUDA(cudaMemcpy(h->st.sim + static_cast<size_t>(env) * ss, sim.data(), ss * sizeof(float), cudaMemcpyHostToDevice));
+    DM_CUDA(cudaMemcpy(h->st.manifold + static_cast<size_t>(env) * nl * dmk::kManifoldFloats, man.data(), man.size() * sizeof(float), cudaMemcpyHostToDevice));
+    DM_CUDA(cudaMemcpy(h->st.time + static_cast<size_t>(env) * dmk::kTimeDoubles, tm, sizeof(tm), cudaMemcpyHostToDevice));
+    DM_CUDA(cudaMemcpy(h->st.flags + static_cast<size_t>(env) * dmk::kFlagInts, fl, sizeof(fl), cudaMemcpyHostToDevice));
+    return 0;
+}
+int dm_get_counters(dm_handle* h, int64_t* out) {
+    DM_CUDA(cudaSetDevice(h->device));
+    DM_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<int> fl(static_cast<size_t>(h->padded_envs) * dmk::kFlagInts);
+    DM_CUDA(cudaMemcpy(fl.data(), h->st.flags, fl.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    int64_t over = 0;
+    for (int e = 0; e < h->num_envs; ++e) over += fl[static_cast<size_t>(e) * dmk::kFlagInts + dmk::kFRowOverflow];
+    out[0] = h->launches; out[1] = over;
+    return 0;
+}
+
+}  // extern "C"

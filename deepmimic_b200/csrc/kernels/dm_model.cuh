@@ -1,0 +1,92 @@
+// Flat, immutable device model ("model blob") and per-environment state layout for the batched
+// DeepMimic step.  Everything the kernels need about a character / controller / clip is
+// pre-digested on the host (capi.cu: build_device_model) from the reference's asset files:
+//   multibody frames + inertias  <- cSimCharacter::BuildMultiBody   (R/DeepMimicCore/sim/SimCharacter.cpp:789-946)
+//   exact-shape inertias for SPD <- cRBDUtil::BuildMomentInertia*   (R/DeepMimicCore/sim/RBDUtil.cpp:615-740)
+//   PD gains / torque limits     <- cImpPDController::InitGains     (R/DeepMimicCore/sim/ImpPDController.cpp:97-127)
+// All lengths are in Bullet's scaled units (x world_scale, sim/World.cpp:229-235), like the reference's
+// physics world; observations / rewards divide back.
+#pragma once
+#include <cstdint>
+
+#include "dm_math.cuh"
+
+namespace dmk {
+
+constexpr int kMaxLinks = 32;   // one lane per link
+constexpr int kMaxDofs = 96;    // 6 + joint dofs (humanoid3d 34, dog3d 70)
+constexpr int kMaxChain = 24;   // longest root->leaf dof chain (humanoid3d 13, dog3d 22)
+constexpr int kMaxChildren = 4;
+constexpr int kMaxRows = 64;    // solver rows kept per env (contact rows come in triples) -- see DESIGN.md capacity note
+constexpr int kManifoldFloats = 48;  // per link: 4 points x 12 floats
+
+enum DevJointType { kJRevolute = 0, kJSpherical = 1, kJFixed = 2 };
+enum DevShape { kSBox = 1, kSCapsule = 2, kSSphere = 3 };
+
+struct DevLink {
+    int parent, jtype, ndof, dof0;        // dof0: index of first joint dof in the (6+ndofs) generalised vector
+    int level, nchild, child[kMaxChildren];
+    int depth0;                           // chain depth of the first joint dof (base dofs have depth 0..5)
+    int last_depth;                       // deepest dof depth on the chain base -> this link (5 for links hanging off the base without dofs)
+    int shape, fall_contact, end_eff, has_limit;
+    uint32_t anc_mask;                    // bit a set <=> link a is an ancestor-or-self
+    float mass;
+    float inertiaB[3];                    // Bullet collision-shape inertia (diag, link frame)
+    float inertiaD[3];                    // exact-shape inertia used by DeepMimic's SPD model
+    float dvec[3], evec[3];               // joint pivot -> COM (this frame) ; parent COM -> pivot (parent frame)
+    float zrot[4];                        // parent->this rotation at q = 0 (x,y,z,w)
+    float axis[3];                        // revolute axis, this frame
+    float kp, kd, tlim;                   // scaled units (x scale^2)
+    float he[3];                          // box half extents / capsule (radius, halfHeight) / sphere (radius)
+    float break_thr;
+    float lim_lo, lim_hi;
+    float child_rot[4];                   // DeepMimic joint frame -> body frame (x,y,z,w)  (cSimBodyJoint::mChildRot)
+    float child_pos[3];                   // joint origin in the body frame, UNscaled (cSimBodyJoint::mChildPos)
+    float joint_w;                        // normalised DiffWeight (SceneImitate.cpp:236-248)
+    float att_pt[3], att_rot[4];          // DeepMimic joint attach point (parent joint frame, UNscaled) and attach rotation (x,y,z,w)
+    float body_att[3];                    // body COM in its joint frame, UNscaled (BodyDefs.Attach*)
+    int pose_off, pose_size;              // DeepMimic pose-vector slot of this joint
+    int act_off, act_size;                // action-vector slot
+};
+
+struct DevModel {
+    int nl, n, maxlevel, cs;              // links, 6+dofs, deepest tree level, chain stride
+    int pose_dim, state_size, action_size;
+    int phase_input, rec_world_root_pos, rec_world_root_rot;
+    int num_frames, loop_motion;
+    int enable_fall_end, enable_contact_fall, sync_root_pos, sync_root_rot, rand_rot_reset;
+    float scale, gravity[3], friction;
+    float total_mass;
+    double motion_dur, cycle_period, query_dt, time_lim_min, time_lim_max, time_end_lim_max;
+    float cycle_delta[3];
+    DevLink link[kMaxLinks];
+    uint8_t chain_dof[kMaxLinks][kMaxChain];  // dof index at chain depth d on the path base -> link (valid for d <= last depth of link)
+    uint8_t dof_depth[kMaxDofs];
+    uint8_t dof_link[kMaxDofs];           // owning link (base dofs: 0)
+    // mocap tables live in separate device arrays: frame_times (double), frames / frame_vel (float, pose layout, root w-first quats)
+};
+
+// ---- per-environment state (env-major blocks; one tile of lanes reads a block with float4 loads)
+// SIM block, floats:  [0..2] basePos [4..7] baseQuat(world->base) [8..10] baseOmega [12..14] baseVel
+//                     [16 + 4 j ..] jointPos(j)  (spherical: quat xyzw; revolute: angle in .x)
+//                     [16 + 4 nl + 4 j ..] jointVel(j) (xyz)
+//                     [16 + 8 nl + 4 j ..] pdTarget(j) (body-frame quat xyzw / angle in .x)
+__host__ __device__ inline int sim_stride(int nl) { return 16 + 12 * nl; }
+// TIME block, doubles: kin_time, ctrl_time, init_time_offset, prev_action_time, timer_time, timer_max, origin[3], origin_rot[4] (w,x,y,z)
+constexpr int kTimeDoubles = 16;
+enum TimeSlot { kTKin = 0, kTCtrl = 1, kTInitOff = 2, kTPrevAct = 3, kTTimer = 4, kTTimerMax = 5, kTOrigin = 6, kTOriginRot = 9 };
+// FLAG block, ints: need_new_action, done (sticky until reset), terminate, valid, fallen, overflow_rows
+constexpr int kFlagInts = 8;
+enum FlagSlot { kFNeedAction = 0, kFDone = 1, kFTerminate = 2, kFValid = 3, kFFallen = 4, kFRowOverflow = 5, kFUpdates = 6 };
+// MANIFOLD block, floats: nl x 4 points x 12 = {valid, lAx,lAy,lAz, wBx,wBy,wBz, impN, impL1, impL2, dist, life}
+
+struct DevState {
+    float* sim;
+    double* time;
+    int* flags;
+    float* manifold;
+    float* pdbg;  // optional debug scratch (n x ...), may be null
+    int num_envs;
+};
+
+}  // namespace dmk

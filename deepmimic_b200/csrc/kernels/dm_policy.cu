@@ -1,0 +1,423 @@
+// Policy-rate (30 Hz) kernels, one tile of W lanes per environment, lane = link/joint:
+//   dm_observe_kernel   : cCtController::RecordState (R/DeepMimicCore/sim/CtController.cpp:281-293,373-478)
+//                       + cSceneImitate::CalcReward / CalcRewardImitate (scenes/SceneImitate.cpp:7-127,163-175)
+//                         against the mocap frame sampled like cMotion::CalcFrame / cKinTree::LerpPoses
+//                         (anim/Motion.cpp:267-293,486-515; anim/KinTree.cpp:1336-1378)
+//   dm_set_action_kernel: cCtPDController::ApplyAction -> ConvertActionToTargetPose (sim/CtPDController.cpp:97-166)
+//   dm_reset_kernel     : cSceneSimChar::ResetScene chain for the environments whose done flag is set
+#include "dm_model.cuh"
+
+namespace dmk {
+
+namespace {
+
+template <int W>
+struct TileP {
+    static __device__ __forceinline__ float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src, W); }
+    static __device__ __forceinline__ V3 shfl3(V3 v, int src) { return mk3(shfl(v.x, src), shfl(v.y, src), shfl(v.z, src)); }
+    static __device__ __forceinline__ float sum(float v) {
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, W);
+        return v;
+    }
+    static __device__ __forceinline__ float minf(float v) {
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o, W));
+        return v;
+    }
+};
+
+__device__ __forceinline__ float norm_angle(float t) {
+    float n = fmodf(t, 6.283185307179586f);
+    if (n > 3.14159265358979f) n -= 6.283185307179586f;
+    else if (n < -3.14159265358979f) n += 6.283185307179586f;
+    return n;
+}
+// Eigen::Quaternion::slerp (the reference's interpolation, anim/KinTree.cpp:1547,1564)
+__device__ __forceinline__ Q4 eigen_slerp(Q4 a, float t, Q4 b) {
+    float d = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    float ad = fabsf(d), s0, s1;
+    if (ad >= 1.0f - 1.1920929e-7f) { s0 = 1.0f - t; s1 = t; }
+    else { float th = acosf(ad), st = sinf(th); s0 = sinf((1.0f - t) * th) / st; s1 = sinf(t * th) / st; }
+    if (d < 0.f) s1 = -s1;
+    return mkq(s0 * a.x + s1 * b.x, s0 * a.y + s1 * b.y, s0 * a.z + s1 * b.z, s0 * a.w + s1 * b.w);
+}
+// squared rotation angle between two unit quaternions with cMathUtil::QuatTheta's dead zone (sin(theta/2) <= 1e-4 -> 0)
+__device__ __forceinline__ float quat_theta_sq(Q4 a, Q4 b) {
+    Q4 dq = qmul(b, qconj(a));
+    float s = sqrtf(dq.x * dq.x + dq.y * dq.y + dq.z * dq.z);
+    if (!(s > 0.0001f)) return 0.f;
+    float th = 2.0f * atan2f(s, fabsf(dq.w));
+    return th * th;
+}
+__device__ __forceinline__ void frame_index(const DevModel& M, const double* ft, double time, int& idx, double& blend, int& cyc) {
+    const double dur = M.motion_dur;
+    if (!M.loop_motion) {
+        cyc = static_cast<int>(floor(time / dur)); cyc = cyc < 0 ? 0 : (cyc > 1 ? 1 : cyc);
+        if (time <= 0) { idx = 0; blend = 0; return; }
+        if (time >= dur) { idx = M.num_frames - 2; blend = 1; return; }
+    } else cyc = static_cast<int>(floor(time / dur));
+    double tt = time - cyc * dur;
+    int lo = 0, hi = M.num_frames;   // upper_bound(tt) - 1
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ft[mid] <= tt) lo = mid; else hi = mid; }
+    if (lo > M.num_frames - 2) lo = M.num_frames - 2;
+    idx = lo;
+    blend = (tt - ft[lo]) / (ft[lo + 1] - ft[lo]);
+}
+// stateless counter-based random numbers (splitmix64 finaliser) -> uniform [0,1)
+__device__ __forceinline__ double u01(unsigned long long seed, unsigned long long a, unsigned long long b) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (a * 2654435761ull + b + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    return static_cast<double>(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// mocap sample for joint `lane` in DeepMimic pose layout: returns the joint quaternion (w-first stored in the table) as Q4 xyzw,
+// the revolute angle in .x, and the joint velocity
+struct KinJoint { Q4 q; V3 w; float ang, angvel; };
+__device__ __forceinline__ KinJoint sample_joint(const DevLink& L, const float* f0, const float* f1, const float* v0, const float* v1, float bl, bool is_root) {
+    KinJoint k; k.q = mkq(0, 0, 0, 1); k.w = mk3(0, 0, 0); k.ang = 0; k.angvel = 0;
+    if (is_root) {
+        Q4 a = mkq(f0[4], f0[5], f0[6], f0[3]), b = mkq(f1[4], f1[5], f1[6], f1[3]);
+        k.q = qnormalize(eigen_slerp(a, bl, b));
+        k.w = mk3((1 - bl) * v0[3] + bl * v1[3], (1 - bl) * v0[4] + bl * v1[4], (1 - bl) * v0[5] + bl * v1[5]);
+    } else if (L.jtype == kJSpherical) {
+        const int o = L.pose_off;
+        Q4 a = mkq(f0[o + 1], f0[o + 2], f0[o + 3], f0[o]), b = mkq(f1[o + 1], f1[o + 2], f1[o + 3], f1[o]);
+        k.q = eigen_slerp(a, bl, b);
+        k.w = mk3((1 - bl) * v0[o] + bl * v1[o], (1 - bl) * v0[o + 1] + bl * v1[o + 1], (1 - bl) * v0[o + 2] + bl * v1[o + 2]);
+    } else if (L.jtype == kJRevolute) {
+        const int o = L.pose_off;
+        k.ang = (1 - bl) * f0[o] + bl * f1[o];
+        k.angvel = (1 - bl) * v0[o] + bl * v1[o];
+    }
+    return k;
+}
+
+}  // namespace
+
+// obs: [N x state_size] floats, reward: [N] floats.  Either pointer may be null.
+template <int W, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) dm_observe_kernel(const DevModel* __restrict__ gm, DevState st, const double* __restrict__ frame_times,
+                                                            const float* __restrict__ frames, const float* __restrict__ frame_vel,
+                                                            float* __restrict__ obs, float* __restrict__ reward, int num_real_envs) {
+    using T = TileP<W>;
+    const int tiles = BLOCK / W, tile = threadIdx.x / W, lane = threadIdx.x % W;
+    const int env = blockIdx.x * tiles + tile;
+    const DevModel& M = *gm;
+    const int nl = M.nl;
+    const bool act = lane < nl;
+    const int li = act ? lane : nl - 1;
+    const DevLink& L = M.link[li];
+    const int ss = sim_stride(nl);
+    const float* sim = st.sim + static_cast<size_t>(env) * ss;
+    const double* tm = st.time + static_cast<size_t>(env) * kTimeDoubles;
+    const int* fl = st.flags + static_cast<size_t>(env) * kFlagInts;
+    const float inv_scale = 1.0f / M.scale;
+    const V3 basePos = mk3(sim[0], sim[1], sim[2]);
+    const Q4 baseQuat = mkq(sim[4], sim[5], sim[6], sim[7]);
+    const V3 baseOmega = mk3(sim[8], sim[9], sim[10]), baseVel = mk3(sim[12], sim[13], sim[14]);
+    const float4 jp = reinterpret_cast<const float4*>(sim + 16)[li];
+    const float4 jv = reinterpret_cast<const float4*>(sim + 16 + 4 * nl)[li];
+    const int parent = L.parent, plane = parent >= 0 ? parent : 0, level = act ? L.level : 1000, jtype = L.jtype;
+    const V3 dvec = mk3(L.dvec[0], L.dvec[1], L.dvec[2]), evec = mk3(L.evec[0], L.evec[1], L.evec[2]);
+    const Q4 zrot = mkq(L.zrot[0], L.zrot[1], L.zrot[2], L.zrot[3]);
+    const V3 axis = mk3(L.axis[0], L.axis[1], L.axis[2]);
+
+    // ---- forward kinematics of the simulated character (world->link rotation, COM position, COM twist in the link frame)
+    Q4 cached;
+    if (jtype == kJSpherical) cached = qmul(mkq(jp.x, jp.y, jp.z, -jp.w), zrot);
+    else if (jtype == kJRevolute) { float s, c; sincosf(-0.5f * jp.x, &s, &c); cached = qmul(mkq(axis.x * s, axis.y * s, axis.z * s, c), zrot); }
+    else cached = zrot;
+    const M3 R = qmat(cached);
+    const V3 r = dvec + mul(R, evec);
+    const M3 Rwb = qmat(baseQuat);
+    M3 Rwl = mul(R, Rwb);
+    V3 pos = basePos + mulT(Rwl, r);
+    V3 wl = mul(Rwb, baseOmega), vl = mul(Rwb, baseVel);
+    { V3 w2 = mul(R, wl); vl = mul(R, vl) - cross(r, w2); wl = w2; }
+    V3 wJ = mk3(0, 0, 0), vJ = mk3(0, 0, 0);
+    if (jtype == kJSpherical) { wJ = mk3(jv.x, jv.y, jv.z); vJ = cross(wJ, dvec); }
+    else if (jtype == kJRevolute) { wJ = jv.x * axis; vJ = cross(wJ, dvec); }
+    for (int lv = 1; lv <= M.maxlevel; ++lv) {
+        M3 pR; for (int k = 0; k < 9; ++k) pR.m[k] = T::shfl(Rwl.m[k], plane);
+        V3 pp = T::shfl3(pos, plane), pw_ = T::shfl3(wl, plane), pv_ = T::shfl3(vl, plane);
+        if (level == lv) {
+            Rwl = mul(R, pR); pos = pp + mulT(Rwl, r);
+            V3 w2 = mul(R, pw_); vl = mul(R, pv_) - cross(r, w2) + vJ; wl = w2 + wJ;
+        }
+    }
+    const V3 lin_w = inv_scale * mulT(Rwl, vl), ang_w = mulT(Rwl, wl);   // cSimBodyLink::mLinVel / mAngVel
+    const V3 bpos = inv_scale * pos;                                       // cSimObj::GetPos
+
+    // ---- heading frame of the simulated root (cKinTree::BuildOriginTrans, KinTree.cpp:1651-1664)
+    const Q4 rootq = qconj(baseQuat);            // root joint rotation (root attach rotation is identity for the shipped characters)
+    const V3 root = inv_scale * basePos;
+    V3 hx = qrot(rootq, mk3(1, 0, 0));
+    const float heading = atan2f(-hx.z, hx.x);
+    float sh, ch; sincosf(-heading, &sh, &ch);
+    auto rotH = [&](V3 v) { return mk3(ch * v.x + sh * v.z, v.y, -sh * v.x + ch * v.z); };   // rotation about y by -heading
+
+    if (obs != nullptr && env < num_real_envs && act) {
+        float* o = obs + static_cast<size_t>(env) * M.state_size;
+        const int ph = M.phase_input ? 1 : 0;
+        if (lane == 0) {
+            if (ph) { double p = fmod(tm[kTCtrl] / M.cycle_period, 1.0); o[0] = static_cast<float>(p < 0 ? 1 + p : p); }
+            o[ph] = root.y;   // root height above the (flat, y = 0) ground in the origin frame
+        }
+        const bool is_root = lane == 0;
+        V3 cp = bpos;
+        if (!(M.rec_world_root_pos && is_root)) { cp = rotH(mk3(bpos.x - root.x, bpos.y, bpos.z - root.z)); cp.y -= root.y; }
+        V3 nrm = mk3(Rwl.m[3], Rwl.m[4], Rwl.m[5]), tan = mk3(Rwl.m[0], Rwl.m[1], Rwl.m[2]);   // link y / x axes in world
+        V3 lv_ = lin_w, av_ = ang_w;
+        if (!(M.rec_world_root_rot && is_root)) { nrm = rotH(nrm); tan = rotH(tan); lv_ = rotH(lv_); av_ = rotH(av_); }
+        float* op = o + ph + 1 + 9 * lane;
+        op[0] = cp.x; op[1] = cp.y; op[2] = cp.z; op[3] = nrm.x; op[4] = nrm.y; op[5] = nrm.z; op[6] = tan.x; op[7] = tan.y; op[8] = tan.z;
+        float* ov = o + ph + 1 + 9 * nl + 6 * lane;
+        ov[0] = lv_.x; ov[1] = lv_.y; ov[2] = lv_.z; ov[3] = av_.x; ov[4] = av_.y; ov[5] = av_.z;
+    }
+    if (reward == nullptr) return;
+
+    // ---- mocap frame at kin_time
+    int idx, cyc; double bld;
+    frame_index(M, frame_times, tm[kTKin], idx, bld, cyc);
+    bld = fmin(fmax(bld, 0.0), 1.0);
+    const float bl = static_cast<float>(bld);
+    const float* f0 = frames + static_cast<size_t>(idx) * M.pose_dim; const float* f1 = f0 + M.pose_dim;
+    const float* v0 = frame_vel + static_cast<size_t>(idx) * M.pose_dim; const float* v1 = v0 + M.pose_dim;
+    const bool clip_over = !M.loop_motion && tm[kTKin] >= M.motion_dur;
+    KinJoint kj = sample_joint(L, f0, f1, v0, v1, bl, lane == 0);
+    if (clip_over) { kj.w = mk3(0, 0, 0); kj.angvel = 0; }
+    const Q4 orot = mkq(static_cast<float>(tm[kTOriginRot + 1]), static_cast<float>(tm[kTOriginRot + 2]), static_cast<float>(tm[kTOriginRot + 3]), static_cast<float>(tm[kTOriginRot]));
+    const V3 org = mk3(static_cast<float>(tm[kTOrigin]), static_cast<float>(tm[kTOrigin + 1]), static_cast<float>(tm[kTOrigin + 2]));
+    // kinematic root in the world
+    V3 kroot = mk3((1 - bl) * f0[0] + bl * f1[0] + (M.loop_motion ? cyc * M.cycle_delta[0] : 0.f), (1 - bl) * f0[1] + bl * f1[1],
+                   (1 - bl) * f0[2] + bl * f1[2] + (M.loop_motion ? cyc * M.cycle_delta[2] : 0.f));
+    kroot = qrot(orot, kroot) + org;
+    V3 kroot_v = mk3((1 - bl) * v0[0] + bl * v1[0], (1 - bl) * v0[1] + bl * v1[1], (1 - bl) * v0[2] + bl * v1[2]);
+    if (clip_over) kroot_v = mk3(0, 0, 0);
+    kroot_v = qrot(orot, kroot_v);
+    Q4 krootq = mkq(0, 0, 0, 1); V3 kroot_w = mk3(0, 0, 0);
+    {
+        KinJoint kr = sample_joint(M.link[0], f0, f1, v0, v1, bl, true);
+        krootq = qmul(orot, kr.q);
+        if (krootq.w < 0) krootq = mkq(-krootq.x, -krootq.y, -krootq.z, -krootq.w);
+        kroot_w = clip_over ? mk3(0, 0, 0) : qrot(orot, kr.w);
+    }
+    // ---- kinematic FK in the world: joint frames (DeepMimic tree), joint origin position, twist
+    const Q4 attq = mkq(L.child_rot[0], L.child_rot[1], L.child_rot[2], L.child_rot[3]);   // joint -> body
+    const V3 att_pt = mk3(L.att_pt[0], L.att_pt[1], L.att_pt[2]);
+    const Q4 att_rot = mkq(L.att_rot[0], L.att_rot[1], L.att_rot[2], L.att_rot[3]);
+    Q4 jq_local = (jtype == kJSpherical) ? kj.q : ((jtype == kJRevolute) ? mkq(0.f, 0.f, sinf(0.5f * kj.ang), cosf(0.5f * kj.ang)) : mkq(0, 0, 0, 1));
+    V3 jw_local = (jtype == kJSpherical) ? kj.w : ((jtype == kJRevolute) ? mk3(0.f, 0.f, kj.angvel) : mk3(0, 0, 0));
+    Q4 kq = krootq; V3 kp = kroot, kw = kroot_w, kv = kroot_v;   // lane 0 values; other lanes filled level by level
+    for (int lv = 1; lv <= M.maxlevel; ++lv) {
+        Q4 pq = mkq(T::shfl(kq.x, plane), T::shfl(kq.y, plane), T::shfl(kq.z, plane), T::shfl(kq.w, plane));
+        V3 pp = T::shfl3(kp, plane), pw_ = T::shfl3(kw, plane), pv_ = T::shfl3(kv, plane);
+        if (level == lv) {
+            V3 off = qrot(pq, att_pt);
+            kp = pp + off;
+            kq = qmul(qmul(pq, att_rot), jq_local);
+            kv = pv_ + cross(pw_, off);
+            kw = pw_ + qrot(kq, jw_local);
+        }
+    }
+    const V3 body_att = mk3(L.body_att[0], L.body_att[1], L.body_att[2]);
+    const V3 kcom_v = kv + cross(kw, qrot(kq, body_att));
+
+    // ---- error terms
+    float pose_e = 0.f, vel_e = 0.f, ee_e = 0.f;
+    if (act && lane > 0) {
+        if (jtype == kJSpherical) {
+            Q4 kb = qmul(qmul(attq, kj.q), qconj(attq));            // clip rotation expressed in the body-frame convention of the sim state
+            pose_e = quat_theta_sq(mkq(jp.x, jp.y, jp.z, jp.w), kb);
+            V3 d = qrot(attq, kj.w) - mk3(jv.x, jv.y, jv.z);
+            vel_e = dot(d, d);
+        } else if (jtype == kJRevolute) {
+            float d = kj.ang - norm_angle(jp.x); pose_e = d * d;
+            float dv = kj.angvel - jv.x; vel_e = dv * dv;
+        }
+        if (L.end_eff) {
+            // joint origin of the simulated link: COM + R_lw * child_pos (cSimBodyJoint::CalcWorldPos)
+            V3 p0 = bpos + mulT(Rwl, mk3(L.child_pos[0], L.child_pos[1], L.child_pos[2]));
+            V3 rel0 = mk3(p0.x - root.x, p0.y, p0.z - root.z);
+            V3 rel1 = mk3(kp.x - kroot.x, kp.y - org.y, kp.z - kroot.z);
+            rel0 = rotH(rel0);
+            V3 khx = qrot(krootq, mk3(1, 0, 0));
+            float kh = atan2f(-khx.z, khx.x), s2, c2; sincosf(-kh, &s2, &c2);
+            rel1 = mk3(c2 * rel1.x + s2 * rel1.z, rel1.y, -s2 * rel1.x + c2 * rel1.z);
+            V3 d = rel1 - rel0;
+            ee_e = dot(d, d);
+        }
+        pose_e *= L.joint_w; vel_e *= L.joint_w;
+    }
+    if (lane == 0) {
+        pose_e = M.link[0].joint_w * quat_theta_sq(rootq, krootq);
+        V3 d = kroot_w - baseOmega;
+        vel_e = M.link[0].joint_w * dot(d, d);
+    }
+    const float pose_err = T::sum(act ? pose_e : 0.f), vel_err = T::sum(act ? vel_e : 0.f), end_eff_err = T::sum(act ? ee_e : 0.f);
+    const float mfrac = act ? L.mass / M.total_mass : 0.f;
+    const V3 com_v0 = mk3(T::sum(mfrac * lin_w.x), T::sum(mfrac * lin_w.y), T::sum(mfrac * lin_w.z));
+    const V3 com_v1 = mk3(T::sum(mfrac * kcom_v.x), T::sum(mfrac * kcom_v.y), T::sum(mfrac * kcom_v.z));
+    if (lane == 0 && env < num_real_envs) {
+        V3 rp0 = root, rp1 = mk3(kroot.x, kroot.y - org.y, kroot.z);
+        V3 dp = rp0 - rp1;
+        float root_rot_err = quat_theta_sq(rootq, krootq);
+        V3 dv = kroot_v - inv_scale * baseVel, dw = kroot_w - baseOmega;
+        float root_err = dot(dp, dp) + 0.1f * root_rot_err + 0.01f * dot(dv, dv) + 0.001f * dot(dw, dw);
+        V3 dc = com_v1 - com_v0;
+        float com_err = 0.1f * dot(dc, dc);
+        const float pose_scale = 2.0f / 15 * nl, vel_scale = 0.1f / 15 * nl;
+        float rwd = 0.5f * expf(-pose_scale * pose_err) + 0.05f * expf(-vel_scale * vel_err) + 0.15f * expf(-10.f * end_eff_err) +
+                    0.2f * expf(-5.f * root_err) + 0.1f * expf(-10.f * com_err);
+        if (fl[kFFallen]) rwd = 0.f;
+        reward[env] = rwd;
+    }
+}
+
+// actions: [N x action_size] floats (DeepMimic action layout)
+__global__ void dm_set_action_kernel(const DevModel* __restrict__ gm, DevState st, const float* __restrict__ actions, int num_real_envs) {
+    const DevModel& M = *gm;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int env = gid / M.nl, j = gid % M.nl;
+    if (env >= num_real_envs || j == 0) return;
+    const DevLink& L = M.link[j];
+    const float* a = actions + static_cast<size_t>(env) * M.action_size + L.act_off;
+    float4* tgt = reinterpret_cast<float4*>(st.sim + static_cast<size_t>(env) * sim_stride(M.nl) + 16 + 8 * M.nl) + j;
+    if (L.jtype == kJSpherical) {
+        V3 em = mk3(a[0], a[1], a[2]);
+        float len = sqrtf(dot(em, em));
+        const float max_len = 6.283185307179586f;
+        if (len > max_len) { em = em * (max_len / len); len = max_len; }
+        Q4 q = mkq(0, 0, 0, 1);
+        if (len > 0.000001f) {
+            V3 ax = em * (1.0f / len);
+            float th = norm_angle(len), s, c;
+            sincosf(0.5f * th, &s, &c);
+            q = mkq(ax.x * s, ax.y * s, ax.z * s, c);
+        }
+        q = qnormalize(q);
+        Q4 cr = mkq(L.child_rot[0], L.child_rot[1], L.child_rot[2], L.child_rot[3]);
+        q = qmul(qmul(cr, q), qconj(cr));
+        *tgt = make_float4(q.x, q.y, q.z, q.w);
+    } else if (L.jtype == kJRevolute) {
+        *tgt = make_float4(a[0], 0.f, 0.f, 0.f);
+    }
+}
+
+// Resets every environment whose done flag is set (or all when force != 0).  kin_time_in / max_time_in (may be null) inject the
+// random draws of the reference's reset (CalcRandKinResetTime, cTimer::Reset) so tests can bypass the RNG.
+template <int W, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) dm_reset_kernel(const DevModel* __restrict__ gm, DevState st, const double* __restrict__ frame_times,
+                                                          const float* __restrict__ frames, const float* __restrict__ frame_vel, int force,
+                                                          const double* __restrict__ kin_time_in, const double* __restrict__ max_time_in,
+                                                          const double* __restrict__ rot_theta_in, unsigned long long seed,
+                                                          unsigned long long env_id_base, int test_mode) {
+    using T = TileP<W>;
+    const int tiles = BLOCK / W, tile = threadIdx.x / W, lane = threadIdx.x % W;
+    const int env = blockIdx.x * tiles + tile;
+    const DevModel& M = *gm;
+    const int nl = M.nl;
+    const bool act = lane < nl;
+    const int li = act ? lane : nl - 1;
+    const DevLink& L = M.link[li];
+    const int ss = sim_stride(nl);
+    float* sim = st.sim + static_cast<size_t>(env) * ss;
+    double* tm = st.time + static_cast<size_t>(env) * kTimeDoubles;
+    int* fl = st.flags + static_cast<size_t>(env) * kFlagInts;
+    const bool doit = force || fl[kFDone] != 0;
+    // draws
+    const unsigned long long gid = env_id_base + env, cnt = static_cast<unsigned long long>(fl[7]);
+    double kt = kin_time_in ? kin_time_in[env] : u01(seed, gid, 3 * cnt) * M.motion_dur;
+    double mt = max_time_in ? max_time_in[env] : (M.time_lim_min + u01(seed, gid, 3 * cnt + 1) * (M.time_lim_max - M.time_lim_min));
+    double th = rot_theta_in ? rot_theta_in[env] : (M.rand_rot_reset ? (-3.14159265358979323846 + u01(seed, gid, 3 * cnt + 2) * 6.283185307179586) : 0.0);
+    if (!M.rand_rot_reset) th = 0.0;
+    if (test_mode) mt = M.time_end_lim_max;
+    int idx, cyc; double bld;
+    frame_index(M, frame_times, kt, idx, bld, cyc);
+    bld = fmin(fmax(bld, 0.0), 1.0);
+    const float bl = static_cast<float>(bld);
+    const float* f0 = frames + static_cast<size_t>(idx) * M.pose_dim; const float* f1 = f0 + M.pose_dim;
+    const float* v0 = frame_vel + static_cast<size_t>(idx) * M.pose_dim; const float* v1 = v0 + M.pose_dim;
+    KinJoint kj = sample_joint(L, f0, f1, v0, v1, bl, lane == 0);
+    const float sth = sinf(0.5f * static_cast<float>(th)), cth = cosf(0.5f * static_cast<float>(th));
+    const Q4 orot = mkq(0.f, sth, 0.f, cth);
+    // root
+    V3 rp = mk3((1 - bl) * f0[0] + bl * f1[0] + (M.loop_motion ? cyc * M.cycle_delta[0] : 0.f), (1 - bl) * f0[1] + bl * f1[1],
+                (1 - bl) * f0[2] + bl * f1[2] + (M.loop_motion ? cyc * M.cycle_delta[2] : 0.f));
+    V3 rv = mk3((1 - bl) * v0[0] + bl * v1[0], (1 - bl) * v0[1] + bl * v1[1], (1 - bl) * v0[2] + bl * v1[2]);
+    KinJoint kr = sample_joint(M.link[0], f0, f1, v0, v1, bl, true);
+    Q4 rq = qmul(orot, kr.q); if (rq.w < 0) rq = mkq(-rq.x, -rq.y, -rq.z, -rq.w);
+    rq = qnormalize(rq);
+    V3 rw = qrot(orot, kr.w);
+    rv = qrot(orot, rv);
+    // simulated state := kinematic state, root x,z := 0 (SyncCharacters + SetCharRandPlacement)
+    V3 basePos = mk3(0.f, M.scale * rp.y, 0.f);
+    Q4 baseQuat = qconj(rq);
+    V3 baseVel = M.scale * rv, baseOmega = rw;
+    float4 jp = make_float4(0, 0, 0, 1), jv = make_float4(0, 0, 0, 0);
+    const Q4 cr = mkq(L.child_rot[0], L.child_rot[1], L.child_rot[2], L.child_rot[3]);
+    if (L.jtype == kJSpherical) {
+        Q4 q = qmul(qmul(cr, kj.q), qconj(cr));
+        V3 w = qrot(cr, kj.w);
+        jp = make_float4(q.x, q.y, q.z, q.w); jv = make_float4(w.x, w.y, w.z, 0.f);
+    } else if (L.jtype == kJRevolute) { jp = make_float4(kj.ang, 0, 0, 0); jv = make_float4(kj.angvel, 0, 0, 0); }
+    // ---- FK for cSceneSimChar::ResolveCharGroundIntersect: lowest AABB point of every link shape
+    const int parent = L.parent, plane = parent >= 0 ? parent : 0, level = act ? L.level : 1000, jtype = L.jtype;
+    const V3 dvec = mk3(L.dvec[0], L.dvec[1], L.dvec[2]), evec = mk3(L.evec[0], L.evec[1], L.evec[2]);
+    const Q4 zrot = mkq(L.zrot[0], L.zrot[1], L.zrot[2], L.zrot[3]);
+    const V3 axis = mk3(L.axis[0], L.axis[1], L.axis[2]);
+    Q4 cached;
+    if (jtype == kJSpherical) cached = qmul(mkq(jp.x, jp.y, jp.z, -jp.w), zrot);
+    else if (jtype == kJRevolute) { float s, c; sincosf(-0.5f * jp.x, &s, &c); cached = qmul(mkq(axis.x * s, axis.y * s, axis.z * s, c), zrot); }
+    else cached = zrot;
+    const M3 R = qmat(cached);
+    const V3 r = dvec + mul(R, evec);
+    const M3 Rwb = qmat(baseQuat);
+    M3 Rwl = mul(R, Rwb);
+    V3 pos = basePos + mulT(Rwl, r);
+    for (int lv = 1; lv <= M.maxlevel; ++lv) {
+        M3 pR; for (int k = 0; k < 9; ++k) pR.m[k] = T::shfl(Rwl.m[k], plane);
+        V3 pp = T::shfl3(pos, plane);
+        if (level == lv) { Rwl = mul(R, pR); pos = pp + mulT(Rwl, r); }
+    }
+    float ext_y;
+    if (L.shape == kSSphere) ext_y = L.he[0];
+    else {
+        // world y extent = |row y of link->world basis| . half extents ; link->world basis row y = column y of Rwl
+        float hx = L.shape == kSCapsule ? L.he[0] : L.he[0], hy = L.shape == kSCapsule ? L.he[0] + L.he[1] : L.he[1], hz = L.shape == kSCapsule ? L.he[0] : L.he[2];
+        ext_y = fabsf(Rwl.m[1]) * hx + fabsf(Rwl.m[4]) * hy + fabsf(Rwl.m[7]) * hz;
+    }
+    float min_h = act ? (pos.y - ext_y) / M.scale - 0.001f : 1e30f;
+    min_h = T::minf(min_h);
+    const float min_violation = fminf(min_h, 0.f);
+    if (min_violation < 0.f) basePos.y += -min_violation * M.scale;
+    if (!doit) return;
+    // ---- commit
+    if (lane == 0) {
+        reinterpret_cast<float4*>(sim)[0] = make_float4(basePos.x, basePos.y, basePos.z, 0.f);
+        reinterpret_cast<float4*>(sim)[1] = make_float4(baseQuat.x, baseQuat.y, baseQuat.z, baseQuat.w);
+        reinterpret_cast<float4*>(sim)[2] = make_float4(baseOmega.x, baseOmega.y, baseOmega.z, 0.f);
+        reinterpret_cast<float4*>(sim)[3] = make_float4(baseVel.x, baseVel.y, baseVel.z, 0.f);
+        // kinematic origin so that the clip's root coincides with the simulated root (SyncKinCharRoot)
+        V3 rrp = qrot(orot, rp);
+        tm[kTKin] = kt; tm[kTCtrl] = kt; tm[kTInitOff] = -kt; tm[kTPrevAct] = kt; tm[kTTimer] = 0.0; tm[kTTimerMax] = mt;
+        tm[kTOrigin] = static_cast<double>(basePos.x / M.scale) - rrp.x; tm[kTOrigin + 1] = static_cast<double>(basePos.y / M.scale) - rrp.y;
+        tm[kTOrigin + 2] = static_cast<double>(basePos.z / M.scale) - rrp.z;
+        tm[kTOriginRot] = cth; tm[kTOriginRot + 1] = 0.0; tm[kTOriginRot + 2] = sth; tm[kTOriginRot + 3] = 0.0;
+        fl[kFNeedAction] = 1; fl[kFDone] = 0; fl[kFTerminate] = 0; fl[kFValid] = 1; fl[kFFallen] = 0; fl[kFUpdates] = 0; fl[7] = fl[7] + 1;
+    }
+    if (act) {
+        reinterpret_cast<float4*>(sim + 16)[lane] = jp;
+        reinterpret_cast<float4*>(sim + 16 + 4 * nl)[lane] = jv;
+        float4* mo = reinterpret_cast<float4*>(st.manifold + (static_cast<size_t>(env) * nl + lane) * kManifoldFloats);
+        for (int k = 0; k < kManifoldFloats / 4; ++k) mo[k] = make_float4(0, 0, 0, 0);
+    }
+}
+
+template __global__ void dm_observe_kernel<16, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
+template __global__ void dm_observe_kernel<32, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
+template __global__ void dm_reset_kernel<16, 64>(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*, unsigned long long, unsigned long long, int);
+template __global__ void dm_reset_kernel<32, 64>(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*, unsigned long long, unsigned long long, int);
+
+}  // namespace dmk

@@ -1,0 +1,96 @@
+/* deepmimic_b200 -- C ABI of the B200-native batched DeepMimic step.
+ *
+ * This is the drop-in boundary for the reference's per-step simulation hot path.  Each entry point
+ * replaces, for a BATCH of independent environments resident on one GPU, the method of the
+ * reference's SWIG-exported facade `cDeepMimicCore` cited next to it (R/ = xbpeng/DeepMimic):
+ *
+ *   dm_create          cDeepMimicCore(), ParseArgs, Init      R/DeepMimicCore/DeepMimicCore.h:12-25,  DeepMimicCore.cpp:6-54
+ *   dm_reset           Reset                                  DeepMimicCore.h:27,                     DeepMimicCore.cpp:61-65
+ *   dm_update          Update(timestep)                       DeepMimicCore.h:26,                     DeepMimicCore.cpp:56-59
+ *   dm_set_action      SetAction(agent_id, action)            DeepMimicCore.h:58,                     DeepMimicCore.cpp:205-212
+ *   dm_record_state    RecordState(agent_id)                  DeepMimicCore.h:56,                     DeepMimicCore.cpp:191-197
+ *   dm_record_goal     RecordGoal(agent_id)                   DeepMimicCore.h:57  (size 0 for scene "imitate")
+ *   dm_calc_reward     CalcReward(agent_id)                   DeepMimicCore.h:77,                     DeepMimicCore.cpp:327-334
+ *   dm_get_flags       NeedNewAction / IsEpisodeEnd / CheckTerminate / CheckValidEpisode
+ *                                                             DeepMimicCore.h:55,83-85
+ *   dm_get_static      GetStateSize .. BuildActionBoundMax, BuildStateNormGroups   DeepMimicCore.h:62-75
+ *   dm_set_mode        SetMode                                DeepMimicCore.h:87
+ *
+ * Plain C: opaque handle, pointers and sizes only, int status (0 = ok) with dm_last_error().  Pointers
+ * named d_* are DEVICE pointers (fp32 unless stated), h_* are host pointers.  One host thread per
+ * handle; all device work is enqueued on the handle's stream (dm_stream) and is stream-ordered.
+ * There is NO CPU fallback: dm_create fails if no CUDA device is usable.
+ */
+#ifndef DEEPMIMIC_B200_H_
+#define DEEPMIMIC_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dm_handle dm_handle;
+
+typedef struct dm_dims {
+    int num_envs;          /* environments simulated by this handle */
+    int num_joints;        /* == bodies (15 humanoid3d, 23 dog3d) */
+    int pose_dim;          /* DeepMimic pose / vel vector length (43 / 83) */
+    int num_dofs;          /* 6 + joint dofs (34 / 70) */
+    int state_size;        /* observation length (227 with phase, 226 without, 347 dog) */
+    int goal_size;         /* 0 for scene "imitate" */
+    int action_size;       /* 28 / 58 */
+    int snapshot_size;     /* doubles per env for dm_get_snapshot / dm_set_snapshot */
+    int updates_per_action;/* 20 for the shipped arg files (30 Hz queries, 600 Hz updates) */
+    int num_update_substeps;
+    double motion_duration;
+} dm_dims;
+
+enum dm_static_kind {
+    DM_STATE_OFFSET = 0, DM_STATE_SCALE = 1, DM_ACTION_OFFSET = 2, DM_ACTION_SCALE = 3,
+    DM_ACTION_BOUND_MIN = 4, DM_ACTION_BOUND_MAX = 5, DM_STATE_NORM_GROUPS = 6
+};
+
+/* asset_root: directory that contains data/ and args/ (arg-file and asset paths are resolved against it).
+ * argv: the reference's argument list, e.g. {"--arg_file", "args/train_humanoid3d_spinkick_args.txt"}.
+ * global_env_offset: index of this handle's first env in the whole job (multi-GPU sharding keeps RNG streams independent of the GPU count). */
+dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int num_envs, int device, uint64_t seed, uint64_t global_env_offset);
+void dm_destroy(dm_handle* h);
+const char* dm_last_error(void);
+int dm_get_dims(dm_handle* h, dm_dims* out);
+int dm_get_static(dm_handle* h, int kind, double* h_out);   /* h_out: state_size or action_size doubles (norm groups as doubles) */
+void* dm_stream(dm_handle* h);                               /* cudaStream_t */
+int dm_sync(dm_handle* h);
+int dm_set_mode(dm_handle* h, int mode);                     /* 0 train, 1 test (cRLScene::eMode) */
+
+/* Resets the envs whose done flag is set (force_all = 0) or every env (force_all != 0).  Optional host arrays
+ * (num_envs doubles each, may be NULL) inject the random draws of the reference's reset: mocap start time,
+ * episode time limit, heading rotation -- used by the parity tests to bypass the RNG. */
+int dm_reset(dm_handle* h, int force_all, const double* h_kin_time, const double* h_max_time, const double* h_rot_theta);
+/* d_actions: [num_envs x action_size] fp32, DeepMimic action layout. */
+int dm_set_action(dm_handle* h, const float* d_actions);
+/* n_updates consecutive Update(dt) calls in one launch; envs whose episode ended freeze until dm_reset. */
+int dm_update(dm_handle* h, double dt, int n_updates);
+int dm_record_state(dm_handle* h, float* d_out);             /* [num_envs x state_size] */
+int dm_record_goal(dm_handle* h, float* d_out);              /* [num_envs x goal_size] (no-op when goal_size == 0) */
+int dm_calc_reward(dm_handle* h, float* d_out);              /* [num_envs] */
+int dm_observe(dm_handle* h, float* d_state, float* d_reward);  /* fused record_state + calc_reward, either may be NULL */
+/* d_flags: [num_envs x 4] int32 = {need_new_action, is_episode_end, check_terminate (0 null / 1 fail), check_valid_episode} */
+int dm_get_flags(dm_handle* h, int32_t* d_flags);
+
+/* ---- host-buffer convenience wrappers (the reference-facing plugin path: host in, host out, copies inside) */
+int dm_step_host(dm_handle* h, const float* h_actions, double dt, int n_updates, float* h_state, float* h_reward, int32_t* h_flags);
+
+/* ---- test hooks: raw per-env simulator state, layout shared with the CPU oracle (doubles):
+ *  [0..2] basePos(scaled) [3..6] baseQuat world->base (x,y,z,w) [7..9] baseOmega [10..12] baseVel(scaled)
+ *  [13 + 4j ..] jointPos(j)  [13 + 4nl + 3j ..] jointVel(j)
+ *  [13 + 7nl + (4j+c)*12 ..] manifold point c of link j: valid, localA xyz, worldB xyz, impulse n/t1/t2, distance, lifetime
+ *  [13 + 55nl ..] kin_time, origin xyz, origin_rot wxyz, ctrl_time, init_time_offset, prev_action_time, need_new_action, timer, timer_max, 2 spare
+ *  [29 + 55nl + 4j ..] PD target of joint j in DeepMimic joint-frame convention (w,x,y,z or angle) */
+int dm_get_snapshot(dm_handle* h, int env, double* h_out);
+int dm_set_snapshot(dm_handle* h, int env, const double* h_in);
+int dm_get_counters(dm_handle* h, int64_t* h_out);           /* {kernel launches so far, row-capacity overflows seen (must stay 0)} */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

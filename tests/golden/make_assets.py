@@ -1,0 +1,32 @@
+"""Packs the reference's DATA files that the tests / smoke / bench need (character, controller, motion,
+terrain JSON and arg files -- inputs of the hot path, not source code) into tests/golden/assets.tar.gz.
+Run in the build container where /root/reference exists:  python tests/golden/make_assets.py
+The GPU box has no /root/reference; tests unpack this archive instead (deepmimic_b200/assets.py)."""
+import os, tarfile
+
+REF = "/root/reference"
+FILES = [
+    "data/characters/humanoid3d.txt", "data/characters/dog3d.txt",
+    "data/controllers/humanoid3d_ctrl.txt", "data/controllers/humanoid3d_phase_rot_ctrl.txt", "data/controllers/humanoid3d_rot_ctrl.txt",
+    "data/controllers/dog3d_ctrl.txt", "data/controllers/dog3d_phase_ctrl.txt", "data/controllers/dog3d_phase_rot_ctrl.txt", "data/controllers/dog3d_rot_ctrl.txt",
+    "data/motions/humanoid3d_spinkick.txt", "data/motions/humanoid3d_walk.txt", "data/motions/humanoid3d_run.txt", "data/motions/humanoid3d_backflip.txt",
+    "data/motions/dog3d_trot.txt", "data/motions/dog3d_pace.txt",
+    "data/terrain/plane.txt",
+    "args/run_humanoid3d_spinkick_args.txt", "args/train_humanoid3d_spinkick_args.txt", "args/run_humanoid3d_walk_args.txt", "args/train_humanoid3d_walk_args.txt",
+    "args/train_humanoid3d_run_args.txt", "args/train_humanoid3d_backflip_args.txt",
+    "args/run_dog3d_trot_args.txt", "args/train_dog3d_trot_args.txt", "args/train_dog3d_pace_args.txt",
+]
+
+def main():
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets.tar.gz")
+    with tarfile.open(out, "w:gz", compresslevel=9) as tf:
+        for f in FILES:
+            p = os.path.join(REF, f)
+            ti = tf.gettarinfo(p, arcname=f)
+            ti.mtime = 0; ti.uid = ti.gid = 0; ti.uname = ti.gname = ""
+            with open(p, "rb") as fh:
+                tf.addfile(ti, fh)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,155 @@
+"""ctypes binding of the CPU oracle (oracle/libdm_oracle.so).  TEST INFRASTRUCTURE: only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+
+def load_oracle():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(REPO, "oracle", "libdm_oracle.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make"], cwd=os.path.join(REPO, "oracle"))
+    L = C.CDLL(path)
+    L.dmo_create.restype = C.c_void_p
+    L.dmo_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p)]
+    L.dmo_last_error.restype = C.c_char_p
+    for f in ("dmo_calc_reward", "dmo_motion_duration", "dmo_get_time", "dmo_calc_reward_terms"):
+        getattr(L, f).restype = C.c_double
+    _LIB = L
+    return L
+
+
+def dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Oracle:
+    def __init__(self, args, asset_root):
+        L = load_oracle()
+        enc = [a.encode() for a in args]
+        arr = (C.c_char_p * len(enc))(*enc)
+        h = L.dmo_create(asset_root.encode(), len(enc), arr)
+        if not h:
+            raise RuntimeError("oracle create failed: %s" % L.dmo_last_error().decode())
+        self.L, self.h = L, C.c_void_p(h)
+        d = (C.c_int * 8)()
+        L.dmo_get_dims(self.h, d)
+        (self.num_joints, self.pose_dim, self.num_dofs, self.state_size, self.action_size, self.goal_size, self.snapshot_size, self.num_frames) = list(d)
+        self.motion_duration = L.dmo_motion_duration(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.dmo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self, kin_time=0.0, rot_theta=0.0, max_time=20.0):
+        self.L.dmo_reset(self.h, C.c_double(kin_time), C.c_double(rot_theta), C.c_double(max_time))
+
+    def update(self, dt):
+        self.L.dmo_update(self.h, C.c_double(dt))
+
+    def set_action(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        self.L.dmo_set_action(self.h, dp(a))
+
+    def record_state(self):
+        out = np.zeros(self.state_size)
+        self.L.dmo_record_state(self.h, dp(out))
+        return out
+
+    def calc_reward(self):
+        return self.L.dmo_calc_reward(self.h)
+
+    def reward_terms(self):
+        e = np.zeros(5)
+        r = self.L.dmo_calc_reward_terms(self.h, dp(e))
+        return r, e
+
+    def need_new_action(self):
+        return bool(self.L.dmo_need_new_action(self.h))
+
+    def is_episode_end(self):
+        return bool(self.L.dmo_is_episode_end(self.h))
+
+    def check_terminate(self):
+        return int(self.L.dmo_check_terminate(self.h))
+
+    def check_valid_episode(self):
+        return bool(self.L.dmo_check_valid_episode(self.h))
+
+    def has_fallen(self):
+        return bool(self.L.dmo_has_fallen(self.h))
+
+    def get_time(self):
+        return self.L.dmo_get_time(self.h)
+
+    def get_pose(self):
+        p, v = np.zeros(self.pose_dim), np.zeros(self.pose_dim)
+        self.L.dmo_get_pose(self.h, dp(p), dp(v))
+        return p, v
+
+    def get_kin_pose(self):
+        p, v = np.zeros(self.pose_dim), np.zeros(self.pose_dim)
+        self.L.dmo_get_kin_pose(self.h, dp(p), dp(v))
+        return p, v
+
+    def kin_frame(self, t):
+        p, v = np.zeros(self.pose_dim), np.zeros(self.pose_dim)
+        self.L.dmo_kin_frame(self.h, C.c_double(t), dp(p), dp(v))
+        return p, v
+
+    def set_pose_vel(self, p, v):
+        p = np.ascontiguousarray(p, dtype=np.float64); v = np.ascontiguousarray(v, dtype=np.float64)
+        self.L.dmo_set_pose_vel(self.h, dp(p), dp(v))
+
+    def get_snapshot(self):
+        s = np.zeros(self.snapshot_size)
+        self.L.dmo_get_snapshot(self.h, dp(s))
+        return s
+
+    def set_snapshot(self, s):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        self.L.dmo_set_snapshot(self.h, dp(s))
+
+    def action_statics(self):
+        o, s, lo, hi = (np.zeros(self.action_size) for _ in range(4))
+        self.L.dmo_action_statics(self.h, dp(o), dp(s), dp(lo), dp(hi))
+        return o, s, lo, hi
+
+    def rbd_mass_bias(self):
+        M = np.zeros((self.pose_dim, self.pose_dim)); Cb = np.zeros(self.pose_dim)
+        self.L.dmo_rbd_mass_bias(self.h, dp(M), dp(Cb))
+        return M, Cb
+
+    def inv_dyna(self, acc):
+        acc = np.ascontiguousarray(acc, dtype=np.float64); tau = np.zeros(self.pose_dim)
+        self.L.dmo_inv_dyna(self.h, dp(acc), dp(tau))
+        return tau
+
+    def spd_tau(self, dt):
+        tau = np.zeros(self.pose_dim)
+        self.L.dmo_spd_tau(self.h, C.c_double(dt), dp(tau))
+        return tau
+
+    def bullet_aba(self, joint_tau, with_gravity=True):
+        jt = np.ascontiguousarray(joint_tau, dtype=np.float32); out = np.zeros(self.num_dofs, dtype=np.float32)
+        self.L.dmo_bullet_aba(self.h, fp(jt), 1 if with_gravity else 0, fp(out))
+        return out
