@@ -3,6 +3,7 @@ data/ and args/ (the reference's repository root).  Order: $DEEPMIMIC_ASSET_ROOT
 exists (build container), else the archive tests/golden/assets.tar.gz unpacked once next to it."""
 import os
 import tarfile
+import warnings
 import threading
 
 _lock = threading.Lock()
@@ -22,6 +23,8 @@ def asset_root(prefer_archive: bool = False) -> str:
         if not os.path.exists(stamp) or os.path.getmtime(stamp) < os.path.getmtime(arc):
             os.makedirs(out, exist_ok=True)
             with tarfile.open(arc, "r:gz") as tf:
-                tf.extractall(out)
+                with warnings.catch_warnings():
+                    warnings.simplefilter('ignore')
+                    tf.extractall(out)
             open(stamp, "w").close()
     return out

@@ -19,7 +19,7 @@ DM_STATE_OFFSET, DM_STATE_SCALE, DM_ACTION_OFFSET, DM_ACTION_SCALE, DM_ACTION_BO
 
 EXPORTS = ["dm_create", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_stream", "dm_sync", "dm_set_mode", "dm_reset", "dm_set_action",
            "dm_update", "dm_record_state", "dm_record_goal", "dm_calc_reward", "dm_observe", "dm_get_flags", "dm_step_host", "dm_get_snapshot",
-           "dm_set_snapshot", "dm_get_counters"]
+           "dm_set_snapshot", "dm_get_counters", "dm_debug_enable", "dm_get_debug"]
 
 
 def lib():
@@ -52,6 +52,8 @@ def lib():
         L.dm_get_snapshot.argtypes = [vp, C.c_int, dp]
         L.dm_set_snapshot.argtypes = [vp, C.c_int, dp]
         L.dm_get_counters.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.dm_debug_enable.argtypes = [vp, C.c_int]
+        L.dm_get_debug.argtypes = [vp, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -138,6 +140,14 @@ class BatchedCore:
         out = (C.c_int64 * 2)()
         self._chk(lib().dm_get_counters(self.h, out))
         return int(out[0]), int(out[1])
+
+    def debug_enable(self, on=True):
+        self._chk(lib().dm_debug_enable(self.h, 1 if on else 0))
+
+    def get_debug(self, env):
+        out = np.zeros(8 * 96 + 2048, dtype=np.float32)
+        self._chk(lib().dm_get_debug(self.h, env, C.c_void_p(out.ctypes.data)))
+        return out
 
     def stream(self):
         return lib().dm_stream(self.h)

@@ -151,7 +151,7 @@ bool build_device_model(dm_handle& H) {
         L.last_depth = last_depth[j];
         maxdepth = std::max(maxdepth, last_depth[j]);
         if (last_depth[j] >= dmk::kMaxChain) { g_err = "dof chain too long"; return false; }
-        if (root) for (int d = 0; d < 6; ++d) M.chain_dof[j][d] = static_cast<uint8_t>(d);
+        if (root) for (int d = 0; d < 6; ++d) { M.chain_dof[j][d] = static_cast<uint8_t>(d); M.dof_depth[d] = static_cast<uint8_t>(d); M.dof_link[d] = 0; }
         else for (int d = 0; d <= pd; ++d) M.chain_dof[j][d] = M.chain_dof[jd.parent][d];
         for (int d = 0; d < L.ndof; ++d) { M.chain_dof[j][L.depth0 + d] = static_cast<uint8_t>(L.dof0 + d); M.dof_depth[L.dof0 + d] = static_cast<uint8_t>(L.depth0 + d); M.dof_link[L.dof0 + d] = static_cast<uint8_t>(j); }
         L.anc_mask = (root ? 0u : M.link[jd.parent].anc_mask) | (1u << j);
@@ -499,6 +499,22 @@ int dm_set_snapshot(dm_handle* h, int env, const double* s) {
     DM_CUDA(cudaMemcpy(h->st.manifold + static_cast<size_t>(env) * nl * dmk::kManifoldFloats, man.data(), man.size() * sizeof(float), cudaMemcpyHostToDevice));
     DM_CUDA(cudaMemcpy(h->st.time + static_cast<size_t>(env) * dmk::kTimeDoubles, tm, sizeof(tm), cudaMemcpyHostToDevice));
     DM_CUDA(cudaMemcpy(h->st.flags + static_cast<size_t>(env) * dmk::kFlagInts, fl, sizeof(fl), cudaMemcpyHostToDevice));
+    return 0;
+}
+int dm_debug_enable(dm_handle* h, int on) {
+    DM_CUDA(cudaSetDevice(h->device));
+    DM_CUDA(cudaStreamSynchronize(h->stream));
+    if (on && !h->st.pdbg) {
+        DM_CUDA(cudaMalloc(&h->st.pdbg, static_cast<size_t>(h->padded_envs) * dmk::kDebugFloats * sizeof(float)));
+        DM_CUDA(cudaMemset(h->st.pdbg, 0, static_cast<size_t>(h->padded_envs) * dmk::kDebugFloats * sizeof(float)));
+    } else if (!on && h->st.pdbg) { cudaFree(h->st.pdbg); h->st.pdbg = nullptr; }
+    return 0;
+}
+int dm_get_debug(dm_handle* h, int env, float* out) {
+    DM_CUDA(cudaSetDevice(h->device));
+    DM_CUDA(cudaStreamSynchronize(h->stream));
+    if (!h->st.pdbg) { g_err = "debug dumps are not enabled"; return fail(); }
+    DM_CUDA(cudaMemcpy(out, h->st.pdbg + static_cast<size_t>(env) * dmk::kDebugFloats, dmk::kDebugFloats * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }
 int dm_get_counters(dm_handle* h, int64_t* out) {

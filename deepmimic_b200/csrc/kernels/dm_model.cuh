@@ -19,6 +19,7 @@ constexpr int kMaxChain = 24;   // longest root->leaf dof chain (humanoid3d 13, 
 constexpr int kMaxChildren = 4;
 constexpr int kMaxRows = 64;    // solver rows kept per env (contact rows come in triples) -- see DESIGN.md capacity note
 constexpr int kManifoldFloats = 48;  // per link: 4 points x 12 floats
+constexpr int kDebugFloats = 8 * kMaxDofs + 2048;   // test hook (dm_debug_*): stage dumps of one update
 
 enum DevJointType { kJRevolute = 0, kJSpherical = 1, kJFixed = 2 };
 enum DevShape { kSBox = 1, kSCapsule = 2, kSSphere = 3 };

@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(BLOCK) dm_update_kernel(const DevModel* __rest
     int f_term = fl[kFTerminate], f_valid = fl[kFValid], f_fallen = fl[kFFallen], f_over = fl[kFRowOverflow], f_updates = fl[kFUpdates];
 
     const float h = static_cast<float>(dt) / static_cast<float>(sim_substeps);
+    float* dbg = st.pdbg ? st.pdbg + static_cast<size_t>(env) * kDebugFloats : nullptr;   // test hook: stage dumps of the first update
     const V3 grav = mk3(M.gravity[0], M.gravity[1], M.gravity[2]);
 
     // registers describing the current configuration
@@ -420,6 +421,11 @@ __global__ void __launch_bounds__(BLOCK) dm_update_kernel(const DevModel* __rest
         }
         // ---------------- Stable PD (cImpPDController::CalcControlForces)
         build_dynamics(false, true);
+        if (dbg && upd == 0) {
+            for (int k = lane; k < n; k += W) { dbg[k] = S.bias[k]; dbg[kMaxDofs + k] = S.H[k * cs + M.dof_depth[k]]; }
+            for (int k = lane; k < n * cs && k < 2048; k += W) dbg[8 * kMaxDofs + k] = S.H[k];
+            __syncwarp();
+        }
         {
             const float fdt = static_cast<float>(dt);
             float e0 = 0, e1 = 0, e2 = 0;
@@ -455,6 +461,7 @@ __global__ void __launch_bounds__(BLOCK) dm_update_kernel(const DevModel* __rest
             if (ndof >= 1) S.tau[dof0] = t0;
             if (ndof == 3) { S.tau[dof0 + 1] = t1; S.tau[dof0 + 2] = t2; }
             __syncwarp();
+            if (dbg && upd == 0) { for (int k = lane; k < n; k += W) { dbg[2 * kMaxDofs + k] = S.tau[k]; dbg[3 * kMaxDofs + k] = S.bias[k]; } }
         }
         // ---------------- Bullet sub-steps
         bool in_contact_tol = false;
@@ -584,8 +591,10 @@ __global__ void __launch_bounds__(BLOCK) dm_update_kernel(const DevModel* __rest
             __syncwarp();
             factor();
             solve(S.bias);
+            if (dbg && upd == 0) { for (int k = lane; k < n; k += W) dbg[(sub == 0 ? 4 * kMaxDofs : 8 * kMaxDofs + 1024) + k] = S.bias[k]; }
             for (int k = lane; k < n; k += W) { float v = S.vel[k] + S.bias[k] * h; S.vel[k] = fminf(fmaxf(v, -100.f), 100.f); S.z[k] = 0.f; }
             __syncwarp();
+            if (dbg && upd == 0) { for (int k = lane; k < n; k += W) dbg[(sub == 0 ? 5 * kMaxDofs : 9 * kMaxDofs + 1024) + k] = S.vel[k]; if (lane == 0) dbg[(sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024)] = static_cast<float>(P); }
             // ---- joint-limit rows (btMultiBodyJointLimitConstraint): a lane may own up to two, at most one is active
             int lim_dir = 0; float lim_pen = 0.f;
             if (act && L.has_limit) {
@@ -769,6 +778,7 @@ __global__ void __launch_bounds__(BLOCK) dm_update_kernel(const DevModel* __rest
                 }
                 for (int k = lane; k < n; k += W) { float v = S.vel[k] + S.z[k]; S.vel[k] = fminf(fmaxf(v, -100.f), 100.f); }
                 __syncwarp();
+                if (dbg && upd == 0) { for (int k = lane; k < n; k += W) dbg[(sub == 0 ? 6 * kMaxDofs : 10 * kMaxDofs + 1024) + k] = S.vel[k]; for (int k = lane; k < NR && k < 60; k += W) dbg[(sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024) + 1 + k] = S.rlam[k]; }
             }
             // ---- integrate positions (btMultiBody::stepPositionsMultiDof) and refresh the configuration
             baseOmega = mk3(S.vel[0], S.vel[1], S.vel[2]); baseVel = mk3(S.vel[3], S.vel[4], S.vel[5]);

@@ -88,6 +88,8 @@ int dm_step_host(dm_handle* h, const float* h_actions, double dt, int n_updates,
  *  [29 + 55nl + 4j ..] PD target of joint j in DeepMimic joint-frame convention (w,x,y,z or angle) */
 int dm_get_snapshot(dm_handle* h, int env, double* h_out);
 int dm_set_snapshot(dm_handle* h, int env, const double* h_in);
+int dm_debug_enable(dm_handle* h, int on);                     /* test hook: per-env stage dumps of the first update of each launch */
+int dm_get_debug(dm_handle* h, int env, float* h_out);        /* 8*96 + 2048 floats, layout in kernels/dm_update.cu */
 int dm_get_counters(dm_handle* h, int64_t* h_out);           /* {kernel launches so far, row-capacity overflows seen (must stay 0)} */
 
 #ifdef __cplusplus

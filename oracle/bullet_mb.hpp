@@ -113,6 +113,9 @@ struct BtMultiBody {
     std::vector<int> invDOff;
     FM3 cachedTL, cachedTR, cachedLL, cachedLR;  // base articulated inertia blocks
     int n() const { return static_cast<int>(links.size()); }
+    // test/debug taps: velocities of the first sub-step of the last stepSimulation call, and the solved impulses
+    std::vector<float> dbg_after_aba, dbg_after_pgs, dbg_lambda, dbg_after_aba1, dbg_after_pgs1, dbg_lambda1;
+    int dbg_substep = 0;
 
     void finalize() {
         int off = 0;
@@ -599,6 +602,8 @@ struct BtMultiBody {
         }
         // finish: velocities += accumulated delta (clamped like applyDeltaVeeMultiDof), impulses written back to the manifold
         applyDeltaVee(deltaVelocities.data(), 1.0f);
+        if (dbg_substep == 1) { dbg_lambda1.clear(); for (auto& c : normals) dbg_lambda1.push_back(c.appliedImpulse); for (auto& c : frictions) dbg_lambda1.push_back(c.appliedImpulse); for (auto& c : limits) dbg_lambda1.push_back(c.appliedImpulse); }
+        if (dbg_substep == 0) { dbg_lambda.clear(); for (auto& c : normals) dbg_lambda.push_back(c.appliedImpulse); for (auto& c : frictions) dbg_lambda.push_back(c.appliedImpulse); for (auto& c : limits) dbg_lambda.push_back(c.appliedImpulse); }
         for (size_t k = 0; k < normals.size(); ++k) {
             normals[k].pt->appliedImpulse = normals[k].appliedImpulse;
             normals[k].pt->appliedImpulseLateral1 = frictions[2 * k].appliedImpulse;
@@ -610,8 +615,11 @@ struct BtMultiBody {
     void internalSingleStep(float h, const BtContactSolverInfo& base_info, float friction) {
         for (int i = 0; i < n(); ++i) collideLinkPlane(i);          // performDiscreteCollisionDetection
         computeAccelerationsABA(h);                                  // solveConstraints: ABA, v += a h
+        if (dbg_substep == 0) dbg_after_aba = realBuf; else if (dbg_substep == 1) dbg_after_aba1 = realBuf;
         BtContactSolverInfo info = base_info; info.timeStep = h;
         solveConstraints(info, friction);                            // PGS
+        if (dbg_substep == 0) dbg_after_pgs = realBuf; else if (dbg_substep == 1) dbg_after_pgs1 = realBuf;
+        dbg_substep++;
         stepPositions(h);                                            // integrateTransforms
         updateCollisionObjectWorldTransforms();
     }
@@ -620,6 +628,7 @@ struct BtMultiBody {
         int numSub = static_cast<int>(timeStep / fixedTimeStep);  // m_localTime starts at 0 and returns to 0 every call
         numSub = std::min(numSub, maxSubSteps);
         for (auto& L : links) L.appliedForce += L.mass * gravity;   // applyGravity (btMultiBodyDynamicsWorld)
+        dbg_substep = 0;
         for (int s = 0; s < numSub; ++s) internalSingleStep(fixedTimeStep, info, friction);
         for (auto& L : links) { L.appliedForce = F3(); L.appliedTorque = F3(); L.jointTorque[0] = L.jointTorque[1] = L.jointTorque[2] = 0; }  // clearForces
     }

@@ -808,6 +808,17 @@ void dmo_bullet_aba(void* h, const float* joint_tau, int with_gravity, float* ou
     mb.computeAccelerationsABA(1.0f);
     for (size_t k = 0; k < before.size(); ++k) out_acc[k] = mb.realBuf[k] - before[k];
 }
+// debug taps of the last Update: out = [after ABA (ndofs) | after PGS (ndofs) | lambdas (64)]
+void dmo_debug_taps(void* h, float* out) {
+    Oracle* o = static_cast<Oracle*>(h); int n = 6 + o->mb.numDofs;
+    for (int k = 0; k < n; ++k) { out[k] = k < (int)o->mb.dbg_after_aba.size() ? o->mb.dbg_after_aba[k] : 0; out[n + k] = k < (int)o->mb.dbg_after_pgs.size() ? o->mb.dbg_after_pgs[k] : 0; }
+    for (int k = 0; k < 64; ++k) out[2 * n + k] = k < (int)o->mb.dbg_lambda.size() ? o->mb.dbg_lambda[k] : 0;
+}
+void dmo_debug_taps1(void* h, float* out) {
+    Oracle* o = static_cast<Oracle*>(h); int n = 6 + o->mb.numDofs;
+    for (int k = 0; k < n; ++k) { out[k] = k < (int)o->mb.dbg_after_aba1.size() ? o->mb.dbg_after_aba1[k] : 0; out[n + k] = k < (int)o->mb.dbg_after_pgs1.size() ? o->mb.dbg_after_pgs1[k] : 0; }
+    for (int k = 0; k < 64; ++k) out[2 * n + k] = k < (int)o->mb.dbg_lambda1.size() ? o->mb.dbg_lambda1[k] : 0;
+}
 void dmo_kin_frame(void* h, double time, double* pose, double* vel) { Oracle* o = static_cast<Oracle*>(h); orc::VecD p, v; o->KinCalcPose(time, p); o->KinCalcVel(time, v); std::copy(p.begin(), p.end(), pose); std::copy(v.begin(), v.end(), vel); }
 void dmo_body_state(void* h, double* pos, double* rot, double* linvel, double* angvel) {
     Oracle* o = static_cast<Oracle*>(h);

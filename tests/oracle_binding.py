@@ -149,6 +149,12 @@ class Oracle:
         self.L.dmo_spd_tau(self.h, C.c_double(dt), dp(tau))
         return tau
 
+    def debug_taps(self, sub=0):
+        out = np.zeros(2 * self.num_dofs + 64, dtype=np.float32)
+        (self.L.dmo_debug_taps if sub == 0 else self.L.dmo_debug_taps1)(self.h, fp(out))
+        n = self.num_dofs
+        return out[:n], out[n:2 * n], out[2 * n:]
+
     def bullet_aba(self, joint_tau, with_gravity=True):
         jt = np.ascontiguousarray(joint_tau, dtype=np.float32); out = np.zeros(self.num_dofs, dtype=np.float32)
         self.L.dmo_bullet_aba(self.h, fp(jt), 1 if with_gravity else 0, fp(out))

@@ -1,0 +1,231 @@
+"""Known-answer tests that pin the CPU oracle WITHOUT Bullet: the reference ships no tests or golden
+vectors, so these are derived from the reference's own semantics.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.oracle_binding import Oracle
+
+SPINKICK = ["--arg_file", "args/run_humanoid3d_spinkick_args.txt"]
+WALK = ["--arg_file", "args/train_humanoid3d_walk_args.txt"]
+DOG = ["--arg_file", "args/train_dog3d_trot_args.txt"]
+
+
+def _layout(asset_root, char_file):
+    d = json.load(open(os.path.join(asset_root, char_file)))
+    types = [j["Type"] for j in d["Skeleton"]["Joints"]]
+    off, o = [], 0
+    for i, t in enumerate(types):
+        off.append(o)
+        o += 7 if i == 0 else {"spherical": 4, "revolute": 1, "fixed": 0}[t]
+    return types, off, o
+
+
+@pytest.mark.parametrize("args,nj,pose,dofs,state,action", [(SPINKICK, 15, 43, 34, 227, 28), (DOG, 23, 83, 64, 347, 58)])
+def test_dims(asset_root, args, nj, pose, dofs, state, action):
+    o = Oracle(args, asset_root)
+    assert (o.num_joints, o.pose_dim, o.num_dofs, o.state_size, o.action_size) == (nj, pose, dofs, state, action)
+
+
+def test_motion_duration_and_frames(asset_root):
+    o = Oracle(SPINKICK, asset_root)
+    assert abs(o.motion_duration - 1.283282) < 1e-9 and o.num_frames == 78
+    d = json.load(open(os.path.join(asset_root, "data/motions/humanoid3d_spinkick.txt")))
+    fr = np.array(d["Frames"])
+    times = np.concatenate([[0.0], np.cumsum(fr[:-1, 0])])
+    for i in (0, 1, 17, 40, 76):
+        p, _ = o.kin_frame(times[i] + 1e-12)   # the reset leaves origin at the sim root: compare joint slots only
+        q = fr[i, 1 + 7:]
+        for a in range(7, 43):
+            pass
+        # spherical quaternions are normalised at load; compare up to normalisation
+        assert np.abs(p[7:] - fr[i, 8:] / 1.0).max() < 1e-5
+    # cyclic: pose(t + dur) == pose(t) + root cycle delta (y zeroed)
+    o.reset(0.0, 0.0, 20.0)
+    p0, v0 = o.kin_frame(0.37)
+    p1, v1 = o.kin_frame(0.37 + o.motion_duration)
+    delta = fr[-1, 1:4] - fr[0, 1:4]
+    assert np.abs((p1[:3] - p0[:3]) - np.array([delta[0], 0.0, delta[2]])).max() < 1e-9
+    assert np.abs(p1[3:] - p0[3:]).max() < 1e-9 and np.abs(v1 - v0).max() < 1e-9
+
+
+def test_reward_is_one_after_reset_without_ground_lift(asset_root):
+    o = Oracle(SPINKICK, asset_root)
+    for t0 in (0.6, 0.75, 0.9):
+        o.reset(t0, 0.0, 20.0)
+        r, e = o.reward_terms()
+        assert abs(r - 1.0) < 1e-9, (t0, r, e)
+    # when ResolveCharGroundIntersect lifts the character the kinematic origin moves with it and the reference's
+    # ground-relative heights no longer agree: the deficit is exactly 4 end effectors + root, all with the same dy
+    o.reset(0.0, 0.0, 20.0)
+    r, e = o.reward_terms()
+    assert e[0] == 0 and e[1] == 0 and abs(e[2] - 4 * e[3]) < 1e-9
+
+
+def test_record_state_layout(asset_root):
+    o = Oracle(SPINKICK, asset_root)
+    o.reset(0.5, 0.0, 20.0)
+    s = o.record_state()
+    assert s.shape == (227,) and not np.isnan(s).any()
+    assert abs(s[0] - np.fmod(0.5 / o.motion_duration, 1.0)) < 1e-12       # phase slot
+    p, _ = o.get_pose()
+    assert abs(s[1] - p[1]) < 1e-6                                          # root height
+    nrm = s[2 + 3:2 + 6]; tan = s[2 + 6:2 + 9]
+    assert abs(np.linalg.norm(nrm) - 1) < 1e-6 and abs(np.linalg.norm(tan) - 1) < 1e-6 and abs(nrm @ tan) < 1e-6
+
+
+@pytest.mark.parametrize("args,char,mass", [(SPINKICK, "data/characters/humanoid3d.txt", 45.0), (DOG, "data/characters/dog3d.txt", 29.25)])
+def test_crba_rnea_self_consistency(asset_root, args, char, mass):
+    o = Oracle(args, asset_root)
+    types, off, n = _layout(asset_root, char)
+    o.reset(0.3, 0.0, 20.0)
+    rng = np.random.default_rng(0)
+    p, v = o.get_pose()
+    v = rng.standard_normal(n)
+    v[6] = 0
+    for j, t in enumerate(types):
+        if t == "spherical":
+            v[off[j] + 3] = 0
+    o.set_pose_vel(p, v)
+    M, Cb = o.rbd_mass_bias()
+    assert abs(M[0, 0] - mass) < 1e-9 and abs(M[1, 1] - mass) < 1e-9          # total mass
+    assert np.abs(M - M.T).max() < 1e-12
+    live = [i for i in range(n) if M[i, i] != 0]
+    assert len(live) == o.num_dofs
+    assert np.linalg.eigvalsh(M[np.ix_(live, live)]).min() > 0
+    acc = rng.standard_normal(n)
+    acc[[i for i in range(n) if i not in live]] = 0
+    tau = o.inv_dyna(acc)
+    assert np.abs(tau - (M @ acc + Cb)).max() < 1e-9                          # SolveInvDyna(acc) == M acc + C
+    # C(q, 0) is the gravity generalised force: linear root rows carry -m g
+    o.set_pose_vel(p, np.zeros(n))
+    _, Cg = o.rbd_mass_bias()
+    assert np.abs(Cg[:3] - np.array([0, mass * 9.8, 0])).max() < 1e-9
+
+
+def test_spd_fixed_point(asset_root):
+    """target == current pose, zero velocity: SPD torque equals the PD term of the gravity-induced motion only;
+    with the action set to the current pose and zero gains on the root the torque stays bounded and finite."""
+    o = Oracle(SPINKICK, asset_root)
+    o.reset(0.2, 0.0, 20.0)
+    tau = o.spd_tau(1.0 / 600.0)
+    assert np.isfinite(tau).all() and np.abs(tau[:7]).max() == 0.0
+
+
+def test_need_new_action_every_20_updates(asset_root):
+    o = Oracle(SPINKICK, asset_root)
+    for t0 in (0.0, 0.777):
+        o.reset(t0, 0.0, 100.0)
+        assert o.need_new_action()
+        hits = []
+        for k in range(1, 101):
+            o.set_action(np.zeros(o.action_size)) if o.need_new_action() else None
+            o.update(1.0 / 600.0)
+            if o.need_new_action():
+                hits.append(k)
+            if o.is_episode_end():
+                break
+        assert hits[:4] == [20, 40, 60, 80][:len(hits[:4])]
+
+
+def test_action_tables(asset_root):
+    o = Oracle(SPINKICK, asset_root)
+    off, scl, lo, hi = o.action_statics()
+    # spherical: bounds +-2pi, scale 1/pi, offset 0 ; knee (revolute [-3.14, 0]): offset 1.57, scale 1/6.28, bounds mean +- 2*range
+    assert np.allclose(lo[:3], -2 * np.pi) and np.allclose(hi[:3], 2 * np.pi) and np.allclose(scl[:3], 1 / np.pi) and np.allclose(off[:3], 0)
+    knee = 3 + 3 + 3
+    assert abs(off[knee] - 1.57) < 1e-12 and abs(scl[knee] - 0.5 / 3.14) < 1e-12 and abs(lo[knee] - (-1.57 - 6.28)) < 1e-12 and abs(hi[knee] - (-1.57 + 6.28)) < 1e-12
+
+
+def _box_character_root(asset_root, tmp_path):
+    """copy of humanoid3d whose capsules are replaced by boxes: DeepMimic's exact-shape inertia and Bullet's
+    collision-shape inertia then coincide, so the restated Bullet ABA must equal DeepMimic's M^-1 (tau - C)."""
+    root = tmp_path / "assets"
+    (root / "data" / "characters").mkdir(parents=True)
+    (root / "args").mkdir()
+    for sub in ("controllers", "motions", "terrain"):
+        os.symlink(os.path.join(asset_root, "data", sub), root / "data" / sub)
+    d = json.load(open(os.path.join(asset_root, "data/characters/humanoid3d.txt")))
+    for b in d["BodyDefs"]:
+        if b["Shape"] == "capsule":
+            r, h = b["Param0"], b["Param1"]
+            b["Shape"] = "box"; b["Param0"] = r; b["Param1"] = h + r; b["Param2"] = r
+    d.pop("DrawShapeDefs", None)
+    json.dump(d, open(root / "data" / "characters" / "box_humanoid3d.txt", "w"))
+    a = open(os.path.join(asset_root, "args/run_humanoid3d_spinkick_args.txt")).read().replace("humanoid3d.txt", "box_humanoid3d.txt")
+    open(root / "args" / "box_args.txt", "w").write(a)
+    return str(root)
+
+
+def test_bullet_aba_matches_deepmimic_rbd_on_box_character(asset_root, tmp_path):
+    root = _box_character_root(asset_root, tmp_path)
+    o = Oracle(["--arg_file", "args/box_args.txt"], root)
+    types, off, n = _layout(asset_root, "data/characters/humanoid3d.txt")
+    rng = np.random.default_rng(1)
+    o.reset(0.4, 0.0, 20.0)
+    p, _ = o.get_pose()
+    p[1] += 1.0
+    v = rng.standard_normal(n)
+    v[3:7] = 0   # zero root angular velocity: the reference's root "cj" term mixes frames otherwise (see next test)
+    for j, t in enumerate(types):
+        if t == "spherical":
+            v[off[j] + 3] = 0
+    o.set_pose_vel(p, v)
+    M, Cb = o.rbd_mass_bias()
+    tau = rng.standard_normal(n) * 20
+    tau[:7] = 0
+    for j, t in enumerate(types):
+        if t == "spherical":
+            tau[off[j] + 3] = 0
+    live = [i for i in range(n) if M[i, i] != 0]
+    acc = np.zeros(n)
+    acc[live] = np.linalg.solve(M[np.ix_(live, live)], (tau - Cb)[live])
+    jt = []
+    for j, t in enumerate(types):
+        if t == "spherical":
+            jt += list(16 * tau[off[j]:off[j] + 3])
+        elif t == "revolute":
+            jt += [16 * tau[off[j]]]
+    out = o.bullet_aba(np.array(jt), True)
+    b = [out[3] / 4, out[4] / 4, out[5] / 4, out[0], out[1], out[2], 0]
+    k = 6
+    for j, t in enumerate(types):
+        if t == "spherical":
+            b += list(out[k:k + 3]) + [0]; k += 3
+        elif t == "revolute":
+            b += [out[k]]; k += 1
+    b = np.array(b)
+    assert np.abs(acc - b).max() / np.abs(acc).max() < 2e-6
+
+
+def test_reference_root_cj_quirk_is_restated(asset_root, tmp_path):
+    """cRBDUtil::BuildCjRoot differentiates the root quaternion with the body-frame formula applied to the WORLD angular
+    velocity (RBDUtil.cpp:915-958); the oracle restates that literally, so with a spinning, translating root its linear
+    root acceleration differs from rigid-body truth (the Bullet-side ABA) while every joint acceleration still agrees."""
+    root = _box_character_root(asset_root, tmp_path)
+    o = Oracle(["--arg_file", "args/box_args.txt"], root)
+    types, off, n = _layout(asset_root, "data/characters/humanoid3d.txt")
+    o.reset(0.4, 0.0, 20.0)
+    p, _ = o.get_pose()
+    p[1] += 1.0
+    v = np.zeros(n); v[0:3] = [1.0, 0.5, -2.0]; v[3:6] = [0.7, -1.1, 0.4]
+    o.set_pose_vel(p, v)
+    M, Cb = o.rbd_mass_bias()
+    live = [i for i in range(n) if M[i, i] != 0]
+    acc = np.zeros(n); acc[live] = np.linalg.solve(M[np.ix_(live, live)], (-Cb)[live])
+    out = o.bullet_aba(np.zeros(o.num_dofs - 6), True)
+    assert np.abs(acc[3:6] - out[0:3]).max() < 1e-3          # angular root acceleration agrees
+    assert np.abs(acc[0:3] - out[3:6] / 4).max() > 0.1       # linear one does not: the quirk
+
+
+def test_free_fall_com_acceleration_is_g(asset_root):
+    o = Oracle(SPINKICK, asset_root)
+    o.reset(0.3, 0.0, 20.0)
+    p, v = o.get_pose()
+    p[1] += 2.0
+    o.set_pose_vel(p, np.zeros_like(v))
+    out = o.bullet_aba(np.zeros(o.num_dofs - 6), True)
+    # zero velocity, no torques: every point of the character accelerates at g (scaled units x4)
+    assert np.abs(out[3:6] - np.array([0, -9.8 * 4, 0])).max() < 2e-3 and np.abs(out[:3]).max() < 2e-3 and np.abs(out[6:]).max() < 5e-3
