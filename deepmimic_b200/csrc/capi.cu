@@ -3,7 +3,9 @@
 // launches CUDA work and fails loudly if the device / kernels are unavailable.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <numeric>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -14,7 +16,7 @@
 #include "kernels/dm_model.cuh"
 
 namespace dmk {
-template <int W, int BLOCK>
+template <int W, bool DEBUG>
 __global__ void dm_update_kernel(const DevModel*, DevState, const double*, const float*, double, int, int, int);
 template <int W, int BLOCK>
 __global__ void dm_observe_kernel(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
@@ -52,7 +54,7 @@ struct dm_handle {
     float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;            // staging for dm_step_host
     float *p_act = nullptr, *p_obs = nullptr, *p_rew = nullptr; int32_t* p_flags = nullptr;  // pinned host staging
     cudaStream_t stream = nullptr;
-    int device = 0, num_envs = 0, padded_envs = 0, W = 32, tiles = 2, maxrows = 36, smem_bytes = 0, mode = 0;
+    int device = 0, num_envs = 0, padded_envs = 0, W = 32, tiles = 2, maxrows = 36, smem_bytes = 0, mode = 0, minb = 4;
     uint64_t seed = 0, env_offset = 0;
     int64_t launches = 0;
     std::vector<double> st_off, st_scale, act_off, act_scale, act_min, act_max, st_groups;
@@ -235,18 +237,17 @@ void build_statics(dm_handle& H) {
     }
 }
 
-template <int W>
+template <int W, bool DEBUG>
 int launch_update(dm_handle* h, double dt, int n_updates) {
-    constexpr int BLOCK = 64;
-    auto kern = dmk::dm_update_kernel<W, BLOCK>;
+    auto kern = dmk::dm_update_kernel<W, DEBUG>;
     static thread_local const void* configured = nullptr;
     if (configured != reinterpret_cast<const void*>(kern)) {
         DM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
         DM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = reinterpret_cast<const void*>(kern);
     }
-    const int grid = h->padded_envs / (BLOCK / W);
-    kern<<<grid, BLOCK, h->smem_bytes, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, dt, n_updates, h->sa.cfg.num_sim_substeps, h->maxrows);
+    const int grid = h->padded_envs / h->tiles;
+    kern<<<grid, h->tiles * W, h->smem_bytes, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, dt, n_updates, h->sa.cfg.num_sim_substeps, h->maxrows);
     DM_CUDA(cudaGetLastError());
     h->launches++;
     return 0;
@@ -297,11 +298,25 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
     const auto& M = h->hm;
     h->W = (M.nl <= 16 && M.cs <= 16) ? 16 : 32;
     if (const char* w = std::getenv("DM_TILE_WIDTH")) { int v = std::atoi(w); if (v == 32 || (v == 16 && M.nl <= 16 && M.cs <= 16)) h->W = v; }
-    h->tiles = 64 / h->W;
-    h->padded_envs = ((num_envs + h->tiles - 1) / h->tiles) * h->tiles;
     h->maxrows = (h->W == 16) ? 36 : 60;
     if (const char* r = std::getenv("DM_MAX_ROWS")) { int v = std::atoi(r); if (v >= 12 && v <= 96) h->maxrows = (v / 3) * 3; }
-    h->smem_bytes = dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, h->tiles);
+    {
+        // one block per SM: as many environments per block as shared memory (227 KB) and 512 threads allow, balanced over the SMs
+        cudaDeviceProp prop;
+        if (!chk(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { fail(); return nullptr; }
+        const int per_env = dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, 1) - dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, 0);
+        const int hot = dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, 0);
+        int max_tiles = std::min(dmk::kUpdateMaxThreads / h->W, (static_cast<int>(prop.sharedMemPerBlockOptin) - hot) / per_env);
+        if (const char* t = std::getenv("DM_TILES_PER_BLOCK")) max_tiles = std::max(1, std::min(max_tiles, std::atoi(t)));
+        const int sms = prop.multiProcessorCount;
+        int tiles = std::min(max_tiles, std::max(1, (num_envs + sms - 1) / sms));
+        if (h->W == 16 && (tiles & 1)) tiles = std::min(max_tiles - (max_tiles & 1), tiles + 1);   // whole warps
+        if (h->W == 16 && (tiles & 1)) tiles = std::max(2, tiles - 1);
+        h->tiles = tiles;
+        const int quantum = (tiles * (64 / h->W)) / std::__gcd(tiles, 64 / h->W);   // multiple of both the update block and the 64-thread policy blocks
+        h->padded_envs = ((num_envs + quantum - 1) / quantum) * quantum;
+        h->smem_bytes = dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, h->tiles);
+    }
     const size_t N = static_cast<size_t>(h->padded_envs);
     const int ss = dmk::sim_stride(M.nl);
     bool ok = chk(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
@@ -403,7 +418,9 @@ int dm_set_action(dm_handle* h, const float* d_actions) {
 }
 int dm_update(dm_handle* h, double dt, int n_updates) {
     DM_CUDA(cudaSetDevice(h->device));
-    return h->W == 16 ? launch_update<16>(h, dt, n_updates) : launch_update<32>(h, dt, n_updates);
+    const bool dbg = h->st.pdbg != nullptr;
+    if (h->W == 16) return dbg ? launch_update<16, true>(h, dt, n_updates) : launch_update<16, false>(h, dt, n_updates);
+    return dbg ? launch_update<32, true>(h, dt, n_updates) : launch_update<32, false>(h, dt, n_updates);
 }
 int dm_observe(dm_handle* h, float* d_state, float* d_reward) {
     DM_CUDA(cudaSetDevice(h->device));
