@@ -17,7 +17,7 @@
 
 namespace dmk {
 template <int W, bool DEBUG>
-__global__ void dm_update_kernel(const DevModel*, DevState, const double*, const float*, double, int, int, int);
+__global__ void dm_update_kernel(const DevModel*, DevState, const double*, const float*, double, int, int, int, int);
 template <int W, int BLOCK>
 __global__ void dm_observe_kernel(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
 template <int W, int BLOCK>
@@ -54,7 +54,7 @@ struct dm_handle {
     float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;            // staging for dm_step_host
     float *p_act = nullptr, *p_obs = nullptr, *p_rew = nullptr; int32_t* p_flags = nullptr;  // pinned host staging
     cudaStream_t stream = nullptr;
-    int device = 0, num_envs = 0, padded_envs = 0, W = 32, tiles = 2, maxrows = 36, smem_bytes = 0, mode = 0, minb = 4;
+    int device = 0, num_envs = 0, padded_envs = 0, W = 32, tiles = 2, maxrows = 36, smem_bytes = 0, mode = 0, minb = 4, sync_every_stage = 0;
     uint64_t seed = 0, env_offset = 0;
     int64_t launches = 0;
     std::vector<double> st_off, st_scale, act_off, act_scale, act_min, act_max, st_groups;
@@ -247,7 +247,7 @@ int launch_update(dm_handle* h, double dt, int n_updates) {
         configured = reinterpret_cast<const void*>(kern);
     }
     const int grid = h->padded_envs / h->tiles;
-    kern<<<grid, h->tiles * W, h->smem_bytes, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, dt, n_updates, h->sa.cfg.num_sim_substeps, h->maxrows);
+    kern<<<grid, h->tiles * W, h->smem_bytes, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, dt, n_updates, h->sa.cfg.num_sim_substeps, h->maxrows, h->sync_every_stage);
     DM_CUDA(cudaGetLastError());
     h->launches++;
     return 0;
@@ -299,6 +299,7 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
     h->W = (M.nl <= 16 && M.cs <= 16) ? 16 : 32;
     if (const char* w = std::getenv("DM_TILE_WIDTH")) { int v = std::atoi(w); if (v == 32 || (v == 16 && M.nl <= 16 && M.cs <= 16)) h->W = v; }
     h->maxrows = (h->W == 16) ? 36 : 60;
+    if (const char* sv = std::getenv("DM_SYNC_EVERY_STAGE")) h->sync_every_stage = std::atoi(sv);
     if (const char* r = std::getenv("DM_MAX_ROWS")) { int v = std::atoi(r); if (v >= 12 && v <= 96) h->maxrows = (v / 3) * 3; }
     {
         // one block per SM: as many environments per block as shared memory (227 KB) and 512 threads allow, balanced over the SMs

@@ -97,8 +97,8 @@ __device__ __forceinline__ Q4 quat_integrate(V3 omega, Q4 quat, bool base_body, 
     if (fAngle * dt > kThr) fAngle = kThr / dt;
     V3 axis;
     if (fAngle < 0.001f) axis = angvel * (0.5f * dt - (dt * dt * dt) * 0.020833333333f * fAngle * fAngle);
-    else axis = angvel * (sinf(0.5f * fAngle * dt) / fAngle);
-    float cw = cosf(fAngle * dt * 0.5f);
+    else axis = angvel * (__sinf(0.5f * fAngle * dt) / fAngle);   // |angle| <= pi/8 (ANGULAR_MOTION_THRESHOLD): fast path error ~1e-7
+    float cw = __cosf(fAngle * dt * 0.5f);
     Q4 r = base_body ? qmul(quat, mkq(-axis.x, -axis.y, -axis.z, cw)) : qmul(mkq(axis.x, axis.y, axis.z, cw), quat);
     float n = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
     return mkq(r.x / n, r.y / n, r.z / n, r.w / n);
@@ -139,7 +139,8 @@ struct Smem {   // per-environment shared-memory carve-up (floats)
 };
 __host__ __device__ inline int smem_floats_per_env(int nl, int n, int cs, int maxrows) {
     int maxpts = maxrows / 3;
-    return nl * 24 + n * cs + 5 * n + maxrows * cs + 3 * maxrows + maxrows + maxpts * 6 + 12;   // + 9 floats world->base rotation (padded)
+    int f = nl * 24 + n * cs + 5 * n + maxrows * cs + 3 * maxrows + maxrows + maxpts * 6 + 12;   // + 9 floats world->base rotation (padded)
+    return ((f + 15) / 32) * 32 + 16;   // stride == 16 (mod 32 banks): the two environments of a warp (W = 16) hit disjoint bank halves
 }
 
 }  // namespace
@@ -147,7 +148,7 @@ __host__ __device__ inline int smem_floats_per_env(int nl, int n, int cs, int ma
 
 template <int W, bool DEBUG>
 __global__ void __launch_bounds__(kUpdateMaxThreads, 1) dm_update_kernel(const DevModel* __restrict__ gm, DevState st, const double* __restrict__ frame_times,
-                                                                 const float* __restrict__ frames, double dt, int n_updates, int sim_substeps, int maxrows) {
+                                                                 const float* __restrict__ frames, double dt, int n_updates, int sim_substeps, int maxrows, int sync_every_stage) {
     using T = Tile<W>;
     extern __shared__ __align__(16) float smem_raw[];
     const int tiles = blockDim.x / W;
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(kUpdateMaxThreads, 1) dm_update_kernel(const D
     };
 
     bool need_kin = true, pending_flags = false;
+    const bool ph_sync_every_stage = sync_every_stage != 0;
     const int stages_per_upd = sim_substeps + 1;
     const int total_stages = n_updates * stages_per_upd;
     #pragma unroll 1
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(kUpdateMaxThreads, 1) dm_update_kernel(const D
         if (stage == total_stages) break;
         // stage-synchronous execution: every warp of the block runs the same stage at the same time, so the (large) kernel streams
         // through the instruction cache once per stage instead of once per warp
-        if (__syncthreads_and(!alive)) break;
+        if (ph_sync_every_stage || (stage % stages_per_upd) == 0) { if (__syncthreads_and(!alive)) break; }
         const int ph = stage % stages_per_upd;      // 0: Stable-PD stage, 1..sim_substeps: Bullet sub-steps
         const bool first_upd = stage < stages_per_upd;
         int P = 0;
@@ -635,20 +637,56 @@ __global__ void __launch_bounds__(kUpdateMaxThreads, 1) dm_update_kernel(const D
         __syncwarp();
 
         // =================================================================== Featherstone's sparse factorisation H = L^T D L in place (lanes = chain depth)
-        #pragma unroll 1
-        for (int k = n - 1; k >= 0; --k) {
+        // (A) joint dofs, leaves first: eliminating dof k touches only the rows of its JOINT ancestors here (columns incl. the 6 base columns)
+#pragma unroll 1
+        for (int k = n - 1; k >= 6; --k) {
             const int lk = HM.dof_link[k], dk = HM.dof_depth[k];
             const float hk = (lane <= dk) ? S.H[k * cs + lane] : 0.f;   // row k on its chain
             const float inv = 1.0f / T::shfl(hk, dk);
             const unsigned char* chn = HM.chain + lk * cs;
-            #pragma unroll 1
-            for (int di = dk - 1; di >= 0; --di) {
+#pragma unroll 1
+            for (int di = dk - 1; di >= 6; --di) {
                 const float a = T::shfl(hk, di) * inv;
                 if (lane <= di) S.H[chn[di] * cs + lane] -= a * hk;
             }
             if (lane < dk) S.H[k * cs + lane] = hk * inv;
             if (lane == dk) S.dinv[k] = inv;
             __syncwarp();
+        }
+        // (B) base block: Schur complement  B -= sum_k L_kb D_k L_kb'  accumulated in registers, lanes = (b, b') pairs of the lower triangle
+        {
+            // pair index q in [0,21): row b, col c <= b
+            int pb[2], pc[2]; float acc[2] = {0.f, 0.f};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int q = lane + u * W;
+                int b = 0;
+                while ((b + 1) * (b + 2) / 2 <= q) ++b;
+                pb[u] = b; pc[u] = q - b * (b + 1) / 2;
+            }
+            const int npass = (21 + W - 1) / W;
+#pragma unroll 1
+            for (int k = 6; k < n; ++k) {
+                const float dkk = 1.0f / S.dinv[k];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) if (u < npass && lane + u * W < 21) acc[u] += S.H[k * cs + pb[u]] * dkk * S.H[k * cs + pc[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) if (u < npass && lane + u * W < 21) S.H[pb[u] * cs + pc[u]] -= acc[u];
+            __syncwarp();
+#pragma unroll 1
+            for (int k = 5; k >= 0; --k) {   // dense 6x6 L^T D L of the base block
+                const float hk = (lane <= k) ? S.H[k * cs + lane] : 0.f;
+                const float inv = 1.0f / T::shfl(hk, k);
+#pragma unroll 1
+                for (int di = k - 1; di >= 0; --di) {
+                    const float a = T::shfl(hk, di) * inv;
+                    if (lane <= di) S.H[di * cs + lane] -= a * hk;
+                }
+                if (lane < k) S.H[k * cs + lane] = hk * inv;
+                if (lane == k) S.dinv[k] = inv;
+                __syncwarp();
+            }
         }
         // =================================================================== x = M^-1 b in place on S.bias
         #pragma unroll 1
@@ -889,10 +927,10 @@ __global__ void __launch_bounds__(kUpdateMaxThreads, 1) dm_update_kernel(const D
 }
 
 // explicit instantiations used by capi.cu: (tile width, debug dumps)
-template __global__ void dm_update_kernel<16, false>(const DevModel*, DevState, const double*, const float*, double, int, int, int);
-template __global__ void dm_update_kernel<32, false>(const DevModel*, DevState, const double*, const float*, double, int, int, int);
-template __global__ void dm_update_kernel<16, true>(const DevModel*, DevState, const double*, const float*, double, int, int, int);
-template __global__ void dm_update_kernel<32, true>(const DevModel*, DevState, const double*, const float*, double, int, int, int);
+template __global__ void dm_update_kernel<16, false>(const DevModel*, DevState, const double*, const float*, double, int, int, int, int);
+template __global__ void dm_update_kernel<32, false>(const DevModel*, DevState, const double*, const float*, double, int, int, int, int);
+template __global__ void dm_update_kernel<16, true>(const DevModel*, DevState, const double*, const float*, double, int, int, int, int);
+template __global__ void dm_update_kernel<32, true>(const DevModel*, DevState, const double*, const float*, double, int, int, int, int);
 
 int dm_update_smem_bytes(int nl, int n, int cs, int maxrows, int tiles) {
     return hot_model_bytes(nl, n, cs) + smem_floats_per_env(nl, n, cs, maxrows) * tiles * static_cast<int>(sizeof(float));
