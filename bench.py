@@ -133,6 +133,7 @@ def main():
     import torch
     import torch.distributed as dist
     from deepmimic_b200.capi import BatchedCore
+    from deepmimic_b200.sharding import StepExchange, pack_rows
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -152,7 +153,7 @@ def main():
         actions = torch.clamp(-off + 0.25 / scl * torch.randn(bank, N, A, device="cuda", generator=g), lo, hi).contiguous()
         out = torch.zeros(N, S + 2, device="cuda")           # [obs | reward | done] rows of this rank
         obs = torch.zeros(N, S, device="cuda"); rew = torch.zeros(N, device="cuda"); flags = torch.zeros(N, 4, dtype=torch.int32, device="cuda")
-        gathered = torch.zeros(world * N, S + 2, device="cuda") if world > 1 else None
+        xchg = StepExchange(world * N, S + 2, rank, world, torch.device("cuda", local_rank))
         flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
         done_total = torch.zeros((), dtype=torch.int64, device="cuda")
 
@@ -163,9 +164,7 @@ def main():
                 core.update(dt, upl)
             if ev: ev[1].record(stream)
             core.observe(obs, rew); core.flags(flags)
-            out[:, :S] = obs; out[:, S] = rew; out[:, S + 1] = flags[:, 1].float()
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, out)
+            xchg.gather(pack_rows(out, obs, rew, flags[:, 1]))    # N > 1: one NCCL all-gather of every rank's [obs | reward | done] rows
             done_total.add_(flags[:, 1].sum())
             core.reset(False)
 

@@ -17,7 +17,7 @@ class DmDims(C.Structure):
 
 DM_STATE_OFFSET, DM_STATE_SCALE, DM_ACTION_OFFSET, DM_ACTION_SCALE, DM_ACTION_BOUND_MIN, DM_ACTION_BOUND_MAX, DM_STATE_NORM_GROUPS = range(7)
 
-EXPORTS = ["dm_create", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_stream", "dm_sync", "dm_set_mode", "dm_reset", "dm_set_action",
+EXPORTS = ["dm_create", "dm_load_host", "dm_get_model_info", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_stream", "dm_sync", "dm_set_mode", "dm_reset", "dm_set_action",
            "dm_update", "dm_record_state", "dm_record_goal", "dm_calc_reward", "dm_observe", "dm_get_flags", "dm_step_host", "dm_get_snapshot",
            "dm_set_snapshot", "dm_get_counters", "dm_debug_enable", "dm_get_debug"]
 
@@ -33,6 +33,9 @@ def lib():
         L.dm_create.restype = vp
         L.dm_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_uint64, C.c_uint64]
         L.dm_destroy.argtypes = [vp]
+        L.dm_load_host.restype = vp
+        L.dm_load_host.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p)]
+        L.dm_get_model_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
         L.dm_last_error.restype = C.c_char_p
         L.dm_get_dims.argtypes = [vp, C.POINTER(DmDims)]
         L.dm_get_static.argtypes = [vp, C.c_int, dp]
@@ -151,3 +154,48 @@ class BatchedCore:
 
     def stream(self):
         return lib().dm_stream(self.h)
+
+
+class HostModel:
+    """dm_load_host handle: the host loaders and the flat model, no device (used by the CPU tests and by tools)."""
+    INFO = dict(parents=0, joint_types=1, dof_offsets=2, pose_offsets=3, fall_bodies=4, end_effectors=5)
+
+    def __init__(self, args, asset_root):
+        L = lib()
+        enc = [a.encode() for a in args]
+        arr = (C.c_char_p * len(enc))(*enc)
+        h = L.dm_load_host(asset_root.encode(), len(enc), arr)
+        if not h:
+            raise RuntimeError("dm_load_host failed: %s" % L.dm_last_error().decode())
+        self.h = C.c_void_p(h)
+        self.dims = DmDims()
+        L.dm_get_dims(self.h, C.byref(self.dims))
+
+    def static(self, kind):
+        n = self.dims.state_size if kind in (DM_STATE_OFFSET, DM_STATE_SCALE, DM_STATE_NORM_GROUPS) else self.dims.action_size
+        out = np.zeros(n, dtype=np.float64)
+        if lib().dm_get_static(self.h, kind, _dptr(out)) != 0:
+            raise RuntimeError(lib().dm_last_error().decode())
+        return out
+
+    def info(self, name):
+        out = (C.c_int * self.dims.num_joints)()
+        if lib().dm_get_model_info(self.h, self.INFO[name], out) != 0:
+            raise RuntimeError(lib().dm_last_error().decode())
+        return np.array(out[:], dtype=np.int64)
+
+    def layout(self):
+        out = (C.c_int * 6)()
+        lib().dm_get_model_info(self.h, 6, out)
+        return dict(zip(("links", "dofs", "chain_stride", "tree_depth", "frames", "loop"), out[:]))
+
+    def close(self):
+        if self.h:
+            lib().dm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -35,6 +35,12 @@ __global__ void dm_flags_kernel(DevState st, int32_t* out, int num_real_envs) {
 }  // namespace dmk
 
 static thread_local std::string g_err;
+// every compute entry point: refuse host-only handles (dm_load_host) loudly, then select the handle's device
+#define DM_DEVICE(h)                                                                                                             \
+    do {                                                                                                                         \
+        if ((h)->stream == nullptr) { g_err = "host-only handle (dm_load_host): no device state, and there is no CPU fallback"; return fail(); } \
+        DM_CUDA(cudaSetDevice((h)->device));                                                                                     \
+    } while (0)
 #define DM_CUDA(call)                                                                                         \
     do {                                                                                                      \
         cudaError_t e_ = (call);                                                                              \
@@ -277,19 +283,46 @@ extern "C" {
 
 const char* dm_last_error(void) { return g_err.c_str(); }
 
-dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int num_envs, int device, uint64_t seed, uint64_t global_env_offset) {
-    std::unique_ptr<dm_handle> h(new dm_handle());
+// host half of dm_create: argument / asset loading and the flat model (no device work)
+static bool load_host_model(dm_handle& H, const char* asset_root, int argc, const char** argv) {
     try {
         std::vector<std::string> args(argv, argv + argc);
         dmh::ArgParser ap;
         ap.LoadArgs(args);
         std::string root = asset_root ? asset_root : "", arg_file;
         if (ap.ParseString("arg_file", arg_file) && !ap.LoadFile(dmh::resolve_path(root, arg_file))) throw std::runtime_error("Failed to load args from: " + arg_file);
-        h->sa = dmh::load_scene_assets(ap, root);
-    } catch (const std::exception& e) { g_err = e.what(); fail(); return nullptr; }
+        H.sa = dmh::load_scene_assets(ap, root);
+    } catch (const std::exception& e) { g_err = e.what(); return false; }
+    if (!build_device_model(H)) return false;
+    build_statics(H);
+    return true;
+}
+
+dm_handle* dm_load_host(const char* asset_root, int argc, const char** argv) {
+    std::unique_ptr<dm_handle> h(new dm_handle());
+    if (!load_host_model(*h, asset_root, argc, argv)) { fail(); return nullptr; }
+    return h.release();
+}
+
+int dm_get_model_info(dm_handle* h, int kind, int* out) {
+    const auto& M = h->hm;
+    switch (kind) {
+        case DM_INFO_PARENTS: for (int j = 0; j < M.nl; ++j) out[j] = M.link[j].parent; break;
+        case DM_INFO_JOINT_TYPES: for (int j = 0; j < M.nl; ++j) out[j] = M.link[j].jtype; break;
+        case DM_INFO_DOF_OFFSETS: for (int j = 0; j < M.nl; ++j) out[j] = M.link[j].dof0; break;
+        case DM_INFO_POSE_OFFSETS: for (int j = 0; j < M.nl; ++j) out[j] = M.link[j].pose_off; break;
+        case DM_INFO_FALL_BODIES: for (int j = 0; j < M.nl; ++j) out[j] = M.link[j].fall_contact; break;
+        case DM_INFO_END_EFFECTORS: for (int j = 0; j < M.nl; ++j) out[j] = M.link[j].end_eff; break;
+        case DM_INFO_LAYOUT: out[0] = M.nl; out[1] = M.n; out[2] = M.cs; out[3] = M.maxlevel; out[4] = M.num_frames; out[5] = M.loop_motion; break;
+        default: g_err = "dm_get_model_info: bad kind"; return fail();
+    }
+    return 0;
+}
+
+dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int num_envs, int device, uint64_t seed, uint64_t global_env_offset) {
+    std::unique_ptr<dm_handle> h(new dm_handle());
+    if (!load_host_model(*h, asset_root, argc, argv)) { fail(); return nullptr; }
     if (num_envs <= 0) { g_err = "num_envs must be positive"; fail(); return nullptr; }
-    if (!build_device_model(*h)) { fail(); return nullptr; }
-    build_statics(*h);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device available: deepmimic_b200 has no CPU fallback"; fail(); return nullptr; }
     auto chk = [&](cudaError_t e, const char* what) { if (e != cudaSuccess) { g_err = std::string(what) + ": " + cudaGetErrorString(e); return false; } return true; };
@@ -394,11 +427,11 @@ int dm_get_static(dm_handle* h, int kind, double* out) {
     return 0;
 }
 void* dm_stream(dm_handle* h) { return h->stream; }
-int dm_sync(dm_handle* h) { DM_CUDA(cudaStreamSynchronize(h->stream)); return 0; }
+int dm_sync(dm_handle* h) { DM_DEVICE(h); DM_CUDA(cudaStreamSynchronize(h->stream)); return 0; }
 int dm_set_mode(dm_handle* h, int mode) { h->mode = mode; return 0; }
 
 int dm_reset(dm_handle* h, int force_all, const double* kt, const double* mt, const double* th) {
-    DM_CUDA(cudaSetDevice(h->device));
+    DM_DEVICE(h);
     const double* src[3] = {kt, mt, th}; const double* dev[3] = {nullptr, nullptr, nullptr};
     std::vector<double> tmp(h->padded_envs);
     for (int k = 0; k < 3; ++k) if (src[k]) {
@@ -410,7 +443,7 @@ int dm_reset(dm_handle* h, int force_all, const double* kt, const double* mt, co
     return h->W == 16 ? launch_reset<16>(h, force_all, dev[0], dev[1], dev[2]) : launch_reset<32>(h, force_all, dev[0], dev[1], dev[2]);
 }
 int dm_set_action(dm_handle* h, const float* d_actions) {
-    DM_CUDA(cudaSetDevice(h->device));
+    DM_DEVICE(h);
     const int total = h->num_envs * h->hm.nl;
     dmk::dm_set_action_kernel<<<(total + 127) / 128, 128, 0, h->stream>>>(h->d_model, h->st, d_actions, h->num_envs);
     DM_CUDA(cudaGetLastError());
@@ -418,27 +451,27 @@ int dm_set_action(dm_handle* h, const float* d_actions) {
     return 0;
 }
 int dm_update(dm_handle* h, double dt, int n_updates) {
-    DM_CUDA(cudaSetDevice(h->device));
+    DM_DEVICE(h);
     const bool dbg = h->st.pdbg != nullptr;
     if (h->W == 16) return dbg ? launch_update<16, true>(h, dt, n_updates) : launch_update<16, false>(h, dt, n_updates);
     return dbg ? launch_update<32, true>(h, dt, n_updates) : launch_update<32, false>(h, dt, n_updates);
 }
 int dm_observe(dm_handle* h, float* d_state, float* d_reward) {
-    DM_CUDA(cudaSetDevice(h->device));
+    DM_DEVICE(h);
     return h->W == 16 ? launch_observe<16>(h, d_state, d_reward) : launch_observe<32>(h, d_state, d_reward);
 }
 int dm_record_state(dm_handle* h, float* d_out) { return dm_observe(h, d_out, nullptr); }
 int dm_record_goal(dm_handle*, float*) { return 0; }
 int dm_calc_reward(dm_handle* h, float* d_out) { return dm_observe(h, nullptr, d_out); }
 int dm_get_flags(dm_handle* h, int32_t* d_flags) {
-    DM_CUDA(cudaSetDevice(h->device));
+    DM_DEVICE(h);
     dmk::dm_flags_kernel<<<(h->num_envs + 127) / 128, 128, 0, h->stream>>>(h->st, d_flags, h->num_envs);
     DM_CUDA(cudaGetLastError());
     h->launches++;
     return 0;
 }
 int dm_step_host(dm_handle* h, const float* h_actions, double dt, int n_updates, float* h_state, float* h_reward, int32_t* h_flags) {
-    DM_CUDA(cudaSetDevice(h->device));
+    DM_DEVICE(h);
     const size_t N = h->num_envs, A = h->hm.action_size, S = h->hm.state_size;
     if (h_actions) {
         std::memcpy(h->p_act, h_actions, N * A * sizeof(float));
@@ -459,7 +492,7 @@ int dm_step_host(dm_handle* h, const float* h_actions, double dt, int n_updates,
 }
 
 int dm_get_snapshot(dm_handle* h, int env, double* s) {
-    DM_CUDA(cudaSetDevice(h->device));
+    DM_DEVICE(h);
     const auto& M = h->hm; const int nl = M.nl, ss = dmk::sim_stride(nl);
     std::vector<float> sim(ss), man(nl * dmk::kManifoldFloats); double tm[dmk::kTimeDoubles]; int fl[dmk::kFlagInts];
     DM_CUDA(cudaStreamSynchronize(h->stream));
@@ -490,7 +523,7 @@ int dm_get_snapshot(dm_handle* h, int env, double* s) {
     return 0;
 }
 int dm_set_snapshot(dm_handle* h, int env, const double* s) {
-    DM_CUDA(cudaSetDevice(h->device));
+    DM_DEVICE(h);
     const auto& M = h->hm; const int nl = M.nl, ss = dmk::sim_stride(nl);
     std::vector<float> sim(ss, 0.f), man(nl * dmk::kManifoldFloats, 0.f); double tm[dmk::kTimeDoubles] = {0}; int fl[dmk::kFlagInts] = {0};
     DM_CUDA(cudaStreamSynchronize(h->stream));
@@ -520,7 +553,7 @@ int dm_set_snapshot(dm_handle* h, int env, const double* s) {
     return 0;
 }
 int dm_debug_enable(dm_handle* h, int on) {
-    DM_CUDA(cudaSetDevice(h->device));
+    DM_DEVICE(h);
     DM_CUDA(cudaStreamSynchronize(h->stream));
     if (on && !h->st.pdbg) {
         DM_CUDA(cudaMalloc(&h->st.pdbg, static_cast<size_t>(h->padded_envs) * dmk::kDebugFloats * sizeof(float)));
@@ -529,14 +562,14 @@ int dm_debug_enable(dm_handle* h, int on) {
     return 0;
 }
 int dm_get_debug(dm_handle* h, int env, float* out) {
-    DM_CUDA(cudaSetDevice(h->device));
+    DM_DEVICE(h);
     DM_CUDA(cudaStreamSynchronize(h->stream));
     if (!h->st.pdbg) { g_err = "debug dumps are not enabled"; return fail(); }
     DM_CUDA(cudaMemcpy(out, h->st.pdbg + static_cast<size_t>(env) * dmk::kDebugFloats, dmk::kDebugFloats * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }
 int dm_get_counters(dm_handle* h, int64_t* out) {
-    DM_CUDA(cudaSetDevice(h->device));
+    DM_DEVICE(h);
     DM_CUDA(cudaStreamSynchronize(h->stream));
     std::vector<int> fl(static_cast<size_t>(h->padded_envs) * dmk::kFlagInts);
     DM_CUDA(cudaMemcpy(fl.data(), h->st.flags, fl.size() * sizeof(int), cudaMemcpyDeviceToHost));

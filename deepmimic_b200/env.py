@@ -1,0 +1,181 @@
+"""Batched mirror of the reference's Python env surface (R/env/deepmimic_env.py:6-187, R/env/env.py:6-230) over the
+C ABI.  Method names and meanings follow DeepMimicEnv; what was a per-agent vector there is an [N, .] CUDA tensor here
+(N environments of this rank), and `agent_id` is accepted and ignored (the imitation scene has one agent).
+For the unmodified single-env reference wrapper use the `DeepMimicCore` package next to this file instead."""
+import numpy as np
+
+from .capi import (BatchedCore, DM_ACTION_BOUND_MAX, DM_ACTION_BOUND_MIN, DM_ACTION_OFFSET, DM_ACTION_SCALE, DM_STATE_NORM_GROUPS,
+                   DM_STATE_OFFSET, DM_STATE_SCALE)
+from .sharding import StepExchange, pack_rows, rank_world, shard_range
+
+
+class DeepMimicBatchEnv:
+    class Terminate:
+        Null, Fail, Succ = 0, 1, 2
+
+    def __init__(self, args, num_envs, asset_root, device=0, seed=0, global_env_offset=0):
+        import torch
+        self.torch = torch
+        self._core = BatchedCore(list(args), num_envs, asset_root, device=device, seed=seed, global_env_offset=global_env_offset)
+        d = self._core.dims
+        self.num_envs, self.device = d.num_envs, torch.device("cuda", device)
+        self.stream = torch.cuda.ExternalStream(self._core.stream(), device=device)
+        with torch.cuda.stream(self.stream):
+            self._obs = torch.zeros(d.num_envs, d.state_size, device=self.device)
+            self._rew = torch.zeros(d.num_envs, device=self.device)
+            self._flags = torch.zeros(d.num_envs, 4, dtype=torch.int32, device=self.device)
+        self._time = 0.0
+        self._core.reset(True)
+
+    # ---- scene control (cDeepMimicCore::Update / Reset / GetTime, DeepMimicCore.cpp:88-139)
+    def update(self, timestep, n_updates=1):
+        self._core.update(timestep, n_updates)
+        self._time += timestep * n_updates
+
+    def reset(self, force_all=False):
+        """Restarts finished episodes (every environment with force_all)."""
+        self._core.reset(force_all)
+
+    def get_time(self):
+        return self._time
+
+    def get_name(self):
+        return "Imitate"
+
+    def is_rl_scene(self):
+        return True
+
+    def get_num_agents(self):
+        return 1
+
+    def get_num_update_substeps(self):
+        return self._core.dims.num_update_substeps
+
+    def set_mode(self, mode):
+        self._core.set_mode(int(mode))
+
+    # ---- per-step queries; tensors are views of buffers rewritten by the next call
+    def _refresh_flags(self):
+        self._core.flags(self._flags)
+        return self._flags
+
+    def need_new_action(self, agent_id=0):
+        return self._refresh_flags()[:, 0].bool()
+
+    def record_state(self, agent_id=0):
+        self._core.observe(self._obs, None)
+        return self._obs
+
+    def record_goal(self, agent_id=0):
+        return self.torch.zeros(self.num_envs, 0, device=self.device)
+
+    def set_action(self, agent_id_or_actions, actions=None):
+        a = agent_id_or_actions if actions is None else actions
+        if tuple(a.shape) != (self.num_envs, self.get_action_size()) or a.dtype != self.torch.float32 or not a.is_cuda:
+            raise ValueError("actions must be a float32 CUDA tensor [%d, %d]" % (self.num_envs, self.get_action_size()))
+        self._core.set_action(a.contiguous())
+
+    def calc_reward(self, agent_id=0):
+        self._core.observe(None, self._rew)
+        return self._rew
+
+    def is_episode_end(self):
+        return self._refresh_flags()[:, 1].bool()
+
+    def check_terminate(self, agent_id=0):
+        return self._refresh_flags()[:, 2]
+
+    def check_valid_episode(self):
+        return self._refresh_flags()[:, 3].bool()
+
+    def step(self, actions, timestep=1.0 / 600.0):
+        """One policy step: SetAction, the controller's query period worth of Update(timestep) calls (20 at the
+        reference's 600 Hz / 30 Hz), then state, reward and flags.  Returns (obs, reward, done, terminate)."""
+        self.set_action(actions)
+        self.update(timestep, self._core.dims.updates_per_action)
+        self._core.observe(self._obs, self._rew)
+        f = self._refresh_flags()
+        return self._obs, self._rew, f[:, 1].bool(), f[:, 2]
+
+    # ---- sizes and normalisation statics (DeepMimicCore.cpp:246-330)
+    def get_action_space(self, agent_id=0):
+        return 0  # ActionSpace.Continuous
+
+    def get_state_size(self, agent_id=0):
+        return self._core.dims.state_size
+
+    def get_goal_size(self, agent_id=0):
+        return self._core.dims.goal_size
+
+    def get_action_size(self, agent_id=0):
+        return self._core.dims.action_size
+
+    def get_num_actions(self, agent_id=0):
+        return 0
+
+    def build_state_offset(self, agent_id=0):
+        return np.array(self._core.static(DM_STATE_OFFSET))
+
+    def build_state_scale(self, agent_id=0):
+        return np.array(self._core.static(DM_STATE_SCALE))
+
+    def build_goal_offset(self, agent_id=0):
+        return np.zeros(0)
+
+    def build_goal_scale(self, agent_id=0):
+        return np.zeros(0)
+
+    def build_action_offset(self, agent_id=0):
+        return np.array(self._core.static(DM_ACTION_OFFSET))
+
+    def build_action_scale(self, agent_id=0):
+        return np.array(self._core.static(DM_ACTION_SCALE))
+
+    def build_action_bound_min(self, agent_id=0):
+        return np.array(self._core.static(DM_ACTION_BOUND_MIN))
+
+    def build_action_bound_max(self, agent_id=0):
+        return np.array(self._core.static(DM_ACTION_BOUND_MAX))
+
+    def build_state_norm_groups(self, agent_id=0):
+        return np.array(self._core.static(DM_STATE_NORM_GROUPS), dtype=np.int32)
+
+    def build_goal_norm_groups(self, agent_id=0):
+        return np.zeros(0, dtype=np.int32)
+
+    def get_reward_min(self, agent_id=0):
+        return 0.0
+
+    def get_reward_max(self, agent_id=0):
+        return 1.0
+
+    def get_reward_fail(self, agent_id=0):
+        return 0.0
+
+    def get_reward_succ(self, agent_id=0):
+        return 1.0
+
+    def sync(self):
+        self._core.sync()
+
+
+class ShardedDeepMimicEnv(DeepMimicBatchEnv):
+    """One process per GPU: this rank owns shard_range(total_envs, rank, world) of the job's environments; `step`
+    additionally all-gathers every rank's [obs | reward | done] rows (NCCL) so each rank returns the whole job's."""
+
+    def __init__(self, args, total_envs, asset_root, seed=0):
+        rank, world, local_rank = rank_world()
+        off, cnt = shard_range(total_envs, rank, world)
+        super().__init__(args, cnt, asset_root, device=local_rank, seed=seed, global_env_offset=off)
+        self.rank, self.world, self.total_envs, self.env_offset = rank, world, total_envs, off
+        S = self.get_state_size()
+        with self.torch.cuda.stream(self.stream):
+            self._rows = self.torch.zeros(cnt, S + 2, device=self.device)
+            self._xchg = StepExchange(total_envs, S + 2, rank, world, self.device)
+
+    def step(self, actions, timestep=1.0 / 600.0):
+        obs, rew, done, _ = super().step(actions, timestep)
+        with self.torch.cuda.stream(self.stream):
+            allrows = self._xchg.gather(pack_rows(self._rows, obs, rew, done))
+        S = self.get_state_size()
+        return allrows[:, :S], allrows[:, S], allrows[:, S + 1] > 0.5
