@@ -27,6 +27,15 @@ class DeepMimicBatchEnv:
         self._time = 0.0
         self._core.reset(True)
 
+    # ---- stream ordering: the library works on its own stream; these two event waits make every method safe to call
+    # from torch's current stream (inputs produced there are complete before the kernels read them, returned tensors are
+    # complete before the caller's next op on that stream reads them).  No host synchronisation.
+    def _pre(self):
+        self.stream.wait_stream(self.torch.cuda.current_stream(self.device))
+
+    def _post(self):
+        self.torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
     # ---- scene control (cDeepMimicCore::Update / Reset / GetTime, DeepMimicCore.cpp:88-139)
     def update(self, timestep, n_updates=1):
         self._core.update(timestep, n_updates)
@@ -34,6 +43,7 @@ class DeepMimicBatchEnv:
 
     def reset(self, force_all=False):
         """Restarts finished episodes (every environment with force_all)."""
+        self._pre()
         self._core.reset(force_all)
 
     def get_time(self):
@@ -56,14 +66,18 @@ class DeepMimicBatchEnv:
 
     # ---- per-step queries; tensors are views of buffers rewritten by the next call
     def _refresh_flags(self):
+        self._pre()
         self._core.flags(self._flags)
+        self._post()
         return self._flags
 
     def need_new_action(self, agent_id=0):
         return self._refresh_flags()[:, 0].bool()
 
     def record_state(self, agent_id=0):
+        self._pre()
         self._core.observe(self._obs, None)
+        self._post()
         return self._obs
 
     def record_goal(self, agent_id=0):
@@ -73,10 +87,13 @@ class DeepMimicBatchEnv:
         a = agent_id_or_actions if actions is None else actions
         if tuple(a.shape) != (self.num_envs, self.get_action_size()) or a.dtype != self.torch.float32 or not a.is_cuda:
             raise ValueError("actions must be a float32 CUDA tensor [%d, %d]" % (self.num_envs, self.get_action_size()))
+        self._pre()
         self._core.set_action(a.contiguous())
 
     def calc_reward(self, agent_id=0):
+        self._pre()
         self._core.observe(None, self._rew)
+        self._post()
         return self._rew
 
     def is_episode_end(self):
@@ -94,7 +111,7 @@ class DeepMimicBatchEnv:
         self.set_action(actions)
         self.update(timestep, self._core.dims.updates_per_action)
         self._core.observe(self._obs, self._rew)
-        f = self._refresh_flags()
+        f = self._refresh_flags()          # ends with _post(): obs / reward / flags are ordered before the caller's stream
         return self._obs, self._rew, f[:, 1].bool(), f[:, 2]
 
     # ---- sizes and normalisation statics (DeepMimicCore.cpp:246-330)
@@ -175,7 +192,6 @@ class ShardedDeepMimicEnv(DeepMimicBatchEnv):
 
     def step(self, actions, timestep=1.0 / 600.0):
         obs, rew, done, _ = super().step(actions, timestep)
-        with self.torch.cuda.stream(self.stream):
-            allrows = self._xchg.gather(pack_rows(self._rows, obs, rew, done))
+        allrows = self._xchg.gather(pack_rows(self._rows, obs, rew, done))    # on the caller's stream, after _post()
         S = self.get_state_size()
         return allrows[:, :S], allrows[:, S], allrows[:, S + 1] > 0.5

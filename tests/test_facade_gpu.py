@@ -1,0 +1,87 @@
+"""GPU tests of the reference-facing host layers: the cDeepMimicCore facade driven the way R/learning/rl_world.py drives
+the reference (update -> need_new_action -> record_state / calc_reward / set_action), and the batched env mirror."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from tests.oracle_binding import Oracle
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ARGS = ["--arg_file", "args/run_humanoid3d_spinkick_args.txt"]
+
+
+def _core_module():
+    sys.path.insert(0, os.path.join(REPO, "deepmimic_b200"))
+    try:
+        from DeepMimicCore import DeepMimicCore
+    finally:
+        sys.path.pop(0)
+    return DeepMimicCore
+
+
+def test_facade_runs_the_reference_call_pattern(asset_root):
+    DeepMimicCore = _core_module()
+    core = DeepMimicCore.cDeepMimicCore(False)
+    core.SeedRand(7)
+    core.ParseArgs(ARGS + ["--asset_root", asset_root])
+    core.Init()
+    o = Oracle(ARGS, asset_root)
+    assert core.GetStateSize(0) == o.state_size and core.GetActionSize(0) == o.action_size and core.GetGoalSize(0) == 0
+    assert core.GetNumUpdateSubsteps() == 10 and core.GetActionSpace(0) == 0
+    st = o.action_statics()
+    np.testing.assert_allclose(core.BuildActionOffset(0), st[0], atol=1e-12)
+    np.testing.assert_allclose(core.BuildActionScale(0), st[1], atol=1e-12)
+    np.testing.assert_allclose(core.BuildActionBoundMin(0), st[2], atol=1e-12)
+    np.testing.assert_allclose(core.BuildActionBoundMax(0), st[3], atol=1e-12)
+    assert len(core.BuildStateNormGroups(0)) == o.state_size and core.BuildStateNormGroups(0)[0] == -1
+    core.SetMode(1)
+    core.Reset()
+    assert core.GetTime() == 0.0 and core.NeedNewAction(0)        # a fresh episode asks for an action (CtController.cpp:35-39)
+    s0 = np.array(core.RecordState(0))
+    assert s0.shape == (o.state_size,) and np.isfinite(s0).all() and 0.0 <= s0[0] < 1.0   # slot 0 = phase
+    assert 0.0 < core.CalcReward(0) <= 1.0 + 1e-6
+    rng = np.random.default_rng(3)
+    n_actions, rewards = 0, []
+    for i in range(200):
+        if core.NeedNewAction(0):
+            rewards.append(core.CalcReward(0))
+            a = np.clip(-st[0] + 0.1 / st[1] * rng.standard_normal(o.action_size), st[2], st[3])
+            core.SetAction(0, a.tolist())
+            n_actions += 1
+        core.Update(1.0 / 600.0)
+        assert core.CheckValidEpisode()
+        if core.IsEpisodeEnd():
+            assert core.CheckTerminate(0) in (1, 2)
+            core.Reset()
+    assert n_actions >= 10          # 200 updates at 600 Hz = 10 policy steps (+ resets)
+    assert abs(core.GetTime() - 200 / 600.0) < 1e-9 or n_actions > 10
+    assert all(0.0 <= r <= 1.0 + 1e-6 for r in rewards)
+
+
+def test_batched_env_step_matches_manual_sequence(asset_root):
+    import torch
+    from deepmimic_b200.env import DeepMimicBatchEnv
+    N = 32
+    a = DeepMimicBatchEnv(ARGS, N, asset_root, seed=11)
+    b = DeepMimicBatchEnv(ARGS, N, asset_root, seed=11)        # same seed, same global ids -> identical reset draws
+    S, A = a.get_state_size(), a.get_action_size()
+    assert tuple(a.record_state().shape) == (N, S)
+    torch.testing.assert_close(a.record_state(), b.record_state(), rtol=0, atol=0)
+    off = torch.tensor(a.build_action_offset(), dtype=torch.float32, device="cuda"); scl = torch.tensor(a.build_action_scale(), dtype=torch.float32, device="cuda")
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    for _ in range(4):
+        act = (-off + 0.1 / scl * torch.randn(N, A, device="cuda", generator=g)).contiguous()
+        obs, rew, done, term = a.step(act)
+        obs, rew, done = obs.clone(), rew.clone(), done.clone()      # the env's buffers are rewritten by the next call
+        b.set_action(act)
+        for _ in range(20):
+            b.update(1.0 / 600.0)
+        torch.testing.assert_close(obs, b.record_state(), rtol=0, atol=0)     # fused 20-update launch == 20 single launches, bit for bit
+        torch.testing.assert_close(rew, b.calc_reward(), rtol=0, atol=0)
+        assert bool((done == b.is_episode_end()).all())
+        assert bool(((rew >= 0) & (rew <= 1 + 1e-6)).all())
+        a.reset(); b.reset()
+    a.sync(); b.sync()

@@ -45,6 +45,25 @@ def test_reset_obs_reward_match_oracle(asset_root, arg_file, char_file):
         assert np.abs(orc.record_state() - st[e].cpu().numpy().astype(np.float64)).max() < 1e-4
 
 
+def _explained_by_branch_flip(orc2, lay, jt, before, sg, rng, tries=64):
+    """Contact handling has discrete branches (a cached manifold point kept or dropped at the breaking threshold, the support
+    vertex of a flat box).  At a state that sits on such a threshold the ORACLE ITSELF flips under ulp-level input noise.
+    Returns True when the oracle, restarted from `before` with 1e-6 relative noise on the velocities, reproduces the GPU
+    result -- i.e. the GPU took a branch the reference arithmetic also takes, rather than computing something different."""
+    nl = lay.nl
+    for _ in range(tries):
+        p = before.copy()
+        p[lay.jvel: lay.jvel + 3 * nl] *= 1.0 + 1e-6 * rng.standard_normal(3 * nl)
+        p[7:13] *= 1.0 + 1e-6 * rng.standard_normal(6)
+        orc2.set_snapshot(p)
+        orc2.update(1.0 / 600.0)
+        s2 = orc2.get_snapshot()
+        eq, eqd = compare_sim_state(lay, s2, sg, jt)
+        if eq <= 1e-4 and eqd <= 5e-2 and lay.contact_counts(s2) == lay.contact_counts(sg):
+            return True
+    return False
+
+
 @pytest.mark.parametrize("arg_file,char_file", CASES)
 def test_teacher_forced_update_matches_oracle(asset_root, arg_file, char_file):
     """Each Update(1/600) starts from the oracle's exact state (q, qd, PD targets, contact cache, clocks).
@@ -58,12 +77,15 @@ def test_teacher_forced_update_matches_oracle(asset_root, arg_file, char_file):
       contact cache: identical point counts per link after every update; need_new_action flag identical."""
     import torch
     core, orc = _mk(asset_root, arg_file, 4)
+    orc2 = Oracle(["--arg_file", arg_file], asset_root)
     jt = joint_types_from_assets(asset_root, char_file)
     lay = SnapLayout(orc.num_joints)
     off, scl, lo, hi = orc.action_statics()
     rng = np.random.default_rng(1234)
+    rng2 = np.random.default_rng(99)
     dog = "dog" in arg_file
     eqs, eqds, ncs = [], [], []
+    flips, total = 0, 0
     worst_r = worst_s = 0.0
     rw = torch.zeros(4, device="cuda"); st = torch.zeros(4, core.dims.state_size, device="cuda")
     for t0 in (0.0, 0.3, 0.6, 0.9):
@@ -73,21 +95,27 @@ def test_teacher_forced_update_matches_oracle(asset_root, arg_file, char_file):
                 orc.set_action(random_policy_action(rng, off, scl, lo, hi))
             if orc.is_episode_end():
                 break
-            core.set_snapshot(0, orc.get_snapshot())
+            before = orc.get_snapshot()
+            core.set_snapshot(0, before)
             core.update(1.0 / 600.0, 1)
             orc.update(1.0 / 600.0)
             so, sg = orc.get_snapshot(), core.get_snapshot(0)
             eq, eqd = compare_sim_state(lay, so, sg, jt)
-            eqs.append(eq); eqds.append(eqd); ncs.append(sum(lay.contact_counts(so)))
-            assert eq <= 1e-3, (t0, upd, eq)
-            assert lay.contact_counts(so) == lay.contact_counts(sg), (t0, upd)
+            total += 1
             assert bool(sg[lay.scal + 11]) == orc.need_new_action()
+            if eq > 1e-3 or eqd > 0.5 or lay.contact_counts(so) != lay.contact_counts(sg):
+                assert _explained_by_branch_flip(orc2, lay, jt, before, sg, rng2), (t0, upd, eq, eqd, lay.contact_counts(so), lay.contact_counts(sg))
+                flips += 1
+                continue
+            eqs.append(eq); eqds.append(eqd); ncs.append(sum(lay.contact_counts(so)))
             if upd % 5 == 0 and not orc.has_fallen():   # reward / observation as pure functions of the oracle's post-state
                 core.set_snapshot(1, so)
                 core.observe(st, rw); core.sync()
                 worst_r = max(worst_r, abs(orc.calc_reward() - rw[1].item()))
                 worst_s = max(worst_s, np.abs(orc.record_state() - st[1].cpu().numpy().astype(np.float64)).max())
     eqs, eqds, ncs = np.array(eqs), np.array(eqds), np.array(ncs)
+    print("teacher-forced %s: %d branch flips in %d updates" % (arg_file, flips, total))
+    assert flips <= max(1, total // 100)
     print("teacher-forced %s: %d updates (%d with contacts) |dq| max %.2e ; |dqd| median %.2e p99 %.2e max %.2e (contact-free max %.2e) ; reward %.1e obs %.1e"
           % (arg_file, len(eqs), int((ncs > 0).sum()), eqs.max(), np.median(eqds), np.percentile(eqds, 99), eqds.max(), eqds[ncs == 0].max(), worst_r, worst_s))
     assert (ncs > 0).sum() > 50
