@@ -25,6 +25,10 @@ __global__ void dm_reset_kernel(const DevModel*, DevState, const double*, const 
                                 unsigned long long, unsigned long long, int);
 __global__ void dm_set_action_kernel(const DevModel*, DevState, const float*, int);
 int dm_update_smem_bytes(int nl, int n, int cs, int maxrows, int tiles);
+template <int W, bool DEBUG>
+__global__ void dm_step_kernel(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
+int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L);
+int dm_step_smem_bytes(const StepLayout& L, int tiles);
 
 __global__ void dm_flags_kernel(DevState st, int32_t* out, int num_real_envs) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,7 +64,8 @@ struct dm_handle {
     float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;            // staging for dm_step_host
     float *p_act = nullptr, *p_obs = nullptr, *p_rew = nullptr; int32_t* p_flags = nullptr;  // pinned host staging
     cudaStream_t stream = nullptr;
-    int device = 0, num_envs = 0, padded_envs = 0, W = 32, tiles = 2, maxrows = 36, smem_bytes = 0, mode = 0, minb = 4, sync_every_stage = 0;
+    int device = 0, num_envs = 0, padded_envs = 0, W = 32, tiles = 2, maxrows = 36, smem_bytes = 0, mode = 0, minb = 4, sync_every_stage = 0, kernel = 3;
+    dmk::StepLayout lay{};
     uint64_t seed = 0, env_offset = 0;
     int64_t launches = 0;
     std::vector<double> st_off, st_scale, act_off, act_scale, act_min, act_max, st_groups;
@@ -244,7 +249,23 @@ void build_statics(dm_handle& H) {
 }
 
 template <int W, bool DEBUG>
+int launch_step(dm_handle* h, double dt, int n_updates) {
+    auto kern = dmk::dm_step_kernel<W, DEBUG>;
+    static thread_local const void* configured = nullptr;
+    if (configured != reinterpret_cast<const void*>(kern)) {
+        DM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+        DM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = reinterpret_cast<const void*>(kern);
+    }
+    const int grid = h->padded_envs / h->tiles;
+    kern<<<grid, h->tiles * W, h->smem_bytes, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, dt, n_updates, h->sa.cfg.num_sim_substeps, h->lay, h->sync_every_stage);
+    DM_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+template <int W, bool DEBUG>
 int launch_update(dm_handle* h, double dt, int n_updates) {
+    if (h->kernel == 3) return launch_step<W, DEBUG>(h, dt, n_updates);
     auto kern = dmk::dm_update_kernel<W, DEBUG>;
     static thread_local const void* configured = nullptr;
     if (configured != reinterpret_cast<const void*>(kern)) {
@@ -338,9 +359,13 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
         // one block per SM: as many environments per block as shared memory (227 KB) and 512 threads allow, balanced over the SMs
         cudaDeviceProp prop;
         if (!chk(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { fail(); return nullptr; }
-        const int per_env = dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, 1) - dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, 0);
-        const int hot = dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, 0);
-        int max_tiles = std::min(dmk::kUpdateMaxThreads / h->W, (static_cast<int>(prop.sharedMemPerBlockOptin) - hot) / per_env);
+        if (const char* kv = std::getenv("DM_KERNEL")) h->kernel = std::atoi(kv);
+        int chain_len = 0;
+        for (int j = 0; j < M.nl; ++j) chain_len = std::max(chain_len, M.link[j].last_depth + 1);
+        dmk::dm_step_layout(M.nl, M.n, chain_len, h->maxrows, &h->lay);
+        const int per_env = h->kernel == 3 ? h->lay.env_floats * 4 : dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, 1) - dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, 0);
+        const int hot = h->kernel == 3 ? h->lay.hot_floats * 4 : dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, 0);
+        int max_tiles = std::min((h->kernel == 3 ? dmk::kStepMaxThreads : dmk::kUpdateMaxThreads) / h->W, (static_cast<int>(prop.sharedMemPerBlockOptin) - hot) / per_env);
         if (const char* t = std::getenv("DM_TILES_PER_BLOCK")) max_tiles = std::max(1, std::min(max_tiles, std::atoi(t)));
         const int sms = prop.multiProcessorCount;
         int tiles = std::min(max_tiles, std::max(1, (num_envs + sms - 1) / sms));
@@ -349,7 +374,7 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
         h->tiles = tiles;
         const int quantum = (tiles * (64 / h->W)) / std::__gcd(tiles, 64 / h->W);   // multiple of both the update block and the 64-thread policy blocks
         h->padded_envs = ((num_envs + quantum - 1) / quantum) * quantum;
-        h->smem_bytes = dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, h->tiles);
+        h->smem_bytes = h->kernel == 3 ? dmk::dm_step_smem_bytes(h->lay, h->tiles) : dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, h->tiles);
     }
     const size_t N = static_cast<size_t>(h->padded_envs);
     const int ss = dmk::sim_stride(M.nl);

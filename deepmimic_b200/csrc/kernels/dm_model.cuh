@@ -19,6 +19,7 @@ constexpr int kMaxChain = 24;   // longest root->leaf dof chain (humanoid3d 13, 
 constexpr int kMaxChildren = 4;
 constexpr int kMaxRows = 64;    // solver rows kept per env (contact rows come in triples) -- see DESIGN.md capacity note
 constexpr int kUpdateMaxThreads = 512;  // dm_update_kernel: one block per SM, up to 32 (W=16) / 16 (W=32) environments per block
+constexpr int kStepMaxThreads = 448;    // dm_step_kernel: 28 (W=16) / 14 (W=32) environments per block -> 144 registers per thread
 constexpr int kManifoldFloats = 48;  // per link: 4 points x 12 floats
 constexpr int kDebugFloats = 8 * kMaxDofs + 2048;   // test hook (dm_debug_*): stage dumps of one update
 
@@ -89,6 +90,14 @@ struct DevState {
     float* manifold;
     float* pdbg;  // optional debug scratch (n x ...), may be null
     int num_envs;
+};
+
+// shared-memory layout of dm_step_kernel (float offsets inside one environment's block), filled by dm_step_layout on the host and
+// passed by value as a kernel parameter (constant bank)
+struct StepLayout {
+    int nl, n, chain_len, maxrows, maxpts;
+    int oU, oR, oA, oW, oV, oY, oLam, oRl, oPp, oPi, oPr, oQ, oG, oZ;
+    int env_floats, hot_floats;
 };
 
 }  // namespace dmk

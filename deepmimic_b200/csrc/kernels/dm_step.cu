@@ -1,0 +1,989 @@
+// Fused per-update kernel (articulated-body formulation): one launch advances every environment by n_updates x Update(dt),
+// i.e. per update exactly what the reference does in cSceneSimChar::Update (R/DeepMimicCore/scenes/SceneSimChar.cpp:136-161):
+//   kin clock / cycle sync  (scenes/SceneImitate.cpp:306-318,420-444)
+//   Stable-PD torques       (sim/ImpPDController.cpp:136-195): (M + dt Kd) a = Kp e + Kd edot - C, tau = Kp e + Kd (edot - dt a)
+//   2 x Bullet sub-step     (sim/World.cpp:93-104): link-vs-plane manifolds, Featherstone forward dynamics, contact / friction /
+//                           joint-limit rows, 10 projected-Gauss-Seidel sweeps, exponential-map integration
+//   controller clock + 30 Hz "need action" edge (sim/CtController.cpp:221-227), fall / explode / timer flags.
+//
+// B200 mapping: one tile of W lanes (16 or 32) per environment, lane = link.  Every linear solve with the joint-space mass
+// matrix is done by the articulated-body recursion (the tree-structured L^T D L factorisation in its O(depth) form): one
+// leaves->root pass builds articulated inertias in registers (parent <- child by warp shuffles), one root->leaves pass
+// propagates accelerations.  The Stable-PD system is the same recursion with dt*Kd added to the joint-space diagonal and
+// DeepMimic's exact-shape inertias; the Bullet sub-steps use Bullet's collision-shape inertias (their unconstrained
+// accelerations are btMultiBody::computeAccelerationsArticulatedBodyAlgorithmMultiDof's).  Constraint rows are built with
+// lanes = rows (each lane walks its row's link chain once), the row coupling matrix J M^-1 J^T is formed explicitly in shared
+// memory and PGS runs in impulse space with lanes = rows (one shuffle + one FMA per row update instead of a reduction).
+// No tensor cores: there is no dense contraction here (34 or 70 dofs, tree-sparse); the path is latency-bound.
+#include "dm_model.cuh"
+
+namespace dmk {
+
+namespace {
+
+template <int W>
+struct Tl {
+    static __device__ __forceinline__ float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src, W); }
+    static __device__ __forceinline__ int shfli(int v, int src) { return __shfl_sync(0xffffffffu, v, src, W); }
+    static __device__ __forceinline__ V3 shfl3(V3 v, int src) { return mk3(shfl(v.x, src), shfl(v.y, src), shfl(v.z, src)); }
+    static __device__ __forceinline__ S6 shfl6(S6 v, int src) { return mks(shfl3(v.a, src), shfl3(v.l, src)); }
+};
+__device__ __forceinline__ int wmax(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// articulated (or rigid) spatial inertia about a link's joint pivot, link axes:  n = ww*w + wv*v ; f = wv^T*w + vv*v
+struct Art {
+    float ww[6];   // xx xy xz yy yz zz
+    float wv[9];   // row major
+    float vv[6];
+};
+__device__ __forceinline__ V3 wvT_mul(const float* g, V3 w) { return mk3(g[0] * w.x + g[3] * w.y + g[6] * w.z, g[1] * w.x + g[4] * w.y + g[7] * w.z, g[2] * w.x + g[5] * w.y + g[8] * w.z); }
+__device__ __forceinline__ V3 wv_mul(const float* g, V3 v) { return mk3(g[0] * v.x + g[1] * v.y + g[2] * v.z, g[3] * v.x + g[4] * v.y + g[5] * v.z, g[6] * v.x + g[7] * v.y + g[8] * v.z); }
+// R^T S R for a symmetric S (R row-major, maps parent -> child axes)
+__device__ __forceinline__ void rot_sym(const M3& R, const float* s, float* o) {
+    // T = S R (3x3), o = R^T T (symmetric)
+    float t[9];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        t[0 + j] = s[0] * R.m[j] + s[1] * R.m[3 + j] + s[2] * R.m[6 + j];
+        t[3 + j] = s[1] * R.m[j] + s[3] * R.m[3 + j] + s[4] * R.m[6 + j];
+        t[6 + j] = s[2] * R.m[j] + s[4] * R.m[3 + j] + s[5] * R.m[6 + j];
+    }
+    o[0] = R.m[0] * t[0] + R.m[3] * t[3] + R.m[6] * t[6];
+    o[1] = R.m[0] * t[1] + R.m[3] * t[4] + R.m[6] * t[7];
+    o[2] = R.m[0] * t[2] + R.m[3] * t[5] + R.m[6] * t[8];
+    o[3] = R.m[1] * t[1] + R.m[4] * t[4] + R.m[7] * t[7];
+    o[4] = R.m[1] * t[2] + R.m[4] * t[5] + R.m[7] * t[8];
+    o[5] = R.m[2] * t[2] + R.m[5] * t[5] + R.m[8] * t[8];
+}
+__device__ __forceinline__ void rot_gen(const M3& R, const float* g, float* o) {
+    float t[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) t[i * 3 + j] = g[i * 3] * R.m[j] + g[i * 3 + 1] * R.m[3 + j] + g[i * 3 + 2] * R.m[6 + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o[i * 3 + j] = R.m[i] * t[j] + R.m[3 + i] * t[3 + j] + R.m[6 + i] * t[6 + j];
+}
+// motion vector, parent pivot frame -> child pivot frame (R parent->child axes, c = parent pivot -> child pivot in parent axes)
+__device__ __forceinline__ S6 xm(const M3& R, V3 c, S6 m) { return mks(mul(R, m.a), mul(R, m.l - cross(c, m.a))); }
+// force vector, child pivot frame -> parent pivot frame
+__device__ __forceinline__ S6 xf(const M3& R, V3 c, S6 f) { V3 l = mulT(R, f.l); return mks(mulT(R, f.a) + cross(c, l), l); }
+
+__device__ __forceinline__ float normalize_angle3(float t) {  // cMathUtil::NormalizeAngle
+    float n = fmodf(t, 6.283185307179586f);
+    if (n > 3.14159265358979f) n -= 6.283185307179586f;
+    else if (n < -3.14159265358979f) n += 6.283185307179586f;
+    return n;
+}
+// rotation vector of a unit quaternion, same semantics as cMathUtil::QuaternionToAxisAngle (theta in [-pi,pi], zero when
+// sin(theta/2) <= 1e-6) but evaluated with atan2 so small angles keep fp32 accuracy
+__device__ __forceinline__ V3 quat_rotvec3(Q4 q) {
+    float s = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
+    if (!(s > 0.000001f)) return mk3(0.f, 0.f, 0.f);
+    float th = normalize_angle3(2.0f * atan2f(s, q.w));
+    float k = th / s;
+    return mk3(q.x * k, q.y * k, q.z * k);
+}
+// btMultiBody::stepPositionsMultiDof's exponential-map quaternion update
+__device__ __forceinline__ Q4 quat_integrate3(V3 omega, Q4 quat, bool base_body, float dt) {
+    V3 angvel = base_body ? omega : qrot(quat, omega);
+    float fAngle = sqrtf(dot(angvel, angvel));
+    const float kThr = 0.5f * 1.57079632679489661923f;
+    if (fAngle * dt > kThr) fAngle = kThr / dt;
+    V3 axis;
+    if (fAngle < 0.001f) axis = angvel * (0.5f * dt - (dt * dt * dt) * 0.020833333333f * fAngle * fAngle);
+    else axis = angvel * (__sinf(0.5f * fAngle * dt) / fAngle);   // |angle| <= pi/8 (ANGULAR_MOTION_THRESHOLD): fast path error ~1e-7
+    float cw = __cosf(fAngle * dt * 0.5f);
+    Q4 r = base_body ? qmul(quat, mkq(-axis.x, -axis.y, -axis.z, cw)) : qmul(mkq(axis.x, axis.y, axis.z, cw), quat);
+    float n = rsqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
+    return mkq(r.x * n, r.y * n, r.z * n, r.w * n);
+}
+
+// ---- block-shared model table, floats per link (LK)
+enum LkSlot { kLC = 0 /*3*/, kLD = 3 /*3*/, kLM = 6, kLWd = 7 /*6*/, kLWb = 13 /*6*/, kLAx = 19 /*3*/, kLInt = 22 /* parent|jtype|ndof|depth0 */, kLInt2 = 23 /* dof0|lastd|nchild */, kLkFloats = 24 };
+
+}  // namespace
+
+int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L) {
+    const int maxpts = maxrows / 3;
+    int o = 0;
+    L->nl = nl; L->n = n; L->chain_len = chain_len; L->maxrows = maxrows; L->maxpts = maxpts;
+    L->oU = o; o += nl * 24;                       // per link: U0 U1 U2 (6 each), 1/D (3), sqrt(1/D) (3)
+    L->oR = o; o += nl * 12;                       // per link: parent->link rotation (9) + pad
+    L->oA = o;                                     // union { world frames + link velocities | packed lower triangle of J M^-1 J^T }
+    const int world = nl * 20, tri = maxrows * (maxrows + 1) / 2;
+    L->oW = o; L->oV = o + nl * 12;
+    o += (world > tri ? world : tri);
+    L->oY = o; o += chain_len * maxrows;           // Yt[depth][row]
+    L->oLam = o; o += maxrows;
+    L->oRl = o; o += maxrows;                      // row -> link (int)
+    L->oPp = o; o += maxpts * 4; L->oPi = o; o += maxpts; L->oPr = o; o += maxpts;
+    L->oQ = o; o += 4 * 8;                         // limit rows: link, dir, penetration, joint rate (<= 8)
+    L->oG = o; o += 21 + 9 + 2;                    // base Cholesky factor (21), world->base rotation (9)
+    L->oZ = o; o += ((n + 3) / 4) * 4;
+    L->env_floats = ((o + 15) / 32) * 32 + 16;     // stride == 16 (mod 32 banks): the two environments of a warp (W = 16) hit disjoint bank halves
+    L->hot_floats = ((nl * kLkFloats + (nl * nl + nl * chain_len + 3) / 4 + 8 + 3) / 4) * 4;
+    return L->hot_floats * 4 + 0;
+}
+int dm_step_smem_bytes(const StepLayout& L, int tiles) { return (L.hot_floats + L.env_floats * tiles) * static_cast<int>(sizeof(float)); }
+
+template <int W, bool DEBUG>
+__global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevModel* __restrict__ gm, DevState st, const double* __restrict__ frame_times,
+                                                                       const float* __restrict__ frames, double dt, int n_updates, int sim_substeps, StepLayout LY, int sync_mode) {
+    using T = Tl<W>;
+    extern __shared__ __align__(16) float sm[];
+    const int tiles = blockDim.x / W;
+    const int tile = threadIdx.x / W;
+    const int lane = threadIdx.x % W;
+    const int env = blockIdx.x * tiles + tile;   // host guarantees num_envs (padded) is a multiple of tiles
+    const DevModel& M = *gm;
+    const int nl = LY.nl, n = LY.n, maxlevel = M.maxlevel, CL = LY.chain_len, MR = LY.maxrows;
+    const bool act = lane < nl;
+    const int li = act ? lane : nl - 1;
+    const DevLink& L = M.link[li];
+
+    // ---- block-shared tables: per-link constants (LK), common chain depth of two links (CD), chain depth -> dof (CH), children per level
+    float* LK = sm;
+    unsigned char* CD = reinterpret_cast<unsigned char*>(sm + nl * kLkFloats);
+    unsigned char* CH = CD + nl * nl;
+    int* LVC = reinterpret_cast<int*>(sm + LY.hot_floats - 8);
+    for (int j = threadIdx.x; j < nl; j += blockDim.x) {
+        const DevLink& K = M.link[j];
+        float* q = LK + j * kLkFloats;
+        const int p = K.parent;
+        for (int k = 0; k < 3; ++k) { q[kLC + k] = K.evec[k] + (p >= 0 ? M.link[p].dvec[k] : 0.f); q[kLD + k] = K.dvec[k]; q[kLAx + k] = K.axis[k]; }
+        q[kLM] = K.mass;
+        // rigid-body inertia about the joint pivot (COM at d): ww = Icom + m (|d|^2 1 - d d^T)
+        const float m = K.mass, dx = K.dvec[0], dy = K.dvec[1], dz = K.dvec[2], dd = dx * dx + dy * dy + dz * dz;
+        const float sh[6] = {m * (dd - dx * dx), -m * dx * dy, -m * dx * dz, m * (dd - dy * dy), -m * dy * dz, m * (dd - dz * dz)};
+        q[kLWd + 0] = K.inertiaD[0] + sh[0]; q[kLWd + 1] = sh[1]; q[kLWd + 2] = sh[2]; q[kLWd + 3] = K.inertiaD[1] + sh[3]; q[kLWd + 4] = sh[4]; q[kLWd + 5] = K.inertiaD[2] + sh[5];
+        q[kLWb + 0] = K.inertiaB[0] + sh[0]; q[kLWb + 1] = sh[1]; q[kLWb + 2] = sh[2]; q[kLWb + 3] = K.inertiaB[1] + sh[3]; q[kLWb + 4] = sh[4]; q[kLWb + 5] = K.inertiaB[2] + sh[5];
+        reinterpret_cast<int*>(q)[kLInt] = (K.parent & 0xff) | ((K.jtype & 0xff) << 8) | ((K.ndof & 0xff) << 16) | ((K.depth0 & 0xff) << 24);
+        reinterpret_cast<int*>(q)[kLInt2] = (K.dof0 & 0xff) | ((K.last_depth & 0xff) << 8) | ((K.nchild & 0xff) << 16);
+        for (int d = 0; d < CL; ++d) CH[j * CL + d] = M.chain_dof[j][d];
+        for (int b = 0; b < nl; ++b) {
+            int c = 0;
+            const int lim = min(K.last_depth, M.link[b].last_depth);
+            while (c <= lim && M.chain_dof[j][c] == M.chain_dof[b][c]) ++c;
+            CD[j * nl + b] = static_cast<unsigned char>(c);
+        }
+    }
+    if (threadIdx.x < 8) {
+        int mx = 0;
+        for (int j = 0; j < nl; ++j) if (M.link[j].level == static_cast<int>(threadIdx.x)) mx = max(mx, M.link[j].nchild);
+        LVC[threadIdx.x] = mx;
+    }
+    __syncthreads();
+    auto lk_i = [&](int j) { return reinterpret_cast<const int*>(LK + j * kLkFloats)[kLInt]; };
+    auto lk_i2 = [&](int j) { return reinterpret_cast<const int*>(LK + j * kLkFloats)[kLInt2]; };
+
+    float* E = sm + LY.hot_floats + tile * LY.env_floats;   // this environment's block
+    float* sU = E + LY.oU; float* sR = E + LY.oR; float* sW = E + LY.oW; float* sV = E + LY.oV; float* sA = E + LY.oA; float* sY = E + LY.oY;
+    float* sLam = E + LY.oLam; int* sRl = reinterpret_cast<int*>(E + LY.oRl);
+    float* sPp = E + LY.oPp; float* sPi = E + LY.oPi; int* sPr = reinterpret_cast<int*>(E + LY.oPr);
+    float* sQ = E + LY.oQ; float* sG = E + LY.oG; float* sZ = E + LY.oZ;
+
+    // ---- per-lane model constants kept in registers
+    const int parent = L.parent, jtype = L.jtype, ndof = act ? L.ndof : 0, dof0 = L.dof0, level = act ? L.level : 1000;
+    const V3 dvec = mk3(L.dvec[0], L.dvec[1], L.dvec[2]);
+    const V3 cvec = mk3(LK[li * kLkFloats + kLC], LK[li * kLkFloats + kLC + 1], LK[li * kLkFloats + kLC + 2]);
+    const V3 axis = mk3(L.axis[0], L.axis[1], L.axis[2]);
+    const float mass = act ? L.mass : 0.f;
+    const int plane = parent >= 0 ? parent : 0;
+    const int nchild = act ? L.nchild : 0;
+    const int child_pack = (L.child[0] & 0xff) | ((L.child[1] & 0xff) << 8) | ((L.child[2] & 0xff) << 16) | ((L.child[3] & 0xff) << 24);
+    auto dir_of = [&](int d) { return (jtype == kJSpherical) ? unit3(d) : axis; };
+
+    // ---- state load (env-major block, float4)
+    const int ss = sim_stride(nl);
+    float* sim = st.sim + static_cast<size_t>(env) * ss;
+    double* tm = st.time + static_cast<size_t>(env) * kTimeDoubles;
+    int* fl = st.flags + static_cast<size_t>(env) * kFlagInts;
+    float* mani = st.manifold + static_cast<size_t>(env) * nl * kManifoldFloats;
+    V3 basePos; Q4 baseQuat; V3 baseOmega, baseVel;
+    {
+        float4 b0 = reinterpret_cast<const float4*>(sim)[0], b1 = reinterpret_cast<const float4*>(sim)[1], b2 = reinterpret_cast<const float4*>(sim)[2],
+               b3 = reinterpret_cast<const float4*>(sim)[3];
+        basePos = mk3(b0.x, b0.y, b0.z); baseQuat = mkq(b1.x, b1.y, b1.z, b1.w); baseOmega = mk3(b2.x, b2.y, b2.z); baseVel = mk3(b3.x, b3.y, b3.z);
+    }
+    float4 jp = reinterpret_cast<const float4*>(sim + 16)[li];
+    float4 jv = reinterpret_cast<const float4*>(sim + 16 + 4 * nl)[li];
+    double kin_time = tm[kTKin], ctrl_time = tm[kTCtrl], prev_act = tm[kTPrevAct], timer = tm[kTTimer];
+    const double init_off = tm[kTInitOff], timer_max = tm[kTTimerMax];
+    double org_x = tm[kTOrigin], org_y = tm[kTOrigin + 1], org_z = tm[kTOrigin + 2];
+    int need_action = fl[kFNeedAction];
+    bool alive = fl[kFDone] == 0;
+    int f_over = fl[kFRowOverflow], f_updates = fl[kFUpdates];
+
+    const float h = static_cast<float>(dt) / static_cast<float>(sim_substeps);
+    const float fdt = static_cast<float>(dt);
+    const V3 grav = mk3(M.gravity[0], M.gravity[1], M.gravity[2]);
+    float* dbg = (DEBUG && st.pdbg) ? st.pdbg + static_cast<size_t>(env) * kDebugFloats : nullptr;   // test hook: stage dumps of the first update
+
+    // configuration / velocity dependent registers
+    M3 R;               // parent->link axes
+    M3 Rwl;             // world->link axes
+    V3 Pw;              // joint pivot, world
+    S6 vel;             // link spatial velocity at the pivot, link axes
+    float tau0 = 0.f, tau1 = 0.f, tau2 = 0.f;   // joint torques of the current update (body-frame components / revolute scalar)
+    bool in_contact_tol = false;
+
+    bool need_kin = true, pending_flags = false;
+    const int stages_per_upd = sim_substeps + 1;
+    const int total_stages = n_updates * stages_per_upd;
+    const int sync_period = sync_mode > 0 ? 1 : (sync_mode == 0 ? stages_per_upd : (sync_mode <= -1000 ? 0 : -sync_mode * stages_per_upd));
+#pragma unroll 1
+    for (int stage = 0; stage <= total_stages; ++stage) {
+        // =================================================================== forward kinematics + link velocities (root -> leaves)
+        if (need_kin) {
+            need_kin = false;
+            const Q4 zrot = mkq(L.zrot[0], L.zrot[1], L.zrot[2], L.zrot[3]);
+            Q4 cached;
+            if (jtype == kJSpherical) cached = qmul(mkq(jp.x, jp.y, jp.z, -jp.w), zrot);
+            else if (jtype == kJRevolute) {
+                float s, c;
+                __sincosf(-0.5f * jp.x, &s, &c);   // |angle| <= pi/2 + limit overshoot: fast path is accurate to ~1 ulp of the result scale
+                cached = qmul(mkq(axis.x * s, axis.y * s, axis.z * s, c), zrot);
+            } else cached = zrot;
+            R = qmat(cached);
+            const M3 Rwb = qmat(baseQuat);
+            V3 jw = mk3(0, 0, 0);
+            if (jtype == kJSpherical) jw = mk3(jv.x, jv.y, jv.z); else if (jtype == kJRevolute) jw = jv.x * axis;
+            if (lane == 0) {
+                Rwl = mul(R, Rwb); Pw = basePos + mulT(Rwb, cvec);
+                vel = xm(R, cvec, mks(mul(Rwb, baseOmega), mul(Rwb, baseVel)));
+                vel.a += jw;
+            }
+#pragma unroll 1
+            for (int lv = 1; lv <= maxlevel; ++lv) {
+                M3 pR; V3 pp; S6 pv;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) pR.m[k] = T::shfl(Rwl.m[k], plane);
+                pp = T::shfl3(Pw, plane);
+                pv = T::shfl6(vel, plane);
+                if (level == lv) { Rwl = mul(R, pR); Pw = pp + mulT(pR, cvec); vel = xm(R, cvec, pv); vel.a += jw; }
+            }
+            if (act) {
+                float* r = sR + lane * 12; float* w = sW + lane * 12;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { r[k] = R.m[k]; w[k] = Rwl.m[k]; }
+                w[9] = Pw.x; w[10] = Pw.y; w[11] = Pw.z;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) sG[21 + k] = Rwb.m[k];
+            }
+            __syncwarp();
+        }
+        // =================================================================== post-update flags of the update that just finished
+        if (pending_flags) {
+            pending_flags = false;
+            need_action = 0;
+            {   // cMathUtil::CheckNextInterval(dt, ctrl_time + init_time_offset, 1/30)
+                const double cur = ctrl_time + init_off, pad = 0.001 * dt, T_ = M.query_dt;
+                int c0 = static_cast<int>(floor((cur + pad) / T_)), c1 = static_cast<int>(floor((cur + pad - dt) / T_));
+                need_action = (c0 != c1) ? 1 : 0;
+            }
+            // fall: any fall-contact link with a manifold point at distance <= 0.001*scale (state of the last sub-step's collision pass)
+            const unsigned fb = __ballot_sync(0xffffffffu, act && L.fall_contact && in_contact_tol);
+            const unsigned fseg = (W == 32) ? fb : ((fb >> (threadIdx.x & 16)) & 0xffffu);
+            const int fallen = (fseg != 0 && M.enable_contact_fall) ? 1 : 0;
+            // exploded velocities: any link |v|, |w| component > 100 in world axes (cSimCharacter::HasVelExploded); v at the COM
+            V3 vw = mulT(Rwl, vel.l + cross(vel.a, dvec)) * (1.0f / M.scale), ww = mulT(Rwl, vel.a);
+            float mx = fmaxf(fmaxf(fmaxf(fabsf(vw.x), fabsf(vw.y)), fabsf(vw.z)), fmaxf(fmaxf(fabsf(ww.x), fabsf(ww.y)), fabsf(ww.z)));
+            const unsigned eb = __ballot_sync(0xffffffffu, act && mx > 100.f);
+            const unsigned eseg = (W == 32) ? eb : ((eb >> (threadIdx.x & 16)) & 0xffffu);
+            if (alive) {
+                int term = (M.enable_fall_end && fallen) ? 1 : 0;
+                if (!term && !M.loop_motion && kin_time >= M.motion_dur) term = 1;
+                f_updates++;
+                const bool end = (timer >= timer_max) || term;
+                if (end || stage == total_stages) {   // commit
+                    if (lane == 0) {
+                        reinterpret_cast<float4*>(sim)[0] = make_float4(basePos.x, basePos.y, basePos.z, 0.f);
+                        reinterpret_cast<float4*>(sim)[1] = make_float4(baseQuat.x, baseQuat.y, baseQuat.z, baseQuat.w);
+                        reinterpret_cast<float4*>(sim)[2] = make_float4(baseOmega.x, baseOmega.y, baseOmega.z, 0.f);
+                        reinterpret_cast<float4*>(sim)[3] = make_float4(baseVel.x, baseVel.y, baseVel.z, 0.f);
+                        tm[kTKin] = kin_time; tm[kTCtrl] = ctrl_time; tm[kTPrevAct] = prev_act; tm[kTTimer] = timer;
+                        tm[kTOrigin] = org_x; tm[kTOrigin + 1] = org_y; tm[kTOrigin + 2] = org_z;
+                        fl[kFNeedAction] = need_action; fl[kFDone] = end ? 1 : 0; fl[kFTerminate] = term; fl[kFValid] = (eseg == 0) ? 1 : 0; fl[kFFallen] = fallen;
+                        fl[kFRowOverflow] = f_over; fl[kFUpdates] = f_updates;
+                    }
+                    if (act) {
+                        reinterpret_cast<float4*>(sim + 16)[lane] = jp;
+                        reinterpret_cast<float4*>(sim + 16 + 4 * nl)[lane] = jv;
+                    }
+                }
+                if (end) alive = false;
+            }
+        }
+        if (stage == total_stages) break;
+        if (sync_period != 0 && (stage % sync_period) == 0) { if (__syncthreads_and(!alive)) break; }
+        const int ph = stage % stages_per_upd;      // 0: Stable-PD stage, 1..sim_substeps: Bullet sub-steps
+        const bool first_upd = stage < stages_per_upd;
+        int P = 0;
+        float mp[48];
+        if (ph == 0) {
+            // ---------------- clocks: cScene::Update, cSceneImitate::UpdateKinChar, cDeepMimicCharController::UpdateCalcTau
+            timer += dt;
+            const double dur = M.motion_dur;
+            double p0 = kin_time / dur; p0 -= floor(p0);
+            kin_time += dt;
+            double p1 = kin_time / dur; p1 -= floor(p1);
+            if (M.loop_motion && p1 < p0 && M.sync_root_pos) {
+                // SyncKinCharNewCycle: snap the clip's root x,z (at the new time) onto the simulated root
+                int cyc = static_cast<int>(floor(kin_time / dur));
+                double tt = kin_time - cyc * dur;
+                int lo = 0, hi = M.num_frames - 1;   // upper_bound - 1
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (frame_times[mid] <= tt) lo = mid; else hi = mid; }
+                double bl = (tt - frame_times[lo]) / (frame_times[lo + 1] - frame_times[lo]);
+                bl = fmin(fmax(bl, 0.0), 1.0);
+                const float* f0 = frames + static_cast<size_t>(lo) * M.pose_dim; const float* f1 = f0 + M.pose_dim;
+                double rx = (1 - bl) * f0[0] + bl * f1[0] + cyc * static_cast<double>(M.cycle_delta[0]);
+                double rz = (1 - bl) * f0[2] + bl * f1[2] + cyc * static_cast<double>(M.cycle_delta[2]);
+                double qw = tm[kTOriginRot], qx = tm[kTOriginRot + 1], qy = tm[kTOriginRot + 2], qz = tm[kTOriginRot + 3];
+                double ry_ = (1 - bl) * f0[1] + bl * f1[1];
+                double ux = qy * rz - qz * ry_, uy = qz * rx - qx * rz, uz = qx * ry_ - qy * rx;
+                ux *= 2; uy *= 2; uz *= 2;
+                double kx = rx + qw * ux + (qy * uz - qz * uy);
+                double kz = rz + qw * uz + (qx * uy - qy * ux);
+                double sx = static_cast<double>(basePos.x) / M.scale, sz = static_cast<double>(basePos.z) / M.scale;
+                org_x += sx - (kx + org_x);
+                org_z += sz - (kz + org_z);
+                org_y = 0.0;   // kin_root.y := ground_h + (kin_root.y - origin.y)  =>  origin.y returns to 0
+            }
+            ctrl_time += dt;
+            if (need_action) { prev_act = ctrl_time; need_action = 0; }
+        } else {
+            // ---------------- collision: link convex vs plane y = 0, persistent manifold of <= 4 points per link (btPersistentManifold)
+            int cnt = 0;
+            {
+                const float4* mg = reinterpret_cast<const float4*>(mani + li * kManifoldFloats);
+#pragma unroll
+                for (int k = 0; k < 12; ++k) { float4 v = mg[k]; mp[4 * k] = v.x; mp[4 * k + 1] = v.y; mp[4 * k + 2] = v.z; mp[4 * k + 3] = v.w; }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (mp[c * 12] != 0.f && cnt == c) cnt = c + 1;
+            const float thr = L.break_thr;
+            const V3 pos = Pw + mulT(Rwl, dvec);     // COM, world (Bullet's link collider frame)
+            V3 dl = mul(Rwl, mk3(0.f, -1.f, 0.f));   // support direction -n in link coordinates
+            V3 vtx;
+            if (L.shape == kSBox) vtx = mk3(dl.x >= 0 ? L.he[0] : -L.he[0], dl.y >= 0 ? L.he[1] : -L.he[1], dl.z >= 0 ? L.he[2] : -L.he[2]);
+            else {
+                V3 sup = mk3(0, 0, 0);
+                if (L.shape == kSCapsule) sup = mk3(0.f, (dl.y >= 0.f) ? L.he[1] : -L.he[1], 0.f);   // first end point wins ties
+                float inv = rsqrtf(dot(dl, dl));
+                vtx = sup + (L.he[0] * inv) * dl;
+            }
+            const V3 vw = pos + mulT(Rwl, vtx);
+            const float dist = vw.y;
+            if (act && dist < thr) {
+                float best = thr * thr; int nearest = -1;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (c < cnt) {
+                    float dx = mp[c * 12 + 1] - vtx.x, dy = mp[c * 12 + 2] - vtx.y, dz = mp[c * 12 + 3] - vtx.z, dd = dx * dx + dy * dy + dz * dz;
+                    if (dd < best) { best = dd; nearest = c; }
+                }
+                int idx = nearest;
+                float k7 = 0, k8 = 0, k9 = 0, k11 = 0;
+                if (nearest >= 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) if (c == nearest) { k7 = mp[c * 12 + 7]; k8 = mp[c * 12 + 8]; k9 = mp[c * 12 + 9]; k11 = mp[c * 12 + 11]; }
+                } else if (cnt < 4) { idx = cnt; cnt++; }
+                else {   // btPersistentManifold::sortCachedPoints
+                    int mpi = -1; float mpen = dist;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) if (mp[c * 12 + 10] < mpen) { mpi = c; mpen = mp[c * 12 + 10]; }
+                    auto Pt = [&](int c) { return mk3(mp[c * 12 + 1], mp[c * 12 + 2], mp[c * 12 + 3]); };
+                    auto area = [&](V3 a, V3 b) { V3 c = cross(a, b); return dot(c, c); };
+                    float res[4] = {0, 0, 0, 0};
+                    if (mpi != 0) res[0] = area(vtx - Pt(1), Pt(3) - Pt(2));
+                    if (mpi != 1) res[1] = area(vtx - Pt(0), Pt(3) - Pt(2));
+                    if (mpi != 2) res[2] = area(vtx - Pt(0), Pt(3) - Pt(1));
+                    if (mpi != 3) res[3] = area(vtx - Pt(0), Pt(2) - Pt(1));
+                    idx = 0; float bv = fabsf(res[0]);
+#pragma unroll
+                    for (int c = 1; c < 4; ++c) if (fabsf(res[c]) > bv) { bv = fabsf(res[c]); idx = c; }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (c == idx) {
+                    float* q = mp + c * 12;
+                    q[0] = 1.f; q[1] = vtx.x; q[2] = vtx.y; q[3] = vtx.z; q[4] = vw.x; q[5] = 0.f; q[6] = vw.z; q[7] = k7; q[8] = k8; q[9] = k9; q[10] = dist; q[11] = k11;
+                }
+            }
+            // refreshContactPoints
+#pragma unroll
+            for (int c = 3; c >= 0; --c) if (c < cnt) {
+                V3 pa = pos + mulT(Rwl, mk3(mp[c * 12 + 1], mp[c * 12 + 2], mp[c * 12 + 3]));
+                mp[c * 12 + 10] = pa.y - mp[c * 12 + 5];
+                mp[c * 12 + 11] += 1.f;
+            }
+#pragma unroll
+            for (int c = 3; c >= 0; --c) if (c < cnt) {
+                V3 pa = pos + mulT(Rwl, mk3(mp[c * 12 + 1], mp[c * 12 + 2], mp[c * 12 + 3]));
+                bool rm = !(mp[c * 12 + 10] <= thr);
+                if (!rm) {
+                    float dx = mp[c * 12 + 4] - pa.x, dy = mp[c * 12 + 5] - (pa.y - mp[c * 12 + 10]), dz = mp[c * 12 + 6] - pa.z;
+                    rm = (dx * dx + dy * dy + dz * dz) > thr * thr;
+                }
+                if (rm) {
+                    const int last = cnt - 1;
+#pragma unroll
+                    for (int l2 = 0; l2 < 4; ++l2) if (l2 == last) {
+                        if (c != l2) for (int k = 0; k < 12; ++k) mp[c * 12 + k] = mp[l2 * 12 + k];
+                        mp[l2 * 12] = 0.f;
+                    }
+                    cnt--;
+                }
+            }
+            if (!act) cnt = 0;
+            in_contact_tol = false;   // cContactManager::Update: distance <= 0.001 * scale
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (c < cnt && mp[c * 12 + 10] <= 0.001f * M.scale) in_contact_tol = true;
+            // exclusive prefix over lanes -> point indices; publish points to the solver
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < W; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o, W); if (lane >= o) incl += t; }
+            const int base = incl - cnt;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (c < cnt) {
+                const int p = base + c;
+                if (p < LY.maxpts) {
+                    V3 pa = pos + mulT(Rwl, mk3(mp[c * 12 + 1], mp[c * 12 + 2], mp[c * 12 + 3]));
+                    sPp[p * 4] = pa.x; sPp[p * 4 + 1] = pa.y; sPp[p * 4 + 2] = pa.z; sPp[p * 4 + 3] = mp[c * 12 + 10];
+                    sPi[p] = mp[c * 12 + 7];
+                    sPr[p] = lane * 4 + c;
+                } else f_over = 1;
+            }
+            P = min(T::shfli(incl, W - 1), LY.maxpts);
+        }
+
+        // =================================================================== bias accelerations (root -> leaves), Stable-PD right-hand side
+        const bool bullet = ph != 0;
+        const M3 Rwb = qmat(baseQuat);
+        V3 jw = mk3(0, 0, 0);
+        if (jtype == kJSpherical) jw = mk3(jv.x, jv.y, jv.z); else if (jtype == kJRevolute) jw = jv.x * axis;
+        S6 ab;
+        {
+            const S6 vb = mks(mul(Rwb, baseOmega), mul(Rwb, baseVel));
+            const V3 w_used = bullet ? vb.a : baseOmega;   // cRBDUtil::BuildCjRoot differentiates the root quaternion with the body-frame formula
+                                                           // applied to the world-frame angular velocity (RBDUtil.cpp:915-958): reproduced in the SPD stage
+            const S6 abB = mks(mk3(0, 0, 0), mul(Rwb, -grav) - cross(w_used, vb.l));
+            const S6 cj = mks(cross(vel.a, jw), cross(vel.l, jw));
+            if (lane == 0) ab = xm(R, cvec, abB) + cj;
+#pragma unroll 1
+            for (int lv = 1; lv <= maxlevel; ++lv) {
+                S6 pa = T::shfl6(ab, plane);
+                if (level == lv) ab = xm(R, cvec, pa) + cj;
+            }
+        }
+        float pe0 = 0.f, pe1 = 0.f, pe2 = 0.f, kdt = 0.f, kd = 0.f;
+        float g0 = tau0, g1 = tau1, g2 = tau2;   // generalised joint force of this stage
+        if (!bullet) {
+            // cImpPDController::CalcControlForces (ImpPDController.cpp:136-195) in the body-frame joint coordinates of the sim state
+            const float4 tg = reinterpret_cast<const float4*>(sim + 16 + 8 * nl)[li];
+            float e0 = 0, e1 = 0, e2 = 0;
+            if (jtype == kJSpherical) {
+                Q4 q = mkq(jp.x, jp.y, jp.z, jp.w);
+                // pose_inc = normalize(q + dt * 0.5 * q (x) (0, w))      (cKinTree::VelToPoseDiff, KinTree.cpp:1581-1610)
+                Q4 dq = qmul(q, mkq(jv.x, jv.y, jv.z, 0.f));
+                Q4 qi = qnormalize(mkq(q.x + 0.5f * fdt * dq.x, q.y + 0.5f * fdt * dq.y, q.z + 0.5f * fdt * dq.z, q.w + 0.5f * fdt * dq.w));
+                V3 e = quat_rotvec3(qmul(qconj(qi), mkq(tg.x, tg.y, tg.z, tg.w)));   // cKinTree::CalcVel(dt = 1) -> CalcQuaternionVelRel
+                e0 = e.x; e1 = e.y; e2 = e.z;
+            } else if (jtype == kJRevolute) {
+                e0 = tg.x - (normalize_angle3(jp.x) + fdt * jv.x);
+            }
+            const float kp = L.kp; kd = L.kd;
+            pe0 = kp * e0; pe1 = kp * e1; pe2 = kp * e2;
+            kdt = fdt * kd;
+            g0 = pe0 - kd * jv.x; g1 = pe1 - kd * jv.y; g2 = pe2 - kd * jv.z;
+        }
+
+        // =================================================================== articulated-body pass (leaves -> root)
+        // pA: bias force of the subtree with zero joint accelerations (recursive Newton-Euler force, gravity as base acceleration);
+        // IA: articulated inertia.  Eliminating dof d of a joint (deepest first) is one step of the tree-structured L^T D L.
+        Art IA; S6 pA;
+        S6 U0, U1, U2; float inv0 = 0.f, inv1 = 0.f, inv2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;
+        {
+            const float* wsel = LK + li * kLkFloats + (bullet ? kLWb : kLWd);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) IA.ww[k] = act ? wsel[k] : 0.f;
+            const V3 md = mass * dvec;
+            IA.wv[0] = 0.f; IA.wv[1] = -md.z; IA.wv[2] = md.y; IA.wv[3] = md.z; IA.wv[4] = 0.f; IA.wv[5] = -md.x; IA.wv[6] = -md.y; IA.wv[7] = md.x; IA.wv[8] = 0.f;
+            IA.vv[0] = mass; IA.vv[1] = 0.f; IA.vv[2] = 0.f; IA.vv[3] = mass; IA.vv[4] = 0.f; IA.vv[5] = mass;
+            // h = I v ; pA = I ab + v x* h
+            const V3 hn = sym_mul(IA.ww, vel.a) + cross(md, vel.l), hf = mass * vel.l + cross(vel.a, md);
+            const V3 an = sym_mul(IA.ww, ab.a) + cross(md, ab.l), af = mass * ab.l + cross(ab.a, md);
+            pA = mks(an + cross(vel.a, hn) + cross(vel.l, hf), af + cross(vel.a, hf));
+            U0 = U1 = U2 = mks(mk3(0, 0, 0), mk3(0, 0, 0));
+        }
+        auto eliminate = [&](int d, float g, S6& Uo, float& invo, float& uo) {
+            const V3 dir = dir_of(d);
+            const V3 Ua = sym_mul(IA.ww, dir), Ul = wvT_mul(IA.wv, dir);
+            const float D = dot(dir, Ua) + kdt;
+            const float inv = 1.0f / D;
+            const float u = g - dot(dir, pA.a);
+            const V3 sa = inv * Ua, sl = inv * Ul;
+            IA.ww[0] -= sa.x * Ua.x; IA.ww[1] -= sa.x * Ua.y; IA.ww[2] -= sa.x * Ua.z; IA.ww[3] -= sa.y * Ua.y; IA.ww[4] -= sa.y * Ua.z; IA.ww[5] -= sa.z * Ua.z;
+            IA.wv[0] -= sa.x * Ul.x; IA.wv[1] -= sa.x * Ul.y; IA.wv[2] -= sa.x * Ul.z; IA.wv[3] -= sa.y * Ul.x; IA.wv[4] -= sa.y * Ul.y; IA.wv[5] -= sa.y * Ul.z;
+            IA.wv[6] -= sa.z * Ul.x; IA.wv[7] -= sa.z * Ul.y; IA.wv[8] -= sa.z * Ul.z;
+            IA.vv[0] -= sl.x * Ul.x; IA.vv[1] -= sl.x * Ul.y; IA.vv[2] -= sl.x * Ul.z; IA.vv[3] -= sl.y * Ul.y; IA.vv[4] -= sl.y * Ul.z; IA.vv[5] -= sl.z * Ul.z;
+            pA.a += u * sa; pA.l += u * sl;
+            Uo = mks(Ua, Ul); invo = inv; uo = u;
+        };
+#pragma unroll 1
+        for (int lv = maxlevel; lv >= 0; --lv) {
+            if (level == lv) {
+                if (ndof == 3) { eliminate(2, g2, U2, inv2, u2); eliminate(1, g1, U1, inv1, u1); }
+                if (ndof >= 1) eliminate(0, g0, U0, inv0, u0);
+            }
+            if (lv == 0) break;
+            // express (IA, pA) of the lanes at this level in their parents' pivot frames
+            Art sd;
+            rot_sym(R, IA.ww, sd.ww); rot_gen(R, IA.wv, sd.wv); rot_sym(R, IA.vv, sd.vv);
+            const S6 sf = xf(R, cvec, pA);
+            {
+                // shift by c:  B' = B + C V ; A' = A - B C + C B'^T   (C = [c]x)
+                const V3 c = cvec;
+                const V3 v0 = mk3(sd.vv[0], sd.vv[1], sd.vv[2]), v1 = mk3(sd.vv[1], sd.vv[3], sd.vv[4]), v2 = mk3(sd.vv[2], sd.vv[4], sd.vv[5]);   // columns (= rows) of V
+                const V3 b0 = mk3(sd.wv[0], sd.wv[1], sd.wv[2]), b1 = mk3(sd.wv[3], sd.wv[4], sd.wv[5]), b2 = mk3(sd.wv[6], sd.wv[7], sd.wv[8]);   // rows of B
+                const V3 k0 = cross(c, v0), k1 = cross(c, v1), k2 = cross(c, v2);   // columns of C V
+                const V3 n0 = mk3(b0.x + k0.x, b0.y + k1.x, b0.z + k2.x), n1 = mk3(b1.x + k0.y, b1.y + k1.y, b1.z + k2.y), n2 = mk3(b2.x + k0.z, b2.y + k1.z, b2.z + k2.z);   // rows of B'
+                const V3 p0 = cross(b0, c), p1 = cross(b1, c), p2 = cross(b2, c);   // rows of B C
+                const V3 q0 = cross(c, n0), q1 = cross(c, n1), q2 = cross(c, n2);   // columns of C B'^T
+                sd.ww[0] += -p0.x + q0.x; sd.ww[1] += -p0.y + q1.x; sd.ww[2] += -p0.z + q2.x;
+                sd.ww[3] += -p1.y + q1.y; sd.ww[4] += -p1.z + q2.y; sd.ww[5] += -p2.z + q2.z;
+                sd.wv[0] = n0.x; sd.wv[1] = n0.y; sd.wv[2] = n0.z; sd.wv[3] = n1.x; sd.wv[4] = n1.y; sd.wv[5] = n1.z; sd.wv[6] = n2.x; sd.wv[7] = n2.y; sd.wv[8] = n2.z;
+            }
+            const int nslot = LVC[lv - 1];
+#pragma unroll 1
+            for (int c = 0; c < nslot; ++c) {
+                const int cl = (c < nchild) ? ((child_pack >> (8 * c)) & 0xff) : -1;
+                const int src = cl >= 0 ? cl : lane;
+                const bool take = cl >= 0 && level == lv - 1;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { float g = T::shfl(sd.ww[k], src); if (take) IA.ww[k] += g; }
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { float g = T::shfl(sd.wv[k], src); if (take) IA.wv[k] += g; }
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { float g = T::shfl(sd.vv[k], src); if (take) IA.vv[k] += g; }
+                const S6 gf = T::shfl6(sf, src);
+                if (take) { pA.a += gf.a; pA.l += gf.l; }
+            }
+        }
+        // ---- base: the (massless) floating base carries the root link's articulated inertia; Cholesky of the 6x6 in the base frame
+        S6 aB = mks(mk3(0, 0, 0), mk3(0, 0, 0));   // base spatial acceleration (deviation from the bias acceleration), base frame
+        if (lane == 0) {
+            Art sd;
+            rot_sym(R, IA.ww, sd.ww); rot_gen(R, IA.wv, sd.wv); rot_sym(R, IA.vv, sd.vv);
+            const S6 sf = xf(R, cvec, pA);
+            const V3 c = cvec;
+            const V3 v0 = mk3(sd.vv[0], sd.vv[1], sd.vv[2]), v1 = mk3(sd.vv[1], sd.vv[3], sd.vv[4]), v2 = mk3(sd.vv[2], sd.vv[4], sd.vv[5]);
+            const V3 b0 = mk3(sd.wv[0], sd.wv[1], sd.wv[2]), b1 = mk3(sd.wv[3], sd.wv[4], sd.wv[5]), b2 = mk3(sd.wv[6], sd.wv[7], sd.wv[8]);
+            const V3 k0 = cross(c, v0), k1 = cross(c, v1), k2 = cross(c, v2);
+            const V3 n0 = mk3(b0.x + k0.x, b0.y + k1.x, b0.z + k2.x), n1 = mk3(b1.x + k0.y, b1.y + k1.y, b1.z + k2.y), n2 = mk3(b2.x + k0.z, b2.y + k1.z, b2.z + k2.z);
+            const V3 p0 = cross(b0, c), p1 = cross(b1, c), p2 = cross(b2, c);
+            const V3 q0 = cross(c, n0), q1 = cross(c, n1), q2 = cross(c, n2);
+            // 6x6 symmetric matrix, coordinates [w(3); v(3)], lower triangle a[i][j], j <= i
+            float a[6][6];
+            a[0][0] = sd.ww[0] - p0.x + q0.x;
+            a[1][0] = sd.ww[1] - p0.y + q1.x; a[1][1] = sd.ww[3] - p1.y + q1.y;
+            a[2][0] = sd.ww[2] - p0.z + q2.x; a[2][1] = sd.ww[4] - p1.z + q2.y; a[2][2] = sd.ww[5] - p2.z + q2.z;
+            a[3][0] = n0.x; a[3][1] = n1.x; a[3][2] = n2.x; a[4][0] = n0.y; a[4][1] = n1.y; a[4][2] = n2.y; a[5][0] = n0.z; a[5][1] = n1.z; a[5][2] = n2.z;   // B'^T
+            a[3][3] = sd.vv[0]; a[4][3] = sd.vv[1]; a[4][4] = sd.vv[3]; a[5][3] = sd.vv[2]; a[5][4] = sd.vv[4]; a[5][5] = sd.vv[5];
+            float gi[6];   // 1 / G_ii
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                float d = a[j][j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) d -= a[j][k] * a[j][k];
+                gi[j] = rsqrtf(d);
+                a[j][j] = d * gi[j];
+#pragma unroll
+                for (int i = j + 1; i < 6; ++i) {
+                    float s = a[i][j];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) s -= a[i][k] * a[j][k];
+                    a[i][j] = s * gi[j];
+                }
+            }
+            // x = -(G G^T)^-1 p
+            float x[6] = {-sf.a.x, -sf.a.y, -sf.a.z, -sf.l.x, -sf.l.y, -sf.l.z};
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                for (int k = 0; k < i; ++k) x[i] -= a[i][k] * x[k];
+                x[i] *= gi[i];
+            }
+#pragma unroll
+            for (int i = 5; i >= 0; --i) {
+#pragma unroll
+                for (int k = i + 1; k < 6; ++k) x[i] -= a[k][i] * x[k];
+                x[i] *= gi[i];
+            }
+            aB = mks(mk3(x[0], x[1], x[2]), mk3(x[3], x[4], x[5]));
+            if (bullet) {   // factor kept for the constraint rows: strict lower part (15) + reciprocal diagonal (6)
+                int o = 0;
+#pragma unroll
+                for (int i = 1; i < 6; ++i)
+#pragma unroll
+                    for (int k = 0; k < i; ++k) sG[o++] = a[i][k];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) sG[15 + i] = gi[i];
+            }
+        }
+        // ---- accelerations (root -> leaves): qdd_d = (u_d - U_d . a') / D_d
+        float qd0 = 0.f, qd1 = 0.f, qd2 = 0.f;
+        S6 al = mks(mk3(0, 0, 0), mk3(0, 0, 0));   // link acceleration deviation
+        auto descend = [&](S6 a, float n0, float n1, float n2) {
+            // n_d: numerator already divided by D_d
+            if (ndof >= 1) { qd0 = n0 - inv0 * sdot(a, U0); a.a += qd0 * dir_of(0); }
+            if (ndof == 3) { qd1 = n1 - inv1 * sdot(a, U1); a.a += qd1 * dir_of(1); qd2 = n2 - inv2 * sdot(a, U2); a.a += qd2 * dir_of(2); }
+            return a;
+        };
+        if (lane == 0) al = descend(xm(R, cvec, aB), u0 * inv0, u1 * inv1, u2 * inv2);
+#pragma unroll 1
+        for (int lv = 1; lv <= maxlevel; ++lv) {
+            S6 pa = T::shfl6(al, plane);
+            if (level == lv) al = descend(xm(R, cvec, pa), u0 * inv0, u1 * inv1, u2 * inv2);
+        }
+
+        if (!bullet) {
+            // ---------------- torques: tau = Kp e + Kd (edot - dt a), clamped by norm (cSimBodyJoint::ClampTotalTorque, SimBodyJoint.cpp:299-307)
+            float t0 = 0, t1 = 0, t2 = 0;
+            if (ndof >= 1) t0 = pe0 + kd * (-jv.x - fdt * qd0);
+            if (ndof == 3) { t1 = pe1 + kd * (-jv.y - fdt * qd1); t2 = pe2 + kd * (-jv.z - fdt * qd2); }
+            const float mag = sqrtf(t0 * t0 + t1 * t1 + t2 * t2);
+            if (mag > L.tlim) { float s = L.tlim / mag; t0 *= s; t1 *= s; t2 *= s; }
+            tau0 = t0; tau1 = t1; tau2 = t2;
+            if (DEBUG && dbg && first_upd) {
+                if (ndof >= 1) { dbg[2 * kMaxDofs + dof0] = t0; dbg[3 * kMaxDofs + dof0] = qd0; }
+                if (ndof == 3) { dbg[2 * kMaxDofs + dof0 + 1] = t1; dbg[2 * kMaxDofs + dof0 + 2] = t2; dbg[3 * kMaxDofs + dof0 + 1] = qd1; dbg[3 * kMaxDofs + dof0 + 2] = qd2; }
+                if (lane == 0) for (int k = 0; k < 6; ++k) dbg[2 * kMaxDofs + k] = 0.f;
+            }
+            continue;
+        }
+
+        // =================================================================== Bullet sub-step: v += a h, constraint rows, PGS, integration
+        const int sub = ph - 1;
+        {
+            // base acceleration in the world-aligned generalised coordinates [omega_w, v_w]
+            V3 dw = mulT(Rwb, mk3(T::shfl(aB.a.x, 0), T::shfl(aB.a.y, 0), T::shfl(aB.a.z, 0)));
+            V3 dv = mulT(Rwb, mk3(T::shfl(aB.l.x, 0), T::shfl(aB.l.y, 0), T::shfl(aB.l.z, 0)));
+            if (DEBUG && dbg && first_upd) {
+                const int o = (sub == 0 ? 4 * kMaxDofs : 8 * kMaxDofs + 1024);
+                if (lane == 0) { dbg[o] = dw.x; dbg[o + 1] = dw.y; dbg[o + 2] = dw.z; dbg[o + 3] = dv.x; dbg[o + 4] = dv.y; dbg[o + 5] = dv.z; }
+                if (ndof >= 1) dbg[o + dof0] = qd0;
+                if (ndof == 3) { dbg[o + dof0 + 1] = qd1; dbg[o + dof0 + 2] = qd2; }
+            }
+            auto cl = [](float v) { return fminf(fmaxf(v, -100.f), 100.f); };   // applyDeltaVeeMultiDof clamp
+            baseOmega = mk3(cl(baseOmega.x + h * dw.x), cl(baseOmega.y + h * dw.y), cl(baseOmega.z + h * dw.z));
+            baseVel = mk3(cl(baseVel.x + h * dv.x), cl(baseVel.y + h * dv.y), cl(baseVel.z + h * dv.z));
+            if (ndof >= 1) jv.x = cl(jv.x + h * qd0);
+            if (ndof == 3) { jv.y = cl(jv.y + h * qd1); jv.z = cl(jv.z + h * qd2); }
+            vel = vel + h * al;   // link velocities are linear in the generalised velocities (the clamp only acts on exploding states)
+            if (DEBUG && dbg && first_upd) {
+                const int o = (sub == 0 ? 5 * kMaxDofs : 9 * kMaxDofs + 1024);
+                if (lane == 0) { dbg[o] = baseOmega.x; dbg[o + 1] = baseOmega.y; dbg[o + 2] = baseOmega.z; dbg[o + 3] = baseVel.x; dbg[o + 4] = baseVel.y; dbg[o + 5] = baseVel.z; dbg[(sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024)] = static_cast<float>(P); }
+                if (ndof >= 1) dbg[o + dof0] = jv.x;
+                if (ndof == 3) { dbg[o + dof0 + 1] = jv.y; dbg[o + dof0 + 2] = jv.z; }
+            }
+        }
+        // publish the per-link factors and velocities for the row builders
+        if (act) {
+            float* u = sU + lane * 24;
+            u[0] = U0.a.x; u[1] = U0.a.y; u[2] = U0.a.z; u[3] = U0.l.x; u[4] = U0.l.y; u[5] = U0.l.z;
+            u[6] = U1.a.x; u[7] = U1.a.y; u[8] = U1.a.z; u[9] = U1.l.x; u[10] = U1.l.y; u[11] = U1.l.z;
+            u[12] = U2.a.x; u[13] = U2.a.y; u[14] = U2.a.z; u[15] = U2.l.x; u[16] = U2.l.y; u[17] = U2.l.z;
+            u[18] = inv0; u[19] = inv1; u[20] = inv2; u[21] = sqrtf(inv0); u[22] = sqrtf(inv1); u[23] = sqrtf(inv2);
+            float* v = sV + lane * 8;
+            v[0] = vel.a.x; v[1] = vel.a.y; v[2] = vel.a.z; v[3] = vel.l.x; v[4] = vel.l.y; v[5] = vel.l.z;
+        }
+        // ---- joint-limit rows (btMultiBodyJointLimitConstraint): a lane owns at most one active row
+        int lim_dir = 0; float lim_pen = 0.f;
+        if (act && L.has_limit) {
+            float p0 = jp.x - L.lim_lo, p1 = L.lim_hi - jp.x;
+            if (!(p0 > 0.f)) { lim_dir = 1; lim_pen = p0; }
+            else if (!(p1 > 0.f)) { lim_dir = -1; lim_pen = p1; }
+        }
+        int linc = lim_dir != 0 ? 1 : 0;
+#pragma unroll
+        for (int o = 1; o < W; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, linc, o, W); if (lane >= o) linc += t; }
+        int NL = T::shfli(linc, W - 1);
+        if (NL > 8) { NL = 8; f_over = 1; }
+        if (lim_dir != 0 && linc - 1 < 8) { sQ[linc - 1] = __int_as_float(lane); sQ[8 + linc - 1] = (lim_dir == -1) ? -1.f : 1.f; sQ[16 + linc - 1] = lim_pen; sQ[24 + linc - 1] = jv.x; }
+        if (NL + 3 * P > MR) { P = (MR - NL) / 3; f_over = 1; }
+        const int NR = NL + 3 * P;
+        const int NRmax = (W == 32) ? NR : wmax(NR);
+        __syncwarp();
+        // row ids in solver order: limits [0,NL) | normals [NL, NL+P) | friction pairs NL+P+2p+{0,1} (t1 = -x, t2 = +z)
+        constexpr int kSlots = (W == 16) ? 3 : 2;
+        float r_rhs[kSlots], r_inv[kSlots], r_lam[kSlots], r_w[kSlots];
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+            r_rhs[s] = 0.f; r_inv[s] = 0.f; r_lam[s] = 0.f; r_w[s] = 0.f;
+            const int rid = lane + s * W;
+            if (s * W < NRmax) {
+                const bool rv_ = rid < NR;
+                int b = 0, kind = 0 /*0 limit 1 normal 2 t1 3 t2*/, p = 0;
+                float lsign = 1.f, lpen = 0.f;
+                if (rv_) {
+                    if (rid < NL) { b = __float_as_int(sQ[rid]); lsign = sQ[8 + rid]; lpen = sQ[16 + rid]; }
+                    else if (rid < NL + P) { kind = 1; p = rid - NL; b = sPr[p] >> 2; }
+                    else { const int f = rid - NL - P; p = f >> 1; kind = 2 + (f & 1); b = sPr[p] >> 2; }
+                    sRl[rid] = b;
+                }
+                // force on link b in its pivot frame
+                S6 f = mks(mk3(0, 0, 0), mk3(0, 0, 0));
+                float rvel = 0.f, pdist = 0.f;
+                if (rv_ && kind != 0) {
+                    const float* w = sW + b * 12;
+                    const V3 pa = mk3(sPp[p * 4], sPp[p * 4 + 1], sPp[p * 4 + 2]);
+                    pdist = sPp[p * 4 + 3];
+                    const V3 dlt = mk3(pa.x - w[9], pa.y - w[10], pa.z - w[11]);
+                    const V3 rel = mk3(w[0] * dlt.x + w[1] * dlt.y + w[2] * dlt.z, w[3] * dlt.x + w[4] * dlt.y + w[5] * dlt.z, w[6] * dlt.x + w[7] * dlt.y + w[8] * dlt.z);
+                    const V3 fl_ = (kind == 1) ? mk3(w[1], w[4], w[7]) : ((kind == 2) ? mk3(-w[0], -w[3], -w[6]) : mk3(w[2], w[5], w[8]));   // Rwl * dir
+                    f = mks(cross(rel, fl_), fl_);
+                    const float* v = sV + b * 8;
+                    const V3 va = mk3(v[0], v[1], v[2]), vl = mk3(v[3], v[4], v[5]);
+                    rvel = dot(fl_, vl + cross(va, rel));
+                }
+                // walk the chain base <- ... <- b
+                float acc = 0.f;
+                int cur = b;
+                bool first = true;
+#pragma unroll 1
+                while (true) {
+                    const int info = lk_i(cur);
+                    const int par = static_cast<int>(static_cast<signed char>(info & 0xff)), jt = (info >> 8) & 0xff, nd = (info >> 16) & 0xff, dp0 = (info >> 24) & 0xff;
+                    const float* u = sU + cur * 24;
+                    const float* lk = LK + cur * kLkFloats;
+#pragma unroll 1
+                    for (int d = nd - 1; d >= 0; --d) {
+                        const V3 dir = (jt == kJSpherical) ? unit3(d) : mk3(lk[kLAx], lk[kLAx + 1], lk[kLAx + 2]);
+                        float t = dot(dir, f.a);
+                        if (first && kind == 0) { t = lsign; rvel = lsign * sQ[24 + rid]; }
+                        const float y = t * u[21 + d];
+                        if (rv_) sY[(dp0 + d) * MR + rid] = y;
+                        acc += y * y;
+                        const float ti = t * u[18 + d];
+                        f.a.x -= ti * u[d * 6]; f.a.y -= ti * u[d * 6 + 1]; f.a.z -= ti * u[d * 6 + 2]; f.l.x -= ti * u[d * 6 + 3]; f.l.y -= ti * u[d * 6 + 4]; f.l.z -= ti * u[d * 6 + 5];
+                    }
+                    first = false;
+                    const float* r = sR + cur * 12;
+                    M3 Rc;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) Rc.m[k] = r[k];
+                    f = xf(Rc, mk3(lk[kLC], lk[kLC + 1], lk[kLC + 2]), f);
+                    if (par < 0) break;
+                    cur = par;
+                }
+                {   // base block: y = G^-1 f
+                    float x[6] = {f.a.x, f.a.y, f.a.z, f.l.x, f.l.y, f.l.z};
+                    int o = 0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                        for (int k = 0; k < i; ++k) x[i] -= sG[o++] * x[k];
+                        x[i] *= sG[15 + i];
+                        if (rv_) sY[i * MR + rid] = x[i];
+                        acc += x[i] * x[i];
+                    }
+                }
+                if (rv_) {
+                    const float inv = acc > 1.1920929e-7f ? 1.0f / acc : 0.f;
+                    float rhs;
+                    if (kind == 1) {   // setupMultiBodyContactConstraint: erp 0.2, restitution 0, no split impulse for multibodies
+                        float perr = 0.f, verr = -rvel;
+                        if (pdist > 0.f) verr -= pdist / h; else perr = -pdist * 0.2f / h;
+                        rhs = perr * inv + verr * inv;
+                        r_lam[s] = sPi[p] * 0.85f;   // SOLVER_USE_WARMSTARTING, warmstartingFactor 0.85
+                    } else if (kind != 0) rhs = -rvel * inv;
+                    else {
+                        float perr = 0.f, verr = -rvel;
+                        const bool combine = lpen > -0.04f;   // split-impulse threshold: deeper violations lose the positional term (btMultiBodyJointLimitConstraint)
+                        if (lpen > 0.f) verr = -lpen / h; else perr = -lpen * 0.2f / h;
+                        rhs = combine ? (perr * inv + verr * inv) : (verr * inv);
+                    }
+                    r_rhs[s] = rhs; r_inv[s] = inv;
+                    sLam[rid] = r_lam[s];
+                }
+            }
+        }
+        __syncwarp();
+        // ---- A = J M^-1 J^T, packed lower triangle (overwrites the world-frame / velocity scratch, no longer needed this sub-step)
+        if (NRmax > 0) {
+            int bj[kSlots], tj[kSlots];
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) { const int rid = lane + s * W; bj[s] = (rid < NR) ? sRl[rid] : 0; tj[s] = rid * (rid + 1) / 2; }
+            __syncwarp();
+#pragma unroll 1
+            for (int i = 0; i < NRmax; ++i) {
+                const bool iv = i < NR;
+                const int bi = iv ? sRl[i] : 0;
+                const unsigned char* cdr = CD + bi * nl;
+                const int ti = i * (i + 1) / 2;
+#pragma unroll
+                for (int s = 0; s < kSlots; ++s) {
+                    const int rid = lane + s * W;
+                    if (s * W <= i) {   // only rows j <= i are stored
+                        const int cd = (iv && rid <= i) ? cdr[bj[s]] : 0;
+                        float acc = 0.f;
+#pragma unroll 1
+                        for (int k = 0; k < cd; ++k) acc += sY[k * MR + i] * sY[k * MR + rid];
+                        if (iv && rid <= i) sA[ti + rid] = acc;
+                    }
+                }
+            }
+            __syncwarp();
+            // warm start: w = A lambda0
+#pragma unroll 1
+            for (int i = NL; i < NL + ((W == 32) ? P : wmax(P)); ++i) {
+                const float l0 = (i < NL + P) ? sLam[i] : 0.f;
+                const int ti = i * (i + 1) / 2;
+#pragma unroll
+                for (int s = 0; s < kSlots; ++s) {
+                    const int rid = lane + s * W;
+                    if (s * W < NRmax && rid < NR && l0 != 0.f) r_w[s] += sA[(rid >= i) ? (rid * (rid + 1) / 2 + i) : (ti + rid)] * l0;
+                }
+            }
+            // ---- projected Gauss-Seidel, 10 sweeps (btMultiBodyConstraintSolver::solveSingleIteration ordering: limits (alternating), normals, frictions)
+            const float mu = M.friction;
+#pragma unroll 1
+            for (int it = 0; it < 10; ++it) {
+#pragma unroll 1
+                for (int u = 0; u < NRmax; ++u) {
+                    const bool valid = u < NR;
+                    const int i = (u < NL) ? ((it & 1) ? u : NL - 1 - u) : u;
+                    const int owner = i & (W - 1), oslot = i / W;
+                    float dI = 0.f;
+                    if (valid && lane == owner) {
+                        float rhs = r_rhs[0], inv = r_inv[0], lam = r_lam[0], w = r_w[0];
+#pragma unroll
+                        for (int s = 1; s < kSlots; ++s) if (oslot == s) { rhs = r_rhs[s]; inv = r_inv[s]; lam = r_lam[s]; w = r_w[s]; }
+                        float lo = 0.f, hi = 1e10f;
+                        bool ok = true;
+                        if (i < NL) hi = 100.f;
+                        else if (i >= NL + P) { const float tot = sLam[NL + ((i - NL - P) >> 1)]; hi = mu * tot; lo = -hi; ok = tot > 0.f; }
+                        if (ok) {
+                            dI = rhs - w * inv;
+                            float sum = lam + dI;
+                            if (sum < lo) { dI = lo - lam; sum = lo; } else if (sum > hi) { dI = hi - lam; sum = hi; }
+#pragma unroll
+                            for (int s = 0; s < kSlots; ++s) if (oslot == s) r_lam[s] = sum;
+                            sLam[i] = sum;
+                        }
+                    }
+                    dI = T::shfl(dI, owner);
+                    const int ti = i * (i + 1) / 2;
+#pragma unroll
+                    for (int s = 0; s < kSlots; ++s) {
+                        const int rid = lane + s * W;
+                        if (s * W < NRmax && rid < NR && valid) r_w[s] += sA[(rid >= i) ? (tj[s] + i) : (ti + rid)] * dI;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        // write impulses back to the manifold (warm start of the next sub-step)
+        __syncwarp();
+        {
+            // each contact point p belongs to (link, slot) = sPr[p]; the owning lane patches its register copy of the manifold
+#pragma unroll 1
+            for (int p = 0; p < ((W == 32) ? P : wmax(P)); ++p) {
+                if (p < P) {
+                    const int ref = sPr[p];
+                    if ((ref >> 2) == lane) {
+                        const float ln = sLam[NL + p], l1 = sLam[NL + P + 2 * p], l2 = sLam[NL + P + 2 * p + 1];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) if (c == (ref & 3)) { mp[c * 12 + 7] = ln; mp[c * 12 + 8] = l1; mp[c * 12 + 9] = l2; }
+                    }
+                }
+            }
+            if (act && alive) {
+                float4* mo = reinterpret_cast<float4*>(mani + li * kManifoldFloats);
+#pragma unroll
+                for (int k = 0; k < 12; ++k) mo[k] = make_float4(mp[4 * k], mp[4 * k + 1], mp[4 * k + 2], mp[4 * k + 3]);
+            }
+        }
+        // ---- z = Y^T lambda (lanes = chain depth), then dv = L^-1 D^-1/2 z by the root -> leaves pass
+        if (NRmax > 0) {
+#pragma unroll 1
+            for (int k = lane; k < n; k += W) sZ[k] = 0.f;
+            __syncwarp();
+#pragma unroll 1
+            for (int i = 0; i < NRmax; ++i) {
+                if (i < NR) {
+                    const int b = sRl[i];
+                    const int lastd = (lk_i2(b) >> 8) & 0xff;
+#pragma unroll 1
+                    for (int k = lane; k <= lastd; k += W) sZ[CH[b * CL + k]] += sY[k * MR + i] * sLam[i];
+                }
+                __syncwarp();
+            }
+            S6 dB = mks(mk3(0, 0, 0), mk3(0, 0, 0));
+            if (lane == 0) {   // base: dB = G^-T z
+                float x[6] = {sZ[0], sZ[1], sZ[2], sZ[3], sZ[4], sZ[5]};
+                float g[15];
+#pragma unroll
+                for (int k = 0; k < 15; ++k) g[k] = sG[k];
+#pragma unroll
+                for (int i = 5; i >= 0; --i) {
+#pragma unroll
+                    for (int k = i + 1; k < 6; ++k) x[i] -= g[k * (k - 1) / 2 + i] * x[k];
+                    x[i] *= sG[15 + i];
+                }
+                dB = mks(mk3(x[0], x[1], x[2]), mk3(x[3], x[4], x[5]));
+            }
+            float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+            if (ndof >= 1) z0 = sZ[dof0] * sqrtf(inv0);
+            if (ndof == 3) { z1 = sZ[dof0 + 1] * sqrtf(inv1); z2 = sZ[dof0 + 2] * sqrtf(inv2); }
+            if (lane == 0) al = descend(xm(R, cvec, dB), z0, z1, z2);
+#pragma unroll 1
+            for (int lv = 1; lv <= maxlevel; ++lv) {
+                S6 pa = T::shfl6(al, plane);
+                if (level == lv) al = descend(xm(R, cvec, pa), z0, z1, z2);
+            }
+            V3 dw = mulT(Rwb, mk3(T::shfl(dB.a.x, 0), T::shfl(dB.a.y, 0), T::shfl(dB.a.z, 0)));
+            V3 dv = mulT(Rwb, mk3(T::shfl(dB.l.x, 0), T::shfl(dB.l.y, 0), T::shfl(dB.l.z, 0)));
+            auto cl = [](float v) { return fminf(fmaxf(v, -100.f), 100.f); };
+            if (NR > 0) {
+                baseOmega = mk3(cl(baseOmega.x + dw.x), cl(baseOmega.y + dw.y), cl(baseOmega.z + dw.z));
+                baseVel = mk3(cl(baseVel.x + dv.x), cl(baseVel.y + dv.y), cl(baseVel.z + dv.z));
+                if (ndof >= 1) jv.x = cl(jv.x + qd0);
+                if (ndof == 3) { jv.y = cl(jv.y + qd1); jv.z = cl(jv.z + qd2); }
+            }
+        }
+        if (DEBUG && dbg && first_upd) {
+            const int o = (sub == 0 ? 6 * kMaxDofs : 10 * kMaxDofs + 1024);
+            if (lane == 0) { dbg[o] = baseOmega.x; dbg[o + 1] = baseOmega.y; dbg[o + 2] = baseOmega.z; dbg[o + 3] = baseVel.x; dbg[o + 4] = baseVel.y; dbg[o + 5] = baseVel.z; }
+            if (ndof >= 1) dbg[o + dof0] = jv.x;
+            if (ndof == 3) { dbg[o + dof0 + 1] = jv.y; dbg[o + dof0 + 2] = jv.z; }
+            // impulses in the order [normals | friction pairs | limits]
+            const int lo_ = (sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024) + 1;
+            for (int k = lane; k < NR && k < 60; k += W) { const int src = (k < 3 * P) ? NL + k : k - 3 * P; dbg[lo_ + k] = sLam[src]; }
+        }
+        // ---- integrate positions (btMultiBody::stepPositionsMultiDof)
+        basePos = basePos + h * baseVel;
+        baseQuat = quat_integrate3(baseOmega, baseQuat, true, h);
+        if (jtype == kJRevolute) jp.x += h * jv.x;
+        else if (jtype == kJSpherical) { Q4 q = quat_integrate3(mk3(jv.x, jv.y, jv.z), mkq(jp.x, jp.y, jp.z, jp.w), false, h); jp = make_float4(q.x, q.y, q.z, q.w); }
+        __syncwarp();
+        need_kin = true;
+        if (ph == sim_substeps) pending_flags = true;
+    }
+}
+
+// explicit instantiations used by capi.cu: (tile width, debug dumps)
+template __global__ void dm_step_kernel<16, false>(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
+template __global__ void dm_step_kernel<32, false>(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
+template __global__ void dm_step_kernel<16, true>(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
+template __global__ void dm_step_kernel<32, true>(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
+
+}  // namespace dmk

@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(kUpdateMaxThreads, 1) dm_update_kernel(const D
     };
 
     bool need_kin = true, pending_flags = false;
-    const bool ph_sync_every_stage = sync_every_stage != 0;
+    // block-wide synchronisation policy: 1 = every stage, 0 = once per update, k < 0 = every -k updates, -1000 = never
+    const int sync_period = sync_every_stage > 0 ? 1 : (sync_every_stage == 0 ? (sim_substeps + 1) : (sync_every_stage <= -1000 ? 0 : -sync_every_stage * (sim_substeps + 1)));
     const int stages_per_upd = sim_substeps + 1;
     const int total_stages = n_updates * stages_per_upd;
     #pragma unroll 1
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(kUpdateMaxThreads, 1) dm_update_kernel(const D
         if (stage == total_stages) break;
         // stage-synchronous execution: every warp of the block runs the same stage at the same time, so the (large) kernel streams
         // through the instruction cache once per stage instead of once per warp
-        if (ph_sync_every_stage || (stage % stages_per_upd) == 0) { if (__syncthreads_and(!alive)) break; }
+        if (sync_period != 0 && (stage % sync_period) == 0) { if (__syncthreads_and(!alive)) break; }
         const int ph = stage % stages_per_upd;      // 0: Stable-PD stage, 1..sim_substeps: Bullet sub-steps
         const bool first_upd = stage < stages_per_upd;
         int P = 0;
