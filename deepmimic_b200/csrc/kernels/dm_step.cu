@@ -228,9 +228,9 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
 
     // configuration / velocity dependent registers
     M3 R;               // parent->link axes
-    M3 Rwl;             // world->link axes
-    V3 Pw;              // joint pivot, world
     S6 vel;             // link spatial velocity at the pivot, link axes
+    auto own_Rwl = [&]() { M3 m; const float* w = sW + li * 12; for (int k = 0; k < 9; ++k) m.m[k] = w[k]; return m; };   // world->link axes (written by the kinematics pass)
+    auto own_Pw = [&]() { const float* w = sW + li * 12; return mk3(w[9], w[10], w[11]); };                             // joint pivot, world
     float tau0 = 0.f, tau1 = 0.f, tau2 = 0.f;   // joint torques of the current update (body-frame components / revolute scalar)
     bool in_contact_tol = false;
 
@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             const M3 Rwb = qmat(baseQuat);
             V3 jw = mk3(0, 0, 0);
             if (jtype == kJSpherical) jw = mk3(jv.x, jv.y, jv.z); else if (jtype == kJRevolute) jw = jv.x * axis;
+            M3 Rwl; V3 Pw;
             if (lane == 0) {
                 Rwl = mul(R, Rwb); Pw = basePos + mulT(Rwb, cvec);
                 vel = xm(R, cvec, mks(mul(Rwb, baseOmega), mul(Rwb, baseVel)));
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             const unsigned fseg = (W == 32) ? fb : ((fb >> (threadIdx.x & 16)) & 0xffffu);
             const int fallen = (fseg != 0 && M.enable_contact_fall) ? 1 : 0;
             // exploded velocities: any link |v|, |w| component > 100 in world axes (cSimCharacter::HasVelExploded); v at the COM
+            const M3 Rwl = own_Rwl();
             V3 vw = mulT(Rwl, vel.l + cross(vel.a, dvec)) * (1.0f / M.scale), ww = mulT(Rwl, vel.a);
             float mx = fmaxf(fmaxf(fmaxf(fabsf(vw.x), fabsf(vw.y)), fabsf(vw.z)), fmaxf(fmaxf(fabsf(ww.x), fabsf(ww.y)), fabsf(ww.z)));
             const unsigned eb = __ballot_sync(0xffffffffu, act && mx > 100.f);
@@ -328,7 +330,6 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         const int ph = stage % stages_per_upd;      // 0: Stable-PD stage, 1..sim_substeps: Bullet sub-steps
         const bool first_upd = stage < stages_per_upd;
         int P = 0;
-        float mp[48];
         if (ph == 0) {
             // ---------------- clocks: cScene::Update, cSceneImitate::UpdateKinChar, cDeepMimicCharController::UpdateCalcTau
             timer += dt;
@@ -363,6 +364,9 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         } else {
             // ---------------- collision: link convex vs plane y = 0, persistent manifold of <= 4 points per link (btPersistentManifold)
             int cnt = 0;
+            float mp[48];
+            const M3 Rwl = own_Rwl();
+            const V3 Pw = own_Pw();
             {
                 const float4* mg = reinterpret_cast<const float4*>(mani + li * kManifoldFloats);
 #pragma unroll
@@ -446,6 +450,11 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             in_contact_tol = false;   // cContactManager::Update: distance <= 0.001 * scale
 #pragma unroll
             for (int c = 0; c < 4; ++c) if (c < cnt && mp[c * 12 + 10] <= 0.001f * M.scale) in_contact_tol = true;
+            if (act && alive) {
+                float4* mo = reinterpret_cast<float4*>(mani + li * kManifoldFloats);
+#pragma unroll
+                for (int k = 0; k < 12; ++k) mo[k] = make_float4(mp[4 * k], mp[4 * k + 1], mp[4 * k + 2], mp[4 * k + 3]);
+            }
             // exclusive prefix over lanes -> point indices; publish points to the solver
             int incl = cnt;
 #pragma unroll
@@ -893,23 +902,12 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         }
         // write impulses back to the manifold (warm start of the next sub-step)
         __syncwarp();
-        {
-            // each contact point p belongs to (link, slot) = sPr[p]; the owning lane patches its register copy of the manifold
 #pragma unroll 1
-            for (int p = 0; p < ((W == 32) ? P : wmax(P)); ++p) {
-                if (p < P) {
-                    const int ref = sPr[p];
-                    if ((ref >> 2) == lane) {
-                        const float ln = sLam[NL + p], l1 = sLam[NL + P + 2 * p], l2 = sLam[NL + P + 2 * p + 1];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) if (c == (ref & 3)) { mp[c * 12 + 7] = ln; mp[c * 12 + 8] = l1; mp[c * 12 + 9] = l2; }
-                    }
-                }
-            }
-            if (act && alive) {
-                float4* mo = reinterpret_cast<float4*>(mani + li * kManifoldFloats);
-#pragma unroll
-                for (int k = 0; k < 12; ++k) mo[k] = make_float4(mp[4 * k], mp[4 * k + 1], mp[4 * k + 2], mp[4 * k + 3]);
+        for (int p = lane; p < P; p += W) {
+            if (alive) {
+                const int ref = sPr[p];
+                float* mpt = mani + (ref >> 2) * kManifoldFloats + (ref & 3) * 12;
+                mpt[7] = sLam[NL + p]; mpt[8] = sLam[NL + P + 2 * p]; mpt[9] = sLam[NL + P + 2 * p + 1];
             }
         }
         // ---- z = Y^T lambda (lanes = chain depth), then dv = L^-1 D^-1/2 z by the root -> leaves pass
