@@ -96,7 +96,7 @@ struct DevState {
 // passed by value as a kernel parameter (constant bank)
 struct StepLayout {
     int nl, n, chain_len, maxrows, maxpts;
-    int oU, oR, oA, oW, oV, oY, oLam, oRl, oPp, oPi, oPr, oQ, oG, oZ;
+    int oU, oR, oA, oW, oV, oY, oLam, oRhs, oInv, oRl, oPp, oPi, oPr, oQ, oG, oZ;
     int env_floats, hot_floats;
 };
 

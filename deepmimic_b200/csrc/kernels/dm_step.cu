@@ -14,6 +14,8 @@
 // accelerations are btMultiBody::computeAccelerationsArticulatedBodyAlgorithmMultiDof's).  Constraint rows are built with
 // lanes = rows (each lane walks its row's link chain once), the row coupling matrix J M^-1 J^T is formed explicitly in shared
 // memory and PGS runs in impulse space with lanes = rows (one shuffle + one FMA per row update instead of a reduction).
+// All spatial quantities of a link are expressed in WORLD axes about the link's own joint pivot, so passing them between
+// parent and child is a pure shift (no rotation of 6x6 blocks).
 // No tensor cores: there is no dense contraction here (34 or 70 dofs, tree-sparse); the path is latency-bound.
 #include "dm_model.cuh"
 
@@ -106,7 +108,8 @@ __device__ __forceinline__ Q4 quat_integrate3(V3 omega, Q4 quat, bool base_body,
 }
 
 // ---- block-shared model table, floats per link (LK)
-enum LkSlot { kLC = 0 /*3*/, kLD = 3 /*3*/, kLM = 6, kLWd = 7 /*6*/, kLWb = 13 /*6*/, kLAx = 19 /*3*/, kLInt = 22 /* parent|jtype|ndof|depth0 */, kLInt2 = 23 /* dof0|lastd|nchild */, kLkFloats = 24 };
+enum LkSlot { kLC = 0 /*3*/, kLD = 3 /*3*/, kLM = 6, kLWd = 7 /*6*/, kLWb = 13 /*6*/, kLAx = 19 /*3*/, kLInt = 22 /* parent|jtype|ndof|depth0 */, kLInt2 = 23 /* dof0|lastd|nchild */,
+              kLZr = 24 /*4*/, kLHe = 28 /*3*/, kLThr = 31, kLKp = 32, kLKd = 33, kLTl = 34, kLLo = 35, kLHi = 36, kLFlg = 37 /* shape | fall<<8 | has_limit<<16 */, kLkFloats = 40 };
 
 }  // namespace
 
@@ -115,13 +118,13 @@ int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L) {
     int o = 0;
     L->nl = nl; L->n = n; L->chain_len = chain_len; L->maxrows = maxrows; L->maxpts = maxpts;
     L->oU = o; o += nl * 24;                       // per link: U0 U1 U2 (6 each), 1/D (3), sqrt(1/D) (3)
-    L->oR = o; o += nl * 12;                       // per link: parent->link rotation (9) + pad
+    L->oR = o; o += nl * 12;                       // per link: joint axes in world axes (9), parent pivot -> pivot (3)
     L->oA = o;                                     // union { world frames + link velocities | packed lower triangle of J M^-1 J^T }
     const int world = nl * 20, tri = maxrows * (maxrows + 1) / 2;
     L->oW = o; L->oV = o + nl * 12;
     o += (world > tri ? world : tri);
     L->oY = o; o += chain_len * maxrows;           // Yt[depth][row]
-    L->oLam = o; o += maxrows;
+    L->oLam = o; o += maxrows; L->oRhs = o; o += maxrows; L->oInv = o; o += maxrows;
     L->oRl = o; o += maxrows;                      // row -> link (int)
     L->oPp = o; o += maxpts * 4; L->oPi = o; o += maxpts; L->oPr = o; o += maxpts;
     L->oQ = o; o += 4 * 8;                         // limit rows: link, dir, penetration, joint rate (<= 8)
@@ -166,6 +169,10 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         q[kLWb + 0] = K.inertiaB[0] + sh[0]; q[kLWb + 1] = sh[1]; q[kLWb + 2] = sh[2]; q[kLWb + 3] = K.inertiaB[1] + sh[3]; q[kLWb + 4] = sh[4]; q[kLWb + 5] = K.inertiaB[2] + sh[5];
         reinterpret_cast<int*>(q)[kLInt] = (K.parent & 0xff) | ((K.jtype & 0xff) << 8) | ((K.ndof & 0xff) << 16) | ((K.depth0 & 0xff) << 24);
         reinterpret_cast<int*>(q)[kLInt2] = (K.dof0 & 0xff) | ((K.last_depth & 0xff) << 8) | ((K.nchild & 0xff) << 16);
+        for (int k = 0; k < 4; ++k) q[kLZr + k] = K.zrot[k];
+        for (int k = 0; k < 3; ++k) q[kLHe + k] = K.he[k];
+        q[kLThr] = K.break_thr; q[kLKp] = K.kp; q[kLKd] = K.kd; q[kLTl] = K.tlim; q[kLLo] = K.lim_lo; q[kLHi] = K.lim_hi;
+        reinterpret_cast<int*>(q)[kLFlg] = (K.shape & 0xff) | ((K.fall_contact & 0xff) << 8) | ((K.has_limit & 0xff) << 16);
         for (int d = 0; d < CL; ++d) CH[j * CL + d] = M.chain_dof[j][d];
         for (int b = 0; b < nl; ++b) {
             int c = 0;
@@ -184,21 +191,21 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     auto lk_i2 = [&](int j) { return reinterpret_cast<const int*>(LK + j * kLkFloats)[kLInt2]; };
 
     float* E = sm + LY.hot_floats + tile * LY.env_floats;   // this environment's block
-    float* sU = E + LY.oU; float* sR = E + LY.oR; float* sW = E + LY.oW; float* sV = E + LY.oV; float* sA = E + LY.oA; float* sY = E + LY.oY;
-    float* sLam = E + LY.oLam; int* sRl = reinterpret_cast<int*>(E + LY.oRl);
+    float* sU = E + LY.oU; float* sS = E + LY.oR; float* sW = E + LY.oW; float* sV = E + LY.oV; float* sA = E + LY.oA; float* sY = E + LY.oY;
+    float* sLam = E + LY.oLam; float* sRhs = E + LY.oRhs; float* sInv = E + LY.oInv; int* sRl = reinterpret_cast<int*>(E + LY.oRl);
     float* sPp = E + LY.oPp; float* sPi = E + LY.oPi; int* sPr = reinterpret_cast<int*>(E + LY.oPr);
     float* sQ = E + LY.oQ; float* sG = E + LY.oG; float* sZ = E + LY.oZ;
 
-    // ---- per-lane model constants kept in registers
+    // ---- per-lane model constants kept in registers (the rest is read from the shared LK table when needed)
+    const float* LKo = LK + li * kLkFloats;
     const int parent = L.parent, jtype = L.jtype, ndof = act ? L.ndof : 0, dof0 = L.dof0, level = act ? L.level : 1000;
-    const V3 dvec = mk3(L.dvec[0], L.dvec[1], L.dvec[2]);
-    const V3 cvec = mk3(LK[li * kLkFloats + kLC], LK[li * kLkFloats + kLC + 1], LK[li * kLkFloats + kLC + 2]);
     const V3 axis = mk3(L.axis[0], L.axis[1], L.axis[2]);
     const float mass = act ? L.mass : 0.f;
     const int plane = parent >= 0 ? parent : 0;
     const int nchild = act ? L.nchild : 0;
     const int child_pack = (L.child[0] & 0xff) | ((L.child[1] & 0xff) << 8) | ((L.child[2] & 0xff) << 16) | ((L.child[3] & 0xff) << 24);
-    auto dir_of = [&](int d) { return (jtype == kJSpherical) ? unit3(d) : axis; };
+    const int lflags = reinterpret_cast<const int*>(LKo)[kLFlg];
+    const int shape = lflags & 0xff; const bool fall_contact = ((lflags >> 8) & 0xff) != 0, has_limit = ((lflags >> 16) & 0xff) != 0;
 
     // ---- state load (env-major block, float4)
     const int ss = sim_stride(nl);
@@ -224,15 +231,20 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     const float h = static_cast<float>(dt) / static_cast<float>(sim_substeps);
     const float fdt = static_cast<float>(dt);
     const V3 grav = mk3(M.gravity[0], M.gravity[1], M.gravity[2]);
+    const float scale = M.scale, mu = M.friction;
     float* dbg = (DEBUG && st.pdbg) ? st.pdbg + static_cast<size_t>(env) * kDebugFloats : nullptr;   // test hook: stage dumps of the first update
 
-    // configuration / velocity dependent registers
-    M3 R;               // parent->link axes
-    S6 vel;             // link spatial velocity at the pivot, link axes
-    auto own_Rwl = [&]() { M3 m; const float* w = sW + li * 12; for (int k = 0; k < 9; ++k) m.m[k] = w[k]; return m; };   // world->link axes (written by the kinematics pass)
-    auto own_Pw = [&]() { const float* w = sW + li * 12; return mk3(w[9], w[10], w[11]); };                             // joint pivot, world
+    // configuration / velocity dependent registers (world axes)
+    V3 S0, S1, S2;      // joint axes: rows of the world->link rotation for a spherical joint, the hinge axis (S0) for a revolute joint
+    V3 cw;              // parent pivot -> own pivot
+    V3 dw;              // own pivot -> centre of mass
+    S6 vel;             // link spatial velocity at the pivot
     float tau0 = 0.f, tau1 = 0.f, tau2 = 0.f;   // joint torques of the current update (body-frame components / revolute scalar)
     bool in_contact_tol = false;
+    auto own_Rwl = [&]() { M3 m; const float* w = sW + li * 12; for (int k = 0; k < 9; ++k) m.m[k] = w[k]; return m; };   // world->link axes (written by the kinematics pass)
+    auto sdir = [&](int d) { return d == 0 ? S0 : (d == 1 ? S1 : S2); };
+    auto shift_m = [](S6 m, V3 c) { return mks(m.a, m.l + cross(m.a, c)); };   // motion vector: reference point moved by +c
+    auto shift_f = [](S6 f, V3 c) { return mks(f.a + cross(c, f.l), f.l); };   // force vector: reference point moved by -c (child pivot -> parent pivot)
 
     bool need_kin = true, pending_flags = false;
     const int stages_per_upd = sim_substeps + 1;
@@ -243,7 +255,8 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         // =================================================================== forward kinematics + link velocities (root -> leaves)
         if (need_kin) {
             need_kin = false;
-            const Q4 zrot = mkq(L.zrot[0], L.zrot[1], L.zrot[2], L.zrot[3]);
+            const Q4 zrot = mkq(LKo[kLZr], LKo[kLZr + 1], LKo[kLZr + 2], LKo[kLZr + 3]);
+            const V3 cvec = mk3(LKo[kLC], LKo[kLC + 1], LKo[kLC + 2]);
             Q4 cached;
             if (jtype == kJSpherical) cached = qmul(mkq(jp.x, jp.y, jp.z, -jp.w), zrot);
             else if (jtype == kJRevolute) {
@@ -251,15 +264,14 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 __sincosf(-0.5f * jp.x, &s, &c);   // |angle| <= pi/2 + limit overshoot: fast path is accurate to ~1 ulp of the result scale
                 cached = qmul(mkq(axis.x * s, axis.y * s, axis.z * s, c), zrot);
             } else cached = zrot;
-            R = qmat(cached);
+            const M3 R = qmat(cached);
             const M3 Rwb = qmat(baseQuat);
             V3 jw = mk3(0, 0, 0);
             if (jtype == kJSpherical) jw = mk3(jv.x, jv.y, jv.z); else if (jtype == kJRevolute) jw = jv.x * axis;
             M3 Rwl; V3 Pw;
             if (lane == 0) {
-                Rwl = mul(R, Rwb); Pw = basePos + mulT(Rwb, cvec);
-                vel = xm(R, cvec, mks(mul(Rwb, baseOmega), mul(Rwb, baseVel)));
-                vel.a += jw;
+                Rwl = mul(R, Rwb); cw = mulT(Rwb, cvec); Pw = basePos + cw;
+                vel = mks(baseOmega + mulT(Rwl, jw), baseVel + cross(baseOmega, cw));
             }
 #pragma unroll 1
             for (int lv = 1; lv <= maxlevel; ++lv) {
@@ -268,17 +280,21 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 for (int k = 0; k < 9; ++k) pR.m[k] = T::shfl(Rwl.m[k], plane);
                 pp = T::shfl3(Pw, plane);
                 pv = T::shfl6(vel, plane);
-                if (level == lv) { Rwl = mul(R, pR); Pw = pp + mulT(pR, cvec); vel = xm(R, cvec, pv); vel.a += jw; }
+                if (level == lv) {
+                    Rwl = mul(R, pR); cw = mulT(pR, cvec); Pw = pp + cw;
+                    vel = mks(pv.a + mulT(Rwl, jw), pv.l + cross(pv.a, cw));
+                }
             }
+            dw = mulT(Rwl, mk3(LKo[kLD], LKo[kLD + 1], LKo[kLD + 2]));
+            S0 = mk3(Rwl.m[0], Rwl.m[1], Rwl.m[2]); S1 = mk3(Rwl.m[3], Rwl.m[4], Rwl.m[5]); S2 = mk3(Rwl.m[6], Rwl.m[7], Rwl.m[8]);
+            if (jtype != kJSpherical) S0 = mulT(Rwl, axis);
             if (act) {
-                float* r = sR + lane * 12; float* w = sW + lane * 12;
+                float* w = sW + lane * 12; float* q = sS + lane * 12;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) { r[k] = R.m[k]; w[k] = Rwl.m[k]; }
+                for (int k = 0; k < 9; ++k) w[k] = Rwl.m[k];
                 w[9] = Pw.x; w[10] = Pw.y; w[11] = Pw.z;
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < 9; ++k) sG[21 + k] = Rwb.m[k];
+                q[0] = S0.x; q[1] = S0.y; q[2] = S0.z; q[3] = S1.x; q[4] = S1.y; q[5] = S1.z; q[6] = S2.x; q[7] = S2.y; q[8] = S2.z;
+                q[9] = cw.x; q[10] = cw.y; q[11] = cw.z;
             }
             __syncwarp();
         }
@@ -292,12 +308,11 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 need_action = (c0 != c1) ? 1 : 0;
             }
             // fall: any fall-contact link with a manifold point at distance <= 0.001*scale (state of the last sub-step's collision pass)
-            const unsigned fb = __ballot_sync(0xffffffffu, act && L.fall_contact && in_contact_tol);
+            const unsigned fb = __ballot_sync(0xffffffffu, act && fall_contact && in_contact_tol);
             const unsigned fseg = (W == 32) ? fb : ((fb >> (threadIdx.x & 16)) & 0xffffu);
             const int fallen = (fseg != 0 && M.enable_contact_fall) ? 1 : 0;
             // exploded velocities: any link |v|, |w| component > 100 in world axes (cSimCharacter::HasVelExploded); v at the COM
-            const M3 Rwl = own_Rwl();
-            V3 vw = mulT(Rwl, vel.l + cross(vel.a, dvec)) * (1.0f / M.scale), ww = mulT(Rwl, vel.a);
+            const V3 vw = (vel.l + cross(vel.a, dw)) * (1.0f / scale), ww = vel.a;
             float mx = fmaxf(fmaxf(fmaxf(fabsf(vw.x), fabsf(vw.y)), fabsf(vw.z)), fmaxf(fmaxf(fabsf(ww.x), fabsf(ww.y)), fabsf(ww.z)));
             const unsigned eb = __ballot_sync(0xffffffffu, act && mx > 100.f);
             const unsigned eseg = (W == 32) ? eb : ((eb >> (threadIdx.x & 16)) & 0xffffu);
@@ -366,7 +381,6 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             int cnt = 0;
             float mp[48];
             const M3 Rwl = own_Rwl();
-            const V3 Pw = own_Pw();
             {
                 const float4* mg = reinterpret_cast<const float4*>(mani + li * kManifoldFloats);
 #pragma unroll
@@ -374,16 +388,17 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) if (mp[c * 12] != 0.f && cnt == c) cnt = c + 1;
-            const float thr = L.break_thr;
-            const V3 pos = Pw + mulT(Rwl, dvec);     // COM, world (Bullet's link collider frame)
+            const float thr = LKo[kLThr];
+            const V3 he = mk3(LKo[kLHe], LKo[kLHe + 1], LKo[kLHe + 2]);
+            const V3 pos = mk3(sW[li * 12 + 9], sW[li * 12 + 10], sW[li * 12 + 11]) + dw;     // COM, world (Bullet's link collider frame)
             V3 dl = mul(Rwl, mk3(0.f, -1.f, 0.f));   // support direction -n in link coordinates
             V3 vtx;
-            if (L.shape == kSBox) vtx = mk3(dl.x >= 0 ? L.he[0] : -L.he[0], dl.y >= 0 ? L.he[1] : -L.he[1], dl.z >= 0 ? L.he[2] : -L.he[2]);
+            if (shape == kSBox) vtx = mk3(dl.x >= 0 ? he.x : -he.x, dl.y >= 0 ? he.y : -he.y, dl.z >= 0 ? he.z : -he.z);
             else {
                 V3 sup = mk3(0, 0, 0);
-                if (L.shape == kSCapsule) sup = mk3(0.f, (dl.y >= 0.f) ? L.he[1] : -L.he[1], 0.f);   // first end point wins ties
+                if (shape == kSCapsule) sup = mk3(0.f, (dl.y >= 0.f) ? he.y : -he.y, 0.f);   // first end point wins ties
                 float inv = rsqrtf(dot(dl, dl));
-                vtx = sup + (L.he[0] * inv) * dl;
+                vtx = sup + (he.x * inv) * dl;
             }
             const V3 vw = pos + mulT(Rwl, vtx);
             const float dist = vw.y;
@@ -449,7 +464,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             if (!act) cnt = 0;
             in_contact_tol = false;   // cContactManager::Update: distance <= 0.001 * scale
 #pragma unroll
-            for (int c = 0; c < 4; ++c) if (c < cnt && mp[c * 12 + 10] <= 0.001f * M.scale) in_contact_tol = true;
+            for (int c = 0; c < 4; ++c) if (c < cnt && mp[c * 12 + 10] <= 0.001f * scale) in_contact_tol = true;
             if (act && alive) {
                 float4* mo = reinterpret_cast<float4*>(mani + li * kManifoldFloats);
 #pragma unroll
@@ -475,21 +490,24 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
 
         // =================================================================== bias accelerations (root -> leaves), Stable-PD right-hand side
         const bool bullet = ph != 0;
-        const M3 Rwb = qmat(baseQuat);
-        V3 jw = mk3(0, 0, 0);
-        if (jtype == kJSpherical) jw = mk3(jv.x, jv.y, jv.z); else if (jtype == kJRevolute) jw = jv.x * axis;
+        V3 jww = mk3(0, 0, 0);   // joint angular velocity, world axes
+        if (jtype == kJSpherical) jww = jv.x * S0 + jv.y * S1 + jv.z * S2; else if (jtype == kJRevolute) jww = jv.x * S0;
         S6 ab;
         {
-            const S6 vb = mks(mul(Rwb, baseOmega), mul(Rwb, baseVel));
-            const V3 w_used = bullet ? vb.a : baseOmega;   // cRBDUtil::BuildCjRoot differentiates the root quaternion with the body-frame formula
-                                                           // applied to the world-frame angular velocity (RBDUtil.cpp:915-958): reproduced in the SPD stage
-            const S6 abB = mks(mk3(0, 0, 0), mul(Rwb, -grav) - cross(w_used, vb.l));
-            const S6 cj = mks(cross(vel.a, jw), cross(vel.l, jw));
-            if (lane == 0) ab = xm(R, cvec, abB) + cj;
+            V3 wxv;
+            if (bullet) wxv = cross(baseOmega, baseVel);
+            else {   // cRBDUtil::BuildCjRoot differentiates the root quaternion with the body-frame formula applied to the world-frame
+                     // angular velocity (RBDUtil.cpp:915-958): reproduced in the Stable-PD stage
+                const M3 Rwb = qmat(baseQuat);
+                wxv = mulT(Rwb, cross(baseOmega, mul(Rwb, baseVel)));
+            }
+            const S6 abB = mks(mk3(0, 0, 0), -grav - wxv);
+            const S6 cj = mks(cross(vel.a, jww), cross(vel.l, jww));
+            if (lane == 0) ab = shift_m(abB, cw) + cj;
 #pragma unroll 1
             for (int lv = 1; lv <= maxlevel; ++lv) {
                 S6 pa = T::shfl6(ab, plane);
-                if (level == lv) ab = xm(R, cvec, pa) + cj;
+                if (level == lv) ab = shift_m(pa, cw) + cj;
             }
         }
         float pe0 = 0.f, pe1 = 0.f, pe2 = 0.f, kdt = 0.f, kd = 0.f;
@@ -508,7 +526,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             } else if (jtype == kJRevolute) {
                 e0 = tg.x - (normalize_angle3(jp.x) + fdt * jv.x);
             }
-            const float kp = L.kp; kd = L.kd;
+            const float kp = LKo[kLKp]; kd = LKo[kLKd];
             pe0 = kp * e0; pe1 = kp * e1; pe2 = kp * e2;
             kdt = fdt * kd;
             g0 = pe0 - kd * jv.x; g1 = pe1 - kd * jv.y; g2 = pe2 - kd * jv.z;
@@ -520,10 +538,12 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         Art IA; S6 pA;
         S6 U0, U1, U2; float inv0 = 0.f, inv1 = 0.f, inv2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;
         {
-            const float* wsel = LK + li * kLkFloats + (bullet ? kLWb : kLWd);
+            const float* wsel = LKo + (bullet ? kLWb : kLWd);
+            float wl[6];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) IA.ww[k] = act ? wsel[k] : 0.f;
-            const V3 md = mass * dvec;
+            for (int k = 0; k < 6; ++k) wl[k] = act ? wsel[k] : 0.f;
+            rot_sym(own_Rwl(), wl, IA.ww);     // link axes -> world axes
+            const V3 md = mass * dw;
             IA.wv[0] = 0.f; IA.wv[1] = -md.z; IA.wv[2] = md.y; IA.wv[3] = md.z; IA.wv[4] = 0.f; IA.wv[5] = -md.x; IA.wv[6] = -md.y; IA.wv[7] = md.x; IA.wv[8] = 0.f;
             IA.vv[0] = mass; IA.vv[1] = 0.f; IA.vv[2] = 0.f; IA.vv[3] = mass; IA.vv[4] = 0.f; IA.vv[5] = mass;
             // h = I v ; pA = I ab + v x* h
@@ -532,8 +552,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             pA = mks(an + cross(vel.a, hn) + cross(vel.l, hf), af + cross(vel.a, hf));
             U0 = U1 = U2 = mks(mk3(0, 0, 0), mk3(0, 0, 0));
         }
-        auto eliminate = [&](int d, float g, S6& Uo, float& invo, float& uo) {
-            const V3 dir = dir_of(d);
+        auto eliminate = [&](V3 dir, float g, S6& Uo, float& invo, float& uo) {
             const V3 Ua = sym_mul(IA.ww, dir), Ul = wvT_mul(IA.wv, dir);
             const float D = dot(dir, Ua) + kdt;
             const float inv = 1.0f / D;
@@ -546,30 +565,30 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             pA.a += u * sa; pA.l += u * sl;
             Uo = mks(Ua, Ul); invo = inv; uo = u;
         };
+        Art sd; S6 sf;
 #pragma unroll 1
         for (int lv = maxlevel; lv >= 0; --lv) {
             if (level == lv) {
-                if (ndof == 3) { eliminate(2, g2, U2, inv2, u2); eliminate(1, g1, U1, inv1, u1); }
-                if (ndof >= 1) eliminate(0, g0, U0, inv0, u0);
+                if (ndof == 3) { eliminate(S2, g2, U2, inv2, u2); eliminate(S1, g1, U1, inv1, u1); }
+                if (ndof >= 1) eliminate(S0, g0, U0, inv0, u0);
             }
-            if (lv == 0) break;
-            // express (IA, pA) of the lanes at this level in their parents' pivot frames
-            Art sd;
-            rot_sym(R, IA.ww, sd.ww); rot_gen(R, IA.wv, sd.wv); rot_sym(R, IA.vv, sd.vv);
-            const S6 sf = xf(R, cvec, pA);
+            // express (IA, pA) about the parent's pivot: shift by c = cw:  B' = B + C V ; A' = A - B C + C B'^T   (C = [c]x)
             {
-                // shift by c:  B' = B + C V ; A' = A - B C + C B'^T   (C = [c]x)
-                const V3 c = cvec;
-                const V3 v0 = mk3(sd.vv[0], sd.vv[1], sd.vv[2]), v1 = mk3(sd.vv[1], sd.vv[3], sd.vv[4]), v2 = mk3(sd.vv[2], sd.vv[4], sd.vv[5]);   // columns (= rows) of V
-                const V3 b0 = mk3(sd.wv[0], sd.wv[1], sd.wv[2]), b1 = mk3(sd.wv[3], sd.wv[4], sd.wv[5]), b2 = mk3(sd.wv[6], sd.wv[7], sd.wv[8]);   // rows of B
+                const V3 c = cw;
+                const V3 v0 = mk3(IA.vv[0], IA.vv[1], IA.vv[2]), v1 = mk3(IA.vv[1], IA.vv[3], IA.vv[4]), v2 = mk3(IA.vv[2], IA.vv[4], IA.vv[5]);   // columns (= rows) of V
+                const V3 b0 = mk3(IA.wv[0], IA.wv[1], IA.wv[2]), b1 = mk3(IA.wv[3], IA.wv[4], IA.wv[5]), b2 = mk3(IA.wv[6], IA.wv[7], IA.wv[8]);   // rows of B
                 const V3 k0 = cross(c, v0), k1 = cross(c, v1), k2 = cross(c, v2);   // columns of C V
                 const V3 n0 = mk3(b0.x + k0.x, b0.y + k1.x, b0.z + k2.x), n1 = mk3(b1.x + k0.y, b1.y + k1.y, b1.z + k2.y), n2 = mk3(b2.x + k0.z, b2.y + k1.z, b2.z + k2.z);   // rows of B'
                 const V3 p0 = cross(b0, c), p1 = cross(b1, c), p2 = cross(b2, c);   // rows of B C
                 const V3 q0 = cross(c, n0), q1 = cross(c, n1), q2 = cross(c, n2);   // columns of C B'^T
-                sd.ww[0] += -p0.x + q0.x; sd.ww[1] += -p0.y + q1.x; sd.ww[2] += -p0.z + q2.x;
-                sd.ww[3] += -p1.y + q1.y; sd.ww[4] += -p1.z + q2.y; sd.ww[5] += -p2.z + q2.z;
+                sd.ww[0] = IA.ww[0] - p0.x + q0.x; sd.ww[1] = IA.ww[1] - p0.y + q1.x; sd.ww[2] = IA.ww[2] - p0.z + q2.x;
+                sd.ww[3] = IA.ww[3] - p1.y + q1.y; sd.ww[4] = IA.ww[4] - p1.z + q2.y; sd.ww[5] = IA.ww[5] - p2.z + q2.z;
                 sd.wv[0] = n0.x; sd.wv[1] = n0.y; sd.wv[2] = n0.z; sd.wv[3] = n1.x; sd.wv[4] = n1.y; sd.wv[5] = n1.z; sd.wv[6] = n2.x; sd.wv[7] = n2.y; sd.wv[8] = n2.z;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) sd.vv[k] = IA.vv[k];
+                sf = shift_f(pA, c);
             }
+            if (lv == 0) break;
             const int nslot = LVC[lv - 1];
 #pragma unroll 1
             for (int c = 0; c < nslot; ++c) {
@@ -586,25 +605,13 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 if (take) { pA.a += gf.a; pA.l += gf.l; }
             }
         }
-        // ---- base: the (massless) floating base carries the root link's articulated inertia; Cholesky of the 6x6 in the base frame
-        S6 aB = mks(mk3(0, 0, 0), mk3(0, 0, 0));   // base spatial acceleration (deviation from the bias acceleration), base frame
+        // ---- base: the (massless) floating base carries the root link's articulated inertia; Cholesky of the 6x6 in world axes at the base
+        // origin, i.e. directly in the generalised base coordinates [omega_w, v_w]
+        S6 aB = mks(mk3(0, 0, 0), mk3(0, 0, 0));
         if (lane == 0) {
-            Art sd;
-            rot_sym(R, IA.ww, sd.ww); rot_gen(R, IA.wv, sd.wv); rot_sym(R, IA.vv, sd.vv);
-            const S6 sf = xf(R, cvec, pA);
-            const V3 c = cvec;
-            const V3 v0 = mk3(sd.vv[0], sd.vv[1], sd.vv[2]), v1 = mk3(sd.vv[1], sd.vv[3], sd.vv[4]), v2 = mk3(sd.vv[2], sd.vv[4], sd.vv[5]);
-            const V3 b0 = mk3(sd.wv[0], sd.wv[1], sd.wv[2]), b1 = mk3(sd.wv[3], sd.wv[4], sd.wv[5]), b2 = mk3(sd.wv[6], sd.wv[7], sd.wv[8]);
-            const V3 k0 = cross(c, v0), k1 = cross(c, v1), k2 = cross(c, v2);
-            const V3 n0 = mk3(b0.x + k0.x, b0.y + k1.x, b0.z + k2.x), n1 = mk3(b1.x + k0.y, b1.y + k1.y, b1.z + k2.y), n2 = mk3(b2.x + k0.z, b2.y + k1.z, b2.z + k2.z);
-            const V3 p0 = cross(b0, c), p1 = cross(b1, c), p2 = cross(b2, c);
-            const V3 q0 = cross(c, n0), q1 = cross(c, n1), q2 = cross(c, n2);
-            // 6x6 symmetric matrix, coordinates [w(3); v(3)], lower triangle a[i][j], j <= i
-            float a[6][6];
-            a[0][0] = sd.ww[0] - p0.x + q0.x;
-            a[1][0] = sd.ww[1] - p0.y + q1.x; a[1][1] = sd.ww[3] - p1.y + q1.y;
-            a[2][0] = sd.ww[2] - p0.z + q2.x; a[2][1] = sd.ww[4] - p1.z + q2.y; a[2][2] = sd.ww[5] - p2.z + q2.z;
-            a[3][0] = n0.x; a[3][1] = n1.x; a[3][2] = n2.x; a[4][0] = n0.y; a[4][1] = n1.y; a[4][2] = n2.y; a[5][0] = n0.z; a[5][1] = n1.z; a[5][2] = n2.z;   // B'^T
+            float a[6][6];   // lower triangle a[i][j], j <= i ; coordinates [w(3); v(3)]
+            a[0][0] = sd.ww[0]; a[1][0] = sd.ww[1]; a[1][1] = sd.ww[3]; a[2][0] = sd.ww[2]; a[2][1] = sd.ww[4]; a[2][2] = sd.ww[5];
+            a[3][0] = sd.wv[0]; a[3][1] = sd.wv[3]; a[3][2] = sd.wv[6]; a[4][0] = sd.wv[1]; a[4][1] = sd.wv[4]; a[4][2] = sd.wv[7]; a[5][0] = sd.wv[2]; a[5][1] = sd.wv[5]; a[5][2] = sd.wv[8];   // B'^T
             a[3][3] = sd.vv[0]; a[4][3] = sd.vv[1]; a[4][4] = sd.vv[3]; a[5][3] = sd.vv[2]; a[5][4] = sd.vv[4]; a[5][5] = sd.vv[5];
             float gi[6];   // 1 / G_ii
 #pragma unroll
@@ -649,18 +656,18 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         }
         // ---- accelerations (root -> leaves): qdd_d = (u_d - U_d . a') / D_d
         float qd0 = 0.f, qd1 = 0.f, qd2 = 0.f;
-        S6 al = mks(mk3(0, 0, 0), mk3(0, 0, 0));   // link acceleration deviation
+        S6 al = mks(mk3(0, 0, 0), mk3(0, 0, 0));   // link acceleration (deviation from the bias acceleration)
         auto descend = [&](S6 a, float n0, float n1, float n2) {
             // n_d: numerator already divided by D_d
-            if (ndof >= 1) { qd0 = n0 - inv0 * sdot(a, U0); a.a += qd0 * dir_of(0); }
-            if (ndof == 3) { qd1 = n1 - inv1 * sdot(a, U1); a.a += qd1 * dir_of(1); qd2 = n2 - inv2 * sdot(a, U2); a.a += qd2 * dir_of(2); }
+            if (ndof >= 1) { qd0 = n0 - inv0 * sdot(a, U0); a.a += qd0 * S0; }
+            if (ndof == 3) { qd1 = n1 - inv1 * sdot(a, U1); a.a += qd1 * S1; qd2 = n2 - inv2 * sdot(a, U2); a.a += qd2 * S2; }
             return a;
         };
-        if (lane == 0) al = descend(xm(R, cvec, aB), u0 * inv0, u1 * inv1, u2 * inv2);
+        if (lane == 0) al = descend(shift_m(aB, cw), u0 * inv0, u1 * inv1, u2 * inv2);
 #pragma unroll 1
         for (int lv = 1; lv <= maxlevel; ++lv) {
             S6 pa = T::shfl6(al, plane);
-            if (level == lv) al = descend(xm(R, cvec, pa), u0 * inv0, u1 * inv1, u2 * inv2);
+            if (level == lv) al = descend(shift_m(pa, cw), u0 * inv0, u1 * inv1, u2 * inv2);
         }
 
         if (!bullet) {
@@ -668,8 +675,8 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             float t0 = 0, t1 = 0, t2 = 0;
             if (ndof >= 1) t0 = pe0 + kd * (-jv.x - fdt * qd0);
             if (ndof == 3) { t1 = pe1 + kd * (-jv.y - fdt * qd1); t2 = pe2 + kd * (-jv.z - fdt * qd2); }
-            const float mag = sqrtf(t0 * t0 + t1 * t1 + t2 * t2);
-            if (mag > L.tlim) { float s = L.tlim / mag; t0 *= s; t1 *= s; t2 *= s; }
+            const float mag = sqrtf(t0 * t0 + t1 * t1 + t2 * t2), tlim = LKo[kLTl];
+            if (mag > tlim) { float s = tlim / mag; t0 *= s; t1 *= s; t2 *= s; }
             tau0 = t0; tau1 = t1; tau2 = t2;
             if (DEBUG && dbg && first_upd) {
                 if (ndof >= 1) { dbg[2 * kMaxDofs + dof0] = t0; dbg[3 * kMaxDofs + dof0] = qd0; }
@@ -681,21 +688,20 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
 
         // =================================================================== Bullet sub-step: v += a h, constraint rows, PGS, integration
         const int sub = ph - 1;
+        auto cl100 = [](float v) { return fminf(fmaxf(v, -100.f), 100.f); };   // applyDeltaVeeMultiDof clamp
         {
-            // base acceleration in the world-aligned generalised coordinates [omega_w, v_w]
-            V3 dw = mulT(Rwb, mk3(T::shfl(aB.a.x, 0), T::shfl(aB.a.y, 0), T::shfl(aB.a.z, 0)));
-            V3 dv = mulT(Rwb, mk3(T::shfl(aB.l.x, 0), T::shfl(aB.l.y, 0), T::shfl(aB.l.z, 0)));
+            // base acceleration: already in the world-aligned generalised coordinates [omega_w, v_w]
+            const V3 dwb = T::shfl3(aB.a, 0), dvb = T::shfl3(aB.l, 0);
             if (DEBUG && dbg && first_upd) {
                 const int o = (sub == 0 ? 4 * kMaxDofs : 8 * kMaxDofs + 1024);
-                if (lane == 0) { dbg[o] = dw.x; dbg[o + 1] = dw.y; dbg[o + 2] = dw.z; dbg[o + 3] = dv.x; dbg[o + 4] = dv.y; dbg[o + 5] = dv.z; }
+                if (lane == 0) { dbg[o] = dwb.x; dbg[o + 1] = dwb.y; dbg[o + 2] = dwb.z; dbg[o + 3] = dvb.x; dbg[o + 4] = dvb.y; dbg[o + 5] = dvb.z; }
                 if (ndof >= 1) dbg[o + dof0] = qd0;
                 if (ndof == 3) { dbg[o + dof0 + 1] = qd1; dbg[o + dof0 + 2] = qd2; }
             }
-            auto cl = [](float v) { return fminf(fmaxf(v, -100.f), 100.f); };   // applyDeltaVeeMultiDof clamp
-            baseOmega = mk3(cl(baseOmega.x + h * dw.x), cl(baseOmega.y + h * dw.y), cl(baseOmega.z + h * dw.z));
-            baseVel = mk3(cl(baseVel.x + h * dv.x), cl(baseVel.y + h * dv.y), cl(baseVel.z + h * dv.z));
-            if (ndof >= 1) jv.x = cl(jv.x + h * qd0);
-            if (ndof == 3) { jv.y = cl(jv.y + h * qd1); jv.z = cl(jv.z + h * qd2); }
+            baseOmega = mk3(cl100(baseOmega.x + h * dwb.x), cl100(baseOmega.y + h * dwb.y), cl100(baseOmega.z + h * dwb.z));
+            baseVel = mk3(cl100(baseVel.x + h * dvb.x), cl100(baseVel.y + h * dvb.y), cl100(baseVel.z + h * dvb.z));
+            if (ndof >= 1) jv.x = cl100(jv.x + h * qd0);
+            if (ndof == 3) { jv.y = cl100(jv.y + h * qd1); jv.z = cl100(jv.z + h * qd2); }
             vel = vel + h * al;   // link velocities are linear in the generalised velocities (the clamp only acts on exploding states)
             if (DEBUG && dbg && first_upd) {
                 const int o = (sub == 0 ? 5 * kMaxDofs : 9 * kMaxDofs + 1024);
@@ -704,6 +710,18 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 if (ndof == 3) { dbg[o + dof0 + 1] = jv.y; dbg[o + dof0 + 2] = jv.z; }
             }
         }
+        // ---- joint-limit rows (btMultiBodyJointLimitConstraint): a lane owns at most one active row
+        int lim_dir = 0; float lim_pen = 0.f;
+        if (act && has_limit) {
+            float p0 = jp.x - LKo[kLLo], p1 = LKo[kLHi] - jp.x;
+            if (!(p0 > 0.f)) { lim_dir = 1; lim_pen = p0; }
+            else if (!(p1 > 0.f)) { lim_dir = -1; lim_pen = p1; }
+        }
+        const unsigned lbal = __ballot_sync(0xffffffffu, lim_dir != 0);
+        const unsigned lseg = (W == 32) ? lbal : ((lbal >> (threadIdx.x & 16)) & 0xffffu);
+        int NL = __popc(lseg);
+        const unsigned anyrow = __ballot_sync(0xffffffffu, NL + P > 0);
+        if (anyrow != 0) {
         // publish the per-link factors and velocities for the row builders
         if (act) {
             float* u = sU + lane * 24;
@@ -714,31 +732,24 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             float* v = sV + lane * 8;
             v[0] = vel.a.x; v[1] = vel.a.y; v[2] = vel.a.z; v[3] = vel.l.x; v[4] = vel.l.y; v[5] = vel.l.z;
         }
-        // ---- joint-limit rows (btMultiBodyJointLimitConstraint): a lane owns at most one active row
-        int lim_dir = 0; float lim_pen = 0.f;
-        if (act && L.has_limit) {
-            float p0 = jp.x - L.lim_lo, p1 = L.lim_hi - jp.x;
-            if (!(p0 > 0.f)) { lim_dir = 1; lim_pen = p0; }
-            else if (!(p1 > 0.f)) { lim_dir = -1; lim_pen = p1; }
+        {
+            const int lidx = __popc(lseg & ((1u << lane) - 1u));
+            if (NL > 8) { NL = 8; f_over = 1; }
+            if (lim_dir != 0 && lidx < 8) { sQ[lidx] = __int_as_float(lane); sQ[8 + lidx] = (lim_dir == -1) ? -1.f : 1.f; sQ[16 + lidx] = lim_pen; sQ[24 + lidx] = jv.x; }
         }
-        int linc = lim_dir != 0 ? 1 : 0;
-#pragma unroll
-        for (int o = 1; o < W; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, linc, o, W); if (lane >= o) linc += t; }
-        int NL = T::shfli(linc, W - 1);
-        if (NL > 8) { NL = 8; f_over = 1; }
-        if (lim_dir != 0 && linc - 1 < 8) { sQ[linc - 1] = __int_as_float(lane); sQ[8 + linc - 1] = (lim_dir == -1) ? -1.f : 1.f; sQ[16 + linc - 1] = lim_pen; sQ[24 + linc - 1] = jv.x; }
         if (NL + 3 * P > MR) { P = (MR - NL) / 3; f_over = 1; }
         const int NR = NL + 3 * P;
         const int NRmax = (W == 32) ? NR : wmax(NR);
+        const int nslots = (NRmax + W - 1) / W;
         __syncwarp();
         // row ids in solver order: limits [0,NL) | normals [NL, NL+P) | friction pairs NL+P+2p+{0,1} (t1 = -x, t2 = +z)
         constexpr int kSlots = (W == 16) ? 3 : 2;
-        float r_rhs[kSlots], r_inv[kSlots], r_lam[kSlots], r_w[kSlots];
+        float r_w[kSlots];
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) {
-            r_rhs[s] = 0.f; r_inv[s] = 0.f; r_lam[s] = 0.f; r_w[s] = 0.f;
+            r_w[s] = 0.f;
             const int rid = lane + s * W;
-            if (s * W < NRmax) {
+            if (s < nslots) {
                 const bool rv_ = rid < NR;
                 int b = 0, kind = 0 /*0 limit 1 normal 2 t1 3 t2*/, p = 0;
                 float lsign = 1.f, lpen = 0.f;
@@ -748,20 +759,17 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                     else { const int f = rid - NL - P; p = f >> 1; kind = 2 + (f & 1); b = sPr[p] >> 2; }
                     sRl[rid] = b;
                 }
-                // force on link b in its pivot frame
+                // unit force of the row on link b, about b's pivot, world axes
                 S6 f = mks(mk3(0, 0, 0), mk3(0, 0, 0));
                 float rvel = 0.f, pdist = 0.f;
                 if (rv_ && kind != 0) {
                     const float* w = sW + b * 12;
-                    const V3 pa = mk3(sPp[p * 4], sPp[p * 4 + 1], sPp[p * 4 + 2]);
                     pdist = sPp[p * 4 + 3];
-                    const V3 dlt = mk3(pa.x - w[9], pa.y - w[10], pa.z - w[11]);
-                    const V3 rel = mk3(w[0] * dlt.x + w[1] * dlt.y + w[2] * dlt.z, w[3] * dlt.x + w[4] * dlt.y + w[5] * dlt.z, w[6] * dlt.x + w[7] * dlt.y + w[8] * dlt.z);
-                    const V3 fl_ = (kind == 1) ? mk3(w[1], w[4], w[7]) : ((kind == 2) ? mk3(-w[0], -w[3], -w[6]) : mk3(w[2], w[5], w[8]));   // Rwl * dir
+                    const V3 rel = mk3(sPp[p * 4] - w[9], sPp[p * 4 + 1] - w[10], sPp[p * 4 + 2] - w[11]);
+                    const V3 fl_ = (kind == 1) ? mk3(0.f, 1.f, 0.f) : ((kind == 2) ? mk3(-1.f, 0.f, 0.f) : mk3(0.f, 0.f, 1.f));
                     f = mks(cross(rel, fl_), fl_);
                     const float* v = sV + b * 8;
-                    const V3 va = mk3(v[0], v[1], v[2]), vl = mk3(v[3], v[4], v[5]);
-                    rvel = dot(fl_, vl + cross(va, rel));
+                    rvel = dot(fl_, mk3(v[3], v[4], v[5]) + cross(mk3(v[0], v[1], v[2]), rel));
                 }
                 // walk the chain base <- ... <- b
                 float acc = 0.f;
@@ -770,13 +778,12 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
 #pragma unroll 1
                 while (true) {
                     const int info = lk_i(cur);
-                    const int par = static_cast<int>(static_cast<signed char>(info & 0xff)), jt = (info >> 8) & 0xff, nd = (info >> 16) & 0xff, dp0 = (info >> 24) & 0xff;
+                    const int par = static_cast<int>(static_cast<signed char>(info & 0xff)), nd = (info >> 16) & 0xff, dp0 = (info >> 24) & 0xff;
                     const float* u = sU + cur * 24;
-                    const float* lk = LK + cur * kLkFloats;
+                    const float* q = sS + cur * 12;
 #pragma unroll 1
                     for (int d = nd - 1; d >= 0; --d) {
-                        const V3 dir = (jt == kJSpherical) ? unit3(d) : mk3(lk[kLAx], lk[kLAx + 1], lk[kLAx + 2]);
-                        float t = dot(dir, f.a);
+                        float t = q[d * 3] * f.a.x + q[d * 3 + 1] * f.a.y + q[d * 3 + 2] * f.a.z;
                         if (first && kind == 0) { t = lsign; rvel = lsign * sQ[24 + rid]; }
                         const float y = t * u[21 + d];
                         if (rv_) sY[(dp0 + d) * MR + rid] = y;
@@ -785,11 +792,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                         f.a.x -= ti * u[d * 6]; f.a.y -= ti * u[d * 6 + 1]; f.a.z -= ti * u[d * 6 + 2]; f.l.x -= ti * u[d * 6 + 3]; f.l.y -= ti * u[d * 6 + 4]; f.l.z -= ti * u[d * 6 + 5];
                     }
                     first = false;
-                    const float* r = sR + cur * 12;
-                    M3 Rc;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) Rc.m[k] = r[k];
-                    f = xf(Rc, mk3(lk[kLC], lk[kLC + 1], lk[kLC + 2]), f);
+                    f = shift_f(f, mk3(q[9], q[10], q[11]));
                     if (par < 0) break;
                     cur = par;
                 }
@@ -807,12 +810,12 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 }
                 if (rv_) {
                     const float inv = acc > 1.1920929e-7f ? 1.0f / acc : 0.f;
-                    float rhs;
+                    float rhs, lam0 = 0.f;
                     if (kind == 1) {   // setupMultiBodyContactConstraint: erp 0.2, restitution 0, no split impulse for multibodies
                         float perr = 0.f, verr = -rvel;
                         if (pdist > 0.f) verr -= pdist / h; else perr = -pdist * 0.2f / h;
                         rhs = perr * inv + verr * inv;
-                        r_lam[s] = sPi[p] * 0.85f;   // SOLVER_USE_WARMSTARTING, warmstartingFactor 0.85
+                        lam0 = sPi[p] * 0.85f;   // SOLVER_USE_WARMSTARTING, warmstartingFactor 0.85
                     } else if (kind != 0) rhs = -rvel * inv;
                     else {
                         float perr = 0.f, verr = -rvel;
@@ -820,14 +823,13 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                         if (lpen > 0.f) verr = -lpen / h; else perr = -lpen * 0.2f / h;
                         rhs = combine ? (perr * inv + verr * inv) : (verr * inv);
                     }
-                    r_rhs[s] = rhs; r_inv[s] = inv;
-                    sLam[rid] = r_lam[s];
+                    sRhs[rid] = rhs; sInv[rid] = inv; sLam[rid] = lam0;
                 }
             }
         }
         __syncwarp();
         // ---- A = J M^-1 J^T, packed lower triangle (overwrites the world-frame / velocity scratch, no longer needed this sub-step)
-        if (NRmax > 0) {
+        {
             int bj[kSlots], tj[kSlots];
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) { const int rid = lane + s * W; bj[s] = (rid < NR) ? sRl[rid] : 0; tj[s] = rid * (rid + 1) / 2; }
@@ -852,56 +854,61 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             }
             __syncwarp();
             // warm start: w = A lambda0
+            const int Pmax = (W == 32) ? P : wmax(P);
+            const int NLmax = (W == 32) ? NL : wmax(NL);
 #pragma unroll 1
-            for (int i = NL; i < NL + ((W == 32) ? P : wmax(P)); ++i) {
-                const float l0 = (i < NL + P) ? sLam[i] : 0.f;
+            for (int p = 0; p < Pmax; ++p) {
+                const int i = NL + p;
+                const float l0 = (p < P) ? sLam[i] : 0.f;
                 const int ti = i * (i + 1) / 2;
 #pragma unroll
                 for (int s = 0; s < kSlots; ++s) {
                     const int rid = lane + s * W;
-                    if (s * W < NRmax && rid < NR && l0 != 0.f) r_w[s] += sA[(rid >= i) ? (rid * (rid + 1) / 2 + i) : (ti + rid)] * l0;
+                    if (s < nslots && rid < NR && l0 != 0.f) r_w[s] += sA[(rid >= i) ? (tj[s] + i) : (ti + rid)] * l0;
                 }
             }
-            // ---- projected Gauss-Seidel, 10 sweeps (btMultiBodyConstraintSolver::solveSingleIteration ordering: limits (alternating), normals, frictions)
-            const float mu = M.friction;
+            // ---- projected Gauss-Seidel, 10 sweeps (btMultiBodyConstraintSolver::solveSingleIteration ordering: limits (alternating), normals,
+            // frictions).  Every lane evaluates the row update from broadcast values; w = A lambda lives in registers, lanes = rows.
+            auto row_update = [&](int i, bool valid, float lo, float hi) {
+                const int owner = i & (W - 1), oslot = i / W;
+                float wsel = r_w[0];
+#pragma unroll
+                for (int s = 1; s < kSlots; ++s) if (oslot == s) wsel = r_w[s];
+                const float wi = T::shfl(wsel, owner);
+                const float lam = sLam[i];
+                float dI = sRhs[i] - wi * sInv[i];
+                float sum = lam + dI;
+                if (sum < lo) { dI = lo - lam; sum = lo; } else if (sum > hi) { dI = hi - lam; sum = hi; }
+                if (!valid) dI = 0.f;
+                if (valid && lane == 0) sLam[i] = sum;
+                const int ti = i * (i + 1) / 2;
+#pragma unroll
+                for (int s = 0; s < kSlots; ++s) {
+                    const int rid = lane + s * W;
+                    if (s < nslots && rid < NR) r_w[s] += sA[(rid >= i) ? (tj[s] + i) : (ti + rid)] * dI;
+                }
+            };
 #pragma unroll 1
             for (int it = 0; it < 10; ++it) {
 #pragma unroll 1
-                for (int u = 0; u < NRmax; ++u) {
-                    const bool valid = u < NR;
-                    const int i = (u < NL) ? ((it & 1) ? u : NL - 1 - u) : u;
-                    const int owner = i & (W - 1), oslot = i / W;
-                    float dI = 0.f;
-                    if (valid && lane == owner) {
-                        float rhs = r_rhs[0], inv = r_inv[0], lam = r_lam[0], w = r_w[0];
-#pragma unroll
-                        for (int s = 1; s < kSlots; ++s) if (oslot == s) { rhs = r_rhs[s]; inv = r_inv[s]; lam = r_lam[s]; w = r_w[s]; }
-                        float lo = 0.f, hi = 1e10f;
-                        bool ok = true;
-                        if (i < NL) hi = 100.f;
-                        else if (i >= NL + P) { const float tot = sLam[NL + ((i - NL - P) >> 1)]; hi = mu * tot; lo = -hi; ok = tot > 0.f; }
-                        if (ok) {
-                            dI = rhs - w * inv;
-                            float sum = lam + dI;
-                            if (sum < lo) { dI = lo - lam; sum = lo; } else if (sum > hi) { dI = hi - lam; sum = hi; }
-#pragma unroll
-                            for (int s = 0; s < kSlots; ++s) if (oslot == s) r_lam[s] = sum;
-                            sLam[i] = sum;
-                        }
-                    }
-                    dI = T::shfl(dI, owner);
-                    const int ti = i * (i + 1) / 2;
-#pragma unroll
-                    for (int s = 0; s < kSlots; ++s) {
-                        const int rid = lane + s * W;
-                        if (s * W < NRmax && rid < NR && valid) r_w[s] += sA[(rid >= i) ? (tj[s] + i) : (ti + rid)] * dI;
-                    }
+                for (int u = 0; u < NLmax; ++u) {
+                    const bool valid = u < NL;
+                    row_update(valid ? ((it & 1) ? u : NL - 1 - u) : 0, valid, 0.f, 100.f);
                     __syncwarp();
                 }
+#pragma unroll 1
+                for (int p = 0; p < Pmax; ++p) row_update((p < P) ? NL + p : 0, p < P, 0.f, 1e10f);
+                __syncwarp();
+#pragma unroll 1
+                for (int f = 0; f < 2 * Pmax; ++f) {
+                    const bool valid = f < 2 * P;
+                    const float tot = valid ? sLam[NL + (f >> 1)] : 0.f;
+                    row_update(valid ? NL + P + f : 0, valid && tot > 0.f, -mu * tot, mu * tot);
+                }
+                __syncwarp();
             }
         }
         // write impulses back to the manifold (warm start of the next sub-step)
-        __syncwarp();
 #pragma unroll 1
         for (int p = lane; p < P; p += W) {
             if (alive) {
@@ -911,7 +918,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             }
         }
         // ---- z = Y^T lambda (lanes = chain depth), then dv = L^-1 D^-1/2 z by the root -> leaves pass
-        if (NRmax > 0) {
+        {
 #pragma unroll 1
             for (int k = lane; k < n; k += W) sZ[k] = 0.f;
             __syncwarp();
@@ -942,30 +949,30 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             float z0 = 0.f, z1 = 0.f, z2 = 0.f;
             if (ndof >= 1) z0 = sZ[dof0] * sqrtf(inv0);
             if (ndof == 3) { z1 = sZ[dof0 + 1] * sqrtf(inv1); z2 = sZ[dof0 + 2] * sqrtf(inv2); }
-            if (lane == 0) al = descend(xm(R, cvec, dB), z0, z1, z2);
+            if (lane == 0) al = descend(shift_m(dB, cw), z0, z1, z2);
 #pragma unroll 1
             for (int lv = 1; lv <= maxlevel; ++lv) {
                 S6 pa = T::shfl6(al, plane);
-                if (level == lv) al = descend(xm(R, cvec, pa), z0, z1, z2);
+                if (level == lv) al = descend(shift_m(pa, cw), z0, z1, z2);
             }
-            V3 dw = mulT(Rwb, mk3(T::shfl(dB.a.x, 0), T::shfl(dB.a.y, 0), T::shfl(dB.a.z, 0)));
-            V3 dv = mulT(Rwb, mk3(T::shfl(dB.l.x, 0), T::shfl(dB.l.y, 0), T::shfl(dB.l.z, 0)));
-            auto cl = [](float v) { return fminf(fmaxf(v, -100.f), 100.f); };
+            const V3 dwb = T::shfl3(dB.a, 0), dvb = T::shfl3(dB.l, 0);
             if (NR > 0) {
-                baseOmega = mk3(cl(baseOmega.x + dw.x), cl(baseOmega.y + dw.y), cl(baseOmega.z + dw.z));
-                baseVel = mk3(cl(baseVel.x + dv.x), cl(baseVel.y + dv.y), cl(baseVel.z + dv.z));
-                if (ndof >= 1) jv.x = cl(jv.x + qd0);
-                if (ndof == 3) { jv.y = cl(jv.y + qd1); jv.z = cl(jv.z + qd2); }
+                baseOmega = mk3(cl100(baseOmega.x + dwb.x), cl100(baseOmega.y + dwb.y), cl100(baseOmega.z + dwb.z));
+                baseVel = mk3(cl100(baseVel.x + dvb.x), cl100(baseVel.y + dvb.y), cl100(baseVel.z + dvb.z));
+                if (ndof >= 1) jv.x = cl100(jv.x + qd0);
+                if (ndof == 3) { jv.y = cl100(jv.y + qd1); jv.z = cl100(jv.z + qd2); }
             }
         }
+        if (DEBUG && dbg && first_upd) {   // impulses in the order [normals | friction pairs | limits]
+            const int lo_ = (sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024) + 1;
+            for (int k = lane; k < NR && k < 60; k += W) { const int src = (k < 3 * P) ? NL + k : k - 3 * P; dbg[lo_ + k] = sLam[src]; }
+        }
+        }   // anyrow
         if (DEBUG && dbg && first_upd) {
             const int o = (sub == 0 ? 6 * kMaxDofs : 10 * kMaxDofs + 1024);
             if (lane == 0) { dbg[o] = baseOmega.x; dbg[o + 1] = baseOmega.y; dbg[o + 2] = baseOmega.z; dbg[o + 3] = baseVel.x; dbg[o + 4] = baseVel.y; dbg[o + 5] = baseVel.z; }
             if (ndof >= 1) dbg[o + dof0] = jv.x;
             if (ndof == 3) { dbg[o + dof0 + 1] = jv.y; dbg[o + dof0 + 2] = jv.z; }
-            // impulses in the order [normals | friction pairs | limits]
-            const int lo_ = (sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024) + 1;
-            for (int k = lane; k < NR && k < 60; k += W) { const int src = (k < 3 * P) ? NL + k : k - 3 * P; dbg[lo_ + k] = sLam[src]; }
         }
         // ---- integrate positions (btMultiBody::stepPositionsMultiDof)
         basePos = basePos + h * baseVel;
