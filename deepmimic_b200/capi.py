@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-_LIB_PATH = os.path.join(_REPO, "deepmimic_b200", "libdeepmimic_b200.so")
+_LIB_PATH = os.environ.get("DM_LIB", os.path.join(_REPO, "deepmimic_b200", "libdeepmimic_b200.so"))   # DM_LIB: profile build (tools/section_profile.py)
 _lib = None
 
 

@@ -374,7 +374,7 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
         h->tiles = tiles;
         const int quantum = (tiles * (64 / h->W)) / std::__gcd(tiles, 64 / h->W);   // multiple of both the update block and the 64-thread policy blocks
         h->padded_envs = ((num_envs + quantum - 1) / quantum) * quantum;
-        h->smem_bytes = h->kernel == 3 ? dmk::dm_step_smem_bytes(h->lay, h->tiles) : dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, h->tiles);
+        h->smem_bytes = h->kernel == 3 ? dmk::dm_step_smem_bytes(h->lay, h->tiles) + 1024 : dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, h->tiles);
     }
     const size_t N = static_cast<size_t>(h->padded_envs);
     const int ss = dmk::sim_stride(M.nl);
@@ -477,7 +477,10 @@ int dm_set_action(dm_handle* h, const float* d_actions) {
 }
 int dm_update(dm_handle* h, double dt, int n_updates) {
     DM_DEVICE(h);
-    const bool dbg = h->st.pdbg != nullptr;
+    bool dbg = h->st.pdbg != nullptr;
+#ifdef DM_PROFILE
+    dbg = false;   // profile build: the production kernel writes its per-warp section counters into the debug buffer
+#endif
     if (h->W == 16) return dbg ? launch_update<16, true>(h, dt, n_updates) : launch_update<16, false>(h, dt, n_updates);
     return dbg ? launch_update<32, true>(h, dt, n_updates) : launch_update<32, false>(h, dt, n_updates);
 }

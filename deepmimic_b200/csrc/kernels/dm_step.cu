@@ -131,10 +131,219 @@ int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L) {
     L->oG = o; o += 21 + 9 + 2;                    // base Cholesky factor (21), world->base rotation (9)
     L->oZ = o; o += ((n + 3) / 4) * 4;
     L->env_floats = ((o + 15) / 32) * 32 + 16;     // stride == 16 (mod 32 banks): the two environments of a warp (W = 16) hit disjoint bank halves
-    L->hot_floats = ((nl * kLkFloats + (nl * nl + nl * chain_len + 3) / 4 + 8 + 3) / 4) * 4;
+    L->hot_floats = ((nl * kLkFloats + (nl * nl + nl * chain_len + 3) / 4 + 8 + 24 + 3) / 4) * 4;
     return L->hot_floats * 4 + 0;
 }
 int dm_step_smem_bytes(const StepLayout& L, int tiles) { return (L.hot_floats + L.env_floats * tiles) * static_cast<int>(sizeof(float)); }
+
+// Constraint rows of one Bullet sub-step for the environment owned by this tile (warp-collective; both environments of a W = 16 warp
+// run it in lockstep).  Input (shared memory): per-link factors U / 1/D, joint axes, pivots, link velocities, contact points, limit
+// rows, base Cholesky factor.  Output: impulses in sLam (also written to the persistent manifold), z = Y^T lambda in sZ.
+// Row ids in solver order: limits [0,NL) | normals [NL, NL+P) | friction pairs NL+P+2p+{0,1} (t1 = -x, t2 = +z).
+template <int W>
+__device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* LK, const unsigned char* CD, const unsigned char* CH, int lane, int NL, int P, float h,
+                                        float mu, float* mani, int alive) {
+    using T = Tl<W>;
+    const StepLayout& LY = *reinterpret_cast<const StepLayout*>(LYS);
+    const int nl = LY.nl, n = LY.n, CL = LY.chain_len, MR = LY.maxrows;
+    float* sU = E + LY.oU; float* sS = E + LY.oR; float* sW = E + LY.oW; float* sV = E + LY.oV; float* sA = E + LY.oA; float* sY = E + LY.oY;
+    float* sLam = E + LY.oLam; float* sRhs = E + LY.oRhs; float* sInv = E + LY.oInv; int* sRl = reinterpret_cast<int*>(E + LY.oRl);
+    float* sPp = E + LY.oPp; float* sPi = E + LY.oPi; int* sPr = reinterpret_cast<int*>(E + LY.oPr);
+    float* sQ = E + LY.oQ; float* sG = E + LY.oG; float* sZ = E + LY.oZ;
+    auto lk_i = [&](int j) { return reinterpret_cast<const int*>(LK + j * kLkFloats)[kLInt]; };
+    auto lk_i2 = [&](int j) { return reinterpret_cast<const int*>(LK + j * kLkFloats)[kLInt2]; };
+    auto shift_f = [](S6 f, V3 c) { return mks(f.a + cross(c, f.l), f.l); };
+    const int NR = NL + 3 * P;
+    const int NRmax = (W == 32) ? NR : wmax(NR);
+    const int nslots = (NRmax + W - 1) / W;
+    constexpr int kSlots = (W == 16) ? 3 : 2;
+    float r_w[kSlots];
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) {
+        r_w[s] = 0.f;
+        const int rid = lane + s * W;
+        if (s < nslots) {
+            const bool rv_ = rid < NR;
+            int b = 0, kind = 0 /*0 limit 1 normal 2 t1 3 t2*/, p = 0;
+            float lsign = 1.f, lpen = 0.f;
+            if (rv_) {
+                if (rid < NL) { b = __float_as_int(sQ[rid]); lsign = sQ[8 + rid]; lpen = sQ[16 + rid]; }
+                else if (rid < NL + P) { kind = 1; p = rid - NL; b = sPr[p] >> 2; }
+                else { const int f = rid - NL - P; p = f >> 1; kind = 2 + (f & 1); b = sPr[p] >> 2; }
+                sRl[rid] = b;
+            }
+            // unit force of the row on link b, about b's pivot, world axes
+            S6 f = mks(mk3(0, 0, 0), mk3(0, 0, 0));
+            float rvel = 0.f, pdist = 0.f;
+            if (rv_ && kind != 0) {
+                const float* w = sW + b * 12;
+                pdist = sPp[p * 4 + 3];
+                const V3 rel = mk3(sPp[p * 4] - w[9], sPp[p * 4 + 1] - w[10], sPp[p * 4 + 2] - w[11]);
+                const V3 fl_ = (kind == 1) ? mk3(0.f, 1.f, 0.f) : ((kind == 2) ? mk3(-1.f, 0.f, 0.f) : mk3(0.f, 0.f, 1.f));
+                f = mks(cross(rel, fl_), fl_);
+                const float* v = sV + b * 8;
+                rvel = dot(fl_, mk3(v[3], v[4], v[5]) + cross(mk3(v[0], v[1], v[2]), rel));
+            }
+            // walk the chain base <- ... <- b
+            float acc = 0.f;
+            int cur = b;
+            bool first = true;
+#pragma unroll 1
+            while (true) {
+                const int info = lk_i(cur);
+                const int par = static_cast<int>(static_cast<signed char>(info & 0xff)), nd = (info >> 16) & 0xff, dp0 = (info >> 24) & 0xff;
+                const float* u = sU + cur * 24;
+                const float* q = sS + cur * 12;
+#pragma unroll 1
+                for (int d = nd - 1; d >= 0; --d) {
+                    float t = q[d * 3] * f.a.x + q[d * 3 + 1] * f.a.y + q[d * 3 + 2] * f.a.z;
+                    if (first && kind == 0) { t = lsign; rvel = lsign * sQ[24 + rid]; }
+                    const float y = t * u[21 + d];
+                    if (rv_) sY[(dp0 + d) * MR + rid] = y;
+                    acc += y * y;
+                    const float ti = t * u[18 + d];
+                    f.a.x -= ti * u[d * 6]; f.a.y -= ti * u[d * 6 + 1]; f.a.z -= ti * u[d * 6 + 2]; f.l.x -= ti * u[d * 6 + 3]; f.l.y -= ti * u[d * 6 + 4]; f.l.z -= ti * u[d * 6 + 5];
+                }
+                first = false;
+                f = shift_f(f, mk3(q[9], q[10], q[11]));
+                if (par < 0) break;
+                cur = par;
+            }
+            {   // base block: y = G^-1 f
+                float x[6] = {f.a.x, f.a.y, f.a.z, f.l.x, f.l.y, f.l.z};
+                int o = 0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                    for (int k = 0; k < i; ++k) x[i] -= sG[o++] * x[k];
+                    x[i] *= sG[15 + i];
+                    if (rv_) sY[i * MR + rid] = x[i];
+                    acc += x[i] * x[i];
+                }
+            }
+            if (rv_) {
+                const float inv = acc > 1.1920929e-7f ? 1.0f / acc : 0.f;
+                float rhs, lam0 = 0.f;
+                if (kind == 1) {   // setupMultiBodyContactConstraint: erp 0.2, restitution 0, no split impulse for multibodies
+                    float perr = 0.f, verr = -rvel;
+                    if (pdist > 0.f) verr -= pdist / h; else perr = -pdist * 0.2f / h;
+                    rhs = perr * inv + verr * inv;
+                    lam0 = sPi[p] * 0.85f;   // SOLVER_USE_WARMSTARTING, warmstartingFactor 0.85
+                } else if (kind != 0) rhs = -rvel * inv;
+                else {
+                    float perr = 0.f, verr = -rvel;
+                    const bool combine = lpen > -0.04f;   // split-impulse threshold: deeper violations lose the positional term (btMultiBodyJointLimitConstraint)
+                    if (lpen > 0.f) verr = -lpen / h; else perr = -lpen * 0.2f / h;
+                    rhs = combine ? (perr * inv + verr * inv) : (verr * inv);
+                }
+                sRhs[rid] = rhs; sInv[rid] = inv; sLam[rid] = lam0;
+            }
+        }
+    }
+    __syncwarp();
+    // ---- A = J M^-1 J^T, packed lower triangle (overwrites the world-frame / velocity scratch, no longer needed this sub-step)
+    int bj[kSlots], tj[kSlots];
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) { const int rid = lane + s * W; bj[s] = (rid < NR) ? sRl[rid] : 0; tj[s] = rid * (rid + 1) / 2; }
+    __syncwarp();
+#pragma unroll 1
+    for (int i = 0; i < NRmax; ++i) {
+        const bool iv = i < NR;
+        const int bi = iv ? sRl[i] : 0;
+        const unsigned char* cdr = CD + bi * nl;
+        const int ti = i * (i + 1) / 2;
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+            const int rid = lane + s * W;
+            if (s * W <= i) {   // only rows j <= i are stored
+                const int cd = (iv && rid <= i) ? cdr[bj[s]] : 0;
+                float acc = 0.f;
+#pragma unroll 1
+                for (int k = 0; k < cd; ++k) acc += sY[k * MR + i] * sY[k * MR + rid];
+                if (iv && rid <= i) sA[ti + rid] = acc;
+            }
+        }
+    }
+    __syncwarp();
+    // warm start: w = A lambda0
+    const int Pmax = (W == 32) ? P : wmax(P);
+    const int NLmax = (W == 32) ? NL : wmax(NL);
+#pragma unroll 1
+    for (int p = 0; p < Pmax; ++p) {
+        const int i = NL + p;
+        const float l0 = (p < P) ? sLam[i] : 0.f;
+        const int ti = i * (i + 1) / 2;
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+            const int rid = lane + s * W;
+            if (s < nslots && rid < NR && l0 != 0.f) r_w[s] += sA[(rid >= i) ? (tj[s] + i) : (ti + rid)] * l0;
+        }
+    }
+    // ---- projected Gauss-Seidel, 10 sweeps (btMultiBodyConstraintSolver::solveSingleIteration ordering: limits (alternating), normals,
+    // frictions).  Every lane evaluates the row update from broadcast values; w = A lambda lives in registers, lanes = rows.
+    auto row_update = [&](int i, bool valid, float lo, float hi) {
+        const int owner = i & (W - 1), oslot = i / W;
+        float wsel = r_w[0];
+#pragma unroll
+        for (int s = 1; s < kSlots; ++s) if (oslot == s) wsel = r_w[s];
+        const float wi = T::shfl(wsel, owner);
+        const float lam = sLam[i];
+        float dI = sRhs[i] - wi * sInv[i];
+        float sum = lam + dI;
+        if (sum < lo) { dI = lo - lam; sum = lo; } else if (sum > hi) { dI = hi - lam; sum = hi; }
+        if (!valid) dI = 0.f;
+        if (valid && lane == 0) sLam[i] = sum;
+        const int ti = i * (i + 1) / 2;
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+            const int rid = lane + s * W;
+            if (s < nslots && rid < NR) r_w[s] += sA[(rid >= i) ? (tj[s] + i) : (ti + rid)] * dI;
+        }
+    };
+#pragma unroll 1
+    for (int it = 0; it < 10; ++it) {
+#pragma unroll 1
+        for (int u = 0; u < NLmax; ++u) {
+            const bool valid = u < NL;
+            row_update(valid ? ((it & 1) ? u : NL - 1 - u) : 0, valid, 0.f, 100.f);
+            __syncwarp();
+        }
+#pragma unroll 1
+        for (int p = 0; p < Pmax; ++p) row_update((p < P) ? NL + p : 0, p < P, 0.f, 1e10f);
+        __syncwarp();
+#pragma unroll 1
+        for (int f = 0; f < 2 * Pmax; ++f) {
+            const bool valid = f < 2 * P;
+            const float tot = valid ? sLam[NL + (f >> 1)] : 0.f;
+            row_update(valid ? NL + P + f : 0, valid && tot > 0.f, -mu * tot, mu * tot);
+        }
+        __syncwarp();
+    }
+    // write impulses back to the manifold (warm start of the next sub-step)
+#pragma unroll 1
+    for (int p = lane; p < P; p += W) {
+        if (alive) {
+            const int ref = sPr[p];
+            float* mpt = mani + (ref >> 2) * kManifoldFloats + (ref & 3) * 12;
+            mpt[7] = sLam[NL + p]; mpt[8] = sLam[NL + P + 2 * p]; mpt[9] = sLam[NL + P + 2 * p + 1];
+        }
+    }
+    // ---- z = Y^T lambda (lanes = chain depth)
+#pragma unroll 1
+    for (int k = lane; k < n; k += W) sZ[k] = 0.f;
+    __syncwarp();
+#pragma unroll 1
+    for (int i = 0; i < NRmax; ++i) {
+        if (i < NR) {
+            const int b = sRl[i];
+            const int lastd = (lk_i2(b) >> 8) & 0xff;
+#pragma unroll 1
+            for (int k = lane; k <= lastd; k += W) sZ[CH[b * CL + k]] += sY[k * MR + i] * sLam[i];
+        }
+        __syncwarp();
+    }
+}
+
 
 template <int W, bool DEBUG>
 __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevModel* __restrict__ gm, DevState st, const double* __restrict__ frame_times,
@@ -156,6 +365,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     unsigned char* CD = reinterpret_cast<unsigned char*>(sm + nl * kLkFloats);
     unsigned char* CH = CD + nl * nl;
     int* LVC = reinterpret_cast<int*>(sm + LY.hot_floats - 8);
+    int* LYS = reinterpret_cast<int*>(sm + LY.hot_floats - 8 - 24);   // shared copy of the layout for the non-inlined routines
     for (int j = threadIdx.x; j < nl; j += blockDim.x) {
         const DevLink& K = M.link[j];
         float* q = LK + j * kLkFloats;
@@ -180,6 +390,10 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             while (c <= lim && M.chain_dof[j][c] == M.chain_dof[b][c]) ++c;
             CD[j * nl + b] = static_cast<unsigned char>(c);
         }
+    }
+    if (threadIdx.x == blockDim.x - 1) {
+        const int* src = reinterpret_cast<const int*>(&LY);
+        for (int k = 0; k < static_cast<int>(sizeof(StepLayout) / sizeof(int)); ++k) LYS[k] = src[k];
     }
     if (threadIdx.x < 8) {
         int mx = 0;
@@ -246,6 +460,15 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     auto shift_m = [](S6 m, V3 c) { return mks(m.a, m.l + cross(m.a, c)); };   // motion vector: reference point moved by +c
     auto shift_f = [](S6 f, V3 c) { return mks(f.a + cross(c, f.l), f.l); };   // force vector: reference point moved by -c (child pivot -> parent pivot)
 
+#ifdef DM_PROFILE
+    // per-warp cycle counters per code section (profile build only): lane 0 accumulates, written to st.pdbg at the end
+    unsigned int* PRF = reinterpret_cast<unsigned int*>(sm + LY.hot_floats + tiles * LY.env_floats) + (threadIdx.x / 32) * 16;
+    if ((threadIdx.x & 31) == 0) for (int k = 0; k < 16; ++k) PRF[k] = 0u;
+    unsigned int prf_t = static_cast<unsigned int>(clock64());
+#define PROF(sec) do { if ((threadIdx.x & 31) == 0) { unsigned int t_ = static_cast<unsigned int>(clock64()); PRF[sec] += t_ - prf_t; prf_t = t_; } } while (0)
+#else
+#define PROF(sec) do { } while (0)
+#endif
     bool need_kin = true, pending_flags = false;
     const int stages_per_upd = sim_substeps + 1;
     const int total_stages = n_updates * stages_per_upd;
@@ -298,6 +521,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             }
             __syncwarp();
         }
+        PROF(0);
         // =================================================================== post-update flags of the update that just finished
         if (pending_flags) {
             pending_flags = false;
@@ -340,8 +564,11 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 if (end) alive = false;
             }
         }
+        PROF(1);
         if (stage == total_stages) break;
         if (sync_period != 0 && (stage % sync_period) == 0) { if (__syncthreads_and(!alive)) break; }
+        PROF(2);
+        if (__ballot_sync(0xffffffffu, alive) == 0u) continue;   // both environments of this warp are frozen
         const int ph = stage % stages_per_upd;      // 0: Stable-PD stage, 1..sim_substeps: Bullet sub-steps
         const bool first_upd = stage < stages_per_upd;
         int P = 0;
@@ -461,7 +688,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                     cnt--;
                 }
             }
-            if (!act) cnt = 0;
+            if (!act || !alive) cnt = 0;   // finished episodes are frozen until dm_reset: no constraint rows for them
             in_contact_tol = false;   // cContactManager::Update: distance <= 0.001 * scale
 #pragma unroll
             for (int c = 0; c < 4; ++c) if (c < cnt && mp[c * 12 + 10] <= 0.001f * scale) in_contact_tol = true;
@@ -488,6 +715,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             P = min(T::shfli(incl, W - 1), LY.maxpts);
         }
 
+        PROF(3);
         // =================================================================== bias accelerations (root -> leaves), Stable-PD right-hand side
         const bool bullet = ph != 0;
         V3 jww = mk3(0, 0, 0);   // joint angular velocity, world axes
@@ -605,6 +833,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 if (take) { pA.a += gf.a; pA.l += gf.l; }
             }
         }
+        PROF(4);
         // ---- base: the (massless) floating base carries the root link's articulated inertia; Cholesky of the 6x6 in world axes at the base
         // origin, i.e. directly in the generalised base coordinates [omega_w, v_w]
         S6 aB = mks(mk3(0, 0, 0), mk3(0, 0, 0));
@@ -654,6 +883,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 for (int i = 0; i < 6; ++i) sG[15 + i] = gi[i];
             }
         }
+        PROF(5);
         // ---- accelerations (root -> leaves): qdd_d = (u_d - U_d . a') / D_d
         float qd0 = 0.f, qd1 = 0.f, qd2 = 0.f;
         S6 al = mks(mk3(0, 0, 0), mk3(0, 0, 0));   // link acceleration (deviation from the bias acceleration)
@@ -678,6 +908,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             const float mag = sqrtf(t0 * t0 + t1 * t1 + t2 * t2), tlim = LKo[kLTl];
             if (mag > tlim) { float s = tlim / mag; t0 *= s; t1 *= s; t2 *= s; }
             tau0 = t0; tau1 = t1; tau2 = t2;
+            PROF(6);
             if (DEBUG && dbg && first_upd) {
                 if (ndof >= 1) { dbg[2 * kMaxDofs + dof0] = t0; dbg[3 * kMaxDofs + dof0] = qd0; }
                 if (ndof == 3) { dbg[2 * kMaxDofs + dof0 + 1] = t1; dbg[2 * kMaxDofs + dof0 + 2] = t2; dbg[3 * kMaxDofs + dof0 + 1] = qd1; dbg[3 * kMaxDofs + dof0 + 2] = qd2; }
@@ -710,9 +941,10 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 if (ndof == 3) { dbg[o + dof0 + 1] = jv.y; dbg[o + dof0 + 2] = jv.z; }
             }
         }
+        PROF(6);
         // ---- joint-limit rows (btMultiBodyJointLimitConstraint): a lane owns at most one active row
         int lim_dir = 0; float lim_pen = 0.f;
-        if (act && has_limit) {
+        if (act && has_limit && alive) {
             float p0 = jp.x - LKo[kLLo], p1 = LKo[kLHi] - jp.x;
             if (!(p0 > 0.f)) { lim_dir = 1; lim_pen = p0; }
             else if (!(p1 > 0.f)) { lim_dir = -1; lim_pen = p1; }
@@ -739,199 +971,13 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         }
         if (NL + 3 * P > MR) { P = (MR - NL) / 3; f_over = 1; }
         const int NR = NL + 3 * P;
-        const int NRmax = (W == 32) ? NR : wmax(NR);
-        const int nslots = (NRmax + W - 1) / W;
         __syncwarp();
-        // row ids in solver order: limits [0,NL) | normals [NL, NL+P) | friction pairs NL+P+2p+{0,1} (t1 = -x, t2 = +z)
-        constexpr int kSlots = (W == 16) ? 3 : 2;
-        float r_w[kSlots];
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) {
-            r_w[s] = 0.f;
-            const int rid = lane + s * W;
-            if (s < nslots) {
-                const bool rv_ = rid < NR;
-                int b = 0, kind = 0 /*0 limit 1 normal 2 t1 3 t2*/, p = 0;
-                float lsign = 1.f, lpen = 0.f;
-                if (rv_) {
-                    if (rid < NL) { b = __float_as_int(sQ[rid]); lsign = sQ[8 + rid]; lpen = sQ[16 + rid]; }
-                    else if (rid < NL + P) { kind = 1; p = rid - NL; b = sPr[p] >> 2; }
-                    else { const int f = rid - NL - P; p = f >> 1; kind = 2 + (f & 1); b = sPr[p] >> 2; }
-                    sRl[rid] = b;
-                }
-                // unit force of the row on link b, about b's pivot, world axes
-                S6 f = mks(mk3(0, 0, 0), mk3(0, 0, 0));
-                float rvel = 0.f, pdist = 0.f;
-                if (rv_ && kind != 0) {
-                    const float* w = sW + b * 12;
-                    pdist = sPp[p * 4 + 3];
-                    const V3 rel = mk3(sPp[p * 4] - w[9], sPp[p * 4 + 1] - w[10], sPp[p * 4 + 2] - w[11]);
-                    const V3 fl_ = (kind == 1) ? mk3(0.f, 1.f, 0.f) : ((kind == 2) ? mk3(-1.f, 0.f, 0.f) : mk3(0.f, 0.f, 1.f));
-                    f = mks(cross(rel, fl_), fl_);
-                    const float* v = sV + b * 8;
-                    rvel = dot(fl_, mk3(v[3], v[4], v[5]) + cross(mk3(v[0], v[1], v[2]), rel));
-                }
-                // walk the chain base <- ... <- b
-                float acc = 0.f;
-                int cur = b;
-                bool first = true;
-#pragma unroll 1
-                while (true) {
-                    const int info = lk_i(cur);
-                    const int par = static_cast<int>(static_cast<signed char>(info & 0xff)), nd = (info >> 16) & 0xff, dp0 = (info >> 24) & 0xff;
-                    const float* u = sU + cur * 24;
-                    const float* q = sS + cur * 12;
-#pragma unroll 1
-                    for (int d = nd - 1; d >= 0; --d) {
-                        float t = q[d * 3] * f.a.x + q[d * 3 + 1] * f.a.y + q[d * 3 + 2] * f.a.z;
-                        if (first && kind == 0) { t = lsign; rvel = lsign * sQ[24 + rid]; }
-                        const float y = t * u[21 + d];
-                        if (rv_) sY[(dp0 + d) * MR + rid] = y;
-                        acc += y * y;
-                        const float ti = t * u[18 + d];
-                        f.a.x -= ti * u[d * 6]; f.a.y -= ti * u[d * 6 + 1]; f.a.z -= ti * u[d * 6 + 2]; f.l.x -= ti * u[d * 6 + 3]; f.l.y -= ti * u[d * 6 + 4]; f.l.z -= ti * u[d * 6 + 5];
-                    }
-                    first = false;
-                    f = shift_f(f, mk3(q[9], q[10], q[11]));
-                    if (par < 0) break;
-                    cur = par;
-                }
-                {   // base block: y = G^-1 f
-                    float x[6] = {f.a.x, f.a.y, f.a.z, f.l.x, f.l.y, f.l.z};
-                    int o = 0;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) {
-#pragma unroll
-                        for (int k = 0; k < i; ++k) x[i] -= sG[o++] * x[k];
-                        x[i] *= sG[15 + i];
-                        if (rv_) sY[i * MR + rid] = x[i];
-                        acc += x[i] * x[i];
-                    }
-                }
-                if (rv_) {
-                    const float inv = acc > 1.1920929e-7f ? 1.0f / acc : 0.f;
-                    float rhs, lam0 = 0.f;
-                    if (kind == 1) {   // setupMultiBodyContactConstraint: erp 0.2, restitution 0, no split impulse for multibodies
-                        float perr = 0.f, verr = -rvel;
-                        if (pdist > 0.f) verr -= pdist / h; else perr = -pdist * 0.2f / h;
-                        rhs = perr * inv + verr * inv;
-                        lam0 = sPi[p] * 0.85f;   // SOLVER_USE_WARMSTARTING, warmstartingFactor 0.85
-                    } else if (kind != 0) rhs = -rvel * inv;
-                    else {
-                        float perr = 0.f, verr = -rvel;
-                        const bool combine = lpen > -0.04f;   // split-impulse threshold: deeper violations lose the positional term (btMultiBodyJointLimitConstraint)
-                        if (lpen > 0.f) verr = -lpen / h; else perr = -lpen * 0.2f / h;
-                        rhs = combine ? (perr * inv + verr * inv) : (verr * inv);
-                    }
-                    sRhs[rid] = rhs; sInv[rid] = inv; sLam[rid] = lam0;
-                }
-            }
-        }
-        __syncwarp();
-        // ---- A = J M^-1 J^T, packed lower triangle (overwrites the world-frame / velocity scratch, no longer needed this sub-step)
+        PROF(7);
+        // rows, J M^-1 J^T, projected Gauss-Seidel and z = Y^T lambda: a separate (non-inlined) warp-collective routine with its own
+        // register budget -- it only needs this environment's shared-memory block
+        solve_rows<W>(E, LYS, LK, CD, CH, lane, NL, P, h, mu, mani, alive ? 1 : 0);
+        PROF(10);
         {
-            int bj[kSlots], tj[kSlots];
-#pragma unroll
-            for (int s = 0; s < kSlots; ++s) { const int rid = lane + s * W; bj[s] = (rid < NR) ? sRl[rid] : 0; tj[s] = rid * (rid + 1) / 2; }
-            __syncwarp();
-#pragma unroll 1
-            for (int i = 0; i < NRmax; ++i) {
-                const bool iv = i < NR;
-                const int bi = iv ? sRl[i] : 0;
-                const unsigned char* cdr = CD + bi * nl;
-                const int ti = i * (i + 1) / 2;
-#pragma unroll
-                for (int s = 0; s < kSlots; ++s) {
-                    const int rid = lane + s * W;
-                    if (s * W <= i) {   // only rows j <= i are stored
-                        const int cd = (iv && rid <= i) ? cdr[bj[s]] : 0;
-                        float acc = 0.f;
-#pragma unroll 1
-                        for (int k = 0; k < cd; ++k) acc += sY[k * MR + i] * sY[k * MR + rid];
-                        if (iv && rid <= i) sA[ti + rid] = acc;
-                    }
-                }
-            }
-            __syncwarp();
-            // warm start: w = A lambda0
-            const int Pmax = (W == 32) ? P : wmax(P);
-            const int NLmax = (W == 32) ? NL : wmax(NL);
-#pragma unroll 1
-            for (int p = 0; p < Pmax; ++p) {
-                const int i = NL + p;
-                const float l0 = (p < P) ? sLam[i] : 0.f;
-                const int ti = i * (i + 1) / 2;
-#pragma unroll
-                for (int s = 0; s < kSlots; ++s) {
-                    const int rid = lane + s * W;
-                    if (s < nslots && rid < NR && l0 != 0.f) r_w[s] += sA[(rid >= i) ? (tj[s] + i) : (ti + rid)] * l0;
-                }
-            }
-            // ---- projected Gauss-Seidel, 10 sweeps (btMultiBodyConstraintSolver::solveSingleIteration ordering: limits (alternating), normals,
-            // frictions).  Every lane evaluates the row update from broadcast values; w = A lambda lives in registers, lanes = rows.
-            auto row_update = [&](int i, bool valid, float lo, float hi) {
-                const int owner = i & (W - 1), oslot = i / W;
-                float wsel = r_w[0];
-#pragma unroll
-                for (int s = 1; s < kSlots; ++s) if (oslot == s) wsel = r_w[s];
-                const float wi = T::shfl(wsel, owner);
-                const float lam = sLam[i];
-                float dI = sRhs[i] - wi * sInv[i];
-                float sum = lam + dI;
-                if (sum < lo) { dI = lo - lam; sum = lo; } else if (sum > hi) { dI = hi - lam; sum = hi; }
-                if (!valid) dI = 0.f;
-                if (valid && lane == 0) sLam[i] = sum;
-                const int ti = i * (i + 1) / 2;
-#pragma unroll
-                for (int s = 0; s < kSlots; ++s) {
-                    const int rid = lane + s * W;
-                    if (s < nslots && rid < NR) r_w[s] += sA[(rid >= i) ? (tj[s] + i) : (ti + rid)] * dI;
-                }
-            };
-#pragma unroll 1
-            for (int it = 0; it < 10; ++it) {
-#pragma unroll 1
-                for (int u = 0; u < NLmax; ++u) {
-                    const bool valid = u < NL;
-                    row_update(valid ? ((it & 1) ? u : NL - 1 - u) : 0, valid, 0.f, 100.f);
-                    __syncwarp();
-                }
-#pragma unroll 1
-                for (int p = 0; p < Pmax; ++p) row_update((p < P) ? NL + p : 0, p < P, 0.f, 1e10f);
-                __syncwarp();
-#pragma unroll 1
-                for (int f = 0; f < 2 * Pmax; ++f) {
-                    const bool valid = f < 2 * P;
-                    const float tot = valid ? sLam[NL + (f >> 1)] : 0.f;
-                    row_update(valid ? NL + P + f : 0, valid && tot > 0.f, -mu * tot, mu * tot);
-                }
-                __syncwarp();
-            }
-        }
-        // write impulses back to the manifold (warm start of the next sub-step)
-#pragma unroll 1
-        for (int p = lane; p < P; p += W) {
-            if (alive) {
-                const int ref = sPr[p];
-                float* mpt = mani + (ref >> 2) * kManifoldFloats + (ref & 3) * 12;
-                mpt[7] = sLam[NL + p]; mpt[8] = sLam[NL + P + 2 * p]; mpt[9] = sLam[NL + P + 2 * p + 1];
-            }
-        }
-        // ---- z = Y^T lambda (lanes = chain depth), then dv = L^-1 D^-1/2 z by the root -> leaves pass
-        {
-#pragma unroll 1
-            for (int k = lane; k < n; k += W) sZ[k] = 0.f;
-            __syncwarp();
-#pragma unroll 1
-            for (int i = 0; i < NRmax; ++i) {
-                if (i < NR) {
-                    const int b = sRl[i];
-                    const int lastd = (lk_i2(b) >> 8) & 0xff;
-#pragma unroll 1
-                    for (int k = lane; k <= lastd; k += W) sZ[CH[b * CL + k]] += sY[k * MR + i] * sLam[i];
-                }
-                __syncwarp();
-            }
             S6 dB = mks(mk3(0, 0, 0), mk3(0, 0, 0));
             if (lane == 0) {   // base: dB = G^-T z
                 float x[6] = {sZ[0], sZ[1], sZ[2], sZ[3], sZ[4], sZ[5]};
@@ -967,6 +1013,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             const int lo_ = (sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024) + 1;
             for (int k = lane; k < NR && k < 60; k += W) { const int src = (k < 3 * P) ? NL + k : k - 3 * P; dbg[lo_ + k] = sLam[src]; }
         }
+        PROF(11);
         }   // anyrow
         if (DEBUG && dbg && first_upd) {
             const int o = (sub == 0 ? 6 * kMaxDofs : 10 * kMaxDofs + 1024);
@@ -982,7 +1029,12 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         __syncwarp();
         need_kin = true;
         if (ph == sim_substeps) pending_flags = true;
+        PROF(12);
     }
+#ifdef DM_PROFILE
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0 && st.pdbg) { unsigned int* o = reinterpret_cast<unsigned int*>(st.pdbg) + (blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32) * 16; for (int k = 0; k < 16; ++k) o[k] = PRF[k]; }
+#endif
 }
 
 // explicit instantiations used by capi.cu: (tile width, debug dumps)
