@@ -142,8 +142,14 @@ int dm_step_smem_bytes(const StepLayout& L, int tiles) { return (L.hot_floats + 
 // Row ids in solver order: limits [0,NL) | normals [NL, NL+P) | friction pairs NL+P+2p+{0,1} (t1 = -x, t2 = +z).
 template <int W>
 __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* LK, const unsigned char* CD, const unsigned char* CH, int lane, int NL, int P, float h,
-                                        float mu, float* mani, int alive) {
+                                        float mu, float* mani, int alive, unsigned int* prf) {
     using T = Tl<W>;
+#ifdef DM_PROFILE
+    unsigned int pt = static_cast<unsigned int>(clock64());
+#define SPROF(sec) do { if ((threadIdx.x & 31) == 0) { unsigned int t_ = static_cast<unsigned int>(clock64()); prf[sec] += t_ - pt; pt = t_; } } while (0)
+#else
+#define SPROF(sec) do { } while (0)
+#endif
     const StepLayout& LY = *reinterpret_cast<const StepLayout*>(LYS);
     const int nl = LY.nl, n = LY.n, CL = LY.chain_len, MR = LY.maxrows;
     float* sU = E + LY.oU; float* sS = E + LY.oR; float* sW = E + LY.oW; float* sV = E + LY.oV; float* sA = E + LY.oA; float* sY = E + LY.oY;
@@ -241,84 +247,225 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
         }
     }
     __syncwarp();
-    // ---- A = J M^-1 J^T, packed lower triangle (overwrites the world-frame / velocity scratch, no longer needed this sub-step)
-    int bj[kSlots], tj[kSlots];
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) { const int rid = lane + s * W; bj[s] = (rid < NR) ? sRl[rid] : 0; tj[s] = rid * (rid + 1) / 2; }
-    __syncwarp();
-#pragma unroll 1
-    for (int i = 0; i < NRmax; ++i) {
-        const bool iv = i < NR;
-        const int bi = iv ? sRl[i] : 0;
-        const unsigned char* cdr = CD + bi * nl;
-        const int ti = i * (i + 1) / 2;
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) {
-            const int rid = lane + s * W;
-            if (s * W <= i) {   // only rows j <= i are stored
-                const int cd = (iv && rid <= i) ? cdr[bj[s]] : 0;
-                float acc = 0.f;
-#pragma unroll 1
-                for (int k = 0; k < cd; ++k) acc += sY[k * MR + i] * sY[k * MR + rid];
-                if (iv && rid <= i) sA[ti + rid] = acc;
-            }
-        }
-    }
-    __syncwarp();
-    // warm start: w = A lambda0
+    SPROF(7);
     const int Pmax = (W == 32) ? P : wmax(P);
     const int NLmax = (W == 32) ? NL : wmax(NL);
+    if (nslots == 1) {
+        // ================= common case: at most W rows -> one row per lane, A stored as a full symmetric W x W square (stride W)
+        const int bjl = (lane < NR) ? sRl[lane] : 0;
+        __syncwarp();
 #pragma unroll 1
-    for (int p = 0; p < Pmax; ++p) {
-        const int i = NL + p;
-        const float l0 = (p < P) ? sLam[i] : 0.f;
-        const int ti = i * (i + 1) / 2;
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) {
-            const int rid = lane + s * W;
-            if (s < nslots && rid < NR && l0 != 0.f) r_w[s] += sA[(rid >= i) ? (tj[s] + i) : (ti + rid)] * l0;
+        for (int i = 0; i < NRmax; ++i) {
+            const bool iv = i < NR;
+            const int bi = iv ? sRl[i] : 0;
+            const int cdi = iv ? ((lk_i2(bi) >> 8) & 0xff) + 1 : 0;          // chain length of row i
+            const int cdm = (W == 32) ? cdi : wmax(cdi);
+            const int cd = (iv && lane <= i) ? CD[bi * nl + bjl] : 0;          // common chain depth of rows i and lane
+            const float* yi = sY + i; const float* yr = sY + lane;
+            float acc = 0.f;
+#pragma unroll 1
+            for (int k = 0; k < cdm; k += 4) {
+                const float a0 = yi[k * MR], a1 = yi[(k + 1) * MR], a2 = yi[(k + 2) * MR], a3 = yi[(k + 3) * MR];
+                const float b0 = yr[k * MR], b1 = yr[(k + 1) * MR], b2 = yr[(k + 2) * MR], b3 = yr[(k + 3) * MR];
+                if (k < cd) acc += a0 * b0;
+                if (k + 1 < cd) acc += a1 * b1;
+                if (k + 2 < cd) acc += a2 * b2;
+                if (k + 3 < cd) acc += a3 * b3;
+            }
+            if (iv && lane <= i) { sA[i * W + lane] = acc; sA[lane * W + i] = acc; }
         }
-    }
-    // ---- projected Gauss-Seidel, 10 sweeps (btMultiBodyConstraintSolver::solveSingleIteration ordering: limits (alternating), normals,
-    // frictions).  Every lane evaluates the row update from broadcast values; w = A lambda lives in registers, lanes = rows.
-    auto row_update = [&](int i, bool valid, float lo, float hi) {
-        const int owner = i & (W - 1), oslot = i / W;
-        float wsel = r_w[0];
-#pragma unroll
-        for (int s = 1; s < kSlots; ++s) if (oslot == s) wsel = r_w[s];
-        const float wi = T::shfl(wsel, owner);
-        const float lam = sLam[i];
-        float dI = sRhs[i] - wi * sInv[i];
-        float sum = lam + dI;
-        if (sum < lo) { dI = lo - lam; sum = lo; } else if (sum > hi) { dI = hi - lam; sum = hi; }
-        if (!valid) dI = 0.f;
-        if (valid && lane == 0) sLam[i] = sum;
-        const int ti = i * (i + 1) / 2;
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) {
-            const int rid = lane + s * W;
-            if (s < nslots && rid < NR) r_w[s] += sA[(rid >= i) ? (tj[s] + i) : (ti + rid)] * dI;
+        __syncwarp();
+        SPROF(8);
+        const float* Ac = sA + lane;                       // column `lane` of A (= row, A is symmetric): Ac[i * W] = A(lane, i)
+        const bool myrow = lane < NR;
+        float w = 0.f;                                     // (A lambda)_lane
+        // warm start: w = A lambda0
+#pragma unroll 1
+        for (int p = 0; p < Pmax; ++p) {
+            const float l0 = (p < P) ? sLam[NL + p] : 0.f;
+            if (myrow && l0 != 0.f) w += Ac[(NL + p) * W] * l0;
         }
-    };
+        // ---- projected Gauss-Seidel, 10 sweeps, rows in blocks of KB consecutive solver rows (see the general path below for the scheme)
+        constexpr int KB = 4;
+        auto block1 = [&](int i0, int nvalid, bool friction, float hi0) {
+            float wi[KB], lam[KB], rhs[KB], inv[KB], lo[KB], hi[KB], dI[KB], ab[KB * (KB - 1) / 2];
+            const float* Ar = sA + i0 * W + i0;            // A(i0 + a, i0 + c) = Ar[a * W + c]
+#pragma unroll
+            for (int a = 0; a < KB; ++a) {
+                wi[a] = T::shfl(w, i0 + a);
+                lam[a] = sLam[i0 + a]; rhs[a] = sRhs[i0 + a]; inv[a] = sInv[i0 + a];
+                lo[a] = 0.f; hi[a] = hi0;
+                if (friction) { const float tot = sLam[NL + ((i0 + a - NL - P) >> 1)]; hi[a] = (tot > 0.f) ? mu * tot : -1.f; lo[a] = -hi[a]; }   // hi < 0: skipped row
+#pragma unroll
+                for (int c = 0; c < a; ++c) ab[a * (a - 1) / 2 + c] = Ar[a * W + c];
+            }
+#pragma unroll
+            for (int a = 0; a < KB; ++a) {
+                float wa = wi[a];
+#pragma unroll
+                for (int c = 0; c < a; ++c) wa += ab[a * (a - 1) / 2 + c] * dI[c];
+                float d = rhs[a] - wa * inv[a];
+                float sum = lam[a] + d;
+                if (sum < lo[a]) { d = lo[a] - lam[a]; sum = lo[a]; } else if (sum > hi[a]) { d = hi[a] - lam[a]; sum = hi[a]; }
+                const bool ok = a < nvalid && !(friction && hi[a] < 0.f);
+                if (!ok) d = 0.f;
+                dI[a] = d;
+                if (ok && lane == 0) sLam[i0 + a] = sum;
+            }
+            if (myrow) {
+                const float* Ai = Ac + i0 * W;
+#pragma unroll
+                for (int a = 0; a < KB; ++a) if (a < nvalid) w += Ai[a * W] * dI[a];
+            }
+        };
 #pragma unroll 1
-    for (int it = 0; it < 10; ++it) {
+        for (int it = 0; it < 10; ++it) {
 #pragma unroll 1
-        for (int u = 0; u < NLmax; ++u) {
-            const bool valid = u < NL;
-            row_update(valid ? ((it & 1) ? u : NL - 1 - u) : 0, valid, 0.f, 100.f);
+            for (int u = 0; u < NLmax; ++u) {
+                const bool valid = u < NL;
+                block1(valid ? ((it & 1) ? u : NL - 1 - u) : 0, valid ? 1 : 0, false, 100.f);   // limit rows one at a time: [0, 100]
+            }
+#pragma unroll 1
+            for (int p = 0; p < Pmax; p += KB) block1(NL + ((p < P) ? p : 0), min(KB, max(0, P - p)), false, 1e10f);
+            __syncwarp();
+#pragma unroll 1
+            for (int f = 0; f < 2 * Pmax; f += KB) block1(NL + P + ((f < 2 * P) ? f : 0), min(KB, max(0, 2 * P - f)), true, 0.f);
             __syncwarp();
         }
-#pragma unroll 1
-        for (int p = 0; p < Pmax; ++p) row_update((p < P) ? NL + p : 0, p < P, 0.f, 1e10f);
+    } else {
+        // ================= general path: up to kSlots rows per lane, A as a packed lower triangle
+        // ---- A = J M^-1 J^T, packed lower triangle (overwrites the world-frame / velocity scratch, no longer needed this sub-step)
+        int bj[kSlots], tj[kSlots];
+    #pragma unroll
+        for (int s = 0; s < kSlots; ++s) { const int rid = lane + s * W; bj[s] = (rid < NR) ? sRl[rid] : 0; tj[s] = rid * (rid + 1) / 2; }
         __syncwarp();
-#pragma unroll 1
-        for (int f = 0; f < 2 * Pmax; ++f) {
-            const bool valid = f < 2 * P;
-            const float tot = valid ? sLam[NL + (f >> 1)] : 0.f;
-            row_update(valid ? NL + P + f : 0, valid && tot > 0.f, -mu * tot, mu * tot);
+    #pragma unroll 1
+        for (int i = 0; i < NRmax; ++i) {
+            const bool iv = i < NR;
+            const int bi = iv ? sRl[i] : 0;
+            const unsigned char* cdr = CD + bi * nl;
+            const int ti = i * (i + 1) / 2;
+            const int cdi = iv ? ((lk_i2(bi) >> 8) & 0xff) + 1 : 0;          // chain length of row i
+            const int cdm = (W == 32) ? cdi : wmax(cdi);
+    #pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                const int rid = lane + s * W;
+                if (s * W <= i) {   // only rows j <= i are stored
+                    const int cd = (iv && rid <= i) ? cdr[bj[s]] : 0;       // common chain depth of rows i and rid
+                    const float* yi = sY + i; const float* yr = sY + ((rid < MR) ? rid : 0);
+                    float acc = 0.f;
+    #pragma unroll 1
+                    for (int k = 0; k < cdm; k += 4) {
+                        const float a0 = yi[k * MR], a1 = yi[(k + 1) * MR], a2 = yi[(k + 2) * MR], a3 = yi[(k + 3) * MR];
+                        const float b0 = yr[k * MR], b1 = yr[(k + 1) * MR], b2 = yr[(k + 2) * MR], b3 = yr[(k + 3) * MR];
+                        if (k < cd) acc += a0 * b0;
+                        if (k + 1 < cd) acc += a1 * b1;
+                        if (k + 2 < cd) acc += a2 * b2;
+                        if (k + 3 < cd) acc += a3 * b3;
+                    }
+                    if (iv && rid <= i) sA[ti + rid] = acc;
+                }
+            }
         }
         __syncwarp();
+        SPROF(8);
+        // warm start: w = A lambda0
+    #pragma unroll 1
+        for (int p = 0; p < Pmax; ++p) {
+            const int i = NL + p;
+            const float l0 = (p < P) ? sLam[i] : 0.f;
+            const int ti = i * (i + 1) / 2;
+    #pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                const int rid = lane + s * W;
+                if (s < nslots && rid < NR && l0 != 0.f) r_w[s] += sA[(rid >= i) ? (tj[s] + i) : (ti + rid)] * l0;
+            }
+        }
+        // ---- projected Gauss-Seidel, 10 sweeps (btMultiBodyConstraintSolver::solveSingleIteration ordering: limits (alternating), normals,
+        // frictions).  w = A lambda lives in registers, lanes = rows.  Rows are processed in blocks of KB consecutive solver rows: the
+        // block's w values are fetched with independent shuffles, the KB sequential Gauss-Seidel updates are evaluated by every lane from
+        // broadcast data (with the in-block corrections A(b,a) dI_a), then each lane applies the KB impulses to its rows -- the same
+        // arithmetic, in the same order, as row-by-row Gauss-Seidel, but one shuffle round trip per block instead of per row.
+        constexpr int KB = 4;
+        auto tri = [](int r, int c) { return r * (r + 1) / 2 + c; };   // r >= c
+        auto block_update = [&](int i0, int nvalid, bool friction) {
+            float wi[KB], lam[KB], rhs[KB], inv[KB], lo[KB], hi[KB], dI[KB], ab[KB * (KB - 1) / 2];
+            int ii[KB];
+    #pragma unroll
+            for (int a = 0; a < KB; ++a) {
+                const int i = (a < nvalid) ? i0 + a : i0;
+                ii[a] = i;
+                const int owner = i & (W - 1), oslot = i / W;
+                float wsel = r_w[0];
+    #pragma unroll
+                for (int s = 1; s < kSlots; ++s) if (oslot == s) wsel = r_w[s];
+                wi[a] = T::shfl(wsel, owner);
+                lam[a] = sLam[i]; rhs[a] = sRhs[i]; inv[a] = sInv[i];
+                lo[a] = 0.f; hi[a] = 1e10f;
+                if (friction) { const float tot = sLam[NL + ((i - NL - P) >> 1)]; hi[a] = (tot > 0.f) ? mu * tot : -1.f; lo[a] = -hi[a]; }   // hi < 0 marks a skipped row
+    #pragma unroll
+                for (int c = 0; c < a; ++c) ab[a * (a - 1) / 2 + c] = sA[tri(i, ii[c])];
+            }
+    #pragma unroll
+            for (int a = 0; a < KB; ++a) {
+                float w = wi[a];
+    #pragma unroll
+                for (int c = 0; c < a; ++c) if (a < nvalid) w += ab[a * (a - 1) / 2 + c] * dI[c];
+                float d = rhs[a] - w * inv[a];
+                float sum = lam[a] + d;
+                if (sum < lo[a]) { d = lo[a] - lam[a]; sum = lo[a]; } else if (sum > hi[a]) { d = hi[a] - lam[a]; sum = hi[a]; }
+                const bool ok = a < nvalid && !(friction && hi[a] < 0.f);
+                if (!ok) d = 0.f;
+                dI[a] = d;
+                if (ok && lane == 0) sLam[ii[a]] = sum;
+            }
+    #pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                const int rid = lane + s * W;
+                if (s < nslots && rid < NR) {
+                    float w = r_w[s];
+    #pragma unroll
+                    for (int a = 0; a < KB; ++a) if (a < nvalid) w += sA[(rid >= ii[a]) ? (tj[s] + ii[a]) : (tri(ii[a], rid))] * dI[a];
+                    r_w[s] = w;
+                }
+            }
+        };
+        auto row_update = [&](int i, bool valid) {   // single limit row: lo = 0, hi = 100
+            const int owner = i & (W - 1), oslot = i / W;
+            float wsel = r_w[0];
+    #pragma unroll
+            for (int s = 1; s < kSlots; ++s) if (oslot == s) wsel = r_w[s];
+            const float wi = T::shfl(wsel, owner);
+            const float lam = sLam[i];
+            float dI = sRhs[i] - wi * sInv[i];
+            float sum = lam + dI;
+            if (sum < 0.f) { dI = -lam; sum = 0.f; } else if (sum > 100.f) { dI = 100.f - lam; sum = 100.f; }
+            if (!valid) dI = 0.f;
+            if (valid && lane == 0) sLam[i] = sum;
+            const int ti = i * (i + 1) / 2;
+    #pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                const int rid = lane + s * W;
+                if (s < nslots && rid < NR) r_w[s] += sA[(rid >= i) ? (tj[s] + i) : (ti + rid)] * dI;
+            }
+        };
+    #pragma unroll 1
+        for (int it = 0; it < 10; ++it) {
+    #pragma unroll 1
+            for (int u = 0; u < NLmax; ++u) {
+                const bool valid = u < NL;
+                row_update(valid ? ((it & 1) ? u : NL - 1 - u) : 0, valid);
+                __syncwarp();
+            }
+    #pragma unroll 1
+            for (int p = 0; p < Pmax; p += KB) block_update(NL + ((p < P) ? p : 0), min(KB, max(0, P - p)), false);
+            __syncwarp();
+    #pragma unroll 1
+            for (int f = 0; f < 2 * Pmax; f += KB) block_update(NL + P + ((f < 2 * P) ? f : 0), min(KB, max(0, 2 * P - f)), true);
+            __syncwarp();
+        }
     }
+    SPROF(9);
     // write impulses back to the manifold (warm start of the next sub-step)
 #pragma unroll 1
     for (int p = lane; p < P; p += W) {
@@ -328,20 +475,31 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
             mpt[7] = sLam[NL + p]; mpt[8] = sLam[NL + P + 2 * p]; mpt[9] = sLam[NL + P + 2 * p + 1];
         }
     }
-    // ---- z = Y^T lambda (lanes = chain depth)
+    // ---- z = Y^T lambda: lane = link accumulates the entries of its own dofs over the rows whose chain passes through it; lanes < 6 also
+    // accumulate the base entry of the same index
+    {
+        const int info = (lane < nl) ? lk_i(lane) : 0;
+        const int nd = (info >> 16) & 0xff, dp0 = (info >> 24) & 0xff;
+        const int d0 = (lane < nl) ? (lk_i2(lane) & 0xff) : 0;
+        float z0 = 0.f, z1 = 0.f, z2 = 0.f, zb = 0.f;
+        const int kb = (lane < 6) ? lane : 0;
 #pragma unroll 1
-    for (int k = lane; k < n; k += W) sZ[k] = 0.f;
-    __syncwarp();
-#pragma unroll 1
-    for (int i = 0; i < NRmax; ++i) {
-        if (i < NR) {
-            const int b = sRl[i];
-            const int lastd = (lk_i2(b) >> 8) & 0xff;
-#pragma unroll 1
-            for (int k = lane; k <= lastd; k += W) sZ[CH[b * CL + k]] += sY[k * MR + i] * sLam[i];
+        for (int i = 0; i < NRmax; ++i) {
+            if (i < NR) {
+                const int b = sRl[i];
+                const float l = sLam[i];
+                zb += sY[kb * MR + i] * l;
+                if (lane < nl && nd > 0 && CD[b * nl + lane] > dp0 + nd - 1) {   // the row's chain contains this link's dofs
+                    z0 += sY[dp0 * MR + i] * l;
+                    if (nd == 3) { z1 += sY[(dp0 + 1) * MR + i] * l; z2 += sY[(dp0 + 2) * MR + i] * l; }
+                }
+            }
         }
-        __syncwarp();
+        if (lane < 6) sZ[lane] = zb;
+        if (lane < nl && nd >= 1) sZ[d0] = z0;
+        if (lane < nl && nd == 3) { sZ[d0 + 1] = z1; sZ[d0 + 2] = z2; }
     }
+    __syncwarp();
 }
 
 
@@ -468,6 +626,11 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
 #define PROF(sec) do { if ((threadIdx.x & 31) == 0) { unsigned int t_ = static_cast<unsigned int>(clock64()); PRF[sec] += t_ - prf_t; prf_t = t_; } } while (0)
 #else
 #define PROF(sec) do { } while (0)
+#endif
+#ifdef DM_PROFILE
+    unsigned int* PRFP = PRF;
+#else
+    unsigned int* PRFP = nullptr;
 #endif
     bool need_kin = true, pending_flags = false;
     const int stages_per_upd = sim_substeps + 1;
@@ -975,7 +1138,10 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         PROF(7);
         // rows, J M^-1 J^T, projected Gauss-Seidel and z = Y^T lambda: a separate (non-inlined) warp-collective routine with its own
         // register budget -- it only needs this environment's shared-memory block
-        solve_rows<W>(E, LYS, LK, CD, CH, lane, NL, P, h, mu, mani, alive ? 1 : 0);
+#ifdef DM_PROFILE
+        { const int nrm = wmax(NR); if ((threadIdx.x & 31) == 0) { PRF[13] += nrm; PRF[14] += 1; } }
+#endif
+        solve_rows<W>(E, LYS, LK, CD, CH, lane, NL, P, h, mu, mani, alive ? 1 : 0, PRFP);
         PROF(10);
         {
             S6 dB = mks(mk3(0, 0, 0), mk3(0, 0, 0));

@@ -37,3 +37,11 @@ slow2 = d[np.arange(nblocks), wosync.argmax(axis=1)]
 print("%-22s %12s %12s" % ("section", "mean warp", "busiest warp/block"))
 for k, nme in enumerate(names):
     print("%-22s %12.0f %12.0f" % (nme, d[:, :, k].mean(), slow2[:, k].mean()))
+
+nr_sum, nr_cnt = d[:, :, 13], d[:, :, 14]
+busy = wosync.argmax(axis=1)
+print("busiest warp per block: constraint sub-steps %.1f of 40, mean max-rows per such sub-step %.1f ; all warps: %.1f of 40, %.1f rows" % (
+    nr_cnt[np.arange(nblocks), busy].mean(), (nr_sum[np.arange(nblocks), busy] / np.maximum(1, nr_cnt[np.arange(nblocks), busy])).mean(),
+    nr_cnt.mean(), nr_sum.sum() / max(1, nr_cnt.sum())))
+sr = d[:, :, 10]
+print("solve_rows cycles per call: busiest %.0f, all %.0f" % ((sr[np.arange(nblocks), busy] / np.maximum(1, nr_cnt[np.arange(nblocks), busy])).mean(), sr.sum() / max(1, nr_cnt.sum())))
