@@ -128,7 +128,7 @@ int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L) {
     L->oRl = o; o += maxrows;                      // row -> link (int)
     L->oPp = o; o += maxpts * 4; L->oPi = o; o += maxpts; L->oPr = o; o += maxpts;
     L->oQ = o; o += 4 * 8;                         // limit rows: link, dir, penetration, joint rate (<= 8)
-    L->oG = o; o += 21 + 9 + 2;                    // base Cholesky factor (21), world->base rotation (9)
+    L->oG = o; o += 21 + 13 + 2;                   // base Cholesky factor (21), base state: position 3, quaternion 4, omega 3, velocity 3
     L->oZ = o; o += ((n + 3) / 4) * 4;
     L->env_floats = ((o + 15) / 32) * 32 + 16;     // stride == 16 (mod 32 banks): the two environments of a warp (W = 16) hit disjoint bank halves
     L->hot_floats = ((nl * kLkFloats + (nl * nl + nl * chain_len + 3) / 4 + 8 + 24 + 3) / 4) * 4;
@@ -585,20 +585,26 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     double* tm = st.time + static_cast<size_t>(env) * kTimeDoubles;
     int* fl = st.flags + static_cast<size_t>(env) * kFlagInts;
     float* mani = st.manifold + static_cast<size_t>(env) * nl * kManifoldFloats;
-    V3 basePos; Q4 baseQuat; V3 baseOmega, baseVel;
-    {
+    float* sB = sG + 21;   // base state, owned by lane 0: position [0..2], quaternion (world->base) [3..6], omega_w [7..9], v_w [10..12]
+    if (lane == 0) {
         float4 b0 = reinterpret_cast<const float4*>(sim)[0], b1 = reinterpret_cast<const float4*>(sim)[1], b2 = reinterpret_cast<const float4*>(sim)[2],
                b3 = reinterpret_cast<const float4*>(sim)[3];
-        basePos = mk3(b0.x, b0.y, b0.z); baseQuat = mkq(b1.x, b1.y, b1.z, b1.w); baseOmega = mk3(b2.x, b2.y, b2.z); baseVel = mk3(b3.x, b3.y, b3.z);
+        sB[0] = b0.x; sB[1] = b0.y; sB[2] = b0.z; sB[3] = b1.x; sB[4] = b1.y; sB[5] = b1.z; sB[6] = b1.w;
+        sB[7] = b2.x; sB[8] = b2.y; sB[9] = b2.z; sB[10] = b3.x; sB[11] = b3.y; sB[12] = b3.z;
     }
+    auto bPos = [&]() { return mk3(sB[0], sB[1], sB[2]); };
+    auto bQuat = [&]() { return mkq(sB[3], sB[4], sB[5], sB[6]); };
+    auto bOmega = [&]() { return mk3(sB[7], sB[8], sB[9]); };
+    auto bVel = [&]() { return mk3(sB[10], sB[11], sB[12]); };
     float4 jp = reinterpret_cast<const float4*>(sim + 16)[li];
     float4 jv = reinterpret_cast<const float4*>(sim + 16 + 4 * nl)[li];
-    double kin_time = tm[kTKin], ctrl_time = tm[kTCtrl], prev_act = tm[kTPrevAct], timer = tm[kTTimer];
-    const double init_off = tm[kTInitOff], timer_max = tm[kTTimerMax];
-    double org_x = tm[kTOrigin], org_y = tm[kTOrigin + 1], org_z = tm[kTOrigin + 2];
+    // the f64 clocks (timer, mocap time, controller time, origin) live in global memory and are advanced in place by lane 0 once per update;
+    // cbits carries what the post-update flags need: bit 0 new-action edge, bit 1 time limit reached, bit 2 non-looping clip finished
     int need_action = fl[kFNeedAction];
+    int cbits = 0;
     bool alive = fl[kFDone] == 0;
     int f_over = fl[kFRowOverflow], f_updates = fl[kFUpdates];
+    __syncwarp();
 
     const float h = static_cast<float>(dt) / static_cast<float>(sim_substeps);
     const float fdt = static_cast<float>(dt);
@@ -651,13 +657,14 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 cached = qmul(mkq(axis.x * s, axis.y * s, axis.z * s, c), zrot);
             } else cached = zrot;
             const M3 R = qmat(cached);
-            const M3 Rwb = qmat(baseQuat);
             V3 jw = mk3(0, 0, 0);
             if (jtype == kJSpherical) jw = mk3(jv.x, jv.y, jv.z); else if (jtype == kJRevolute) jw = jv.x * axis;
             M3 Rwl; V3 Pw;
             if (lane == 0) {
-                Rwl = mul(R, Rwb); cw = mulT(Rwb, cvec); Pw = basePos + cw;
-                vel = mks(baseOmega + mulT(Rwl, jw), baseVel + cross(baseOmega, cw));
+                const M3 Rwb = qmat(bQuat());
+                const V3 bo = bOmega();
+                Rwl = mul(R, Rwb); cw = mulT(Rwb, cvec); Pw = bPos() + cw;
+                vel = mks(bo + mulT(Rwl, jw), bVel() + cross(bo, cw));
             }
 #pragma unroll 1
             for (int lv = 1; lv <= maxlevel; ++lv) {
@@ -688,12 +695,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         // =================================================================== post-update flags of the update that just finished
         if (pending_flags) {
             pending_flags = false;
-            need_action = 0;
-            {   // cMathUtil::CheckNextInterval(dt, ctrl_time + init_time_offset, 1/30)
-                const double cur = ctrl_time + init_off, pad = 0.001 * dt, T_ = M.query_dt;
-                int c0 = static_cast<int>(floor((cur + pad) / T_)), c1 = static_cast<int>(floor((cur + pad - dt) / T_));
-                need_action = (c0 != c1) ? 1 : 0;
-            }
+            need_action = cbits & 1;
             // fall: any fall-contact link with a manifold point at distance <= 0.001*scale (state of the last sub-step's collision pass)
             const unsigned fb = __ballot_sync(0xffffffffu, act && fall_contact && in_contact_tol);
             const unsigned fseg = (W == 32) ? fb : ((fb >> (threadIdx.x & 16)) & 0xffffu);
@@ -705,17 +707,15 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             const unsigned eseg = (W == 32) ? eb : ((eb >> (threadIdx.x & 16)) & 0xffffu);
             if (alive) {
                 int term = (M.enable_fall_end && fallen) ? 1 : 0;
-                if (!term && !M.loop_motion && kin_time >= M.motion_dur) term = 1;
+                if (!term && (cbits & 4)) term = 1;
                 f_updates++;
-                const bool end = (timer >= timer_max) || term;
+                const bool end = (cbits & 2) || term;
                 if (end || stage == total_stages) {   // commit
                     if (lane == 0) {
-                        reinterpret_cast<float4*>(sim)[0] = make_float4(basePos.x, basePos.y, basePos.z, 0.f);
-                        reinterpret_cast<float4*>(sim)[1] = make_float4(baseQuat.x, baseQuat.y, baseQuat.z, baseQuat.w);
-                        reinterpret_cast<float4*>(sim)[2] = make_float4(baseOmega.x, baseOmega.y, baseOmega.z, 0.f);
-                        reinterpret_cast<float4*>(sim)[3] = make_float4(baseVel.x, baseVel.y, baseVel.z, 0.f);
-                        tm[kTKin] = kin_time; tm[kTCtrl] = ctrl_time; tm[kTPrevAct] = prev_act; tm[kTTimer] = timer;
-                        tm[kTOrigin] = org_x; tm[kTOrigin + 1] = org_y; tm[kTOrigin + 2] = org_z;
+                        reinterpret_cast<float4*>(sim)[0] = make_float4(sB[0], sB[1], sB[2], 0.f);
+                        reinterpret_cast<float4*>(sim)[1] = make_float4(sB[3], sB[4], sB[5], sB[6]);
+                        reinterpret_cast<float4*>(sim)[2] = make_float4(sB[7], sB[8], sB[9], 0.f);
+                        reinterpret_cast<float4*>(sim)[3] = make_float4(sB[10], sB[11], sB[12], 0.f);
                         fl[kFNeedAction] = need_action; fl[kFDone] = end ? 1 : 0; fl[kFTerminate] = term; fl[kFValid] = (eseg == 0) ? 1 : 0; fl[kFFallen] = fallen;
                         fl[kFRowOverflow] = f_over; fl[kFUpdates] = f_updates;
                     }
@@ -737,35 +737,51 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         int P = 0;
         if (ph == 0) {
             // ---------------- clocks: cScene::Update, cSceneImitate::UpdateKinChar, cDeepMimicCharController::UpdateCalcTau
-            timer += dt;
-            const double dur = M.motion_dur;
-            double p0 = kin_time / dur; p0 -= floor(p0);
-            kin_time += dt;
-            double p1 = kin_time / dur; p1 -= floor(p1);
-            if (M.loop_motion && p1 < p0 && M.sync_root_pos) {
-                // SyncKinCharNewCycle: snap the clip's root x,z (at the new time) onto the simulated root
-                int cyc = static_cast<int>(floor(kin_time / dur));
-                double tt = kin_time - cyc * dur;
-                int lo = 0, hi = M.num_frames - 1;   // upper_bound - 1
-                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (frame_times[mid] <= tt) lo = mid; else hi = mid; }
-                double bl = (tt - frame_times[lo]) / (frame_times[lo + 1] - frame_times[lo]);
-                bl = fmin(fmax(bl, 0.0), 1.0);
-                const float* f0 = frames + static_cast<size_t>(lo) * M.pose_dim; const float* f1 = f0 + M.pose_dim;
-                double rx = (1 - bl) * f0[0] + bl * f1[0] + cyc * static_cast<double>(M.cycle_delta[0]);
-                double rz = (1 - bl) * f0[2] + bl * f1[2] + cyc * static_cast<double>(M.cycle_delta[2]);
-                double qw = tm[kTOriginRot], qx = tm[kTOriginRot + 1], qy = tm[kTOriginRot + 2], qz = tm[kTOriginRot + 3];
-                double ry_ = (1 - bl) * f0[1] + bl * f1[1];
-                double ux = qy * rz - qz * ry_, uy = qz * rx - qx * rz, uz = qx * ry_ - qy * rx;
-                ux *= 2; uy *= 2; uz *= 2;
-                double kx = rx + qw * ux + (qy * uz - qz * uy);
-                double kz = rz + qw * uz + (qx * uy - qy * ux);
-                double sx = static_cast<double>(basePos.x) / M.scale, sz = static_cast<double>(basePos.z) / M.scale;
-                org_x += sx - (kx + org_x);
-                org_z += sz - (kz + org_z);
-                org_y = 0.0;   // kin_root.y := ground_h + (kin_root.y - origin.y)  =>  origin.y returns to 0
+            int cb = 0;
+            if (lane == 0 && alive) {
+                const double timer = tm[kTTimer] + dt;
+                double kin_time = tm[kTKin];
+                const double dur = M.motion_dur;
+                double p0 = kin_time / dur; p0 -= floor(p0);
+                kin_time += dt;
+                double p1 = kin_time / dur; p1 -= floor(p1);
+                if (M.loop_motion && p1 < p0 && M.sync_root_pos) {
+                    // SyncKinCharNewCycle: snap the clip's root x,z (at the new time) onto the simulated root
+                    double org_x = tm[kTOrigin], org_z = tm[kTOrigin + 2];
+                    int cyc = static_cast<int>(floor(kin_time / dur));
+                    double tt = kin_time - cyc * dur;
+                    int lo = 0, hi = M.num_frames - 1;   // upper_bound - 1
+                    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (frame_times[mid] <= tt) lo = mid; else hi = mid; }
+                    double bl = (tt - frame_times[lo]) / (frame_times[lo + 1] - frame_times[lo]);
+                    bl = fmin(fmax(bl, 0.0), 1.0);
+                    const float* f0 = frames + static_cast<size_t>(lo) * M.pose_dim; const float* f1 = f0 + M.pose_dim;
+                    double rx = (1 - bl) * f0[0] + bl * f1[0] + cyc * static_cast<double>(M.cycle_delta[0]);
+                    double rz = (1 - bl) * f0[2] + bl * f1[2] + cyc * static_cast<double>(M.cycle_delta[2]);
+                    double qw = tm[kTOriginRot], qx = tm[kTOriginRot + 1], qy = tm[kTOriginRot + 2], qz = tm[kTOriginRot + 3];
+                    double ry_ = (1 - bl) * f0[1] + bl * f1[1];
+                    double ux = qy * rz - qz * ry_, uy = qz * rx - qx * rz, uz = qx * ry_ - qy * rx;
+                    ux *= 2; uy *= 2; uz *= 2;
+                    double kx = rx + qw * ux + (qy * uz - qz * uy);
+                    double kz = rz + qw * uz + (qx * uy - qy * ux);
+                    double sx = static_cast<double>(sB[0]) / M.scale, sz = static_cast<double>(sB[2]) / M.scale;
+                    org_x += sx - (kx + org_x);
+                    org_z += sz - (kz + org_z);
+                    tm[kTOrigin] = org_x; tm[kTOrigin + 2] = org_z;
+                    tm[kTOrigin + 1] = 0.0;   // kin_root.y := ground_h + (kin_root.y - origin.y)  =>  origin.y returns to 0
+                }
+                const double ctrl_time = tm[kTCtrl] + dt;
+                if (need_action) tm[kTPrevAct] = ctrl_time;
+                tm[kTTimer] = timer; tm[kTKin] = kin_time; tm[kTCtrl] = ctrl_time;
+                {   // cMathUtil::CheckNextInterval(dt, ctrl_time + init_time_offset, 1/30), evaluated for the flags after this update
+                    const double cur = ctrl_time + tm[kTInitOff], pad = 0.001 * dt, T_ = M.query_dt;
+                    int c0 = static_cast<int>(floor((cur + pad) / T_)), c1 = static_cast<int>(floor((cur + pad - dt) / T_));
+                    cb = (c0 != c1) ? 1 : 0;
+                }
+                if (timer >= tm[kTTimerMax]) cb |= 2;
+                if (!M.loop_motion && kin_time >= dur) cb |= 4;
             }
-            ctrl_time += dt;
-            if (need_action) { prev_act = ctrl_time; need_action = 0; }
+            cbits = T::shfli(cb, 0);
+            need_action = 0;
         } else {
             // ---------------- collision: link convex vs plane y = 0, persistent manifold of <= 4 points per link (btPersistentManifold)
             int cnt = 0;
@@ -885,16 +901,18 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         if (jtype == kJSpherical) jww = jv.x * S0 + jv.y * S1 + jv.z * S2; else if (jtype == kJRevolute) jww = jv.x * S0;
         S6 ab;
         {
-            V3 wxv;
-            if (bullet) wxv = cross(baseOmega, baseVel);
-            else {   // cRBDUtil::BuildCjRoot differentiates the root quaternion with the body-frame formula applied to the world-frame
-                     // angular velocity (RBDUtil.cpp:915-958): reproduced in the Stable-PD stage
-                const M3 Rwb = qmat(baseQuat);
-                wxv = mulT(Rwb, cross(baseOmega, mul(Rwb, baseVel)));
-            }
-            const S6 abB = mks(mk3(0, 0, 0), -grav - wxv);
             const S6 cj = mks(cross(vel.a, jww), cross(vel.l, jww));
-            if (lane == 0) ab = shift_m(abB, cw) + cj;
+            if (lane == 0) {
+                const V3 bo = bOmega(), bv = bVel();
+                V3 wxv;
+                if (bullet) wxv = cross(bo, bv);
+                else {   // cRBDUtil::BuildCjRoot differentiates the root quaternion with the body-frame formula applied to the world-frame
+                         // angular velocity (RBDUtil.cpp:915-958): reproduced in the Stable-PD stage
+                    const M3 Rwb = qmat(bQuat());
+                    wxv = mulT(Rwb, cross(bo, mul(Rwb, bv)));
+                }
+                ab = shift_m(mks(mk3(0, 0, 0), -grav - wxv), cw) + cj;
+            }
 #pragma unroll 1
             for (int lv = 1; lv <= maxlevel; ++lv) {
                 S6 pa = T::shfl6(ab, plane);
@@ -1084,22 +1102,26 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         const int sub = ph - 1;
         auto cl100 = [](float v) { return fminf(fmaxf(v, -100.f), 100.f); };   // applyDeltaVeeMultiDof clamp
         {
-            // base acceleration: already in the world-aligned generalised coordinates [omega_w, v_w]
-            const V3 dwb = T::shfl3(aB.a, 0), dvb = T::shfl3(aB.l, 0);
+            // base acceleration: already in the world-aligned generalised coordinates [omega_w, v_w] (lane 0 owns the base state)
+            if (lane == 0) {
+                if (DEBUG && dbg && first_upd) {
+                    const int o = (sub == 0 ? 4 * kMaxDofs : 8 * kMaxDofs + 1024);
+                    dbg[o] = aB.a.x; dbg[o + 1] = aB.a.y; dbg[o + 2] = aB.a.z; dbg[o + 3] = aB.l.x; dbg[o + 4] = aB.l.y; dbg[o + 5] = aB.l.z;
+                }
+                sB[7] = cl100(sB[7] + h * aB.a.x); sB[8] = cl100(sB[8] + h * aB.a.y); sB[9] = cl100(sB[9] + h * aB.a.z);
+                sB[10] = cl100(sB[10] + h * aB.l.x); sB[11] = cl100(sB[11] + h * aB.l.y); sB[12] = cl100(sB[12] + h * aB.l.z);
+            }
             if (DEBUG && dbg && first_upd) {
                 const int o = (sub == 0 ? 4 * kMaxDofs : 8 * kMaxDofs + 1024);
-                if (lane == 0) { dbg[o] = dwb.x; dbg[o + 1] = dwb.y; dbg[o + 2] = dwb.z; dbg[o + 3] = dvb.x; dbg[o + 4] = dvb.y; dbg[o + 5] = dvb.z; }
                 if (ndof >= 1) dbg[o + dof0] = qd0;
                 if (ndof == 3) { dbg[o + dof0 + 1] = qd1; dbg[o + dof0 + 2] = qd2; }
             }
-            baseOmega = mk3(cl100(baseOmega.x + h * dwb.x), cl100(baseOmega.y + h * dwb.y), cl100(baseOmega.z + h * dwb.z));
-            baseVel = mk3(cl100(baseVel.x + h * dvb.x), cl100(baseVel.y + h * dvb.y), cl100(baseVel.z + h * dvb.z));
             if (ndof >= 1) jv.x = cl100(jv.x + h * qd0);
             if (ndof == 3) { jv.y = cl100(jv.y + h * qd1); jv.z = cl100(jv.z + h * qd2); }
             vel = vel + h * al;   // link velocities are linear in the generalised velocities (the clamp only acts on exploding states)
             if (DEBUG && dbg && first_upd) {
                 const int o = (sub == 0 ? 5 * kMaxDofs : 9 * kMaxDofs + 1024);
-                if (lane == 0) { dbg[o] = baseOmega.x; dbg[o + 1] = baseOmega.y; dbg[o + 2] = baseOmega.z; dbg[o + 3] = baseVel.x; dbg[o + 4] = baseVel.y; dbg[o + 5] = baseVel.z; dbg[(sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024)] = static_cast<float>(P); }
+                if (lane == 0) { for (int k = 0; k < 6; ++k) dbg[o + k] = sB[7 + k]; dbg[(sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024)] = static_cast<float>(P); }
                 if (ndof >= 1) dbg[o + dof0] = jv.x;
                 if (ndof == 3) { dbg[o + dof0 + 1] = jv.y; dbg[o + dof0 + 2] = jv.z; }
             }
@@ -1167,10 +1189,11 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 S6 pa = T::shfl6(al, plane);
                 if (level == lv) al = descend(shift_m(pa, cw), z0, z1, z2);
             }
-            const V3 dwb = T::shfl3(dB.a, 0), dvb = T::shfl3(dB.l, 0);
             if (NR > 0) {
-                baseOmega = mk3(cl100(baseOmega.x + dwb.x), cl100(baseOmega.y + dwb.y), cl100(baseOmega.z + dwb.z));
-                baseVel = mk3(cl100(baseVel.x + dvb.x), cl100(baseVel.y + dvb.y), cl100(baseVel.z + dvb.z));
+                if (lane == 0) {
+                    sB[7] = cl100(sB[7] + dB.a.x); sB[8] = cl100(sB[8] + dB.a.y); sB[9] = cl100(sB[9] + dB.a.z);
+                    sB[10] = cl100(sB[10] + dB.l.x); sB[11] = cl100(sB[11] + dB.l.y); sB[12] = cl100(sB[12] + dB.l.z);
+                }
                 if (ndof >= 1) jv.x = cl100(jv.x + qd0);
                 if (ndof == 3) { jv.y = cl100(jv.y + qd1); jv.z = cl100(jv.z + qd2); }
             }
@@ -1183,13 +1206,16 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         }   // anyrow
         if (DEBUG && dbg && first_upd) {
             const int o = (sub == 0 ? 6 * kMaxDofs : 10 * kMaxDofs + 1024);
-            if (lane == 0) { dbg[o] = baseOmega.x; dbg[o + 1] = baseOmega.y; dbg[o + 2] = baseOmega.z; dbg[o + 3] = baseVel.x; dbg[o + 4] = baseVel.y; dbg[o + 5] = baseVel.z; }
+            if (lane == 0) for (int k = 0; k < 6; ++k) dbg[o + k] = sB[7 + k];
             if (ndof >= 1) dbg[o + dof0] = jv.x;
             if (ndof == 3) { dbg[o + dof0 + 1] = jv.y; dbg[o + dof0 + 2] = jv.z; }
         }
         // ---- integrate positions (btMultiBody::stepPositionsMultiDof)
-        basePos = basePos + h * baseVel;
-        baseQuat = quat_integrate3(baseOmega, baseQuat, true, h);
+        if (lane == 0) {
+            sB[0] += h * sB[10]; sB[1] += h * sB[11]; sB[2] += h * sB[12];
+            const Q4 q = quat_integrate3(bOmega(), bQuat(), true, h);
+            sB[3] = q.x; sB[4] = q.y; sB[5] = q.z; sB[6] = q.w;
+        }
         if (jtype == kJRevolute) jp.x += h * jv.x;
         else if (jtype == kJSpherical) { Q4 q = quat_integrate3(mk3(jv.x, jv.y, jv.z), mkq(jp.x, jp.y, jp.z, jp.w), false, h); jp = make_float4(q.x, q.y, q.z, q.w); }
         __syncwarp();
