@@ -16,15 +16,12 @@
 #include "kernels/dm_model.cuh"
 
 namespace dmk {
-template <int W, bool DEBUG>
-__global__ void dm_update_kernel(const DevModel*, DevState, const double*, const float*, double, int, int, int, int);
 template <int W, int BLOCK>
 __global__ void dm_observe_kernel(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
 template <int W, int BLOCK>
 __global__ void dm_reset_kernel(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*,
                                 unsigned long long, unsigned long long, int);
 __global__ void dm_set_action_kernel(const DevModel*, DevState, const float*, int);
-int dm_update_smem_bytes(int nl, int n, int cs, int maxrows, int tiles);
 template <int W, bool DEBUG>
 __global__ void dm_step_kernel(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
 int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L);
@@ -64,7 +61,7 @@ struct dm_handle {
     float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;            // staging for dm_step_host
     float *p_act = nullptr, *p_obs = nullptr, *p_rew = nullptr; int32_t* p_flags = nullptr;  // pinned host staging
     cudaStream_t stream = nullptr;
-    int device = 0, num_envs = 0, padded_envs = 0, W = 32, tiles = 2, maxrows = 36, smem_bytes = 0, mode = 0, minb = 4, sync_every_stage = 0, kernel = 3;
+    int device = 0, num_envs = 0, padded_envs = 0, W = 32, tiles = 2, maxrows = 36, smem_bytes = 0, mode = 0, minb = 4, sync_every_stage = 0;
     dmk::StepLayout lay{};
     uint64_t seed = 0, env_offset = 0;
     int64_t launches = 0;
@@ -264,21 +261,7 @@ int launch_step(dm_handle* h, double dt, int n_updates) {
     return 0;
 }
 template <int W, bool DEBUG>
-int launch_update(dm_handle* h, double dt, int n_updates) {
-    if (h->kernel == 3) return launch_step<W, DEBUG>(h, dt, n_updates);
-    auto kern = dmk::dm_update_kernel<W, DEBUG>;
-    static thread_local const void* configured = nullptr;
-    if (configured != reinterpret_cast<const void*>(kern)) {
-        DM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-        DM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = reinterpret_cast<const void*>(kern);
-    }
-    const int grid = h->padded_envs / h->tiles;
-    kern<<<grid, h->tiles * W, h->smem_bytes, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, dt, n_updates, h->sa.cfg.num_sim_substeps, h->maxrows, h->sync_every_stage);
-    DM_CUDA(cudaGetLastError());
-    h->launches++;
-    return 0;
-}
+int launch_update(dm_handle* h, double dt, int n_updates) { return launch_step<W, DEBUG>(h, dt, n_updates); }
 template <int W>
 int launch_observe(dm_handle* h, float* d_state, float* d_reward) {
     constexpr int BLOCK = 64;
@@ -350,8 +333,8 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
     if (!chk(cudaSetDevice(device), "cudaSetDevice")) { fail(); return nullptr; }
     h->device = device; h->seed = seed; h->env_offset = global_env_offset; h->num_envs = num_envs;
     const auto& M = h->hm;
-    h->W = (M.nl <= 16 && M.cs <= 16) ? 16 : 32;
-    if (const char* w = std::getenv("DM_TILE_WIDTH")) { int v = std::atoi(w); if (v == 32 || (v == 16 && M.nl <= 16 && M.cs <= 16)) h->W = v; }
+    h->W = (M.nl <= 16) ? 16 : 32;   // lanes per environment: one lane per link
+    if (const char* w = std::getenv("DM_TILE_WIDTH")) { int v = std::atoi(w); if (v == 32 || (v == 16 && M.nl <= 16)) h->W = v; }
     h->maxrows = (h->W == 16) ? 36 : 60;
     if (const char* sv = std::getenv("DM_SYNC_EVERY_STAGE")) h->sync_every_stage = std::atoi(sv);
     if (const char* r = std::getenv("DM_MAX_ROWS")) { int v = std::atoi(r); if (v >= 12 && v <= 96) h->maxrows = (v / 3) * 3; }
@@ -359,13 +342,12 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
         // one block per SM: as many environments per block as shared memory (227 KB) and 512 threads allow, balanced over the SMs
         cudaDeviceProp prop;
         if (!chk(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { fail(); return nullptr; }
-        if (const char* kv = std::getenv("DM_KERNEL")) h->kernel = std::atoi(kv);
         int chain_len = 0;
         for (int j = 0; j < M.nl; ++j) chain_len = std::max(chain_len, M.link[j].last_depth + 1);
         dmk::dm_step_layout(M.nl, M.n, chain_len, h->maxrows, &h->lay);
-        const int per_env = h->kernel == 3 ? h->lay.env_floats * 4 : dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, 1) - dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, 0);
-        const int hot = h->kernel == 3 ? h->lay.hot_floats * 4 : dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, 0);
-        int max_tiles = std::min((h->kernel == 3 ? dmk::kStepMaxThreads : dmk::kUpdateMaxThreads) / h->W, (static_cast<int>(prop.sharedMemPerBlockOptin) - hot) / per_env);
+        const int per_env = h->lay.env_floats * 4;
+        const int hot = h->lay.hot_floats * 4 + 1024;
+        int max_tiles = std::min(dmk::kStepMaxThreads / h->W, (static_cast<int>(prop.sharedMemPerBlockOptin) - hot) / per_env);
         if (const char* t = std::getenv("DM_TILES_PER_BLOCK")) max_tiles = std::max(1, std::min(max_tiles, std::atoi(t)));
         const int sms = prop.multiProcessorCount;
         int tiles = std::min(max_tiles, std::max(1, (num_envs + sms - 1) / sms));
@@ -374,7 +356,7 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
         h->tiles = tiles;
         const int quantum = (tiles * (64 / h->W)) / std::__gcd(tiles, 64 / h->W);   // multiple of both the update block and the 64-thread policy blocks
         h->padded_envs = ((num_envs + quantum - 1) / quantum) * quantum;
-        h->smem_bytes = h->kernel == 3 ? dmk::dm_step_smem_bytes(h->lay, h->tiles) + 1024 : dmk::dm_update_smem_bytes(M.nl, M.n, M.cs, h->maxrows, h->tiles);
+        h->smem_bytes = dmk::dm_step_smem_bytes(h->lay, h->tiles) + 1024;
     }
     const size_t N = static_cast<size_t>(h->padded_envs);
     const int ss = dmk::sim_stride(M.nl);

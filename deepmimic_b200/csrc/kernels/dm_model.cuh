@@ -17,8 +17,6 @@ constexpr int kMaxLinks = 32;   // one lane per link
 constexpr int kMaxDofs = 96;    // 6 + joint dofs (humanoid3d 34, dog3d 70)
 constexpr int kMaxChain = 24;   // longest root->leaf dof chain (humanoid3d 13, dog3d 22)
 constexpr int kMaxChildren = 4;
-constexpr int kMaxRows = 64;    // solver rows kept per env (contact rows come in triples) -- see DESIGN.md capacity note
-constexpr int kUpdateMaxThreads = 512;  // dm_update_kernel: one block per SM, up to 32 (W=16) / 16 (W=32) environments per block
 constexpr int kStepMaxThreads = 448;    // dm_step_kernel: 28 (W=16) / 14 (W=32) environments per block -> 144 registers per thread
 constexpr int kManifoldFloats = 48;  // per link: 4 points x 12 floats
 constexpr int kDebugFloats = 8 * kMaxDofs + 2048;   // test hook (dm_debug_*): stage dumps of one update

@@ -16,6 +16,9 @@
 // memory and PGS runs in impulse space with lanes = rows (one shuffle + one FMA per row update instead of a reduction).
 // All spatial quantities of a link are expressed in WORLD axes about the link's own joint pivot, so passing them between
 // parent and child is a pure shift (no rotation of 6x6 blocks).
+// The update is split into phase routines (kinematics, collision, articulated-body solve, constraint rows + PGS, velocity correction)
+// that are deliberately NOT inlined: they exchange state through the environment's shared-memory block, so each phase gets the full
+// register budget and the main loop only carries the joint state of its link.
 // No tensor cores: there is no dense contraction here (34 or 70 dofs, tree-sparse); the path is latency-bound.
 #include "dm_model.cuh"
 
@@ -120,7 +123,7 @@ int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L) {
     L->oU = o; o += nl * 24;                       // per link: U0 U1 U2 (6 each), 1/D (3), sqrt(1/D) (3)
     L->oR = o; o += nl * 12;                       // per link: joint axes in world axes (9), parent pivot -> pivot (3)
     L->oA = o;                                     // union { world frames + link velocities | packed lower triangle of J M^-1 J^T }
-    const int world = nl * 20, tri = maxrows * (maxrows + 1) / 2;
+    const int world = nl * 24, tri = maxrows * (maxrows + 1) / 2;   // world: Rwl 9 + pivot 3 | link velocity 6 + pivot->COM 3 (+3 pad)
     L->oW = o; L->oV = o + nl * 12;
     o += (world > tri ? world : tri);
     L->oY = o; o += chain_len * maxrows;           // Yt[depth][row]
@@ -187,7 +190,7 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
                 const V3 rel = mk3(sPp[p * 4] - w[9], sPp[p * 4 + 1] - w[10], sPp[p * 4 + 2] - w[11]);
                 const V3 fl_ = (kind == 1) ? mk3(0.f, 1.f, 0.f) : ((kind == 2) ? mk3(-1.f, 0.f, 0.f) : mk3(0.f, 0.f, 1.f));
                 f = mks(cross(rel, fl_), fl_);
-                const float* v = sV + b * 8;
+                const float* v = sV + b * 12;
                 rvel = dot(fl_, mk3(v[3], v[4], v[5]) + cross(mk3(v[0], v[1], v[2]), rel));
             }
             // walk the chain base <- ... <- b
@@ -198,20 +201,39 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
             while (true) {
                 const int info = lk_i(cur);
                 const int par = static_cast<int>(static_cast<signed char>(info & 0xff)), nd = (info >> 16) & 0xff, dp0 = (info >> 24) & 0xff;
-                const float* u = sU + cur * 24;
-                const float* q = sS + cur * 12;
-#pragma unroll 1
-                for (int d = nd - 1; d >= 0; --d) {
-                    float t = q[d * 3] * f.a.x + q[d * 3 + 1] * f.a.y + q[d * 3 + 2] * f.a.z;
+                const float4* u4 = reinterpret_cast<const float4*>(sU + cur * 24);
+                const float4* q4 = reinterpret_cast<const float4*>(sS + cur * 12);
+                const float4 ua = u4[0], ub = u4[1], uc = u4[2], ud = u4[3], ue = u4[4], uf = u4[5];   // U0 U1 U2 | 1/D | sqrt(1/D)
+                const float4 qa = q4[0], qb = q4[1], qc = q4[2];                                        // S0 S1 S2 | cw
+                if (nd == 3) {
+                    {   // dof 2
+                        const float t = qb.z * f.a.x + qb.w * f.a.y + qc.x * f.a.z;
+                        const float y = t * uf.w;
+                        if (rv_) sY[(dp0 + 2) * MR + rid] = y;
+                        acc += y * y;
+                        const float ti = t * uf.x;
+                        f.a.x -= ti * ud.x; f.a.y -= ti * ud.y; f.a.z -= ti * ud.z; f.l.x -= ti * ud.w; f.l.y -= ti * ue.x; f.l.z -= ti * ue.y;
+                    }
+                    {   // dof 1
+                        const float t = qa.w * f.a.x + qb.x * f.a.y + qb.y * f.a.z;
+                        const float y = t * uf.z;
+                        if (rv_) sY[(dp0 + 1) * MR + rid] = y;
+                        acc += y * y;
+                        const float ti = t * ue.w;
+                        f.a.x -= ti * ub.z; f.a.y -= ti * ub.w; f.a.z -= ti * uc.x; f.l.x -= ti * uc.y; f.l.y -= ti * uc.z; f.l.z -= ti * uc.w;
+                    }
+                }
+                if (nd >= 1) {   // dof 0
+                    float t = qa.x * f.a.x + qa.y * f.a.y + qa.z * f.a.z;
                     if (first && kind == 0) { t = lsign; rvel = lsign * sQ[24 + rid]; }
-                    const float y = t * u[21 + d];
-                    if (rv_) sY[(dp0 + d) * MR + rid] = y;
+                    const float y = t * uf.y;
+                    if (rv_) sY[dp0 * MR + rid] = y;
                     acc += y * y;
-                    const float ti = t * u[18 + d];
-                    f.a.x -= ti * u[d * 6]; f.a.y -= ti * u[d * 6 + 1]; f.a.z -= ti * u[d * 6 + 2]; f.l.x -= ti * u[d * 6 + 3]; f.l.y -= ti * u[d * 6 + 4]; f.l.z -= ti * u[d * 6 + 5];
+                    const float ti = t * ue.z;
+                    f.a.x -= ti * ua.x; f.a.y -= ti * ua.y; f.a.z -= ti * ua.z; f.l.x -= ti * ua.w; f.l.y -= ti * ub.x; f.l.z -= ti * ub.y;
                 }
                 first = false;
-                f = shift_f(f, mk3(q[9], q[10], q[11]));
+                f = shift_f(f, mk3(qc.y, qc.z, qc.w));
                 if (par < 0) break;
                 cur = par;
             }
@@ -258,13 +280,11 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
         for (int i = 0; i < NRmax; ++i) {
             const bool iv = i < NR;
             const int bi = iv ? sRl[i] : 0;
-            const int cdi = iv ? ((lk_i2(bi) >> 8) & 0xff) + 1 : 0;          // chain length of row i
-            const int cdm = (W == 32) ? cdi : wmax(cdi);
             const int cd = (iv && lane <= i) ? CD[bi * nl + bjl] : 0;          // common chain depth of rows i and lane
             const float* yi = sY + i; const float* yr = sY + lane;
             float acc = 0.f;
 #pragma unroll 1
-            for (int k = 0; k < cdm; k += 4) {
+            for (int k = 0; k < CL; k += 4) {   // entries past the common depth are masked (reads past the chain length stay inside the block)
                 const float a0 = yi[k * MR], a1 = yi[(k + 1) * MR], a2 = yi[(k + 2) * MR], a3 = yi[(k + 3) * MR];
                 const float b0 = yr[k * MR], b1 = yr[(k + 1) * MR], b2 = yr[(k + 2) * MR], b3 = yr[(k + 3) * MR];
                 if (k < cd) acc += a0 * b0;
@@ -287,14 +307,16 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
         }
         // ---- projected Gauss-Seidel, 10 sweeps, rows in blocks of KB consecutive solver rows (see the general path below for the scheme)
         constexpr int KB = 4;
-        auto block1 = [&](int i0, int nvalid, bool friction, float hi0) {
-            float wi[KB], lam[KB], rhs[KB], inv[KB], lo[KB], hi[KB], dI[KB], ab[KB * (KB - 1) / 2];
+        auto block1 = [&](int i0, int nvalid, bool friction) {
+            float wi[KB], lam[KB], rhs[KB], inv[KB], lo[KB], hi[KB], dI[KB], ab[KB * (KB - 1) / 2], av[KB];
             const float* Ar = sA + i0 * W + i0;            // A(i0 + a, i0 + c) = Ar[a * W + c]
+            const float* Ai = Ac + i0 * W;                 // A(lane, i0 + a) = Ai[a * W]
 #pragma unroll
             for (int a = 0; a < KB; ++a) {
                 wi[a] = T::shfl(w, i0 + a);
+                av[a] = (a < nvalid) ? Ai[a * W] : 0.f;
                 lam[a] = sLam[i0 + a]; rhs[a] = sRhs[i0 + a]; inv[a] = sInv[i0 + a];
-                lo[a] = 0.f; hi[a] = hi0;
+                lo[a] = 0.f; hi[a] = 1e10f;
                 if (friction) { const float tot = sLam[NL + ((i0 + a - NL - P) >> 1)]; hi[a] = (tot > 0.f) ? mu * tot : -1.f; lo[a] = -hi[a]; }   // hi < 0: skipped row
 #pragma unroll
                 for (int c = 0; c < a; ++c) ab[a * (a - 1) / 2 + c] = Ar[a * W + c];
@@ -305,31 +327,44 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
 #pragma unroll
                 for (int c = 0; c < a; ++c) wa += ab[a * (a - 1) / 2 + c] * dI[c];
                 float d = rhs[a] - wa * inv[a];
-                float sum = lam[a] + d;
-                if (sum < lo[a]) { d = lo[a] - lam[a]; sum = lo[a]; } else if (sum > hi[a]) { d = hi[a] - lam[a]; sum = hi[a]; }
+                const float sum = lam[a] + d;
+                const float sc = fminf(fmaxf(sum, lo[a]), hi[a]);   // same result as the reference's two-sided if: d is only replaced when the sum was clamped
+                d = (sc == sum) ? d : sc - lam[a];
                 const bool ok = a < nvalid && !(friction && hi[a] < 0.f);
-                if (!ok) d = 0.f;
+                d = ok ? d : 0.f;
                 dI[a] = d;
-                if (ok && lane == 0) sLam[i0 + a] = sum;
+                if (ok && lane == 0) sLam[i0 + a] = sc;
             }
             if (myrow) {
-                const float* Ai = Ac + i0 * W;
 #pragma unroll
-                for (int a = 0; a < KB; ++a) if (a < nvalid) w += Ai[a * W] * dI[a];
+                for (int a = 0; a < KB; ++a) w += av[a] * dI[a];
             }
+        };
+        auto limit1 = [&](int i, bool valid) {   // one joint-limit row: impulse in [0, 100]
+            const float wi = T::shfl(w, i);
+            const float av = Ac[i * W];
+            const float lam = sLam[i];
+            float d = sRhs[i] - wi * sInv[i];
+            const float sum = lam + d;
+            const float sc = fminf(fmaxf(sum, 0.f), 100.f);
+            d = (sc == sum) ? d : sc - lam;
+            d = valid ? d : 0.f;
+            if (valid && lane == 0) sLam[i] = sc;
+            if (myrow) w += av * d;
         };
 #pragma unroll 1
         for (int it = 0; it < 10; ++it) {
 #pragma unroll 1
             for (int u = 0; u < NLmax; ++u) {
                 const bool valid = u < NL;
-                block1(valid ? ((it & 1) ? u : NL - 1 - u) : 0, valid ? 1 : 0, false, 100.f);   // limit rows one at a time: [0, 100]
+                limit1(valid ? ((it & 1) ? u : NL - 1 - u) : 0, valid);
+                __syncwarp();
             }
 #pragma unroll 1
-            for (int p = 0; p < Pmax; p += KB) block1(NL + ((p < P) ? p : 0), min(KB, max(0, P - p)), false, 1e10f);
+            for (int p = 0; p < Pmax; p += KB) block1(NL + ((p < P) ? p : 0), min(KB, max(0, P - p)), false);
             __syncwarp();
 #pragma unroll 1
-            for (int f = 0; f < 2 * Pmax; f += KB) block1(NL + P + ((f < 2 * P) ? f : 0), min(KB, max(0, 2 * P - f)), true, 0.f);
+            for (int f = 0; f < 2 * Pmax; f += KB) block1(NL + P + ((f < 2 * P) ? f : 0), min(KB, max(0, 2 * P - f)), true);
             __syncwarp();
         }
     } else {
@@ -503,6 +538,451 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
 }
 
 
+// ---- per-lane context handed to the phase routines (all in registers)
+struct Ctx {
+    float* E;              // this environment's shared-memory block
+    const int* LYS;        // layout (shared copy of StepLayout)
+    const float* LK;       // block-shared link constants
+    const int* LVC;        // children per tree level
+    int lane, li;          // lane in the tile, link index (clamped for idle lanes)
+    int plane, level, ndof, jtype, nchild, child_pack, maxlevel;
+    bool act;
+};
+__device__ __forceinline__ const StepLayout& lay_of(const Ctx& c) { return *reinterpret_cast<const StepLayout*>(c.LYS); }
+__device__ __forceinline__ S6 shift_m(S6 m, V3 c) { return mks(m.a, m.l + cross(m.a, c)); }   // motion vector: reference point moved by +c
+__device__ __forceinline__ S6 shift_f(S6 f, V3 c) { return mks(f.a + cross(c, f.l), f.l); }   // force vector: child pivot -> parent pivot (child = parent + c)
+__device__ __forceinline__ float cl100(float v) { return fminf(fmaxf(v, -100.f), 100.f); }   // applyDeltaVeeMultiDof clamp
+
+// Forward kinematics and link velocities, root -> leaves.  Writes per link: world->link rotation + pivot (sW), joint axes in world axes +
+// parent pivot -> pivot (sS), spatial velocity at the pivot + pivot -> COM (sV).  Base state is read from sB by lane 0.
+template <int W>
+__device__ __noinline__ void kin_pass(Ctx c, float4 jp, float4 jv) {
+    using T = Tl<W>;
+    const StepLayout& LY = lay_of(c);
+    float* sS = c.E + LY.oR; float* sW = c.E + LY.oW; float* sV = c.E + LY.oV; const float* sB = c.E + LY.oG + 21;
+    const float* LKo = c.LK + c.li * kLkFloats;
+    const V3 axis = mk3(LKo[kLAx], LKo[kLAx + 1], LKo[kLAx + 2]);
+    const Q4 zrot = mkq(LKo[kLZr], LKo[kLZr + 1], LKo[kLZr + 2], LKo[kLZr + 3]);
+    const V3 cvec = mk3(LKo[kLC], LKo[kLC + 1], LKo[kLC + 2]);
+    Q4 cached;
+    if (c.jtype == kJSpherical) cached = qmul(mkq(jp.x, jp.y, jp.z, -jp.w), zrot);
+    else if (c.jtype == kJRevolute) {
+        float s, co;
+        __sincosf(-0.5f * jp.x, &s, &co);   // |angle| <= pi/2 + limit overshoot: fast path is accurate to ~1 ulp of the result scale
+        cached = qmul(mkq(axis.x * s, axis.y * s, axis.z * s, co), zrot);
+    } else cached = zrot;
+    const M3 R = qmat(cached);
+    V3 jw = mk3(0, 0, 0);
+    if (c.jtype == kJSpherical) jw = mk3(jv.x, jv.y, jv.z); else if (c.jtype == kJRevolute) jw = jv.x * axis;
+    M3 Rwl; V3 Pw, cw; S6 vel;
+    if (c.lane == 0) {
+        const M3 Rwb = qmat(mkq(sB[3], sB[4], sB[5], sB[6]));
+        const V3 bo = mk3(sB[7], sB[8], sB[9]);
+        Rwl = mul(R, Rwb); cw = mulT(Rwb, cvec); Pw = mk3(sB[0], sB[1], sB[2]) + cw;
+        vel = mks(bo + mulT(Rwl, jw), mk3(sB[10], sB[11], sB[12]) + cross(bo, cw));
+    }
+#pragma unroll 1
+    for (int lv = 1; lv <= c.maxlevel; ++lv) {
+        M3 pR; V3 pp; S6 pv;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) pR.m[k] = T::shfl(Rwl.m[k], c.plane);
+        pp = T::shfl3(Pw, c.plane);
+        pv = T::shfl6(vel, c.plane);
+        if (c.level == lv) {
+            Rwl = mul(R, pR); cw = mulT(pR, cvec); Pw = pp + cw;
+            vel = mks(pv.a + mulT(Rwl, jw), pv.l + cross(pv.a, cw));
+        }
+    }
+    if (c.act) {
+        const V3 dw = mulT(Rwl, mk3(LKo[kLD], LKo[kLD + 1], LKo[kLD + 2]));
+        V3 S0 = mk3(Rwl.m[0], Rwl.m[1], Rwl.m[2]);
+        if (c.jtype != kJSpherical) S0 = mulT(Rwl, axis);
+        float* w = sW + c.lane * 12; float* q = sS + c.lane * 12; float* v = sV + c.lane * 12;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k] = Rwl.m[k];
+        w[9] = Pw.x; w[10] = Pw.y; w[11] = Pw.z;
+        q[0] = S0.x; q[1] = S0.y; q[2] = S0.z; q[3] = Rwl.m[3]; q[4] = Rwl.m[4]; q[5] = Rwl.m[5]; q[6] = Rwl.m[6]; q[7] = Rwl.m[7]; q[8] = Rwl.m[8];
+        q[9] = cw.x; q[10] = cw.y; q[11] = cw.z;
+        v[0] = vel.a.x; v[1] = vel.a.y; v[2] = vel.a.z; v[3] = vel.l.x; v[4] = vel.l.y; v[5] = vel.l.z; v[6] = dw.x; v[7] = dw.y; v[8] = dw.z;
+    }
+    __syncwarp();
+}
+
+// Collision of this lane's link with the plane y = 0: persistent manifold of <= 4 points (btPersistentManifold), one new point per
+// sub-step from the support vertex (btConvexPlaneCollisionAlgorithm), refresh with the breaking threshold.  The manifold lives in global
+// memory; the points of the environment are published to shared memory for the row builder.
+// Returns P | in_contact_tol << 8 | overflow << 9.
+template <int W>
+__device__ __noinline__ int collide(Ctx c, float* mani, int alive, float scale) {
+    using T = Tl<W>;
+    const StepLayout& LY = lay_of(c);
+    const float* sW = c.E + LY.oW; const float* sV = c.E + LY.oV;
+    float* sPp = c.E + LY.oPp; float* sPi = c.E + LY.oPi; int* sPr = reinterpret_cast<int*>(c.E + LY.oPr);
+    const float* LKo = c.LK + c.li * kLkFloats;
+    const int shape = reinterpret_cast<const int*>(LKo)[kLFlg] & 0xff;
+    int cnt = 0;
+    float mp[48];
+    M3 Rwl;
+    {
+        const float* w = sW + c.li * 12;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rwl.m[k] = w[k];
+    }
+    {
+        const float4* mg = reinterpret_cast<const float4*>(mani + c.li * kManifoldFloats);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) { float4 v = mg[k]; mp[4 * k] = v.x; mp[4 * k + 1] = v.y; mp[4 * k + 2] = v.z; mp[4 * k + 3] = v.w; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (mp[k * 12] != 0.f && cnt == k) cnt = k + 1;
+    const float thr = LKo[kLThr];
+    const V3 he = mk3(LKo[kLHe], LKo[kLHe + 1], LKo[kLHe + 2]);
+    const V3 pos = mk3(sW[c.li * 12 + 9] + sV[c.li * 12 + 6], sW[c.li * 12 + 10] + sV[c.li * 12 + 7], sW[c.li * 12 + 11] + sV[c.li * 12 + 8]);   // COM, world (Bullet's link collider frame)
+    V3 dl = mul(Rwl, mk3(0.f, -1.f, 0.f));   // support direction -n in link coordinates
+    V3 vtx;
+    if (shape == kSBox) vtx = mk3(dl.x >= 0 ? he.x : -he.x, dl.y >= 0 ? he.y : -he.y, dl.z >= 0 ? he.z : -he.z);
+    else {
+        V3 sup = mk3(0, 0, 0);
+        if (shape == kSCapsule) sup = mk3(0.f, (dl.y >= 0.f) ? he.y : -he.y, 0.f);   // first end point wins ties
+        float inv = rsqrtf(dot(dl, dl));
+        vtx = sup + (he.x * inv) * dl;
+    }
+    const V3 vw = pos + mulT(Rwl, vtx);
+    const float dist = vw.y;
+    if (c.act && dist < thr) {
+        float best = thr * thr; int nearest = -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (k < cnt) {
+            float dx = mp[k * 12 + 1] - vtx.x, dy = mp[k * 12 + 2] - vtx.y, dz = mp[k * 12 + 3] - vtx.z, dd = dx * dx + dy * dy + dz * dz;
+            if (dd < best) { best = dd; nearest = k; }
+        }
+        int idx = nearest;
+        float k7 = 0, k8 = 0, k9 = 0, k11 = 0;
+        if (nearest >= 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (k == nearest) { k7 = mp[k * 12 + 7]; k8 = mp[k * 12 + 8]; k9 = mp[k * 12 + 9]; k11 = mp[k * 12 + 11]; }
+        } else if (cnt < 4) { idx = cnt; cnt++; }
+        else {   // btPersistentManifold::sortCachedPoints
+            int mpi = -1; float mpen = dist;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (mp[k * 12 + 10] < mpen) { mpi = k; mpen = mp[k * 12 + 10]; }
+            auto Pt = [&](int k) { return mk3(mp[k * 12 + 1], mp[k * 12 + 2], mp[k * 12 + 3]); };
+            auto area = [&](V3 a, V3 b) { V3 x = cross(a, b); return dot(x, x); };
+            float res[4] = {0, 0, 0, 0};
+            if (mpi != 0) res[0] = area(vtx - Pt(1), Pt(3) - Pt(2));
+            if (mpi != 1) res[1] = area(vtx - Pt(0), Pt(3) - Pt(2));
+            if (mpi != 2) res[2] = area(vtx - Pt(0), Pt(3) - Pt(1));
+            if (mpi != 3) res[3] = area(vtx - Pt(0), Pt(2) - Pt(1));
+            idx = 0; float bv = fabsf(res[0]);
+#pragma unroll
+            for (int k = 1; k < 4; ++k) if (fabsf(res[k]) > bv) { bv = fabsf(res[k]); idx = k; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (k == idx) {
+            float* q = mp + k * 12;
+            q[0] = 1.f; q[1] = vtx.x; q[2] = vtx.y; q[3] = vtx.z; q[4] = vw.x; q[5] = 0.f; q[6] = vw.z; q[7] = k7; q[8] = k8; q[9] = k9; q[10] = dist; q[11] = k11;
+        }
+    }
+    // refreshContactPoints
+#pragma unroll
+    for (int k = 3; k >= 0; --k) if (k < cnt) {
+        V3 pa = pos + mulT(Rwl, mk3(mp[k * 12 + 1], mp[k * 12 + 2], mp[k * 12 + 3]));
+        mp[k * 12 + 10] = pa.y - mp[k * 12 + 5];
+        mp[k * 12 + 11] += 1.f;
+    }
+#pragma unroll
+    for (int k = 3; k >= 0; --k) if (k < cnt) {
+        V3 pa = pos + mulT(Rwl, mk3(mp[k * 12 + 1], mp[k * 12 + 2], mp[k * 12 + 3]));
+        bool rm = !(mp[k * 12 + 10] <= thr);
+        if (!rm) {
+            float dx = mp[k * 12 + 4] - pa.x, dy = mp[k * 12 + 5] - (pa.y - mp[k * 12 + 10]), dz = mp[k * 12 + 6] - pa.z;
+            rm = (dx * dx + dy * dy + dz * dz) > thr * thr;
+        }
+        if (rm) {
+            const int last = cnt - 1;
+#pragma unroll
+            for (int l2 = 0; l2 < 4; ++l2) if (l2 == last) {
+                if (k != l2) for (int j = 0; j < 12; ++j) mp[k * 12 + j] = mp[l2 * 12 + j];
+                mp[l2 * 12] = 0.f;
+            }
+            cnt--;
+        }
+    }
+    if (!c.act || !alive) cnt = 0;   // finished episodes are frozen until dm_reset: no constraint rows for them
+    int tol = 0;                     // cContactManager::Update: distance <= 0.001 * scale
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (k < cnt && mp[k * 12 + 10] <= 0.001f * scale) tol = 1;
+    if (c.act && alive) {
+        float4* mo = reinterpret_cast<float4*>(mani + c.li * kManifoldFloats);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) mo[k] = make_float4(mp[4 * k], mp[4 * k + 1], mp[4 * k + 2], mp[4 * k + 3]);
+    }
+    // exclusive prefix over lanes -> point indices; publish points to the solver
+    int incl = cnt, over = 0;
+#pragma unroll
+    for (int o = 1; o < W; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o, W); if (c.lane >= o) incl += t; }
+    const int base = incl - cnt;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (k < cnt) {
+        const int p = base + k;
+        if (p < LY.maxpts) {
+            V3 pa = pos + mulT(Rwl, mk3(mp[k * 12 + 1], mp[k * 12 + 2], mp[k * 12 + 3]));
+            sPp[p * 4] = pa.x; sPp[p * 4 + 1] = pa.y; sPp[p * 4 + 2] = pa.z; sPp[p * 4 + 3] = mp[k * 12 + 10];
+            sPi[p] = mp[k * 12 + 7];
+            sPr[p] = c.lane * 4 + k;
+        } else over = 1;
+    }
+    const int P = min(T::shfli(incl, W - 1), LY.maxpts);
+    __syncwarp();
+    return P | (tol << 8) | (over << 9);
+}
+
+// Articulated-body solve of  H qdd = g - C  for this environment (H: joint-space inertia, + kdt on the joint diagonal for Stable-PD).
+//   root -> leaves: bias accelerations; leaves -> root: articulated inertia IA and bias force pA, one scalar elimination per dof
+//   (deepest first) = one step of the tree-structured L^T D L; base: 6x6 Cholesky in world axes (= the generalised base coordinates);
+//   root -> leaves: accelerations.  Bullet sub-steps (bullet != 0) also publish the factors (sU, sG), advance the link velocities in sV
+//   and the base velocity in sB by h * acceleration.  Returns this link's joint accelerations.
+template <int W, bool DEBUG>
+__device__ __noinline__ float3 aba_solve(Ctx c, float g0, float g1, float g2, float kdt, int bullet, float jvx, float jvy, float jvz, float gx, float gy, float gz, float h,
+                                         float* dbg_acc) {
+    using T = Tl<W>;
+    const StepLayout& LY = lay_of(c);
+    float* sU = c.E + LY.oU; const float* sS = c.E + LY.oR; const float* sW = c.E + LY.oW; float* sV = c.E + LY.oV; float* sG = c.E + LY.oG; float* sB = sG + 21;
+    const float* LKo = c.LK + c.li * kLkFloats;
+    const float mass = c.act ? LKo[kLM] : 0.f;
+    const float* q = sS + c.li * 12;
+    const V3 S0 = mk3(q[0], q[1], q[2]), S1 = mk3(q[3], q[4], q[5]), S2 = mk3(q[6], q[7], q[8]), cw = mk3(q[9], q[10], q[11]);
+    const float* vv = sV + c.li * 12;
+    const S6 vel = mks(mk3(vv[0], vv[1], vv[2]), mk3(vv[3], vv[4], vv[5]));
+    const V3 dw = mk3(vv[6], vv[7], vv[8]);
+    V3 jww = mk3(0, 0, 0);   // joint angular velocity, world axes
+    if (c.jtype == kJSpherical) jww = jvx * S0 + jvy * S1 + jvz * S2; else if (c.jtype == kJRevolute) jww = jvx * S0;
+    // ---- bias accelerations (root -> leaves)
+    S6 ab;
+    {
+        const S6 cj = mks(cross(vel.a, jww), cross(vel.l, jww));
+        if (c.lane == 0) {
+            const V3 bo = mk3(sB[7], sB[8], sB[9]), bv = mk3(sB[10], sB[11], sB[12]);
+            V3 wxv;
+            if (bullet) wxv = cross(bo, bv);
+            else {   // cRBDUtil::BuildCjRoot differentiates the root quaternion with the body-frame formula applied to the world-frame
+                     // angular velocity (RBDUtil.cpp:915-958): reproduced in the Stable-PD stage
+                const M3 Rwb = qmat(mkq(sB[3], sB[4], sB[5], sB[6]));
+                wxv = mulT(Rwb, cross(bo, mul(Rwb, bv)));
+            }
+            ab = shift_m(mks(mk3(0, 0, 0), mk3(-gx, -gy, -gz) - wxv), cw) + cj;
+        }
+#pragma unroll 1
+        for (int lv = 1; lv <= c.maxlevel; ++lv) {
+            S6 pa = T::shfl6(ab, c.plane);
+            if (c.level == lv) ab = shift_m(pa, cw) + cj;
+        }
+    }
+    // ---- leaves -> root
+    Art IA; S6 pA;
+    S6 U0, U1, U2; float inv0 = 0.f, inv1 = 0.f, inv2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;
+    {
+        const float* wsel = LKo + (bullet ? kLWb : kLWd);
+        float wl[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) wl[k] = c.act ? wsel[k] : 0.f;
+        M3 Rwl;
+        {
+            const float* w = sW + c.li * 12;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Rwl.m[k] = w[k];
+        }
+        rot_sym(Rwl, wl, IA.ww);     // link axes -> world axes
+        const V3 md = mass * dw;
+        IA.wv[0] = 0.f; IA.wv[1] = -md.z; IA.wv[2] = md.y; IA.wv[3] = md.z; IA.wv[4] = 0.f; IA.wv[5] = -md.x; IA.wv[6] = -md.y; IA.wv[7] = md.x; IA.wv[8] = 0.f;
+        IA.vv[0] = mass; IA.vv[1] = 0.f; IA.vv[2] = 0.f; IA.vv[3] = mass; IA.vv[4] = 0.f; IA.vv[5] = mass;
+        // h = I v ; pA = I ab + v x* h
+        const V3 hn = sym_mul(IA.ww, vel.a) + cross(md, vel.l), hf = mass * vel.l + cross(vel.a, md);
+        const V3 an = sym_mul(IA.ww, ab.a) + cross(md, ab.l), af = mass * ab.l + cross(ab.a, md);
+        pA = mks(an + cross(vel.a, hn) + cross(vel.l, hf), af + cross(vel.a, hf));
+        U0 = U1 = U2 = mks(mk3(0, 0, 0), mk3(0, 0, 0));
+    }
+    auto eliminate = [&](V3 dir, float g, S6& Uo, float& invo, float& uo) {
+        const V3 Ua = sym_mul(IA.ww, dir), Ul = wvT_mul(IA.wv, dir);
+        const float D = dot(dir, Ua) + kdt;
+        const float inv = 1.0f / D;
+        const float u = g - dot(dir, pA.a);
+        const V3 sa = inv * Ua, sl = inv * Ul;
+        IA.ww[0] -= sa.x * Ua.x; IA.ww[1] -= sa.x * Ua.y; IA.ww[2] -= sa.x * Ua.z; IA.ww[3] -= sa.y * Ua.y; IA.ww[4] -= sa.y * Ua.z; IA.ww[5] -= sa.z * Ua.z;
+        IA.wv[0] -= sa.x * Ul.x; IA.wv[1] -= sa.x * Ul.y; IA.wv[2] -= sa.x * Ul.z; IA.wv[3] -= sa.y * Ul.x; IA.wv[4] -= sa.y * Ul.y; IA.wv[5] -= sa.y * Ul.z;
+        IA.wv[6] -= sa.z * Ul.x; IA.wv[7] -= sa.z * Ul.y; IA.wv[8] -= sa.z * Ul.z;
+        IA.vv[0] -= sl.x * Ul.x; IA.vv[1] -= sl.x * Ul.y; IA.vv[2] -= sl.x * Ul.z; IA.vv[3] -= sl.y * Ul.y; IA.vv[4] -= sl.y * Ul.z; IA.vv[5] -= sl.z * Ul.z;
+        pA.a += u * sa; pA.l += u * sl;
+        Uo = mks(Ua, Ul); invo = inv; uo = u;
+    };
+    Art sd; S6 sf;
+#pragma unroll 1
+    for (int lv = c.maxlevel; lv >= 0; --lv) {
+        if (c.level == lv) {
+            if (c.ndof == 3) { eliminate(S2, g2, U2, inv2, u2); eliminate(S1, g1, U1, inv1, u1); }
+            if (c.ndof >= 1) eliminate(S0, g0, U0, inv0, u0);
+        }
+        // express (IA, pA) about the parent's pivot: shift by c = cw:  B' = B + C V ; A' = A - B C + C B'^T   (C = [c]x)
+        {
+            const V3 v0 = mk3(IA.vv[0], IA.vv[1], IA.vv[2]), v1 = mk3(IA.vv[1], IA.vv[3], IA.vv[4]), v2 = mk3(IA.vv[2], IA.vv[4], IA.vv[5]);   // columns (= rows) of V
+            const V3 b0 = mk3(IA.wv[0], IA.wv[1], IA.wv[2]), b1 = mk3(IA.wv[3], IA.wv[4], IA.wv[5]), b2 = mk3(IA.wv[6], IA.wv[7], IA.wv[8]);   // rows of B
+            const V3 k0 = cross(cw, v0), k1 = cross(cw, v1), k2 = cross(cw, v2);   // columns of C V
+            const V3 n0 = mk3(b0.x + k0.x, b0.y + k1.x, b0.z + k2.x), n1 = mk3(b1.x + k0.y, b1.y + k1.y, b1.z + k2.y), n2 = mk3(b2.x + k0.z, b2.y + k1.z, b2.z + k2.z);   // rows of B'
+            const V3 p0 = cross(b0, cw), p1 = cross(b1, cw), p2 = cross(b2, cw);   // rows of B C
+            const V3 q0 = cross(cw, n0), q1 = cross(cw, n1), q2 = cross(cw, n2);   // columns of C B'^T
+            sd.ww[0] = IA.ww[0] - p0.x + q0.x; sd.ww[1] = IA.ww[1] - p0.y + q1.x; sd.ww[2] = IA.ww[2] - p0.z + q2.x;
+            sd.ww[3] = IA.ww[3] - p1.y + q1.y; sd.ww[4] = IA.ww[4] - p1.z + q2.y; sd.ww[5] = IA.ww[5] - p2.z + q2.z;
+            sd.wv[0] = n0.x; sd.wv[1] = n0.y; sd.wv[2] = n0.z; sd.wv[3] = n1.x; sd.wv[4] = n1.y; sd.wv[5] = n1.z; sd.wv[6] = n2.x; sd.wv[7] = n2.y; sd.wv[8] = n2.z;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sd.vv[k] = IA.vv[k];
+            sf = shift_f(pA, cw);
+        }
+        if (lv == 0) break;
+        const int nslot = c.LVC[lv - 1];
+#pragma unroll 1
+        for (int k = 0; k < nslot; ++k) {
+            const int chl = (k < c.nchild) ? ((c.child_pack >> (8 * k)) & 0xff) : -1;
+            const int src = chl >= 0 ? chl : c.lane;
+            const bool take = chl >= 0 && c.level == lv - 1;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) { float g = T::shfl(sd.ww[j], src); if (take) IA.ww[j] += g; }
+#pragma unroll
+            for (int j = 0; j < 9; ++j) { float g = T::shfl(sd.wv[j], src); if (take) IA.wv[j] += g; }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) { float g = T::shfl(sd.vv[j], src); if (take) IA.vv[j] += g; }
+            const S6 gf = T::shfl6(sf, src);
+            if (take) { pA.a += gf.a; pA.l += gf.l; }
+        }
+    }
+    // ---- base: the (massless) floating base carries the root link's articulated inertia; Cholesky of the 6x6 in world axes at the base
+    // origin, i.e. directly in the generalised base coordinates [omega_w, v_w]
+    S6 aB = mks(mk3(0, 0, 0), mk3(0, 0, 0));
+    if (c.lane == 0) {
+        float a[6][6];   // lower triangle a[i][j], j <= i ; coordinates [w(3); v(3)]
+        a[0][0] = sd.ww[0]; a[1][0] = sd.ww[1]; a[1][1] = sd.ww[3]; a[2][0] = sd.ww[2]; a[2][1] = sd.ww[4]; a[2][2] = sd.ww[5];
+        a[3][0] = sd.wv[0]; a[3][1] = sd.wv[3]; a[3][2] = sd.wv[6]; a[4][0] = sd.wv[1]; a[4][1] = sd.wv[4]; a[4][2] = sd.wv[7]; a[5][0] = sd.wv[2]; a[5][1] = sd.wv[5]; a[5][2] = sd.wv[8];   // B'^T
+        a[3][3] = sd.vv[0]; a[4][3] = sd.vv[1]; a[4][4] = sd.vv[3]; a[5][3] = sd.vv[2]; a[5][4] = sd.vv[4]; a[5][5] = sd.vv[5];
+        float gi[6];   // 1 / G_ii
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            float d = a[j][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) d -= a[j][k] * a[j][k];
+            gi[j] = rsqrtf(d);
+            a[j][j] = d * gi[j];
+#pragma unroll
+            for (int i = j + 1; i < 6; ++i) {
+                float s = a[i][j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) s -= a[i][k] * a[j][k];
+                a[i][j] = s * gi[j];
+            }
+        }
+        // x = -(G G^T)^-1 p
+        float x[6] = {-sf.a.x, -sf.a.y, -sf.a.z, -sf.l.x, -sf.l.y, -sf.l.z};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int k = 0; k < i; ++k) x[i] -= a[i][k] * x[k];
+            x[i] *= gi[i];
+        }
+#pragma unroll
+        for (int i = 5; i >= 0; --i) {
+#pragma unroll
+            for (int k = i + 1; k < 6; ++k) x[i] -= a[k][i] * x[k];
+            x[i] *= gi[i];
+        }
+        aB = mks(mk3(x[0], x[1], x[2]), mk3(x[3], x[4], x[5]));
+        if (bullet) {   // factor kept for the constraint rows: strict lower part (15) + reciprocal diagonal (6); base velocity += h * acceleration
+            int o = 0;
+#pragma unroll
+            for (int i = 1; i < 6; ++i)
+#pragma unroll
+                for (int k = 0; k < i; ++k) sG[o++] = a[i][k];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) sG[15 + i] = gi[i];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) sB[7 + i] = cl100(sB[7 + i] + h * x[i]);
+        }
+        if (DEBUG && dbg_acc) for (int i = 0; i < 6; ++i) dbg_acc[i] = x[i];
+    }
+    // ---- accelerations (root -> leaves): qdd_d = (u_d - U_d . a') / D_d
+    float qd0 = 0.f, qd1 = 0.f, qd2 = 0.f;
+    S6 al = mks(mk3(0, 0, 0), mk3(0, 0, 0));   // link acceleration (deviation from the bias acceleration)
+    auto descend = [&](S6 a) {
+        if (c.ndof >= 1) { qd0 = inv0 * (u0 - sdot(a, U0)); a.a += qd0 * S0; }
+        if (c.ndof == 3) { qd1 = inv1 * (u1 - sdot(a, U1)); a.a += qd1 * S1; qd2 = inv2 * (u2 - sdot(a, U2)); a.a += qd2 * S2; }
+        return a;
+    };
+    if (c.lane == 0) al = descend(shift_m(aB, cw));
+#pragma unroll 1
+    for (int lv = 1; lv <= c.maxlevel; ++lv) {
+        S6 pa = T::shfl6(al, c.plane);
+        if (c.level == lv) al = descend(shift_m(pa, cw));
+    }
+    if (bullet && c.act) {   // publish the factors and the advanced link velocity (linear in the generalised velocities; the clamp only acts on exploding states)
+        float* u = sU + c.lane * 24;
+        u[0] = U0.a.x; u[1] = U0.a.y; u[2] = U0.a.z; u[3] = U0.l.x; u[4] = U0.l.y; u[5] = U0.l.z;
+        u[6] = U1.a.x; u[7] = U1.a.y; u[8] = U1.a.z; u[9] = U1.l.x; u[10] = U1.l.y; u[11] = U1.l.z;
+        u[12] = U2.a.x; u[13] = U2.a.y; u[14] = U2.a.z; u[15] = U2.l.x; u[16] = U2.l.y; u[17] = U2.l.z;
+        u[18] = inv0; u[19] = inv1; u[20] = inv2; u[21] = sqrtf(inv0); u[22] = sqrtf(inv1); u[23] = sqrtf(inv2);
+        float* v = sV + c.lane * 12;
+        v[0] = vel.a.x + h * al.a.x; v[1] = vel.a.y + h * al.a.y; v[2] = vel.a.z + h * al.a.z;
+        v[3] = vel.l.x + h * al.l.x; v[4] = vel.l.y + h * al.l.y; v[5] = vel.l.z + h * al.l.z;
+    }
+    __syncwarp();
+    return make_float3(qd0, qd1, qd2);
+}
+
+// Velocity correction of the constraint impulses: dv = L^-1 D^-1/2 z with z = Y^T lambda (sZ), by the root -> leaves pass over the factors
+// published by aba_solve.  Lane 0 also corrects the base velocity in sB.  Returns this link's joint-rate corrections.
+template <int W>
+__device__ __noinline__ float3 dv_pass(Ctx c) {
+    using T = Tl<W>;
+    const StepLayout& LY = lay_of(c);
+    const float* sU = c.E + LY.oU; const float* sS = c.E + LY.oR; float* sG = c.E + LY.oG; float* sB = sG + 21; const float* sZ = c.E + LY.oZ;
+    const float* q = sS + c.li * 12;
+    const V3 S0 = mk3(q[0], q[1], q[2]), S1 = mk3(q[3], q[4], q[5]), S2 = mk3(q[6], q[7], q[8]), cw = mk3(q[9], q[10], q[11]);
+    const float* u = sU + c.li * 24;
+    const int dof0 = reinterpret_cast<const int*>(c.LK + c.li * kLkFloats)[kLInt2] & 0xff;
+    S6 dB = mks(mk3(0, 0, 0), mk3(0, 0, 0));
+    if (c.lane == 0) {   // base: dB = G^-T z
+        float x[6] = {sZ[0], sZ[1], sZ[2], sZ[3], sZ[4], sZ[5]};
+        float g[15];
+#pragma unroll
+        for (int k = 0; k < 15; ++k) g[k] = sG[k];
+#pragma unroll
+        for (int i = 5; i >= 0; --i) {
+#pragma unroll
+            for (int k = i + 1; k < 6; ++k) x[i] -= g[k * (k - 1) / 2 + i] * x[k];
+            x[i] *= sG[15 + i];
+        }
+        dB = mks(mk3(x[0], x[1], x[2]), mk3(x[3], x[4], x[5]));
+#pragma unroll
+        for (int i = 0; i < 6; ++i) sB[7 + i] = cl100(sB[7 + i] + x[i]);
+    }
+    float z0 = 0.f, z1 = 0.f, z2 = 0.f, qd0 = 0.f, qd1 = 0.f, qd2 = 0.f;
+    if (c.ndof >= 1) z0 = sZ[dof0] * u[21];
+    if (c.ndof == 3) { z1 = sZ[dof0 + 1] * u[22]; z2 = sZ[dof0 + 2] * u[23]; }
+    auto descend = [&](S6 a) {
+        if (c.ndof >= 1) { qd0 = z0 - u[18] * (a.a.x * u[0] + a.a.y * u[1] + a.a.z * u[2] + a.l.x * u[3] + a.l.y * u[4] + a.l.z * u[5]); a.a += qd0 * S0; }
+        if (c.ndof == 3) {
+            qd1 = z1 - u[19] * (a.a.x * u[6] + a.a.y * u[7] + a.a.z * u[8] + a.l.x * u[9] + a.l.y * u[10] + a.l.z * u[11]); a.a += qd1 * S1;
+            qd2 = z2 - u[20] * (a.a.x * u[12] + a.a.y * u[13] + a.a.z * u[14] + a.l.x * u[15] + a.l.y * u[16] + a.l.z * u[17]); a.a += qd2 * S2;
+        }
+        return a;
+    };
+    S6 al = mks(mk3(0, 0, 0), mk3(0, 0, 0));
+    if (c.lane == 0) al = descend(shift_m(dB, cw));
+#pragma unroll 1
+    for (int lv = 1; lv <= c.maxlevel; ++lv) {
+        S6 pa = T::shfl6(al, c.plane);
+        if (c.level == lv) al = descend(shift_m(pa, cw));
+    }
+    __syncwarp();
+    return make_float3(qd0, qd1, qd2);
+}
+
 template <int W, bool DEBUG>
 __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevModel* __restrict__ gm, DevState st, const double* __restrict__ frame_times,
                                                                        const float* __restrict__ frames, double dt, int n_updates, int sim_substeps, StepLayout LY, int sync_mode) {
@@ -513,17 +993,16 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     const int lane = threadIdx.x % W;
     const int env = blockIdx.x * tiles + tile;   // host guarantees num_envs (padded) is a multiple of tiles
     const DevModel& M = *gm;
-    const int nl = LY.nl, n = LY.n, maxlevel = M.maxlevel, CL = LY.chain_len, MR = LY.maxrows;
+    const int nl = LY.nl, CL = LY.chain_len;
     const bool act = lane < nl;
     const int li = act ? lane : nl - 1;
-    const DevLink& L = M.link[li];
 
     // ---- block-shared tables: per-link constants (LK), common chain depth of two links (CD), chain depth -> dof (CH), children per level
     float* LK = sm;
     unsigned char* CD = reinterpret_cast<unsigned char*>(sm + nl * kLkFloats);
     unsigned char* CH = CD + nl * nl;
     int* LVC = reinterpret_cast<int*>(sm + LY.hot_floats - 8);
-    int* LYS = reinterpret_cast<int*>(sm + LY.hot_floats - 8 - 24);   // shared copy of the layout for the non-inlined routines
+    int* LYS = reinterpret_cast<int*>(sm + LY.hot_floats - 8 - 24);   // shared copy of the layout for the phase routines
     for (int j = threadIdx.x; j < nl; j += blockDim.x) {
         const DevLink& K = M.link[j];
         float* q = LK + j * kLkFloats;
@@ -543,10 +1022,10 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         reinterpret_cast<int*>(q)[kLFlg] = (K.shape & 0xff) | ((K.fall_contact & 0xff) << 8) | ((K.has_limit & 0xff) << 16);
         for (int d = 0; d < CL; ++d) CH[j * CL + d] = M.chain_dof[j][d];
         for (int b = 0; b < nl; ++b) {
-            int c = 0;
+            int cnt = 0;
             const int lim = min(K.last_depth, M.link[b].last_depth);
-            while (c <= lim && M.chain_dof[j][c] == M.chain_dof[b][c]) ++c;
-            CD[j * nl + b] = static_cast<unsigned char>(c);
+            while (cnt <= lim && M.chain_dof[j][cnt] == M.chain_dof[b][cnt]) ++cnt;
+            CD[j * nl + b] = static_cast<unsigned char>(cnt);
         }
     }
     if (threadIdx.x == blockDim.x - 1) {
@@ -559,25 +1038,23 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         LVC[threadIdx.x] = mx;
     }
     __syncthreads();
-    auto lk_i = [&](int j) { return reinterpret_cast<const int*>(LK + j * kLkFloats)[kLInt]; };
-    auto lk_i2 = [&](int j) { return reinterpret_cast<const int*>(LK + j * kLkFloats)[kLInt2]; };
 
-    float* E = sm + LY.hot_floats + tile * LY.env_floats;   // this environment's block
-    float* sU = E + LY.oU; float* sS = E + LY.oR; float* sW = E + LY.oW; float* sV = E + LY.oV; float* sA = E + LY.oA; float* sY = E + LY.oY;
-    float* sLam = E + LY.oLam; float* sRhs = E + LY.oRhs; float* sInv = E + LY.oInv; int* sRl = reinterpret_cast<int*>(E + LY.oRl);
-    float* sPp = E + LY.oPp; float* sPi = E + LY.oPi; int* sPr = reinterpret_cast<int*>(E + LY.oPr);
-    float* sQ = E + LY.oQ; float* sG = E + LY.oG; float* sZ = E + LY.oZ;
-
-    // ---- per-lane model constants kept in registers (the rest is read from the shared LK table when needed)
+    Ctx C;
+    {
+        const DevLink& L = M.link[li];
+        C.E = sm + LY.hot_floats + tile * LY.env_floats; C.LYS = LYS; C.LK = LK; C.LVC = LVC;
+        C.lane = lane; C.li = li; C.plane = L.parent >= 0 ? L.parent : 0; C.level = act ? L.level : 1000; C.ndof = act ? L.ndof : 0; C.jtype = L.jtype;
+        C.nchild = act ? L.nchild : 0;
+        C.child_pack = (L.child[0] & 0xff) | ((L.child[1] & 0xff) << 8) | ((L.child[2] & 0xff) << 16) | ((L.child[3] & 0xff) << 24);
+        C.maxlevel = M.maxlevel; C.act = act;
+    }
+    float* E = C.E;
+    float* sV = E + LY.oV; float* sG = E + LY.oG; float* sQ = E + LY.oQ; float* sLam = E + LY.oLam;
     const float* LKo = LK + li * kLkFloats;
-    const int parent = L.parent, jtype = L.jtype, ndof = act ? L.ndof : 0, dof0 = L.dof0, level = act ? L.level : 1000;
-    const V3 axis = mk3(L.axis[0], L.axis[1], L.axis[2]);
-    const float mass = act ? L.mass : 0.f;
-    const int plane = parent >= 0 ? parent : 0;
-    const int nchild = act ? L.nchild : 0;
-    const int child_pack = (L.child[0] & 0xff) | ((L.child[1] & 0xff) << 8) | ((L.child[2] & 0xff) << 16) | ((L.child[3] & 0xff) << 24);
+    const int ndof = C.ndof, jtype = C.jtype;
+    const int dof0 = reinterpret_cast<const int*>(LKo)[kLInt2] & 0xff;
     const int lflags = reinterpret_cast<const int*>(LKo)[kLFlg];
-    const int shape = lflags & 0xff; const bool fall_contact = ((lflags >> 8) & 0xff) != 0, has_limit = ((lflags >> 16) & 0xff) != 0;
+    const bool fall_contact = ((lflags >> 8) & 0xff) != 0, has_limit = ((lflags >> 16) & 0xff) != 0;
 
     // ---- state load (env-major block, float4)
     const int ss = sim_stride(nl);
@@ -592,10 +1069,6 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         sB[0] = b0.x; sB[1] = b0.y; sB[2] = b0.z; sB[3] = b1.x; sB[4] = b1.y; sB[5] = b1.z; sB[6] = b1.w;
         sB[7] = b2.x; sB[8] = b2.y; sB[9] = b2.z; sB[10] = b3.x; sB[11] = b3.y; sB[12] = b3.z;
     }
-    auto bPos = [&]() { return mk3(sB[0], sB[1], sB[2]); };
-    auto bQuat = [&]() { return mkq(sB[3], sB[4], sB[5], sB[6]); };
-    auto bOmega = [&]() { return mk3(sB[7], sB[8], sB[9]); };
-    auto bVel = [&]() { return mk3(sB[10], sB[11], sB[12]); };
     float4 jp = reinterpret_cast<const float4*>(sim + 16)[li];
     float4 jv = reinterpret_cast<const float4*>(sim + 16 + 4 * nl)[li];
     // the f64 clocks (timer, mocap time, controller time, origin) live in global memory and are advanced in place by lane 0 once per update;
@@ -608,21 +1081,12 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
 
     const float h = static_cast<float>(dt) / static_cast<float>(sim_substeps);
     const float fdt = static_cast<float>(dt);
-    const V3 grav = mk3(M.gravity[0], M.gravity[1], M.gravity[2]);
+    const float gx = M.gravity[0], gy = M.gravity[1], gz = M.gravity[2];
     const float scale = M.scale, mu = M.friction;
     float* dbg = (DEBUG && st.pdbg) ? st.pdbg + static_cast<size_t>(env) * kDebugFloats : nullptr;   // test hook: stage dumps of the first update
 
-    // configuration / velocity dependent registers (world axes)
-    V3 S0, S1, S2;      // joint axes: rows of the world->link rotation for a spherical joint, the hinge axis (S0) for a revolute joint
-    V3 cw;              // parent pivot -> own pivot
-    V3 dw;              // own pivot -> centre of mass
-    S6 vel;             // link spatial velocity at the pivot
     float tau0 = 0.f, tau1 = 0.f, tau2 = 0.f;   // joint torques of the current update (body-frame components / revolute scalar)
     bool in_contact_tol = false;
-    auto own_Rwl = [&]() { M3 m; const float* w = sW + li * 12; for (int k = 0; k < 9; ++k) m.m[k] = w[k]; return m; };   // world->link axes (written by the kinematics pass)
-    auto sdir = [&](int d) { return d == 0 ? S0 : (d == 1 ? S1 : S2); };
-    auto shift_m = [](S6 m, V3 c) { return mks(m.a, m.l + cross(m.a, c)); };   // motion vector: reference point moved by +c
-    auto shift_f = [](S6 f, V3 c) { return mks(f.a + cross(c, f.l), f.l); };   // force vector: reference point moved by -c (child pivot -> parent pivot)
 
 #ifdef DM_PROFILE
     // per-warp cycle counters per code section (profile build only): lane 0 accumulates, written to st.pdbg at the end
@@ -630,12 +1094,9 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     if ((threadIdx.x & 31) == 0) for (int k = 0; k < 16; ++k) PRF[k] = 0u;
     unsigned int prf_t = static_cast<unsigned int>(clock64());
 #define PROF(sec) do { if ((threadIdx.x & 31) == 0) { unsigned int t_ = static_cast<unsigned int>(clock64()); PRF[sec] += t_ - prf_t; prf_t = t_; } } while (0)
-#else
-#define PROF(sec) do { } while (0)
-#endif
-#ifdef DM_PROFILE
     unsigned int* PRFP = PRF;
 #else
+#define PROF(sec) do { } while (0)
     unsigned int* PRFP = nullptr;
 #endif
     bool need_kin = true, pending_flags = false;
@@ -644,53 +1105,8 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     const int sync_period = sync_mode > 0 ? 1 : (sync_mode == 0 ? stages_per_upd : (sync_mode <= -1000 ? 0 : -sync_mode * stages_per_upd));
 #pragma unroll 1
     for (int stage = 0; stage <= total_stages; ++stage) {
-        // =================================================================== forward kinematics + link velocities (root -> leaves)
-        if (need_kin) {
-            need_kin = false;
-            const Q4 zrot = mkq(LKo[kLZr], LKo[kLZr + 1], LKo[kLZr + 2], LKo[kLZr + 3]);
-            const V3 cvec = mk3(LKo[kLC], LKo[kLC + 1], LKo[kLC + 2]);
-            Q4 cached;
-            if (jtype == kJSpherical) cached = qmul(mkq(jp.x, jp.y, jp.z, -jp.w), zrot);
-            else if (jtype == kJRevolute) {
-                float s, c;
-                __sincosf(-0.5f * jp.x, &s, &c);   // |angle| <= pi/2 + limit overshoot: fast path is accurate to ~1 ulp of the result scale
-                cached = qmul(mkq(axis.x * s, axis.y * s, axis.z * s, c), zrot);
-            } else cached = zrot;
-            const M3 R = qmat(cached);
-            V3 jw = mk3(0, 0, 0);
-            if (jtype == kJSpherical) jw = mk3(jv.x, jv.y, jv.z); else if (jtype == kJRevolute) jw = jv.x * axis;
-            M3 Rwl; V3 Pw;
-            if (lane == 0) {
-                const M3 Rwb = qmat(bQuat());
-                const V3 bo = bOmega();
-                Rwl = mul(R, Rwb); cw = mulT(Rwb, cvec); Pw = bPos() + cw;
-                vel = mks(bo + mulT(Rwl, jw), bVel() + cross(bo, cw));
-            }
-#pragma unroll 1
-            for (int lv = 1; lv <= maxlevel; ++lv) {
-                M3 pR; V3 pp; S6 pv;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) pR.m[k] = T::shfl(Rwl.m[k], plane);
-                pp = T::shfl3(Pw, plane);
-                pv = T::shfl6(vel, plane);
-                if (level == lv) {
-                    Rwl = mul(R, pR); cw = mulT(pR, cvec); Pw = pp + cw;
-                    vel = mks(pv.a + mulT(Rwl, jw), pv.l + cross(pv.a, cw));
-                }
-            }
-            dw = mulT(Rwl, mk3(LKo[kLD], LKo[kLD + 1], LKo[kLD + 2]));
-            S0 = mk3(Rwl.m[0], Rwl.m[1], Rwl.m[2]); S1 = mk3(Rwl.m[3], Rwl.m[4], Rwl.m[5]); S2 = mk3(Rwl.m[6], Rwl.m[7], Rwl.m[8]);
-            if (jtype != kJSpherical) S0 = mulT(Rwl, axis);
-            if (act) {
-                float* w = sW + lane * 12; float* q = sS + lane * 12;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) w[k] = Rwl.m[k];
-                w[9] = Pw.x; w[10] = Pw.y; w[11] = Pw.z;
-                q[0] = S0.x; q[1] = S0.y; q[2] = S0.z; q[3] = S1.x; q[4] = S1.y; q[5] = S1.z; q[6] = S2.x; q[7] = S2.y; q[8] = S2.z;
-                q[9] = cw.x; q[10] = cw.y; q[11] = cw.z;
-            }
-            __syncwarp();
-        }
+        // =================================================================== forward kinematics + link velocities
+        if (need_kin) { need_kin = false; kin_pass<W>(C, jp, jv); }
         PROF(0);
         // =================================================================== post-update flags of the update that just finished
         if (pending_flags) {
@@ -701,8 +1117,10 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             const unsigned fseg = (W == 32) ? fb : ((fb >> (threadIdx.x & 16)) & 0xffffu);
             const int fallen = (fseg != 0 && M.enable_contact_fall) ? 1 : 0;
             // exploded velocities: any link |v|, |w| component > 100 in world axes (cSimCharacter::HasVelExploded); v at the COM
-            const V3 vw = (vel.l + cross(vel.a, dw)) * (1.0f / scale), ww = vel.a;
-            float mx = fmaxf(fmaxf(fmaxf(fabsf(vw.x), fabsf(vw.y)), fabsf(vw.z)), fmaxf(fmaxf(fabsf(ww.x), fabsf(ww.y)), fabsf(ww.z)));
+            const float* v = sV + li * 12;
+            const V3 wa = mk3(v[0], v[1], v[2]);
+            const V3 vw = (mk3(v[3], v[4], v[5]) + cross(wa, mk3(v[6], v[7], v[8]))) * (1.0f / scale);
+            float mx = fmaxf(fmaxf(fmaxf(fabsf(vw.x), fabsf(vw.y)), fabsf(vw.z)), fmaxf(fmaxf(fabsf(wa.x), fabsf(wa.y)), fabsf(wa.z)));
             const unsigned eb = __ballot_sync(0xffffffffu, act && mx > 100.f);
             const unsigned eseg = (W == 32) ? eb : ((eb >> (threadIdx.x & 16)) & 0xffffu);
             if (alive) {
@@ -734,7 +1152,6 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         if (__ballot_sync(0xffffffffu, alive) == 0u) continue;   // both environments of this warp are frozen
         const int ph = stage % stages_per_upd;      // 0: Stable-PD stage, 1..sim_substeps: Bullet sub-steps
         const bool first_upd = stage < stages_per_upd;
-        int P = 0;
         if (ph == 0) {
             // ---------------- clocks: cScene::Update, cSceneImitate::UpdateKinChar, cDeepMimicCharController::UpdateCalcTau
             int cb = 0;
@@ -782,147 +1199,8 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             }
             cbits = T::shfli(cb, 0);
             need_action = 0;
-        } else {
-            // ---------------- collision: link convex vs plane y = 0, persistent manifold of <= 4 points per link (btPersistentManifold)
-            int cnt = 0;
-            float mp[48];
-            const M3 Rwl = own_Rwl();
-            {
-                const float4* mg = reinterpret_cast<const float4*>(mani + li * kManifoldFloats);
-#pragma unroll
-                for (int k = 0; k < 12; ++k) { float4 v = mg[k]; mp[4 * k] = v.x; mp[4 * k + 1] = v.y; mp[4 * k + 2] = v.z; mp[4 * k + 3] = v.w; }
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) if (mp[c * 12] != 0.f && cnt == c) cnt = c + 1;
-            const float thr = LKo[kLThr];
-            const V3 he = mk3(LKo[kLHe], LKo[kLHe + 1], LKo[kLHe + 2]);
-            const V3 pos = mk3(sW[li * 12 + 9], sW[li * 12 + 10], sW[li * 12 + 11]) + dw;     // COM, world (Bullet's link collider frame)
-            V3 dl = mul(Rwl, mk3(0.f, -1.f, 0.f));   // support direction -n in link coordinates
-            V3 vtx;
-            if (shape == kSBox) vtx = mk3(dl.x >= 0 ? he.x : -he.x, dl.y >= 0 ? he.y : -he.y, dl.z >= 0 ? he.z : -he.z);
-            else {
-                V3 sup = mk3(0, 0, 0);
-                if (shape == kSCapsule) sup = mk3(0.f, (dl.y >= 0.f) ? he.y : -he.y, 0.f);   // first end point wins ties
-                float inv = rsqrtf(dot(dl, dl));
-                vtx = sup + (he.x * inv) * dl;
-            }
-            const V3 vw = pos + mulT(Rwl, vtx);
-            const float dist = vw.y;
-            if (act && dist < thr) {
-                float best = thr * thr; int nearest = -1;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) if (c < cnt) {
-                    float dx = mp[c * 12 + 1] - vtx.x, dy = mp[c * 12 + 2] - vtx.y, dz = mp[c * 12 + 3] - vtx.z, dd = dx * dx + dy * dy + dz * dz;
-                    if (dd < best) { best = dd; nearest = c; }
-                }
-                int idx = nearest;
-                float k7 = 0, k8 = 0, k9 = 0, k11 = 0;
-                if (nearest >= 0) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) if (c == nearest) { k7 = mp[c * 12 + 7]; k8 = mp[c * 12 + 8]; k9 = mp[c * 12 + 9]; k11 = mp[c * 12 + 11]; }
-                } else if (cnt < 4) { idx = cnt; cnt++; }
-                else {   // btPersistentManifold::sortCachedPoints
-                    int mpi = -1; float mpen = dist;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) if (mp[c * 12 + 10] < mpen) { mpi = c; mpen = mp[c * 12 + 10]; }
-                    auto Pt = [&](int c) { return mk3(mp[c * 12 + 1], mp[c * 12 + 2], mp[c * 12 + 3]); };
-                    auto area = [&](V3 a, V3 b) { V3 c = cross(a, b); return dot(c, c); };
-                    float res[4] = {0, 0, 0, 0};
-                    if (mpi != 0) res[0] = area(vtx - Pt(1), Pt(3) - Pt(2));
-                    if (mpi != 1) res[1] = area(vtx - Pt(0), Pt(3) - Pt(2));
-                    if (mpi != 2) res[2] = area(vtx - Pt(0), Pt(3) - Pt(1));
-                    if (mpi != 3) res[3] = area(vtx - Pt(0), Pt(2) - Pt(1));
-                    idx = 0; float bv = fabsf(res[0]);
-#pragma unroll
-                    for (int c = 1; c < 4; ++c) if (fabsf(res[c]) > bv) { bv = fabsf(res[c]); idx = c; }
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) if (c == idx) {
-                    float* q = mp + c * 12;
-                    q[0] = 1.f; q[1] = vtx.x; q[2] = vtx.y; q[3] = vtx.z; q[4] = vw.x; q[5] = 0.f; q[6] = vw.z; q[7] = k7; q[8] = k8; q[9] = k9; q[10] = dist; q[11] = k11;
-                }
-            }
-            // refreshContactPoints
-#pragma unroll
-            for (int c = 3; c >= 0; --c) if (c < cnt) {
-                V3 pa = pos + mulT(Rwl, mk3(mp[c * 12 + 1], mp[c * 12 + 2], mp[c * 12 + 3]));
-                mp[c * 12 + 10] = pa.y - mp[c * 12 + 5];
-                mp[c * 12 + 11] += 1.f;
-            }
-#pragma unroll
-            for (int c = 3; c >= 0; --c) if (c < cnt) {
-                V3 pa = pos + mulT(Rwl, mk3(mp[c * 12 + 1], mp[c * 12 + 2], mp[c * 12 + 3]));
-                bool rm = !(mp[c * 12 + 10] <= thr);
-                if (!rm) {
-                    float dx = mp[c * 12 + 4] - pa.x, dy = mp[c * 12 + 5] - (pa.y - mp[c * 12 + 10]), dz = mp[c * 12 + 6] - pa.z;
-                    rm = (dx * dx + dy * dy + dz * dz) > thr * thr;
-                }
-                if (rm) {
-                    const int last = cnt - 1;
-#pragma unroll
-                    for (int l2 = 0; l2 < 4; ++l2) if (l2 == last) {
-                        if (c != l2) for (int k = 0; k < 12; ++k) mp[c * 12 + k] = mp[l2 * 12 + k];
-                        mp[l2 * 12] = 0.f;
-                    }
-                    cnt--;
-                }
-            }
-            if (!act || !alive) cnt = 0;   // finished episodes are frozen until dm_reset: no constraint rows for them
-            in_contact_tol = false;   // cContactManager::Update: distance <= 0.001 * scale
-#pragma unroll
-            for (int c = 0; c < 4; ++c) if (c < cnt && mp[c * 12 + 10] <= 0.001f * scale) in_contact_tol = true;
-            if (act && alive) {
-                float4* mo = reinterpret_cast<float4*>(mani + li * kManifoldFloats);
-#pragma unroll
-                for (int k = 0; k < 12; ++k) mo[k] = make_float4(mp[4 * k], mp[4 * k + 1], mp[4 * k + 2], mp[4 * k + 3]);
-            }
-            // exclusive prefix over lanes -> point indices; publish points to the solver
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < W; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o, W); if (lane >= o) incl += t; }
-            const int base = incl - cnt;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) if (c < cnt) {
-                const int p = base + c;
-                if (p < LY.maxpts) {
-                    V3 pa = pos + mulT(Rwl, mk3(mp[c * 12 + 1], mp[c * 12 + 2], mp[c * 12 + 3]));
-                    sPp[p * 4] = pa.x; sPp[p * 4 + 1] = pa.y; sPp[p * 4 + 2] = pa.z; sPp[p * 4 + 3] = mp[c * 12 + 10];
-                    sPi[p] = mp[c * 12 + 7];
-                    sPr[p] = lane * 4 + c;
-                } else f_over = 1;
-            }
-            P = min(T::shfli(incl, W - 1), LY.maxpts);
-        }
-
-        PROF(3);
-        // =================================================================== bias accelerations (root -> leaves), Stable-PD right-hand side
-        const bool bullet = ph != 0;
-        V3 jww = mk3(0, 0, 0);   // joint angular velocity, world axes
-        if (jtype == kJSpherical) jww = jv.x * S0 + jv.y * S1 + jv.z * S2; else if (jtype == kJRevolute) jww = jv.x * S0;
-        S6 ab;
-        {
-            const S6 cj = mks(cross(vel.a, jww), cross(vel.l, jww));
-            if (lane == 0) {
-                const V3 bo = bOmega(), bv = bVel();
-                V3 wxv;
-                if (bullet) wxv = cross(bo, bv);
-                else {   // cRBDUtil::BuildCjRoot differentiates the root quaternion with the body-frame formula applied to the world-frame
-                         // angular velocity (RBDUtil.cpp:915-958): reproduced in the Stable-PD stage
-                    const M3 Rwb = qmat(bQuat());
-                    wxv = mulT(Rwb, cross(bo, mul(Rwb, bv)));
-                }
-                ab = shift_m(mks(mk3(0, 0, 0), -grav - wxv), cw) + cj;
-            }
-#pragma unroll 1
-            for (int lv = 1; lv <= maxlevel; ++lv) {
-                S6 pa = T::shfl6(ab, plane);
-                if (level == lv) ab = shift_m(pa, cw) + cj;
-            }
-        }
-        float pe0 = 0.f, pe1 = 0.f, pe2 = 0.f, kdt = 0.f, kd = 0.f;
-        float g0 = tau0, g1 = tau1, g2 = tau2;   // generalised joint force of this stage
-        if (!bullet) {
-            // cImpPDController::CalcControlForces (ImpPDController.cpp:136-195) in the body-frame joint coordinates of the sim state
+            PROF(3);
+            // ---------------- cImpPDController::CalcControlForces (ImpPDController.cpp:136-195) in the body-frame joint coordinates of the sim state
             const float4 tg = reinterpret_cast<const float4*>(sim + 16 + 8 * nl)[li];
             float e0 = 0, e1 = 0, e2 = 0;
             if (jtype == kJSpherical) {
@@ -935,190 +1213,38 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             } else if (jtype == kJRevolute) {
                 e0 = tg.x - (normalize_angle3(jp.x) + fdt * jv.x);
             }
-            const float kp = LKo[kLKp]; kd = LKo[kLKd];
-            pe0 = kp * e0; pe1 = kp * e1; pe2 = kp * e2;
-            kdt = fdt * kd;
-            g0 = pe0 - kd * jv.x; g1 = pe1 - kd * jv.y; g2 = pe2 - kd * jv.z;
-        }
-
-        // =================================================================== articulated-body pass (leaves -> root)
-        // pA: bias force of the subtree with zero joint accelerations (recursive Newton-Euler force, gravity as base acceleration);
-        // IA: articulated inertia.  Eliminating dof d of a joint (deepest first) is one step of the tree-structured L^T D L.
-        Art IA; S6 pA;
-        S6 U0, U1, U2; float inv0 = 0.f, inv1 = 0.f, inv2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;
-        {
-            const float* wsel = LKo + (bullet ? kLWb : kLWd);
-            float wl[6];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) wl[k] = act ? wsel[k] : 0.f;
-            rot_sym(own_Rwl(), wl, IA.ww);     // link axes -> world axes
-            const V3 md = mass * dw;
-            IA.wv[0] = 0.f; IA.wv[1] = -md.z; IA.wv[2] = md.y; IA.wv[3] = md.z; IA.wv[4] = 0.f; IA.wv[5] = -md.x; IA.wv[6] = -md.y; IA.wv[7] = md.x; IA.wv[8] = 0.f;
-            IA.vv[0] = mass; IA.vv[1] = 0.f; IA.vv[2] = 0.f; IA.vv[3] = mass; IA.vv[4] = 0.f; IA.vv[5] = mass;
-            // h = I v ; pA = I ab + v x* h
-            const V3 hn = sym_mul(IA.ww, vel.a) + cross(md, vel.l), hf = mass * vel.l + cross(vel.a, md);
-            const V3 an = sym_mul(IA.ww, ab.a) + cross(md, ab.l), af = mass * ab.l + cross(ab.a, md);
-            pA = mks(an + cross(vel.a, hn) + cross(vel.l, hf), af + cross(vel.a, hf));
-            U0 = U1 = U2 = mks(mk3(0, 0, 0), mk3(0, 0, 0));
-        }
-        auto eliminate = [&](V3 dir, float g, S6& Uo, float& invo, float& uo) {
-            const V3 Ua = sym_mul(IA.ww, dir), Ul = wvT_mul(IA.wv, dir);
-            const float D = dot(dir, Ua) + kdt;
-            const float inv = 1.0f / D;
-            const float u = g - dot(dir, pA.a);
-            const V3 sa = inv * Ua, sl = inv * Ul;
-            IA.ww[0] -= sa.x * Ua.x; IA.ww[1] -= sa.x * Ua.y; IA.ww[2] -= sa.x * Ua.z; IA.ww[3] -= sa.y * Ua.y; IA.ww[4] -= sa.y * Ua.z; IA.ww[5] -= sa.z * Ua.z;
-            IA.wv[0] -= sa.x * Ul.x; IA.wv[1] -= sa.x * Ul.y; IA.wv[2] -= sa.x * Ul.z; IA.wv[3] -= sa.y * Ul.x; IA.wv[4] -= sa.y * Ul.y; IA.wv[5] -= sa.y * Ul.z;
-            IA.wv[6] -= sa.z * Ul.x; IA.wv[7] -= sa.z * Ul.y; IA.wv[8] -= sa.z * Ul.z;
-            IA.vv[0] -= sl.x * Ul.x; IA.vv[1] -= sl.x * Ul.y; IA.vv[2] -= sl.x * Ul.z; IA.vv[3] -= sl.y * Ul.y; IA.vv[4] -= sl.y * Ul.z; IA.vv[5] -= sl.z * Ul.z;
-            pA.a += u * sa; pA.l += u * sl;
-            Uo = mks(Ua, Ul); invo = inv; uo = u;
-        };
-        Art sd; S6 sf;
-#pragma unroll 1
-        for (int lv = maxlevel; lv >= 0; --lv) {
-            if (level == lv) {
-                if (ndof == 3) { eliminate(S2, g2, U2, inv2, u2); eliminate(S1, g1, U1, inv1, u1); }
-                if (ndof >= 1) eliminate(S0, g0, U0, inv0, u0);
-            }
-            // express (IA, pA) about the parent's pivot: shift by c = cw:  B' = B + C V ; A' = A - B C + C B'^T   (C = [c]x)
-            {
-                const V3 c = cw;
-                const V3 v0 = mk3(IA.vv[0], IA.vv[1], IA.vv[2]), v1 = mk3(IA.vv[1], IA.vv[3], IA.vv[4]), v2 = mk3(IA.vv[2], IA.vv[4], IA.vv[5]);   // columns (= rows) of V
-                const V3 b0 = mk3(IA.wv[0], IA.wv[1], IA.wv[2]), b1 = mk3(IA.wv[3], IA.wv[4], IA.wv[5]), b2 = mk3(IA.wv[6], IA.wv[7], IA.wv[8]);   // rows of B
-                const V3 k0 = cross(c, v0), k1 = cross(c, v1), k2 = cross(c, v2);   // columns of C V
-                const V3 n0 = mk3(b0.x + k0.x, b0.y + k1.x, b0.z + k2.x), n1 = mk3(b1.x + k0.y, b1.y + k1.y, b1.z + k2.y), n2 = mk3(b2.x + k0.z, b2.y + k1.z, b2.z + k2.z);   // rows of B'
-                const V3 p0 = cross(b0, c), p1 = cross(b1, c), p2 = cross(b2, c);   // rows of B C
-                const V3 q0 = cross(c, n0), q1 = cross(c, n1), q2 = cross(c, n2);   // columns of C B'^T
-                sd.ww[0] = IA.ww[0] - p0.x + q0.x; sd.ww[1] = IA.ww[1] - p0.y + q1.x; sd.ww[2] = IA.ww[2] - p0.z + q2.x;
-                sd.ww[3] = IA.ww[3] - p1.y + q1.y; sd.ww[4] = IA.ww[4] - p1.z + q2.y; sd.ww[5] = IA.ww[5] - p2.z + q2.z;
-                sd.wv[0] = n0.x; sd.wv[1] = n0.y; sd.wv[2] = n0.z; sd.wv[3] = n1.x; sd.wv[4] = n1.y; sd.wv[5] = n1.z; sd.wv[6] = n2.x; sd.wv[7] = n2.y; sd.wv[8] = n2.z;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) sd.vv[k] = IA.vv[k];
-                sf = shift_f(pA, c);
-            }
-            if (lv == 0) break;
-            const int nslot = LVC[lv - 1];
-#pragma unroll 1
-            for (int c = 0; c < nslot; ++c) {
-                const int cl = (c < nchild) ? ((child_pack >> (8 * c)) & 0xff) : -1;
-                const int src = cl >= 0 ? cl : lane;
-                const bool take = cl >= 0 && level == lv - 1;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) { float g = T::shfl(sd.ww[k], src); if (take) IA.ww[k] += g; }
-#pragma unroll
-                for (int k = 0; k < 9; ++k) { float g = T::shfl(sd.wv[k], src); if (take) IA.wv[k] += g; }
-#pragma unroll
-                for (int k = 0; k < 6; ++k) { float g = T::shfl(sd.vv[k], src); if (take) IA.vv[k] += g; }
-                const S6 gf = T::shfl6(sf, src);
-                if (take) { pA.a += gf.a; pA.l += gf.l; }
-            }
-        }
-        PROF(4);
-        // ---- base: the (massless) floating base carries the root link's articulated inertia; Cholesky of the 6x6 in world axes at the base
-        // origin, i.e. directly in the generalised base coordinates [omega_w, v_w]
-        S6 aB = mks(mk3(0, 0, 0), mk3(0, 0, 0));
-        if (lane == 0) {
-            float a[6][6];   // lower triangle a[i][j], j <= i ; coordinates [w(3); v(3)]
-            a[0][0] = sd.ww[0]; a[1][0] = sd.ww[1]; a[1][1] = sd.ww[3]; a[2][0] = sd.ww[2]; a[2][1] = sd.ww[4]; a[2][2] = sd.ww[5];
-            a[3][0] = sd.wv[0]; a[3][1] = sd.wv[3]; a[3][2] = sd.wv[6]; a[4][0] = sd.wv[1]; a[4][1] = sd.wv[4]; a[4][2] = sd.wv[7]; a[5][0] = sd.wv[2]; a[5][1] = sd.wv[5]; a[5][2] = sd.wv[8];   // B'^T
-            a[3][3] = sd.vv[0]; a[4][3] = sd.vv[1]; a[4][4] = sd.vv[3]; a[5][3] = sd.vv[2]; a[5][4] = sd.vv[4]; a[5][5] = sd.vv[5];
-            float gi[6];   // 1 / G_ii
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                float d = a[j][j];
-#pragma unroll
-                for (int k = 0; k < j; ++k) d -= a[j][k] * a[j][k];
-                gi[j] = rsqrtf(d);
-                a[j][j] = d * gi[j];
-#pragma unroll
-                for (int i = j + 1; i < 6; ++i) {
-                    float s = a[i][j];
-#pragma unroll
-                    for (int k = 0; k < j; ++k) s -= a[i][k] * a[j][k];
-                    a[i][j] = s * gi[j];
-                }
-            }
-            // x = -(G G^T)^-1 p
-            float x[6] = {-sf.a.x, -sf.a.y, -sf.a.z, -sf.l.x, -sf.l.y, -sf.l.z};
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-#pragma unroll
-                for (int k = 0; k < i; ++k) x[i] -= a[i][k] * x[k];
-                x[i] *= gi[i];
-            }
-#pragma unroll
-            for (int i = 5; i >= 0; --i) {
-#pragma unroll
-                for (int k = i + 1; k < 6; ++k) x[i] -= a[k][i] * x[k];
-                x[i] *= gi[i];
-            }
-            aB = mks(mk3(x[0], x[1], x[2]), mk3(x[3], x[4], x[5]));
-            if (bullet) {   // factor kept for the constraint rows: strict lower part (15) + reciprocal diagonal (6)
-                int o = 0;
-#pragma unroll
-                for (int i = 1; i < 6; ++i)
-#pragma unroll
-                    for (int k = 0; k < i; ++k) sG[o++] = a[i][k];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) sG[15 + i] = gi[i];
-            }
-        }
-        PROF(5);
-        // ---- accelerations (root -> leaves): qdd_d = (u_d - U_d . a') / D_d
-        float qd0 = 0.f, qd1 = 0.f, qd2 = 0.f;
-        S6 al = mks(mk3(0, 0, 0), mk3(0, 0, 0));   // link acceleration (deviation from the bias acceleration)
-        auto descend = [&](S6 a, float n0, float n1, float n2) {
-            // n_d: numerator already divided by D_d
-            if (ndof >= 1) { qd0 = n0 - inv0 * sdot(a, U0); a.a += qd0 * S0; }
-            if (ndof == 3) { qd1 = n1 - inv1 * sdot(a, U1); a.a += qd1 * S1; qd2 = n2 - inv2 * sdot(a, U2); a.a += qd2 * S2; }
-            return a;
-        };
-        if (lane == 0) al = descend(shift_m(aB, cw), u0 * inv0, u1 * inv1, u2 * inv2);
-#pragma unroll 1
-        for (int lv = 1; lv <= maxlevel; ++lv) {
-            S6 pa = T::shfl6(al, plane);
-            if (level == lv) al = descend(shift_m(pa, cw), u0 * inv0, u1 * inv1, u2 * inv2);
-        }
-
-        if (!bullet) {
+            const float kp = LKo[kLKp], kd = LKo[kLKd];
+            const float pe0 = kp * e0, pe1 = kp * e1, pe2 = kp * e2;
+            const float3 qdd = aba_solve<W, DEBUG>(C, pe0 - kd * jv.x, pe1 - kd * jv.y, pe2 - kd * jv.z, fdt * kd, 0, jv.x, jv.y, jv.z, gx, gy, gz, h, nullptr);
             // ---------------- torques: tau = Kp e + Kd (edot - dt a), clamped by norm (cSimBodyJoint::ClampTotalTorque, SimBodyJoint.cpp:299-307)
             float t0 = 0, t1 = 0, t2 = 0;
-            if (ndof >= 1) t0 = pe0 + kd * (-jv.x - fdt * qd0);
-            if (ndof == 3) { t1 = pe1 + kd * (-jv.y - fdt * qd1); t2 = pe2 + kd * (-jv.z - fdt * qd2); }
+            if (ndof >= 1) t0 = pe0 + kd * (-jv.x - fdt * qdd.x);
+            if (ndof == 3) { t1 = pe1 + kd * (-jv.y - fdt * qdd.y); t2 = pe2 + kd * (-jv.z - fdt * qdd.z); }
             const float mag = sqrtf(t0 * t0 + t1 * t1 + t2 * t2), tlim = LKo[kLTl];
             if (mag > tlim) { float s = tlim / mag; t0 *= s; t1 *= s; t2 *= s; }
             tau0 = t0; tau1 = t1; tau2 = t2;
-            PROF(6);
             if (DEBUG && dbg && first_upd) {
-                if (ndof >= 1) { dbg[2 * kMaxDofs + dof0] = t0; dbg[3 * kMaxDofs + dof0] = qd0; }
-                if (ndof == 3) { dbg[2 * kMaxDofs + dof0 + 1] = t1; dbg[2 * kMaxDofs + dof0 + 2] = t2; dbg[3 * kMaxDofs + dof0 + 1] = qd1; dbg[3 * kMaxDofs + dof0 + 2] = qd2; }
+                if (ndof >= 1) { dbg[2 * kMaxDofs + dof0] = t0; dbg[3 * kMaxDofs + dof0] = qdd.x; }
+                if (ndof == 3) { dbg[2 * kMaxDofs + dof0 + 1] = t1; dbg[2 * kMaxDofs + dof0 + 2] = t2; dbg[3 * kMaxDofs + dof0 + 1] = qdd.y; dbg[3 * kMaxDofs + dof0 + 2] = qdd.z; }
                 if (lane == 0) for (int k = 0; k < 6; ++k) dbg[2 * kMaxDofs + k] = 0.f;
             }
+            PROF(4);
             continue;
         }
-
-        // =================================================================== Bullet sub-step: v += a h, constraint rows, PGS, integration
+        // =================================================================== Bullet sub-step
         const int sub = ph - 1;
-        auto cl100 = [](float v) { return fminf(fmaxf(v, -100.f), 100.f); };   // applyDeltaVeeMultiDof clamp
+        int P;
         {
-            // base acceleration: already in the world-aligned generalised coordinates [omega_w, v_w] (lane 0 owns the base state)
-            if (lane == 0) {
-                if (DEBUG && dbg && first_upd) {
-                    const int o = (sub == 0 ? 4 * kMaxDofs : 8 * kMaxDofs + 1024);
-                    dbg[o] = aB.a.x; dbg[o + 1] = aB.a.y; dbg[o + 2] = aB.a.z; dbg[o + 3] = aB.l.x; dbg[o + 4] = aB.l.y; dbg[o + 5] = aB.l.z;
-                }
-                sB[7] = cl100(sB[7] + h * aB.a.x); sB[8] = cl100(sB[8] + h * aB.a.y); sB[9] = cl100(sB[9] + h * aB.a.z);
-                sB[10] = cl100(sB[10] + h * aB.l.x); sB[11] = cl100(sB[11] + h * aB.l.y); sB[12] = cl100(sB[12] + h * aB.l.z);
-            }
-            if (DEBUG && dbg && first_upd) {
-                const int o = (sub == 0 ? 4 * kMaxDofs : 8 * kMaxDofs + 1024);
-                if (ndof >= 1) dbg[o + dof0] = qd0;
-                if (ndof == 3) { dbg[o + dof0 + 1] = qd1; dbg[o + dof0 + 2] = qd2; }
-            }
-            if (ndof >= 1) jv.x = cl100(jv.x + h * qd0);
-            if (ndof == 3) { jv.y = cl100(jv.y + h * qd1); jv.z = cl100(jv.z + h * qd2); }
-            vel = vel + h * al;   // link velocities are linear in the generalised velocities (the clamp only acts on exploding states)
+            const int r = collide<W>(C, mani, alive ? 1 : 0, scale);
+            P = r & 0xff; in_contact_tol = ((r >> 8) & 1) != 0; if (r >> 9) f_over = 1;
+        }
+        PROF(3);
+        {   // unconstrained accelerations, v += a h (the base and the link velocities are advanced inside)
+            float* dacc = (DEBUG && dbg && first_upd) ? dbg + (sub == 0 ? 4 * kMaxDofs : 8 * kMaxDofs + 1024) : nullptr;
+            const float3 qdd = aba_solve<W, DEBUG>(C, tau0, tau1, tau2, 0.f, 1, jv.x, jv.y, jv.z, gx, gy, gz, h, dacc);
+            if (DEBUG && dacc) { if (ndof >= 1) dacc[dof0] = qdd.x; if (ndof == 3) { dacc[dof0 + 1] = qdd.y; dacc[dof0 + 2] = qdd.z; } }
+            if (ndof >= 1) jv.x = cl100(jv.x + h * qdd.x);
+            if (ndof == 3) { jv.y = cl100(jv.y + h * qdd.y); jv.z = cl100(jv.z + h * qdd.z); }
             if (DEBUG && dbg && first_upd) {
                 const int o = (sub == 0 ? 5 * kMaxDofs : 9 * kMaxDofs + 1024);
                 if (lane == 0) { for (int k = 0; k < 6; ++k) dbg[o + k] = sB[7 + k]; dbg[(sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024)] = static_cast<float>(P); }
@@ -1126,7 +1252,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 if (ndof == 3) { dbg[o + dof0 + 1] = jv.y; dbg[o + dof0 + 2] = jv.z; }
             }
         }
-        PROF(6);
+        PROF(4);
         // ---- joint-limit rows (btMultiBodyJointLimitConstraint): a lane owns at most one active row
         int lim_dir = 0; float lim_pen = 0.f;
         if (act && has_limit && alive) {
@@ -1139,71 +1265,31 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         int NL = __popc(lseg);
         const unsigned anyrow = __ballot_sync(0xffffffffu, NL + P > 0);
         if (anyrow != 0) {
-        // publish the per-link factors and velocities for the row builders
-        if (act) {
-            float* u = sU + lane * 24;
-            u[0] = U0.a.x; u[1] = U0.a.y; u[2] = U0.a.z; u[3] = U0.l.x; u[4] = U0.l.y; u[5] = U0.l.z;
-            u[6] = U1.a.x; u[7] = U1.a.y; u[8] = U1.a.z; u[9] = U1.l.x; u[10] = U1.l.y; u[11] = U1.l.z;
-            u[12] = U2.a.x; u[13] = U2.a.y; u[14] = U2.a.z; u[15] = U2.l.x; u[16] = U2.l.y; u[17] = U2.l.z;
-            u[18] = inv0; u[19] = inv1; u[20] = inv2; u[21] = sqrtf(inv0); u[22] = sqrtf(inv1); u[23] = sqrtf(inv2);
-            float* v = sV + lane * 8;
-            v[0] = vel.a.x; v[1] = vel.a.y; v[2] = vel.a.z; v[3] = vel.l.x; v[4] = vel.l.y; v[5] = vel.l.z;
-        }
-        {
-            const int lidx = __popc(lseg & ((1u << lane) - 1u));
-            if (NL > 8) { NL = 8; f_over = 1; }
-            if (lim_dir != 0 && lidx < 8) { sQ[lidx] = __int_as_float(lane); sQ[8 + lidx] = (lim_dir == -1) ? -1.f : 1.f; sQ[16 + lidx] = lim_pen; sQ[24 + lidx] = jv.x; }
-        }
-        if (NL + 3 * P > MR) { P = (MR - NL) / 3; f_over = 1; }
-        const int NR = NL + 3 * P;
-        __syncwarp();
-        PROF(7);
-        // rows, J M^-1 J^T, projected Gauss-Seidel and z = Y^T lambda: a separate (non-inlined) warp-collective routine with its own
-        // register budget -- it only needs this environment's shared-memory block
+            {
+                const int lidx = __popc(lseg & ((1u << lane) - 1u));
+                if (NL > 8) { NL = 8; f_over = 1; }
+                if (lim_dir != 0 && lidx < 8) { sQ[lidx] = __int_as_float(lane); sQ[8 + lidx] = (lim_dir == -1) ? -1.f : 1.f; sQ[16 + lidx] = lim_pen; sQ[24 + lidx] = jv.x; }
+            }
+            if (NL + 3 * P > LY.maxrows) { P = (LY.maxrows - NL) / 3; f_over = 1; }
+            const int NR = NL + 3 * P;
+            __syncwarp();
+            PROF(5);
 #ifdef DM_PROFILE
-        { const int nrm = wmax(NR); if ((threadIdx.x & 31) == 0) { PRF[13] += nrm; PRF[14] += 1; } }
+            { const int nrm = wmax(NR); if ((threadIdx.x & 31) == 0) { PRF[13] += nrm; PRF[14] += 1; } }
 #endif
-        solve_rows<W>(E, LYS, LK, CD, CH, lane, NL, P, h, mu, mani, alive ? 1 : 0, PRFP);
-        PROF(10);
-        {
-            S6 dB = mks(mk3(0, 0, 0), mk3(0, 0, 0));
-            if (lane == 0) {   // base: dB = G^-T z
-                float x[6] = {sZ[0], sZ[1], sZ[2], sZ[3], sZ[4], sZ[5]};
-                float g[15];
-#pragma unroll
-                for (int k = 0; k < 15; ++k) g[k] = sG[k];
-#pragma unroll
-                for (int i = 5; i >= 0; --i) {
-#pragma unroll
-                    for (int k = i + 1; k < 6; ++k) x[i] -= g[k * (k - 1) / 2 + i] * x[k];
-                    x[i] *= sG[15 + i];
-                }
-                dB = mks(mk3(x[0], x[1], x[2]), mk3(x[3], x[4], x[5]));
-            }
-            float z0 = 0.f, z1 = 0.f, z2 = 0.f;
-            if (ndof >= 1) z0 = sZ[dof0] * sqrtf(inv0);
-            if (ndof == 3) { z1 = sZ[dof0 + 1] * sqrtf(inv1); z2 = sZ[dof0 + 2] * sqrtf(inv2); }
-            if (lane == 0) al = descend(shift_m(dB, cw), z0, z1, z2);
-#pragma unroll 1
-            for (int lv = 1; lv <= maxlevel; ++lv) {
-                S6 pa = T::shfl6(al, plane);
-                if (level == lv) al = descend(shift_m(pa, cw), z0, z1, z2);
-            }
+            solve_rows<W>(E, LYS, LK, CD, CH, lane, NL, P, h, mu, mani, alive ? 1 : 0, PRFP);
+            PROF(10);
+            const float3 dq = dv_pass<W>(C);
             if (NR > 0) {
-                if (lane == 0) {
-                    sB[7] = cl100(sB[7] + dB.a.x); sB[8] = cl100(sB[8] + dB.a.y); sB[9] = cl100(sB[9] + dB.a.z);
-                    sB[10] = cl100(sB[10] + dB.l.x); sB[11] = cl100(sB[11] + dB.l.y); sB[12] = cl100(sB[12] + dB.l.z);
-                }
-                if (ndof >= 1) jv.x = cl100(jv.x + qd0);
-                if (ndof == 3) { jv.y = cl100(jv.y + qd1); jv.z = cl100(jv.z + qd2); }
+                if (ndof >= 1) jv.x = cl100(jv.x + dq.x);
+                if (ndof == 3) { jv.y = cl100(jv.y + dq.y); jv.z = cl100(jv.z + dq.z); }
             }
+            if (DEBUG && dbg && first_upd) {   // impulses in the order [normals | friction pairs | limits]
+                const int lo_ = (sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024) + 1;
+                for (int k = lane; k < NR && k < 60; k += W) { const int src = (k < 3 * P) ? NL + k : k - 3 * P; dbg[lo_ + k] = sLam[src]; }
+            }
+            PROF(11);
         }
-        if (DEBUG && dbg && first_upd) {   // impulses in the order [normals | friction pairs | limits]
-            const int lo_ = (sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024) + 1;
-            for (int k = lane; k < NR && k < 60; k += W) { const int src = (k < 3 * P) ? NL + k : k - 3 * P; dbg[lo_ + k] = sLam[src]; }
-        }
-        PROF(11);
-        }   // anyrow
         if (DEBUG && dbg && first_upd) {
             const int o = (sub == 0 ? 6 * kMaxDofs : 10 * kMaxDofs + 1024);
             if (lane == 0) for (int k = 0; k < 6; ++k) dbg[o + k] = sB[7 + k];
@@ -1213,7 +1299,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         // ---- integrate positions (btMultiBody::stepPositionsMultiDof)
         if (lane == 0) {
             sB[0] += h * sB[10]; sB[1] += h * sB[11]; sB[2] += h * sB[12];
-            const Q4 q = quat_integrate3(bOmega(), bQuat(), true, h);
+            const Q4 q = quat_integrate3(mk3(sB[7], sB[8], sB[9]), mkq(sB[3], sB[4], sB[5], sB[6]), true, h);
             sB[3] = q.x; sB[4] = q.y; sB[5] = q.z; sB[6] = q.w;
         }
         if (jtype == kJRevolute) jp.x += h * jv.x;
