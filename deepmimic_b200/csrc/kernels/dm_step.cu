@@ -983,6 +983,31 @@ __device__ __noinline__ float3 dv_pass(Ctx c) {
     return make_float3(qd0, qd1, qd2);
 }
 
+// Link velocities from the generalised velocities (root -> leaves), for the environments flagged by `want`.  Only needed when Bullet's
+// per-coordinate velocity clamp (maxCoordinateVelocity = 100) fired in the velocity update: otherwise aba_solve's v + h a is the same thing.
+template <int W>
+__device__ __noinline__ void vel_pass(Ctx c, float jvx, float jvy, float jvz, bool want) {
+    using T = Tl<W>;
+    const StepLayout& LY = lay_of(c);
+    const float* sS = c.E + LY.oR; float* sV = c.E + LY.oV; const float* sB = c.E + LY.oG + 21;
+    const float* q = sS + c.li * 12;
+    const V3 S0 = mk3(q[0], q[1], q[2]), S1 = mk3(q[3], q[4], q[5]), S2 = mk3(q[6], q[7], q[8]), cw = mk3(q[9], q[10], q[11]);
+    V3 jww = mk3(0, 0, 0);
+    if (c.jtype == kJSpherical) jww = jvx * S0 + jvy * S1 + jvz * S2; else if (c.jtype == kJRevolute) jww = jvx * S0;
+    S6 vel = mks(mk3(0, 0, 0), mk3(0, 0, 0));
+    if (c.lane == 0) { const V3 bo = mk3(sB[7], sB[8], sB[9]); vel = mks(bo + jww, mk3(sB[10], sB[11], sB[12]) + cross(bo, cw)); }
+#pragma unroll 1
+    for (int lv = 1; lv <= c.maxlevel; ++lv) {
+        const S6 pv = T::shfl6(vel, c.plane);
+        if (c.level == lv) vel = mks(pv.a + jww, pv.l + cross(pv.a, cw));
+    }
+    if (c.act && want) {
+        float* v = sV + c.lane * 12;
+        v[0] = vel.a.x; v[1] = vel.a.y; v[2] = vel.a.z; v[3] = vel.l.x; v[4] = vel.l.y; v[5] = vel.l.z;
+    }
+    __syncwarp();
+}
+
 template <int W, bool DEBUG>
 __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevModel* __restrict__ gm, DevState st, const double* __restrict__ frame_times,
                                                                        const float* __restrict__ frames, double dt, int n_updates, int sim_substeps, StepLayout LY, int sync_mode) {
@@ -1243,8 +1268,15 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             float* dacc = (DEBUG && dbg && first_upd) ? dbg + (sub == 0 ? 4 * kMaxDofs : 8 * kMaxDofs + 1024) : nullptr;
             const float3 qdd = aba_solve<W, DEBUG>(C, tau0, tau1, tau2, 0.f, 1, jv.x, jv.y, jv.z, gx, gy, gz, h, dacc);
             if (DEBUG && dacc) { if (ndof >= 1) dacc[dof0] = qdd.x; if (ndof == 3) { dacc[dof0 + 1] = qdd.y; dacc[dof0 + 2] = qdd.z; } }
-            if (ndof >= 1) jv.x = cl100(jv.x + h * qdd.x);
-            if (ndof == 3) { jv.y = cl100(jv.y + h * qdd.y); jv.z = cl100(jv.z + h * qdd.z); }
+            bool hit = false;   // a generalised velocity reached Bullet's clamp: the link velocities must be rebuilt from the clamped values
+            if (ndof >= 1) { const float v = jv.x + h * qdd.x; jv.x = cl100(v); hit |= fabsf(v) > 100.f; }
+            if (ndof == 3) { const float v1 = jv.y + h * qdd.y, v2 = jv.z + h * qdd.z; jv.y = cl100(v1); jv.z = cl100(v2); hit |= fabsf(v1) > 100.f || fabsf(v2) > 100.f; }
+            if (lane == 0) for (int k = 0; k < 6; ++k) hit |= fabsf(sB[7 + k]) >= 100.f;
+            const unsigned hb = __ballot_sync(0xffffffffu, hit);
+            if (hb != 0u) {
+                const unsigned hseg = (W == 32) ? hb : ((hb >> (threadIdx.x & 16)) & 0xffffu);
+                vel_pass<W>(C, jv.x, jv.y, jv.z, hseg != 0u);
+            }
             if (DEBUG && dbg && first_upd) {
                 const int o = (sub == 0 ? 5 * kMaxDofs : 9 * kMaxDofs + 1024);
                 if (lane == 0) { for (int k = 0; k < 6; ++k) dbg[o + k] = sB[7 + k]; dbg[(sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024)] = static_cast<float>(P); }
@@ -1283,6 +1315,10 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             if (NR > 0) {
                 if (ndof >= 1) jv.x = cl100(jv.x + dq.x);
                 if (ndof == 3) { jv.y = cl100(jv.y + dq.y); jv.z = cl100(jv.z + dq.z); }
+            }
+            if (DEBUG && dbg && first_upd) {   // solver rows in solver order: right-hand side, 1 / A_ii, impulse (test hook)
+                const float* sRhs_ = E + LY.oRhs; const float* sInv_ = E + LY.oInv;
+                for (int k = lane; k < NR && k < 64; k += W) { float* o = dbg + 8 * kMaxDofs + sub * 256; o[k] = sRhs_[k]; o[64 + k] = sInv_[k]; o[128 + k] = sLam[k]; }
             }
             if (DEBUG && dbg && first_upd) {   // impulses in the order [normals | friction pairs | limits]
                 const int lo_ = (sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024) + 1;

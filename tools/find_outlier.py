@@ -49,6 +49,9 @@ for t0 in (0.0, 0.3, 0.6, 0.9):
                 print(" sub %d: gpu rows P=%g | v_aba diff %.3g (argmax %d) | v_pgs diff %.3g (argmax %d)" % (
                     sub, P, np.abs(vaba - oaba).max(), np.abs(vaba - oaba).argmax(), np.abs(vpgs - opgs).max(), np.abs(vpgs - opgs).argmax()))
                 print("   lam gpu", lam[:36]); print("   lam orc", olam[:36].astype(np.float64))
+            for sub in (0, 1):
+                o = 8 * K + sub * 256
+                print('   sub %d rows: rhs' % sub, d[o:o + 6], 'inv', d[o + 64:o + 70], 'lam', d[o + 128:o + 134])
             # per-joint limit proximity
             import json
             ch = json.load(open(os.path.join(root, char)))
