@@ -236,7 +236,7 @@ def main():
                        "episodes_finished_in_timed_region": done_count, "solver_row_overflows": overflow,
                        "collective": "nccl all_gather of [N x (%d+2)] fp32 per step" % S if world > 1 else "none (1 GPU)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "dm_update_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": "dm_step_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "note": "latency/issue-bound path: state stays on chip for the whole launch, HBM fraction is small by construction (SURVEY 8d)"},
             "e2e": {"value": e2e_value, "unit": "policy_steps/s", "h2d_bytes_per_step": int(N * A * 4), "d2h_bytes_per_step": int(N * (S + 1 + 4) * 4)},
