@@ -1130,6 +1130,12 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     const int sync_period = sync_mode > 0 ? 1 : (sync_mode == 0 ? stages_per_upd : (sync_mode <= -1000 ? 0 : -sync_mode * stages_per_upd));
 #pragma unroll 1
     for (int stage = 0; stage <= total_stages; ++stage) {
+        // the manifold of this lane's link is read by the collision pass of a Bullet sub-step: start pulling its two cache lines in now
+        if ((stage % stages_per_upd) != 0 && act && alive) {
+            const float* mp_ = mani + li * kManifoldFloats;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(mp_));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(mp_ + 32));
+        }
         // =================================================================== forward kinematics + link velocities
         if (need_kin) { need_kin = false; kin_pass<W>(C, jp, jv); }
         PROF(0);

@@ -163,3 +163,45 @@ def test_free_running_statistics_match_oracle(asset_root):
     assert np.nanmax(np.abs(g[:, :2] - o[:, :2])) < 5e-3
     assert abs(np.nanmean(g) - np.nanmean(o)) < 0.03
     assert abs(g_done.mean() - o_done.mean()) < 0.15
+
+
+def test_many_contacts_general_solver_path(asset_root):
+    """With fall termination switched off the character ends up lying on the ground with up to ~10 contact points (30+ solver rows):
+    more rows than lanes, so the packed-triangle / multi-slot path of the constraint solver is exercised (the common path handles
+    <= W rows).  Same teacher-forced comparison and tolerances as above."""
+    args = ["--enable_char_contact_fall", "false", "--arg_file", "args/run_humanoid3d_spinkick_args.txt"]
+    import torch
+    from deepmimic_b200.capi import BatchedCore
+    core = BatchedCore(args, 4, asset_root, device=0, seed=3)
+    orc = Oracle(args, asset_root); orc2 = Oracle(args, asset_root)
+    jt = joint_types_from_assets(asset_root, "data/characters/humanoid3d.txt")
+    lay = SnapLayout(orc.num_joints)
+    rng2 = np.random.default_rng(5)
+    orc.reset(0.3, 0.0, 20.0)
+    zero = np.zeros(orc.action_size)
+    eqs, eqds, ncs, flips = [], [], [], 0
+    for upd in range(900):
+        if orc.need_new_action():
+            orc.set_action(zero)
+        assert not orc.is_episode_end()
+        before = orc.get_snapshot()
+        if upd < 600:          # let it fall on the oracle alone; compare the contact-rich part
+            orc.update(1.0 / 600.0)
+            continue
+        core.set_snapshot(0, before)
+        core.update(1.0 / 600.0, 1)
+        orc.update(1.0 / 600.0)
+        so, sg = orc.get_snapshot(), core.get_snapshot(0)
+        eq, eqd = compare_sim_state(lay, so, sg, jt)
+        if eq > 1e-3 or eqd > 0.5 or lay.contact_counts(so) != lay.contact_counts(sg):
+            assert _explained_by_branch_flip(orc2, lay, jt, before, sg, rng2), (upd, eq, eqd, lay.contact_counts(so), lay.contact_counts(sg))
+            flips += 1
+            continue
+        eqs.append(eq); eqds.append(eqd); ncs.append(sum(lay.contact_counts(so)))
+    eqs, eqds, ncs = np.array(eqs), np.array(eqds), np.array(ncs)
+    print("many contacts: %d updates, contact points max %d mean %.1f, branch flips %d ; |dq| max %.2e ; |dqd| median %.2e p99 %.2e max %.2e"
+          % (len(eqs), ncs.max(), ncs.mean(), flips, eqs.max(), np.median(eqds), np.percentile(eqds, 99), eqds.max()))
+    assert ncs.max() >= 6            # more than 16 rows at some point
+    assert flips <= max(2, len(eqs) // 50)
+    assert np.median(eqds) <= 2e-3 and np.percentile(eqds, 99) <= 5e-2 and eqds.max() <= 0.5
+    assert core.counters()[1] == 0   # row capacity (36 rows) not exceeded
