@@ -1,0 +1,160 @@
+"""Batched policy rollout over the batched environment: what the reference does per env and per MPI worker
+in RLWorld.update_agents -> RLAgent._update_new_action (R/learning/rl_world.py:94-132, R/learning/rl_agent.py:319-343), done for all
+N environments of a rank at once with observations, actions and rewards staying on the device.
+
+  DeviceNormalizer   R/learning/normalizer.py (mean / std / clip, group-wise running statistics), torch tensors
+  GaussianMLPPolicy  actor of PPOAgent: fc_2layers_1024units -> Gaussian mean (+ state-independent log-std bias = log(noise))
+                     (R/learning/ppo_agent.py:52-90, pg_agent.py:140-160, nets/fc_2layers_1024units.py, tf_util.py:27-39)
+  BatchedRollout     record_state -> normalise -> actor -> un-normalise -> set_action -> 20 x update -> reward / flags -> masked reset,
+                     collecting [T, N, .] trajectory tensors for a learner
+
+The MLP runs as plain torch matmuls (cuBLAS): a library GEMM, not part of the hand-written hot path.  Loading the reference's TF1
+checkpoints is not implemented (weights are random-initialised the way the reference initialises them)."""
+import math
+
+import numpy as np
+
+
+class DeviceNormalizer:
+    NORM_GROUP_SINGLE = 0
+    NORM_GROUP_NONE = -1
+
+    def __init__(self, size, group_ids=None, eps=0.02, clip=float("inf"), device="cpu"):
+        import torch
+        self.torch = torch
+        self.eps, self.clip = eps, clip
+        self.mean = torch.zeros(size, device=device)
+        self.mean_sq = torch.zeros(size, device=device)
+        self.std = torch.ones(size, device=device)
+        self.count = 0
+        g = np.zeros(size, dtype=np.int64) if group_ids is None else np.asarray(group_ids, dtype=np.int64)
+        self.group_ids = g
+        self.new_count = 0
+        self.new_sum = torch.zeros(size, device=device)
+        self.new_sum_sq = torch.zeros(size, device=device)
+
+    def set_mean_std(self, mean, std):
+        t = self.torch
+        self.mean = t.as_tensor(np.asarray(mean), dtype=t.float32, device=self.mean.device).clone()
+        self.std = t.as_tensor(np.asarray(std), dtype=t.float32, device=self.mean.device).clone()
+        self.mean_sq = self.std * self.std + self.mean * self.mean
+
+    def normalize(self, x):
+        y = (x - self.mean) / self.std
+        return y if math.isinf(self.clip) else y.clamp(-self.clip, self.clip)
+
+    def unnormalize(self, y):
+        return y * self.std + self.mean
+
+    def record(self, x):
+        x = x.reshape(-1, self.mean.numel())
+        self.new_count += x.shape[0]
+        self.new_sum += x.sum(dim=0)
+        self.new_sum_sq += (x * x).sum(dim=0)
+
+    def _process_group_data(self, new, old):
+        out = new.clone()
+        for gid in np.unique(self.group_ids):
+            idx = self.torch.as_tensor(np.nonzero(self.group_ids == gid)[0], device=new.device)
+            if gid == self.NORM_GROUP_NONE:
+                out[idx] = old[idx]
+            elif gid != self.NORM_GROUP_SINGLE:
+                out[idx] = new[idx].mean()
+        return out
+
+    def update(self, all_reduce=None):
+        """Fold the recorded samples into the running statistics; `all_reduce(tensor)` sums over ranks (torch.distributed) if given."""
+        t = self.torch
+        cnt = t.tensor([float(self.new_count)], device=self.mean.device)
+        s, sq = self.new_sum.clone(), self.new_sum_sq.clone()
+        if all_reduce is not None:
+            for x in (cnt, s, sq):
+                all_reduce(x)
+        n = int(cnt.item())
+        if n > 0:
+            total = self.count + n
+            new_mean = self._process_group_data(s / n, self.mean)
+            new_mean_sq = self._process_group_data(sq / n, self.mean_sq)
+            w_old, w_new = self.count / total, n / total
+            self.mean = w_old * self.mean + w_new * new_mean
+            self.mean_sq = w_old * self.mean_sq + w_new * new_mean_sq
+            self.count = total
+            self.std = t.sqrt((self.mean_sq - self.mean * self.mean).clamp_min(0)).clamp_min(self.eps)
+        self.new_count = 0
+        self.new_sum.zero_(); self.new_sum_sq.zero_()
+
+
+def build_policy(state_size, action_size, init_output_scale=0.01, noise=0.05, hidden=(1024, 512)):
+    import torch
+
+    class GaussianMLPPolicy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            dims = [state_size] + list(hidden)
+            self.hidden = torch.nn.ModuleList([torch.nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:])])
+            for l in self.hidden:
+                torch.nn.init.xavier_uniform_(l.weight); torch.nn.init.zeros_(l.bias)
+            self.mean = torch.nn.Linear(dims[-1], action_size)
+            torch.nn.init.uniform_(self.mean.weight, -init_output_scale, init_output_scale); torch.nn.init.zeros_(self.mean.bias)
+            self.logstd = torch.nn.Parameter(torch.full((action_size,), math.log(noise)))
+
+        def forward(self, norm_s):
+            h = norm_s
+            for l in self.hidden:
+                h = torch.relu(l(h))      # fc_net leaves the last layer linear, build_net applies the activation afterwards
+            return self.mean(h)
+
+        def sample(self, norm_s, explore_mask=None, generator=None):
+            """Normalised action and its log-probability; rows with explore_mask False take the mode."""
+            mu = self.forward(norm_s)
+            std = self.logstd.exp()
+            eps = torch.randn(mu.shape, device=mu.device, generator=generator)
+            if explore_mask is not None:
+                eps = eps * explore_mask[:, None].to(eps.dtype)
+            a = mu + std * eps
+            logp = (-0.5 * eps * eps - self.logstd - 0.5 * math.log(2 * math.pi)).sum(dim=-1)
+            return a, logp
+
+    return GaussianMLPPolicy()
+
+
+class BatchedRollout:
+    def __init__(self, env, policy=None, exp_rate=1.0, noise=0.05, seed=0):
+        import torch
+        self.torch, self.env = torch, env
+        dev = env.device
+        S, A = env.get_state_size(), env.get_action_size()
+        self.policy = (policy or build_policy(S, A, noise=noise)).to(dev)
+        self.s_norm = DeviceNormalizer(S, env.build_state_norm_groups(), device=dev)
+        self.s_norm.set_mean_std(-env.build_state_offset(), 1.0 / env.build_state_scale())
+        self.a_norm = DeviceNormalizer(A, device=dev)
+        self.a_norm.set_mean_std(-env.build_action_offset(), 1.0 / env.build_action_scale())
+        self.exp_rate = exp_rate
+        self.gen = torch.Generator(device=dev); self.gen.manual_seed(seed)
+
+    @property
+    def stream(self):
+        return self.env.stream
+
+    def collect(self, num_steps, record_stats=True):
+        """num_steps policy steps of all environments; returns dict of [T, N, .] tensors (states, actions, logps, rewards, dones)."""
+        t, env = self.torch, self.env
+        N, S, A = env.num_envs, env.get_state_size(), env.get_action_size()
+        out = dict(states=t.empty(num_steps, N, S, device=env.device), actions=t.empty(num_steps, N, A, device=env.device),
+                   logps=t.empty(num_steps, N, device=env.device), rewards=t.empty(num_steps, N, device=env.device),
+                   dones=t.empty(num_steps, N, dtype=t.bool, device=env.device), terminate=t.empty(num_steps, N, dtype=t.int32, device=env.device))
+        with t.no_grad():
+            s = env.record_state()
+            for k in range(num_steps):
+                out["states"][k] = s
+                if record_stats:
+                    self.s_norm.record(s)
+                explore = t.rand(N, device=env.device, generator=self.gen) < self.exp_rate
+                na, logp = self.policy.sample(self.s_norm.normalize(s), explore, self.gen)
+                a = self.a_norm.unnormalize(na).contiguous()
+                s, r, done, term = env.step(a)
+                out["actions"][k] = a; out["logps"][k] = logp; out["rewards"][k] = r; out["dones"][k] = done; out["terminate"][k] = term
+                env.reset()                # restarts exactly the finished episodes
+                if bool(done.any()):
+                    s = env.record_state()
+        return out

@@ -85,3 +85,26 @@ def test_batched_env_step_matches_manual_sequence(asset_root):
         assert bool(((rew >= 0) & (rew <= 1 + 1e-6)).all())
         a.reset(); b.reset()
     a.sync(); b.sync()
+
+
+def test_batched_rollout_collects_trajectories(asset_root):
+    """device-resident policy rollout (normaliser + Gaussian MLP actor + batched env)."""
+    import torch
+    from deepmimic_b200.env import DeepMimicBatchEnv
+    from deepmimic_b200.rollout import BatchedRollout
+    N, T = 64, 6
+    env = DeepMimicBatchEnv(["--arg_file", "args/train_humanoid3d_spinkick_args.txt"], N, asset_root, seed=21)
+    ro = BatchedRollout(env, seed=1)
+    tr = ro.collect(T)
+    torch.cuda.synchronize()
+    S, A = env.get_state_size(), env.get_action_size()
+    assert tuple(tr["states"].shape) == (T, N, S) and tuple(tr["actions"].shape) == (T, N, A)
+    assert bool(torch.isfinite(tr["states"]).all()) and bool(torch.isfinite(tr["actions"]).all()) and bool(torch.isfinite(tr["logps"]).all())
+    assert bool(((tr["rewards"] >= 0) & (tr["rewards"] <= 1 + 1e-6)).all())
+    # a freshly initialised actor (output weights +-0.01) gives small normalised actions: the un-normalised action stays near -action_offset
+    off = torch.tensor(env.build_action_offset(), dtype=torch.float32, device="cuda"); scl = torch.tensor(env.build_action_scale(), dtype=torch.float32, device="cuda")
+    assert float((((tr["actions"][0] + off) * scl).abs()).max()) < 10.0
+    assert ro.s_norm.new_count == T * N
+    ro.s_norm.update()
+    assert ro.s_norm.count == T * N
+    assert abs(float(ro.s_norm.mean[0]) - 0.5) < 1e-6          # the phase slot (norm group NONE) keeps its fixed statistics
