@@ -114,7 +114,7 @@ def main():
             return 0
         cores = os.cpu_count() or 1
         # each "step" is a bounded sample: all host cores run independent single-env episodes for a fixed wall time
-        per_step_seconds = max(3.0, min(20.0, 60.0 / max(1, a.steps + a.warmup)))
+        per_step_seconds = max(0.3, min(20.0, 90.0 / max(1, a.steps + a.warmup)))   # whole run ~90 s whatever K and W are
         vals = []
         for s in range(a.warmup + a.steps):
             v, _ = cpu_policy_steps_per_sec(a.arg_file, root, per_step_seconds, cores)
