@@ -54,6 +54,7 @@ struct Oracle {
     D3 cycle_root_delta;
     // ---- cScene timer
     double timer_time = 0, timer_max = 0;
+    VecD prev_pose, prev_vel;   // cSceneImitateAMP::mPrevPose / mPrevVel: sim pose / vel at the last applied action
     int mode = 0;  // 0 train, 1 test
     VecD joint_weights;
 
@@ -421,6 +422,7 @@ struct Oracle {
             }
             KinMoveOrigin(SimRootPos() - GetRootPos(kin_pose));  // cKinCharacter::SetRootPos (KinCharacter.cpp:239-244)
         }
+        InitHist();   // cSceneImitateAMP::Reset (SceneImitateAMP.cpp:58-68)
     }
     // cSceneSimChar::ResolveCharGroundIntersect (SceneSimChar.cpp:542-583); AABBs from btCollisionShape::getAabb [B288-mem]
     void ResolveCharGroundIntersect() {
@@ -480,7 +482,7 @@ struct Oracle {
     // cSimCharacter::Update -> cCtPDController -> cImpPDController::CalcControlForces -> joint.ApplyTau
     void UpdateSimChar(double dt) {
         ctrl_time += dt;  // cDeepMimicCharController::UpdateCalcTau (DeepMimicCharController.cpp:71-78)
-        if (need_new_action) { prev_action_time = ctrl_time; need_new_action = false; }
+        if (need_new_action) { prev_action_time = ctrl_time; need_new_action = false; UpdateHist(); }  // HandleNewAction -> cSceneImitateAMP::NewActionUpdate
         VecD tau(ndof, 0.0);
         if (dt > 0) {
             rbd.Update(pose, vel);                         // cImpPDController::UpdateRBDModel (ImpPDController.cpp:129-134)
@@ -546,6 +548,81 @@ struct Oracle {
     }
     int StateSize() const { return (sa.ctrl.enable_phase_input ? 1 : 0) + nj * 9 + 1 + nj * 6; }  // CtController.cpp:41-46,300-330
     // cCtController::RecordState / BuildStatePose / BuildStateVel / BuildStatePhase (CtController.cpp:281-293,373-478)
+    // =================================================================== AMP observations (cSceneImitateAMP, SceneImitateAMP.cpp)
+    void InitHist() {   // :153-165 -- the kinematic character one query period before the controller time
+        const double t = ctrl_time - 1.0 / sa.ctrl.query_rate;
+        KinCalcPose(t, prev_pose); KinCalcVel(t, prev_vel);
+    }
+    void UpdateHist() { prev_pose = pose; prev_vel = vel; }   // :167-172
+    int AmpObsPoseSize() const {   // :214-242
+        int size = 1 + 6 + 3 * static_cast<int>(EndEffectors().size());
+        for (int j = 1; j < nj; ++j) size += (cm->joints[j].type == dmh::kSpherical) ? 6 : cm->joints[j].param_size;
+        return size;
+    }
+    int AmpObsVelSize() const { return ndof - cm->joints[0].param_size + 3 + 3; }   // :244-258
+    int AmpObsSize() const { return 2 * (AmpObsPoseSize() + AmpObsVelSize()); }    // :75-84
+    std::vector<int> EndEffectors() const { std::vector<int> e; for (int j = 0; j < nj; ++j) if (cm->joints[j].is_end_eff) e.push_back(j); return e; }
+    int RecordAMPObsPose(const VecD& p, double ground_h, const DQ& ref_rot, int off, double* out) const {   // :296-365
+        int o = off;
+        const D3 root_pos = GetRootPos(p);
+        DQ root_rot = GetRootRot(p);
+        out[o++] = root_pos.y - ground_h;
+        if (sa.cfg.enable_amp_obs_local_root) root_rot = ref_rot * root_rot;
+        D3 nrm = QuatRotVec(root_rot, D3(0, 1, 0)), tan = QuatRotVec(root_rot, D3(1, 0, 0));   // cMathUtil::CalcNormalTangent (MathUtil.cpp:617-623)
+        out[o] = nrm.x; out[o + 1] = nrm.y; out[o + 2] = nrm.z; out[o + 3] = tan.x; out[o + 4] = tan.y; out[o + 5] = tan.z; o += 6;
+        for (int j = 1; j < nj; ++j) {
+            const auto& jd = cm->joints[j];
+            if (jd.type == dmh::kSpherical) {
+                DQ q(p[jd.param_offset], p[jd.param_offset + 1], p[jd.param_offset + 2], p[jd.param_offset + 3]);
+                D3 n = QuatRotVec(q, D3(0, 1, 0)), t = QuatRotVec(q, D3(1, 0, 0));
+                out[o] = n.x; out[o + 1] = n.y; out[o + 2] = n.z; out[o + 3] = t.x; out[o + 4] = t.y; out[o + 5] = t.z; o += 6;
+            } else for (int k = 0; k < jd.param_size; ++k) out[o++] = p[jd.param_offset + k];
+        }
+        for (int e : EndEffectors()) {   // cKinTree::CalcBodyPartPos (KinTree.cpp:272-281): joint_to_world * BodyJointTrans.col(3)
+            const DT jw = JointWorldTrans(*cm, p, e);
+            D3 bp = jw.R * BodyJointTrans(*cm, e).t + jw.t;
+            bp = QuatRotVec(ref_rot, bp - root_pos);
+            out[o] = bp.x; out[o + 1] = bp.y; out[o + 2] = bp.z; o += 3;
+        }
+        return o - off;
+    }
+    int RecordAMPObsVel(const VecD& v, const DQ& ref_rot, int off, double* out) const {   // :367-397
+        int o = off;
+        D3 rv = GetRootVel(v), rw = GetRootAngVel(v);
+        if (sa.cfg.enable_amp_obs_local_root) { rv = QuatRotVec(ref_rot, rv); rw = QuatRotVec(ref_rot, rw); }
+        out[o] = rv.x; out[o + 1] = rv.y; out[o + 2] = rv.z; out[o + 3] = rw.x; out[o + 4] = rw.y; out[o + 5] = rw.z; o += 6;
+        const int rs = cm->joints[0].param_size;
+        for (int k = rs; k < ndof; ++k) out[o++] = v[k];
+        return o - off;
+    }
+    void BuildAMPObs(const VecD& pp, const VecD& pv, const VecD& p, const VecD& v, double ground_h, double* out) const {   // :279-294
+        const DQ ref_rot = AxisAngleToQuaternion(D3(0, 1, 0), -CalcHeading(GetRootRot(p)));   // cKinTree::CalcHeadingRot (KinTree.cpp:1629-1635)
+        int o = 0;
+        o += RecordAMPObsPose(p, ground_h, ref_rot, o, out);
+        o += RecordAMPObsPose(pp, ground_h, ref_rot, o, out);
+        o += RecordAMPObsVel(v, ref_rot, o, out);
+        o += RecordAMPObsVel(pv, ref_rot, o, out);
+    }
+    void RecordAMPObsAgent(double* out) const { BuildAMPObs(prev_pose, prev_vel, pose, vel, 0.0, out); }   // :101-113 (flat ground at 0)
+    // :115-140 with the random mocap time injected; cMotion::CalcFrame / CalcFrameVel of the raw clip (no origin, no cycle offset)
+    void MotionCalcFrame(double time, VecD& p, VecD& v) const {
+        int idx; double blend;
+        CalcIndexBlend(time, idx, blend);
+        const double b = std::min(std::max(blend, 0.0), 1.0);
+        LerpPoses(*cm, sa.motion.frame(idx), sa.motion.frame(idx + 1), b, p);
+        v.assign(ndof, 0.0);
+        if (!(!sa.motion.loop && time >= sa.motion.duration())) {
+            const double* v0 = &frame_vel[static_cast<size_t>(idx) * ndof]; const double* v1 = &frame_vel[static_cast<size_t>(idx + 1) * ndof];
+            for (int k = 0; k < ndof; ++k) v[k] = (1.0 - blend) * v0[k] + blend * v1[k];
+        }
+    }
+    void RecordAMPObsExpert(double rand_kin_time, double* out) const {
+        VecD p, v, pp, pv;
+        MotionCalcFrame(rand_kin_time, p, v);
+        MotionCalcFrame(rand_kin_time - 1.0 / sa.ctrl.query_rate, pp, pv);
+        BuildAMPObs(pp, pv, p, v, origin.y, out);
+    }
+
     void RecordState(double* out) const {
         int ph = sa.ctrl.enable_phase_input ? 1 : 0;
         // cKinTree::BuildOriginTrans (KinTree.cpp:1651-1664) on the sim character's pose
@@ -780,6 +857,9 @@ void dmo_reset(void* h, double kin_time, double rand_theta, double max_time) { s
 void dmo_update(void* h, double dt) { static_cast<Oracle*>(h)->Update(dt); }
 void dmo_set_action(void* h, const double* a) { static_cast<Oracle*>(h)->SetAction(a); }
 void dmo_record_state(void* h, double* out) { static_cast<Oracle*>(h)->RecordState(out); }
+int dmo_amp_obs_size(void* h) { return static_cast<Oracle*>(h)->AmpObsSize(); }
+void dmo_record_amp_obs_agent(void* h, double* out) { static_cast<Oracle*>(h)->RecordAMPObsAgent(out); }
+void dmo_record_amp_obs_expert(void* h, double kin_time, double* out) { static_cast<Oracle*>(h)->RecordAMPObsExpert(kin_time, out); }
 double dmo_calc_reward(void* h) { return static_cast<Oracle*>(h)->CalcReward(); }
 double dmo_calc_reward_terms(void* h, double* errs) { return static_cast<Oracle*>(h)->CalcReward(errs); }
 int dmo_need_new_action(void* h) { return static_cast<Oracle*>(h)->need_new_action ? 1 : 0; }

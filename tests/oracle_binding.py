@@ -78,6 +78,19 @@ class Oracle:
     def calc_reward(self):
         return self.L.dmo_calc_reward(self.h)
 
+    def amp_obs_size(self):
+        return int(self.L.dmo_amp_obs_size(self.h))
+
+    def record_amp_obs_agent(self):
+        out = np.zeros(self.amp_obs_size())
+        self.L.dmo_record_amp_obs_agent(self.h, dp(out))
+        return out
+
+    def record_amp_obs_expert(self, kin_time):
+        out = np.zeros(self.amp_obs_size())
+        self.L.dmo_record_amp_obs_expert(self.h, C.c_double(kin_time), dp(out))
+        return out
+
     def reward_terms(self):
         e = np.zeros(5)
         r = self.L.dmo_calc_reward_terms(self.h, dp(e))

@@ -229,3 +229,52 @@ def test_free_fall_com_acceleration_is_g(asset_root):
     out = o.bullet_aba(np.zeros(o.num_dofs - 6), True)
     # zero velocity, no torques: every point of the character accelerates at g (scaled units x4)
     assert np.abs(out[3:6] - np.array([0, -9.8 * 4, 0])).max() < 2e-3 and np.abs(out[:3]).max() < 2e-3 and np.abs(out[6:]).max() < 5e-3
+
+
+def test_amp_observation_known_answers(asset_root):
+    """cSceneImitateAMP::BuildAMPObs (SceneImitateAMP.cpp:279-397): layout [pose now | pose prev | vel now | vel prev]; humanoid
+    (1 + 6 + 8*6 + 4 + 4*3) = 71 and (6 + 36) = 42 -> 226."""
+    o = Oracle(SPINKICK, asset_root)
+    assert o.amp_obs_size() == 226
+    d = Oracle(DOG, asset_root)
+    assert d.amp_obs_size() == 2 * ((1 + 6 + 18 * 6 + 4 + 4 * 3) + (6 + 83 - 7))
+    t0 = 0.6
+    o.reset(t0, 0.0, 20.0)
+    a = o.record_amp_obs_agent()
+    e = o.record_amp_obs_expert(t0)
+    assert np.isfinite(a).all() and np.isfinite(e).all()
+    P, V = 71, 42
+    # right after a reset the simulated character is the clip pose: joint rotations (norm / tangent or angle) agree with the expert sample,
+    # and so does the previous frame (InitHist samples the clip one query period earlier)
+    np.testing.assert_allclose(a[7:7 + 52], e[7:7 + 52], atol=2e-6)
+    np.testing.assert_allclose(a[P + 7:P + 7 + 52], e[P + 7:P + 7 + 52], atol=2e-6)
+    # joint velocities: sim == clip after reset
+    np.testing.assert_allclose(a[2 * P + 6:2 * P + V], e[2 * P + 6:2 * P + V], atol=2e-5)
+    # normal / tangent pairs are orthonormal
+    types = [j["Type"] for j in json.load(open(os.path.join(asset_root, "data/characters/humanoid3d.txt")))["Skeleton"]["Joints"]]
+    k = 1
+    for blk in [(1, "spherical")] + list(enumerate(types))[1:]:      # root rotation block, then the joints in file order
+        if blk[1] == "spherical":
+            n, t = a[k:k + 3], a[k + 3:k + 6]
+            assert abs(np.dot(n, n) - 1) < 1e-6 and abs(np.dot(t, t) - 1) < 1e-6 and abs(np.dot(n, t)) < 1e-6
+            k += 6
+        elif blk[1] == "revolute":
+            k += 1
+    assert k == 7 + 52
+    # root height above the ground = pose y
+    pose, _ = o.get_pose()
+    assert a[0] == pytest.approx(pose[1], abs=1e-12)
+    # heading-local variant: the current root tangent has no z component (heading removed), end effectors are in the heading frame either way
+    ol = Oracle(["--enable_amp_obs_local_root", "true"] + SPINKICK, asset_root)
+    ol.reset(t0, 1.0, 20.0)
+    al = ol.record_amp_obs_agent()
+    assert abs(al[6]) < 1e-9
+    np.testing.assert_allclose(al[7:7 + 52], a[7:7 + 52], atol=2e-6)   # joint part independent of the flag
+    # after an action is applied the history is the pose the action was chosen from
+    o.set_action(np.zeros(o.action_size))
+    before = o.record_amp_obs_agent()[0:P]
+    o.update(1.0 / 600.0)
+    after = o.record_amp_obs_agent()
+    # prev pose: joint rotations are heading independent -> equal to the "now" block before the update; root height too
+    np.testing.assert_allclose(after[P + 7:P + 7 + 52], before[7:7 + 52], atol=1e-12)
+    assert after[P] == pytest.approx(before[0], abs=1e-12)
