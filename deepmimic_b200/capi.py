@@ -12,13 +12,13 @@ _lib = None
 
 class DmDims(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("num_envs", "num_joints", "pose_dim", "num_dofs", "state_size", "goal_size", "action_size", "snapshot_size",
-                                        "updates_per_action", "num_update_substeps")] + [("motion_duration", C.c_double)]
+                                        "updates_per_action", "num_update_substeps")] + [("motion_duration", C.c_double), ("amp_obs_size", C.c_int)]
 
 
 DM_STATE_OFFSET, DM_STATE_SCALE, DM_ACTION_OFFSET, DM_ACTION_SCALE, DM_ACTION_BOUND_MIN, DM_ACTION_BOUND_MAX, DM_STATE_NORM_GROUPS = range(7)
 
 EXPORTS = ["dm_create", "dm_load_host", "dm_get_model_info", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_stream", "dm_sync", "dm_set_mode", "dm_reset", "dm_set_action",
-           "dm_update", "dm_record_state", "dm_record_goal", "dm_calc_reward", "dm_observe", "dm_get_flags", "dm_step_host", "dm_get_snapshot",
+           "dm_update", "dm_record_state", "dm_record_goal", "dm_calc_reward", "dm_record_amp_obs_agent", "dm_record_amp_obs_expert", "dm_amp_obs_host", "dm_observe", "dm_get_flags", "dm_step_host", "dm_get_snapshot",
            "dm_set_snapshot", "dm_get_counters", "dm_debug_enable", "dm_get_debug"]
 
 
@@ -49,6 +49,9 @@ def lib():
         L.dm_record_state.argtypes = [vp, fp]
         L.dm_record_goal.argtypes = [vp, fp]
         L.dm_calc_reward.argtypes = [vp, fp]
+        L.dm_record_amp_obs_agent.argtypes = [vp, fp]
+        L.dm_record_amp_obs_expert.argtypes = [vp, dp, fp]
+        L.dm_amp_obs_host.argtypes = [vp, C.c_int, dp, fp]
         L.dm_observe.argtypes = [vp, fp, fp]
         L.dm_get_flags.argtypes = [vp, ip]
         L.dm_step_host.argtypes = [vp, fp, C.c_double, C.c_int, fp, fp, ip]
@@ -116,6 +119,13 @@ class BatchedCore:
     def observe(self, state=None, reward=None):
         self._chk(lib().dm_observe(self.h, C.c_void_p(state.data_ptr()) if state is not None else None,
                                    C.c_void_p(reward.data_ptr()) if reward is not None else None))
+
+    def amp_obs_agent(self, out):  # torch float32 cuda tensor [N, amp_obs_size]
+        self._chk(lib().dm_record_amp_obs_agent(self.h, C.c_void_p(out.data_ptr())))
+
+    def amp_obs_expert(self, out, kin_time=None):
+        kt = None if kin_time is None else np.ascontiguousarray(kin_time, dtype=np.float64)
+        self._chk(lib().dm_record_amp_obs_expert(self.h, _dptr(kt), C.c_void_p(out.data_ptr())))
 
     def flags(self, out):  # torch int32 cuda tensor [N, 4]
         self._chk(lib().dm_get_flags(self.h, C.c_void_p(out.data_ptr())))

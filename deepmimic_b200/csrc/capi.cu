@@ -22,6 +22,8 @@ template <int W, int BLOCK>
 __global__ void dm_reset_kernel(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*,
                                 unsigned long long, unsigned long long, int);
 __global__ void dm_set_action_kernel(const DevModel*, DevState, const float*, int);
+template <int W, int BLOCK>
+__global__ void dm_amp_obs_kernel(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int);
 template <int W, bool DEBUG>
 __global__ void dm_step_kernel(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
 int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L);
@@ -58,6 +60,7 @@ struct dm_handle {
     float* d_frame_vel = nullptr;
     double* d_inj[3] = {nullptr, nullptr, nullptr};
     int32_t* d_flags4 = nullptr;
+    float *d_amp = nullptr, *p_amp = nullptr;                              // staging for dm_amp_obs_host
     float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;            // staging for dm_step_host
     float *p_act = nullptr, *p_obs = nullptr, *p_rew = nullptr; int32_t* p_flags = nullptr;  // pinned host staging
     cudaStream_t stream = nullptr;
@@ -65,6 +68,7 @@ struct dm_handle {
     dmk::StepLayout lay{};
     uint64_t seed = 0, env_offset = 0;
     int64_t launches = 0;
+    uint64_t amp_calls = 0;
     std::vector<double> st_off, st_scale, act_off, act_scale, act_min, act_max, st_groups;
 };
 
@@ -123,6 +127,12 @@ bool build_device_model(dm_handle& H) {
     M.pose_dim = cm.pose_dim;
     M.phase_input = sa.ctrl.enable_phase_input; M.rec_world_root_pos = sa.ctrl.record_world_root_pos; M.rec_world_root_rot = sa.ctrl.record_world_root_rot;
     M.state_size = (M.phase_input ? 1 : 0) + 1 + nl * 9 + nl * 6;
+    M.amp_local_root = sa.cfg.enable_amp_obs_local_root ? 1 : 0;
+    {   // cSceneImitateAMP::GetAMPObsSize (SceneImitateAMP.cpp:75-84,214-258)
+        int pose_sz = 1 + 6, nee = 0;
+        for (int j = 0; j < nl; ++j) { const auto& jd = cm.joints[j]; if (jd.is_end_eff) ++nee; if (j > 0) pose_sz += (jd.type == dmh::kSpherical) ? 6 : jd.param_size; }
+        M.amp_obs_size = 2 * (pose_sz + 3 * nee + 6 + (cm.pose_dim - cm.joints[0].param_size));
+    }
     M.num_frames = sa.motion.num_frames; M.loop_motion = sa.motion.loop;
     M.enable_fall_end = sa.cfg.enable_fall_end; M.enable_contact_fall = sa.cfg.enable_char_contact_fall; M.sync_root_pos = sa.cfg.sync_char_root_pos;
     M.sync_root_rot = sa.cfg.sync_char_root_rot; M.rand_rot_reset = sa.cfg.enable_rand_rot_reset;
@@ -370,6 +380,8 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
               chk(cudaMalloc(&h->d_frames, sizeof(float) * M.num_frames * M.pose_dim), "cudaMalloc frames") &&
               chk(cudaMalloc(&h->d_frame_vel, sizeof(float) * M.num_frames * M.pose_dim), "cudaMalloc frame_vel") &&
               chk(cudaMalloc(&h->d_flags4, N * 4 * sizeof(int32_t)), "cudaMalloc flags4") &&
+              chk(cudaMalloc(&h->d_amp, N * M.amp_obs_size * sizeof(float)), "cudaMalloc amp") && chk(cudaMallocHost(&h->p_amp, N * M.amp_obs_size * sizeof(float)), "cudaMallocHost amp") &&
+              chk(cudaMalloc(&h->st.hist, N * 2 * M.pose_dim * sizeof(float)), "cudaMalloc hist") && chk(cudaMemset(h->st.hist, 0, N * 2 * M.pose_dim * sizeof(float)), "memset hist") &&
               chk(cudaMalloc(&h->d_act, N * std::max(1, M.action_size) * sizeof(float)), "cudaMalloc act") &&
               chk(cudaMalloc(&h->d_obs, N * M.state_size * sizeof(float)), "cudaMalloc obs") && chk(cudaMalloc(&h->d_rew, N * sizeof(float)), "cudaMalloc rew") &&
               chk(cudaMallocHost(&h->p_act, N * std::max(1, M.action_size) * sizeof(float)), "cudaMallocHost") &&
@@ -406,7 +418,7 @@ void dm_destroy(dm_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_model); cudaFree(h->st.sim); cudaFree(h->st.time); cudaFree(h->st.flags); cudaFree(h->st.manifold);
+    cudaFree(h->d_amp); cudaFreeHost(h->p_amp); cudaFree(h->st.hist); cudaFree(h->d_model); cudaFree(h->st.sim); cudaFree(h->st.time); cudaFree(h->st.flags); cudaFree(h->st.manifold);
     cudaFree(h->d_frame_times); cudaFree(h->d_frames); cudaFree(h->d_frame_vel); cudaFree(h->d_flags4); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew);
     for (auto& p : h->d_inj) cudaFree(p);
     cudaFreeHost(h->p_act); cudaFreeHost(h->p_obs); cudaFreeHost(h->p_rew); cudaFreeHost(h->p_flags);
@@ -416,7 +428,7 @@ void dm_destroy(dm_handle* h) {
 
 int dm_get_dims(dm_handle* h, dm_dims* o) {
     const auto& M = h->hm;
-    o->num_envs = h->num_envs; o->num_joints = M.nl; o->pose_dim = M.pose_dim; o->num_dofs = M.n; o->state_size = M.state_size; o->goal_size = 0;
+    o->num_envs = h->num_envs; o->num_joints = M.nl; o->pose_dim = M.pose_dim; o->num_dofs = M.n; o->state_size = M.state_size; o->goal_size = 0; o->amp_obs_size = M.amp_obs_size;
     o->action_size = M.action_size; o->snapshot_size = 29 + 59 * M.nl;
     o->num_update_substeps = h->sa.cfg.num_update_substeps;
     o->updates_per_action = 20;
@@ -472,6 +484,41 @@ int dm_observe(dm_handle* h, float* d_state, float* d_reward) {
 }
 int dm_record_state(dm_handle* h, float* d_out) { return dm_observe(h, d_out, nullptr); }
 int dm_record_goal(dm_handle*, float*) { return 0; }
+static int launch_amp(dm_handle* h, float* d_out, int expert, const double* d_times) {
+    constexpr int BLOCK = 64;
+    if (h->W == 16) dmk::dm_amp_obs_kernel<16, BLOCK><<<h->padded_envs / (BLOCK / 16), BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, d_out, expert, d_times, h->num_envs);
+    else dmk::dm_amp_obs_kernel<32, BLOCK><<<h->padded_envs / (BLOCK / 32), BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, d_out, expert, d_times, h->num_envs);
+    DM_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+int dm_record_amp_obs_agent(dm_handle* h, float* d_out) { DM_DEVICE(h); return launch_amp(h, d_out, 0, nullptr); }
+int dm_amp_obs_host(dm_handle* h, int expert, const double* h_kin_time, float* h_out) {
+    DM_DEVICE(h);
+    if (expert ? dm_record_amp_obs_expert(h, h_kin_time, h->d_amp) : dm_record_amp_obs_agent(h, h->d_amp)) return 1;
+    const size_t bytes = static_cast<size_t>(h->num_envs) * h->hm.amp_obs_size * sizeof(float);
+    DM_CUDA(cudaMemcpyAsync(h->p_amp, h->d_amp, bytes, cudaMemcpyDeviceToHost, h->stream));
+    DM_CUDA(cudaStreamSynchronize(h->stream));
+    std::memcpy(h_out, h->p_amp, bytes);
+    return 0;
+}
+int dm_record_amp_obs_expert(dm_handle* h, const double* h_kin_time, float* d_out) {
+    DM_DEVICE(h);
+    std::vector<double> tmp(h->padded_envs, 0.0);
+    if (h_kin_time) std::copy(h_kin_time, h_kin_time + h->num_envs, tmp.begin());
+    else {   // cSceneImitateAMP::RecordAMPObsExpert draws U(0, duration) per call; here a counter-based stream per (seed, env, call)
+        const double dur = h->hm.motion_dur;
+        for (int e = 0; e < h->num_envs; ++e) {
+            unsigned long long z = h->seed + 0x9E3779B97F4A7C15ull * ((h->env_offset + e) * 2654435761ull + 0x51ed27ull + h->amp_calls);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+            tmp[e] = dur * static_cast<double>(z >> 11) * (1.0 / 9007199254740992.0);
+        }
+        h->amp_calls++;
+    }
+    DM_CUDA(cudaMemcpyAsync(h->d_inj[0], tmp.data(), sizeof(double) * h->padded_envs, cudaMemcpyHostToDevice, h->stream));
+    DM_CUDA(cudaStreamSynchronize(h->stream));   // tmp is pageable host memory
+    return launch_amp(h, d_out, 1, h->d_inj[0]);
+}
 int dm_calc_reward(dm_handle* h, float* d_out) { return dm_observe(h, nullptr, d_out); }
 int dm_get_flags(dm_handle* h, int32_t* d_flags) {
     DM_DEVICE(h);

@@ -122,12 +122,12 @@ public:
     virtual double GetRewardFail(int) const { return 0; }
     virtual double GetRewardSucc(int) const { return 1; }
     virtual bool EnableAMPTaskReward() const { return false; }
-    virtual int GetAMPObsSize() const { return 0; }
-    virtual std::vector<double> GetAMPObsOffset() const { return std::vector<double>(); }
-    virtual std::vector<double> GetAMPObsScale() const { return std::vector<double>(); }
-    virtual std::vector<int> GetAMPObsNormGroup() const { return std::vector<int>(); }
-    virtual std::vector<double> RecordAMPObsExpert(int) { return std::vector<double>(); }
-    virtual std::vector<double> RecordAMPObsAgent(int) { return std::vector<double>(); }
+    virtual int GetAMPObsSize() const { return mDims.amp_obs_size; }
+    virtual std::vector<double> GetAMPObsOffset() const { return std::vector<double>(mDims.amp_obs_size, 0.0); }   // SceneImitateAMP.cpp:86-89
+    virtual std::vector<double> GetAMPObsScale() const { return std::vector<double>(mDims.amp_obs_size, 1.0); }    // :91-94
+    virtual std::vector<int> GetAMPObsNormGroup() const { return std::vector<int>(mDims.amp_obs_size, 0); }         // gNormGroupSingle, :96-99
+    virtual std::vector<double> RecordAMPObsExpert(int agent_id) { return AmpObs(1, agent_id); }
+    virtual std::vector<double> RecordAMPObsAgent(int agent_id) { return AmpObs(0, agent_id); }
     virtual bool IsEpisodeEnd() { Refresh(); for (int e = 0; e < mNumEnvs; ++e) if (mFlags[4 * e + 1]) return true; return false; }
     virtual bool CheckValidEpisode() { Refresh(); for (int e = 0; e < mNumEnvs; ++e) if (!mFlags[4 * e + 3]) return false; return true; }
     virtual int CheckTerminate(int agent_id) { Refresh(); return mFlags[4 * Env(agent_id) + 2]; }
@@ -150,6 +150,13 @@ private:
         FlushActions();
         Check(dm_step_host(mHandle, nullptr, 0.0, 0, mState.data(), mReward.data(), mFlags.data()));
         mFresh = true;
+    }
+    std::vector<double> AmpObs(int expert, int agent_id) {
+        FlushActions();
+        std::vector<float> buf(static_cast<size_t>(mNumEnvs) * mDims.amp_obs_size);
+        Check(dm_amp_obs_host(mHandle, expert, nullptr, buf.data()));
+        const float* p = &buf[static_cast<size_t>(Env(agent_id)) * mDims.amp_obs_size];
+        return std::vector<double>(p, p + mDims.amp_obs_size);
     }
     std::vector<double> Static(int kind, int n) const {
         std::vector<double> v(n);

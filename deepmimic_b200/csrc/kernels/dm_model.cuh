@@ -52,7 +52,7 @@ struct DevLink {
 
 struct DevModel {
     int nl, n, maxlevel, cs;              // links, 6+dofs, deepest tree level, chain stride
-    int pose_dim, state_size, action_size;
+    int pose_dim, state_size, action_size, amp_obs_size, amp_local_root;
     int phase_input, rec_world_root_pos, rec_world_root_rot;
     int num_frames, loop_motion;
     int enable_fall_end, enable_contact_fall, sync_root_pos, sync_root_rot, rand_rot_reset;
@@ -86,6 +86,7 @@ struct DevState {
     double* time;
     int* flags;
     float* manifold;
+    float* hist;  // AMP history: DeepMimic pose | vel vectors (2 * pose_dim floats per env) of the simulated character at the last applied action
     float* pdbg;  // optional debug scratch (n x ...), may be null
     int num_envs;
 };

@@ -93,6 +93,69 @@ __device__ __forceinline__ KinJoint sample_joint(const DevLink& L, const float* 
     return k;
 }
 
+
+// DeepMimic pose / vel entries of one joint from the simulated state: cSimCharacter::BuildPose / BuildVel (SimCharacter.cpp:1428-1507),
+// cSimBodyJoint::BuildPose / BuildVel (SimBodyJoint.cpp:342-445).  q: joint rotation (x,y,z,w) in the joint frame (root: world rotation),
+// p: root position / (angle, -, -), w: joint-local angular velocity / (rate, -, -), v: root linear velocity.
+struct DmJoint { Q4 q; V3 p, w, v; };
+__device__ __forceinline__ DmJoint sim_joint_to_dm(const DevModel& M, const DevLink& L, const float* sim, int j, bool is_root) {
+    DmJoint d; d.q = mkq(0, 0, 0, 1); d.p = mk3(0, 0, 0); d.w = mk3(0, 0, 0); d.v = mk3(0, 0, 0);
+    const float inv_scale = 1.0f / M.scale;
+    if (is_root) {
+        d.p = inv_scale * mk3(sim[0], sim[1], sim[2]);
+        d.q = qconj(mkq(sim[4], sim[5], sim[6], sim[7]));
+        if (d.q.w < 0) d.q = mkq(-d.q.x, -d.q.y, -d.q.z, -d.q.w);
+        d.w = mk3(sim[8], sim[9], sim[10]);
+        d.v = inv_scale * mk3(sim[12], sim[13], sim[14]);
+        return d;
+    }
+    const float4 jp = reinterpret_cast<const float4*>(sim + 16)[j];
+    const float4 jv = reinterpret_cast<const float4*>(sim + 16 + 4 * M.nl)[j];
+    if (L.jtype == kJSpherical) {
+        const Q4 cr = mkq(L.child_rot[0], L.child_rot[1], L.child_rot[2], L.child_rot[3]);
+        Q4 q = qmul(qmul(qconj(cr), mkq(jp.x, jp.y, jp.z, jp.w)), cr);
+        if (q.w < 0) q = mkq(-q.x, -q.y, -q.z, -q.w);
+        d.q = q;
+        d.w = qrot(qconj(cr), mk3(jv.x, jv.y, jv.z));
+    } else if (L.jtype == kJRevolute) { d.p.x = norm_angle(jp.x); d.w.x = jv.x; }
+    return d;
+}
+// write / read one joint of a DeepMimic pose | vel pair stored as floats (quaternions w-first, like the reference's vectors)
+__device__ __forceinline__ void hist_store(float* h, int pose_dim, const DevLink& L, bool is_root, const DmJoint& d) {
+    float* p = h + L.pose_off; float* v = h + pose_dim + L.pose_off;
+    if (is_root) { p[0] = d.p.x; p[1] = d.p.y; p[2] = d.p.z; p[3] = d.q.w; p[4] = d.q.x; p[5] = d.q.y; p[6] = d.q.z; v[0] = d.v.x; v[1] = d.v.y; v[2] = d.v.z; v[3] = d.w.x; v[4] = d.w.y; v[5] = d.w.z; v[6] = 0.f; }
+    else if (L.jtype == kJSpherical) { p[0] = d.q.w; p[1] = d.q.x; p[2] = d.q.y; p[3] = d.q.z; v[0] = d.w.x; v[1] = d.w.y; v[2] = d.w.z; v[3] = 0.f; }
+    else if (L.jtype == kJRevolute) { p[0] = d.p.x; v[0] = d.w.x; }
+}
+__device__ __forceinline__ DmJoint hist_load(const float* h, int pose_dim, const DevLink& L, bool is_root) {
+    DmJoint d; d.q = mkq(0, 0, 0, 1); d.p = mk3(0, 0, 0); d.w = mk3(0, 0, 0); d.v = mk3(0, 0, 0);
+    const float* p = h + L.pose_off; const float* v = h + pose_dim + L.pose_off;
+    if (is_root) { d.p = mk3(p[0], p[1], p[2]); d.q = mkq(p[4], p[5], p[6], p[3]); d.v = mk3(v[0], v[1], v[2]); d.w = mk3(v[3], v[4], v[5]); }
+    else if (L.jtype == kJSpherical) { d.q = mkq(p[1], p[2], p[3], p[0]); d.w = mk3(v[0], v[1], v[2]); }
+    else if (L.jtype == kJRevolute) { d.p.x = p[0]; d.w.x = v[0]; }
+    return d;
+}
+// raw clip sample (cMotion::CalcFrame / CalcFrameVel: no origin, no cycle offset) for joint `lane`
+__device__ __forceinline__ DmJoint clip_joint(const DevModel& M, const DevLink& L, const double* ft, const float* frames, const float* frame_vel, double time, bool is_root) {
+    int idx, cyc; double bld;
+    frame_index(M, ft, time, idx, bld, cyc);
+    const float blv = static_cast<float>(bld);
+    const float bl = static_cast<float>(fmin(fmax(bld, 0.0), 1.0));
+    const float* f0 = frames + static_cast<size_t>(idx) * M.pose_dim; const float* f1 = f0 + M.pose_dim;
+    const float* v0 = frame_vel + static_cast<size_t>(idx) * M.pose_dim; const float* v1 = v0 + M.pose_dim;
+    const bool over = !M.loop_motion && time >= M.motion_dur;
+    KinJoint k = sample_joint(L, f0, f1, v0, v1, bl, is_root);
+    DmJoint d; d.q = k.q; d.p = mk3(k.ang, 0, 0); d.w = (L.jtype == kJRevolute && !is_root) ? mk3(0, 0, 0) : mk3(0, 0, 0); d.v = mk3(0, 0, 0);
+    const int o = L.pose_off;
+    if (is_root) {
+        d.p = mk3((1 - bl) * f0[0] + bl * f1[0], (1 - bl) * f0[1] + bl * f1[1], (1 - bl) * f0[2] + bl * f1[2]);
+        if (!over) { d.v = mk3((1 - blv) * v0[0] + blv * v1[0], (1 - blv) * v0[1] + blv * v1[1], (1 - blv) * v0[2] + blv * v1[2]);
+                     d.w = mk3((1 - blv) * v0[3] + blv * v1[3], (1 - blv) * v0[4] + blv * v1[4], (1 - blv) * v0[5] + blv * v1[5]); }
+    } else if (L.jtype == kJSpherical) { if (!over) d.w = mk3((1 - blv) * v0[o] + blv * v1[o], (1 - blv) * v0[o + 1] + blv * v1[o + 1], (1 - blv) * v0[o + 2] + blv * v1[o + 2]); }
+    else if (L.jtype == kJRevolute) { if (!over) d.w.x = (1 - blv) * v0[o] + blv * v1[o]; }
+    return d;
+}
+
 }  // namespace
 
 // obs: [N x state_size] floats, reward: [N] floats.  Either pointer may be null.
@@ -275,13 +338,107 @@ __global__ void __launch_bounds__(BLOCK) dm_observe_kernel(const DevModel* __res
     }
 }
 
+// AMP observations (cSceneImitateAMP::BuildAMPObs, SceneImitateAMP.cpp:279-397): [pose now | pose prev | vel now | vel prev], one tile per
+// environment, lane = joint.  expert == 0: "now" is the simulated character, "prev" the history block (RecordAMPObsAgent, :101-113);
+// expert != 0: the raw clip at expert_time[env] and one query period earlier, ground height = the kinematic origin's y (:115-140).
+template <int W, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) dm_amp_obs_kernel(const DevModel* __restrict__ gm, DevState st, const double* __restrict__ frame_times,
+                                                            const float* __restrict__ frames, const float* __restrict__ frame_vel, float* __restrict__ out,
+                                                            int expert, const double* __restrict__ expert_time, int num_real_envs) {
+    using T = TileP<W>;
+    const int tiles = BLOCK / W, tile = threadIdx.x / W, lane = threadIdx.x % W;
+    const int env = blockIdx.x * tiles + tile;
+    const DevModel& M = *gm;
+    const int nl = M.nl;
+    const bool act = lane < nl;
+    const int li = act ? lane : nl - 1;
+    const DevLink& L = M.link[li];
+    const int parent = L.parent, plane = parent >= 0 ? parent : 0, level = act ? L.level : 1000, jtype = L.jtype;
+    const bool is_root = lane == 0;
+    const float* sim = st.sim + static_cast<size_t>(env) * sim_stride(nl);
+    const double* tm = st.time + static_cast<size_t>(env) * kTimeDoubles;
+    DmJoint now, prev;
+    float ground_h = 0.f;
+    if (!expert) {
+        now = sim_joint_to_dm(M, L, sim, li, is_root);
+        prev = hist_load(st.hist + static_cast<size_t>(env) * 2 * M.pose_dim, M.pose_dim, L, is_root);
+    } else {
+        const double t = expert_time[env];
+        now = clip_joint(M, L, frame_times, frames, frame_vel, t, is_root);
+        prev = clip_joint(M, L, frame_times, frames, frame_vel, t - M.query_dt, is_root);
+        ground_h = static_cast<float>(tm[kTOrigin + 1]);
+    }
+    // heading of the current root (cKinTree::CalcHeadingRot, KinTree.cpp:1629-1635): rotation about y by -heading
+    const Q4 rq_now = mkq(T::shfl(now.q.x, 0), T::shfl(now.q.y, 0), T::shfl(now.q.z, 0), T::shfl(now.q.w, 0));
+    const V3 hx = qrot(rq_now, mk3(1, 0, 0));
+    const float heading = atan2f(-hx.z, hx.x);
+    float sh, ch; sincosf(-heading, &sh, &ch);
+    auto rotH = [&](V3 v) { return mk3(ch * v.x + sh * v.z, v.y, -sh * v.x + ch * v.z); };
+    const Q4 refq = mkq(0.f, sinf(-0.5f * heading), 0.f, cosf(-0.5f * heading));
+    // layout offsets: joint block sizes by an exclusive scan over the lanes
+    const int jsz = (!act || is_root) ? 0 : (jtype == kJSpherical ? 6 : (jtype == kJRevolute ? 1 : 0));
+    int incl = jsz, eincl = (act && L.end_eff) ? 1 : 0;
+#pragma unroll
+    for (int o = 1; o < W; o <<= 1) { int t1 = __shfl_up_sync(0xffffffffu, incl, o, W), t2 = __shfl_up_sync(0xffffffffu, eincl, o, W); if (lane >= o) { incl += t1; eincl += t2; } }
+    const int joff = incl - jsz, eidx = eincl - ((act && L.end_eff) ? 1 : 0);
+    const int jtot = __shfl_sync(0xffffffffu, incl, W - 1, W), etot = __shfl_sync(0xffffffffu, eincl, W - 1, W);
+    const int pose_size = 1 + 6 + jtot + 3 * etot;
+    const int vel_size = 6 + (M.pose_dim - 7);
+    float* o = (env < num_real_envs) ? out + static_cast<size_t>(env) * (2 * (pose_size + vel_size)) : nullptr;
+    // kinematic tree of both poses: joint world rotation / origin (cKinTree::JointWorldTrans)
+    const V3 att_pt = mk3(L.att_pt[0], L.att_pt[1], L.att_pt[2]);
+    const Q4 att_rot = mkq(L.att_rot[0], L.att_rot[1], L.att_rot[2], L.att_rot[3]);
+    const V3 body_att = mk3(L.body_att[0], L.body_att[1], L.body_att[2]);
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+        const DmJoint& d = blk == 0 ? now : prev;
+        Q4 jq = (jtype == kJSpherical) ? d.q : ((jtype == kJRevolute) ? mkq(0.f, 0.f, sinf(0.5f * d.p.x), cosf(0.5f * d.p.x)) : mkq(0, 0, 0, 1));
+        Q4 kq = d.q; V3 kp = d.p;       // lane 0: root rotation / position
+        for (int lv = 1; lv <= M.maxlevel; ++lv) {
+            Q4 pq = mkq(T::shfl(kq.x, plane), T::shfl(kq.y, plane), T::shfl(kq.z, plane), T::shfl(kq.w, plane));
+            V3 pp = T::shfl3(kp, plane);
+            if (level == lv) { kp = pp + qrot(pq, att_pt); kq = qmul(qmul(pq, att_rot), jq); }
+        }
+        const V3 root_pos = T::shfl3(kp, 0);
+        if (o == nullptr || !act) continue;
+        float* ob = o + blk * pose_size;
+        if (is_root) {
+            ob[0] = d.p.y - ground_h;
+            Q4 rr = d.q;
+            if (M.amp_local_root) rr = qmul(refq, rr);
+            const V3 nrm = qrot(rr, mk3(0, 1, 0)), tan = qrot(rr, mk3(1, 0, 0));   // cMathUtil::CalcNormalTangent (MathUtil.cpp:617-623)
+            ob[1] = nrm.x; ob[2] = nrm.y; ob[3] = nrm.z; ob[4] = tan.x; ob[5] = tan.y; ob[6] = tan.z;
+        } else if (jtype == kJSpherical) {
+            const V3 nrm = qrot(d.q, mk3(0, 1, 0)), tan = qrot(d.q, mk3(1, 0, 0));
+            float* q = ob + 7 + joff;
+            q[0] = nrm.x; q[1] = nrm.y; q[2] = nrm.z; q[3] = tan.x; q[4] = tan.y; q[5] = tan.z;
+        } else if (jtype == kJRevolute) ob[7 + joff] = d.p.x;
+        if (L.end_eff) {   // cKinTree::CalcBodyPartPos (KinTree.cpp:272-281) relative to the root, in the heading frame of the current pose
+            const V3 bp = rotH(kp + qrot(kq, body_att) - root_pos);
+            float* e = ob + 7 + jtot + 3 * eidx;
+            e[0] = bp.x; e[1] = bp.y; e[2] = bp.z;
+        }
+        // velocities (RecordAMPObsVel, :367-397): root lin / ang, then the joint part of the vel vector
+        float* ov = o + 2 * pose_size + blk * vel_size;
+        if (is_root) {
+            V3 rv = d.v, rw = d.w;
+            if (M.amp_local_root) { rv = rotH(rv); rw = rotH(rw); }
+            ov[0] = rv.x; ov[1] = rv.y; ov[2] = rv.z; ov[3] = rw.x; ov[4] = rw.y; ov[5] = rw.z;
+        } else if (jtype == kJSpherical) { float* q = ov + 6 + (L.pose_off - 7); q[0] = d.w.x; q[1] = d.w.y; q[2] = d.w.z; q[3] = 0.f; }
+        else if (jtype == kJRevolute) ov[6 + (L.pose_off - 7)] = d.w.x;
+    }
+}
+
 // actions: [N x action_size] floats (DeepMimic action layout)
 __global__ void dm_set_action_kernel(const DevModel* __restrict__ gm, DevState st, const float* __restrict__ actions, int num_real_envs) {
     const DevModel& M = *gm;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int env = gid / M.nl, j = gid % M.nl;
-    if (env >= num_real_envs || j == 0) return;
+    if (env >= num_real_envs) return;
     const DevLink& L = M.link[j];
+    // cSceneImitateAMP::UpdateHist (SceneImitateAMP.cpp:167-172): the pose / vel the new action was chosen from
+    if (st.hist) hist_store(st.hist + static_cast<size_t>(env) * 2 * M.pose_dim, M.pose_dim, L, j == 0, sim_joint_to_dm(M, L, st.sim + static_cast<size_t>(env) * sim_stride(M.nl), j, j == 0));
+    if (j == 0) return;
     const float* a = actions + static_cast<size_t>(env) * M.action_size + L.act_off;
     float4* tgt = reinterpret_cast<float4*>(st.sim + static_cast<size_t>(env) * sim_stride(M.nl) + 16 + 8 * M.nl) + j;
     if (L.jtype == kJSpherical) {
@@ -407,6 +564,22 @@ __global__ void __launch_bounds__(BLOCK) dm_reset_kernel(const DevModel* __restr
         tm[kTOriginRot] = cth; tm[kTOriginRot + 1] = 0.0; tm[kTOriginRot + 2] = sth; tm[kTOriginRot + 3] = 0.0;
         fl[kFNeedAction] = 1; fl[kFDone] = 0; fl[kFTerminate] = 0; fl[kFValid] = 1; fl[kFFallen] = 0; fl[kFUpdates] = 0; fl[7] = fl[7] + 1;
     }
+    if (act && st.hist) {
+        // cSceneImitateAMP::InitHist (SceneImitateAMP.cpp:153-165): the kinematic character one query period before the controller time,
+        // with the final origin (cKinCharacter::CalcPose / CalcVel, KinCharacter.cpp:363-406)
+        const double tprev = kt - M.query_dt;
+        DmJoint d = clip_joint(M, L, frame_times, frames, frame_vel, tprev, lane == 0);
+        if (lane == 0) {
+            int idx, cyc; double bld;
+            frame_index(M, frame_times, tprev, idx, bld, cyc);
+            if (M.loop_motion) { d.p.x += cyc * M.cycle_delta[0]; d.p.z += cyc * M.cycle_delta[2]; }
+            const V3 org = mk3(basePos.x / M.scale, basePos.y / M.scale, basePos.z / M.scale) - qrot(orot, rp);
+            d.p = qrot(orot, d.p) + org;
+            d.q = qmul(orot, d.q); if (d.q.w < 0) d.q = mkq(-d.q.x, -d.q.y, -d.q.z, -d.q.w);
+            d.v = qrot(orot, d.v); d.w = qrot(orot, d.w);
+        }
+        hist_store(st.hist + static_cast<size_t>(env) * 2 * M.pose_dim, M.pose_dim, L, lane == 0, d);
+    }
     if (act) {
         reinterpret_cast<float4*>(sim + 16)[lane] = jp;
         reinterpret_cast<float4*>(sim + 16 + 4 * nl)[lane] = jv;
@@ -417,6 +590,8 @@ __global__ void __launch_bounds__(BLOCK) dm_reset_kernel(const DevModel* __restr
 
 template __global__ void dm_observe_kernel<16, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
 template __global__ void dm_observe_kernel<32, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
+template __global__ void dm_amp_obs_kernel<16, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int);
+template __global__ void dm_amp_obs_kernel<32, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int);
 template __global__ void dm_reset_kernel<16, 64>(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*, unsigned long long, unsigned long long, int);
 template __global__ void dm_reset_kernel<32, 64>(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*, unsigned long long, unsigned long long, int);
 

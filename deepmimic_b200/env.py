@@ -96,6 +96,32 @@ class DeepMimicBatchEnv:
         self._post()
         return self._rew
 
+    # ---- AMP observations (R/env/deepmimic_env.py:147-166)
+    def get_amp_obs_size(self):
+        return self._core.dims.amp_obs_size
+
+    def get_amp_obs_offset(self):
+        return np.zeros(self.get_amp_obs_size())
+
+    def get_amp_obs_scale(self):
+        return np.ones(self.get_amp_obs_size())
+
+    def get_amp_obs_norm_group(self):
+        return np.zeros(self.get_amp_obs_size(), dtype=np.int32)
+
+    def _amp_buf(self):
+        if not hasattr(self, "_amp"):
+            self._amp = self.torch.zeros(self.num_envs, self.get_amp_obs_size(), device=self.device)
+        return self._amp
+
+    def record_amp_obs_agent(self, agent_id=0):
+        self._pre(); self._core.amp_obs_agent(self._amp_buf()); self._post()
+        return self._amp
+
+    def record_amp_obs_expert(self, agent_id=0, kin_time=None):
+        self._pre(); self._core.amp_obs_expert(self._amp_buf(), kin_time); self._post()
+        return self._amp
+
     def is_episode_end(self):
         return self._refresh_flags()[:, 1].bool()
 

@@ -43,6 +43,7 @@ typedef struct dm_dims {
     int updates_per_action;/* 20 for the shipped arg files (30 Hz queries, 600 Hz updates) */
     int num_update_substeps;
     double motion_duration;
+    int amp_obs_size;      /* AMP observation length (226 humanoid3d): GetAMPObsSize, DeepMimicCore.h:78 */
 } dm_dims;
 
 enum dm_static_kind {
@@ -83,6 +84,13 @@ int dm_update(dm_handle* h, double dt, int n_updates);
 int dm_record_state(dm_handle* h, float* d_out);             /* [num_envs x state_size] */
 int dm_record_goal(dm_handle* h, float* d_out);              /* [num_envs x goal_size] (no-op when goal_size == 0) */
 int dm_calc_reward(dm_handle* h, float* d_out);              /* [num_envs] */
+/* AMP observations (RecordAMPObsAgent / RecordAMPObsExpert, DeepMimicCore.h:81-82; cSceneImitateAMP::BuildAMPObs): [num_envs x amp_obs_size].
+ * Agent: simulated pose / vel now and at the last dm_set_action (call dm_set_action exactly when need_new_action is set, like the
+ * reference's agent).  Expert: the clip at h_kin_time[env] (NULL: random U(0, duration) per env and call) and one query period earlier. */
+int dm_record_amp_obs_agent(dm_handle* h, float* d_out);
+int dm_record_amp_obs_expert(dm_handle* h, const double* h_kin_time, float* d_out);
+/* Same with a host output buffer [num_envs x amp_obs_size] (device -> host copy inside); used by the cDeepMimicCore facade. */
+int dm_amp_obs_host(dm_handle* h, int expert, const double* h_kin_time, float* h_out);
 int dm_observe(dm_handle* h, float* d_state, float* d_reward);  /* fused record_state + calc_reward, either may be NULL */
 /* d_flags: [num_envs x 4] int32 = {need_new_action, is_episode_end, check_terminate (0 null / 1 fail), check_valid_episode} */
 int dm_get_flags(dm_handle* h, int32_t* d_flags);
