@@ -39,14 +39,13 @@ __device__ __forceinline__ int wmax(int v) {
     return v;
 }
 
-// articulated (or rigid) spatial inertia about a link's joint pivot, link axes:  n = ww*w + wv*v ; f = wv^T*w + vv*v
+// articulated (or rigid) spatial inertia about a link's joint pivot, world axes:  n = ww*w + wv*v ; f = wv^T*w + vv*v
 struct Art {
     float ww[6];   // xx xy xz yy yz zz
     float wv[9];   // row major
     float vv[6];
 };
 __device__ __forceinline__ V3 wvT_mul(const float* g, V3 w) { return mk3(g[0] * w.x + g[3] * w.y + g[6] * w.z, g[1] * w.x + g[4] * w.y + g[7] * w.z, g[2] * w.x + g[5] * w.y + g[8] * w.z); }
-__device__ __forceinline__ V3 wv_mul(const float* g, V3 v) { return mk3(g[0] * v.x + g[1] * v.y + g[2] * v.z, g[3] * v.x + g[4] * v.y + g[5] * v.z, g[6] * v.x + g[7] * v.y + g[8] * v.z); }
 // R^T S R for a symmetric S (R row-major, maps parent -> child axes)
 __device__ __forceinline__ void rot_sym(const M3& R, const float* s, float* o) {
     // T = S R (3x3), o = R^T T (symmetric)
@@ -64,22 +63,6 @@ __device__ __forceinline__ void rot_sym(const M3& R, const float* s, float* o) {
     o[4] = R.m[1] * t[2] + R.m[4] * t[5] + R.m[7] * t[8];
     o[5] = R.m[2] * t[2] + R.m[5] * t[5] + R.m[8] * t[8];
 }
-__device__ __forceinline__ void rot_gen(const M3& R, const float* g, float* o) {
-    float t[9];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) t[i * 3 + j] = g[i * 3] * R.m[j] + g[i * 3 + 1] * R.m[3 + j] + g[i * 3 + 2] * R.m[6 + j];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) o[i * 3 + j] = R.m[i] * t[j] + R.m[3 + i] * t[3 + j] + R.m[6 + i] * t[6 + j];
-}
-// motion vector, parent pivot frame -> child pivot frame (R parent->child axes, c = parent pivot -> child pivot in parent axes)
-__device__ __forceinline__ S6 xm(const M3& R, V3 c, S6 m) { return mks(mul(R, m.a), mul(R, m.l - cross(c, m.a))); }
-// force vector, child pivot frame -> parent pivot frame
-__device__ __forceinline__ S6 xf(const M3& R, V3 c, S6 f) { V3 l = mulT(R, f.l); return mks(mulT(R, f.a) + cross(c, l), l); }
-
 __device__ __forceinline__ float normalize_angle3(float t) {  // cMathUtil::NormalizeAngle
     float n = fmodf(t, 6.283185307179586f);
     if (n > 3.14159265358979f) n -= 6.283185307179586f;
@@ -154,7 +137,7 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
 #define SPROF(sec) do { } while (0)
 #endif
     const StepLayout& LY = *reinterpret_cast<const StepLayout*>(LYS);
-    const int nl = LY.nl, n = LY.n, CL = LY.chain_len, MR = LY.maxrows;
+    const int nl = LY.nl, CL = LY.chain_len, MR = LY.maxrows;
     float* sU = E + LY.oU; float* sS = E + LY.oR; float* sW = E + LY.oW; float* sV = E + LY.oV; float* sA = E + LY.oA; float* sY = E + LY.oY;
     float* sLam = E + LY.oLam; float* sRhs = E + LY.oRhs; float* sInv = E + LY.oInv; int* sRl = reinterpret_cast<int*>(E + LY.oRl);
     float* sPp = E + LY.oPp; float* sPi = E + LY.oPi; int* sPr = reinterpret_cast<int*>(E + LY.oPr);

@@ -37,6 +37,9 @@ def test_facade_runs_the_reference_call_pattern(asset_root):
     np.testing.assert_allclose(core.BuildActionBoundMin(0), st[2], atol=1e-12)
     np.testing.assert_allclose(core.BuildActionBoundMax(0), st[3], atol=1e-12)
     assert len(core.BuildStateNormGroups(0)) == o.state_size and core.BuildStateNormGroups(0)[0] == -1
+    # AMP observation surface (DeepMimicCore.h:76-82)
+    assert core.GetAMPObsSize() == o.amp_obs_size() == 226 and not core.EnableAMPTaskReward()
+    assert core.GetAMPObsOffset() == [0.0] * 226 and core.GetAMPObsScale() == [1.0] * 226 and core.GetAMPObsNormGroup() == [0] * 226
     core.SetMode(1)
     core.Reset()
     assert core.GetTime() == 0.0 and core.NeedNewAction(0)        # a fresh episode asks for an action (CtController.cpp:35-39)
@@ -56,6 +59,8 @@ def test_facade_runs_the_reference_call_pattern(asset_root):
         if core.IsEpisodeEnd():
             assert core.CheckTerminate(0) in (1, 2)
             core.Reset()
+    ag, ex = np.array(core.RecordAMPObsAgent(0)), np.array(core.RecordAMPObsExpert(0))
+    assert ag.shape == (226,) and ex.shape == (226,) and np.isfinite(ag).all() and np.isfinite(ex).all()
     assert n_actions >= 10          # 200 updates at 600 Hz = 10 policy steps (+ resets)
     assert abs(core.GetTime() - 200 / 600.0) < 1e-9 or n_actions > 10
     assert all(0.0 <= r <= 1.0 + 1e-6 for r in rewards)
