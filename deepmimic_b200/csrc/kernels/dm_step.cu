@@ -257,25 +257,29 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
     const int NLmax = (W == 32) ? NL : wmax(NL);
     if (nslots == 1) {
         // ================= common case: at most W rows -> one row per lane, A stored as a full symmetric W x W square (stride W)
-        const int bjl = (lane < NR) ? sRl[lane] : 0;
-        __syncwarp();
+        // lanes = (i, j <= i) pairs of the lower triangle, W pairs per pass
+        const int npair = NR * (NR + 1) / 2, npmax = NRmax * (NRmax + 1) / 2;
 #pragma unroll 1
-        for (int i = 0; i < NRmax; ++i) {
-            const bool iv = i < NR;
-            const int bi = iv ? sRl[i] : 0;
-            const int cd = (iv && lane <= i) ? CD[bi * nl + bjl] : 0;          // common chain depth of rows i and lane
-            const float* yi = sY + i; const float* yr = sY + lane;
+        for (int q0 = 0; q0 < npmax; q0 += W) {
+            const int q = q0 + lane;
+            const bool pv = q < npair;
+            int i = static_cast<int>((sqrtf(8.0f * static_cast<float>(q) + 1.0f) - 1.0f) * 0.5f);
+            if (i * (i + 1) / 2 > q) --i;
+            if ((i + 1) * (i + 2) / 2 <= q) ++i;
+            const int j = q - i * (i + 1) / 2;
+            const int cd = pv ? CD[sRl[i] * nl + sRl[j]] : 0;          // common chain depth of rows i and j
+            const float* yi = sY + (pv ? i : 0); const float* yj = sY + (pv ? j : 0);
             float acc = 0.f;
 #pragma unroll 1
             for (int k = 0; k < CL; k += 4) {   // entries past the common depth are masked (reads past the chain length stay inside the block)
                 const float a0 = yi[k * MR], a1 = yi[(k + 1) * MR], a2 = yi[(k + 2) * MR], a3 = yi[(k + 3) * MR];
-                const float b0 = yr[k * MR], b1 = yr[(k + 1) * MR], b2 = yr[(k + 2) * MR], b3 = yr[(k + 3) * MR];
+                const float b0 = yj[k * MR], b1 = yj[(k + 1) * MR], b2 = yj[(k + 2) * MR], b3 = yj[(k + 3) * MR];
                 if (k < cd) acc += a0 * b0;
                 if (k + 1 < cd) acc += a1 * b1;
                 if (k + 2 < cd) acc += a2 * b2;
                 if (k + 3 < cd) acc += a3 * b3;
             }
-            if (iv && lane <= i) { sA[i * W + lane] = acc; sA[lane * W + i] = acc; }
+            if (pv) { sA[i * W + j] = acc; sA[j * W + i] = acc; }
         }
         __syncwarp();
         SPROF(8);
