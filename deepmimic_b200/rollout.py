@@ -118,6 +118,22 @@ def build_policy(state_size, action_size, init_output_scale=0.01, noise=0.05, hi
     return GaussianMLPPolicy()
 
 
+def load_actor_weights(policy, actor):
+    """Copies a reference actor (deepmimic_b200.tf_checkpoint.load_actor, or the tests/golden fixture keys w0 b0 w1 b1 wm bm logstd) into a
+    GaussianMLPPolicy.  TF dense kernels are [in, out]; torch Linear weights are [out, in]."""
+    import torch
+    if "hidden" in actor:
+        hidden, mean, logstd = actor["hidden"], actor["mean"], actor["logstd"]
+    else:
+        hidden, mean, logstd = [(actor["w0"], actor["b0"]), (actor["w1"], actor["b1"])], (actor["wm"], actor["bm"]), actor["logstd"]
+    with torch.no_grad():
+        for layer, (w, b) in zip(policy.hidden, hidden):
+            layer.weight.copy_(torch.as_tensor(np.asarray(w, dtype=np.float32)).t()); layer.bias.copy_(torch.as_tensor(np.asarray(b, dtype=np.float32)))
+        policy.mean.weight.copy_(torch.as_tensor(np.asarray(mean[0], dtype=np.float32)).t()); policy.mean.bias.copy_(torch.as_tensor(np.asarray(mean[1], dtype=np.float32)))
+        policy.logstd.copy_(torch.as_tensor(np.asarray(logstd, dtype=np.float32)))
+    return policy
+
+
 class BatchedRollout:
     def __init__(self, env, policy=None, exp_rate=1.0, noise=0.05, seed=0):
         import torch

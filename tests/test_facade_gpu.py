@@ -113,3 +113,27 @@ def test_batched_rollout_collects_trajectories(asset_root):
     ro.s_norm.update()
     assert ro.s_norm.count == T * N
     assert abs(float(ro.s_norm.mean[0]) - 0.5) < 1e-6          # the phase slot (norm group NONE) keeps its fixed statistics
+
+
+
+def test_pretrained_reference_policy_tracks_the_clip_on_the_gpu(asset_root):
+    """Behavioural pin of the CUDA path against the real reference: its pretrained spin-kick policy (tests/golden fixture) runs 32 batched
+    environments started at evenly spaced clip phases for the 20 s test episode.  The oracle keeps all 32 of these on their feet with mean
+    reward 0.91 (and loses 1 of 64 randomly phased starts); the bar here: at most 2 falls, mean imitation reward > 0.85."""
+    import torch
+    from deepmimic_b200.env import DeepMimicBatchEnv
+    from deepmimic_b200.rollout import BatchedRollout, build_policy, load_actor_weights
+    f = np.load(os.path.join(REPO, "tests", "golden", "policy_humanoid3d_spinkick_fp16.npz"))
+    N, T = 32, 600
+    env = DeepMimicBatchEnv(ARGS, N, asset_root, seed=4)
+    env.set_mode(1)                      # test mode: 20 s episodes (time_end_lim_max)
+    env._core.reset(True, kin_time=np.linspace(0.0, 1.28, N, endpoint=False), max_time=np.full(N, 20.0), rot_theta=np.zeros(N))
+    ro = BatchedRollout(env, policy=load_actor_weights(build_policy(env.get_state_size(), env.get_action_size()), f), exp_rate=0.0)
+    ro.s_norm.set_mean_std(f["s_mean"], f["s_std"]); ro.a_norm.set_mean_std(f["a_mean"], f["a_std"])
+    tr = ro.collect(T - 1, record_stats=False)          # 599 policy steps = 19.97 s: the time limit is not reached, so any `done` is a fall
+    torch.cuda.synchronize()
+    falls = int(tr["dones"].sum())
+    mean_r = float(tr["rewards"].mean())
+    print("pretrained policy on the GPU: %d falls in %d episodes, mean reward %.3f" % (falls, N, mean_r))
+    assert falls <= 2, falls
+    assert mean_r > 0.85, mean_r

@@ -278,3 +278,60 @@ def test_amp_observation_known_answers(asset_root):
     # prev pose: joint rotations are heading independent -> equal to the "now" block before the update; root height too
     np.testing.assert_allclose(after[P + 7:P + 7 + 52], before[7:7 + 52], atol=1e-12)
     assert after[P] == pytest.approx(before[0], abs=1e-12)
+
+
+# ---- behavioural pin against the REAL reference: policies trained by the reference in Bullet 2.88 must work in this restatement
+def _run_policy_in_oracle(o, actor, t0, steps=600):
+    hidden = actor["hidden"]
+    rew = []
+    o.reset(t0, 0.0, 20.0)
+    for _ in range(steps):
+        if o.is_episode_end():
+            break
+        x = (o.record_state() - actor["s_norm_mean"]) / actor["s_norm_std"]
+        for w, b in hidden:
+            x = np.maximum(x @ w + b, 0.0)
+        o.set_action((x @ actor["mean"][0] + actor["mean"][1]) * actor["a_norm_std"] + actor["a_norm_mean"])   # mode of the Gaussian actor
+        for _ in range(20):
+            o.update(1.0 / 600.0)
+            if o.is_episode_end():
+                break
+        rew.append(o.calc_reward())
+    return len(rew), float(np.mean(rew)), o.has_fallen(), o.get_time()
+
+
+def _fixture_actor():
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", "policy_humanoid3d_spinkick_fp16.npz"))
+    g = lambda k: f[k].astype(np.float64)
+    return dict(hidden=[(g("w0"), g("b0")), (g("w1"), g("b1"))], mean=(g("wm"), g("bm")), s_norm_mean=g("s_mean"), s_norm_std=g("s_std"),
+                a_norm_mean=g("a_mean"), a_norm_std=g("a_std"))
+
+
+def test_pretrained_reference_policy_tracks_the_clip_in_the_oracle(asset_root):
+    """The reference's own pretrained spin-kick policy (tests/golden fixture made from R/data/policies/humanoid3d/humanoid3d_spinkick.ckpt)
+    drives the oracle for the whole 20 s test episode without falling and keeps the imitation reward high (0.90 measured).  The policy was
+    trained in the real Bullet simulation, so this is a statistical pin of the restated physics + reward + observation against the reference."""
+    o = Oracle(SPINKICK, asset_root)
+    o.L.dmo_set_mode(o.h, 1)
+    for t0 in (0.0, 0.5):
+        n, mean_r, fallen, t = _run_policy_in_oracle(o, _fixture_actor(), t0)
+        assert n == 600 and not fallen and t >= 20.0 - 1e-6, (t0, n, fallen, t)
+        assert mean_r > 0.85, (t0, mean_r)
+
+
+@pytest.mark.parametrize("clip,min_reward", [("walk", 0.8), ("backflip", 0.75), ("cartwheel", 0.8), ("jump", 0.85)])
+def test_more_pretrained_policies_from_the_reference_tree(clip, min_reward):
+    """Same check for other skills, reading the TF1 checkpoints directly (deepmimic_b200/tf_checkpoint.py); needs the reference checkout."""
+    ref = "/root/reference"
+    ckpt = os.path.join(ref, "data/policies/humanoid3d/humanoid3d_%s.ckpt" % clip)
+    if not os.path.exists(ckpt + ".index"):
+        pytest.skip("reference checkout with pretrained policies not available")
+    from deepmimic_b200.tf_checkpoint import load_actor
+    a = load_actor(ckpt)
+    a = {k: ([(w.astype(np.float64), b.astype(np.float64)) for w, b in v] if k == "hidden" else (tuple(x.astype(np.float64) for x in v) if k == "mean" else v.astype(np.float64)))
+         for k, v in a.items()}
+    o = Oracle(["--arg_file", "args/run_humanoid3d_%s_args.txt" % clip], ref)
+    o.L.dmo_set_mode(o.h, 1)
+    n, mean_r, fallen, t = _run_policy_in_oracle(o, a, 0.0)
+    assert n == 600 and not fallen, (clip, n, fallen)
+    assert mean_r > min_reward, (clip, mean_r)
