@@ -319,18 +319,19 @@ def test_pretrained_reference_policy_tracks_the_clip_in_the_oracle(asset_root):
         assert mean_r > 0.85, (t0, mean_r)
 
 
-@pytest.mark.parametrize("clip,min_reward", [("walk", 0.8), ("backflip", 0.75), ("cartwheel", 0.8), ("jump", 0.85)])
-def test_more_pretrained_policies_from_the_reference_tree(clip, min_reward):
+@pytest.mark.parametrize("char,clip,min_reward", [("humanoid3d", "walk", 0.8), ("humanoid3d", "backflip", 0.75), ("humanoid3d", "cartwheel", 0.8),
+                                                   ("humanoid3d", "jump", 0.85), ("dog3d", "trot", 0.85), ("dog3d", "pace", 0.8), ("dog3d", "canter", 0.8)])
+def test_more_pretrained_policies_from_the_reference_tree(char, clip, min_reward):
     """Same check for other skills, reading the TF1 checkpoints directly (deepmimic_b200/tf_checkpoint.py); needs the reference checkout."""
     ref = "/root/reference"
-    ckpt = os.path.join(ref, "data/policies/humanoid3d/humanoid3d_%s.ckpt" % clip)
+    ckpt = os.path.join(ref, "data/policies/%s/%s_%s.ckpt" % (char, char, clip))
     if not os.path.exists(ckpt + ".index"):
         pytest.skip("reference checkout with pretrained policies not available")
     from deepmimic_b200.tf_checkpoint import load_actor
     a = load_actor(ckpt)
     a = {k: ([(w.astype(np.float64), b.astype(np.float64)) for w, b in v] if k == "hidden" else (tuple(x.astype(np.float64) for x in v) if k == "mean" else v.astype(np.float64)))
          for k, v in a.items()}
-    o = Oracle(["--arg_file", "args/run_humanoid3d_%s_args.txt" % clip], ref)
+    o = Oracle(["--arg_file", "args/run_%s_%s_args.txt" % (char, clip)], ref)
     o.L.dmo_set_mode(o.h, 1)
     n, mean_r, fallen, t = _run_policy_in_oracle(o, a, 0.0)
     assert n == 600 and not fallen, (clip, n, fallen)
