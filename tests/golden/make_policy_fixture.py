@@ -1,5 +1,5 @@
-"""Generates tests/golden/policy_humanoid3d_spinkick_fp16.npz from the reference's pretrained TF1 checkpoint
-(R/data/policies/humanoid3d/humanoid3d_spinkick.ckpt) with deepmimic_b200/tf_checkpoint.py: the PPO actor (227-1024-512-28, stored as
+"""Generates tests/golden/policy_<char>_<clip>_fp16.npz (humanoid3d spinkick, dog3d trot) from the reference's pretrained TF1 checkpoints
+(R/data/policies/<char>/<char>_<clip>.ckpt) with deepmimic_b200/tf_checkpoint.py: the PPO actor (227-1024-512-28, stored as
 float16 to keep the fixture small) and the state / action normaliser statistics (float32).  Run here, where /root/reference exists:
     python tests/golden/make_policy_fixture.py"""
 import os
@@ -12,10 +12,11 @@ sys.path.insert(0, REPO)
 from deepmimic_b200.tf_checkpoint import load_actor  # noqa: E402
 
 ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
-a = load_actor(os.path.join(ref, "data/policies/humanoid3d/humanoid3d_spinkick.ckpt"))
-out = dict(w0=a["hidden"][0][0].astype(np.float16), b0=a["hidden"][0][1].astype(np.float16), w1=a["hidden"][1][0].astype(np.float16),
-           b1=a["hidden"][1][1].astype(np.float16), wm=a["mean"][0].astype(np.float16), bm=a["mean"][1].astype(np.float16), logstd=a["logstd"],
-           s_mean=a["s_norm_mean"], s_std=a["s_norm_std"], a_mean=a["a_norm_mean"], a_std=a["a_norm_std"])
-path = os.path.join(REPO, "tests", "golden", "policy_humanoid3d_spinkick_fp16.npz")
-np.savez_compressed(path, **out)
-print("wrote", path, os.path.getsize(path), "bytes")
+for char, clip in (("humanoid3d", "spinkick"), ("dog3d", "trot")):
+    a = load_actor(os.path.join(ref, "data/policies/%s/%s_%s.ckpt" % (char, char, clip)))
+    out = dict(w0=a["hidden"][0][0].astype(np.float16), b0=a["hidden"][0][1].astype(np.float16), w1=a["hidden"][1][0].astype(np.float16),
+               b1=a["hidden"][1][1].astype(np.float16), wm=a["mean"][0].astype(np.float16), bm=a["mean"][1].astype(np.float16), logstd=a["logstd"],
+               s_mean=a["s_norm_mean"], s_std=a["s_norm_std"], a_mean=a["a_norm_mean"], a_std=a["a_norm_std"])
+    path = os.path.join(REPO, "tests", "golden", "policy_%s_%s_fp16.npz" % (char, clip))
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")

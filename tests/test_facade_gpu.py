@@ -116,25 +116,27 @@ def test_batched_rollout_collects_trajectories(asset_root):
 
 
 
-def test_pretrained_reference_policy_tracks_the_clip_on_the_gpu(asset_root):
-    """Behavioural pin of the CUDA path against the real reference: its pretrained spin-kick policy (tests/golden fixture) runs 32 batched
-    environments started at evenly spaced clip phases for the 20 s test episode.  The oracle keeps all 32 of these on their feet with mean
-    reward 0.91 (and loses 1 of 64 randomly phased starts; trajectories are chaotic, so the CUDA path may lose a different few); the bar here:
-    at most 4 falls of 32, mean imitation reward > 0.8."""
+@pytest.mark.parametrize("char,clip,arg_file,period", [("humanoid3d", "spinkick", "args/run_humanoid3d_spinkick_args.txt", 1.28),
+                                                        ("dog3d", "trot", "args/run_dog3d_trot_args.txt", 0.51)])
+def test_pretrained_reference_policy_tracks_the_clip_on_the_gpu(asset_root, char, clip, arg_file, period):
+    """Behavioural pin of the CUDA path against the real reference: its pretrained policies (tests/golden fixtures, made from
+    R/data/policies/**.ckpt) run 32 batched environments started at evenly spaced clip phases for the 20 s test episode.  The oracle keeps
+    all 32 spin-kick starts on their feet with mean reward 0.91 (and loses 1 of 64 randomly phased starts; trajectories are chaotic, so
+    the CUDA path may lose a different few); the dog trots at 0.94.  The bar here: at most 4 falls of 32, mean imitation reward > 0.8."""
     import torch
     from deepmimic_b200.env import DeepMimicBatchEnv
     from deepmimic_b200.rollout import BatchedRollout, build_policy, load_actor_weights
-    f = np.load(os.path.join(REPO, "tests", "golden", "policy_humanoid3d_spinkick_fp16.npz"))
+    f = np.load(os.path.join(REPO, "tests", "golden", "policy_%s_%s_fp16.npz" % (char, clip)))
     N, T = 32, 600
-    env = DeepMimicBatchEnv(ARGS, N, asset_root, seed=4)
+    env = DeepMimicBatchEnv(["--arg_file", arg_file], N, asset_root, seed=4)
     env.set_mode(1)                      # test mode: 20 s episodes (time_end_lim_max)
-    env._core.reset(True, kin_time=np.linspace(0.0, 1.28, N, endpoint=False), max_time=np.full(N, 20.0), rot_theta=np.zeros(N))
+    env._core.reset(True, kin_time=np.linspace(0.0, period, N, endpoint=False), max_time=np.full(N, 20.0), rot_theta=np.zeros(N))
     ro = BatchedRollout(env, policy=load_actor_weights(build_policy(env.get_state_size(), env.get_action_size()), f), exp_rate=0.0)
     ro.s_norm.set_mean_std(f["s_mean"], f["s_std"]); ro.a_norm.set_mean_std(f["a_mean"], f["a_std"])
     tr = ro.collect(T - 1, record_stats=False)          # 599 policy steps = 19.97 s: the time limit is not reached, so any `done` is a fall
     torch.cuda.synchronize()
     falls = int(tr["dones"].sum())
     mean_r = float(tr["rewards"].mean())
-    print("pretrained policy on the GPU: %d falls in %d episodes, mean reward %.3f" % (falls, N, mean_r))
+    print("pretrained %s %s policy on the GPU: %d falls in %d episodes, mean reward %.3f" % (char, clip, falls, N, mean_r))
     assert falls <= 4, falls
     assert mean_r > 0.8, mean_r
