@@ -336,3 +336,23 @@ def test_more_pretrained_policies_from_the_reference_tree(char, clip, min_reward
     n, mean_r, fallen, t = _run_policy_in_oracle(o, a, 0.0)
     assert n == 600 and not fallen, (clip, n, fallen)
     assert mean_r > min_reward, (clip, mean_r)
+
+
+@pytest.mark.parametrize("arg_file,ckpt", [("args/run_amp_dog3d_trot_args.txt", "dog3d_amp/dog3d_amp_trot"), ("args/run_amp_humanoid3d_backflip_args.txt", "humanoid3d_amp/humanoid3d_amp_backflip"),
+                                           ("args/run_amp_humanoid3d_crawl_args.txt", "humanoid3d_amp/humanoid3d_amp_crawl")])
+def test_pretrained_amp_policies_stay_up_in_the_oracle(arg_file, ckpt):
+    """The reference's AMP policies (scene imitate_amp: no phase input, state 226 / 346) are not phase-locked to the clip, so the imitation
+    reward says little -- but they must keep the character going (back-flipping, crawling, trotting) for the whole 20 s without a fall."""
+    ref = "/root/reference"
+    path = os.path.join(ref, "data/policies", ckpt + ".ckpt")
+    if not os.path.exists(path + ".index"):
+        pytest.skip("reference checkout with pretrained policies not available")
+    from deepmimic_b200.tf_checkpoint import load_actor
+    a = load_actor(path)
+    a = {k: ([(w.astype(np.float64), b.astype(np.float64)) for w, b in v] if k == "hidden" else (tuple(x.astype(np.float64) for x in v) if k == "mean" else v.astype(np.float64)))
+         for k, v in a.items()}
+    o = Oracle(["--arg_file", arg_file], ref)
+    o.L.dmo_set_mode(o.h, 1)
+    assert o.state_size == a["s_norm_mean"].shape[0]
+    n, mean_r, fallen, t = _run_policy_in_oracle(o, a, 0.0)
+    assert n == 600 and not fallen and t >= 20.0 - 1e-6, (arg_file, n, fallen, t)
