@@ -306,6 +306,9 @@ static bool load_host_model(dm_handle& H, const char* asset_root, int argc, cons
         std::string root = asset_root ? asset_root : "", arg_file;
         if (ap.ParseString("arg_file", arg_file) && !ap.LoadFile(dmh::resolve_path(root, arg_file))) throw std::runtime_error("Failed to load args from: " + arg_file);
         H.sa = dmh::load_scene_assets(ap, root);
+        // scenes on the accelerated path: "imitate" and its AMP variant (same character, controller, clip and dynamics; AMP observations on top).
+        // The AMP task scenes (heading / target / dribble / strike) add goals, task rewards and clip datasets that are not built: refuse them loudly.
+        if (H.sa.cfg.scene != "imitate" && H.sa.cfg.scene != "imitate_amp") throw std::runtime_error("Unsupported scene: " + H.sa.cfg.scene + " (supported: imitate, imitate_amp)");
     } catch (const std::exception& e) { g_err = e.what(); return false; }
     if (!build_device_model(H)) return false;
     build_statics(H);
