@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <cstdio>
 #include <numeric>
 #include <cstring>
@@ -258,11 +260,18 @@ void build_statics(dm_handle& H) {
 template <int W, bool DEBUG>
 int launch_step(dm_handle* h, double dt, int n_updates) {
     auto kern = dmk::dm_step_kernel<W, DEBUG>;
-    static thread_local const void* configured = nullptr;
-    if (configured != reinterpret_cast<const void*>(kern)) {
-        DM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-        DM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = reinterpret_cast<const void*>(kern);
+    // opt in to the large dynamic shared-memory carve-out; the limit is raised whenever a handle needs more than any earlier one on
+    // this device (attributes are per device and per function: several handles of different sizes may live in one process)
+    static std::mutex mu;
+    static std::map<int, int> configured;   // device -> bytes configured for this instantiation
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        int& have = configured[h->device];
+        if (h->smem_bytes > have) {
+            DM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+            DM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            have = h->smem_bytes;
+        }
     }
     const int grid = h->padded_envs / h->tiles;
     kern<<<grid, h->tiles * W, h->smem_bytes, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, dt, n_updates, h->sa.cfg.num_sim_substeps, h->lay, h->sync_every_stage);
