@@ -17,7 +17,7 @@ class DmDims(C.Structure):
 
 DM_STATE_OFFSET, DM_STATE_SCALE, DM_ACTION_OFFSET, DM_ACTION_SCALE, DM_ACTION_BOUND_MIN, DM_ACTION_BOUND_MAX, DM_STATE_NORM_GROUPS = range(7)
 
-EXPORTS = ["dm_create", "dm_load_host", "dm_get_model_info", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_stream", "dm_sync", "dm_set_mode", "dm_reset", "dm_set_action",
+EXPORTS = ["dm_create", "dm_load_host", "dm_get_model_info", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_stream", "dm_sync", "dm_set_mode", "dm_set_sample_count", "dm_get_time_limits", "dm_reset", "dm_set_action",
            "dm_update", "dm_record_state", "dm_record_goal", "dm_calc_reward", "dm_record_amp_obs_agent", "dm_record_amp_obs_expert", "dm_amp_obs_host", "dm_observe", "dm_get_flags", "dm_step_host", "dm_get_snapshot",
            "dm_set_snapshot", "dm_get_counters", "dm_debug_enable", "dm_get_debug"]
 
@@ -43,6 +43,8 @@ def lib():
         L.dm_stream.argtypes = [vp]
         L.dm_sync.argtypes = [vp]
         L.dm_set_mode.argtypes = [vp, C.c_int]
+        L.dm_set_sample_count.argtypes = [vp, C.c_longlong]
+        L.dm_get_time_limits.argtypes = [vp, dp]
         L.dm_reset.argtypes = [vp, C.c_int, dp, dp, dp]
         L.dm_set_action.argtypes = [vp, fp]
         L.dm_update.argtypes = [vp, C.c_double, C.c_int]
@@ -136,6 +138,14 @@ class BatchedCore:
     def set_mode(self, mode):
         self._chk(lib().dm_set_mode(self.h, mode))
 
+    def set_sample_count(self, count):
+        self._chk(lib().dm_set_sample_count(self.h, int(count)))
+
+    def time_limits(self):
+        out = np.zeros(3, dtype=np.float64)
+        self._chk(lib().dm_get_time_limits(self.h, _dptr(out)))
+        return out
+
     def step_host(self, actions, dt, n_updates, state, reward, flags):  # numpy host arrays
         p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
         self._chk(lib().dm_step_host(self.h, p(actions), dt, n_updates, p(state), p(reward), p(flags)))
@@ -186,6 +196,15 @@ class HostModel:
         out = np.zeros(n, dtype=np.float64)
         if lib().dm_get_static(self.h, kind, _dptr(out)) != 0:
             raise RuntimeError(lib().dm_last_error().decode())
+        return out
+
+    def set_sample_count(self, count):
+        if lib().dm_set_sample_count(self.h, int(count)) != 0:
+            raise RuntimeError(lib().dm_last_error().decode())
+
+    def time_limits(self):
+        out = np.zeros(3, dtype=np.float64)
+        lib().dm_get_time_limits(self.h, _dptr(out))
         return out
 
     def info(self, name):

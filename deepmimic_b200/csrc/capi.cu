@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <map>
 #include <mutex>
+#include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <numeric>
 #include <cstring>
@@ -460,6 +462,30 @@ int dm_get_static(dm_handle* h, int kind, double* out) {
 void* dm_stream(dm_handle* h) { return h->stream; }
 int dm_sync(dm_handle* h) { DM_DEVICE(h); DM_CUDA(cudaStreamSynchronize(h->stream)); return 0; }
 int dm_set_mode(dm_handle* h, int mode) { h->mode = mode; return 0; }
+// cRLSceneSimChar::SetSampleCount -> UpdateTimerParams (RLSceneSimChar.cpp:223-227,330-347): the episode time limits move from
+// (time_lim_min, time_lim_max) to (time_end_lim_min, time_end_lim_max) with lerp = clamp(count / anneal_samples, 0, 1)^4.
+int dm_set_sample_count(dm_handle* h, long long count) {
+    const dmh::SceneConfig& c = h->sa.cfg;
+    if (c.anneal_samples <= 0) return 0;
+    double t = static_cast<double>(count) / static_cast<double>(c.anneal_samples);
+    t = std::min(std::max(t, 0.0), 1.0);
+    const double lerp = std::pow(t, 4.0);
+    auto mix = [lerp](double a, double b) { return (a == b) ? a : (1.0 - lerp) * a + lerp * b; };   // cMathUtil::Lerp; a == b keeps infinities finite-safe
+    h->hm.time_lim_min = mix(c.time_lim_min, c.time_end_lim_min);
+    h->hm.time_lim_max = mix(c.time_lim_max, c.time_end_lim_max);
+    if (h->stream != nullptr) {   // device handle: the reset kernel reads the limits from the model blob, stream-ordered
+        DM_CUDA(cudaSetDevice(h->device));
+        static_assert(offsetof(dmk::DevModel, time_lim_max) == offsetof(dmk::DevModel, time_lim_min) + sizeof(double), "time limits must be adjacent");
+        DM_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h->d_model) + offsetof(dmk::DevModel, time_lim_min), &h->hm.time_lim_min, 2 * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+        DM_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+int dm_get_time_limits(dm_handle* h, double* out) {
+    out[0] = h->hm.time_lim_min; out[1] = h->hm.time_lim_max; out[2] = h->hm.time_end_lim_max;
+    return 0;
+}
 
 int dm_reset(dm_handle* h, int force_all, const double* kt, const double* mt, const double* th) {
     DM_DEVICE(h);

@@ -132,7 +132,7 @@ public:
     virtual bool CheckValidEpisode() { Refresh(); for (int e = 0; e < mNumEnvs; ++e) if (!mFlags[4 * e + 3]) return false; return true; }
     virtual int CheckTerminate(int agent_id) { Refresh(); return mFlags[4 * Env(agent_id) + 2]; }
     virtual void SetMode(int mode) { if (mHandle) dm_set_mode(mHandle, mode); }
-    virtual void SetSampleCount(int) {}
+    virtual void SetSampleCount(int count) { if (mHandle) dm_set_sample_count(mHandle, count); }
     // extension: batch size of this facade
     int GetNumEnvs() const { return mNumEnvs; }
 

@@ -64,6 +64,13 @@ class DeepMimicBatchEnv:
     def set_mode(self, mode):
         self._core.set_mode(int(mode))
 
+    def set_sample_count(self, count):
+        """RLWorld feeds the learner's sample count back every iteration (R/learning/rl_agent.py -> env.set_sample_count):
+        anneals the episode time limits of the following resets."""
+        self._pre()
+        self._core.set_sample_count(int(count))
+        self._post()
+
     # ---- per-step queries; tensors are views of buffers rewritten by the next call
     def _refresh_flags(self):
         self._pre()

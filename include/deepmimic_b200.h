@@ -15,6 +15,7 @@
  *                                                             DeepMimicCore.h:55,83-85
  *   dm_get_static      GetStateSize .. BuildActionBoundMax, BuildStateNormGroups   DeepMimicCore.h:62-75
  *   dm_set_mode        SetMode                                DeepMimicCore.h:87
+ *   dm_set_sample_count SetSampleCount                        DeepMimicCore.h:88,                     DeepMimicCore.cpp:626-633
  *
  * Plain C: opaque handle, pointers and sizes only, int status (0 = ok) with dm_last_error().  Pointers
  * named d_* are DEVICE pointers (fp32 unless stated), h_* are host pointers.  One host thread per
@@ -72,6 +73,11 @@ int dm_get_static(dm_handle* h, int kind, double* h_out);   /* h_out: state_size
 void* dm_stream(dm_handle* h);                               /* cudaStream_t */
 int dm_sync(dm_handle* h);
 int dm_set_mode(dm_handle* h, int mode);                     /* 0 train, 1 test (cRLScene::eMode) */
+/* Training-sample count of the learner: anneals the episode time limits used by the next resets from (--time_lim_min/max) to
+ * (--time_end_lim_min/max) with clamp(count / --anneal_samples, 0, 1)^4 (cRLSceneSimChar::UpdateTimerParams, RLSceneSimChar.cpp:330-347).
+ * No-op without --anneal_samples.  Host logic: also valid on dm_load_host handles. */
+int dm_set_sample_count(dm_handle* h, long long count);
+int dm_get_time_limits(dm_handle* h, double* h_out3);        /* current train-mode min, max and the test-mode limit (seconds) */
 
 /* Resets the envs whose done flag is set (force_all = 0) or every env (force_all != 0).  Optional host arrays
  * (num_envs doubles each, may be NULL) inject the random draws of the reference's reset: mocap start time,

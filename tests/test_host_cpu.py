@@ -81,6 +81,24 @@ def test_loader_errors_are_reported(asset_root):
     assert L.dm_last_error()
 
 
+def test_sample_count_anneals_episode_time_limits(asset_root):
+    """cRLSceneSimChar::UpdateTimerParams (RLSceneSimChar.cpp:330-347): Blend(params, params_end, clamp(count / anneal, 0, 1)^4)."""
+    m = capi.HostModel(["--arg_file", ARG_FILES[0]], asset_root)     # time_lim 0.5 -> 20 over --anneal_samples 32000000
+    np.testing.assert_allclose(m.time_limits(), [0.5, 0.5, 20.0])
+    for count, t in [(0, 0.0), (8000000, 0.25), (16000000, 0.5), (32000000, 1.0), (10 ** 9, 1.0), (-5, 0.0)]:
+        m.set_sample_count(count)
+        want = 0.5 + (20.0 - 0.5) * t ** 4
+        np.testing.assert_allclose(m.time_limits(), [want, want, 20.0], rtol=1e-14)
+    # different min / max; and no --anneal_samples: the count is ignored
+    m = capi.HostModel(["--time_lim_min", "1", "--time_lim_max", "3", "--time_end_lim_min", "5", "--time_end_lim_max", "11", "--anneal_samples", "100",
+                        "--arg_file", ARG_FILES[0]], asset_root)
+    m.set_sample_count(50)
+    np.testing.assert_allclose(m.time_limits(), [1 + 4 / 16.0, 3 + 8 / 16.0, 11.0], rtol=1e-14)
+    m = capi.HostModel(["--anneal_samples", "-1", "--arg_file", ARG_FILES[0]], asset_root)
+    m.set_sample_count(10 ** 8)
+    np.testing.assert_allclose(m.time_limits(), [0.5, 0.5, 20.0])
+
+
 def test_compute_entry_points_fail_loudly_without_device(asset_root):
     """No CPU fallback: a host-only handle refuses every compute call; dm_create refuses when no CUDA device exists."""
     L = capi.lib()

@@ -1,0 +1,32 @@
+"""GPU test of SetSampleCount (cRLSceneSimChar::UpdateTimerParams, RLSceneSimChar.cpp:330-347): the episode time limit drawn by the
+reset kernel follows the annealed limits.  (Written at the end of round 1 after the GPU budget was spent: first run is the driver's.)"""
+import numpy as np
+import pytest
+
+from deepmimic_b200 import capi
+
+pytestmark = pytest.mark.gpu
+ARGS = ["--arg_file", "args/train_humanoid3d_spinkick_args.txt"]     # time_lim 0.5 -> 20 over 32e6 samples
+
+
+def _timer_max(core, env):
+    nj = core.dims.num_joints
+    return core.get_snapshot(env)[13 + 55 * nj + 13]                 # snapshot layout: include/deepmimic_b200.h (dm_snapshot_size)
+
+
+def test_reset_uses_the_annealed_time_limit(asset_root):
+    core = capi.BatchedCore(ARGS, 64, asset_root, seed=5)
+    core.reset(force_all=True)
+    assert _timer_max(core, 0) == 0.5 and _timer_max(core, 63) == 0.5
+    core.set_sample_count(16000000)
+    core.reset(force_all=True)
+    want = 0.5 + 19.5 * 0.5 ** 4
+    np.testing.assert_allclose([_timer_max(core, e) for e in (0, 31, 63)], want, rtol=1e-14)
+    core.set_sample_count(10 ** 9)
+    core.reset(force_all=True)
+    assert _timer_max(core, 7) == 20.0
+    core.set_mode(1)                                                  # test mode: always the end limit (RLSceneSimChar.cpp:277-284)
+    core.set_sample_count(0)
+    core.reset(force_all=True)
+    assert _timer_max(core, 7) == 20.0
+    core.close()
