@@ -55,6 +55,7 @@ struct DevModel {
     int pose_dim, state_size, action_size, amp_obs_size, amp_local_root;
     int phase_input, rec_world_root_pos, rec_world_root_rot;
     int num_frames, loop_motion;
+    int end_at_clip_end;                  // cSceneImitate::CheckTerminate only (SceneImitate.cpp:193-205): a finished non-looping clip fails the episode
     int enable_fall_end, enable_contact_fall, sync_root_pos, sync_root_rot, rand_rot_reset;
     float scale, gravity[3], friction;
     float total_mass;

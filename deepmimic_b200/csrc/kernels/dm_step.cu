@@ -1213,7 +1213,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                     cb = (c0 != c1) ? 1 : 0;
                 }
                 if (timer >= tm[kTTimerMax]) cb |= 2;
-                if (!M.loop_motion && kin_time >= dur) cb |= 4;
+                if (M.end_at_clip_end && kin_time >= dur) cb |= 4;
             }
             cbits = T::shfli(cb, 0);
             need_action = 0;

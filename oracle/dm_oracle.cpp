@@ -731,7 +731,8 @@ struct Oracle {
     // cRLSceneSimChar::CheckTerminate + cSceneImitate::CheckTerminate (RLSceneSimChar.cpp:187-197; SceneImitate.cpp:193-205)
     int CheckTerminate() const {
         bool fail = sa.cfg.enable_fall_end && HasFallen();
-        if (!fail && !sa.motion.loop && kin_time >= sa.motion.duration()) fail = true;
+        // the AMP scenes use cRLSceneSimChar::CheckTerminate alone (SceneImitateAMP.cpp:185-189): no motion-over failure there
+        if (!fail && sa.cfg.scene == "imitate" && !sa.motion.loop && kin_time >= sa.motion.duration()) fail = true;
         return fail ? 1 : 0;
     }
     bool IsEpisodeEnd() const { return timer_time >= timer_max || CheckTerminate() != 0; }  // RLScene.cpp:36-50

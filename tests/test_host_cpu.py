@@ -76,6 +76,8 @@ def test_loader_errors_are_reported(asset_root):
         capi.HostModel(["--scene", "imitate", "--character_files", "data/characters/nope.txt"], asset_root)
     with pytest.raises(RuntimeError, match="Unsupported scene"):
         capi.HostModel(["--scene", "heading_amp", "--arg_file", ARG_FILES[0]], asset_root)     # first key wins: the scene is overridden
+    with pytest.raises(RuntimeError, match="Unsupported timer type"):
+        capi.HostModel(["--timer_type", "exp", "--arg_file", ARG_FILES[0]], asset_root)
     m = capi.HostModel(["--scene", "imitate_amp", "--arg_file", ARG_FILES[0]], asset_root)       # the AMP variant of the imitate scene loads
     assert m.dims.amp_obs_size == 226
     assert L.dm_last_error()

@@ -231,6 +231,36 @@ def test_free_fall_com_acceleration_is_g(asset_root):
     assert np.abs(out[3:6] - np.array([0, -9.8 * 4, 0])).max() < 2e-3 and np.abs(out[:3]).max() < 2e-3 and np.abs(out[6:]).max() < 5e-3
 
 
+def make_short_nonlooping_clip(asset_root, tmp_path, frames=6):
+    """The first `frames` frames of the walk clip with "Loop": "none" (the shipped test assets only hold looping clips)."""
+    import json
+    src = json.load(open(os.path.join(asset_root, "data/motions/humanoid3d_walk.txt")))
+    clip = {"Loop": "none", "Frames": src["Frames"][:frames]}
+    path = os.path.join(str(tmp_path), "short_nonlooping.txt")
+    json.dump(clip, open(path, "w"))
+    return path, sum(f[0] for f in clip["Frames"][:-1])
+
+
+def test_finished_clip_fails_the_episode_in_imitate_only(asset_root, tmp_path):
+    """cSceneImitate::CheckTerminate adds cMotion::IsOver (SceneImitate.cpp:193-205, Motion.cpp:529-532); the AMP scenes use
+    cRLSceneSimChar::CheckTerminate alone (SceneImitateAMP.cpp:185-189)."""
+    clip, dur = make_short_nonlooping_clip(asset_root, tmp_path)
+    res = {}
+    for scene in ("imitate", "imitate_amp"):
+        o = Oracle(["--scene", scene, "--motion_file", clip, "--arg_file", "args/train_humanoid3d_walk_args.txt"], asset_root)
+        o.reset(0.0, 0.0, 20.0)
+        n = int(np.ceil(dur * 600.0)) + 2
+        hist = []
+        for i in range(n):
+            o.update(1.0 / 600.0)
+            hist.append((o.check_terminate(), o.is_episode_end(), o.has_fallen()))
+        res[scene] = hist
+        assert not any(h[2] for h in hist)                      # nobody falls in 0.2 s
+    k = int(np.floor(dur * 600.0)) - 2
+    assert all(h[0] == 0 for h in res["imitate"][:k]) and res["imitate"][-1][0] == 1 and res["imitate"][-1][1]
+    assert all(h[0] == 0 and not h[1] for h in res["imitate_amp"])
+
+
 def test_amp_observation_known_answers(asset_root):
     """cSceneImitateAMP::BuildAMPObs (SceneImitateAMP.cpp:279-397): layout [pose now | pose prev | vel now | vel prev]; humanoid
     (1 + 6 + 8*6 + 4 + 4*3) = 71 and (6 + 36) = 42 -> 226."""

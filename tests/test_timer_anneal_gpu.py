@@ -30,3 +30,22 @@ def test_reset_uses_the_annealed_time_limit(asset_root):
     core.reset(force_all=True)
     assert _timer_max(core, 7) == 20.0
     core.close()
+
+
+def test_finished_clip_fails_the_episode_in_imitate_only(asset_root, tmp_path):
+    """cSceneImitate::CheckTerminate vs cSceneImitateAMP::CheckTerminate (SceneImitate.cpp:193-205, SceneImitateAMP.cpp:185-189)."""
+    import torch
+    from tests.test_oracle_kat import make_short_nonlooping_clip
+    clip, dur = make_short_nonlooping_clip(asset_root, tmp_path)
+    n = int(np.ceil(dur * 600.0)) + 2
+    for scene, want in (("imitate", 1), ("imitate_amp", 0)):
+        core = capi.BatchedCore(["--scene", scene, "--motion_file", clip, "--arg_file", "args/train_humanoid3d_walk_args.txt"], 32, asset_root, seed=1)
+        core.reset(force_all=True, kin_time=np.zeros(32), max_time=np.full(32, 20.0), rot_theta=np.zeros(32))
+        flags = torch.zeros(32, 4, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()                                      # the library works on its own stream
+        core.update(1.0 / 600.0, n)
+        core.flags(flags)
+        core.sync()
+        f = flags.cpu().numpy()
+        assert (f[:, 2] == want).all() and (f[:, 1] == want).all(), (scene, f[:4])
+        core.close()
