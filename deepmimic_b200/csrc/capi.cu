@@ -324,6 +324,7 @@ static bool load_host_model(dm_handle& H, const char* asset_root, int argc, cons
         // scenes on the accelerated path: "imitate" and its AMP variant (same character, controller, clip and dynamics; AMP observations on top).
         // The AMP task scenes (heading / target / dribble / strike) add goals, task rewards and clip datasets that are not built: refuse them loudly.
         if (H.sa.cfg.scene != "imitate" && H.sa.cfg.scene != "imitate_amp") throw std::runtime_error("Unsupported scene: " + H.sa.cfg.scene + " (supported: imitate, imitate_amp)");
+        if (H.sa.cfg.kin_ctrl == "clips") throw std::runtime_error("Unsupported kinematic controller: clips (clip datasets are not on the accelerated path; supported: motion)");
     } catch (const std::exception& e) { g_err = e.what(); return false; }
     if (!build_device_model(H)) return false;
     build_statics(H);

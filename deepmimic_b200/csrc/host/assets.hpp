@@ -106,6 +106,15 @@ struct SceneConfig {
     double time_end_lim_min = std::numeric_limits<double>::infinity();
     double time_end_lim_max = std::numeric_limits<double>::infinity();
     int anneal_samples = -1;
+    // AMP task scenes (cSceneTargetAMP::ParseArgs SceneTargetAMP.cpp:107-120, cSceneHeadingAMP::ParseArgs SceneHeadingAMP.cpp:71-88);
+    // defaults are the constructors' (SceneTargetAMP.cpp:89-101, SceneHeadingAMP.cpp:50-65)
+    double rand_target_time_min = 1, rand_target_time_max = 5;
+    double max_target_dist = 3, target_succ_dist = 0.5, tar_fail_dist = std::numeric_limits<double>::infinity();
+    double tar_speed = 1, pos_reward_scale = 1;
+    bool enable_min_tar_vel = false;
+    double max_heading_turn_rate = 0.15, sharp_turn_prob = 0.025, speed_change_prob = 0.1;
+    double tar_speed_min = 1, tar_speed_max = 1, vel_reward_scale = 1;
+    bool is_task_scene() const { return scene == "target_amp" || scene == "heading_amp"; }
 };
 
 inline int joint_param_size(int type, bool is_root) {
@@ -301,6 +310,23 @@ inline SceneConfig parse_scene_config(const ArgParser& ap) {
     ap.ParseDouble("time_end_lim_min", sc.time_end_lim_min);
     ap.ParseDouble("time_end_lim_max", sc.time_end_lim_max);
     ap.ParseInt("anneal_samples", sc.anneal_samples);
+    if (sc.scene == "heading_amp") { sc.rand_target_time_min = 0.2; sc.rand_target_time_max = 0.5; }
+    ap.ParseDouble("rand_target_time_min", sc.rand_target_time_min);
+    ap.ParseDouble("rand_target_time_max", sc.rand_target_time_max);
+    ap.ParseDouble("max_target_dist", sc.max_target_dist);
+    ap.ParseDouble("target_succ_dist", sc.target_succ_dist);
+    ap.ParseDouble("tar_fail_dist", sc.tar_fail_dist);
+    ap.ParseDouble("tar_speed", sc.tar_speed);
+    ap.ParseBool("enable_min_tar_vel", sc.enable_min_tar_vel);
+    ap.ParseDouble("pos_reward_scale", sc.pos_reward_scale);
+    ap.ParseDouble("max_heading_turn_rate", sc.max_heading_turn_rate);
+    ap.ParseDouble("sharp_turn_prob", sc.sharp_turn_prob);
+    ap.ParseDouble("speed_change_prob", sc.speed_change_prob);
+    sc.tar_speed_min = sc.tar_speed_max = sc.tar_speed;
+    ap.ParseDouble("tar_speed_min", sc.tar_speed_min);
+    ap.ParseDouble("tar_speed_max", sc.tar_speed_max);
+    if (sc.scene == "heading_amp") sc.tar_speed = std::min(std::max(sc.tar_speed, sc.tar_speed_min), sc.tar_speed_max);   // SceneHeadingAMP.cpp:85
+    ap.ParseDouble("vel_reward_scale", sc.vel_reward_scale);
     return sc;
 }
 
@@ -309,8 +335,36 @@ struct SceneAssets {
     SceneConfig cfg;
     CharModel character;
     CtrlParams ctrl;
-    MotionClip motion;
+    MotionClip motion;                 // the clip of --kin_ctrl motion; clips[0] with --kin_ctrl clips
+    // --kin_ctrl clips: the dataset of cClipsController (anim/ClipsController.cpp:114-214): clips, their weights and the sampling CDF
+    std::vector<MotionClip> clips;
+    std::vector<double> clip_weights, clip_cdf;
+    std::vector<std::string> clip_files;
+    // cClipsController::SelectNewMotion (ClipsController.cpp:226-236): upper_bound of a uniform draw in the CDF
+    int select_clip(double u01) const {
+        auto it = std::upper_bound(clip_cdf.begin(), clip_cdf.end(), u01);
+        return std::min(static_cast<int>(it - clip_cdf.begin()), static_cast<int>(clip_cdf.size()) - 1);
+    }
 };
+
+// cClipsController::LoadParams / LoadMotions / BuildClipsCDF (anim/ClipsController.cpp:114-214)
+inline void load_clip_dataset(const std::string& path, const std::string& asset_root, SceneAssets& sa) {
+    Json root = Json::parseFile(path);
+    const Json& motions = root["Motions"];
+    if (!motions.isArray() || motions.size() == 0) throw std::runtime_error("Failed to load clips controller parameters from file " + path);
+    double sum = 0;
+    for (size_t i = 0; i < motions.size(); ++i) {
+        const Json& e = motions[i];
+        const std::string file = e["File"].asString();
+        sa.clip_files.push_back(file);
+        sa.clips.push_back(load_motion(resolve_path(asset_root, file), sa.character));
+        const double w = e.get("Weight", 1.0);
+        sa.clip_weights.push_back(w);
+        sum += w;
+        sa.clip_cdf.push_back(sum);
+    }
+    for (auto& c : sa.clip_cdf) c /= sum;
+}
 
 inline SceneAssets load_scene_assets(const ArgParser& ap, const std::string& asset_root) {
     SceneAssets sa;
@@ -325,7 +379,13 @@ inline SceneAssets load_scene_assets(const ArgParser& ap, const std::string& ass
     if (sa.cfg.ctrl_file.empty()) throw std::runtime_error("no --char_ctrl_files given");
     sa.ctrl = load_controller(resolve_path(asset_root, sa.cfg.ctrl_file), sa.character);
     if (sa.cfg.motion_file.empty()) throw std::runtime_error("no --motion_file given");
-    sa.motion = load_motion(resolve_path(asset_root, sa.cfg.motion_file), sa.character);
+    if (sa.cfg.kin_ctrl == "clips") {   // cKinCtrlBuilder::BuildClipsController (anim/KinCtrlBuilder.cpp:66-73)
+        load_clip_dataset(resolve_path(asset_root, sa.cfg.motion_file), asset_root, sa);
+        sa.motion = sa.clips[0];
+    } else {
+        sa.motion = load_motion(resolve_path(asset_root, sa.cfg.motion_file), sa.character);
+        sa.clips.push_back(sa.motion); sa.clip_weights.push_back(1.0); sa.clip_cdf.push_back(1.0); sa.clip_files.push_back(sa.cfg.motion_file);
+    }
     return sa;
 }
 

@@ -118,6 +118,50 @@ def build_policy(state_size, action_size, init_output_scale=0.01, noise=0.05, hi
     return GaussianMLPPolicy()
 
 
+def build_gated_policy(state_size, goal_size, action_size, init_output_scale=0.01, noise=0.05, hidden=(1024, 512), gate_common=128, gate_hidden=64):
+    """The goal-conditioned actor of the reference's AMP task agents, `fc_2layers_gated_1024units`
+    (R/learning/nets/fc_2layers_gated_1024units.py:6-58): the trunk sees [norm_s, norm_g]; every hidden layer's pre-activation is scaled by
+    2*sigmoid(.) and shifted by a bias, both computed from the normalised goal through gate_common (128, relu) and a 64-unit relu layer."""
+    import torch
+
+    class GatedGaussianMLPPolicy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            dims = [state_size + goal_size] + list(hidden)
+            lin = torch.nn.Linear
+            self.goal_size = goal_size
+            self.hidden = torch.nn.ModuleList([lin(a, b) for a, b in zip(dims[:-1], dims[1:])])
+            self.gate_common = lin(goal_size, gate_common)
+            self.gate_hidden = torch.nn.ModuleList([lin(gate_common, gate_hidden) for _ in hidden])
+            self.gate_bias = torch.nn.ModuleList([lin(gate_hidden, h) for h in hidden])
+            self.gate_scale = torch.nn.ModuleList([lin(gate_hidden, h) for h in hidden])
+            for l in list(self.hidden) + [self.gate_common] + list(self.gate_hidden) + list(self.gate_bias) + list(self.gate_scale):
+                torch.nn.init.xavier_uniform_(l.weight); torch.nn.init.zeros_(l.bias)
+            self.mean = lin(dims[-1], action_size)
+            torch.nn.init.uniform_(self.mean.weight, -init_output_scale, init_output_scale); torch.nn.init.zeros_(self.mean.bias)
+            self.logstd = torch.nn.Parameter(torch.full((action_size,), math.log(noise)))
+
+        def forward(self, norm_s, norm_g):
+            gc = torch.relu(self.gate_common(norm_g))
+            h = torch.cat([norm_s, norm_g], dim=-1)
+            for l, gh, gb, gs in zip(self.hidden, self.gate_hidden, self.gate_bias, self.gate_scale):
+                gate = torch.relu(gh(gc))
+                h = torch.relu(2.0 * torch.sigmoid(gs(gate)) * l(h) + gb(gate))
+            return self.mean(h)
+
+        def sample(self, norm_s, norm_g, explore_mask=None, generator=None):
+            mu = self.forward(norm_s, norm_g)
+            std = self.logstd.exp()
+            eps = torch.randn(mu.shape, device=mu.device, generator=generator)
+            if explore_mask is not None:
+                eps = eps * explore_mask[:, None].to(eps.dtype)
+            a = mu + std * eps
+            logp = (-0.5 * eps * eps - self.logstd - 0.5 * math.log(2 * math.pi)).sum(dim=-1)
+            return a, logp
+
+    return GatedGaussianMLPPolicy()
+
+
 def load_actor_weights(policy, actor):
     """Copies a reference actor (deepmimic_b200.tf_checkpoint.load_actor, or the tests/golden fixture keys w0 b0 w1 b1 wm bm logstd) into a
     GaussianMLPPolicy.  TF dense kernels are [in, out]; torch Linear weights are [out, in]."""
@@ -131,6 +175,11 @@ def load_actor_weights(policy, actor):
             layer.weight.copy_(torch.as_tensor(np.asarray(w, dtype=np.float32)).t()); layer.bias.copy_(torch.as_tensor(np.asarray(b, dtype=np.float32)))
         policy.mean.weight.copy_(torch.as_tensor(np.asarray(mean[0], dtype=np.float32)).t()); policy.mean.bias.copy_(torch.as_tensor(np.asarray(mean[1], dtype=np.float32)))
         policy.logstd.copy_(torch.as_tensor(np.asarray(logstd, dtype=np.float32)))
+        if "gate_common" in actor:
+            put = lambda layer, wb: (layer.weight.copy_(torch.as_tensor(np.asarray(wb[0], dtype=np.float32)).t()), layer.bias.copy_(torch.as_tensor(np.asarray(wb[1], dtype=np.float32))))
+            put(policy.gate_common, actor["gate_common"])
+            for i, g in enumerate(actor["gates"]):
+                put(policy.gate_hidden[i], g["hidden"]); put(policy.gate_bias[i], g["bias"]); put(policy.gate_scale[i], g["scale"])
     return policy
 
 

@@ -124,6 +124,12 @@ def load_actor(prefix):
     while a + "%d/dense/kernel" % k in t:
         hidden.append((t[a + "%d/dense/kernel" % k], t[a + "%d/dense/bias" % k])); k += 1
     out = dict(hidden=hidden, mean=(t[a + "dist_gauss_diag/mean/kernel"], t[a + "dist_gauss_diag/mean/bias"]), logstd=t[a + "dist_gauss_diag/logstd/bias"])
+    if a + "gate_common/0/dense/kernel" in t:
+        # fc_2layers_gated_1024units (R/learning/nets/fc_2layers_gated_1024units.py): goal -> gate_common (128) -> per hidden layer a 64-unit
+        # gate layer feeding a bias head (dense) and a scale head (dense_1)
+        g = lambda name: (t[a + name + "/kernel"], t[a + name + "/bias"])
+        out["gate_common"] = g("gate_common/0/dense")
+        out["gates"] = [dict(hidden=g("gate%d/0/dense" % i), bias=g("gate%d/dense" % i), scale=g("gate%d/dense_1" % i)) for i in range(len(hidden))]
     for nm in ("s_norm", "g_norm", "a_norm"):
         for st in ("mean", "std"):
             key = "agent/resource/%s/%s" % (nm, st)

@@ -8,6 +8,7 @@
 //   cSimCharacter / cSimBodyJoint / cSimBodyLink       R/DeepMimicCore/sim/*.cpp
 //   cCtPDController / cImpPDController                 R/DeepMimicCore/sim/*.cpp
 //   cKinCharacter / cMotion / cMotionController        R/DeepMimicCore/anim/*.cpp
+//   cClipsController (clip datasets), cSceneImitateAMP, cSceneTargetAMP, cSceneHeadingAMP (goal, task reward, target updates)
 // DeepMimic's own math runs in double (rbd.hpp, omath.hpp); the Bullet 2.88 stage runs in float
 // (bullet_mb.hpp).  PARITY UNPINNED: the reference ships no tests or golden vectors and Bullet is
 // an un-vendored dependency, so this oracle is pinned only by the known-answer tests of
@@ -46,8 +47,12 @@ struct Oracle {
     VecD action;
     std::vector<int> ctrl_off, ctrl_size;
     int action_size = 0;
-    // ---- cKinCharacter + cMotionController
-    std::vector<double> frame_vel;
+    // ---- cKinCharacter + cMotionController / cClipsController (the active clip of the dataset; one clip with --kin_ctrl motion)
+    int cur_clip = 0;
+    std::vector<std::vector<double>> clip_frame_vel;
+    std::vector<D3> clip_cycle_delta;
+    const dmh::MotionClip& Mot() const { return sa.clips[cur_clip]; }
+    const std::vector<double>& FrameVel() const { return clip_frame_vel[cur_clip]; }
     double kin_time = 0;
     D3 origin; DQ origin_rot;
     VecD kin_pose, kin_vel;
@@ -57,11 +62,28 @@ struct Oracle {
     VecD prev_pose, prev_vel;   // cSceneImitateAMP::mPrevPose / mPrevVel: sim pose / vel at the last applied action
     int mode = 0;  // 0 train, 1 test
     VecD joint_weights;
+    // ---- AMP task scenes: cSceneTargetAMP / cSceneHeadingAMP (scenes/SceneTargetAMP.cpp, SceneHeadingAMP.cpp)
+    enum SceneKind { kImitate = 0, kImitateAMP = 1, kTargetAMP = 2, kHeadingAMP = 3 };
+    int scene_kind = kImitate;
+    bool IsTask() const { return scene_kind == kTargetAMP || scene_kind == kHeadingAMP; }
+    double tgt_timer_time = 0, tgt_timer_max = 0;   // mTargetTimer
+    D3 target_pos;                                   // mTargetPos
+    double target_speed = 1, target_heading = 0;     // mTargetSpeed, mTargetHeading
+    D3 prev_action_com;                              // cDeepMimicCharController::mPrevActionCOM
+    // The in-episode random draws of the task scenes come from a stateless counter-based stream shared with the CUDA path
+    // (same splitmix64 finaliser as dm_policy.cu's u01): draw k of environment `task_env` is U01(task_seed, task_env, k).
+    // The reference's std::mt19937 streams cannot be reproduced, so parity is defined on this stream.
+    uint64_t task_seed = 0, task_env = 0, task_counter = 0;
 
     // =================================================================== construction
     void Init(const dmh::SceneAssets& assets) {
         sa = assets; cm = &sa.character; nj = cm->num_joints(); ndof = cm->pose_dim; scale = sa.cfg.world_scale;
-        if (sa.cfg.scene != "imitate") std::printf("[oracle] scene '%s': only the imitate hot path is restated\n", sa.cfg.scene.c_str());
+        if (sa.cfg.scene == "imitate") scene_kind = kImitate;
+        else if (sa.cfg.scene == "imitate_amp") scene_kind = kImitateAMP;
+        else if (sa.cfg.scene == "target_amp") scene_kind = kTargetAMP;
+        else if (sa.cfg.scene == "heading_amp") scene_kind = kHeadingAMP;
+        else throw std::runtime_error("oracle: scene '" + sa.cfg.scene + "' is not restated (imitate, imitate_amp, target_amp, heading_amp)");
+        target_speed = sa.cfg.tar_speed;
         BuildKinMotion();
         BuildSimCharacter();
         BuildController();
@@ -71,28 +93,38 @@ struct Oracle {
         for (int j = 0; j < nj; ++j) { joint_weights[j] = cm->joints[j].diff_weight; sum += std::fabs(joint_weights[j]); }
         for (auto& w : joint_weights) w /= sum;
         timer_max = sa.cfg.time_lim_max;
+        prev_pose = pose0; prev_vel = vel0;
         Reset(0.0, 0.0, timer_max);
     }
 
-    // cMotion::BuildFrameVel with cKinCharacter::CalcFrameVel (Motion.cpp:170-191, KinCharacter.cpp:433-437)
+    // cMotion::BuildFrameVel with cKinCharacter::CalcFrameVel (Motion.cpp:170-191, KinCharacter.cpp:433-437), for every clip of the dataset
     void BuildKinMotion() {
-        const auto& mc = sa.motion;
-        frame_vel.assign(static_cast<size_t>(mc.num_frames) * ndof, 0.0);
-        VecD f0(ndof), f1(ndof), v;
-        for (int f = 0; f < mc.num_frames - 1; ++f) {
-            double dt = mc.frame_times[f + 1] - mc.frame_times[f];
-            std::copy(mc.frame(f), mc.frame(f) + ndof, f0.begin());
-            std::copy(mc.frame(f + 1), mc.frame(f + 1) + ndof, f1.begin());
-            CalcVel(*cm, f0, f1, dt, v);
-            std::copy(v.begin(), v.end(), frame_vel.begin() + static_cast<size_t>(f) * ndof);
+        clip_frame_vel.assign(sa.clips.size(), {});
+        clip_cycle_delta.assign(sa.clips.size(), D3());
+        for (size_t c = 0; c < sa.clips.size(); ++c) {
+            const auto& mc = sa.clips[c];
+            std::vector<double>& frame_vel = clip_frame_vel[c];
+            frame_vel.assign(static_cast<size_t>(mc.num_frames) * ndof, 0.0);
+            VecD f0(ndof), f1(ndof), v;
+            for (int f = 0; f < mc.num_frames - 1; ++f) {
+                double dt = mc.frame_times[f + 1] - mc.frame_times[f];
+                std::copy(mc.frame(f), mc.frame(f) + ndof, f0.begin());
+                std::copy(mc.frame(f + 1), mc.frame(f + 1) + ndof, f1.begin());
+                CalcVel(*cm, f0, f1, dt, v);
+                std::copy(v.begin(), v.end(), frame_vel.begin() + static_cast<size_t>(f) * ndof);
+            }
+            if (mc.num_frames > 1) std::copy(frame_vel.begin() + static_cast<size_t>(mc.num_frames - 2) * ndof, frame_vel.begin() + static_cast<size_t>(mc.num_frames - 1) * ndof,
+                                             frame_vel.begin() + static_cast<size_t>(mc.num_frames - 1) * ndof);
+            // cKinController::CalcCycleRootDelta (KinController.cpp:149-161)
+            const double* fb = mc.frame(0); const double* fe = mc.frame(mc.num_frames - 1);
+            clip_cycle_delta[c] = D3(fe[0] - fb[0], 0, fe[2] - fb[2]);
         }
-        if (mc.num_frames > 1) std::copy(frame_vel.begin() + static_cast<size_t>(mc.num_frames - 2) * ndof, frame_vel.begin() + static_cast<size_t>(mc.num_frames - 1) * ndof,
-                                         frame_vel.begin() + static_cast<size_t>(mc.num_frames - 1) * ndof);
-        // cKinController::CalcCycleRootDelta (KinController.cpp:149-161)
-        const double* fb = mc.frame(0); const double* fe = mc.frame(mc.num_frames - 1);
-        cycle_root_delta = D3(fe[0] - fb[0], 0, fe[2] - fb[2]);
-        cycle_period = mc.duration();  // cSceneImitate::BuildController (SceneImitate.cpp:250-264)
+        ActivateMotion(0);
+        // cSceneImitate::BuildController (SceneImitate.cpp:250-264): the duration of the clip active at build time (a random one with
+        // --kin_ctrl clips; only the phase input reads it, which the clip-dataset controllers do not enable)
+        cycle_period = Mot().duration();
     }
+    void ActivateMotion(int id) { cur_clip = id; cycle_root_delta = clip_cycle_delta[id]; }   // cClipsController::ActivateMotion (ClipsController.cpp:238-242)
 
     // cSimCharacter::BuildMultiBody / BuildConstraints / BuildJoints (SimCharacter.cpp:789-973,1036-1086)
     void BuildSimCharacter() {
@@ -325,28 +357,29 @@ struct Oracle {
 
     // =================================================================== kinematic character
     // cMotion::CalcIndexBlend (Motion.cpp:486-515)
-    void CalcIndexBlend(double time, int& idx, double& blend) const {
-        const auto& mc = sa.motion;
+    static void CalcIndexBlendOf(const dmh::MotionClip& mc, double time, int& idx, double& blend) {
         double max_time = mc.duration();
         if (!mc.loop) {
             if (time <= 0) { idx = 0; blend = 0; return; }
             if (time >= max_time) { idx = mc.num_frames - 2; blend = 1; return; }
         }
-        int cycle = CalcCycleCount(time);
+        int cycle = CalcCycleCountOf(mc, time);
         time -= cycle * max_time;
         auto it = std::upper_bound(mc.frame_times.begin(), mc.frame_times.end(), time);
         idx = static_cast<int>(it - mc.frame_times.begin()) - 1;
         double t0 = mc.frame_times[idx], t1 = mc.frame_times[idx + 1];
         blend = (time - t0) / (t1 - t0);
     }
-    int CalcCycleCount(double time) const {  // Motion.cpp:476-484
-        int count = static_cast<int>(std::floor(time / sa.motion.duration()));
-        if (!sa.motion.loop) count = std::min(std::max(count, 0), 1);
+    static int CalcCycleCountOf(const dmh::MotionClip& mc, double time) {  // Motion.cpp:476-484
+        int count = static_cast<int>(std::floor(time / mc.duration()));
+        if (!mc.loop) count = std::min(std::max(count, 0), 1);
         return count;
     }
+    void CalcIndexBlend(double time, int& idx, double& blend) const { CalcIndexBlendOf(Mot(), time, idx, blend); }
+    int CalcCycleCount(double time) const { return CalcCycleCountOf(Mot(), time); }
     double KinPhase(double t) const {  // cMotion::CalcPhase (Motion.cpp:27-40)
-        double ph = t / sa.motion.duration();
-        if (sa.motion.loop) ph -= std::floor(ph); else ph = std::min(std::max(ph, 0.0), 1.0);
+        double ph = t / Mot().duration();
+        if (Mot().loop) ph -= std::floor(ph); else ph = std::min(std::max(ph, 0.0), 1.0);
         return ph;
     }
     // cKinCharacter::CalcPose (KinCharacter.cpp:363-386) <- cMotionController::CalcPose (MotionController.cpp:25-41) <- cMotion::CalcFrame
@@ -354,8 +387,8 @@ struct Oracle {
         int idx; double blend;
         CalcIndexBlend(time, idx, blend);
         blend = std::min(std::max(blend, 0.0), 1.0);  // cMathUtil::Saturate in cMotion::BlendFrames
-        LerpPoses(*cm, sa.motion.frame(idx), sa.motion.frame(idx + 1), blend, out);
-        if (sa.motion.loop) { D3 off = static_cast<double>(CalcCycleCount(time)) * cycle_root_delta; out[0] += off.x; out[1] += off.y; out[2] += off.z; }
+        LerpPoses(*cm, Mot().frame(idx), Mot().frame(idx + 1), blend, out);
+        if (Mot().loop) { D3 off = static_cast<double>(CalcCycleCount(time)) * cycle_root_delta; out[0] += off.x; out[1] += off.y; out[2] += off.z; }
         D3 rp = GetRootPos(out); DQ rr = GetRootRot(out);
         rr = StandardizeQuat(origin_rot * rr);
         rp = QuatRotVec(origin_rot, rp) + origin;
@@ -364,10 +397,10 @@ struct Oracle {
     // cKinCharacter::CalcVel (KinCharacter.cpp:388-406) <- cMotion::CalcFrameVel (Motion.cpp:276-293)
     void KinCalcVel(double time, VecD& out) const {
         out.assign(ndof, 0.0);
-        if (!(!sa.motion.loop && time >= sa.motion.duration())) {
+        if (!(!Mot().loop && time >= Mot().duration())) {
             int idx; double blend;
             CalcIndexBlend(time, idx, blend);
-            const double* v0 = &frame_vel[static_cast<size_t>(idx) * ndof]; const double* v1 = &frame_vel[static_cast<size_t>(idx + 1) * ndof];
+            const double* v0 = &FrameVel()[static_cast<size_t>(idx) * ndof]; const double* v1 = &FrameVel()[static_cast<size_t>(idx + 1) * ndof];
             for (int k = 0; k < ndof; ++k) out[k] = (1.0 - blend) * v0[k] + blend * v1[k];
         }
         D3 rv = QuatRotVec(origin_rot, GetRootVel(out)), rw = QuatRotVec(origin_rot, GetRootAngVel(out));
@@ -389,7 +422,12 @@ struct Oracle {
     // =================================================================== reset
     // cSceneSimChar::ResetScene (SceneSimChar.cpp:628-644) with the RNG draws injected: kin_time ~ U(0,dur),
     // rand_theta ~ U(-pi,pi) (only if --enable_rand_rot_reset), max_time ~ U(time_lim_min, time_lim_max).
-    void Reset(double rand_kin_time, double rand_theta, double max_time) {
+    // With --kin_ctrl clips the controller also draws a new clip (cClipsController::Reset, ClipsController.cpp:37-46): injected as
+    // `clip` (< 0 keeps the active one).  Note the reference draws rand_kin_time from U(0, duration of the PREVIOUS clip) because
+    // CalcRandKinResetTime runs before kin_char->Reset() (SceneImitate.cpp:331-338); a sampler that wants the reference's
+    // distribution must do the same.
+    void Reset(double rand_kin_time, double rand_theta, double max_time, int clip = -1) {
+        if (clip >= 0) ActivateMotion(clip);
         timer_time = 0;
         timer_max = (mode == 1) ? sa.cfg.time_end_lim_max : max_time;  // cRLSceneSimChar::ResetTimers (RLSceneSimChar.cpp:277-284)
         mb.clearContacts();                                            // cWorld::Reset (World.cpp:75-91)
@@ -397,6 +435,7 @@ struct Oracle {
         // cSceneImitate::ResetCharacters (SceneImitate.cpp:320-329)
         SetPose(pose0); SetVel(vel0);                                  // cCharacter::Reset
         ctrl_time = 0; need_new_action = true; prev_action_time = 0; init_time_offset = 0;  // cDeepMimicCharController::ResetParams / cCtController::ResetParams
+        prev_action_com = D3();                                                             // DeepMimicCharController.cpp:227-228
         // ResetKinChar (SceneImitate.cpp:331-349)
         origin_rot = DQ(); origin = D3();
         kin_time = rand_kin_time;
@@ -422,7 +461,10 @@ struct Oracle {
             }
             KinMoveOrigin(SimRootPos() - GetRootPos(kin_pose));  // cKinCharacter::SetRootPos (KinCharacter.cpp:239-244)
         }
-        InitHist();   // cSceneImitateAMP::Reset (SceneImitateAMP.cpp:58-68)
+        // cSceneImitateAMP::Reset (SceneImitateAMP.cpp:58-68).  cSceneTargetAMP::Reset calls cSceneImitate::Reset directly
+        // (SceneTargetAMP.cpp:129-134), so the task scenes keep the history of the last applied action across resets.
+        if (!IsTask()) InitHist();
+        if (IsTask()) { TargetTimerReset(); ResetTarget(); }   // SceneTargetAMP.cpp:132-133
     }
     // cSceneSimChar::ResolveCharGroundIntersect (SceneSimChar.cpp:542-583); AABBs from btCollisionShape::getAabb [B288-mem]
     void ResolveCharGroundIntersect() {
@@ -457,6 +499,10 @@ struct Oracle {
         UpdateLinkVel();
         BuildPoseVel();
         need_new_action = CheckNextInterval(dt, ctrl_time + init_time_offset, 1.0 / sa.ctrl.query_rate);  // CtController.cpp:221-227
+        if (IsTask()) {   // cSceneTargetAMP::Update (SceneTargetAMP.cpp:136-145)
+            UpdateTarget(dt);
+            if (tgt_timer_time >= tgt_timer_max) TargetTimerReset();
+        }
     }
     // cSceneImitate::UpdateKinChar + SyncKinCharNewCycle (SceneImitate.cpp:306-318,420-444)
     void UpdateKinChar(double dt) {
@@ -482,7 +528,7 @@ struct Oracle {
     // cSimCharacter::Update -> cCtPDController -> cImpPDController::CalcControlForces -> joint.ApplyTau
     void UpdateSimChar(double dt) {
         ctrl_time += dt;  // cDeepMimicCharController::UpdateCalcTau (DeepMimicCharController.cpp:71-78)
-        if (need_new_action) { prev_action_time = ctrl_time; need_new_action = false; UpdateHist(); }  // HandleNewAction -> cSceneImitateAMP::NewActionUpdate
+        if (need_new_action) { prev_action_time = ctrl_time; prev_action_com = CalcCOM(); need_new_action = false; UpdateHist(); }  // HandleNewAction (DeepMimicCharController.cpp:262-267) -> cSceneImitateAMP::NewActionUpdate
         VecD tau(ndof, 0.0);
         if (dt > 0) {
             rbd.Update(pose, vel);                         // cImpPDController::UpdateRBDModel (ImpPDController.cpp:129-134)
@@ -605,21 +651,26 @@ struct Oracle {
     }
     void RecordAMPObsAgent(double* out) const { BuildAMPObs(prev_pose, prev_vel, pose, vel, 0.0, out); }   // :101-113 (flat ground at 0)
     // :115-140 with the random mocap time injected; cMotion::CalcFrame / CalcFrameVel of the raw clip (no origin, no cycle offset)
-    void MotionCalcFrame(double time, VecD& p, VecD& v) const {
+    void MotionCalcFrame(int clip, double time, VecD& p, VecD& v) const {
+        const dmh::MotionClip& mc = sa.clips[clip];
+        const std::vector<double>& fv = clip_frame_vel[clip];
         int idx; double blend;
-        CalcIndexBlend(time, idx, blend);
+        CalcIndexBlendOf(mc, time, idx, blend);
         const double b = std::min(std::max(blend, 0.0), 1.0);
-        LerpPoses(*cm, sa.motion.frame(idx), sa.motion.frame(idx + 1), b, p);
+        LerpPoses(*cm, mc.frame(idx), mc.frame(idx + 1), b, p);
         v.assign(ndof, 0.0);
-        if (!(!sa.motion.loop && time >= sa.motion.duration())) {
-            const double* v0 = &frame_vel[static_cast<size_t>(idx) * ndof]; const double* v1 = &frame_vel[static_cast<size_t>(idx + 1) * ndof];
+        if (!(!mc.loop && time >= mc.duration())) {
+            const double* v0 = &fv[static_cast<size_t>(idx) * ndof]; const double* v1 = &fv[static_cast<size_t>(idx + 1) * ndof];
             for (int k = 0; k < ndof; ++k) v[k] = (1.0 - blend) * v0[k] + blend * v1[k];
         }
     }
-    void RecordAMPObsExpert(double rand_kin_time, double* out) const {
+    // clip < 0: the active clip (cSceneImitateAMP::SampleExpertMotion without a clips controller, :260-277); otherwise the clip the
+    // dataset sampler drew (cClipsController::SampleMotionID) with rand_kin_time ~ U(0, that clip's duration)
+    void RecordAMPObsExpert(int clip, double rand_kin_time, double* out) const {
         VecD p, v, pp, pv;
-        MotionCalcFrame(rand_kin_time, p, v);
-        MotionCalcFrame(rand_kin_time - 1.0 / sa.ctrl.query_rate, pp, pv);
+        const int c = clip < 0 ? cur_clip : clip;
+        MotionCalcFrame(c, rand_kin_time, p, v);
+        MotionCalcFrame(c, rand_kin_time - 1.0 / sa.ctrl.query_rate, pp, pv);
         BuildAMPObs(pp, pv, p, v, origin.y, out);
     }
 
@@ -671,6 +722,8 @@ struct Oracle {
     }
     // cSceneImitate::CalcReward / CalcRewardImitate (SceneImitate.cpp:7-127,163-175)
     double CalcReward(double* dbg = nullptr) const {
+        if (scene_kind == kTargetAMP) return CalcRewardTarget();
+        if (scene_kind == kHeadingAMP) return CalcRewardHeading();
         if (HasFallen()) return 0;
         double pose_w = 0.5, vel_w = 0.05, end_eff_w = 0.15, root_w = 0.2, com_w = 0.1;
         double total_w = pose_w + vel_w + end_eff_w + root_w + com_w;
@@ -728,11 +781,139 @@ struct Oracle {
                end_eff_w * std::exp(-err_scale * end_eff_scale * end_eff_err) + root_w * std::exp(-err_scale * root_scale * root_err) +
                com_w * std::exp(-err_scale * com_scale * com_err);
     }
+    // =================================================================== AMP task scenes
+    // stateless counter-based uniform in [0,1): identical to dm_policy.cu's u01
+    static double U01(uint64_t seed, uint64_t a, uint64_t b) {
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (a * 2654435761ull + b + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+        return static_cast<double>(z >> 11) * (1.0 / 9007199254740992.0);
+    }
+    double Draw() { return U01(task_seed, task_env, task_counter++); }
+    double RandDouble(double lo, double hi) { return (lo == hi) ? lo : lo + Draw() * (hi - lo); }   // cRand::RandDouble (util/Rand.cpp:30-41): no draw when min == max
+    bool FlipCoin(double p) { return RandDouble(0, 1) < p; }                                         // util/Rand.cpp:137-140
+    double RandDoubleNorm(double mean, double stdev) {   // util/Rand.cpp:50-55; Box-Muller on two stream draws (std::normal_distribution is implementation-defined)
+        const double u1 = Draw(), u2 = Draw();
+        return mean + stdev * std::sqrt(-2.0 * std::log(1.0 - u1)) * std::cos(2.0 * M_PI * u2);
+    }
+    void TargetTimerReset() { tgt_timer_time = 0; tgt_timer_max = RandDouble(sa.cfg.rand_target_time_min, sa.cfg.rand_target_time_max); }   // cTimer::Reset, uniform (util/Timer.cpp:51-69)
+    // cSimCharacter::CalcCOM (SimCharacter.cpp:398-416)
+    D3 CalcCOM() const {
+        D3 com; double tm = 0;
+        for (int b = 0; b < nj; ++b) { com += cm->bodies[b].mass * BodyPos(b); tm += cm->bodies[b].mass; }
+        return com / tm;
+    }
+    // cSceneTargetAMP::SampleRandTargetPos / ResetTargetPos (SceneTargetAMP.cpp:259-279)
+    void ResetTargetPos() {
+        const D3 root = SimRootPos();
+        const double dist = RandDouble(0.0, sa.cfg.max_target_dist);
+        const double theta = RandDouble(0.0, 2.0 * M_PI);
+        target_pos = D3(root.x + dist * std::cos(theta), 0, root.z + dist * std::sin(theta));
+    }
+    void SetTargetSpeed(double v) {   // cSceneHeadingAMP::SetTargetSpeed clamps (SceneHeadingAMP.cpp:90-94)
+        target_speed = (scene_kind == kHeadingAMP) ? std::min(std::max(v, sa.cfg.tar_speed_min), sa.cfg.tar_speed_max) : v;
+    }
+    // cSceneTargetAMP::ResetTarget / cSceneHeadingAMP::ResetTarget (SceneTargetAMP.cpp:248-251, SceneHeadingAMP.cpp:207-217)
+    void ResetTarget() {
+        ResetTargetPos();
+        if (scene_kind == kHeadingAMP) {
+            const double speed = RandDouble(sa.cfg.tar_speed_min, sa.cfg.tar_speed_max);
+            target_heading = 0;
+            SetTargetSpeed(speed);
+        }
+    }
+    // cSceneTargetAMP::UpdateTarget / cSceneHeadingAMP::UpdateTarget (SceneTargetAMP.cpp:232-246, SceneHeadingAMP.cpp:192-205);
+    // mEnableRandTargetPos stays true in both scenes (set by the cSceneTargetAMP constructor), mEnableTargetPos false, mEnableRandSpeed true
+    void UpdateTarget(double dt) {
+        tgt_timer_time += dt;
+        const bool timer_end = tgt_timer_time >= tgt_timer_max;
+        if (timer_end) ResetTargetPos();
+        if (scene_kind == kHeadingAMP && timer_end) {
+            // UpdateTargetHeading (SceneHeadingAMP.cpp:148-180)
+            double delta_heading;
+            if (FlipCoin(sa.cfg.sharp_turn_prob)) delta_heading = RandDouble(-M_PI, M_PI);
+            else delta_heading = RandDoubleNorm(0, sa.cfg.max_heading_turn_rate);
+            target_heading += delta_heading;
+            // UpdateTargetSpeed (SceneHeadingAMP.cpp:182-190)
+            if (FlipCoin(sa.cfg.speed_change_prob)) SetTargetSpeed(RandDouble(sa.cfg.tar_speed_min, sa.cfg.tar_speed_max));
+        }
+    }
+    int GoalSize() const { return IsTask() ? 3 : 0; }   // SceneTargetAMP.cpp:217-220, SceneHeadingAMP.cpp:131-134; 0 otherwise (RLSceneSimChar.cpp:88-91)
+    // cSceneTargetAMP::RecordGoal (SceneTargetAMP.cpp:185-215) / cSceneHeadingAMP::RecordGoal (SceneHeadingAMP.cpp:136-151)
+    void RecordGoal(double* out) const {
+        if (scene_kind == kTargetAMP) {
+            const D3 root = SimRootPos();
+            D3 rel = target_pos - root; rel.y = 0;
+            const double dist = norm(rel);
+            if (dist > 0.0001) {
+                const DM3 Rh = RotateMatAxis(D3(0, 1, 0), -CalcHeading(GetRootRot(pose)));   // cKinTree::BuildOriginTrans applied to a direction (w = 0)
+                rel = (Rh * rel) / dist;
+            } else rel = D3(1, 0, 0);
+            out[0] = rel.x; out[1] = rel.z; out[2] = dist;
+        } else if (scene_kind == kHeadingAMP) {
+            const double th = target_heading - CalcHeading(GetRootRot(pose));
+            out[0] = std::cos(th); out[1] = -std::sin(th); out[2] = target_speed;
+        }
+    }
+    bool CheckTarDistFail() const {   // SceneTargetAMP.cpp:281-292; always false in the heading scene (SceneHeadingAMP.cpp:219-222)
+        if (scene_kind != kTargetAMP) return false;
+        D3 d = SimRootPos() - target_pos; d.y = 0;
+        return sqnorm(d) > sa.cfg.tar_fail_dist * sa.cfg.tar_fail_dist;
+    }
+    bool CheckTargetSucc() const {   // SceneTargetAMP.cpp:171-183
+        D3 d = target_pos - SimRootPos(); d.y = 0;
+        return norm(d) < sa.cfg.target_succ_dist;
+    }
+    // cSceneTargetAMP::CalcReward (SceneTargetAMP.cpp:3-80)
+    double CalcRewardTarget() const {
+        const double pos_reward_w = 0.6, vel_reward_w = 0.4;
+        if (CheckTarDistFail() || HasFallen()) return 0.0;
+        const double tar_speed = target_speed;
+        const double vel_err_scale = 4 / (tar_speed * tar_speed);
+        D3 root_tar_delta = target_pos - SimRootPos(); root_tar_delta.y = 0;
+        const double root_tar_dist_sq = sqnorm(root_tar_delta);
+        const double pos_reward = std::exp(-sa.cfg.pos_reward_scale * root_tar_dist_sq);
+        double vel_reward = 0;
+        if (root_tar_dist_sq < sa.cfg.target_succ_dist * sa.cfg.target_succ_dist) vel_reward = 1.0;
+        else {
+            const double step_dur = ctrl_time - prev_action_time;
+            const D3 com = CalcCOM();
+            D3 com_tar_delta = target_pos - com; com_tar_delta.y = 0;
+            const double com_tar_dist = norm(com_tar_delta);
+            D3 com_tar_dir;
+            if (com_tar_dist > 0.0001) com_tar_dir = com_tar_delta / com_tar_dist;
+            const double avg_vel = dot(com_tar_dir, com - prev_action_com) / step_dur;
+            double vel_err = tar_speed - avg_vel;
+            if (avg_vel < 0) vel_reward = 0.0;
+            else {
+                if (sa.cfg.enable_min_tar_vel) vel_err = std::max(vel_err, 0.0);
+                vel_reward = std::exp(-vel_err_scale * vel_err * vel_err);
+            }
+        }
+        return pos_reward_w * pos_reward + vel_reward_w * vel_reward;
+    }
+    // cSceneHeadingAMP::CalcReward (SceneHeadingAMP.cpp:3-48)
+    double CalcRewardHeading() const {
+        if (HasFallen()) return 0.0;
+        const D3 com = CalcCOM();
+        const D3 tar_dir(std::cos(target_heading), 0, -std::sin(target_heading));
+        const double step_dur = ctrl_time - prev_action_time;
+        D3 avg_vel = (com - prev_action_com) / step_dur; avg_vel.y = 0;
+        const double avg_speed = dot(tar_dir, avg_vel);
+        double vel_reward = 0;
+        if (avg_speed > 0.0) {
+            double vel_err = target_speed - avg_speed;
+            if (sa.cfg.enable_min_tar_vel) vel_err = std::max(vel_err, 0.0);
+            vel_reward = std::exp(-sa.cfg.vel_reward_scale * vel_err * vel_err);
+        }
+        return vel_reward;
+    }
+
     // cRLSceneSimChar::CheckTerminate + cSceneImitate::CheckTerminate (RLSceneSimChar.cpp:187-197; SceneImitate.cpp:193-205)
     int CheckTerminate() const {
         bool fail = sa.cfg.enable_fall_end && HasFallen();
         // the AMP scenes use cRLSceneSimChar::CheckTerminate alone (SceneImitateAMP.cpp:185-189): no motion-over failure there
-        if (!fail && sa.cfg.scene == "imitate" && !sa.motion.loop && kin_time >= sa.motion.duration()) fail = true;
+        if (!fail && scene_kind == kImitate && !Mot().loop && kin_time >= Mot().duration()) fail = true;
+        if (!fail && scene_kind == kTargetAMP && CheckTarDistFail()) fail = true;   // cSceneTargetAMP::CheckTerminate (SceneTargetAMP.cpp:294-319)
         return fail ? 1 : 0;
     }
     bool IsEpisodeEnd() const { return timer_time >= timer_max || CheckTerminate() != 0; }  // RLScene.cpp:36-50
@@ -850,17 +1031,46 @@ void dmo_destroy(void* h) { delete static_cast<Oracle*>(h); }
 // out[0..7] = num_joints, pose_dim, bullet_dofs(6+n), state_size, action_size, goal_size, snapshot_size, num_frames
 void dmo_get_dims(void* h, int* out) {
     Oracle* o = static_cast<Oracle*>(h);
-    out[0] = o->nj; out[1] = o->ndof; out[2] = 6 + o->mb.numDofs; out[3] = o->StateSize(); out[4] = o->action_size; out[5] = 0; out[6] = o->SnapshotSize(); out[7] = o->sa.motion.num_frames;
+    out[0] = o->nj; out[1] = o->ndof; out[2] = 6 + o->mb.numDofs; out[3] = o->StateSize(); out[4] = o->action_size; out[5] = o->GoalSize(); out[6] = o->SnapshotSize(); out[7] = o->sa.motion.num_frames;
 }
-double dmo_motion_duration(void* h) { return static_cast<Oracle*>(h)->sa.motion.duration(); }
+double dmo_motion_duration(void* h) { return static_cast<Oracle*>(h)->Mot().duration(); }
 void dmo_set_mode(void* h, int mode) { static_cast<Oracle*>(h)->mode = mode; }
 void dmo_reset(void* h, double kin_time, double rand_theta, double max_time) { static_cast<Oracle*>(h)->Reset(kin_time, rand_theta, max_time); }
+void dmo_reset_clip(void* h, int clip, double kin_time, double rand_theta, double max_time) { static_cast<Oracle*>(h)->Reset(kin_time, rand_theta, max_time, clip); }
+// clip dataset of --kin_ctrl clips: count; per clip duration / weight / cdf / loop flag; active clip; cClipsController::SelectNewMotion on a given uniform draw
+int dmo_num_clips(void* h) { return static_cast<int>(static_cast<Oracle*>(h)->sa.clips.size()); }
+void dmo_clip_table(void* h, double* dur, double* weight, double* cdf, int* loop) {
+    Oracle* o = static_cast<Oracle*>(h);
+    for (size_t c = 0; c < o->sa.clips.size(); ++c) { dur[c] = o->sa.clips[c].duration(); weight[c] = o->sa.clip_weights[c]; cdf[c] = o->sa.clip_cdf[c]; loop[c] = o->sa.clips[c].loop ? 1 : 0; }
+}
+int dmo_current_clip(void* h) { return static_cast<Oracle*>(h)->cur_clip; }
+int dmo_select_clip(void* h, double u01) { return static_cast<Oracle*>(h)->sa.select_clip(u01); }
+// AMP task scenes
+void dmo_set_task_stream(void* h, unsigned long long seed, unsigned long long env, unsigned long long counter) { Oracle* o = static_cast<Oracle*>(h); o->task_seed = seed; o->task_env = env; o->task_counter = counter; }
+unsigned long long dmo_task_counter(void* h) { return static_cast<Oracle*>(h)->task_counter; }
+double dmo_u01(unsigned long long seed, unsigned long long a, unsigned long long b) { return Oracle::U01(seed, a, b); }
+void dmo_record_goal(void* h, double* out) { static_cast<Oracle*>(h)->RecordGoal(out); }
+// out[0..7] = target_pos xyz, target_speed, target_heading, target timer time, target timer max, prev_action_com x (then y, z in out[8], out[9])
+void dmo_get_task_state(void* h, double* out) {
+    Oracle* o = static_cast<Oracle*>(h);
+    out[0] = o->target_pos.x; out[1] = o->target_pos.y; out[2] = o->target_pos.z; out[3] = o->target_speed; out[4] = o->target_heading;
+    out[5] = o->tgt_timer_time; out[6] = o->tgt_timer_max; out[7] = o->prev_action_com.x; out[8] = o->prev_action_com.y; out[9] = o->prev_action_com.z;
+}
+void dmo_set_task_state(void* h, const double* in) {
+    Oracle* o = static_cast<Oracle*>(h);
+    o->target_pos = orc::D3(in[0], in[1], in[2]); o->target_speed = in[3]; o->target_heading = in[4]; o->tgt_timer_time = in[5]; o->tgt_timer_max = in[6];
+    o->prev_action_com = orc::D3(in[7], in[8], in[9]);
+}
+int dmo_check_target_succ(void* h) { return static_cast<Oracle*>(h)->CheckTargetSucc() ? 1 : 0; }
+int dmo_enable_amp_task_reward(void* h) { return static_cast<Oracle*>(h)->IsTask() ? 1 : 0; }   // SceneTargetAMP.cpp:222-225
+void dmo_calc_com(void* h, double* out) { orc::D3 c = static_cast<Oracle*>(h)->CalcCOM(); out[0] = c.x; out[1] = c.y; out[2] = c.z; }
 void dmo_update(void* h, double dt) { static_cast<Oracle*>(h)->Update(dt); }
 void dmo_set_action(void* h, const double* a) { static_cast<Oracle*>(h)->SetAction(a); }
 void dmo_record_state(void* h, double* out) { static_cast<Oracle*>(h)->RecordState(out); }
 int dmo_amp_obs_size(void* h) { return static_cast<Oracle*>(h)->AmpObsSize(); }
 void dmo_record_amp_obs_agent(void* h, double* out) { static_cast<Oracle*>(h)->RecordAMPObsAgent(out); }
-void dmo_record_amp_obs_expert(void* h, double kin_time, double* out) { static_cast<Oracle*>(h)->RecordAMPObsExpert(kin_time, out); }
+void dmo_record_amp_obs_expert(void* h, double kin_time, double* out) { static_cast<Oracle*>(h)->RecordAMPObsExpert(-1, kin_time, out); }
+void dmo_record_amp_obs_expert_clip(void* h, int clip, double kin_time, double* out) { static_cast<Oracle*>(h)->RecordAMPObsExpert(clip, kin_time, out); }
 double dmo_calc_reward(void* h) { return static_cast<Oracle*>(h)->CalcReward(); }
 double dmo_calc_reward_terms(void* h, double* errs) { return static_cast<Oracle*>(h)->CalcReward(errs); }
 int dmo_need_new_action(void* h) { return static_cast<Oracle*>(h)->need_new_action ? 1 : 0; }

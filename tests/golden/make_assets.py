@@ -15,7 +15,23 @@ FILES = [
     "args/run_humanoid3d_spinkick_args.txt", "args/train_humanoid3d_spinkick_args.txt", "args/run_humanoid3d_walk_args.txt", "args/train_humanoid3d_walk_args.txt",
     "args/train_humanoid3d_run_args.txt", "args/train_humanoid3d_backflip_args.txt",
     "args/run_dog3d_trot_args.txt", "args/train_dog3d_trot_args.txt", "args/train_dog3d_pace_args.txt",
+    # AMP task scenes (target / heading); their 48 MB clip dataset is replaced in the tests by the authored mini dataset below
+    "args/train_amp_target_humanoid3d_locomotion_args.txt", "args/train_amp_heading_humanoid3d_locomotion_args.txt",
 ]
+
+# Authored here (not reference data): a cClipsController dataset over clips that are already in the archive, in the reference's format
+# (R/data/datasets/humanoid3d_clips_locomotion.txt).  Tests pass it with --motion_file, which wins over the arg file's entry.
+MINI_DATASET = "data/datasets/test_clips_mini.txt"
+MINI_DATASET_TEXT = """{
+	"Motions":
+	[
+		{"Weight": 20, "File": "data/motions/humanoid3d_run.txt"},
+		{"Weight": 3, "File": "data/motions/humanoid3d_walk.txt"},
+		{"Weight": 1, "File": "data/motions/humanoid3d_spinkick.txt"},
+		{"File": "data/motions/humanoid3d_backflip.txt"}
+	]
+}
+"""
 
 def main():
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets.tar.gz")
@@ -26,6 +42,11 @@ def main():
             ti.mtime = 0; ti.uid = ti.gid = 0; ti.uname = ti.gname = ""
             with open(p, "rb") as fh:
                 tf.addfile(ti, fh)
+        import io
+        data = MINI_DATASET_TEXT.encode()
+        ti = tarfile.TarInfo(MINI_DATASET)
+        ti.size = len(data); ti.mtime = 0; ti.mode = 0o644
+        tf.addfile(ti, io.BytesIO(data))
     print("wrote", out, os.path.getsize(out), "bytes")
 
 if __name__ == "__main__":

@@ -21,8 +21,12 @@ def load_oracle():
     L.dmo_create.restype = C.c_void_p
     L.dmo_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p)]
     L.dmo_last_error.restype = C.c_char_p
-    for f in ("dmo_calc_reward", "dmo_motion_duration", "dmo_get_time", "dmo_calc_reward_terms"):
+    for f in ("dmo_calc_reward", "dmo_motion_duration", "dmo_get_time", "dmo_calc_reward_terms", "dmo_u01"):
         getattr(L, f).restype = C.c_double
+    L.dmo_u01.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+    L.dmo_set_task_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
+    L.dmo_task_counter.restype = C.c_uint64
+    L.dmo_task_counter.argtypes = [C.c_void_p]
     _LIB = L
     return L
 
@@ -60,8 +64,65 @@ class Oracle:
         except Exception:
             pass
 
-    def reset(self, kin_time=0.0, rot_theta=0.0, max_time=20.0):
-        self.L.dmo_reset(self.h, C.c_double(kin_time), C.c_double(rot_theta), C.c_double(max_time))
+    def reset(self, kin_time=0.0, rot_theta=0.0, max_time=20.0, clip=None):
+        if clip is None:
+            self.L.dmo_reset(self.h, C.c_double(kin_time), C.c_double(rot_theta), C.c_double(max_time))
+        else:
+            self.L.dmo_reset_clip(self.h, int(clip), C.c_double(kin_time), C.c_double(rot_theta), C.c_double(max_time))
+        self.motion_duration = self.L.dmo_motion_duration(self.h)
+
+    # ---- clip dataset (--kin_ctrl clips)
+    def num_clips(self):
+        return int(self.L.dmo_num_clips(self.h))
+
+    def clip_table(self):
+        n = self.num_clips()
+        dur, w, cdf = np.zeros(n), np.zeros(n), np.zeros(n)
+        loop = np.zeros(n, dtype=np.int32)
+        self.L.dmo_clip_table(self.h, dp(dur), dp(w), dp(cdf), loop.ctypes.data_as(C.POINTER(C.c_int)))
+        return dur, w, cdf, loop
+
+    def current_clip(self):
+        return int(self.L.dmo_current_clip(self.h))
+
+    def select_clip(self, u01):
+        return int(self.L.dmo_select_clip(self.h, C.c_double(u01)))
+
+    # ---- AMP task scenes (target_amp / heading_amp)
+    def set_task_stream(self, seed, env, counter=0):
+        self.L.dmo_set_task_stream(self.h, seed, env, counter)
+
+    def task_counter(self):
+        return int(self.L.dmo_task_counter(self.h))
+
+    def u01(self, seed, a, b):
+        return float(self.L.dmo_u01(seed, a, b))
+
+    def record_goal(self):
+        out = np.zeros(self.goal_size)
+        self.L.dmo_record_goal(self.h, dp(out))
+        return out
+
+    def task_state(self):
+        """dict(target_pos, target_speed, target_heading, timer, timer_max, prev_action_com)"""
+        o = np.zeros(10)
+        self.L.dmo_get_task_state(self.h, dp(o))
+        return dict(target_pos=o[0:3].copy(), target_speed=o[3], target_heading=o[4], timer=o[5], timer_max=o[6], prev_action_com=o[7:10].copy())
+
+    def set_task_state(self, target_pos, target_speed, target_heading, timer, timer_max, prev_action_com):
+        o = np.concatenate([np.asarray(target_pos, dtype=np.float64), [target_speed, target_heading, timer, timer_max], np.asarray(prev_action_com, dtype=np.float64)])
+        self.L.dmo_set_task_state(self.h, dp(o))
+
+    def check_target_succ(self):
+        return bool(self.L.dmo_check_target_succ(self.h))
+
+    def enable_amp_task_reward(self):
+        return bool(self.L.dmo_enable_amp_task_reward(self.h))
+
+    def calc_com(self):
+        o = np.zeros(3)
+        self.L.dmo_calc_com(self.h, dp(o))
+        return o
 
     def update(self, dt):
         self.L.dmo_update(self.h, C.c_double(dt))
@@ -86,9 +147,12 @@ class Oracle:
         self.L.dmo_record_amp_obs_agent(self.h, dp(out))
         return out
 
-    def record_amp_obs_expert(self, kin_time):
+    def record_amp_obs_expert(self, kin_time, clip=None):
         out = np.zeros(self.amp_obs_size())
-        self.L.dmo_record_amp_obs_expert(self.h, C.c_double(kin_time), dp(out))
+        if clip is None:
+            self.L.dmo_record_amp_obs_expert(self.h, C.c_double(kin_time), dp(out))
+        else:
+            self.L.dmo_record_amp_obs_expert_clip(self.h, int(clip), C.c_double(kin_time), dp(out))
         return out
 
     def reward_terms(self):
@@ -132,6 +196,13 @@ class Oracle:
     def set_pose_vel(self, p, v):
         p = np.ascontiguousarray(p, dtype=np.float64); v = np.ascontiguousarray(v, dtype=np.float64)
         self.L.dmo_set_pose_vel(self.h, dp(p), dp(v))
+
+    def body_state(self):
+        """World position, rotation (w,x,y,z), linear and angular velocity of every body."""
+        n = self.num_joints
+        pos, rot, lv, av = np.zeros((n, 3)), np.zeros((n, 4)), np.zeros((n, 3)), np.zeros((n, 3))
+        self.L.dmo_body_state(self.h, dp(pos), dp(rot), dp(lv), dp(av))
+        return pos, rot, lv, av
 
     def get_snapshot(self):
         s = np.zeros(self.snapshot_size)

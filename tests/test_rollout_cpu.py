@@ -63,3 +63,41 @@ def test_policy_head_shapes_and_logp():
     z = (a - mu) / p.logstd.exp()
     ref = (-0.5 * z * z - p.logstd - 0.5 * math.log(2 * math.pi)).sum(-1)
     torch.testing.assert_close(logp, ref, rtol=1e-4, atol=1e-4)
+
+
+def _random_gated_actor(rng, s_dim=226, g_dim=3, a_dim=28, hidden=(1024, 512)):
+    w = lambda i, o: (rng.standard_normal((i, o)) / math.sqrt(i)).astype(np.float32)
+    b = lambda o: (0.1 * rng.standard_normal(o)).astype(np.float32)
+    dims = [s_dim + g_dim] + list(hidden)
+    return dict(hidden=[(w(i, o), b(o)) for i, o in zip(dims[:-1], dims[1:])], mean=(w(dims[-1], a_dim), b(a_dim)), logstd=b(a_dim),
+                gate_common=(w(g_dim, 128), b(128)), gates=[dict(hidden=(w(128, 64), b(64)), bias=(w(64, h), b(h)), scale=(w(64, h), b(h))) for h in hidden],
+                s_norm_mean=np.zeros(s_dim), s_norm_std=np.ones(s_dim), g_norm_mean=np.zeros(g_dim), g_norm_std=np.ones(g_dim),
+                a_norm_mean=np.zeros(a_dim), a_norm_std=np.ones(a_dim))
+
+
+def test_gated_policy_matches_numpy_restatement_of_the_reference_net():
+    """build_gated_policy vs. a numpy restatement of fc_2layers_gated_1024units (R/learning/nets/fc_2layers_gated_1024units.py:6-58)."""
+    import torch
+    from deepmimic_b200.rollout import build_gated_policy, load_actor_weights
+    from tests.test_task_scenes_cpu import _f64, gated_actor_mode
+    rng = np.random.default_rng(4)
+    actor = _random_gated_actor(rng)
+    pol = load_actor_weights(build_gated_policy(226, 3, 28), actor).double()
+    s, g = rng.standard_normal((5, 226)), rng.standard_normal((5, 3))
+    with torch.no_grad():
+        got = pol(torch.as_tensor(s), torch.as_tensor(g)).numpy()
+    want = np.stack([gated_actor_mode(_f64(actor), s[i], g[i]) for i in range(5)])
+    np.testing.assert_allclose(got, want, atol=1e-10)
+    a, logp = pol.sample(torch.as_tensor(s), torch.as_tensor(g), explore_mask=torch.zeros(5, dtype=torch.bool))
+    np.testing.assert_allclose(a.detach().numpy(), want, atol=1e-10)            # no exploration: the mode
+
+
+def test_checkpoint_reader_returns_the_gate_layers_of_a_task_policy():
+    import os
+    ckpt = "/root/reference/data/policies/humanoid3d_amp/humanoid3d_amp_heading_locomotion.ckpt"
+    if not os.path.exists(ckpt + ".index"):
+        pytest.skip("reference checkout with pretrained policies not available")
+    from deepmimic_b200.tf_checkpoint import load_actor
+    a = load_actor(ckpt)
+    assert [w.shape for w, _ in a["hidden"]] == [(229, 1024), (1024, 512)] and a["gate_common"][0].shape == (3, 128)
+    assert [g["scale"][0].shape for g in a["gates"]] == [(64, 1024), (64, 512)] and a["g_norm_mean"].shape == (3,)

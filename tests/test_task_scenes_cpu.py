@@ -1,0 +1,311 @@
+"""CPU tests of the oracle's restatement of the AMP task scenes: cSceneTargetAMP / cSceneHeadingAMP goals, task
+rewards, target updates and termination (R/DeepMimicCore/scenes/SceneTargetAMP.cpp, SceneHeadingAMP.cpp), the clip dataset of
+cClipsController (anim/ClipsController.cpp) and the counter-based draw stream the CUDA path will share.  Known-answer tests against
+independent numpy restatements of the cited formulas; behavioural pins with the reference's pretrained task policies.
+The CUDA path does not run these scenes yet (dm_create refuses them): this is the oracle-first half of the row."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from tests.oracle_binding import Oracle
+
+MINI = ["--motion_file", "data/datasets/test_clips_mini.txt"]
+TARGET = MINI + ["--arg_file", "args/train_amp_target_humanoid3d_locomotion_args.txt"]
+HEADING = MINI + ["--arg_file", "args/train_amp_heading_humanoid3d_locomotion_args.txt"]
+MASK = (1 << 64) - 1
+
+
+def u01(seed, a, b):
+    """splitmix64 finaliser on seed + golden * (a * 2654435761 + b + 1) -> [0, 1): the stream of dm_policy.cu's u01."""
+    z = (seed + 0x9E3779B97F4A7C15 * ((a * 2654435761 + b + 1) & MASK)) & MASK
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & MASK
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & MASK
+    z ^= z >> 31
+    return (z >> 11) * (1.0 / 9007199254740992.0)
+
+
+class Stream:
+    def __init__(self, seed, env, counter=0):
+        self.seed, self.env, self.k = seed, env, counter
+
+    def draw(self):
+        v = u01(self.seed, self.env, self.k); self.k += 1
+        return v
+
+    def uniform(self, lo, hi):
+        return lo if lo == hi else lo + self.draw() * (hi - lo)
+
+    def coin(self, p):
+        return self.uniform(0.0, 1.0) < p
+
+    def normal(self, mean, std):
+        u1, u2 = self.draw(), self.draw()
+        return mean + std * math.sqrt(-2.0 * math.log(1.0 - u1)) * math.cos(2.0 * math.pi * u2)
+
+
+def heading_of(pose):
+    """cKinTree::CalcHeading (KinTree.cpp:1615-1627): rotate (1,0,0) by the root quaternion, heading = atan2(-z, x)."""
+    w, x, y, z = pose[3:7]
+    rx = 1 - 2 * (y * y + z * z); rz = 2 * (x * z - w * y)
+    return math.atan2(-rz, rx)
+
+
+def masses(asset_root):
+    c = json.load(open(os.path.join(asset_root, "data/characters/humanoid3d.txt")))
+    return np.array([b["Mass"] for b in c["BodyDefs"]])
+
+
+def com_of(o, asset_root):
+    m = masses(asset_root)
+    return (m[:, None] * o.body_state()[0]).sum(0) / m.sum()
+
+
+def step_policy(o, action=None, updates=20):
+    o.set_action(np.zeros(o.action_size) if action is None else action)
+    for _ in range(updates):
+        o.update(1.0 / 600.0)
+
+
+def test_stream_matches_the_documented_hash(asset_root):
+    o = Oracle(TARGET, asset_root)
+    for seed, a, b in [(0, 0, 0), (1, 2, 3), (0xDEADBEEF, 4095, 10 ** 6), (MASK, 7, 1 << 40)]:
+        assert o.u01(seed, a, b) == u01(seed, a, b)
+    xs = np.array([u01(5, 9, k) for k in range(20000)])
+    assert 0.0 <= xs.min() and xs.max() < 1.0 and abs(xs.mean() - 0.5) < 0.01 and abs(xs.var() - 1 / 12.0) < 0.003
+
+
+def test_clip_dataset_tables_and_sampler(asset_root):
+    """cClipsController::LoadMotions / BuildClipsCDF / SelectNewMotion (ClipsController.cpp:145-236)."""
+    o = Oracle(TARGET, asset_root)
+    dur, w, cdf, loop = o.clip_table()
+    assert o.num_clips() == 4 and list(w) == [20.0, 3.0, 1.0, 1.0]          # a missing "Weight" means 1
+    np.testing.assert_allclose(cdf, np.cumsum(w) / w.sum(), rtol=1e-15)
+    for f, d in zip(["run", "walk", "spinkick", "backflip"], dur):
+        fr = json.load(open(os.path.join(asset_root, "data/motions/humanoid3d_%s.txt" % f)))["Frames"]
+        assert d == pytest.approx(sum(x[0] for x in fr[:-1]), rel=1e-12)
+    for u, want in [(0.0, 0), (0.79999, 0), (0.8, 1), (0.91, 1), (0.92, 2), (0.95999, 2), (0.96, 3), (0.999999, 3)]:
+        assert o.select_clip(u) == want                                         # std::upper_bound: cdf[i] <= u moves on
+    # a reset with an injected clip activates it: duration, cycle delta and the kinematic pose come from that clip
+    for c in range(4):
+        o.reset(0.2, 0.0, 20.0, clip=c)
+        assert o.current_clip() == c and o.motion_duration == dur[c]
+    o.reset(0.2, 0.0, 20.0)                                                     # no clip given: the active one stays
+    assert o.current_clip() == 3
+    # expert observations come from the sampled clip, not the active one (cSceneImitateAMP::SampleExpertMotion, SceneImitateAMP.cpp:260-277)
+    e0, e1 = o.record_amp_obs_expert(0.3, clip=0), o.record_amp_obs_expert(0.3, clip=1)
+    assert np.isfinite(e0).all() and np.abs(e0 - e1).max() > 1e-2
+    single = Oracle(["--arg_file", "args/train_humanoid3d_walk_args.txt", "--scene", "imitate_amp", "--enable_amp_obs_local_root", "true"], asset_root)
+    es = single.record_amp_obs_expert(0.3)                                      # clip 1 is the walk clip
+    keep = np.ones(226, dtype=bool); keep[[0, 71]] = False                       # root heights are relative to each kinematic character's own origin height
+    np.testing.assert_allclose(es[keep], e1[keep], atol=1e-12)
+
+
+@pytest.mark.parametrize("args,size", [(TARGET, 3), (HEADING, 3), (["--arg_file", "args/train_humanoid3d_walk_args.txt"], 0)])
+def test_goal_size_and_task_reward_flag(asset_root, args, size):
+    o = Oracle(args, asset_root)
+    assert o.goal_size == size and o.enable_amp_task_reward() == (size > 0)
+    assert o.state_size == (226 if size else 227) and o.amp_obs_size() == 226
+
+
+def test_reset_draw_order_target(asset_root):
+    """cSceneTargetAMP::Reset (SceneTargetAMP.cpp:129-134): timer max ~ U(5, 10), then target = root + dist (cos, 0, sin) with
+    dist ~ U(0, max_target_dist), theta ~ U(0, 2 pi) (SceneTargetAMP.cpp:259-274)."""
+    o = Oracle(TARGET, asset_root)
+    o.set_task_stream(77, 12, 0)
+    o.reset(0.25, 1.1, 20.0, clip=1)
+    s = Stream(77, 12)
+    tmax = s.uniform(5.0, 10.0); dist = s.uniform(0.0, 10.0); th = s.uniform(0.0, 2 * math.pi)
+    t = o.task_state()
+    root = o.get_pose()[0][:3]
+    assert t["timer"] == 0.0 and t["timer_max"] == pytest.approx(tmax, rel=1e-15) and o.task_counter() == 3
+    np.testing.assert_allclose(t["target_pos"], [root[0] + dist * math.cos(th), 0.0, root[2] + dist * math.sin(th)], atol=1e-12)
+    assert t["target_speed"] == 1.0 and np.all(t["prev_action_com"] == 0.0)      # DeepMimicCharController.cpp:227-228
+
+
+def test_target_goal_and_reward_known_answers(asset_root):
+    o = Oracle(TARGET, asset_root)
+    o.set_task_stream(3, 0, 0)
+    o.reset(0.4, -2.0, 20.0, clip=0)
+    step_policy(o); step_policy(o)                                                # prev-action bookkeeping is live now
+    pose = o.get_pose()[0]
+    root, hd = pose[:3], heading_of(pose)
+    com = com_of(o, asset_root)
+    np.testing.assert_allclose(o.calc_com(), com, atol=1e-12)
+    t = o.task_state()
+    # cDeepMimicCharController::UpdateCalcTau advances the clock BEFORE HandleNewAction stamps it (DeepMimicCharController.cpp:71-78,262-267), so
+    # at the next query the step lasted 19 updates on that clock while the COM moved for 20: the reference's average speed runs 20/19 high
+    dt_step = 19 / 600.0
+    vel_terms = []
+    vel = (com - t["prev_action_com"]) / dt_step; vel[1] = 0.0                    # planar COM velocity on the controller's clock
+    ang = math.atan2(vel[2], vel[0]) + math.acos(0.5 / np.linalg.norm(vel))       # a direction along which the COM moves at 0.5 m/s
+    partial = [com[0] + 4.0 * math.cos(ang), 0.0, com[2] + 4.0 * math.sin(ang)]
+    for tar in ([root[0] + 3.0, 0.0, root[2] - 1.5], [root[0] - 0.2, 0.0, root[2] + 0.1], [root[0] + 14.0, 0.0, root[2] + 6.0], [root[0], 0.0, root[2]], partial):
+        tar = np.array(tar)
+        o.set_task_state(tar, 1.0, 0.0, t["timer"], t["timer_max"], t["prev_action_com"])
+        rel = tar - root; rel[1] = 0.0
+        dist = np.linalg.norm(rel)
+        # RecordGoal (SceneTargetAMP.cpp:185-215): direction in the heading frame, then the distance
+        if dist > 1e-4:
+            c, s_ = math.cos(-hd), math.sin(-hd)                                 # rotation about +y by -heading
+            loc = np.array([c * rel[0] + s_ * rel[2], 0.0, -s_ * rel[0] + c * rel[2]]) / dist
+        else:
+            loc = np.array([1.0, 0.0, 0.0])
+        np.testing.assert_allclose(o.record_goal(), [loc[0], loc[2], dist], atol=1e-12)
+        # CalcReward (SceneTargetAMP.cpp:3-80)
+        fail = dist * dist > 15.0 ** 2
+        if fail:
+            want = 0.0
+        else:
+            pos_r = math.exp(-0.5 * dist * dist)                                 # --pos_reward_scale 0.5
+            if dist * dist < 0.25:
+                vel_r = 1.0
+            else:
+                d = tar - com; d[1] = 0.0
+                dirn = d / np.linalg.norm(d)
+                avg_vel = float(dirn @ (com - t["prev_action_com"])) / dt_step
+                err = max(1.0 - avg_vel, 0.0)                                    # --enable_min_tar_vel true, --tar_speed 1
+                vel_r = 0.0 if avg_vel < 0 else math.exp(-4.0 * err * err)
+                vel_terms.append(vel_r)
+            want = 0.6 * pos_r + 0.4 * vel_r
+        assert o.calc_reward() == pytest.approx(want, abs=1e-9)
+        assert o.check_terminate() == (1 if fail else 0) and o.check_target_succ() == (dist < 0.5)   # SceneTargetAMP.cpp:171-183,281-319
+    assert any(0.0 < v < 1.0 for v in vel_terms), vel_terms                        # the velocity branch was exercised non-trivially
+    # moving away from the target: no velocity reward
+    away = com + 5.0 * (t["prev_action_com"] - com) / np.linalg.norm((t["prev_action_com"] - com)[[0, 2]])
+    o.set_task_state([away[0], 0.0, away[2]], 1.0, 0.0, t["timer"], t["timer_max"], t["prev_action_com"])
+    d2 = (away[0] - root[0]) ** 2 + (away[2] - root[2]) ** 2
+    assert o.calc_reward() == pytest.approx(0.6 * math.exp(-0.5 * d2), abs=1e-9)
+
+
+def test_heading_goal_reward_and_update_sequence(asset_root):
+    o = Oracle(HEADING, asset_root)
+    o.set_task_stream(11, 5, 0)
+    o.reset(0.1, 0.7, 20.0, clip=0)
+    s = Stream(11, 5)
+    tmax = s.uniform(0.2, 0.5)
+    s.uniform(0.0, 10.0); s.uniform(0.0, 2 * math.pi)                             # the (unused) target position is still drawn: mEnableRandTargetPos stays true
+    speed = s.uniform(1.0, 5.0)
+    t = o.task_state()
+    assert t["timer_max"] == pytest.approx(tmax, rel=1e-15) and t["target_speed"] == pytest.approx(speed, rel=1e-15) and t["target_heading"] == 0.0
+    # replay 3 s of target updates (SceneTargetAMP.cpp:136-145,232-246; SceneHeadingAMP.cpp:148-205) against the stream
+    heading, timer = 0.0, 0.0
+    changes = 0
+    for k in range(1800):
+        o.update(1.0 / 600.0)
+        timer += 1.0 / 600.0
+        if timer >= tmax:
+            s.uniform(0.0, 10.0); s.uniform(0.0, 2 * math.pi)                     # ResetTargetPos
+            heading += s.uniform(-math.pi, math.pi) if s.coin(0.01) else s.normal(0.0, 0.15)
+            if s.coin(0.02):
+                speed = min(max(s.uniform(1.0, 5.0), 1.0), 5.0)
+            timer, tmax = 0.0, s.uniform(0.2, 0.5)
+            changes += 1
+        t = o.task_state()
+        assert t["target_heading"] == pytest.approx(heading, abs=1e-12) and t["target_speed"] == pytest.approx(speed, rel=1e-15)
+        assert t["timer"] == pytest.approx(timer, abs=1e-12) and t["timer_max"] == pytest.approx(tmax, rel=1e-15)
+    assert changes >= 5 and o.task_counter() == s.k
+    # goal (SceneHeadingAMP.cpp:136-151) and reward (SceneHeadingAMP.cpp:3-48) at a need-new-action boundary
+    o.reset(0.1, 0.7, 20.0, clip=1)
+    step_policy(o); step_policy(o)
+    pose = o.get_pose()[0]
+    t = o.task_state()
+    com = com_of(o, asset_root)
+    for th, spd in [(0.0, 1.0), (1.3, 2.5), (-2.0, 4.0), (math.pi, 1.5)]:
+        o.set_task_state(t["target_pos"], spd, th, t["timer"], t["timer_max"], t["prev_action_com"])
+        rel = th - heading_of(pose)
+        np.testing.assert_allclose(o.record_goal(), [math.cos(rel), -math.sin(rel), spd], atol=1e-12)
+        v = (com - t["prev_action_com"]) / (19 / 600.0); v[1] = 0.0                  # 19, not 20: see the target test
+        sp = math.cos(th) * v[0] - math.sin(th) * v[2]
+        want = math.exp(-0.25 * (spd - sp) ** 2) if sp > 0 else 0.0              # --vel_reward_scale 0.25, enable_min_tar_vel false here
+        assert o.calc_reward() == pytest.approx(want, abs=1e-9)
+    assert o.check_terminate() == 0                                               # no distance failure in the heading scene
+
+
+def test_task_scenes_keep_the_action_history_across_resets(asset_root):
+    """cSceneTargetAMP::Reset calls cSceneImitate::Reset, not cSceneImitateAMP::Reset (SceneTargetAMP.cpp:129-134): no InitHist, the
+    previous-pose half of the agent observation stays the state at the last applied action.  imitate_amp re-initialises it from the clip."""
+    pose_size = 71                                                                # 71 pose + 42 vel floats per time step (SceneImitateAMP.cpp:214-258)
+    for args, keeps in ((TARGET, True), (["--scene", "imitate_amp", "--arg_file", "args/train_humanoid3d_walk_args.txt"], False)):
+        o = Oracle(args, asset_root)
+        o.set_task_stream(1, 0, 0)
+        o.reset(0.3, 0.0, 20.0)
+        step_policy(o); step_policy(o, updates=7)
+        before = o.record_amp_obs_agent()[pose_size:2 * pose_size]
+        o.reset(0.9, 0.0, 20.0)
+        after = o.record_amp_obs_agent()[pose_size:2 * pose_size]
+        same = np.allclose(before[7:-12], after[7:-12], atol=1e-12)               # joint rotations of the history pose (heading-frame free)
+        assert same == keeps
+
+
+def _f64(a):
+    if isinstance(a, dict):
+        return {k: _f64(v) for k, v in a.items()}
+    if isinstance(a, (list, tuple)):
+        return type(a)(_f64(v) for v in a)
+    return np.asarray(a, dtype=np.float64)
+
+
+def gated_actor_mode(actor, s, g):
+    """fc_2layers_gated_1024units (R/learning/nets/fc_2layers_gated_1024units.py:6-58) + Gaussian mode, numpy."""
+    relu = lambda x: np.maximum(x, 0.0)
+    ns = (s - actor["s_norm_mean"]) / actor["s_norm_std"]; ng = (g - actor["g_norm_mean"]) / actor["g_norm_std"]
+    gc = relu(ng @ actor["gate_common"][0] + actor["gate_common"][1])
+    h = np.concatenate([ns, ng], axis=-1)
+    for (w, b), gt in zip(actor["hidden"], actor["gates"]):
+        gh = relu(gc @ gt["hidden"][0] + gt["hidden"][1])
+        scale = 2.0 / (1.0 + np.exp(-(gh @ gt["scale"][0] + gt["scale"][1])))
+        h = relu(scale * (h @ w + b) + gh @ gt["bias"][0] + gt["bias"][1])
+    return (h @ actor["mean"][0] + actor["mean"][1]) * actor["a_norm_std"] + actor["a_norm_mean"]
+
+
+def run_task_policy(arg_file, ckpt, seed, clip, t0, theta, steps=600):
+    from deepmimic_b200.tf_checkpoint import load_actor
+    ref = "/root/reference"
+    a = _f64(load_actor(os.path.join(ref, "data/policies", ckpt + ".ckpt")))
+    o = Oracle(["--arg_file", arg_file], ref)
+    o.L.dmo_set_mode(o.h, 1)
+    o.set_task_stream(seed, 0, 0)
+    o.reset(t0, theta, 20.0, clip=clip)
+    rew, succ, dist = [], 0, []
+    for _ in range(steps):
+        if o.is_episode_end():
+            break
+        g = o.record_goal()
+        dist.append(g[2])
+        o.set_action(gated_actor_mode(a, o.record_state(), g))
+        for _ in range(20):
+            o.update(1.0 / 600.0)
+            if o.is_episode_end():
+                break
+        rew.append(o.calc_reward())
+        succ += o.check_target_succ()
+    return len(rew), float(np.mean(rew)), o.has_fallen(), succ, np.array(dist), o
+
+
+needs_reference = pytest.mark.skipif(not os.path.exists("/root/reference/data/policies/humanoid3d_amp/humanoid3d_amp_target_locomotion.ckpt.index"),
+                                     reason="reference checkout with pretrained policies not available")
+
+
+@needs_reference
+@pytest.mark.parametrize("seed,clip,t0,theta", [(1, 0, 0.3, 0.4), (2, 30, 1.0, -2.5)])
+def test_pretrained_target_policy_walks_to_its_targets_in_the_oracle(seed, clip, t0, theta):
+    """The reference's own target-location policy (trained in the real simulator on goals from the real RecordGoal) reaches the targets
+    the oracle draws: it spends a good part of the 20 s inside the 0.5 m success radius and never falls.  A wrong goal frame, sign or
+    target update would send it elsewhere."""
+    n, mean_r, fallen, succ, dist, o = run_task_policy("args/run_amp_target_humanoid3d_locomotion_args.txt", "humanoid3d_amp/humanoid3d_amp_target_locomotion",
+                                                       seed, clip, t0, theta)
+    assert n == 600 and not fallen, (n, fallen)
+    assert succ >= 60 and dist.min() < 0.2 and mean_r > 0.4, (succ, dist.min(), mean_r)
+
+
+@needs_reference
+@pytest.mark.parametrize("seed,clip,t0,theta", [(1, 0, 0.3, 0.4), (5, 17, 0.5, 2.0)])
+def test_pretrained_heading_policy_follows_heading_and_speed_in_the_oracle(seed, clip, t0, theta):
+    """Same for the heading policy: the task reward exp(-0.25 (v* - v)^2) of the oracle's heading / speed commands stays high for 20 s."""
+    n, mean_r, fallen, succ, dist, o = run_task_policy("args/run_amp_heading_humanoid3d_locomotion_args.txt", "humanoid3d_amp/humanoid3d_amp_heading_locomotion",
+                                                       seed, clip, t0, theta)
+    assert n == 600 and not fallen, (n, fallen)
+    assert mean_r > 0.8, mean_r
