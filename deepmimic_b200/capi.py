@@ -18,7 +18,7 @@ class DmDims(C.Structure):
 DM_STATE_OFFSET, DM_STATE_SCALE, DM_ACTION_OFFSET, DM_ACTION_SCALE, DM_ACTION_BOUND_MIN, DM_ACTION_BOUND_MAX, DM_STATE_NORM_GROUPS = range(7)
 
 EXPORTS = ["dm_create", "dm_load_host", "dm_get_model_info", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_stream", "dm_sync", "dm_set_mode", "dm_set_sample_count", "dm_get_time_limits", "dm_reset", "dm_set_action",
-           "dm_update", "dm_record_state", "dm_record_goal", "dm_calc_reward", "dm_record_amp_obs_agent", "dm_record_amp_obs_expert", "dm_amp_obs_host", "dm_observe", "dm_get_flags", "dm_step_host", "dm_get_snapshot",
+           "dm_update", "dm_record_state", "dm_record_goal", "dm_goal_host", "dm_get_task_state", "dm_set_task_state", "dm_get_task_params", "dm_calc_reward", "dm_record_amp_obs_agent", "dm_record_amp_obs_expert", "dm_amp_obs_host", "dm_observe", "dm_get_flags", "dm_step_host", "dm_get_snapshot",
            "dm_set_snapshot", "dm_get_counters", "dm_debug_enable", "dm_get_debug"]
 
 
@@ -51,6 +51,10 @@ def lib():
         L.dm_record_state.argtypes = [vp, fp]
         L.dm_record_goal.argtypes = [vp, fp]
         L.dm_calc_reward.argtypes = [vp, fp]
+        L.dm_goal_host.argtypes = [vp, fp]
+        L.dm_get_task_state.argtypes = [vp, C.c_int, dp]
+        L.dm_set_task_state.argtypes = [vp, C.c_int, dp]
+        L.dm_get_task_params.argtypes = [vp, dp, C.POINTER(C.c_uint64)]
         L.dm_record_amp_obs_agent.argtypes = [vp, fp]
         L.dm_record_amp_obs_expert.argtypes = [vp, dp, fp]
         L.dm_amp_obs_host.argtypes = [vp, C.c_int, dp, fp]
@@ -121,6 +125,29 @@ class BatchedCore:
     def observe(self, state=None, reward=None):
         self._chk(lib().dm_observe(self.h, C.c_void_p(state.data_ptr()) if state is not None else None,
                                    C.c_void_p(reward.data_ptr()) if reward is not None else None))
+
+    def record_goal(self, out):  # torch float32 cuda tensor [N, goal_size]; task scenes only
+        self._chk(lib().dm_record_goal(self.h, C.c_void_p(out.data_ptr())))
+
+    def goal_host(self):
+        out = np.zeros((self.num_envs, 3), dtype=np.float32)
+        self._chk(lib().dm_goal_host(self.h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def task_state(self, env):
+        out = np.zeros(16, dtype=np.float64)
+        self._chk(lib().dm_get_task_state(self.h, env, _dptr(out)))
+        return out
+
+    def set_task_state(self, env, block):
+        b = np.ascontiguousarray(block, dtype=np.float64)
+        self._chk(lib().dm_set_task_state(self.h, env, _dptr(b)))
+
+    def task_params(self):
+        out = np.zeros(16, dtype=np.float64)
+        key = (C.c_uint64 * 2)()
+        self._chk(lib().dm_get_task_params(self.h, _dptr(out), key))
+        return out, int(key[0]), int(key[1])
 
     def amp_obs_agent(self, out):  # torch float32 cuda tensor [N, amp_obs_size]
         self._chk(lib().dm_record_amp_obs_agent(self.h, C.c_void_p(out.data_ptr())))
@@ -197,6 +224,12 @@ class HostModel:
         if lib().dm_get_static(self.h, kind, _dptr(out)) != 0:
             raise RuntimeError(lib().dm_last_error().decode())
         return out
+
+    def task_params(self):
+        out = np.zeros(16, dtype=np.float64)
+        key = (C.c_uint64 * 2)()
+        lib().dm_get_task_params(self.h, _dptr(out), key)
+        return out, int(key[0]), int(key[1])
 
     def set_sample_count(self, count):
         if lib().dm_set_sample_count(self.h, int(count)) != 0:

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <numeric>
 #include <cstring>
 #include <memory>
@@ -28,8 +29,10 @@ __global__ void dm_reset_kernel(const DevModel*, DevState, const double*, const 
 __global__ void dm_set_action_kernel(const DevModel*, DevState, const float*, int);
 template <int W, int BLOCK>
 __global__ void dm_amp_obs_kernel(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int);
-template <int W, bool DEBUG>
+template <int W, bool DEBUG, bool TASK>
 __global__ void dm_step_kernel(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
+__global__ void dm_task_reset_kernel(const DevModel*, DevState, int);
+__global__ void dm_task_observe_kernel(const DevModel*, DevState, float*, float*, int);
 int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L);
 int dm_step_smem_bytes(const StepLayout& L, int tiles);
 
@@ -65,6 +68,7 @@ struct dm_handle {
     double* d_inj[3] = {nullptr, nullptr, nullptr};
     int32_t* d_flags4 = nullptr;
     float *d_amp = nullptr, *p_amp = nullptr;                              // staging for dm_amp_obs_host
+    float *d_goal = nullptr, *p_goal = nullptr;                            // staging for dm_goal_host (task scenes)
     float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;            // staging for dm_step_host
     float *p_act = nullptr, *p_obs = nullptr, *p_rew = nullptr; int32_t* p_flags = nullptr;  // pinned host staging
     cudaStream_t stream = nullptr;
@@ -144,6 +148,18 @@ bool build_device_model(dm_handle& H) {
     M.motion_dur = sa.motion.duration(); M.cycle_period = sa.motion.duration(); M.query_dt = 1.0 / sa.ctrl.query_rate;
     M.time_lim_min = sa.cfg.time_lim_min; M.time_lim_max = sa.cfg.time_lim_max; M.time_end_lim_max = sa.cfg.time_end_lim_max;
     M.total_mass = static_cast<float>(cm.total_mass());
+    {   // AMP task scenes (dm_task.cuh)
+        const dmh::SceneConfig& c = sa.cfg;
+        M.task_kind = c.scene == "target_amp" ? dmk::kTaskTarget : (c.scene == "heading_amp" ? dmk::kTaskHeading : dmk::kTaskNone);
+        dmk::TaskParams& T = M.task;
+        T.timer_min = c.rand_target_time_min; T.timer_max = c.rand_target_time_max;
+        T.max_target_dist = c.max_target_dist; T.target_succ_dist = c.target_succ_dist; T.tar_fail_dist = c.tar_fail_dist; T.pos_reward_scale = c.pos_reward_scale;
+        T.max_heading_turn_rate = c.max_heading_turn_rate; T.sharp_turn_prob = c.sharp_turn_prob; T.speed_change_prob = c.speed_change_prob;
+        T.tar_speed_min = c.tar_speed_min; T.tar_speed_max = c.tar_speed_max; T.vel_reward_scale = c.vel_reward_scale; T.tar_speed = c.tar_speed;
+        T.enable_min_tar_vel = c.enable_min_tar_vel ? 1 : 0;
+        M.task_seed = H.seed ^ 0x7461736b73ull;   // "tasks": a stream of its own next to the reset draws
+        M.env_id_base = H.env_offset;
+    }
     {
         const double* fb = sa.motion.frame(0); const double* fe = sa.motion.frame(sa.motion.num_frames - 1);
         M.cycle_delta[0] = static_cast<float>(fe[0] - fb[0]); M.cycle_delta[1] = 0.f; M.cycle_delta[2] = static_cast<float>(fe[2] - fb[2]);
@@ -260,9 +276,9 @@ void build_statics(dm_handle& H) {
     }
 }
 
-template <int W, bool DEBUG>
+template <int W, bool DEBUG, bool TASK>
 int launch_step(dm_handle* h, double dt, int n_updates) {
-    auto kern = dmk::dm_step_kernel<W, DEBUG>;
+    auto kern = dmk::dm_step_kernel<W, DEBUG, TASK>;
     // opt in to the large dynamic shared-memory carve-out; the limit is raised whenever a handle needs more than any earlier one on
     // this device (attributes are per device and per function: several handles of different sizes may live in one process)
     static std::mutex mu;
@@ -283,7 +299,13 @@ int launch_step(dm_handle* h, double dt, int n_updates) {
     return 0;
 }
 template <int W, bool DEBUG>
-int launch_update(dm_handle* h, double dt, int n_updates) { return launch_step<W, DEBUG>(h, dt, n_updates); }
+int launch_update(dm_handle* h, double dt, int n_updates) {
+    if (h->hm.task_kind != dmk::kTaskNone) {   // AMP task scenes: the instantiation that also advances the task block (no debug dumps there)
+        if (DEBUG) { g_err = "dm_debug_enable is not available in the AMP task scenes"; return fail(); }
+        return launch_step<W, false, true>(h, dt, n_updates);
+    }
+    return launch_step<W, DEBUG, false>(h, dt, n_updates);
+}
 template <int W>
 int launch_observe(dm_handle* h, float* d_state, float* d_reward) {
     constexpr int BLOCK = 64;
@@ -323,8 +345,15 @@ static bool load_host_model(dm_handle& H, const char* asset_root, int argc, cons
         H.sa = dmh::load_scene_assets(ap, root);
         // scenes on the accelerated path: "imitate" and its AMP variant (same character, controller, clip and dynamics; AMP observations on top).
         // The AMP task scenes (heading / target / dribble / strike) add goals, task rewards and clip datasets that are not built: refuse them loudly.
-        if (H.sa.cfg.scene != "imitate" && H.sa.cfg.scene != "imitate_amp") throw std::runtime_error("Unsupported scene: " + H.sa.cfg.scene + " (supported: imitate, imitate_amp)");
-        if (H.sa.cfg.kin_ctrl == "clips") throw std::runtime_error("Unsupported kinematic controller: clips (clip datasets are not on the accelerated path; supported: motion)");
+        // The AMP task scenes target_amp / heading_amp have their device code written (dm_task.cuh, dm_step_kernel<.., TASK>, dm_task_*_kernel)
+        // but it has not run on hardware yet: they are accepted only with DM_EXPERIMENTAL_TASK_SCENES=1, otherwise refused like every other scene.
+        const char* exp_env = std::getenv("DM_EXPERIMENTAL_TASK_SCENES");
+        const bool experimental = exp_env != nullptr && exp_env[0] == '1';
+        const bool task_scene = H.sa.cfg.is_task_scene();
+        if (H.sa.cfg.scene != "imitate" && H.sa.cfg.scene != "imitate_amp" && !(task_scene && experimental))
+            throw std::runtime_error("Unsupported scene: " + H.sa.cfg.scene + " (supported: imitate, imitate_amp)");
+        if (H.sa.cfg.kin_ctrl == "clips" && H.sa.clips.size() != 1)
+            throw std::runtime_error("Unsupported kinematic controller: clips with more than one clip (clip datasets are not on the accelerated path; supported: motion)");
     } catch (const std::exception& e) { g_err = e.what(); return false; }
     if (!build_device_model(H)) return false;
     build_statics(H);
@@ -361,6 +390,7 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
     auto chk = [&](cudaError_t e, const char* what) { if (e != cudaSuccess) { g_err = std::string(what) + ": " + cudaGetErrorString(e); return false; } return true; };
     if (!chk(cudaSetDevice(device), "cudaSetDevice")) { fail(); return nullptr; }
     h->device = device; h->seed = seed; h->env_offset = global_env_offset; h->num_envs = num_envs;
+    h->hm.task_seed = seed ^ 0x7461736b73ull; h->hm.env_id_base = global_env_offset;   // the model blob is uploaded below
     const auto& M = h->hm;
     h->W = (M.nl <= 16) ? 16 : 32;   // lanes per environment: one lane per link
     if (const char* w = std::getenv("DM_TILE_WIDTH")) { int v = std::atoi(w); if (v == 32 || (v == 16 && M.nl <= 16)) h->W = v; }
@@ -409,6 +439,13 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
     for (int k = 0; k < 3 && ok; ++k) ok = chk(cudaMalloc(&h->d_inj[k], N * sizeof(double)), "cudaMalloc inject");
     if (!ok) { fail(); dm_destroy(h.release()); return nullptr; }
     h->st.pdbg = nullptr; h->st.num_envs = h->padded_envs;
+    if (M.task_kind != dmk::kTaskNone) {
+        if (!(chk(cudaMalloc(&h->st.task, N * dmk::kTaskDoubles * sizeof(double)), "cudaMalloc task") &&
+              chk(cudaMemset(h->st.task, 0, N * dmk::kTaskDoubles * sizeof(double)), "memset task") &&
+              chk(cudaMalloc(&h->d_goal, N * 3 * sizeof(float)), "cudaMalloc goal") && chk(cudaMallocHost(&h->p_goal, N * 3 * sizeof(float)), "cudaMallocHost goal"))) {
+            fail(); dm_destroy(h.release()); return nullptr;
+        }
+    }
     std::vector<float> frames(static_cast<size_t>(M.num_frames) * M.pose_dim), fvel(frames.size());
     std::vector<double> fv = build_frame_vel(h->sa.character, h->sa.motion);
     for (size_t i = 0; i < frames.size(); ++i) { frames[i] = static_cast<float>(h->sa.motion.frames[i]); fvel[i] = static_cast<float>(fv[i]); }
@@ -437,6 +474,7 @@ void dm_destroy(dm_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->st.task); cudaFree(h->d_goal); cudaFreeHost(h->p_goal);
     cudaFree(h->d_amp); cudaFreeHost(h->p_amp); cudaFree(h->st.hist); cudaFree(h->d_model); cudaFree(h->st.sim); cudaFree(h->st.time); cudaFree(h->st.flags); cudaFree(h->st.manifold);
     cudaFree(h->d_frame_times); cudaFree(h->d_frames); cudaFree(h->d_frame_vel); cudaFree(h->d_flags4); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew);
     for (auto& p : h->d_inj) cudaFree(p);
@@ -447,7 +485,7 @@ void dm_destroy(dm_handle* h) {
 
 int dm_get_dims(dm_handle* h, dm_dims* o) {
     const auto& M = h->hm;
-    o->num_envs = h->num_envs; o->num_joints = M.nl; o->pose_dim = M.pose_dim; o->num_dofs = M.n; o->state_size = M.state_size; o->goal_size = 0; o->amp_obs_size = M.amp_obs_size;
+    o->num_envs = h->num_envs; o->num_joints = M.nl; o->pose_dim = M.pose_dim; o->num_dofs = M.n; o->state_size = M.state_size; o->goal_size = M.task_kind != dmk::kTaskNone ? 3 : 0; o->amp_obs_size = M.amp_obs_size;
     o->action_size = M.action_size; o->snapshot_size = 29 + 59 * M.nl;
     o->num_update_substeps = h->sa.cfg.num_update_substeps;
     o->updates_per_action = 20;
@@ -502,7 +540,13 @@ int dm_reset(dm_handle* h, int force_all, const double* kt, const double* mt, co
         DM_CUDA(cudaStreamSynchronize(h->stream));
         dev[k] = h->d_inj[k];
     }
-    return h->W == 16 ? launch_reset<16>(h, force_all, dev[0], dev[1], dev[2]) : launch_reset<32>(h, force_all, dev[0], dev[1], dev[2]);
+    if (h->W == 16 ? launch_reset<16>(h, force_all, dev[0], dev[1], dev[2]) : launch_reset<32>(h, force_all, dev[0], dev[1], dev[2])) return 1;
+    if (h->hm.task_kind != dmk::kTaskNone) {   // cSceneTargetAMP::Reset's own part for the environments that were just reset
+        dmk::dm_task_reset_kernel<<<(h->padded_envs + 127) / 128, 128, 0, h->stream>>>(h->d_model, h->st, h->padded_envs);
+        DM_CUDA(cudaGetLastError());
+        h->launches++;
+    }
+    return 0;
 }
 int dm_set_action(dm_handle* h, const float* d_actions) {
     DM_DEVICE(h);
@@ -521,12 +565,59 @@ int dm_update(dm_handle* h, double dt, int n_updates) {
     if (h->W == 16) return dbg ? launch_update<16, true>(h, dt, n_updates) : launch_update<16, false>(h, dt, n_updates);
     return dbg ? launch_update<32, true>(h, dt, n_updates) : launch_update<32, false>(h, dt, n_updates);
 }
+static int launch_task_observe(dm_handle* h, float* d_goal, float* d_reward) {
+    dmk::dm_task_observe_kernel<<<(h->num_envs + 127) / 128, 128, 0, h->stream>>>(h->d_model, h->st, d_goal, d_reward, h->num_envs);
+    DM_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
 int dm_observe(dm_handle* h, float* d_state, float* d_reward) {
     DM_DEVICE(h);
-    return h->W == 16 ? launch_observe<16>(h, d_state, d_reward) : launch_observe<32>(h, d_state, d_reward);
+    const bool task = h->hm.task_kind != dmk::kTaskNone;   // the task scenes replace CalcReward (SceneTargetAMP.cpp:3-80, SceneHeadingAMP.cpp:3-48)
+    float* d_imitate_reward = task ? nullptr : d_reward;
+    if (d_state != nullptr || d_imitate_reward != nullptr)
+        if (h->W == 16 ? launch_observe<16>(h, d_state, d_imitate_reward) : launch_observe<32>(h, d_state, d_imitate_reward)) return 1;
+    if (task && d_reward != nullptr) return launch_task_observe(h, nullptr, d_reward);
+    return 0;
 }
 int dm_record_state(dm_handle* h, float* d_out) { return dm_observe(h, d_out, nullptr); }
-int dm_record_goal(dm_handle*, float*) { return 0; }
+int dm_record_goal(dm_handle* h, float* d_out) {
+    if (h->hm.task_kind == dmk::kTaskNone) return 0;
+    DM_DEVICE(h);
+    return launch_task_observe(h, d_out, nullptr);
+}
+int dm_goal_host(dm_handle* h, float* h_out) {
+    if (h->hm.task_kind == dmk::kTaskNone) return 0;
+    DM_DEVICE(h);
+    if (launch_task_observe(h, h->d_goal, nullptr)) return 1;
+    DM_CUDA(cudaMemcpyAsync(h->p_goal, h->d_goal, static_cast<size_t>(h->num_envs) * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    DM_CUDA(cudaStreamSynchronize(h->stream));
+    std::memcpy(h_out, h->p_goal, static_cast<size_t>(h->num_envs) * 3 * sizeof(float));
+    return 0;
+}
+// test hooks of the task scenes: the environment's task block (dm_task.cuh: TaskSlot) and the scene constants as the device sees them
+int dm_get_task_state(dm_handle* h, int env, double* h_out) {
+    if (h->hm.task_kind == dmk::kTaskNone) { g_err = "dm_get_task_state: not a task scene"; return fail(); }
+    DM_DEVICE(h);
+    DM_CUDA(cudaStreamSynchronize(h->stream));
+    DM_CUDA(cudaMemcpy(h_out, h->st.task + static_cast<size_t>(env) * dmk::kTaskDoubles, dmk::kTaskDoubles * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int dm_set_task_state(dm_handle* h, int env, const double* h_in) {
+    if (h->hm.task_kind == dmk::kTaskNone) { g_err = "dm_set_task_state: not a task scene"; return fail(); }
+    DM_DEVICE(h);
+    DM_CUDA(cudaStreamSynchronize(h->stream));
+    DM_CUDA(cudaMemcpy(h->st.task + static_cast<size_t>(env) * dmk::kTaskDoubles, h_in, dmk::kTaskDoubles * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+int dm_get_task_params(dm_handle* h, double* o, unsigned long long* stream) {
+    const dmk::TaskParams& T = h->hm.task;
+    o[0] = h->hm.task_kind; o[1] = T.timer_min; o[2] = T.timer_max; o[3] = T.max_target_dist; o[4] = T.target_succ_dist; o[5] = T.tar_fail_dist; o[6] = T.pos_reward_scale;
+    o[7] = T.max_heading_turn_rate; o[8] = T.sharp_turn_prob; o[9] = T.speed_change_prob; o[10] = T.tar_speed_min; o[11] = T.tar_speed_max; o[12] = T.vel_reward_scale;
+    o[13] = T.tar_speed; o[14] = T.enable_min_tar_vel; o[15] = 0;
+    if (stream) { stream[0] = h->hm.task_seed; stream[1] = h->hm.env_id_base; }
+    return 0;
+}
 static int launch_amp(dm_handle* h, float* d_out, int expert, const double* d_times) {
     constexpr int BLOCK = 64;
     if (h->W == 16) dmk::dm_amp_obs_kernel<16, BLOCK><<<h->padded_envs / (BLOCK / 16), BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, d_out, expert, d_times, h->num_envs);

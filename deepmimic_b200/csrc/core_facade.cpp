@@ -90,7 +90,14 @@ public:
         const float* s = &mState[static_cast<size_t>(Env(agent_id)) * mDims.state_size];
         return std::vector<double>(s, s + mDims.state_size);
     }
-    virtual std::vector<double> RecordGoal(int) const { return std::vector<double>(); }
+    virtual std::vector<double> RecordGoal(int agent_id) {
+        if (mDims.goal_size == 0) return std::vector<double>();
+        FlushActions();
+        std::vector<float> buf(static_cast<size_t>(mNumEnvs) * mDims.goal_size);
+        Check(dm_goal_host(mHandle, buf.data()));
+        const float* p = &buf[static_cast<size_t>(Env(agent_id)) * mDims.goal_size];
+        return std::vector<double>(p, p + mDims.goal_size);
+    }
     virtual void SetAction(int agent_id, const std::vector<double>& action) {
         if (static_cast<int>(action.size()) != mDims.action_size) Fatal("SetAction: wrong action size");
         float* a = &mActions[static_cast<size_t>(Env(agent_id)) * mDims.action_size];
@@ -105,8 +112,8 @@ public:
     virtual int GetNumActions(int) const { return 0; }
     virtual std::vector<double> BuildStateOffset(int) const { return Static(DM_STATE_OFFSET, mDims.state_size); }
     virtual std::vector<double> BuildStateScale(int) const { return Static(DM_STATE_SCALE, mDims.state_size); }
-    virtual std::vector<double> BuildGoalOffset(int) const { return std::vector<double>(); }
-    virtual std::vector<double> BuildGoalScale(int) const { return std::vector<double>(); }
+    virtual std::vector<double> BuildGoalOffset(int) const { return std::vector<double>(mDims.goal_size, 0.0); }   // RLSceneSimChar.cpp:111-116
+    virtual std::vector<double> BuildGoalScale(int) const { return std::vector<double>(mDims.goal_size, 1.0); }
     virtual std::vector<double> BuildActionOffset(int) const { return Static(DM_ACTION_OFFSET, mDims.action_size); }
     virtual std::vector<double> BuildActionScale(int) const { return Static(DM_ACTION_SCALE, mDims.action_size); }
     virtual std::vector<double> BuildActionBoundMin(int) const { return Static(DM_ACTION_BOUND_MIN, mDims.action_size); }
@@ -115,13 +122,13 @@ public:
         std::vector<double> g = Static(DM_STATE_NORM_GROUPS, mDims.state_size);
         return std::vector<int>(g.begin(), g.end());
     }
-    virtual std::vector<int> BuildGoalNormGroups(int) const { return std::vector<int>(); }
+    virtual std::vector<int> BuildGoalNormGroups(int) const { return std::vector<int>(mDims.goal_size, 0); }
     virtual double CalcReward(int agent_id) { Refresh(); return mReward[Env(agent_id)]; }
     virtual double GetRewardMin(int) const { return 0; }
     virtual double GetRewardMax(int) const { return 1; }
     virtual double GetRewardFail(int) const { return 0; }
     virtual double GetRewardSucc(int) const { return 1; }
-    virtual bool EnableAMPTaskReward() const { return false; }
+    virtual bool EnableAMPTaskReward() const { return mDims.goal_size > 0; }   // true in the task scenes (SceneTargetAMP.cpp:222-225)
     virtual int GetAMPObsSize() const { return mDims.amp_obs_size; }
     virtual std::vector<double> GetAMPObsOffset() const { return std::vector<double>(mDims.amp_obs_size, 0.0); }   // SceneImitateAMP.cpp:86-89
     virtual std::vector<double> GetAMPObsScale() const { return std::vector<double>(mDims.amp_obs_size, 1.0); }    // :91-94

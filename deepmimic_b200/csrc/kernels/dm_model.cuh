@@ -11,6 +11,8 @@
 
 #include "dm_math.cuh"
 
+#include "dm_task.cuh"
+
 namespace dmk {
 
 constexpr int kMaxLinks = 32;   // one lane per link
@@ -61,6 +63,10 @@ struct DevModel {
     float total_mass;
     double motion_dur, cycle_period, query_dt, time_lim_min, time_lim_max, time_end_lim_max;
     float cycle_delta[3];
+    // AMP task scenes (dm_task.cuh); task_kind == kTaskNone for imitate / imitate_amp
+    int task_kind;
+    TaskParams task;
+    unsigned long long task_seed, env_id_base;   // draw stream: u01(task_seed, env_id_base + env, k)
     DevLink link[kMaxLinks];
     uint8_t chain_dof[kMaxLinks][kMaxChain];  // dof index at chain depth d on the path base -> link (valid for d <= last depth of link)
     uint8_t dof_depth[kMaxDofs];
@@ -89,6 +95,7 @@ struct DevState {
     float* manifold;
     float* hist;  // AMP history: DeepMimic pose | vel vectors (2 * pose_dim floats per env) of the simulated character at the last applied action
     float* pdbg;  // optional debug scratch (n x ...), may be null
+    double* task; // AMP task scenes: kTaskDoubles per env (dm_task.cuh), null otherwise
     int num_envs;
 };
 

@@ -588,6 +588,51 @@ __global__ void __launch_bounds__(BLOCK) dm_reset_kernel(const DevModel* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------- AMP task scenes
+// One thread per environment; the per-update part of the task logic runs inside dm_step_kernel<.., TASK = true> (dm_task.cuh).
+// NOT YET RUN ON HARDWARE (written after round 1's GPU budget was spent): the scenes stay refused by dm_create unless
+// DM_EXPERIMENTAL_TASK_SCENES=1, and their GPU parity tests are opt-in.
+
+// After dm_reset_kernel: environments whose reset counter moved get cSceneTargetAMP::Reset's part (SceneTargetAMP.cpp:129-134):
+// target timer, target position around the new root, heading 0 and a fresh speed (heading scene), previous-action COM 0.
+__global__ void dm_task_reset_kernel(const DevModel* __restrict__ gm, DevState st, int num_envs) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= num_envs) return;
+    const DevModel& M = *gm;
+    double* tk = st.task + static_cast<size_t>(env) * kTaskDoubles;
+    const int* fl = st.flags + static_cast<size_t>(env) * kFlagInts;
+    if (static_cast<double>(fl[7]) == tk[kKResetSeen]) return;
+    const float* sim = st.sim + static_cast<size_t>(env) * sim_stride(M.nl);
+    TaskRng rng{M.task_seed, M.env_id_base + static_cast<unsigned long long>(env), tk + kKCounter};
+    task_reset(M.task_kind, M.task, tk, rng, static_cast<double>(sim[0]) / M.scale, static_cast<double>(sim[2]) / M.scale);
+    tk[kKCom] = tk[kKCom + 1] = tk[kKCom + 2] = 0.0;
+    tk[kKResetSeen] = static_cast<double>(fl[7]);
+}
+
+// RecordGoal ([N x 3], SceneTargetAMP.cpp:185-215 / SceneHeadingAMP.cpp:136-151) and CalcReward ([N], SceneTargetAMP.cpp:3-80 /
+// SceneHeadingAMP.cpp:3-48) from the committed base state and the task block.  Either pointer may be null.
+__global__ void dm_task_observe_kernel(const DevModel* __restrict__ gm, DevState st, float* __restrict__ goal, float* __restrict__ reward, int num_real_envs) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= num_real_envs) return;
+    const DevModel& M = *gm;
+    const double* tk = st.task + static_cast<size_t>(env) * kTaskDoubles;
+    const double* tm = st.time + static_cast<size_t>(env) * kTimeDoubles;
+    const int* fl = st.flags + static_cast<size_t>(env) * kFlagInts;
+    const float* sim = st.sim + static_cast<size_t>(env) * sim_stride(M.nl);
+    const double rx = static_cast<double>(sim[0]) / M.scale, rz = static_cast<double>(sim[2]) / M.scale;
+    if (goal != nullptr) {
+        // heading of the root joint (cKinTree::CalcHeading): the root rotation is the inverse of the stored world->base quaternion
+        const double qx = -static_cast<double>(sim[4]), qy = -static_cast<double>(sim[5]), qz = -static_cast<double>(sim[6]), qw = static_cast<double>(sim[7]);
+        const double hx = 1.0 - 2.0 * (qy * qy + qz * qz), hz = 2.0 * (qx * qz - qw * qy);   // rotate (1, 0, 0)
+        double g[3];
+        task_goal(M.task_kind, tk, rx, rz, atan2(-hz, hx), g);
+        float* o = goal + static_cast<size_t>(env) * 3;
+        o[0] = static_cast<float>(g[0]); o[1] = static_cast<float>(g[1]); o[2] = static_cast<float>(g[2]);
+    }
+    if (reward != nullptr)
+        reward[env] = static_cast<float>(task_reward(M.task_kind, M.task, tk, fl[kFFallen] != 0, rx, rz, tm[kTCtrl] - tm[kTPrevAct]));
+}
+
 template __global__ void dm_observe_kernel<16, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
 template __global__ void dm_observe_kernel<32, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
 template __global__ void dm_amp_obs_kernel<16, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int);

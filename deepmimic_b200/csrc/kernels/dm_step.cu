@@ -539,6 +539,17 @@ __device__ __forceinline__ const StepLayout& lay_of(const Ctx& c) { return *rein
 __device__ __forceinline__ S6 shift_m(S6 m, V3 c) { return mks(m.a, m.l + cross(m.a, c)); }   // motion vector: reference point moved by +c
 __device__ __forceinline__ S6 shift_f(S6 f, V3 c) { return mks(f.a + cross(c, f.l), f.l); }   // force vector: child pivot -> parent pivot (child = parent + c)
 __device__ __forceinline__ float cl100(float v) { return fminf(fmaxf(v, -100.f), 100.f); }   // applyDeltaVeeMultiDof clamp
+// cSimCharacter::CalcCOM (SimCharacter.cpp:398-416) over the lanes of one environment: w = this link's sW entry (pivot at [9..11]),
+// v = its sV entry (pivot -> COM at [6..8]), both as left by kin_pass; returns the unscaled COM on every lane of the tile
+template <int W>
+__device__ __forceinline__ V3 tile_com(const float* w, const float* v, float mass, float inv_total) {
+    float cx = mass * (w[9] + v[6]), cy = mass * (w[10] + v[7]), cz = mass * (w[11] + v[8]);
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) {
+        cx += __shfl_xor_sync(0xffffffffu, cx, o, W); cy += __shfl_xor_sync(0xffffffffu, cy, o, W); cz += __shfl_xor_sync(0xffffffffu, cz, o, W);
+    }
+    return mk3(cx * inv_total, cy * inv_total, cz * inv_total);
+}
 
 // Forward kinematics and link velocities, root -> leaves.  Writes per link: world->link rotation + pivot (sW), joint axes in world axes +
 // parent pivot -> pivot (sS), spatial velocity at the pivot + pivot -> COM (sV).  Base state is read from sB by lane 0.
@@ -995,7 +1006,7 @@ __device__ __noinline__ void vel_pass(Ctx c, float jvx, float jvy, float jvz, bo
     __syncwarp();
 }
 
-template <int W, bool DEBUG>
+template <int W, bool DEBUG, bool TASK>
 __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevModel* __restrict__ gm, DevState st, const double* __restrict__ frame_times,
                                                                        const float* __restrict__ frames, double dt, int n_updates, int sim_substeps, StepLayout LY, int sync_mode) {
     using T = Tl<W>;
@@ -1074,6 +1085,9 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     double* tm = st.time + static_cast<size_t>(env) * kTimeDoubles;
     int* fl = st.flags + static_cast<size_t>(env) * kFlagInts;
     float* mani = st.manifold + static_cast<size_t>(env) * nl * kManifoldFloats;
+    // AMP task scenes (TASK instantiations only): the environment's task block, advanced by lane 0 after every update (dm_task.cuh)
+    double* tk = nullptr;
+    if constexpr (TASK) tk = st.task + static_cast<size_t>(env) * kTaskDoubles;
     float* sB = sG + 21;   // base state, owned by lane 0: position [0..2], quaternion (world->base) [3..6], omega_w [7..9], v_w [10..12]
     if (lane == 0) {
         float4 b0 = reinterpret_cast<const float4*>(sim)[0], b1 = reinterpret_cast<const float4*>(sim)[1], b2 = reinterpret_cast<const float4*>(sim)[2],
@@ -1141,9 +1155,25 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             float mx = fmaxf(fmaxf(fmaxf(fabsf(vw.x), fabsf(vw.y)), fabsf(vw.z)), fmaxf(fmaxf(fabsf(wa.x), fabsf(wa.y)), fabsf(wa.z)));
             const unsigned eb = __ballot_sync(0xffffffffu, act && mx > 100.f);
             const unsigned eseg = (W == 32) ? eb : ((eb >> (threadIdx.x & 16)) & 0xffffu);
+            int task_fail = 0;
+            if constexpr (TASK) {
+                // cSceneTargetAMP::Update: target timer / position / heading / speed after the scene update, then the distance failure of
+                // CheckTerminate; the COM is kept for CalcReward (SceneTargetAMP.cpp:3-80,136-145,294-319)
+                const V3 com = tile_com<W>(E + LY.oW + li * 12, v, act ? LKo[kLM] : 0.f, 1.0f / (M.total_mass * scale));
+                int tf = 0;
+                if (lane == 0 && alive) {
+                    TaskRng rng{M.task_seed, M.env_id_base + static_cast<unsigned long long>(env), tk + kKCounter};
+                    const double rx = static_cast<double>(sB[0]) / M.scale, rz = static_cast<double>(sB[2]) / M.scale;
+                    task_update(M.task_kind, M.task, tk, rng, dt, rx, rz);
+                    tk[kKCom] = com.x; tk[kKCom + 1] = com.y; tk[kKCom + 2] = com.z;
+                    tf = task_dist_fail(M.task_kind, M.task, tk, rx, rz) ? 1 : 0;
+                }
+                task_fail = T::shfli(tf, 0);
+            }
             if (alive) {
                 int term = (M.enable_fall_end && fallen) ? 1 : 0;
                 if (!term && (cbits & 4)) term = 1;
+                if (TASK && !term && task_fail) term = 1;
                 f_updates++;
                 const bool end = (cbits & 2) || term;
                 if (end || stage == total_stages) {   // commit
@@ -1173,6 +1203,13 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         if (ph == 0) {
             // ---------------- clocks: cScene::Update, cSceneImitate::UpdateKinChar, cDeepMimicCharController::UpdateCalcTau
             int cb = 0;
+            if constexpr (TASK) {
+                // cDeepMimicCharController::HandleNewAction (DeepMimicCharController.cpp:262-267): COM of the state the new action starts from
+                if (__ballot_sync(0xffffffffu, alive && need_action) != 0u) {
+                    const V3 com = tile_com<W>(E + LY.oW + li * 12, sV + li * 12, act ? LKo[kLM] : 0.f, 1.0f / (M.total_mass * scale));
+                    if (lane == 0 && alive && need_action) { tk[kKPrevCom] = com.x; tk[kKPrevCom + 1] = com.y; tk[kKPrevCom + 2] = com.z; }
+                }
+            }
             if (lane == 0 && alive) {
                 const double timer = tm[kTTimer] + dt;
                 double kin_time = tm[kTKin];
@@ -1345,9 +1382,12 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
 }
 
 // explicit instantiations used by capi.cu: (tile width, debug dumps)
-template __global__ void dm_step_kernel<16, false>(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
-template __global__ void dm_step_kernel<32, false>(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
-template __global__ void dm_step_kernel<16, true>(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
-template __global__ void dm_step_kernel<32, true>(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
+template __global__ void dm_step_kernel<16, false, false>(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
+template __global__ void dm_step_kernel<32, false, false>(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
+template __global__ void dm_step_kernel<16, true, false>(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
+template __global__ void dm_step_kernel<32, true, false>(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
+// AMP task scenes (target_amp / heading_amp): same step with the task block advanced after every update
+template __global__ void dm_step_kernel<16, false, true>(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
+template __global__ void dm_step_kernel<32, false, true>(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
 
 }  // namespace dmk

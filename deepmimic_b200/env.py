@@ -88,7 +88,17 @@ class DeepMimicBatchEnv:
         return self._obs
 
     def record_goal(self, agent_id=0):
-        return self.torch.zeros(self.num_envs, 0, device=self.device)
+        """[N, goal_size] float32 (goal_size 0 outside the AMP task scenes, 3 in target_amp / heading_amp)."""
+        g = self._core.dims.goal_size
+        if g == 0:
+            return self.torch.zeros(self.num_envs, 0, device=self.device)
+        if getattr(self, "_goal", None) is None:
+            with self.torch.cuda.stream(self.stream):
+                self._goal = self.torch.zeros(self.num_envs, g, device=self.device)
+        self._pre()
+        self._core.record_goal(self._goal)
+        self._post()
+        return self._goal
 
     def set_action(self, agent_id_or_actions, actions=None):
         a = agent_id_or_actions if actions is None else actions
@@ -106,6 +116,9 @@ class DeepMimicBatchEnv:
     # ---- AMP observations (R/env/deepmimic_env.py:147-166)
     def get_amp_obs_size(self):
         return self._core.dims.amp_obs_size
+
+    def enable_amp_task_reward(self):
+        return self._core.dims.goal_size > 0                # cSceneTargetAMP::EnableAMPTaskReward (SceneTargetAMP.cpp:222-225); false in imitate_amp
 
     def get_amp_obs_offset(self):
         return np.zeros(self.get_amp_obs_size())
@@ -170,10 +183,10 @@ class DeepMimicBatchEnv:
         return np.array(self._core.static(DM_STATE_SCALE))
 
     def build_goal_offset(self, agent_id=0):
-        return np.zeros(0)
+        return np.zeros(self._core.dims.goal_size)          # cRLSceneSimChar::BuildGoalOffsetScale (RLSceneSimChar.cpp:111-116)
 
     def build_goal_scale(self, agent_id=0):
-        return np.zeros(0)
+        return np.ones(self._core.dims.goal_size)
 
     def build_action_offset(self, agent_id=0):
         return np.array(self._core.static(DM_ACTION_OFFSET))
@@ -191,7 +204,7 @@ class DeepMimicBatchEnv:
         return np.array(self._core.static(DM_STATE_NORM_GROUPS), dtype=np.int32)
 
     def build_goal_norm_groups(self, agent_id=0):
-        return np.zeros(0, dtype=np.int32)
+        return np.zeros(self._core.dims.goal_size, dtype=np.int32)   # gNormGroupSingle (RLSceneSimChar.cpp:136-140)
 
     def get_reward_min(self, agent_id=0):
         return 0.0

@@ -89,6 +89,15 @@ int dm_set_action(dm_handle* h, const float* d_actions);
 int dm_update(dm_handle* h, double dt, int n_updates);
 int dm_record_state(dm_handle* h, float* d_out);             /* [num_envs x state_size] */
 int dm_record_goal(dm_handle* h, float* d_out);              /* [num_envs x goal_size] (no-op when goal_size == 0) */
+/* AMP task scenes target_amp / heading_amp (cSceneTargetAMP / cSceneHeadingAMP: RecordGoal, CalcReward, target updates; goal_size 3).
+ * EXPERIMENTAL: the device code is written but has not run on hardware; dm_create accepts these scenes only with
+ * DM_EXPERIMENTAL_TASK_SCENES=1 in the environment.  dm_goal_host is RecordGoal into a host buffer [num_envs x 3]; the task-state hooks
+ * expose one environment's task block (16 doubles: target x, z, speed, heading, timer, timer max, previous-action COM[3], COM[3], draw
+ * counter, reset counter) and the scene constants + draw-stream key for the parity tests. */
+int dm_goal_host(dm_handle* h, float* h_out);
+int dm_get_task_state(dm_handle* h, int env, double* h_out16);
+int dm_set_task_state(dm_handle* h, int env, const double* h_in16);
+int dm_get_task_params(dm_handle* h, double* h_out16, unsigned long long* h_stream2);
 int dm_calc_reward(dm_handle* h, float* d_out);              /* [num_envs] */
 /* AMP observations (RecordAMPObsAgent / RecordAMPObsExpert, DeepMimicCore.h:81-82; cSceneImitateAMP::BuildAMPObs): [num_envs x amp_obs_size].
  * Agent: simulated pose / vel now and at the last dm_set_action (call dm_set_action exactly when need_new_action is set, like the

@@ -309,3 +309,98 @@ def test_pretrained_heading_policy_follows_heading_and_speed_in_the_oracle(seed,
                                                        seed, clip, t0, theta)
     assert n == 600 and not fallen, (n, fallen)
     assert mean_r > 0.8, mean_r
+
+
+# ------------------------------------------------------------------------------------------------ device-side task logic, run on the host
+@pytest.fixture(scope="module")
+def task_shim(tmp_path_factory):
+    """deepmimic_b200/csrc/kernels/dm_task.cuh (what the TASK instantiation of dm_step_kernel and the dm_task_* kernels execute per
+    environment) compiled with g++ through tests/task_shim.cpp."""
+    import ctypes as C
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = str(tmp_path_factory.mktemp("shim") / "libtask_shim.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", os.path.join(here, "task_shim.cpp"), "-o", so])
+    L = C.CDLL(so)
+    d, dp_, u64 = C.c_double, C.POINTER(C.c_double), C.c_uint64
+    L.shim_reset.argtypes = [dp_, dp_, u64, u64, d, d]
+    L.shim_update.argtypes = [dp_, dp_, u64, u64, d, d, d]
+    L.shim_dist_fail.argtypes = [dp_, dp_, d, d]
+    L.shim_goal.argtypes = [dp_, dp_, d, d, d, dp_]
+    L.shim_reward.argtypes = [dp_, dp_, C.c_int, d, d, d]
+    L.shim_reward.restype = d
+    return L
+
+
+def _ptr(a):
+    import ctypes as C
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@pytest.mark.parametrize("args", [TARGET, HEADING])
+def test_device_task_logic_matches_the_oracle_on_the_host(asset_root, task_shim, args, monkeypatch):
+    """Drives dm_task.cuh (host build) with the oracle's root positions and compares the whole task block, the goal, the reward and the
+    distance failure with the oracle after every update of a 6 s episode under a random policy.  Also checks that the C-ABI host loader
+    fills the scene constants the device code receives."""
+    from deepmimic_b200 import capi
+    monkeypatch.setenv("DM_EXPERIMENTAL_TASK_SCENES", "1")
+    single = ["--kin_ctrl", "motion", "--motion_file", "data/motions/humanoid3d_run.txt"] + args[2:]   # the device path takes one clip for now
+    if args is TARGET:
+        single = ["--rand_target_time_min", "1", "--rand_target_time_max", "2", "--tar_fail_dist", "6"] + single   # several re-targets and a distance failure in 6 s
+    hm = capi.HostModel(single, asset_root)
+    P, _, _ = hm.task_params()
+    assert hm.dims.goal_size == 3 and P[0] == (1 if args is TARGET else 2)
+    o = Oracle(single, asset_root)
+    seed, env = 99, 1234
+    o.set_task_stream(seed, env, 0)
+    o.reset(0.2, 0.9, 20.0)
+    t = np.zeros(16)
+    root = o.get_pose()[0][:3]
+    task_shim.shim_reset(_ptr(P), _ptr(t), seed, env, root[0], root[2])
+
+    def compare():
+        ts = o.task_state()
+        want = np.array([ts["target_pos"][0], ts["target_pos"][2], ts["target_speed"], ts["target_heading"], ts["timer"], ts["timer_max"]])
+        # the reset target hangs off cSimCharacter::GetRootPos (float Bullet state); the shim is fed the double pose the oracle was reset with
+        np.testing.assert_allclose(t[:2], want[:2], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(t[2:6], want[2:], rtol=0, atol=1e-12)
+        assert int(t[12]) == o.task_counter()
+    compare()
+    rng = np.random.default_rng(0)
+    st = o.action_statics()
+    n_goal = n_far = 0
+    for k in range(3600):
+        if o.need_new_action():
+            pose = o.get_pose()[0]
+            com = o.calc_com()
+            ts = o.task_state()
+            t[6:9] = ts["prev_action_com"]; t[9:12] = com
+            g = np.zeros(3)
+            task_shim.shim_goal(_ptr(P), _ptr(t), pose[0], pose[2], heading_of(pose), _ptr(g))
+            np.testing.assert_allclose(g, o.record_goal(), atol=1e-12)
+            if k > 0:
+                r = task_shim.shim_reward(_ptr(P), _ptr(t), int(o.has_fallen()), pose[0], pose[2], 19.0 / 600.0)
+                assert r == pytest.approx(o.calc_reward(), abs=1e-9)
+            n_goal += 1
+            o.set_action(np.clip(-st[0] + 0.1 / st[1] * rng.standard_normal(o.action_size), st[2], st[3]))
+        o.update(1.0 / 600.0)
+        root = o.get_pose()[0][:3]
+        task_shim.shim_update(_ptr(P), _ptr(t), seed, env, 1.0 / 600.0, root[0], root[2])
+        compare()
+        tp = o.task_state()["target_pos"]
+        too_far = args is TARGET and (root[0] - tp[0]) ** 2 + (root[2] - tp[2]) ** 2 > P[5] ** 2
+        assert task_shim.shim_dist_fail(_ptr(P), _ptr(t), root[0], root[2]) == (1 if too_far else 0)
+        if too_far:
+            n_far += 1
+            assert o.check_terminate() == 1
+    assert n_goal == 180 and o.task_counter() > (3 if args is TARGET else 50) and (n_far > 0) == (args is TARGET)
+
+
+def test_task_scenes_stay_refused_without_the_opt_in(asset_root, monkeypatch):
+    from deepmimic_b200 import capi
+    monkeypatch.delenv("DM_EXPERIMENTAL_TASK_SCENES", raising=False)
+    with pytest.raises(RuntimeError, match="Unsupported scene"):
+        capi.HostModel(["--kin_ctrl", "motion", "--motion_file", "data/motions/humanoid3d_run.txt"] + TARGET[2:], asset_root)
+    monkeypatch.setenv("DM_EXPERIMENTAL_TASK_SCENES", "1")
+    with pytest.raises(RuntimeError, match="more than one clip"):
+        capi.HostModel(TARGET, asset_root)                                      # clip datasets are oracle-only so far

@@ -1,0 +1,73 @@
+"""GPU parity tests of the AMP task scenes (target_amp / heading_amp) against the oracle.
+
+OPT-IN: the device half of these scenes (dm_task.cuh inside dm_step_kernel<.., TASK>, dm_task_reset_kernel, dm_task_observe_kernel) was
+written after round 1's GPU budget was spent and has never run on hardware.  dm_create refuses the scenes unless
+DM_EXPERIMENTAL_TASK_SCENES=1; these tests additionally need DM_RUN_UNVALIDATED_GPU_TESTS=1 so that the default `pytest -m gpu` run only
+contains tests of code that has been validated on a B200.  Round 2: run with both variables set, fix what breaks, then drop the gates."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.oracle_binding import Oracle
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("DM_RUN_UNVALIDATED_GPU_TESTS") != "1", reason="task-scene device code not yet validated on hardware (opt-in)")]
+
+SINGLE = ["--kin_ctrl", "motion", "--motion_file", "data/motions/humanoid3d_run.txt"]
+TARGET = ["--rand_target_time_min", "1", "--rand_target_time_max", "2"] + SINGLE + ["--arg_file", "args/train_amp_target_humanoid3d_locomotion_args.txt"]
+HEADING = SINGLE + ["--arg_file", "args/train_amp_heading_humanoid3d_locomotion_args.txt"]
+N = 32
+
+
+@pytest.mark.parametrize("args", [TARGET, HEADING])
+def test_task_goal_reward_and_updates_match_the_oracle(asset_root, args, monkeypatch):
+    """Free-running comparison over 3 s under one random action sequence per environment: same draw stream (seed, global env id), so the
+    target timers, headings and speeds must agree exactly in count and to rounding in value; goals and rewards to the fp32 state's accuracy."""
+    import torch
+    from deepmimic_b200 import capi
+    monkeypatch.setenv("DM_EXPERIMENTAL_TASK_SCENES", "1")
+    core = capi.BatchedCore(args, N, asset_root, seed=21, global_env_offset=100)
+    P, task_seed, env_base = core.task_params()
+    assert core.dims.goal_size == 3 and env_base == 100
+    kin_time = np.linspace(0.0, 0.7, N); theta = np.linspace(-3.0, 3.0, N); max_time = np.full(N, 20.0)
+    core.reset(force_all=True, kin_time=kin_time, max_time=max_time, rot_theta=theta)
+    oracles = []
+    for e in range(N):
+        o = Oracle(args, asset_root)
+        o.set_task_stream(task_seed, env_base + e, 0)
+        o.reset(kin_time[e], theta[e], 20.0)
+        oracles.append(o)
+    goal = torch.zeros(N, 3, device="cuda"); rew = torch.zeros(N, device="cuda"); flags = torch.zeros(N, 4, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(5)
+    st = oracles[0].action_statics()
+    worst_goal = worst_rew = 0.0
+    for step in range(90):
+        core.record_goal(goal); core.observe(None, rew); core.flags(flags); core.sync()
+        g, r, f = goal.cpu().numpy(), rew.cpu().numpy(), flags.cpu().numpy()
+        for e, o in enumerate(oracles):
+            if f[e, 1] or o.is_episode_end():
+                assert bool(f[e, 1]) == o.is_episode_end(), (step, e)
+                continue
+            tb = core.task_state(e); ts = o.task_state()
+            assert int(tb[12]) == o.task_counter(), (step, e)                               # same number of draws consumed
+            np.testing.assert_allclose(tb[2:6], [ts["target_speed"], ts["target_heading"], ts["timer"], ts["timer_max"]], atol=1e-9)
+            np.testing.assert_allclose([tb[0], tb[1]], ts["target_pos"][[0, 2]], atol=2e-3)  # target = root position (fp32 sim state) + draw
+            og = o.record_goal()
+            worst_goal = max(worst_goal, float(np.abs(g[e] - og).max()))
+            if step > 0:
+                worst_rew = max(worst_rew, abs(float(r[e]) - o.calc_reward()))
+        a = np.clip(-st[0] + 0.1 / st[1] * rng.standard_normal((N, oracles[0].action_size)), st[2], st[3])
+        core.set_action(torch.as_tensor(a, dtype=torch.float32, device="cuda"))
+        torch.cuda.synchronize()
+        core.update(1.0 / 600.0, 20)
+        for e, o in enumerate(oracles):
+            if not o.is_episode_end():
+                o.set_action(a[e].astype(np.float32).astype(np.float64))
+                for _ in range(20):
+                    o.update(1.0 / 600.0)
+                    if o.is_episode_end():
+                        break
+    assert worst_goal < 5e-3 and worst_rew < 1e-2, (worst_goal, worst_rew)
+    core.close()
