@@ -188,8 +188,13 @@ class BatchedRollout:
         import torch
         self.torch, self.env = torch, env
         dev = env.device
-        S, A = env.get_state_size(), env.get_action_size()
-        self.policy = (policy or build_policy(S, A, noise=noise)).to(dev)
+        S, A, G = env.get_state_size(), env.get_action_size(), env.get_goal_size()
+        self.goal_size = G
+        # goal-conditioned scenes (AMP tasks) use the reference's gated actor; everything else the plain 1024-512 MLP
+        self.policy = (policy or (build_gated_policy(S, G, A, noise=noise) if G > 0 else build_policy(S, A, noise=noise))).to(dev)
+        if G > 0:
+            self.g_norm = DeviceNormalizer(G, env.build_goal_norm_groups(), device=dev)
+            self.g_norm.set_mean_std(-env.build_goal_offset(), 1.0 / env.build_goal_scale())
         self.s_norm = DeviceNormalizer(S, env.build_state_norm_groups(), device=dev)
         self.s_norm.set_mean_std(-env.build_state_offset(), 1.0 / env.build_state_scale())
         self.a_norm = DeviceNormalizer(A, device=dev)
@@ -208,6 +213,9 @@ class BatchedRollout:
         out = dict(states=t.empty(num_steps, N, S, device=env.device), actions=t.empty(num_steps, N, A, device=env.device),
                    logps=t.empty(num_steps, N, device=env.device), rewards=t.empty(num_steps, N, device=env.device),
                    dones=t.empty(num_steps, N, dtype=t.bool, device=env.device), terminate=t.empty(num_steps, N, dtype=t.int32, device=env.device))
+        G = self.goal_size
+        if G > 0:
+            out["goals"] = t.empty(num_steps, N, G, device=env.device)
         with t.no_grad():
             s = env.record_state()
             for k in range(num_steps):
@@ -215,7 +223,14 @@ class BatchedRollout:
                 if record_stats:
                     self.s_norm.record(s)
                 explore = t.rand(N, device=env.device, generator=self.gen) < self.exp_rate
-                na, logp = self.policy.sample(self.s_norm.normalize(s), explore, self.gen)
+                if G > 0:   # RLAgent._update_new_action records the goal next to the state (R/learning/rl_agent.py:319-343)
+                    g = env.record_goal()
+                    out["goals"][k] = g
+                    if record_stats:
+                        self.g_norm.record(g)
+                    na, logp = self.policy.sample(self.s_norm.normalize(s), self.g_norm.normalize(g), explore, self.gen)
+                else:
+                    na, logp = self.policy.sample(self.s_norm.normalize(s), explore, self.gen)
                 a = self.a_norm.unnormalize(na).contiguous()
                 s, r, done, term = env.step(a)
                 out["actions"][k] = a; out["logps"][k] = logp; out["rewards"][k] = r; out["dones"][k] = done; out["terminate"][k] = term

@@ -54,7 +54,7 @@ def test_policy_head_shapes_and_logp():
     torch.manual_seed(0)
     p = build_policy(227, 28, init_output_scale=0.01, noise=0.05)
     assert [l.weight.shape for l in p.hidden] == [(1024, 227), (512, 1024)] and p.mean.weight.shape == (28, 512)
-    assert float(p.mean.weight.abs().max()) <= 0.01 and float(p.logstd[0]) == pytest.approx(math.log(0.05))
+    assert float(p.mean.weight.detach().abs().max()) <= 0.01 and float(p.logstd.detach()[0]) == pytest.approx(math.log(0.05))
     s = torch.randn(7, 227)
     mask = torch.tensor([1, 0, 1, 1, 0, 1, 1], dtype=torch.bool)
     a, logp = p.sample(s, mask)
@@ -101,3 +101,68 @@ def test_checkpoint_reader_returns_the_gate_layers_of_a_task_policy():
     a = load_actor(ckpt)
     assert [w.shape for w, _ in a["hidden"]] == [(229, 1024), (1024, 512)] and a["gate_common"][0].shape == (3, 128)
     assert [g["scale"][0].shape for g in a["gates"]] == [(64, 1024), (64, 512)] and a["g_norm_mean"].shape == (3,)
+
+
+class _FakeEnv:
+    """CPU stand-in with DeepMimicBatchEnv's surface, enough to exercise BatchedRollout.collect's control flow without a GPU."""
+
+    def __init__(self, n, goal_size):
+        import torch
+        self.torch, self.num_envs, self.device, self.G = torch, n, torch.device("cpu"), goal_size
+        self.t = torch.zeros(n)
+        self.resets = 0
+        self.done = torch.zeros(n, dtype=torch.bool)
+
+    def get_state_size(self, agent_id=0): return 5
+    def get_action_size(self, agent_id=0): return 2
+    def get_goal_size(self, agent_id=0): return self.G
+    def build_state_norm_groups(self, agent_id=0): return np.zeros(5, dtype=np.int32)
+    def build_goal_norm_groups(self, agent_id=0): return np.zeros(self.G, dtype=np.int32)
+    def build_state_offset(self, agent_id=0): return np.zeros(5)
+    def build_state_scale(self, agent_id=0): return np.ones(5)
+    def build_goal_offset(self, agent_id=0): return np.zeros(self.G)
+    def build_goal_scale(self, agent_id=0): return np.ones(self.G)
+    def build_action_offset(self, agent_id=0): return np.array([-1.0, 0.5])
+    def build_action_scale(self, agent_id=0): return np.array([2.0, 4.0])
+
+    def record_state(self, agent_id=0):
+        return self.t[:, None] + self.torch.arange(5.0)[None, :]
+
+    def record_goal(self, agent_id=0):
+        return self.torch.stack([self.t, -self.t, self.torch.ones_like(self.t)], dim=1)[:, :self.G]
+
+    def step(self, a):
+        self.last_action = a.clone()
+        self.t = self.t + 1.0
+        self.done = self.t >= 3.0 + self.torch.arange(float(self.num_envs)) % 2      # episodes of 3 or 4 steps
+        return self.record_state(), a.sum(dim=1), self.done.clone(), self.done.to(self.torch.int32)
+
+    def reset(self, force_all=False):
+        self.resets += int(self.done.sum())
+        self.t = self.torch.where(self.done, self.torch.zeros_like(self.t), self.t)
+        self.done = self.torch.zeros_like(self.done)
+
+
+@pytest.mark.parametrize("goal_size", [0, 3])
+def test_rollout_collect_control_flow_with_and_without_goals(goal_size):
+    import torch
+    from deepmimic_b200.rollout import BatchedRollout
+    env = _FakeEnv(4, goal_size)
+    ro = BatchedRollout(env, exp_rate=0.0, seed=1)
+    assert type(ro.policy).__name__ == ("GatedGaussianMLPPolicy" if goal_size else "GaussianMLPPolicy")
+    traj = ro.collect(9, record_stats=False)
+    assert traj["states"].shape == (9, 4, 5) and traj["actions"].shape == (9, 4, 2) and traj["dones"].dtype == torch.bool
+    assert ("goals" in traj) == (goal_size > 0)
+    # episodes restart: env 0 (3 steps) is done at k = 2, 5, 8; env 1 (4 steps) at k = 3, 7
+    assert traj["dones"][:, 0].nonzero().flatten().tolist() == [2, 5, 8] and traj["dones"][:, 1].nonzero().flatten().tolist() == [3, 7]
+    assert env.resets == 3 + 2 + 3 + 2
+    assert torch.equal(traj["states"][3, 0], torch.arange(5.0))                 # the state after a reset is re-recorded
+    if goal_size:
+        assert torch.equal(traj["goals"][4, 1], torch.tensor([0.0, -0.0, 1.0]))  # and so is the goal
+    # exp_rate 0: the action is the un-normalised mode, a = mean_a + std_a * mu with mean = -offset, std = 1 / scale
+    with torch.no_grad():
+        s0 = traj["states"][0]
+        mu = ro.policy(ro.s_norm.normalize(s0), ro.g_norm.normalize(traj["goals"][0])) if goal_size else ro.policy(ro.s_norm.normalize(s0))
+    want = torch.tensor([1.0, -0.5]) + mu * torch.tensor([0.5, 0.25])
+    assert torch.allclose(traj["actions"][0], want, atol=1e-6)
+    assert torch.allclose(traj["rewards"][0], traj["actions"][0].sum(dim=1))
