@@ -345,6 +345,21 @@ static bool load_host_model(dm_handle& H, const char* asset_root, int argc, cons
         H.sa = dmh::load_scene_assets(ap, root);
         // scenes on the accelerated path: "imitate" and its AMP variant (same character, controller, clip and dynamics; AMP observations on top).
         // The AMP task scenes (heading / target / dribble / strike) add goals, task rewards and clip datasets that are not built: refuse them loudly.
+        // options of the reference's scene that the batched path does not implement are refused, never ignored
+        {
+            const dmh::SceneConfig& c = H.sa.cfg;
+            std::vector<std::string> v;
+            if (!c.char_ctrl.empty() && c.char_ctrl != "ct_pd") throw std::runtime_error("Unsupported character controller: " + c.char_ctrl + " (supported: ct_pd)");
+            if (ap.ParseStrings("character_files", v) && v.size() > 1) throw std::runtime_error("Unsupported: more than one character per scene");
+            if (ap.ParseStrings("char_types", v) && !v.empty() && v[0] != "general") throw std::runtime_error("Unsupported character type: " + v[0] + " (supported: general)");
+            bool soft = false;
+            if (ap.ParseBool("enable_char_soft_contact", soft) && soft) throw std::runtime_error("Unsupported: --enable_char_soft_contact true");
+            if (c.enable_root_rot_fail) throw std::runtime_error("Unsupported: --enable_root_rot_fail true");
+            if (!c.terrain_file.empty()) {   // cGroundBuilder: only the flat plane (data/terrain/plane.txt) is on the path
+                dmh::Json t = dmh::Json::parseFile(dmh::resolve_path(root, c.terrain_file));
+                if (t["Type"].asString("") != "plane") throw std::runtime_error("Unsupported terrain type: " + t["Type"].asString("") + " (supported: plane)");
+            }
+        }
         // The AMP task scenes target_amp / heading_amp have their device code written (dm_task.cuh, dm_step_kernel<.., TASK>, dm_task_*_kernel)
         // but it has not run on hardware yet: they are accepted only with DM_EXPERIMENTAL_TASK_SCENES=1, otherwise refused like every other scene.
         const char* exp_env = std::getenv("DM_EXPERIMENTAL_TASK_SCENES");

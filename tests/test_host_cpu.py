@@ -76,6 +76,11 @@ def test_loader_errors_are_reported(asset_root):
         capi.HostModel(["--scene", "imitate", "--character_files", "data/characters/nope.txt"], asset_root)
     with pytest.raises(RuntimeError, match="Unsupported scene"):
         capi.HostModel(["--scene", "heading_amp", "--arg_file", ARG_FILES[0]], asset_root)     # first key wins: the scene is overridden
+    for extra, msg in ((["--char_ctrls", "ct_vel"], "Unsupported character controller"), (["--enable_char_soft_contact", "true"], "enable_char_soft_contact"),
+                       (["--enable_root_rot_fail", "true"], "enable_root_rot_fail"), (["--char_types", "biped3d"], "Unsupported character type"),
+                       (["--character_files", "data/characters/humanoid3d.txt", "data/characters/dog3d.txt"], "more than one character")):
+        with pytest.raises(RuntimeError, match=msg):
+            capi.HostModel(extra + ["--arg_file", ARG_FILES[0]], asset_root)
     with pytest.raises(RuntimeError, match="Unsupported timer type"):
         capi.HostModel(["--timer_type", "exp", "--arg_file", ARG_FILES[0]], asset_root)
     m = capi.HostModel(["--scene", "imitate_amp", "--arg_file", ARG_FILES[0]], asset_root)       # the AMP variant of the imitate scene loads
