@@ -454,10 +454,10 @@ struct Oracle {
         // SyncKinCharRoot (SceneImitate.cpp:386-418)
         {
             if (sa.cfg.sync_char_root_rot) {
+                // cCharacter::RotateRoot -> virtual SetRootRotation -> cKinCharacter::SetRootRotation -> RotateOrigin (Character.cpp:210-216,
+                // KinCharacter.cpp:243-248,285-327): the heading difference goes into the kinematic character's ORIGIN rotation and persists
                 double sim_heading = CalcHeading(SimRootRot()), kin_heading = CalcHeading(GetRootRot(kin_pose));
-                DQ drot = AxisAngleToQuaternion(D3(0, 1, 0), sim_heading - kin_heading);
-                DQ rr = qnormalized(drot * GetRootRot(kin_pose));  // cCharacter::RotateRoot (Character.cpp:195-201): pose only, origin untouched
-                kin_pose[3] = rr.w; kin_pose[4] = rr.x; kin_pose[5] = rr.y; kin_pose[6] = rr.z;
+                KinRotateOrigin(AxisAngleToQuaternion(D3(0, 1, 0), sim_heading - kin_heading));
             }
             KinMoveOrigin(SimRootPos() - GetRootPos(kin_pose));  // cKinCharacter::SetRootPos (KinCharacter.cpp:239-244)
         }
@@ -511,10 +511,9 @@ struct Oracle {
         KinPose();
         double curr_phase = KinPhase(kin_time);
         if (curr_phase < prev_phase) {
-            if (sa.cfg.sync_char_root_rot) {
+            if (sa.cfg.sync_char_root_rot) {   // RotateRoot -> RotateOrigin, as in Reset's SyncKinCharRoot
                 double sim_heading = CalcHeading(SimRootRot()), kin_heading = CalcHeading(GetRootRot(kin_pose));
-                DQ rr = qnormalized(AxisAngleToQuaternion(D3(0, 1, 0), sim_heading - kin_heading) * GetRootRot(kin_pose));
-                kin_pose[3] = rr.w; kin_pose[4] = rr.x; kin_pose[5] = rr.y; kin_pose[6] = rr.z;
+                KinRotateOrigin(AxisAngleToQuaternion(D3(0, 1, 0), sim_heading - kin_heading));
             }
             if (sa.cfg.sync_char_root_pos) {
                 D3 sim_root = SimRootPos(), kin_root = GetRootPos(kin_pose);

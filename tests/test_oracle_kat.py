@@ -261,6 +261,50 @@ def test_finished_clip_fails_the_episode_in_imitate_only(asset_root, tmp_path):
     assert all(h[0] == 0 and not h[1] for h in res["imitate_amp"])
 
 
+def test_root_rotation_sync_rotates_the_kinematic_origin(asset_root):
+    """--sync_char_root_rot true (dog3d_spin): SyncKinCharRoot / SyncKinCharNewCycle call RotateRoot, whose virtual SetRootRotation lands in
+    cKinCharacter::RotateOrigin (SceneImitate.cpp:386-444, Character.cpp:210-216, KinCharacter.cpp:243-248,285-327): the heading difference
+    becomes part of the ORIGIN rotation and persists over the following updates."""
+    def heading(q):   # pose quaternion (w, x, y, z): cKinTree::CalcHeading
+        w, x, y, z = q
+        return np.arctan2(-(2 * (x * z - w * y)), 1 - 2 * (y * y + z * z))
+    o = Oracle(["--sync_char_root_rot", "true", "--arg_file", "args/train_humanoid3d_walk_args.txt"], asset_root)
+    o.reset(0.2, 0.0, 20.0)
+    nj = o.num_joints
+    origin_rot = lambda: o.get_snapshot()[13 + 55 * nj + 4: 13 + 55 * nj + 8]
+    np.testing.assert_allclose(origin_rot(), [1, 0, 0, 0], atol=1e-8)           # sim was just synced to the clip (through float state): nothing to rotate
+    # turn the simulated character by 0.7 rad about +y and run through the end of the cycle with the default PD targets
+    p, v = o.get_pose()
+    c, s_ = np.cos(0.35), np.sin(0.35)
+    w, x, y, z = p[3:7]
+    p[3:7] = [c * w - s_ * y, c * x + s_ * z, c * y + s_ * w, c * z - s_ * x]    # (c, 0, s, 0) * q
+    o.set_pose_vel(p, v)
+    dur = o.motion_duration
+    n = int(np.ceil((dur - 0.2) * 600.0)) + 1
+    for _ in range(n):
+        o.update(1.0 / 600.0)
+    q = origin_rot()
+    assert abs(2 * np.arctan2(q[2], q[0])) > 0.3                                  # the origin picked up (most of) the turn ...
+    kin, sim = o.get_kin_pose()[0], o.get_pose()[0]
+    for _ in range(30):                                                           # ... and keeps it: no snap back on the next updates
+        o.update(1.0 / 600.0)
+    np.testing.assert_allclose(origin_rot(), q, atol=1e-12)
+    # right after the wrap the two headings agreed
+    o2 = Oracle(["--sync_char_root_rot", "true", "--arg_file", "args/train_humanoid3d_walk_args.txt"], asset_root)
+    o2.reset(0.2, 0.0, 20.0)
+    o2.set_pose_vel(p, v)
+    prev = 0.0
+    for k in range(n + 5):
+        o2.update(1.0 / 600.0)
+        ph = (0.2 + (k + 1) / 600.0) / dur % 1.0
+        if ph < prev:
+            assert abs(heading(o2.get_kin_pose()[0][3:7]) - heading(o2.get_pose()[0][3:7])) < 2e-2   # one update of motion apart
+            break
+        prev = ph
+    else:
+        raise AssertionError("no cycle wrap seen")
+
+
 def test_amp_observation_known_answers(asset_root):
     """cSceneImitateAMP::BuildAMPObs (SceneImitateAMP.cpp:279-397): layout [pose now | pose prev | vel now | vel prev]; humanoid
     (1 + 6 + 8*6 + 4 + 4*3) = 71 and (6 + 36) = 42 -> 226."""
@@ -350,7 +394,8 @@ def test_pretrained_reference_policy_tracks_the_clip_in_the_oracle(asset_root):
 
 
 @pytest.mark.parametrize("char,clip,min_reward", [("humanoid3d", "walk", 0.8), ("humanoid3d", "backflip", 0.75), ("humanoid3d", "cartwheel", 0.8),
-                                                   ("humanoid3d", "jump", 0.85), ("dog3d", "trot", 0.85), ("dog3d", "pace", 0.8), ("dog3d", "canter", 0.8)])
+                                                   ("humanoid3d", "jump", 0.85), ("dog3d", "trot", 0.85), ("dog3d", "pace", 0.8), ("dog3d", "canter", 0.8),
+                                                   ("dog3d", "spin", 0.75)])   # spin: --sync_char_root_rot true (0.44 when the sync only touched the pose, 0.80 with RotateOrigin)
 def test_more_pretrained_policies_from_the_reference_tree(char, clip, min_reward):
     """Same check for other skills, reading the TF1 checkpoints directly (deepmimic_b200/tf_checkpoint.py); needs the reference checkout."""
     ref = "/root/reference"
