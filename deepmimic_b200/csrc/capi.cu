@@ -29,7 +29,7 @@ __global__ void dm_reset_kernel(const DevModel*, DevState, const double*, const 
 __global__ void dm_set_action_kernel(const DevModel*, DevState, const float*, int);
 template <int W, int BLOCK>
 __global__ void dm_amp_obs_kernel(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int);
-template <int W, bool DEBUG, bool TASK>
+template <int W, bool DEBUG, int VAR>
 __global__ void dm_step_kernel(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
 __global__ void dm_task_reset_kernel(const DevModel*, DevState, int);
 __global__ void dm_task_observe_kernel(const DevModel*, DevState, float*, float*, int);
@@ -127,7 +127,11 @@ bool build_device_model(dm_handle& H) {
     const int nl = cm.num_joints();
     if (nl > dmk::kMaxLinks) { g_err = "character has more links than lanes (32)"; return false; }
     if (cm.joints[0].type != dmh::kNone) { g_err = "only floating-base characters (root joint type 'none') are supported"; return false; }
-    if (sa.cfg.sync_char_root_rot) { g_err = "--sync_char_root_rot true is not supported by the batched path"; return false; }
+    if (sa.cfg.sync_char_root_rot) {
+        // device code written (dm_step_kernel<.., kVarRootRot>) but not yet run on hardware: opt-in like the task scenes
+        const char* e = std::getenv("DM_EXPERIMENTAL_ROOT_ROT_SYNC");
+        if (!(e && e[0] == '1')) { g_err = "--sync_char_root_rot true is not supported by the batched path"; return false; }
+    }
     const double sc = sa.cfg.world_scale;
     M.nl = nl; M.scale = static_cast<float>(sc);
     M.gravity[0] = static_cast<float>(sa.cfg.gravity.x * sc); M.gravity[1] = static_cast<float>(sa.cfg.gravity.y * sc); M.gravity[2] = static_cast<float>(sa.cfg.gravity.z * sc);
@@ -276,9 +280,9 @@ void build_statics(dm_handle& H) {
     }
 }
 
-template <int W, bool DEBUG, bool TASK>
+template <int W, bool DEBUG, int VAR>
 int launch_step(dm_handle* h, double dt, int n_updates) {
-    auto kern = dmk::dm_step_kernel<W, DEBUG, TASK>;
+    auto kern = dmk::dm_step_kernel<W, DEBUG, VAR>;
     // opt in to the large dynamic shared-memory carve-out; the limit is raised whenever a handle needs more than any earlier one on
     // this device (attributes are per device and per function: several handles of different sizes may live in one process)
     static std::mutex mu;
@@ -302,9 +306,14 @@ template <int W, bool DEBUG>
 int launch_update(dm_handle* h, double dt, int n_updates) {
     if (h->hm.task_kind != dmk::kTaskNone) {   // AMP task scenes: the instantiation that also advances the task block (no debug dumps there)
         if (DEBUG) { g_err = "dm_debug_enable is not available in the AMP task scenes"; return fail(); }
-        return launch_step<W, false, true>(h, dt, n_updates);
+        if (h->hm.sync_root_rot) { g_err = "--sync_char_root_rot in an AMP task scene is not built"; return fail(); }
+        return launch_step<W, false, dmk::kVarTask>(h, dt, n_updates);
     }
-    return launch_step<W, DEBUG, false>(h, dt, n_updates);
+    if (h->hm.sync_root_rot) {   // --sync_char_root_rot true: the instantiation with the heading sync at clip wraps
+        if (DEBUG) { g_err = "dm_debug_enable is not available with --sync_char_root_rot"; return fail(); }
+        return launch_step<W, false, dmk::kVarRootRot>(h, dt, n_updates);
+    }
+    return launch_step<W, DEBUG, 0>(h, dt, n_updates);
 }
 template <int W>
 int launch_observe(dm_handle* h, float* d_state, float* d_reward) {

@@ -19,6 +19,7 @@ constexpr int kMaxLinks = 32;   // one lane per link
 constexpr int kMaxDofs = 96;    // 6 + joint dofs (humanoid3d 34, dog3d 70)
 constexpr int kMaxChain = 24;   // longest root->leaf dof chain (humanoid3d 13, dog3d 22)
 constexpr int kMaxChildren = 4;
+enum StepVariant { kVarTask = 1, kVarRootRot = 2 };   // dm_step_kernel<W, DEBUG, VAR>: optional scene features, one instantiation each
 constexpr int kStepMaxThreads = 448;    // dm_step_kernel: 28 (W=16) / 14 (W=32) environments per block (14 warps: 128 registers per thread)
 constexpr int kManifoldFloats = 48;  // per link: 4 points x 12 floats
 constexpr int kDebugFloats = 8 * kMaxDofs + 2048;   // test hook (dm_debug_*): stage dumps of one update

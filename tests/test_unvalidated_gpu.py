@@ -1,8 +1,10 @@
-"""GPU parity tests of the AMP task scenes (target_amp / heading_amp) against the oracle.
+"""GPU parity tests of device code that has never run on hardware: the AMP task scenes (target_amp / heading_amp) and the
+--sync_char_root_rot heading sync, each against the oracle.
 
-OPT-IN: the device half of these scenes (dm_task.cuh inside dm_step_kernel<.., TASK>, dm_task_reset_kernel, dm_task_observe_kernel) was
+OPT-IN: the device half of the task scenes (dm_task.cuh inside dm_step_kernel<.., TASK>, dm_task_reset_kernel, dm_task_observe_kernel) was
 written after round 1's GPU budget was spent and has never run on hardware.  dm_create refuses the scenes unless
-DM_EXPERIMENTAL_TASK_SCENES=1; these tests additionally need DM_RUN_UNVALIDATED_GPU_TESTS=1 so that the default `pytest -m gpu` run only
+DM_EXPERIMENTAL_TASK_SCENES=1; --sync_char_root_rot needs DM_EXPERIMENTAL_ROOT_ROT_SYNC=1 (dm_step_kernel<.., kVarRootRot>);
+these tests additionally need DM_RUN_UNVALIDATED_GPU_TESTS=1 so that the default `pytest -m gpu` run only
 contains tests of code that has been validated on a B200.  Round 2: run with both variables set, fix what breaks, then drop the gates."""
 import os
 
@@ -70,4 +72,37 @@ def test_task_goal_reward_and_updates_match_the_oracle(asset_root, args, monkeyp
                     if o.is_episode_end():
                         break
     assert worst_goal < 5e-3 and worst_rew < 1e-2, (worst_goal, worst_rew)
+    core.close()
+
+
+def test_root_rotation_sync_matches_the_oracle_across_a_clip_wrap(asset_root, monkeypatch):
+    """--sync_char_root_rot true: the character is turned by 0.7 rad before the clip wraps; after the wrap the kinematic origin (position and
+    rotation, snapshot slots 1..7 of the clock block) must have picked up the same heading correction as in the oracle and keep it."""
+    from deepmimic_b200 import capi
+    monkeypatch.setenv("DM_EXPERIMENTAL_ROOT_ROT_SYNC", "1")
+    args = ["--sync_char_root_rot", "true", "--arg_file", "args/train_humanoid3d_walk_args.txt"]
+    core = capi.BatchedCore(args, 4, asset_root, seed=3)
+    o = Oracle(args, asset_root)
+    o.reset(0.2, 0.0, 20.0)
+    core.reset(force_all=True, kin_time=np.full(4, 0.2), max_time=np.full(4, 20.0), rot_theta=np.zeros(4))
+    p, v = o.get_pose()
+    c, s_ = np.cos(0.35), np.sin(0.35)
+    w, x, y, z = p[3:7]
+    p[3:7] = [c * w - s_ * y, c * x + s_ * z, c * y + s_ * w, c * z - s_ * x]
+    o.set_pose_vel(p, v)
+    snap = o.get_snapshot()
+    for e in range(4):
+        core.set_snapshot(e, snap)
+    n = int(np.ceil((o.motion_duration - 0.2) * 600.0)) + 30
+    core.update(1.0 / 600.0, n)
+    for _ in range(n):
+        o.update(1.0 / 600.0)
+    core.sync()
+    nj = o.num_joints
+    want = o.get_snapshot()[13 + 55 * nj: 13 + 55 * nj + 8]
+    got = core.get_snapshot(2)[13 + 55 * nj: 13 + 55 * nj + 8]
+    assert abs(2 * np.arctan2(want[6], want[4])) > 0.3                          # the oracle's origin did turn
+    np.testing.assert_allclose(got[0], want[0], atol=1e-9)                      # mocap clock
+    np.testing.assert_allclose(got[1:4], want[1:4], atol=5e-3)                  # origin position
+    np.testing.assert_allclose(got[4:8], want[4:8], atol=5e-3)                  # origin rotation (w, x, y, z)
     core.close()
