@@ -1221,7 +1221,16 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 double p0 = kin_time / dur; p0 -= floor(p0);
                 kin_time += dt;
                 double p1 = kin_time / dur; p1 -= floor(p1);
-                if (M.loop_motion && p1 < p0 && (M.sync_root_pos || (ROOTROT && M.sync_root_rot))) {
+                if constexpr (ROOTROT) {
+                    // --sync_char_root_rot instantiation: the whole wrap handling is the shared host / device routine of dm_task.cuh
+                    // (checked against the oracle on the host, tests/test_task_scenes_cpu.py)
+                    if (M.loop_motion && p1 < p0 && (M.sync_root_pos || M.sync_root_rot)) {
+                        const double simq[4] = {static_cast<double>(sB[3]), static_cast<double>(sB[4]), static_cast<double>(sB[5]), static_cast<double>(sB[6])};
+                        kin_wrap_sync(frame_times, frames, M.pose_dim, M.num_frames, M.cycle_delta, dur, kin_time, tm + kTOrigin, tm + kTOriginRot,
+                                      static_cast<double>(sB[0]) / M.scale, static_cast<double>(sB[2]) / M.scale, simq, M.sync_root_pos != 0, M.sync_root_rot != 0);
+                    }
+                }
+                if (!ROOTROT && M.loop_motion && p1 < p0 && M.sync_root_pos) {
                     // SyncKinCharNewCycle: snap the clip's root x,z (at the new time) onto the simulated root
                     double org_x = tm[kTOrigin], org_z = tm[kTOrigin + 2];
                     int cyc = static_cast<int>(floor(kin_time / dur));
@@ -1240,39 +1249,6 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                     double kx = rx + qw * ux + (qy * uz - qz * uy);
                     double kz = rz + qw * uz + (qx * uy - qy * ux);
                     double sx = static_cast<double>(sB[0]) / M.scale, sz = static_cast<double>(sB[2]) / M.scale;
-                    if constexpr (ROOTROT) {
-                        if (M.sync_root_rot) {
-                            // RotateRoot(drot) -> cKinCharacter::RotateOrigin (KinCharacter.cpp:285-327): drot = rotation about +y by
-                            // (simulated heading - kinematic heading); origin_rot := drot * origin_rot, origin := root + drot (origin - root).
-                            // kinematic root rotation = origin_rot * slerp(frame roots) (Eigen slerp, shortest arc)
-                            double a0 = f0[3], a1 = f0[4], a2 = f0[5], a3 = f0[6], b0 = f1[3], b1 = f1[4], b2 = f1[5], b3 = f1[6];   // (w, x, y, z)
-                            double dq = a0 * b0 + a1 * b1 + a2 * b2 + a3 * b3, ad = fabs(dq), s0, s1;
-                            if (ad >= 1.0 - 2.220446049250313e-16) { s0 = 1.0 - bl; s1 = bl; }
-                            else { const double th = acos(ad), sn = sin(th); s0 = sin((1.0 - bl) * th) / sn; s1 = sin(bl * th) / sn; }
-                            if (dq < 0) s1 = -s1;
-                            const double cw = s0 * a0 + s1 * b0, cx = s0 * a1 + s1 * b1, cy = s0 * a2 + s1 * b2, cz = s0 * a3 + s1 * b3;
-                            // k = origin_rot * c
-                            const double kw = qw * cw - qx * cx - qy * cy - qz * cz, kqx = qw * cx + qx * cw + qy * cz - qz * cy,
-                                         kqy = qw * cy - qx * cz + qy * cw + qz * cx, kqz = qw * cz + qx * cy - qy * cx + qz * cw;
-                            // heading = atan2(-z, x) of the rotated +x axis (cKinTree::CalcHeading)
-                            const double kin_heading = atan2(-2.0 * (kqx * kqz - kw * kqy), 1.0 - 2.0 * (kqy * kqy + kqz * kqz));
-                            const double bx = -static_cast<double>(sB[3]), by = -static_cast<double>(sB[4]), bz = -static_cast<double>(sB[5]), bw = static_cast<double>(sB[6]);
-                            const double sim_heading = atan2(-2.0 * (bx * bz - bw * by), 1.0 - 2.0 * (by * by + bz * bz));
-                            const double ha = 0.5 * (sim_heading - kin_heading), dc = cos(ha), ds = sin(ha);   // drot = (dc, 0, ds, 0)
-                            // origin_rot := normalize(drot * origin_rot)
-                            double nw = dc * qw - ds * qy, nx = dc * qx + ds * qz, ny = dc * qy + ds * qw, nz = dc * qz - ds * qx;
-                            const double nn = 1.0 / sqrt(nw * nw + nx * nx + ny * ny + nz * nz);
-                            nw *= nn; nx *= nn; ny *= nn; nz *= nn;
-                            tm[kTOriginRot] = nw; tm[kTOriginRot + 1] = nx; tm[kTOriginRot + 2] = ny; tm[kTOriginRot + 3] = nz;
-                            // origin := root + drot (origin - root), root = origin + k (world position of the kinematic root); y is unchanged
-                            const double ox = -kx, oz = -kz;                         // origin - root
-                            const double c2 = dc * dc - ds * ds, s2 = 2.0 * dc * ds;  // rotation about +y by 2 ha: x' = c x + s z, z' = -s x + c z
-                            const double wx = org_x + kx, wz = org_z + kz;           // root world position
-                            org_x = wx + (c2 * ox + s2 * oz);
-                            org_z = wz + (-s2 * ox + c2 * oz);
-                            kx = wx - org_x; kz = wz - org_z;                         // root relative to the rotated origin
-                        }
-                    }
                     if (M.sync_root_pos) {
                         org_x += sx - (kx + org_x);
                         org_z += sz - (kz + org_z);

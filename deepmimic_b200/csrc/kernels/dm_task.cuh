@@ -158,4 +158,61 @@ DM_HD double task_reward(int kind, const TaskParams& P, const double* t, bool fa
     return vel_reward;
 }
 
+// cSceneImitate::SyncKinCharNewCycle (SceneImitate.cpp:420-444) when the looping clip wraps: samples the clip's root at the new mocap time,
+// then (sync_rot) RotateRoot -> cKinCharacter::RotateOrigin (KinCharacter.cpp:285-327) with the rotation about +y by (simulated heading -
+// kinematic heading), then (sync_pos) moves the origin so the kinematic root's x, z sit on the simulated root and its height offset above the
+// (flat, y = 0) ground is kept.  origin: 3 doubles, origin_rot: 4 doubles (w, x, y, z), both in / out.  frames: float pose table with the root
+// at [0..2] and its quaternion (w, x, y, z) at [3..6]; sim_quat: the stored world->base quaternion (x, y, z, w) of the simulated character.
+DM_HD void kin_wrap_sync(const double* frame_times, const float* frames, int pose_dim, int num_frames, const float* cycle_delta, double dur, double kin_time,
+                         double* origin, double* origin_rot, double sim_x, double sim_z, const double* sim_quat, bool sync_pos, bool sync_rot) {
+    double org_x = origin[0], org_z = origin[2];
+    const int cyc = static_cast<int>(floor(kin_time / dur));
+    const double tt = kin_time - cyc * dur;
+    int lo = 0, hi = num_frames - 1;   // upper_bound - 1
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (frame_times[mid] <= tt) lo = mid; else hi = mid; }
+    double bl = (tt - frame_times[lo]) / (frame_times[lo + 1] - frame_times[lo]);
+    bl = fmin(fmax(bl, 0.0), 1.0);
+    const float* f0 = frames + static_cast<size_t>(lo) * pose_dim; const float* f1 = f0 + pose_dim;
+    const double rx = (1 - bl) * f0[0] + bl * f1[0] + cyc * static_cast<double>(cycle_delta[0]);
+    const double rz = (1 - bl) * f0[2] + bl * f1[2] + cyc * static_cast<double>(cycle_delta[2]);
+    const double ry = (1 - bl) * f0[1] + bl * f1[1];
+    const double qw = origin_rot[0], qx = origin_rot[1], qy = origin_rot[2], qz = origin_rot[3];
+    double ux = qy * rz - qz * ry, uy = qz * rx - qx * rz, uz = qx * ry - qy * rx;
+    ux *= 2; uy *= 2; uz *= 2;
+    double kx = rx + qw * ux + (qy * uz - qz * uy);   // root relative to the origin, rotated by origin_rot
+    double kz = rz + qw * uz + (qx * uy - qy * ux);
+    if (sync_rot) {
+        // kinematic root rotation = origin_rot * slerp(frame roots) (Eigen slerp, shortest arc)
+        const double a0 = f0[3], a1 = f0[4], a2 = f0[5], a3 = f0[6], b0 = f1[3], b1 = f1[4], b2 = f1[5], b3 = f1[6];
+        const double dq = a0 * b0 + a1 * b1 + a2 * b2 + a3 * b3, ad = fabs(dq);
+        double s0, s1;
+        if (ad >= 1.0 - 2.220446049250313e-16) { s0 = 1.0 - bl; s1 = bl; }
+        else { const double th = acos(ad), sn = sin(th); s0 = sin((1.0 - bl) * th) / sn; s1 = sin(bl * th) / sn; }
+        if (dq < 0) s1 = -s1;
+        const double cw = s0 * a0 + s1 * b0, cx = s0 * a1 + s1 * b1, cy = s0 * a2 + s1 * b2, cz = s0 * a3 + s1 * b3;
+        const double kw = qw * cw - qx * cx - qy * cy - qz * cz, kqx = qw * cx + qx * cw + qy * cz - qz * cy,
+                     kqy = qw * cy - qx * cz + qy * cw + qz * cx, kqz = qw * cz + qx * cy - qy * cx + qz * cw;
+        // heading = atan2(-z, x) of the rotated +x axis (cKinTree::CalcHeading)
+        const double kin_heading = atan2(-2.0 * (kqx * kqz - kw * kqy), 1.0 - 2.0 * (kqy * kqy + kqz * kqz));
+        const double bx = -sim_quat[0], by = -sim_quat[1], bz = -sim_quat[2], bw = sim_quat[3];   // root rotation = inverse of world->base
+        const double sim_heading = atan2(-2.0 * (bx * bz - bw * by), 1.0 - 2.0 * (by * by + bz * bz));
+        const double ha = 0.5 * (sim_heading - kin_heading), dc = cos(ha), ds = sin(ha);           // drot = (dc, 0, ds, 0)
+        double nw = dc * qw - ds * qy, nx = dc * qx + ds * qz, ny = dc * qy + ds * qw, nz = dc * qz - ds * qx;   // drot * origin_rot
+        const double nn = 1.0 / sqrt(nw * nw + nx * nx + ny * ny + nz * nz);
+        origin_rot[0] = nw * nn; origin_rot[1] = nx * nn; origin_rot[2] = ny * nn; origin_rot[3] = nz * nn;
+        // origin := root + drot (origin - root); rotation about +y by 2 ha: x' = c x + s z, z' = -s x + c z; y unchanged
+        const double c2 = dc * dc - ds * ds, s2 = 2.0 * dc * ds;
+        const double wx = org_x + kx, wz = org_z + kz;   // world position of the kinematic root
+        org_x = wx + (c2 * (-kx) + s2 * (-kz));
+        org_z = wz + (-s2 * (-kx) + c2 * (-kz));
+        kx = wx - org_x; kz = wz - org_z;
+    }
+    if (sync_pos) {
+        org_x += sim_x - (kx + org_x);
+        org_z += sim_z - (kz + org_z);
+        origin[1] = 0.0;   // kin_root.y := ground_h + (kin_root.y - origin.y)  =>  origin.y returns to the ground height 0
+    }
+    origin[0] = org_x; origin[2] = org_z;
+}
+
 }  // namespace dmk

@@ -404,3 +404,52 @@ def test_task_scenes_stay_refused_without_the_opt_in(asset_root, monkeypatch):
     monkeypatch.setenv("DM_EXPERIMENTAL_TASK_SCENES", "1")
     with pytest.raises(RuntimeError, match="more than one clip"):
         capi.HostModel(TARGET, asset_root)                                      # clip datasets are oracle-only so far
+
+
+@pytest.mark.parametrize("sync_rot", [True, False])
+def test_device_clip_wrap_sync_matches_the_oracle_on_the_host(asset_root, task_shim, sync_rot):
+    """kin_wrap_sync (dm_task.cuh; what dm_step_kernel<.., kVarRootRot> runs at a clip wrap) against the oracle's SyncKinCharNewCycle: the
+    character is turned by 0.7 rad and drifts until the walk clip wraps; the routine gets the pre-update clocks, origin and simulated base
+    state from the oracle's snapshot and the fp32 clip table the device holds, and must reproduce the oracle's origin after that update."""
+    import ctypes as C
+    args = ["--sync_char_root_rot", "true" if sync_rot else "false", "--arg_file", "args/train_humanoid3d_walk_args.txt"]
+    o = Oracle(args, asset_root)
+    o.reset(0.2, 0.0, 20.0)
+    p, v = o.get_pose()
+    c, s_ = math.cos(0.35), math.sin(0.35)
+    w, x, y, z = p[3:7]
+    p[3:7] = [c * w - s_ * y, c * x + s_ * z, c * y + s_ * w, c * z - s_ * x]
+    o.set_pose_vel(p, v)
+    # the clip table as the device stores it: fp32 frames, root x / z recentred on frame 0, quaternions normalised, cumulative frame times
+    fr = np.array(json.load(open(os.path.join(asset_root, "data/motions/humanoid3d_walk.txt")))["Frames"], dtype=np.float64)
+    times = np.concatenate([[0.0], np.cumsum(fr[:-1, 0])])
+    frames = fr[:, 1:].copy()
+    frames[:, 0] -= frames[0, 0]; frames[:, 2] -= frames[0, 2]
+    frames[:, 3:7] /= np.linalg.norm(frames[:, 3:7], axis=1, keepdims=True)
+    f32 = np.ascontiguousarray(frames, dtype=np.float32)
+    cyc_delta = np.array([f32[-1, 0] - f32[0, 0], 0.0, f32[-1, 2] - f32[0, 2]], dtype=np.float32)
+    dur = o.motion_duration
+    assert dur == pytest.approx(times[-1], rel=1e-12)
+    task_shim.shim_wrap_sync.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c_float), C.c_double, C.c_double,
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int, C.c_int]
+    nj, scale = o.num_joints, 4.0
+    clk = 13 + 55 * nj
+    wraps = 0
+    for k in range(int(2.2 * dur * 600)):
+        pre = o.get_snapshot()
+        kin_time = pre[clk] + 1.0 / 600.0
+        wrap = (kin_time / dur) % 1.0 < (pre[clk] / dur) % 1.0
+        o.update(1.0 / 600.0)
+        if not wrap:
+            continue
+        wraps += 1
+        origin = pre[clk + 1: clk + 4].copy(); origin_rot = pre[clk + 4: clk + 8].copy()
+        simq = pre[3:7].copy()
+        task_shim.shim_wrap_sync(_ptr(times), f32.ctypes.data_as(C.POINTER(C.c_float)), f32.shape[1], f32.shape[0], cyc_delta.ctypes.data_as(C.POINTER(C.c_float)),
+                                 dur, kin_time, _ptr(origin), _ptr(origin_rot), pre[0] / scale, pre[2] / scale, _ptr(simq), 1, 1 if sync_rot else 0)
+        post = o.get_snapshot()
+        np.testing.assert_allclose(origin, post[clk + 1: clk + 4], atol=1e-5)       # the oracle reads the root through float link frames
+        np.testing.assert_allclose(origin_rot, post[clk + 4: clk + 8], atol=1e-5)
+        turned = abs(2 * math.atan2(post[clk + 6], post[clk + 4]))
+        assert (turned > 0.3) == sync_rot
+    assert wraps == 2
