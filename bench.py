@@ -200,7 +200,10 @@ def main():
         done_count = int(done_total.item())
 
         # ---- end-to-end through the host-buffer C-ABI call (pinned staging, H2D actions + D2H obs/reward/flags every step)
-        h_act = actions[0].cpu().numpy().copy(); h_obs = np.zeros((N, S), np.float32); h_rew = np.zeros(N, np.float32); h_fl = np.zeros((N, 4), np.int32)
+        # host buffers are page-locked (the contract's "from pinned host memory"); the tensors own the memory, the numpy arrays are views
+        t_act = actions[0].cpu().pin_memory(); t_obs = torch.zeros(N, S, dtype=torch.float32).pin_memory()
+        t_rew = torch.zeros(N, dtype=torch.float32).pin_memory(); t_fl = torch.zeros(N, 4, dtype=torch.int32).pin_memory()
+        h_act, h_obs, h_rew, h_fl = t_act.numpy(), t_obs.numpy(), t_rew.numpy(), t_fl.numpy()
         for _ in range(2):
             core.step_host(h_act, dt, 20, h_obs, h_rew, h_fl); core.reset(False)
         core.sync()

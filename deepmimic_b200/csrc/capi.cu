@@ -685,24 +685,33 @@ int dm_get_flags(dm_handle* h, int32_t* d_flags) {
     h->launches++;
     return 0;
 }
+// true when the host pointer is page-locked (cudaMallocHost / cudaHostRegister): the copy engines can address it directly
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
 int dm_step_host(dm_handle* h, const float* h_actions, double dt, int n_updates, float* h_state, float* h_reward, int32_t* h_flags) {
     DM_DEVICE(h);
     const size_t N = h->num_envs, A = h->hm.action_size, S = h->hm.state_size;
+    // page-locked caller buffers are used as they are; pageable ones go through the handle's pinned staging buffers (one extra host copy)
+    const bool pa = h_actions && is_pinned_host(h_actions), ps = h_state && is_pinned_host(h_state), pr = h_reward && is_pinned_host(h_reward),
+               pf = h_flags && is_pinned_host(h_flags);
     if (h_actions) {
-        std::memcpy(h->p_act, h_actions, N * A * sizeof(float));
-        DM_CUDA(cudaMemcpyAsync(h->d_act, h->p_act, N * A * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        if (!pa) std::memcpy(h->p_act, h_actions, N * A * sizeof(float));
+        DM_CUDA(cudaMemcpyAsync(h->d_act, pa ? h_actions : h->p_act, N * A * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         if (dm_set_action(h, h->d_act)) return 1;
     }
     if (n_updates > 0 && dm_update(h, dt, n_updates)) return 1;
     if (dm_observe(h, h_state ? h->d_obs : nullptr, h_reward ? h->d_rew : nullptr)) return 1;
     if (h_flags && dm_get_flags(h, h->d_flags4)) return 1;
-    if (h_state) DM_CUDA(cudaMemcpyAsync(h->p_obs, h->d_obs, N * S * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    if (h_reward) DM_CUDA(cudaMemcpyAsync(h->p_rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    if (h_flags) DM_CUDA(cudaMemcpyAsync(h->p_flags, h->d_flags4, N * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (h_state) DM_CUDA(cudaMemcpyAsync(ps ? h_state : h->p_obs, h->d_obs, N * S * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (h_reward) DM_CUDA(cudaMemcpyAsync(pr ? h_reward : h->p_rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (h_flags) DM_CUDA(cudaMemcpyAsync(pf ? h_flags : h->p_flags, h->d_flags4, N * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     DM_CUDA(cudaStreamSynchronize(h->stream));
-    if (h_state) std::memcpy(h_state, h->p_obs, N * S * sizeof(float));
-    if (h_reward) std::memcpy(h_reward, h->p_rew, N * sizeof(float));
-    if (h_flags) std::memcpy(h_flags, h->p_flags, N * 4 * sizeof(int32_t));
+    if (h_state && !ps) std::memcpy(h_state, h->p_obs, N * S * sizeof(float));
+    if (h_reward && !pr) std::memcpy(h_reward, h->p_rew, N * sizeof(float));
+    if (h_flags && !pf) std::memcpy(h_flags, h->p_flags, N * 4 * sizeof(int32_t));
     return 0;
 }
 

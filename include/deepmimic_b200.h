@@ -110,7 +110,8 @@ int dm_observe(dm_handle* h, float* d_state, float* d_reward);  /* fused record_
 /* d_flags: [num_envs x 4] int32 = {need_new_action, is_episode_end, check_terminate (0 null / 1 fail), check_valid_episode} */
 int dm_get_flags(dm_handle* h, int32_t* d_flags);
 
-/* ---- host-buffer convenience wrappers (the reference-facing plugin path: host in, host out, copies inside) */
+/* ---- host-buffer convenience wrappers (the reference-facing plugin path: host in, host out, copies inside).  Page-locked caller buffers
+ * (cudaMallocHost / cudaHostRegister) are DMA'd directly; pageable ones pass through the handle's pinned staging buffers. */
 int dm_step_host(dm_handle* h, const float* h_actions, double dt, int n_updates, float* h_state, float* h_reward, int32_t* h_flags);
 
 /* ---- test hooks: raw per-env simulator state, layout shared with the CPU oracle (doubles):

@@ -49,3 +49,26 @@ def test_finished_clip_fails_the_episode_in_imitate_only(asset_root, tmp_path):
         f = flags.cpu().numpy()
         assert (f[:, 2] == want).all() and (f[:, 1] == want).all(), (scene, f[:4])
         core.close()
+
+
+def test_step_host_gives_the_same_result_through_pinned_and_pageable_buffers(asset_root):
+    """dm_step_host DMA's page-locked caller buffers directly and stages pageable ones: same numbers either way."""
+    import torch
+    args = ["--arg_file", "args/run_humanoid3d_spinkick_args.txt"]
+    n = 48
+    res = []
+    for pinned in (False, True):
+        core = capi.BatchedCore(args, n, asset_root, seed=11)
+        d = core.dims
+        mk = (lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype).pin_memory()) if pinned else (lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype))
+        act, obs, rew, fl = mk(n, d.action_size), mk(n, d.state_size), mk(n), mk(n, 4, dtype=torch.int32)
+        rng = np.random.default_rng(2)
+        off, scl = core.static(capi.DM_ACTION_OFFSET), core.static(capi.DM_ACTION_SCALE)
+        for k in range(3):
+            act.copy_(torch.as_tensor((-off + 0.1 / scl * rng.standard_normal((n, d.action_size))).astype(np.float32)))
+            core.step_host(act.numpy(), 1.0 / 600.0, 20, obs.numpy(), rew.numpy(), fl.numpy())
+        res.append((obs.numpy().copy(), rew.numpy().copy(), fl.numpy().copy()))
+        core.close()
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+    assert np.isfinite(res[0][0]).all() and (res[0][1] > 0).all()
