@@ -106,3 +106,30 @@ def test_root_rotation_sync_matches_the_oracle_across_a_clip_wrap(asset_root, mo
     np.testing.assert_allclose(got[1:4], want[1:4], atol=5e-3)                  # origin position
     np.testing.assert_allclose(got[4:8], want[4:8], atol=5e-3)                  # origin rotation (w, x, y, z)
     core.close()
+
+
+@pytest.mark.parametrize("task,args", [("target", TARGET), ("heading", HEADING)])
+def test_fixture_task_policies_through_the_cuda_path(asset_root, task, args, monkeypatch):
+    """The reference's pretrained task policies (fp16 fixtures) driving 64 environments for 20 s through the batched env + goal-conditioned
+    rollout: no falls to speak of, targets reached / heading followed, like in the oracle (tests/test_task_scenes_cpu.py)."""
+    import torch
+    from deepmimic_b200.env import DeepMimicBatchEnv
+    from deepmimic_b200.rollout import BatchedRollout, build_gated_policy, load_actor_weights
+    from tests.test_task_scenes_cpu import fixture_task_actor
+    monkeypatch.setenv("DM_EXPERIMENTAL_TASK_SCENES", "1")
+    a = fixture_task_actor(task)
+    env = DeepMimicBatchEnv(args, num_envs=64, asset_root=asset_root, seed=9)
+    env.set_mode(1)
+    env.reset(True)
+    ro = BatchedRollout(env, policy=load_actor_weights(build_gated_policy(226, 3, 28), a), exp_rate=0.0)
+    ro.s_norm.set_mean_std(a["s_norm_mean"], a["s_norm_std"]); ro.g_norm.set_mean_std(a["g_norm_mean"], a["g_norm_std"]); ro.a_norm.set_mean_std(a["a_norm_mean"], a["a_norm_std"])
+    traj = ro.collect(600, record_stats=False)
+    torch.cuda.synchronize()
+    falls = int((traj["terminate"] == 1).sum())
+    mean_r = float(traj["rewards"].mean())
+    assert falls <= 6, falls
+    if task == "target":
+        inside = (traj["goals"][:, :, 2] < 0.5).float().mean()
+        assert float(inside) > 0.08 and mean_r > 0.4, (float(inside), mean_r)
+    else:
+        assert mean_r > 0.8, mean_r
