@@ -18,7 +18,7 @@ class DmDims(C.Structure):
 DM_STATE_OFFSET, DM_STATE_SCALE, DM_ACTION_OFFSET, DM_ACTION_SCALE, DM_ACTION_BOUND_MIN, DM_ACTION_BOUND_MAX, DM_STATE_NORM_GROUPS = range(7)
 
 EXPORTS = ["dm_create", "dm_load_host", "dm_get_model_info", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_stream", "dm_sync", "dm_set_mode", "dm_set_sample_count", "dm_get_time_limits", "dm_reset", "dm_set_action",
-           "dm_update", "dm_record_state", "dm_record_goal", "dm_goal_host", "dm_get_task_state", "dm_set_task_state", "dm_get_task_params", "dm_calc_reward", "dm_record_amp_obs_agent", "dm_record_amp_obs_expert", "dm_amp_obs_host", "dm_observe", "dm_get_flags", "dm_step_host", "dm_get_snapshot",
+           "dm_update", "dm_record_state", "dm_record_goal", "dm_goal_host", "dm_reset_clips", "dm_record_amp_obs_expert_clips", "dm_get_clip_table", "dm_get_task_state", "dm_set_task_state", "dm_get_task_params", "dm_calc_reward", "dm_record_amp_obs_agent", "dm_record_amp_obs_expert", "dm_amp_obs_host", "dm_observe", "dm_get_flags", "dm_step_host", "dm_get_snapshot",
            "dm_set_snapshot", "dm_get_counters", "dm_debug_enable", "dm_get_debug"]
 
 
@@ -52,6 +52,9 @@ def lib():
         L.dm_record_goal.argtypes = [vp, fp]
         L.dm_calc_reward.argtypes = [vp, fp]
         L.dm_goal_host.argtypes = [vp, fp]
+        L.dm_reset_clips.argtypes = [vp, C.c_int, C.POINTER(C.c_int), dp, dp, dp]
+        L.dm_record_amp_obs_expert_clips.argtypes = [vp, C.POINTER(C.c_int), dp, fp]
+        L.dm_get_clip_table.argtypes = [vp, C.POINTER(C.c_int), dp, dp]
         L.dm_get_task_state.argtypes = [vp, C.c_int, dp]
         L.dm_set_task_state.argtypes = [vp, C.c_int, dp]
         L.dm_get_task_params.argtypes = [vp, dp, C.POINTER(C.c_uint64)]
@@ -111,10 +114,21 @@ class BatchedCore:
         self._chk(lib().dm_get_static(self.h, kind, _dptr(out)))
         return out
 
-    def reset(self, force_all=True, kin_time=None, max_time=None, rot_theta=None):
+    def reset(self, force_all=True, kin_time=None, max_time=None, rot_theta=None, clip=None):
         f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
         kt, mt, th = f(kin_time), f(max_time), f(rot_theta)
-        self._chk(lib().dm_reset(self.h, 1 if force_all else 0, _dptr(kt), _dptr(mt), _dptr(th)))
+        if clip is None:
+            self._chk(lib().dm_reset(self.h, 1 if force_all else 0, _dptr(kt), _dptr(mt), _dptr(th)))
+        else:   # task scenes with a clip dataset: the controller's clip draw injected
+            c = np.ascontiguousarray(clip, dtype=np.int32)
+            self._chk(lib().dm_reset_clips(self.h, 1 if force_all else 0, c.ctypes.data_as(C.POINTER(C.c_int)), _dptr(kt), _dptr(mt), _dptr(th)))
+
+    def clip_table(self):
+        n = C.c_int(0)
+        lib().dm_get_clip_table(self.h, C.byref(n), None, None)
+        dur, cdf = np.zeros(n.value), np.zeros(n.value)
+        lib().dm_get_clip_table(self.h, C.byref(n), _dptr(dur), _dptr(cdf))
+        return dur, cdf
 
     def set_action(self, actions):  # torch float32 cuda tensor [N, A]
         self._chk(lib().dm_set_action(self.h, C.c_void_p(actions.data_ptr())))
@@ -152,9 +166,13 @@ class BatchedCore:
     def amp_obs_agent(self, out):  # torch float32 cuda tensor [N, amp_obs_size]
         self._chk(lib().dm_record_amp_obs_agent(self.h, C.c_void_p(out.data_ptr())))
 
-    def amp_obs_expert(self, out, kin_time=None):
+    def amp_obs_expert(self, out, kin_time=None, clip=None):
         kt = None if kin_time is None else np.ascontiguousarray(kin_time, dtype=np.float64)
-        self._chk(lib().dm_record_amp_obs_expert(self.h, _dptr(kt), C.c_void_p(out.data_ptr())))
+        if clip is None:
+            self._chk(lib().dm_record_amp_obs_expert(self.h, _dptr(kt), C.c_void_p(out.data_ptr())))
+        else:
+            c = np.ascontiguousarray(clip, dtype=np.int32)
+            self._chk(lib().dm_record_amp_obs_expert_clips(self.h, c.ctypes.data_as(C.POINTER(C.c_int)), _dptr(kt), C.c_void_p(out.data_ptr())))
 
     def flags(self, out):  # torch int32 cuda tensor [N, 4]
         self._chk(lib().dm_get_flags(self.h, C.c_void_p(out.data_ptr())))
@@ -230,6 +248,13 @@ class HostModel:
         key = (C.c_uint64 * 2)()
         lib().dm_get_task_params(self.h, _dptr(out), key)
         return out, int(key[0]), int(key[1])
+
+    def clip_table(self):
+        n = C.c_int(0)
+        lib().dm_get_clip_table(self.h, C.byref(n), None, None)
+        dur, cdf = np.zeros(n.value), np.zeros(n.value)
+        lib().dm_get_clip_table(self.h, C.byref(n), _dptr(dur), _dptr(cdf))
+        return dur, cdf
 
     def set_sample_count(self, count):
         if lib().dm_set_sample_count(self.h, int(count)) != 0:

@@ -23,12 +23,12 @@
 namespace dmk {
 template <int W, int BLOCK>
 __global__ void dm_observe_kernel(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
-template <int W, int BLOCK>
+template <int W, int BLOCK, bool TASKV>
 __global__ void dm_reset_kernel(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*,
-                                unsigned long long, unsigned long long, int);
+                                unsigned long long, unsigned long long, int, const int*);
 __global__ void dm_set_action_kernel(const DevModel*, DevState, const float*, int);
-template <int W, int BLOCK>
-__global__ void dm_amp_obs_kernel(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int);
+template <int W, int BLOCK, bool TASKV>
+__global__ void dm_amp_obs_kernel(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int, const int*);
 template <int W, bool DEBUG, int VAR>
 __global__ void dm_step_kernel(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
 __global__ void dm_task_reset_kernel(const DevModel*, DevState, int);
@@ -69,6 +69,9 @@ struct dm_handle {
     int32_t* d_flags4 = nullptr;
     float *d_amp = nullptr, *p_amp = nullptr;                              // staging for dm_amp_obs_host
     float *d_goal = nullptr, *p_goal = nullptr;                            // staging for dm_goal_host (task scenes)
+    dmk::ClipTable ctab{};                                                  // host copy of the clip dataset table (task scenes)
+    dmk::ClipTable* d_ctab = nullptr; int* d_clip_inj = nullptr;           // device table; injected clip ids (reset / expert observations)
+    int total_frames = 0;
     float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;            // staging for dm_step_host
     float *p_act = nullptr, *p_obs = nullptr, *p_rew = nullptr; int32_t* p_flags = nullptr;  // pinned host staging
     cudaStream_t stream = nullptr;
@@ -325,10 +328,13 @@ int launch_observe(dm_handle* h, float* d_state, float* d_reward) {
     return 0;
 }
 template <int W>
-int launch_reset(dm_handle* h, int force, const double* kt, const double* mt, const double* th) {
+int launch_reset(dm_handle* h, int force, const double* kt, const double* mt, const double* th, const int* clip) {
     constexpr int BLOCK = 64;
     const int grid = h->padded_envs / (BLOCK / W);
-    dmk::dm_reset_kernel<W, BLOCK><<<grid, BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, force, kt, mt, th, h->seed, h->env_offset, h->mode);
+    if (h->hm.task_kind != dmk::kTaskNone)   // task scenes: per-environment clip of the dataset, action history kept across resets
+        dmk::dm_reset_kernel<W, BLOCK, true><<<grid, BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, force, kt, mt, th, h->seed, h->env_offset, h->mode, clip);
+    else
+        dmk::dm_reset_kernel<W, BLOCK, false><<<grid, BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, force, kt, mt, th, h->seed, h->env_offset, h->mode, nullptr);
     DM_CUDA(cudaGetLastError());
     h->launches++;
     return 0;
@@ -376,8 +382,9 @@ static bool load_host_model(dm_handle& H, const char* asset_root, int argc, cons
         const bool task_scene = H.sa.cfg.is_task_scene();
         if (H.sa.cfg.scene != "imitate" && H.sa.cfg.scene != "imitate_amp" && !(task_scene && experimental))
             throw std::runtime_error("Unsupported scene: " + H.sa.cfg.scene + " (supported: imitate, imitate_amp)");
-        if (H.sa.cfg.kin_ctrl == "clips" && H.sa.clips.size() != 1)
-            throw std::runtime_error("Unsupported kinematic controller: clips with more than one clip (clip datasets are not on the accelerated path; supported: motion)");
+        if (H.sa.clips.size() != 1 && !task_scene)
+            throw std::runtime_error("Unsupported kinematic controller: clips with more than one clip outside the AMP task scenes (supported: motion)");
+        if (static_cast<int>(H.sa.clips.size()) > dmk::kMaxClips) throw std::runtime_error("clip dataset larger than the device clip table (" + std::to_string(dmk::kMaxClips) + ")");
     } catch (const std::exception& e) { g_err = e.what(); return false; }
     if (!build_device_model(H)) return false;
     build_statics(H);
@@ -443,15 +450,29 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
     }
     const size_t N = static_cast<size_t>(h->padded_envs);
     const int ss = dmk::sim_stride(M.nl);
+    // mocap tables: the frames of every clip of the scene, concatenated (one clip unless --kin_ctrl clips; clip 0 = the model's clip)
+    h->total_frames = 0;
+    h->ctab = dmk::ClipTable{};
+    h->ctab.num_clips = static_cast<int>(h->sa.clips.size());
+    for (size_t c = 0; c < h->sa.clips.size(); ++c) {
+        const dmh::MotionClip& mc = h->sa.clips[c];
+        dmk::ClipInfo& ci = h->ctab.info[c];
+        ci.dur = mc.duration(); ci.frame_off = h->total_frames; ci.num_frames = mc.num_frames; ci.loop = mc.loop ? 1 : 0;
+        const double* fb = mc.frame(0); const double* fe = mc.frame(mc.num_frames - 1);
+        ci.cycle_delta[0] = static_cast<float>(fe[0] - fb[0]); ci.cycle_delta[1] = 0.f; ci.cycle_delta[2] = static_cast<float>(fe[2] - fb[2]);
+        h->ctab.cdf[c] = h->sa.clip_cdf[c];
+        h->total_frames += mc.num_frames;
+    }
+    const size_t TF = static_cast<size_t>(h->total_frames);
     bool ok = chk(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
               chk(cudaMalloc(&h->d_model, sizeof(dmk::DevModel)), "cudaMalloc model") &&
               chk(cudaMalloc(&h->st.sim, N * ss * sizeof(float)), "cudaMalloc sim") &&
               chk(cudaMalloc(&h->st.time, N * dmk::kTimeDoubles * sizeof(double)), "cudaMalloc time") &&
               chk(cudaMalloc(&h->st.flags, N * dmk::kFlagInts * sizeof(int)), "cudaMalloc flags") &&
               chk(cudaMalloc(&h->st.manifold, N * M.nl * dmk::kManifoldFloats * sizeof(float)), "cudaMalloc manifold") &&
-              chk(cudaMalloc(&h->d_frame_times, sizeof(double) * M.num_frames), "cudaMalloc frame_times") &&
-              chk(cudaMalloc(&h->d_frames, sizeof(float) * M.num_frames * M.pose_dim), "cudaMalloc frames") &&
-              chk(cudaMalloc(&h->d_frame_vel, sizeof(float) * M.num_frames * M.pose_dim), "cudaMalloc frame_vel") &&
+              chk(cudaMalloc(&h->d_frame_times, sizeof(double) * TF), "cudaMalloc frame_times") &&
+              chk(cudaMalloc(&h->d_frames, sizeof(float) * TF * M.pose_dim), "cudaMalloc frames") &&
+              chk(cudaMalloc(&h->d_frame_vel, sizeof(float) * TF * M.pose_dim), "cudaMalloc frame_vel") &&
               chk(cudaMalloc(&h->d_flags4, N * 4 * sizeof(int32_t)), "cudaMalloc flags4") &&
               chk(cudaMalloc(&h->d_amp, N * M.amp_obs_size * sizeof(float)), "cudaMalloc amp") && chk(cudaMallocHost(&h->p_amp, N * M.amp_obs_size * sizeof(float)), "cudaMallocHost amp") &&
               chk(cudaMalloc(&h->st.hist, N * 2 * M.pose_dim * sizeof(float)), "cudaMalloc hist") && chk(cudaMemset(h->st.hist, 0, N * 2 * M.pose_dim * sizeof(float)), "memset hist") &&
@@ -466,15 +487,26 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
     if (M.task_kind != dmk::kTaskNone) {
         if (!(chk(cudaMalloc(&h->st.task, N * dmk::kTaskDoubles * sizeof(double)), "cudaMalloc task") &&
               chk(cudaMemset(h->st.task, 0, N * dmk::kTaskDoubles * sizeof(double)), "memset task") &&
-              chk(cudaMalloc(&h->d_goal, N * 3 * sizeof(float)), "cudaMalloc goal") && chk(cudaMallocHost(&h->p_goal, N * 3 * sizeof(float)), "cudaMallocHost goal"))) {
+              chk(cudaMalloc(&h->d_goal, N * 3 * sizeof(float)), "cudaMalloc goal") && chk(cudaMallocHost(&h->p_goal, N * 3 * sizeof(float)), "cudaMallocHost goal") &&
+              chk(cudaMalloc(&h->st.clip, N * sizeof(int)), "cudaMalloc clip") && chk(cudaMemset(h->st.clip, 0, N * sizeof(int)), "memset clip") &&
+              chk(cudaMalloc(&h->d_clip_inj, N * sizeof(int)), "cudaMalloc clip inject") &&
+              chk(cudaMalloc(&h->d_ctab, sizeof(dmk::ClipTable)), "cudaMalloc clip table") &&
+              chk(cudaMemcpy(h->d_ctab, &h->ctab, sizeof(dmk::ClipTable), cudaMemcpyHostToDevice), "memcpy clip table"))) {
             fail(); dm_destroy(h.release()); return nullptr;
         }
     }
-    std::vector<float> frames(static_cast<size_t>(M.num_frames) * M.pose_dim), fvel(frames.size());
-    std::vector<double> fv = build_frame_vel(h->sa.character, h->sa.motion);
-    for (size_t i = 0; i < frames.size(); ++i) { frames[i] = static_cast<float>(h->sa.motion.frames[i]); fvel[i] = static_cast<float>(fv[i]); }
+    h->st.ctab = h->d_ctab;
+    std::vector<float> frames(TF * M.pose_dim), fvel(frames.size());
+    std::vector<double> ftimes(TF);
+    for (size_t c = 0; c < h->sa.clips.size(); ++c) {
+        const dmh::MotionClip& mc = h->sa.clips[c];
+        const std::vector<double> fv = build_frame_vel(h->sa.character, mc);
+        const size_t off = static_cast<size_t>(h->ctab.info[c].frame_off);
+        std::copy(mc.frame_times.begin(), mc.frame_times.end(), ftimes.begin() + off);
+        for (size_t i = 0; i < mc.frames.size(); ++i) { frames[off * M.pose_dim + i] = static_cast<float>(mc.frames[i]); fvel[off * M.pose_dim + i] = static_cast<float>(fv[i]); }
+    }
     ok = chk(cudaMemcpy(h->d_model, &h->hm, sizeof(dmk::DevModel), cudaMemcpyHostToDevice), "memcpy model") &&
-         chk(cudaMemcpy(h->d_frame_times, h->sa.motion.frame_times.data(), sizeof(double) * M.num_frames, cudaMemcpyHostToDevice), "memcpy ft") &&
+         chk(cudaMemcpy(h->d_frame_times, ftimes.data(), sizeof(double) * TF, cudaMemcpyHostToDevice), "memcpy ft") &&
          chk(cudaMemcpy(h->d_frames, frames.data(), sizeof(float) * frames.size(), cudaMemcpyHostToDevice), "memcpy frames") &&
          chk(cudaMemcpy(h->d_frame_vel, fvel.data(), sizeof(float) * fvel.size(), cudaMemcpyHostToDevice), "memcpy fvel") &&
          chk(cudaMemset(h->st.sim, 0, N * ss * sizeof(float)), "memset") && chk(cudaMemset(h->st.time, 0, N * dmk::kTimeDoubles * sizeof(double)), "memset") &&
@@ -498,7 +530,7 @@ void dm_destroy(dm_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->st.task); cudaFree(h->d_goal); cudaFreeHost(h->p_goal);
+    cudaFree(h->st.task); cudaFree(h->d_goal); cudaFreeHost(h->p_goal); cudaFree(h->st.clip); cudaFree(h->d_clip_inj); cudaFree(h->d_ctab);
     cudaFree(h->d_amp); cudaFreeHost(h->p_amp); cudaFree(h->st.hist); cudaFree(h->d_model); cudaFree(h->st.sim); cudaFree(h->st.time); cudaFree(h->st.flags); cudaFree(h->st.manifold);
     cudaFree(h->d_frame_times); cudaFree(h->d_frames); cudaFree(h->d_frame_vel); cudaFree(h->d_flags4); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew);
     for (auto& p : h->d_inj) cudaFree(p);
@@ -554,7 +586,7 @@ int dm_get_time_limits(dm_handle* h, double* out) {
     return 0;
 }
 
-int dm_reset(dm_handle* h, int force_all, const double* kt, const double* mt, const double* th) {
+int dm_reset_clips(dm_handle* h, int force_all, const int* h_clip, const double* kt, const double* mt, const double* th) {
     DM_DEVICE(h);
     const double* src[3] = {kt, mt, th}; const double* dev[3] = {nullptr, nullptr, nullptr};
     std::vector<double> tmp(h->padded_envs);
@@ -564,12 +596,31 @@ int dm_reset(dm_handle* h, int force_all, const double* kt, const double* mt, co
         DM_CUDA(cudaStreamSynchronize(h->stream));
         dev[k] = h->d_inj[k];
     }
-    if (h->W == 16 ? launch_reset<16>(h, force_all, dev[0], dev[1], dev[2]) : launch_reset<32>(h, force_all, dev[0], dev[1], dev[2])) return 1;
+    const int* dclip = nullptr;
+    if (h_clip) {
+        if (h->hm.task_kind == dmk::kTaskNone) { g_err = "dm_reset_clips: clip ids can only be injected in the AMP task scenes"; return fail(); }
+        std::vector<int> ct(h->padded_envs);
+        for (int e = 0; e < h->padded_envs; ++e) {
+            ct[e] = h_clip[e < h->num_envs ? e : h->num_envs - 1];
+            if (ct[e] < 0 || ct[e] >= h->ctab.num_clips) { g_err = "dm_reset_clips: clip id out of range"; return fail(); }
+        }
+        DM_CUDA(cudaMemcpyAsync(h->d_clip_inj, ct.data(), sizeof(int) * h->padded_envs, cudaMemcpyHostToDevice, h->stream));
+        DM_CUDA(cudaStreamSynchronize(h->stream));
+        dclip = h->d_clip_inj;
+    }
+    if (h->W == 16 ? launch_reset<16>(h, force_all, dev[0], dev[1], dev[2], dclip) : launch_reset<32>(h, force_all, dev[0], dev[1], dev[2], dclip)) return 1;
     if (h->hm.task_kind != dmk::kTaskNone) {   // cSceneTargetAMP::Reset's own part for the environments that were just reset
         dmk::dm_task_reset_kernel<<<(h->padded_envs + 127) / 128, 128, 0, h->stream>>>(h->d_model, h->st, h->padded_envs);
         DM_CUDA(cudaGetLastError());
         h->launches++;
     }
+    return 0;
+}
+int dm_reset(dm_handle* h, int force_all, const double* kt, const double* mt, const double* th) { return dm_reset_clips(h, force_all, nullptr, kt, mt, th); }
+int dm_get_clip_table(dm_handle* h, int* num_clips, double* h_dur, double* h_cdf) {
+    const int n = static_cast<int>(h->sa.clips.size());
+    if (num_clips) *num_clips = n;
+    for (int c = 0; c < n; ++c) { if (h_dur) h_dur[c] = h->sa.clips[c].duration(); if (h_cdf) h_cdf[c] = h->sa.clip_cdf[c]; }
     return 0;
 }
 int dm_set_action(dm_handle* h, const float* d_actions) {
@@ -642,10 +693,13 @@ int dm_get_task_params(dm_handle* h, double* o, unsigned long long* stream) {
     if (stream) { stream[0] = h->hm.task_seed; stream[1] = h->hm.env_id_base; }
     return 0;
 }
-static int launch_amp(dm_handle* h, float* d_out, int expert, const double* d_times) {
+static int launch_amp(dm_handle* h, float* d_out, int expert, const double* d_times, const int* d_clips = nullptr) {
     constexpr int BLOCK = 64;
-    if (h->W == 16) dmk::dm_amp_obs_kernel<16, BLOCK><<<h->padded_envs / (BLOCK / 16), BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, d_out, expert, d_times, h->num_envs);
-    else dmk::dm_amp_obs_kernel<32, BLOCK><<<h->padded_envs / (BLOCK / 32), BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, d_out, expert, d_times, h->num_envs);
+    if (d_clips) {   // expert samples from per-environment dataset clips (task scenes)
+        if (h->W == 16) dmk::dm_amp_obs_kernel<16, BLOCK, true><<<h->padded_envs / (BLOCK / 16), BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, d_out, expert, d_times, h->num_envs, d_clips);
+        else dmk::dm_amp_obs_kernel<32, BLOCK, true><<<h->padded_envs / (BLOCK / 32), BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, d_out, expert, d_times, h->num_envs, d_clips);
+    } else if (h->W == 16) dmk::dm_amp_obs_kernel<16, BLOCK, false><<<h->padded_envs / (BLOCK / 16), BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, d_out, expert, d_times, h->num_envs, nullptr);
+    else dmk::dm_amp_obs_kernel<32, BLOCK, false><<<h->padded_envs / (BLOCK / 32), BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, d_out, expert, d_times, h->num_envs, nullptr);
     DM_CUDA(cudaGetLastError());
     h->launches++;
     return 0;
@@ -660,23 +714,40 @@ int dm_amp_obs_host(dm_handle* h, int expert, const double* h_kin_time, float* h
     std::memcpy(h_out, h->p_amp, bytes);
     return 0;
 }
-int dm_record_amp_obs_expert(dm_handle* h, const double* h_kin_time, float* d_out) {
+// host-side counter-based uniform for the expert draws (same finaliser as the device streams)
+static double host_u01(unsigned long long seed, unsigned long long a, unsigned long long b) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (a * 2654435761ull + b + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    return static_cast<double>(z >> 11) * (1.0 / 9007199254740992.0);
+}
+int dm_record_amp_obs_expert_clips(dm_handle* h, const int* h_clip, const double* h_kin_time, float* d_out) {
     DM_DEVICE(h);
+    const bool task = h->hm.task_kind != dmk::kTaskNone;
+    if (h_clip && !task) { g_err = "dm_record_amp_obs_expert_clips: clip ids can only be given in the AMP task scenes"; return fail(); }
     std::vector<double> tmp(h->padded_envs, 0.0);
+    std::vector<int> ct(h->padded_envs, 0);
+    if (task) {   // cSceneImitateAMP::SampleExpertMotion: cClipsController::SampleMotionID per call (SceneImitateAMP.cpp:260-277)
+        for (int e = 0; e < h->num_envs; ++e) {
+            ct[e] = h_clip ? h_clip[e] : dmk::select_clip(h->ctab, host_u01(h->seed ^ 0x657870636c6970ull, h->env_offset + e, h->amp_calls));
+            if (ct[e] < 0 || ct[e] >= h->ctab.num_clips) { g_err = "dm_record_amp_obs_expert_clips: clip id out of range"; return fail(); }
+        }
+    }
     if (h_kin_time) std::copy(h_kin_time, h_kin_time + h->num_envs, tmp.begin());
     else {   // cSceneImitateAMP::RecordAMPObsExpert draws U(0, duration) per call; here a counter-based stream per (seed, env, call)
-        const double dur = h->hm.motion_dur;
         for (int e = 0; e < h->num_envs; ++e) {
+            const double dur = task ? h->ctab.info[ct[e]].dur : h->hm.motion_dur;
             unsigned long long z = h->seed + 0x9E3779B97F4A7C15ull * ((h->env_offset + e) * 2654435761ull + 0x51ed27ull + h->amp_calls);
             z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
             tmp[e] = dur * static_cast<double>(z >> 11) * (1.0 / 9007199254740992.0);
         }
-        h->amp_calls++;
     }
+    if (!h_kin_time || (task && !h_clip)) h->amp_calls++;
     DM_CUDA(cudaMemcpyAsync(h->d_inj[0], tmp.data(), sizeof(double) * h->padded_envs, cudaMemcpyHostToDevice, h->stream));
-    DM_CUDA(cudaStreamSynchronize(h->stream));   // tmp is pageable host memory
-    return launch_amp(h, d_out, 1, h->d_inj[0]);
+    if (task) DM_CUDA(cudaMemcpyAsync(h->d_clip_inj, ct.data(), sizeof(int) * h->padded_envs, cudaMemcpyHostToDevice, h->stream));
+    DM_CUDA(cudaStreamSynchronize(h->stream));   // tmp / ct are pageable host memory
+    return launch_amp(h, d_out, 1, h->d_inj[0], task ? h->d_clip_inj : nullptr);
 }
+int dm_record_amp_obs_expert(dm_handle* h, const double* h_kin_time, float* d_out) { return dm_record_amp_obs_expert_clips(h, nullptr, h_kin_time, d_out); }
 int dm_calc_reward(dm_handle* h, float* d_out) { return dm_observe(h, nullptr, d_out); }
 int dm_get_flags(dm_handle* h, int32_t* d_flags) {
     DM_DEVICE(h);

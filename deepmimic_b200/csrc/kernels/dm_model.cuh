@@ -75,6 +75,38 @@ struct DevModel {
     // mocap tables live in separate device arrays: frame_times (double), frames / frame_vel (float, pose layout, root w-first quats)
 };
 
+// ---- clip dataset of --kin_ctrl clips (cClipsController, anim/ClipsController.cpp): the frames of all clips are concatenated in the
+// mocap tables (clip 0 first, so a one-clip scene is laid out exactly like --kin_ctrl motion); one table per handle in global memory
+constexpr int kMaxClips = 128;
+struct ClipInfo {
+    double dur;               // cMotion::GetDuration
+    int frame_off;            // first frame of the clip in frame_times / frames / frame_vel (frame_times restart at 0 for every clip)
+    int num_frames, loop;
+    float cycle_delta[3];     // cKinController::CalcCycleRootDelta
+};
+struct ClipTable {
+    int num_clips, pad_;
+    double cdf[kMaxClips];    // cClipsController::BuildClipsCDF
+    ClipInfo info[kMaxClips];
+};
+// what the clip samplers read: DevModel (the scene's single clip) in the plain instantiations, this view of one dataset clip in the CLIPS ones
+struct ClipModel {
+    double motion_dur, query_dt;
+    int loop_motion, num_frames, pose_dim;
+    float cycle_delta[3];
+};
+__host__ __device__ inline ClipModel clip_model(const ClipInfo& c, int pose_dim, double query_dt) {
+    ClipModel m; m.motion_dur = c.dur; m.query_dt = query_dt; m.loop_motion = c.loop; m.num_frames = c.num_frames; m.pose_dim = pose_dim;
+    m.cycle_delta[0] = c.cycle_delta[0]; m.cycle_delta[1] = c.cycle_delta[1]; m.cycle_delta[2] = c.cycle_delta[2];
+    return m;
+}
+// cClipsController::SelectNewMotion (ClipsController.cpp:226-236): std::upper_bound of a uniform draw in the CDF
+__host__ __device__ inline int select_clip(const ClipTable& t, double u) {
+    int lo = 0, hi = t.num_clips;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (t.cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+    return lo < t.num_clips ? lo : t.num_clips - 1;
+}
+
 // ---- per-environment state (env-major blocks; one tile of lanes reads a block with float4 loads)
 // SIM block, floats:  [0..2] basePos [4..7] baseQuat(world->base) [8..10] baseOmega [12..14] baseVel
 //                     [16 + 4 j ..] jointPos(j)  (spherical: quat xyzw; revolute: angle in .x)
@@ -97,6 +129,8 @@ struct DevState {
     float* hist;  // AMP history: DeepMimic pose | vel vectors (2 * pose_dim floats per env) of the simulated character at the last applied action
     float* pdbg;  // optional debug scratch (n x ...), may be null
     double* task; // AMP task scenes: kTaskDoubles per env (dm_task.cuh), null otherwise
+    int* clip;    // --kin_ctrl clips: active clip of every env, null for single-clip scenes
+    const ClipTable* ctab;
     int num_envs;
 };
 

@@ -50,7 +50,9 @@ __device__ __forceinline__ float quat_theta_sq(Q4 a, Q4 b) {
     float th = 2.0f * atan2f(s, fabsf(dq.w));
     return th * th;
 }
-__device__ __forceinline__ void frame_index(const DevModel& M, const double* ft, double time, int& idx, double& blend, int& cyc) {
+// MT: DevModel (the scene's clip) or ClipModel (one clip of a dataset) -- both expose motion_dur / loop_motion / num_frames / pose_dim
+template <class MT>
+__device__ __forceinline__ void frame_index(const MT& M, const double* ft, double time, int& idx, double& blend, int& cyc) {
     const double dur = M.motion_dur;
     if (!M.loop_motion) {
         cyc = static_cast<int>(floor(time / dur)); cyc = cyc < 0 ? 0 : (cyc > 1 ? 1 : cyc);
@@ -136,7 +138,8 @@ __device__ __forceinline__ DmJoint hist_load(const float* h, int pose_dim, const
     return d;
 }
 // raw clip sample (cMotion::CalcFrame / CalcFrameVel: no origin, no cycle offset) for joint `lane`
-__device__ __forceinline__ DmJoint clip_joint(const DevModel& M, const DevLink& L, const double* ft, const float* frames, const float* frame_vel, double time, bool is_root) {
+template <class MT>
+__device__ __forceinline__ DmJoint clip_joint(const MT& M, const DevLink& L, const double* ft, const float* frames, const float* frame_vel, double time, bool is_root) {
     int idx, cyc; double bld;
     frame_index(M, ft, time, idx, bld, cyc);
     const float blv = static_cast<float>(bld);
@@ -155,6 +158,10 @@ __device__ __forceinline__ DmJoint clip_joint(const DevModel& M, const DevLink& 
     else if (L.jtype == kJRevolute) { if (!over) d.w.x = (1 - blv) * v0[o] + blv * v1[o]; }
     return d;
 }
+// the clip description a kernel samples from: the model itself, or the per-environment dataset clip in the CLIPS instantiations
+template <bool CLIPS> struct ClipPick;
+template <> struct ClipPick<false> { static __device__ __forceinline__ const DevModel& get(const DevModel& m, const ClipModel&) { return m; } };
+template <> struct ClipPick<true> { static __device__ __forceinline__ const ClipModel& get(const DevModel&, const ClipModel& c) { return c; } };
 
 }  // namespace
 
@@ -341,10 +348,13 @@ __global__ void __launch_bounds__(BLOCK) dm_observe_kernel(const DevModel* __res
 // AMP observations (cSceneImitateAMP::BuildAMPObs, SceneImitateAMP.cpp:279-397): [pose now | pose prev | vel now | vel prev], one tile per
 // environment, lane = joint.  expert == 0: "now" is the simulated character, "prev" the history block (RecordAMPObsAgent, :101-113);
 // expert != 0: the raw clip at expert_time[env] and one query period earlier, ground height = the kinematic origin's y (:115-140).
-template <int W, int BLOCK>
+// TASKV: the expert sample comes from clip expert_clip[env] of the dataset (cSceneImitateAMP::SampleExpertMotion with a clips controller,
+// SceneImitateAMP.cpp:260-277) instead of the scene's single clip
+template <int W, int BLOCK, bool TASKV>
 __global__ void __launch_bounds__(BLOCK) dm_amp_obs_kernel(const DevModel* __restrict__ gm, DevState st, const double* __restrict__ frame_times,
                                                             const float* __restrict__ frames, const float* __restrict__ frame_vel, float* __restrict__ out,
-                                                            int expert, const double* __restrict__ expert_time, int num_real_envs) {
+                                                            int expert, const double* __restrict__ expert_time, int num_real_envs,
+                                                            const int* __restrict__ expert_clip) {
     using T = TileP<W>;
     const int tiles = BLOCK / W, tile = threadIdx.x / W, lane = threadIdx.x % W;
     const int env = blockIdx.x * tiles + tile;
@@ -364,8 +374,15 @@ __global__ void __launch_bounds__(BLOCK) dm_amp_obs_kernel(const DevModel* __res
         prev = hist_load(st.hist + static_cast<size_t>(env) * 2 * M.pose_dim, M.pose_dim, L, is_root);
     } else {
         const double t = expert_time[env];
-        now = clip_joint(M, L, frame_times, frames, frame_vel, t, is_root);
-        prev = clip_joint(M, L, frame_times, frames, frame_vel, t - M.query_dt, is_root);
+        ClipModel CM;
+        if constexpr (TASKV) {
+            const ClipInfo& ci = st.ctab->info[expert_clip[env]];
+            CM = clip_model(ci, M.pose_dim, M.query_dt);
+            frame_times += ci.frame_off; frames += static_cast<size_t>(ci.frame_off) * M.pose_dim; frame_vel += static_cast<size_t>(ci.frame_off) * M.pose_dim;
+        }
+        const auto& KM = ClipPick<TASKV>::get(M, CM);
+        now = clip_joint(KM, L, frame_times, frames, frame_vel, t, is_root);
+        prev = clip_joint(KM, L, frame_times, frames, frame_vel, t - M.query_dt, is_root);
         ground_h = static_cast<float>(tm[kTOrigin + 1]);
     }
     // heading of the current root (cKinTree::CalcHeadingRot, KinTree.cpp:1629-1635): rotation about y by -heading
@@ -464,12 +481,14 @@ __global__ void dm_set_action_kernel(const DevModel* __restrict__ gm, DevState s
 
 // Resets every environment whose done flag is set (or all when force != 0).  kin_time_in / max_time_in (may be null) inject the
 // random draws of the reference's reset (CalcRandKinResetTime, cTimer::Reset) so tests can bypass the RNG.
-template <int W, int BLOCK>
+// TASKV (AMP task scenes): every environment samples its own clip of the dataset (st.clip / st.ctab; clip_in injects the controller's draw)
+// and the action history is NOT re-initialised (cSceneTargetAMP::Reset bypasses cSceneImitateAMP::Reset, SceneTargetAMP.cpp:129-134).
+template <int W, int BLOCK, bool TASKV>
 __global__ void __launch_bounds__(BLOCK) dm_reset_kernel(const DevModel* __restrict__ gm, DevState st, const double* __restrict__ frame_times,
                                                           const float* __restrict__ frames, const float* __restrict__ frame_vel, int force,
                                                           const double* __restrict__ kin_time_in, const double* __restrict__ max_time_in,
                                                           const double* __restrict__ rot_theta_in, unsigned long long seed,
-                                                          unsigned long long env_id_base, int test_mode) {
+                                                          unsigned long long env_id_base, int test_mode, const int* __restrict__ clip_in) {
     using T = TileP<W>;
     const int tiles = BLOCK / W, tile = threadIdx.x / W, lane = threadIdx.x % W;
     const int env = blockIdx.x * tiles + tile;
@@ -485,13 +504,28 @@ __global__ void __launch_bounds__(BLOCK) dm_reset_kernel(const DevModel* __restr
     const bool doit = force || fl[kFDone] != 0;
     // draws
     const unsigned long long gid = env_id_base + env, cnt = static_cast<unsigned long long>(fl[7]);
-    double kt = kin_time_in ? kin_time_in[env] : u01(seed, gid, 3 * cnt) * M.motion_dur;
+    ClipModel CM;
+    double reset_time_span = M.motion_dur;
+    int new_clip = 0;
+    if constexpr (TASKV) {
+        const ClipTable& CT = *st.ctab;
+        const int prev_clip = st.clip[env];
+        // cSceneImitate::ResetKinChar draws the start time from U(0, duration of the clip that was active BEFORE the controller's reset picks
+        // the new one) -- CalcRandKinResetTime runs first (SceneImitate.cpp:331-338)
+        reset_time_span = CT.info[prev_clip].dur;
+        new_clip = doit ? (clip_in ? clip_in[env] : select_clip(CT, u01(seed ^ 0x636c697073ull, gid, cnt))) : prev_clip;
+        const ClipInfo& ci = CT.info[new_clip];
+        CM = clip_model(ci, M.pose_dim, M.query_dt);
+        frame_times += ci.frame_off; frames += static_cast<size_t>(ci.frame_off) * M.pose_dim; frame_vel += static_cast<size_t>(ci.frame_off) * M.pose_dim;
+    }
+    const auto& KM = ClipPick<TASKV>::get(M, CM);
+    double kt = kin_time_in ? kin_time_in[env] : u01(seed, gid, 3 * cnt) * reset_time_span;
     double mt = max_time_in ? max_time_in[env] : (M.time_lim_min + u01(seed, gid, 3 * cnt + 1) * (M.time_lim_max - M.time_lim_min));
     double th = rot_theta_in ? rot_theta_in[env] : (M.rand_rot_reset ? (-3.14159265358979323846 + u01(seed, gid, 3 * cnt + 2) * 6.283185307179586) : 0.0);
     if (!M.rand_rot_reset) th = 0.0;
     if (test_mode) mt = M.time_end_lim_max;
     int idx, cyc; double bld;
-    frame_index(M, frame_times, kt, idx, bld, cyc);
+    frame_index(KM, frame_times, kt, idx, bld, cyc);
     bld = fmin(fmax(bld, 0.0), 1.0);
     const float bl = static_cast<float>(bld);
     const float* f0 = frames + static_cast<size_t>(idx) * M.pose_dim; const float* f1 = f0 + M.pose_dim;
@@ -500,8 +534,8 @@ __global__ void __launch_bounds__(BLOCK) dm_reset_kernel(const DevModel* __restr
     const float sth = sinf(0.5f * static_cast<float>(th)), cth = cosf(0.5f * static_cast<float>(th));
     const Q4 orot = mkq(0.f, sth, 0.f, cth);
     // root
-    V3 rp = mk3((1 - bl) * f0[0] + bl * f1[0] + (M.loop_motion ? cyc * M.cycle_delta[0] : 0.f), (1 - bl) * f0[1] + bl * f1[1],
-                (1 - bl) * f0[2] + bl * f1[2] + (M.loop_motion ? cyc * M.cycle_delta[2] : 0.f));
+    V3 rp = mk3((1 - bl) * f0[0] + bl * f1[0] + (KM.loop_motion ? cyc * KM.cycle_delta[0] : 0.f), (1 - bl) * f0[1] + bl * f1[1],
+                (1 - bl) * f0[2] + bl * f1[2] + (KM.loop_motion ? cyc * KM.cycle_delta[2] : 0.f));
     V3 rv = mk3((1 - bl) * v0[0] + bl * v1[0], (1 - bl) * v0[1] + bl * v1[1], (1 - bl) * v0[2] + bl * v1[2]);
     KinJoint kr = sample_joint(M.link[0], f0, f1, v0, v1, bl, true);
     Q4 rq = qmul(orot, kr.q); if (rq.w < 0) rq = mkq(-rq.x, -rq.y, -rq.z, -rq.w);
@@ -563,16 +597,17 @@ __global__ void __launch_bounds__(BLOCK) dm_reset_kernel(const DevModel* __restr
         tm[kTOrigin + 2] = static_cast<double>(basePos.z / M.scale) - rrp.z;
         tm[kTOriginRot] = cth; tm[kTOriginRot + 1] = 0.0; tm[kTOriginRot + 2] = sth; tm[kTOriginRot + 3] = 0.0;
         fl[kFNeedAction] = 1; fl[kFDone] = 0; fl[kFTerminate] = 0; fl[kFValid] = 1; fl[kFFallen] = 0; fl[kFUpdates] = 0; fl[7] = fl[7] + 1;
+        if constexpr (TASKV) st.clip[env] = new_clip;
     }
-    if (act && st.hist) {
+    if (!TASKV && act && st.hist) {
         // cSceneImitateAMP::InitHist (SceneImitateAMP.cpp:153-165): the kinematic character one query period before the controller time,
         // with the final origin (cKinCharacter::CalcPose / CalcVel, KinCharacter.cpp:363-406)
         const double tprev = kt - M.query_dt;
-        DmJoint d = clip_joint(M, L, frame_times, frames, frame_vel, tprev, lane == 0);
+        DmJoint d = clip_joint(KM, L, frame_times, frames, frame_vel, tprev, lane == 0);
         if (lane == 0) {
             int idx, cyc; double bld;
-            frame_index(M, frame_times, tprev, idx, bld, cyc);
-            if (M.loop_motion) { d.p.x += cyc * M.cycle_delta[0]; d.p.z += cyc * M.cycle_delta[2]; }
+            frame_index(KM, frame_times, tprev, idx, bld, cyc);
+            if (KM.loop_motion) { d.p.x += cyc * KM.cycle_delta[0]; d.p.z += cyc * KM.cycle_delta[2]; }
             const V3 org = mk3(basePos.x / M.scale, basePos.y / M.scale, basePos.z / M.scale) - qrot(orot, rp);
             d.p = qrot(orot, d.p) + org;
             d.q = qmul(orot, d.q); if (d.q.w < 0) d.q = mkq(-d.q.x, -d.q.y, -d.q.z, -d.q.w);
@@ -635,9 +670,13 @@ __global__ void dm_task_observe_kernel(const DevModel* __restrict__ gm, DevState
 
 template __global__ void dm_observe_kernel<16, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
 template __global__ void dm_observe_kernel<32, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
-template __global__ void dm_amp_obs_kernel<16, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int);
-template __global__ void dm_amp_obs_kernel<32, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int);
-template __global__ void dm_reset_kernel<16, 64>(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*, unsigned long long, unsigned long long, int);
-template __global__ void dm_reset_kernel<32, 64>(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*, unsigned long long, unsigned long long, int);
+template __global__ void dm_amp_obs_kernel<16, 64, false>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int, const int*);
+template __global__ void dm_amp_obs_kernel<32, 64, false>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int, const int*);
+template __global__ void dm_amp_obs_kernel<16, 64, true>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int, const int*);
+template __global__ void dm_amp_obs_kernel<32, 64, true>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int, const int*);
+template __global__ void dm_reset_kernel<16, 64, false>(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*, unsigned long long, unsigned long long, int, const int*);
+template __global__ void dm_reset_kernel<32, 64, false>(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*, unsigned long long, unsigned long long, int, const int*);
+template __global__ void dm_reset_kernel<16, 64, true>(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*, unsigned long long, unsigned long long, int, const int*);
+template __global__ void dm_reset_kernel<32, 64, true>(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*, unsigned long long, unsigned long long, int, const int*);
 
 }  // namespace dmk

@@ -1217,7 +1217,9 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             if (lane == 0 && alive) {
                 const double timer = tm[kTTimer] + dt;
                 double kin_time = tm[kTKin];
-                const double dur = M.motion_dur;
+                double dur_ = M.motion_dur;
+                if constexpr (TASK) dur_ = st.ctab->info[st.clip[env]].dur;   // the environment's own clip of the dataset
+                const double dur = dur_;
                 double p0 = kin_time / dur; p0 -= floor(p0);
                 kin_time += dt;
                 double p1 = kin_time / dur; p1 -= floor(p1);
@@ -1230,7 +1232,16 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                                       static_cast<double>(sB[0]) / M.scale, static_cast<double>(sB[2]) / M.scale, simq, M.sync_root_pos != 0, M.sync_root_rot != 0);
                     }
                 }
-                if (!ROOTROT && M.loop_motion && p1 < p0 && M.sync_root_pos) {
+                if constexpr (TASK) {
+                    // task scenes: same wrap handling on the environment's own clip of the dataset
+                    const ClipInfo& ci = st.ctab->info[st.clip[env]];
+                    if (ci.loop && p1 < p0 && M.sync_root_pos) {
+                        const double simq[4] = {static_cast<double>(sB[3]), static_cast<double>(sB[4]), static_cast<double>(sB[5]), static_cast<double>(sB[6])};
+                        kin_wrap_sync(frame_times + ci.frame_off, frames + static_cast<size_t>(ci.frame_off) * M.pose_dim, M.pose_dim, ci.num_frames, ci.cycle_delta, dur, kin_time,
+                                      tm + kTOrigin, tm + kTOriginRot, static_cast<double>(sB[0]) / M.scale, static_cast<double>(sB[2]) / M.scale, simq, true, false);
+                    }
+                }
+                if (!ROOTROT && !TASK && M.loop_motion && p1 < p0 && M.sync_root_pos) {
                     // SyncKinCharNewCycle: snap the clip's root x,z (at the new time) onto the simulated root
                     double org_x = tm[kTOrigin], org_z = tm[kTOrigin + 2];
                     int cyc = static_cast<int>(floor(kin_time / dur));

@@ -95,6 +95,12 @@ int dm_record_goal(dm_handle* h, float* d_out);              /* [num_envs x goal
  * expose one environment's task block (16 doubles: target x, z, speed, heading, timer, timer max, previous-action COM[3], COM[3], draw
  * counter, reset counter) and the scene constants + draw-stream key for the parity tests. */
 int dm_goal_host(dm_handle* h, float* h_out);
+/* Clip datasets (--kin_ctrl clips, cClipsController; task scenes only, experimental like them).  dm_reset_clips = dm_reset with the
+ * controller's clip draw injected (h_clip: num_envs ints, may be NULL); dm_record_amp_obs_expert_clips = the expert observation from a given
+ * clip per environment (cSceneImitateAMP::SampleExpertMotion); dm_get_clip_table reports the dataset (durations, sampling CDF). */
+int dm_reset_clips(dm_handle* h, int force_all, const int* h_clip, const double* h_kin_time, const double* h_max_time, const double* h_rot_theta);
+int dm_record_amp_obs_expert_clips(dm_handle* h, const int* h_clip, const double* h_kin_time, float* d_out);
+int dm_get_clip_table(dm_handle* h, int* num_clips, double* h_dur, double* h_cdf);
 int dm_get_task_state(dm_handle* h, int env, double* h_out16);
 int dm_set_task_state(dm_handle* h, int env, const double* h_in16);
 int dm_get_task_params(dm_handle* h, double* h_out16, unsigned long long* h_stream2);

@@ -402,8 +402,13 @@ def test_task_scenes_stay_refused_without_the_opt_in(asset_root, monkeypatch):
     with pytest.raises(RuntimeError, match="Unsupported scene"):
         capi.HostModel(["--kin_ctrl", "motion", "--motion_file", "data/motions/humanoid3d_run.txt"] + TARGET[2:], asset_root)
     monkeypatch.setenv("DM_EXPERIMENTAL_TASK_SCENES", "1")
-    with pytest.raises(RuntimeError, match="more than one clip"):
-        capi.HostModel(TARGET, asset_root)                                      # clip datasets are oracle-only so far
+    m = capi.HostModel(TARGET, asset_root)                                      # the mini dataset (4 clips) loads in a task scene ...
+    assert m.dims.goal_size == 3
+    dur, cdf = m.clip_table()
+    o = Oracle(TARGET, asset_root)
+    np.testing.assert_array_equal(dur, o.clip_table()[0]); np.testing.assert_array_equal(cdf, o.clip_table()[2])
+    with pytest.raises(RuntimeError, match="more than one clip"):               # ... but not in the plain AMP imitation scene
+        capi.HostModel(["--scene", "imitate_amp"] + TARGET, asset_root)
 
 
 @pytest.mark.parametrize("sync_rot", [True, False])

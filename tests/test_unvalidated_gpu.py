@@ -16,9 +16,9 @@ from tests.oracle_binding import Oracle
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("DM_RUN_UNVALIDATED_GPU_TESTS") != "1", reason="task-scene device code not yet validated on hardware (opt-in)")]
 
-SINGLE = ["--kin_ctrl", "motion", "--motion_file", "data/motions/humanoid3d_run.txt"]
-TARGET = ["--rand_target_time_min", "1", "--rand_target_time_max", "2"] + SINGLE + ["--arg_file", "args/train_amp_target_humanoid3d_locomotion_args.txt"]
-HEADING = SINGLE + ["--arg_file", "args/train_amp_heading_humanoid3d_locomotion_args.txt"]
+MINI = ["--motion_file", "data/datasets/test_clips_mini.txt"]                    # 4-clip dataset of the committed asset archive (--kin_ctrl clips)
+TARGET = ["--rand_target_time_min", "1", "--rand_target_time_max", "2"] + MINI + ["--arg_file", "args/train_amp_target_humanoid3d_locomotion_args.txt"]
+HEADING = MINI + ["--arg_file", "args/train_amp_heading_humanoid3d_locomotion_args.txt"]
 N = 32
 
 
@@ -32,14 +32,24 @@ def test_task_goal_reward_and_updates_match_the_oracle(asset_root, args, monkeyp
     core = capi.BatchedCore(args, N, asset_root, seed=21, global_env_offset=100)
     P, task_seed, env_base = core.task_params()
     assert core.dims.goal_size == 3 and env_base == 100
-    kin_time = np.linspace(0.0, 0.7, N); theta = np.linspace(-3.0, 3.0, N); max_time = np.full(N, 20.0)
-    core.reset(force_all=True, kin_time=kin_time, max_time=max_time, rot_theta=theta)
+    kin_time = np.linspace(0.0, 0.7, N); theta = np.linspace(-3.0, 3.0, N); max_time = np.full(N, 20.0); clip = np.arange(N) % 4
+    core.reset(force_all=True, kin_time=kin_time, max_time=max_time, rot_theta=theta, clip=clip)
     oracles = []
     for e in range(N):
         o = Oracle(args, asset_root)
         o.set_task_stream(task_seed, env_base + e, 0)
-        o.reset(kin_time[e], theta[e], 20.0)
+        o.reset(kin_time[e], theta[e], 20.0, clip=int(clip[e]))
         oracles.append(o)
+    # the reset state itself (one clip per environment) and the expert observations from given clips
+    st0 = torch.zeros(N, core.dims.state_size, device="cuda"); amp = torch.zeros(N, core.dims.amp_obs_size, device="cuda")
+    torch.cuda.synchronize()
+    core.observe(st0, None)
+    eclip = (np.arange(N) + 1) % 4; etime = np.linspace(0.05, 0.75, N)
+    core.amp_obs_expert(amp, kin_time=etime, clip=eclip)
+    core.sync()
+    for e, o in enumerate(oracles):
+        np.testing.assert_allclose(st0[e].cpu().numpy(), o.record_state(), atol=2e-4)
+        np.testing.assert_allclose(amp[e].cpu().numpy(), o.record_amp_obs_expert(etime[e], clip=int(eclip[e])), atol=2e-3)
     goal = torch.zeros(N, 3, device="cuda"); rew = torch.zeros(N, device="cuda"); flags = torch.zeros(N, 4, dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
     rng = np.random.default_rng(5)
