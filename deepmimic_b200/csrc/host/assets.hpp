@@ -114,7 +114,12 @@ struct SceneConfig {
     bool enable_min_tar_vel = false;
     double max_heading_turn_rate = 0.15, sharp_turn_prob = 0.025, speed_change_prob = 0.1;
     double tar_speed_min = 1, tar_speed_max = 1, vel_reward_scale = 1;
-    bool is_task_scene() const { return scene == "target_amp" || scene == "heading_amp"; }
+    // cSceneHeadingAMPGetup::ParseArgs (SceneHeadingAMPGetup.cpp:76-85; constructor defaults :60-70)
+    std::vector<int> getup_motion_ids;
+    double getup_height_root = 0.5, getup_height_head = 0.5, recover_episode_prob = 0.0;
+    int head_id = 0;
+    bool is_task_scene() const { return scene == "target_amp" || scene == "heading_amp" || scene == "heading_amp_getup"; }
+    bool is_heading_scene() const { return scene == "heading_amp" || scene == "heading_amp_getup"; }
 };
 
 inline int joint_param_size(int type, bool is_root) {
@@ -310,7 +315,7 @@ inline SceneConfig parse_scene_config(const ArgParser& ap) {
     ap.ParseDouble("time_end_lim_min", sc.time_end_lim_min);
     ap.ParseDouble("time_end_lim_max", sc.time_end_lim_max);
     ap.ParseInt("anneal_samples", sc.anneal_samples);
-    if (sc.scene == "heading_amp") { sc.rand_target_time_min = 0.2; sc.rand_target_time_max = 0.5; }
+    if (sc.is_heading_scene()) { sc.rand_target_time_min = 0.2; sc.rand_target_time_max = 0.5; }
     ap.ParseDouble("rand_target_time_min", sc.rand_target_time_min);
     ap.ParseDouble("rand_target_time_max", sc.rand_target_time_max);
     ap.ParseDouble("max_target_dist", sc.max_target_dist);
@@ -325,8 +330,13 @@ inline SceneConfig parse_scene_config(const ArgParser& ap) {
     sc.tar_speed_min = sc.tar_speed_max = sc.tar_speed;
     ap.ParseDouble("tar_speed_min", sc.tar_speed_min);
     ap.ParseDouble("tar_speed_max", sc.tar_speed_max);
-    if (sc.scene == "heading_amp") sc.tar_speed = std::min(std::max(sc.tar_speed, sc.tar_speed_min), sc.tar_speed_max);   // SceneHeadingAMP.cpp:85
+    if (sc.is_heading_scene()) sc.tar_speed = std::min(std::max(sc.tar_speed, sc.tar_speed_min), sc.tar_speed_max);   // SceneHeadingAMP.cpp:85
     ap.ParseDouble("vel_reward_scale", sc.vel_reward_scale);
+    ap.ParseInts("getup_motion_ids", sc.getup_motion_ids);
+    ap.ParseDouble("getup_height_root", sc.getup_height_root);
+    ap.ParseDouble("getup_height_head", sc.getup_height_head);
+    ap.ParseInt("head_id", sc.head_id);
+    ap.ParseDouble("recover_episode_prob", sc.recover_episode_prob);
     return sc;
 }
 

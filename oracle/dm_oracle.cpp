@@ -8,7 +8,7 @@
 //   cSimCharacter / cSimBodyJoint / cSimBodyLink       R/DeepMimicCore/sim/*.cpp
 //   cCtPDController / cImpPDController                 R/DeepMimicCore/sim/*.cpp
 //   cKinCharacter / cMotion / cMotionController        R/DeepMimicCore/anim/*.cpp
-//   cClipsController (clip datasets), cSceneImitateAMP, cSceneTargetAMP, cSceneHeadingAMP (goal, task reward, target updates)
+//   cClipsController (clip datasets), cSceneImitateAMP, cSceneTargetAMP, cSceneHeadingAMP, cSceneHeadingAMPGetup (goal, task reward, target updates)
 // DeepMimic's own math runs in double (rbd.hpp, omath.hpp); the Bullet 2.88 stage runs in float
 // (bullet_mb.hpp).  PARITY UNPINNED: the reference ships no tests or golden vectors and Bullet is
 // an un-vendored dependency, so this oracle is pinned only by the known-answer tests of
@@ -63,9 +63,14 @@ struct Oracle {
     int mode = 0;  // 0 train, 1 test
     VecD joint_weights;
     // ---- AMP task scenes: cSceneTargetAMP / cSceneHeadingAMP (scenes/SceneTargetAMP.cpp, SceneHeadingAMP.cpp)
-    enum SceneKind { kImitate = 0, kImitateAMP = 1, kTargetAMP = 2, kHeadingAMP = 3 };
+    enum SceneKind { kImitate = 0, kImitateAMP = 1, kTargetAMP = 2, kHeadingAMP = 3, kHeadingGetup = 4 };
     int scene_kind = kImitate;
-    bool IsTask() const { return scene_kind == kTargetAMP || scene_kind == kHeadingAMP; }
+    bool IsTask() const { return scene_kind == kTargetAMP || scene_kind == kHeadingAMP || scene_kind == kHeadingGetup; }
+    bool IsHeading() const { return scene_kind == kHeadingAMP || scene_kind == kHeadingGetup; }
+    // cSceneHeadingAMPGetup (scenes/SceneHeadingAMPGetup.cpp): mGetupTimer (max = mGetupTime), mGetupMotionFlags
+    double getup_time = 0, getup_timer_time = 0;
+    std::vector<char> getup_flags;
+    bool CheckGettingUp() const { return !(getup_timer_time >= getup_time); }   // :296-299
     double tgt_timer_time = 0, tgt_timer_max = 0;   // mTargetTimer
     D3 target_pos;                                   // mTargetPos
     double target_speed = 1, target_heading = 0;     // mTargetSpeed, mTargetHeading
@@ -82,7 +87,16 @@ struct Oracle {
         else if (sa.cfg.scene == "imitate_amp") scene_kind = kImitateAMP;
         else if (sa.cfg.scene == "target_amp") scene_kind = kTargetAMP;
         else if (sa.cfg.scene == "heading_amp") scene_kind = kHeadingAMP;
-        else throw std::runtime_error("oracle: scene '" + sa.cfg.scene + "' is not restated (imitate, imitate_amp, target_amp, heading_amp)");
+        else if (sa.cfg.scene == "heading_amp_getup") scene_kind = kHeadingGetup;
+        else throw std::runtime_error("oracle: scene '" + sa.cfg.scene + "' is not restated (imitate, imitate_amp, target_amp, heading_amp, heading_amp_getup)");
+        if (scene_kind == kHeadingGetup) {   // Init: RecordGetupMotionFlags + CalcGetupTime (:87-98,221-243,262-287)
+            getup_flags.assign(sa.clips.size(), 0);
+            for (int id : sa.cfg.getup_motion_ids) {
+                if (id < 0 || id >= static_cast<int>(sa.clips.size())) throw std::runtime_error("oracle: getup_motion_ids out of range");
+                getup_flags[id] = 1; getup_time = std::max(getup_time, sa.clips[id].duration());
+            }
+            getup_timer_time = getup_time;   // ResetGetupTimer -> EndGetup
+        }
         target_speed = sa.cfg.tar_speed;
         BuildKinMotion();
         BuildSimCharacter();
@@ -427,6 +441,7 @@ struct Oracle {
     // CalcRandKinResetTime runs before kin_char->Reset() (SceneImitate.cpp:331-338); a sampler that wants the reference's
     // distribution must do the same.
     void Reset(double rand_kin_time, double rand_theta, double max_time, int clip = -1) {
+        if (scene_kind == kHeadingGetup && ActivateRecoveryEpisode()) { ResetRecoveryEpisode(max_time); return; }   // SceneHeadingAMPGetup.cpp:111-123
         if (clip >= 0) ActivateMotion(clip);
         timer_time = 0;
         timer_max = (mode == 1) ? sa.cfg.time_end_lim_max : max_time;  // cRLSceneSimChar::ResetTimers (RLSceneSimChar.cpp:277-284)
@@ -465,6 +480,24 @@ struct Oracle {
         // (SceneTargetAMP.cpp:129-134), so the task scenes keep the history of the last applied action across resets.
         if (!IsTask()) InitHist();
         if (IsTask()) { TargetTimerReset(); ResetTarget(); }   // SceneTargetAMP.cpp:132-133
+        if (scene_kind == kHeadingGetup) {
+            // ResetTimers (virtual, inside the base reset) -> ResetGetupTimer -> EndGetup; then SyncGetupTimer: an episode that starts in a
+            // get-up clip starts getting up at the clip's time (SceneHeadingAMPGetup.cpp:161-165,179-199)
+            getup_timer_time = getup_time;
+            if (getup_flags[cur_clip]) getup_timer_time = kin_time;
+        }
+    }
+    // cSceneHeadingAMPGetup::ActivateRecoveryEpisode (:301-317).  The member mIsRecoveryEpisode is shadowed by a local in Reset() and never
+    // becomes true, so the "!mIsRecoveryEpisode" guard never blocks.
+    bool ActivateRecoveryEpisode() {
+        if (mode == 0 && sa.cfg.recover_episode_prob > 0.0 && CheckTerminate() == 1) return FlipCoin(sa.cfg.recover_episode_prob);
+        return false;
+    }
+    // cSceneHeadingAMPGetup::ResetRecoveryEpisode (:40-58): the fallen character stays where it is; only the timers and the controller restart
+    void ResetRecoveryEpisode(double max_time) {
+        timer_time = 0; timer_max = (mode == 1) ? sa.cfg.time_end_lim_max : max_time;   // ResetTimers
+        getup_timer_time = 0;                                                            // ResetGetupTimer (-> EndGetup) then BeginGetup
+        ctrl_time = 0; need_new_action = true; prev_action_time = 0; init_time_offset = 0; prev_action_com = D3();   // ctrl->Reset()
     }
     // cSceneSimChar::ResolveCharGroundIntersect (SceneSimChar.cpp:542-583); AABBs from btCollisionShape::getAabb [B288-mem]
     void ResolveCharGroundIntersect() {
@@ -487,7 +520,8 @@ struct Oracle {
     // =================================================================== per-update hot loop
     // cSceneSimChar::Update (SceneSimChar.cpp:136-161)
     void Update(double dt) {
-        timer_time += dt;                    // cScene::Update
+        timer_time += dt;                    // cScene::Update -> UpdateTimers
+        if (scene_kind == kHeadingGetup) getup_timer_time += dt;   // cSceneHeadingAMPGetup::UpdateTimers (:167-171)
         if (dt < 0) return;
         UpdateKinChar(dt);                   // cSceneImitate::UpdateCharacters (SceneImitate.cpp:300-304)
         UpdateSimChar(dt);
@@ -502,6 +536,9 @@ struct Oracle {
         if (IsTask()) {   // cSceneTargetAMP::Update (SceneTargetAMP.cpp:136-145)
             UpdateTarget(dt);
             if (tgt_timer_time >= tgt_timer_max) TargetTimerReset();
+        }
+        if (scene_kind == kHeadingGetup && mode == 1) {   // UpdateTestGetup (:245-254): a fall in test mode starts a get-up instead of ending the episode
+            if (ContactFall() && !CheckGettingUp()) getup_timer_time = 0;
         }
     }
     // cSceneImitate::UpdateKinChar + SyncKinCharNewCycle (SceneImitate.cpp:306-318,420-444)
@@ -713,16 +750,25 @@ struct Oracle {
         for (int k = 0; k < m.n; ++k) if (m.pt[k].distance1 <= tol) return true;
         return false;
     }
+    bool ContactFall() const {   // cSimCharacter::HasFallen: any fall-contact body touching the ground
+        if (sa.cfg.enable_char_contact_fall) for (int b = 0; b < nj; ++b) if (cm->bodies[b].fall_contact && BodyInContact(b)) return true;
+        return false;
+    }
     bool HasFallen() const {  // cSceneImitate::HasFallen (SceneImitate.cpp:466-475) -> cSceneSimChar::HasFallen (SceneSimChar.cpp:822-841)
-        bool fallen = false;
-        if (sa.cfg.enable_char_contact_fall) for (int b = 0; b < nj; ++b) if (cm->bodies[b].fall_contact && BodyInContact(b)) { fallen = true; break; }
+        // cSceneHeadingAMPGetup::HasFallenContact (:256-265): no contact fall while getting up
+        bool fallen = (scene_kind == kHeadingGetup && CheckGettingUp()) ? false : ContactFall();
         if (sa.cfg.enable_root_rot_fail) fallen |= QuatDiffTheta(SimRootRot(), GetRootRot(kin_pose)) > 0.5 * M_PI;
         return fallen;
     }
     // cSceneImitate::CalcReward / CalcRewardImitate (SceneImitate.cpp:7-127,163-175)
     double CalcReward(double* dbg = nullptr) const {
         if (scene_kind == kTargetAMP) return CalcRewardTarget();
-        if (scene_kind == kHeadingAMP) return CalcRewardHeading();
+        if (scene_kind == kHeadingGetup && CheckGettingUp()) {   // cSceneHeadingAMPGetup::CalcRewardGetup (:18-38), flat ground at 0
+            const double root_h = std::min(std::max(SimRootPos().y / sa.cfg.getup_height_root, 0.0), 1.0);
+            const double head_h = std::min(std::max(BodyPos(sa.cfg.head_id).y / sa.cfg.getup_height_head, 0.0), 1.0);
+            return 0.2 * root_h + 0.8 * head_h;
+        }
+        if (IsHeading()) return CalcRewardHeading();
         if (HasFallen()) return 0;
         double pose_w = 0.5, vel_w = 0.05, end_eff_w = 0.15, root_w = 0.2, com_w = 0.1;
         double total_w = pose_w + vel_w + end_eff_w + root_w + com_w;
@@ -809,12 +855,12 @@ struct Oracle {
         target_pos = D3(root.x + dist * std::cos(theta), 0, root.z + dist * std::sin(theta));
     }
     void SetTargetSpeed(double v) {   // cSceneHeadingAMP::SetTargetSpeed clamps (SceneHeadingAMP.cpp:90-94)
-        target_speed = (scene_kind == kHeadingAMP) ? std::min(std::max(v, sa.cfg.tar_speed_min), sa.cfg.tar_speed_max) : v;
+        target_speed = IsHeading() ? std::min(std::max(v, sa.cfg.tar_speed_min), sa.cfg.tar_speed_max) : v;
     }
     // cSceneTargetAMP::ResetTarget / cSceneHeadingAMP::ResetTarget (SceneTargetAMP.cpp:248-251, SceneHeadingAMP.cpp:207-217)
     void ResetTarget() {
         ResetTargetPos();
-        if (scene_kind == kHeadingAMP) {
+        if (IsHeading()) {
             const double speed = RandDouble(sa.cfg.tar_speed_min, sa.cfg.tar_speed_max);
             target_heading = 0;
             SetTargetSpeed(speed);
@@ -826,7 +872,7 @@ struct Oracle {
         tgt_timer_time += dt;
         const bool timer_end = tgt_timer_time >= tgt_timer_max;
         if (timer_end) ResetTargetPos();
-        if (scene_kind == kHeadingAMP && timer_end) {
+        if (IsHeading() && timer_end) {
             // UpdateTargetHeading (SceneHeadingAMP.cpp:148-180)
             double delta_heading;
             if (FlipCoin(sa.cfg.sharp_turn_prob)) delta_heading = RandDouble(-M_PI, M_PI);
@@ -836,7 +882,7 @@ struct Oracle {
             if (FlipCoin(sa.cfg.speed_change_prob)) SetTargetSpeed(RandDouble(sa.cfg.tar_speed_min, sa.cfg.tar_speed_max));
         }
     }
-    int GoalSize() const { return IsTask() ? 3 : 0; }   // SceneTargetAMP.cpp:217-220, SceneHeadingAMP.cpp:131-134; 0 otherwise (RLSceneSimChar.cpp:88-91)
+    int GoalSize() const { return scene_kind == kHeadingGetup ? 4 : (IsTask() ? 3 : 0); }   // + getup phase (SceneHeadingAMPGetup.cpp:135-140)   // SceneTargetAMP.cpp:217-220, SceneHeadingAMP.cpp:131-134; 0 otherwise (RLSceneSimChar.cpp:88-91)
     // cSceneTargetAMP::RecordGoal (SceneTargetAMP.cpp:185-215) / cSceneHeadingAMP::RecordGoal (SceneHeadingAMP.cpp:136-151)
     void RecordGoal(double* out) const {
         if (scene_kind == kTargetAMP) {
@@ -848,9 +894,10 @@ struct Oracle {
                 rel = (Rh * rel) / dist;
             } else rel = D3(1, 0, 0);
             out[0] = rel.x; out[1] = rel.z; out[2] = dist;
-        } else if (scene_kind == kHeadingAMP) {
+        } else if (IsHeading()) {
             const double th = target_heading - CalcHeading(GetRootRot(pose));
             out[0] = std::cos(th); out[1] = -std::sin(th); out[2] = target_speed;
+            if (scene_kind == kHeadingGetup) out[3] = std::min(std::max(1.0 - getup_timer_time / getup_time, 0.0), 1.0);   // CalcGetupPhase (:289-294)
         }
     }
     bool CheckTarDistFail() const {   // SceneTargetAMP.cpp:281-292; always false in the heading scene (SceneHeadingAMP.cpp:219-222)
@@ -1059,6 +1106,11 @@ void dmo_set_task_state(void* h, const double* in) {
     Oracle* o = static_cast<Oracle*>(h);
     o->target_pos = orc::D3(in[0], in[1], in[2]); o->target_speed = in[3]; o->target_heading = in[4]; o->tgt_timer_time = in[5]; o->tgt_timer_max = in[6];
     o->prev_action_com = orc::D3(in[7], in[8], in[9]);
+}
+// heading_amp_getup: out[0] = get-up timer, out[1] = get-up time (its end), out[2] = getting up (0 / 1), out[3] = contact fall ignoring the get-up override
+void dmo_get_getup_state(void* h, double* out) {
+    Oracle* o = static_cast<Oracle*>(h);
+    out[0] = o->getup_timer_time; out[1] = o->getup_time; out[2] = o->CheckGettingUp() ? 1 : 0; out[3] = o->ContactFall() ? 1 : 0;
 }
 int dmo_check_target_succ(void* h) { return static_cast<Oracle*>(h)->CheckTargetSucc() ? 1 : 0; }
 int dmo_enable_amp_task_reward(void* h) { return static_cast<Oracle*>(h)->IsTask() ? 1 : 0; }   // SceneTargetAMP.cpp:222-225

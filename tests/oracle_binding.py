@@ -113,6 +113,12 @@ class Oracle:
         o = np.concatenate([np.asarray(target_pos, dtype=np.float64), [target_speed, target_heading, timer, timer_max], np.asarray(prev_action_com, dtype=np.float64)])
         self.L.dmo_set_task_state(self.h, dp(o))
 
+    def getup_state(self):
+        """heading_amp_getup: dict(timer, getup_time, getting_up, contact_fall)"""
+        o = np.zeros(4)
+        self.L.dmo_get_getup_state(self.h, dp(o))
+        return dict(timer=o[0], getup_time=o[1], getting_up=bool(o[2]), contact_fall=bool(o[3]))
+
     def check_target_succ(self):
         return bool(self.L.dmo_check_target_succ(self.h))
 

@@ -407,6 +407,8 @@ def test_task_scenes_stay_refused_without_the_opt_in(asset_root, monkeypatch):
     dur, cdf = m.clip_table()
     o = Oracle(TARGET, asset_root)
     np.testing.assert_array_equal(dur, o.clip_table()[0]); np.testing.assert_array_equal(cdf, o.clip_table()[2])
+    with pytest.raises(RuntimeError, match="Unsupported scene"):                # the get-up variant is restated in the oracle only
+        capi.HostModel(["--scene", "heading_amp_getup", "--getup_motion_ids", "1", "2"] + HEADING, asset_root)
     with pytest.raises(RuntimeError, match="more than one clip"):               # ... but not in the plain AMP imitation scene
         capi.HostModel(["--scene", "imitate_amp"] + TARGET, asset_root)
 
@@ -495,3 +497,131 @@ def test_fixture_task_policies_in_the_oracle_without_the_reference_tree(asset_ro
         assert succ >= 60 and np.mean(rew) > 0.4, (succ, np.mean(rew))      # measured: 161 steps inside the radius, mean 0.60
     else:
         assert np.mean(rew) > 0.85, np.mean(rew)                              # measured: 0.96
+
+
+# ------------------------------------------------------------------------------------------------ heading_amp_getup (cSceneHeadingAMPGetup)
+# the logic does not care what the flagged clips show: clips 1 and 2 of the mini dataset stand in for the get-up motions
+GETUP = ["--scene", "heading_amp_getup", "--getup_motion_ids", "1", "2", "--getup_height_root", "1.2", "--getup_height_head", "2.0", "--head_id", "2"] + HEADING   # heights above a standing character: unsaturated reward
+
+
+def test_getup_goal_reward_and_timer_known_answers(asset_root):
+    """SceneHeadingAMPGetup.cpp: goal = heading goal + get-up phase (:125-140,289-294), get-up reward (:18-38), timer sync with a get-up clip at
+    reset (:179-199), no contact fall while getting up (:256-265)."""
+    o = Oracle(GETUP, asset_root)
+    dur = o.clip_table()[0]
+    T = max(dur[1], dur[2])
+    assert o.goal_size == 4 and o.getup_state()["getup_time"] == T
+    o.set_task_stream(2, 0, 0)
+    o.reset(0.4, 0.3, 20.0, clip=1)                                               # starts inside a get-up clip: getting up from its time
+    g = o.getup_state()
+    assert g["getting_up"] and g["timer"] == 0.4
+    goal = o.record_goal()
+    assert goal[3] == pytest.approx(1.0 - 0.4 / T, abs=1e-12)
+    np.testing.assert_allclose(goal[:2], [math.cos(-heading_of(o.get_pose()[0])), -math.sin(-heading_of(o.get_pose()[0]))], atol=1e-12)   # target heading 0
+    step_policy(o)
+    root_y, head_y = o.get_pose()[0][1], o.body_state()[0][2][1]
+    want = 0.2 * min(max(root_y / 1.2, 0.0), 1.0) + 0.8 * min(max(head_y / 2.0, 0.0), 1.0)
+    assert o.calc_reward() == pytest.approx(want, abs=1e-12) and 0.5 < want < 1.0
+    assert o.getup_state()["timer"] == pytest.approx(0.4 + 20 / 600.0, abs=1e-12)
+    # throw the character down while it is "getting up": contact, but neither fallen nor terminated; once the get-up time is over it is
+    rng = np.random.default_rng(1)
+    st = o.action_statics()
+    seen_protected = seen_fail = False
+    for k in range(120):
+        step_policy(o, np.clip(-st[0] + 1.0 / st[1] * rng.standard_normal(o.action_size), st[2], st[3]))
+        g = o.getup_state()
+        if g["contact_fall"] and g["getting_up"]:
+            seen_protected = True
+            assert not o.has_fallen() and o.check_terminate() == 0
+        if g["contact_fall"] and not g["getting_up"]:
+            seen_fail = True
+            assert o.has_fallen() and o.check_terminate() == 1 and o.calc_reward() == 0.0   # heading reward of a fallen character
+            break
+    assert seen_protected and seen_fail
+    # an episode that starts in an ordinary clip is not getting up: phase 0 and the heading reward
+    o.reset(0.2, 0.0, 20.0, clip=0)
+    assert not o.getup_state()["getting_up"] and o.record_goal()[3] == 0.0
+    o2 = Oracle(HEADING, asset_root)
+    o2.set_task_stream(2, 0, o.task_counter() - 4); o2.reset(0.2, 0.0, 20.0, clip=0)   # the reset consumed 4 draws in both scenes
+    for _ in range(3):
+        step_policy(o); step_policy(o2)
+    assert o.calc_reward() == o2.calc_reward() and np.array_equal(o.record_goal()[:3], o2.record_goal())
+
+
+def test_getup_recovery_episodes_and_test_mode_getups(asset_root):
+    """ActivateRecoveryEpisode / ResetRecoveryEpisode (:40-58,301-317): after a failed episode, with probability p the fallen character is NOT
+    reset -- timers and controller restart and it has to get up.  Test mode: a fall starts a get-up instead of ending the episode (:245-254)."""
+    rng = np.random.default_rng(3)
+
+    def fall(o):
+        st = o.action_statics()
+        for _ in range(200):
+            step_policy(o, np.clip(-st[0] + 1.0 / st[1] * rng.standard_normal(o.action_size), st[2], st[3]))
+            if o.is_episode_end():
+                return
+        raise AssertionError("the character did not fall")
+
+    o = Oracle(["--recover_episode_prob", "1"] + GETUP, asset_root)
+    o.set_task_stream(8, 3, 0)
+    o.reset(0.2, 0.0, 20.0, clip=0)
+    fall(o)
+    assert o.check_terminate() == 1
+    pose, vel = o.get_pose()
+    k0, tgt = o.task_counter(), o.task_state()
+    o.reset(0.5, 1.0, 7.0, clip=3)                                                 # the injected clip / time / rotation are ignored: recovery
+    assert o.task_counter() == k0 + 1                                              # only the coin was drawn
+    p2, v2 = o.get_pose()
+    assert np.array_equal(pose, p2) and np.array_equal(vel, v2) and o.current_clip() == 0
+    g = o.getup_state()
+    assert g["getting_up"] and g["timer"] == 0.0 and o.record_goal()[3] == 1.0
+    assert o.get_time() == 0.0 and o.need_new_action() and not o.is_episode_end() and not o.has_fallen()
+    t2 = o.task_state()
+    assert t2["timer_max"] == tgt["timer_max"] and np.array_equal(t2["target_pos"], tgt["target_pos"]) and np.all(t2["prev_action_com"] == 0)
+    for _ in range(20):
+        step_policy(o)
+    assert o.get_time() == pytest.approx(20 * 20 / 600.0, abs=1e-9)               # the 7 s limit of the recovery episode is live
+    # probability 0 (and test mode): ordinary reset
+    o = Oracle(["--recover_episode_prob", "0"] + GETUP, asset_root)
+    o.set_task_stream(8, 3, 0); o.reset(0.2, 0.0, 20.0, clip=0)
+    fall(o)
+    o.reset(0.5, 0.0, 20.0, clip=1)
+    assert o.current_clip() == 1 and o.getup_state()["timer"] == 0.5 and not o.has_fallen()
+    # test mode: the fall flips the scene into getting up and the episode goes on
+    o = Oracle(GETUP, asset_root)
+    o.L.dmo_set_mode(o.h, 1)
+    o.set_task_stream(8, 3, 0); o.reset(0.2, 0.0, 20.0, clip=0)
+    st = o.action_statics()
+    began = False
+    for _ in range(200):
+        step_policy(o, np.clip(-st[0] + 1.0 / st[1] * rng.standard_normal(o.action_size), st[2], st[3]))
+        if o.getup_state()["getting_up"]:
+            began = True
+            assert o.getup_state()["contact_fall"] or o.getup_state()["timer"] > 0
+            assert not o.is_episode_end() and not o.has_fallen()
+            break
+    assert began
+
+
+@needs_reference
+@pytest.mark.parametrize("clip", [2, 3])
+def test_pretrained_getup_policy_stands_up_and_follows_the_heading_in_the_oracle(clip):
+    """The reference's heading + get-up policy starts lying on the ground (get-up clips 2 / 3 of its dataset), stands up (head above 1.3 m)
+    and then earns the heading reward for the rest of the 20 s (0.97 measured over the last 10 s)."""
+    from deepmimic_b200.tf_checkpoint import load_actor
+    ref = "/root/reference"
+    a = _f64(load_actor(os.path.join(ref, "data/policies/humanoid3d_amp/humanoid3d_amp_heading_getup_locomotion_getup.ckpt")))
+    o = Oracle(["--arg_file", "args/run_amp_heading_getup_humanoid3d_locomotion_getup_args.txt"], ref)
+    o.L.dmo_set_mode(o.h, 1)
+    o.set_task_stream(4, 0, 0)
+    o.reset(0.0, 0.4, 20.0, clip=clip)
+    assert o.record_goal()[3] == 1.0 and o.body_state()[0][2][1] < 0.5            # phase 1, head near the ground
+    rew, head = [], []
+    for _ in range(600):
+        if o.is_episode_end():
+            break
+        o.set_action(gated_actor_mode(a, o.record_state(), o.record_goal()))
+        for _ in range(20):
+            o.update(1.0 / 600.0)
+        rew.append(o.calc_reward()); head.append(o.body_state()[0][2][1])
+    assert len(rew) == 600 and not o.has_fallen()
+    assert max(head) > 1.3 and head[-1] > 1.25 and np.mean(rew[300:]) > 0.85, (max(head), head[-1], np.mean(rew[300:]))
