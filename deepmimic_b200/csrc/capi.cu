@@ -379,7 +379,7 @@ static bool load_host_model(dm_handle& H, const char* asset_root, int argc, cons
         // but it has not run on hardware yet: they are accepted only with DM_EXPERIMENTAL_TASK_SCENES=1, otherwise refused like every other scene.
         const char* exp_env = std::getenv("DM_EXPERIMENTAL_TASK_SCENES");
         const bool experimental = exp_env != nullptr && exp_env[0] == '1';
-        const bool task_scene = H.sa.cfg.scene == "target_amp" || H.sa.cfg.scene == "heading_amp";   // heading_amp_getup: oracle only so far
+        const bool task_scene = H.sa.cfg.scene == "target_amp" || H.sa.cfg.scene == "heading_amp";   // heading_amp_getup, strike_amp: oracle only so far
         if (H.sa.cfg.scene != "imitate" && H.sa.cfg.scene != "imitate_amp" && !(task_scene && experimental))
             throw std::runtime_error("Unsupported scene: " + H.sa.cfg.scene + " (supported: imitate, imitate_amp)");
         if (H.sa.clips.size() != 1 && !task_scene)

@@ -118,7 +118,11 @@ struct SceneConfig {
     std::vector<int> getup_motion_ids;
     double getup_height_root = 0.5, getup_height_head = 0.5, recover_episode_prob = 0.0;
     int head_id = 0;
-    bool is_task_scene() const { return scene == "target_amp" || scene == "heading_amp" || scene == "heading_amp_getup"; }
+    // cSceneStrikeAMP::ParseArgs (SceneStrikeAMP.cpp:212-229; constructor defaults :192-206)
+    V3 target_min = V3(-0.5, 1.2, 0.6), target_max = V3(0.5, 1.4, 1.1);
+    double target_radius = 0.2, target_hit_reset_time = 2.0, tar_reward_scale = 2.0, hit_tar_speed = 1.5, init_hit_prob = 0.0, tar_far_prob = 0.4, tar_near_dist = 1.4;
+    std::vector<int> strike_bodies, fail_tar_contact_bodies;
+    bool is_task_scene() const { return scene == "target_amp" || scene == "heading_amp" || scene == "heading_amp_getup" || scene == "strike_amp"; }
     bool is_heading_scene() const { return scene == "heading_amp" || scene == "heading_amp_getup"; }
 };
 
@@ -332,6 +336,20 @@ inline SceneConfig parse_scene_config(const ArgParser& ap) {
     ap.ParseDouble("tar_speed_max", sc.tar_speed_max);
     if (sc.is_heading_scene()) sc.tar_speed = std::min(std::max(sc.tar_speed, sc.tar_speed_min), sc.tar_speed_max);   // SceneHeadingAMP.cpp:85
     ap.ParseDouble("vel_reward_scale", sc.vel_reward_scale);
+    {
+        std::vector<double> v3;
+        if (ap.ParseDoubles("target_min", v3) && v3.size() >= 3) sc.target_min = V3(v3[0], v3[1], v3[2]);
+        if (ap.ParseDoubles("target_max", v3) && v3.size() >= 3) sc.target_max = V3(v3[0], v3[1], v3[2]);
+    }
+    ap.ParseDouble("target_radius", sc.target_radius);
+    ap.ParseDouble("target_hit_reset_time", sc.target_hit_reset_time);
+    ap.ParseDouble("tar_reward_scale", sc.tar_reward_scale);
+    ap.ParseDouble("hit_tar_speed", sc.hit_tar_speed);
+    ap.ParseDouble("init_hit_prob", sc.init_hit_prob);
+    ap.ParseDouble("tar_far_prob", sc.tar_far_prob);
+    ap.ParseDouble("tar_near_dist", sc.tar_near_dist);
+    ap.ParseInts("strike_bodies", sc.strike_bodies);
+    ap.ParseInts("fail_tar_contact_bodies", sc.fail_tar_contact_bodies);
     ap.ParseInts("getup_motion_ids", sc.getup_motion_ids);
     ap.ParseDouble("getup_height_root", sc.getup_height_root);
     ap.ParseDouble("getup_height_head", sc.getup_height_head);

@@ -8,7 +8,7 @@
 //   cSimCharacter / cSimBodyJoint / cSimBodyLink       R/DeepMimicCore/sim/*.cpp
 //   cCtPDController / cImpPDController                 R/DeepMimicCore/sim/*.cpp
 //   cKinCharacter / cMotion / cMotionController        R/DeepMimicCore/anim/*.cpp
-//   cClipsController (clip datasets), cSceneImitateAMP, cSceneTargetAMP, cSceneHeadingAMP, cSceneHeadingAMPGetup (goal, task reward, target updates)
+//   cClipsController (clip datasets), cSceneImitateAMP, cSceneTargetAMP, cSceneHeadingAMP, cSceneHeadingAMPGetup, cSceneStrikeAMP (goal, task reward, target updates)
 // DeepMimic's own math runs in double (rbd.hpp, omath.hpp); the Bullet 2.88 stage runs in float
 // (bullet_mb.hpp).  PARITY UNPINNED: the reference ships no tests or golden vectors and Bullet is
 // an un-vendored dependency, so this oracle is pinned only by the known-answer tests of
@@ -63,9 +63,13 @@ struct Oracle {
     int mode = 0;  // 0 train, 1 test
     VecD joint_weights;
     // ---- AMP task scenes: cSceneTargetAMP / cSceneHeadingAMP (scenes/SceneTargetAMP.cpp, SceneHeadingAMP.cpp)
-    enum SceneKind { kImitate = 0, kImitateAMP = 1, kTargetAMP = 2, kHeadingAMP = 3, kHeadingGetup = 4 };
+    enum SceneKind { kImitate = 0, kImitateAMP = 1, kTargetAMP = 2, kHeadingAMP = 3, kHeadingGetup = 4, kStrikeAMP = 5 };
     int scene_kind = kImitate;
-    bool IsTask() const { return scene_kind == kTargetAMP || scene_kind == kHeadingAMP || scene_kind == kHeadingGetup; }
+    bool IsTask() const { return scene_kind == kTargetAMP || scene_kind == kHeadingAMP || scene_kind == kHeadingGetup || scene_kind == kStrikeAMP; }
+    // cSceneStrikeAMP (scenes/SceneStrikeAMP.cpp): mTargetHit, mTargetHitTime; the target is a point in space (hits are detected by distance
+    // and speed of the strike bodies, SceneStrikeAMP.cpp:440-481), so no prop bodies are involved
+    bool target_hit = false;
+    double target_hit_time = -1.0;
     bool IsHeading() const { return scene_kind == kHeadingAMP || scene_kind == kHeadingGetup; }
     // cSceneHeadingAMPGetup (scenes/SceneHeadingAMPGetup.cpp): mGetupTimer (max = mGetupTime), mGetupMotionFlags
     double getup_time = 0, getup_timer_time = 0;
@@ -88,7 +92,8 @@ struct Oracle {
         else if (sa.cfg.scene == "target_amp") scene_kind = kTargetAMP;
         else if (sa.cfg.scene == "heading_amp") scene_kind = kHeadingAMP;
         else if (sa.cfg.scene == "heading_amp_getup") scene_kind = kHeadingGetup;
-        else throw std::runtime_error("oracle: scene '" + sa.cfg.scene + "' is not restated (imitate, imitate_amp, target_amp, heading_amp, heading_amp_getup)");
+        else if (sa.cfg.scene == "strike_amp") scene_kind = kStrikeAMP;
+        else throw std::runtime_error("oracle: scene '" + sa.cfg.scene + "' is not restated (imitate, imitate_amp, target_amp, heading_amp, heading_amp_getup, strike_amp)");
         if (scene_kind == kHeadingGetup) {   // Init: RecordGetupMotionFlags + CalcGetupTime (:87-98,221-243,262-287)
             getup_flags.assign(sa.clips.size(), 0);
             for (int id : sa.cfg.getup_motion_ids) {
@@ -763,6 +768,7 @@ struct Oracle {
     // cSceneImitate::CalcReward / CalcRewardImitate (SceneImitate.cpp:7-127,163-175)
     double CalcReward(double* dbg = nullptr) const {
         if (scene_kind == kTargetAMP) return CalcRewardTarget();
+        if (scene_kind == kStrikeAMP) return CalcRewardStrike();
         if (scene_kind == kHeadingGetup && CheckGettingUp()) {   // cSceneHeadingAMPGetup::CalcRewardGetup (:18-38), flat ground at 0
             const double root_h = std::min(std::max(SimRootPos().y / sa.cfg.getup_height_root, 0.0), 1.0);
             const double head_h = std::min(std::max(BodyPos(sa.cfg.head_id).y / sa.cfg.getup_height_head, 0.0), 1.0);
@@ -849,6 +855,7 @@ struct Oracle {
     }
     // cSceneTargetAMP::SampleRandTargetPos / ResetTargetPos (SceneTargetAMP.cpp:259-279)
     void ResetTargetPos() {
+        if (scene_kind == kStrikeAMP) { ResetTargetPosStrike(); return; }
         const D3 root = SimRootPos();
         const double dist = RandDouble(0.0, sa.cfg.max_target_dist);
         const double theta = RandDouble(0.0, 2.0 * M_PI);
@@ -860,6 +867,10 @@ struct Oracle {
     // cSceneTargetAMP::ResetTarget / cSceneHeadingAMP::ResetTarget (SceneTargetAMP.cpp:248-251, SceneHeadingAMP.cpp:207-217)
     void ResetTarget() {
         ResetTargetPos();
+        if (scene_kind == kStrikeAMP) {   // cSceneStrikeAMP::ResetTarget / ResetTargetHit (SceneStrikeAMP.cpp:300-316,376-383); GetTime() = scene timer
+            if (mode == 0 && sa.cfg.init_hit_prob > 0.0) SetTargetHit(FlipCoin(sa.cfg.init_hit_prob));
+            target_hit_time = target_hit ? RandDouble(timer_time - sa.cfg.target_hit_reset_time, timer_time) : -1.0;
+        }
         if (IsHeading()) {
             const double speed = RandDouble(sa.cfg.tar_speed_min, sa.cfg.tar_speed_max);
             target_heading = 0;
@@ -871,6 +882,10 @@ struct Oracle {
     void UpdateTarget(double dt) {
         tgt_timer_time += dt;
         const bool timer_end = tgt_timer_time >= tgt_timer_max;
+        if (scene_kind == kStrikeAMP) {   // CheckTargetReset is false here (:385-388): the target only moves at a reset; UpdateTarget (:289-298)
+            if (!target_hit) SetTargetHit(CheckTargetHit());
+            return;
+        }
         if (timer_end) ResetTargetPos();
         if (IsHeading() && timer_end) {
             // UpdateTargetHeading (SceneHeadingAMP.cpp:148-180)
@@ -882,7 +897,7 @@ struct Oracle {
             if (FlipCoin(sa.cfg.speed_change_prob)) SetTargetSpeed(RandDouble(sa.cfg.tar_speed_min, sa.cfg.tar_speed_max));
         }
     }
-    int GoalSize() const { return scene_kind == kHeadingGetup ? 4 : (IsTask() ? 3 : 0); }   // + getup phase (SceneHeadingAMPGetup.cpp:135-140)   // SceneTargetAMP.cpp:217-220, SceneHeadingAMP.cpp:131-134; 0 otherwise (RLSceneSimChar.cpp:88-91)
+    int GoalSize() const { return (scene_kind == kHeadingGetup || scene_kind == kStrikeAMP) ? 4 : (IsTask() ? 3 : 0); }   // + getup phase (SceneHeadingAMPGetup.cpp:135-140)   // SceneTargetAMP.cpp:217-220, SceneHeadingAMP.cpp:131-134; 0 otherwise (RLSceneSimChar.cpp:88-91)
     // cSceneTargetAMP::RecordGoal (SceneTargetAMP.cpp:185-215) / cSceneHeadingAMP::RecordGoal (SceneHeadingAMP.cpp:136-151)
     void RecordGoal(double* out) const {
         if (scene_kind == kTargetAMP) {
@@ -894,6 +909,13 @@ struct Oracle {
                 rel = (Rh * rel) / dist;
             } else rel = D3(1, 0, 0);
             out[0] = rel.x; out[1] = rel.z; out[2] = dist;
+        } else if (scene_kind == kStrikeAMP) {   // cSceneStrikeAMP::RecordGoal (:407-430): target in the origin frame (translation included) + hit phase
+            const D3 root = SimRootPos();
+            const DM3 Rh = RotateMatAxis(D3(0, 1, 0), -CalcHeading(GetRootRot(pose)));
+            const D3 rp = GetRootPos(pose);
+            const D3 loc = Rh * (target_pos - D3(rp.x, 0, rp.z));   // cKinTree::BuildOriginTrans: origin = root x, z on the ground
+            out[0] = loc.x; out[1] = loc.y; out[2] = loc.z; out[3] = CalcHitPhase();
+            (void)root;
         } else if (IsHeading()) {
             const double th = target_heading - CalcHeading(GetRootRot(pose));
             out[0] = std::cos(th); out[1] = -std::sin(th); out[2] = target_speed;
@@ -901,7 +923,7 @@ struct Oracle {
         }
     }
     bool CheckTarDistFail() const {   // SceneTargetAMP.cpp:281-292; always false in the heading scene (SceneHeadingAMP.cpp:219-222)
-        if (scene_kind != kTargetAMP) return false;
+        if (scene_kind != kTargetAMP && scene_kind != kStrikeAMP) return false;
         D3 d = SimRootPos() - target_pos; d.y = 0;
         return sqnorm(d) > sa.cfg.tar_fail_dist * sa.cfg.tar_fail_dist;
     }
@@ -954,12 +976,96 @@ struct Oracle {
         return vel_reward;
     }
 
+    // ------------------------------------------------------------------- cSceneStrikeAMP (scenes/SceneStrikeAMP.cpp)
+    void SetTargetHit(bool hit) { if (!target_hit && hit) target_hit_time = timer_time; target_hit = hit; }   // :246-255
+    // ResetTargetPos / ResetTargetPosFar / ResetTargetPosNear (:318-374)
+    void ResetTargetPosStrike() {
+        const D3 root = SimRootPos();
+        const dmh::V3 &mn = sa.cfg.target_min, &mx = sa.cfg.target_max;
+        double theta, h, dist;
+        if (FlipCoin(sa.cfg.tar_far_prob)) { theta = RandDouble(-M_PI, M_PI); h = RandDouble(mn.y, mx.y); dist = RandDouble(mn.z, sa.cfg.max_target_dist); }
+        else { theta = RandDouble(mn.x, mx.x); h = RandDouble(mn.y, mx.y); dist = RandDouble(mn.z, mx.z); }
+        SetTargetHit(false);
+        target_pos = D3(root.x + dist * std::cos(theta), h, root.z - dist * std::sin(theta));   // flat ground at 0
+    }
+    // CheckTargetHit (:440-481): a strike body inside the target sphere, moving towards the target (seen from the root) fast enough
+    bool CheckTargetHit() const {
+        D3 d = target_pos - SimRootPos(); d.y = 0;
+        const double n = norm(d);
+        D3 dir; if (n > 1e-5) dir = d / n;
+        for (int b : sa.cfg.strike_bodies) {
+            if (sqnorm(target_pos - BodyPos(b)) < sa.cfg.target_radius * sa.cfg.target_radius) {
+                const double speed = dot(dir, link_lin_vel[b]);
+                if (speed >= sa.cfg.hit_tar_speed || sa.cfg.hit_tar_speed == 0.0) return true;
+            }
+        }
+        return false;
+    }
+    bool CheckTarContactFail() const {   // :489-508
+        for (int b : sa.cfg.fail_tar_contact_bodies) if (sqnorm(target_pos - BodyPos(b)) < sa.cfg.target_radius * sa.cfg.target_radius) return true;
+        return false;
+    }
+    bool CheckTarHitSucc() const { return target_hit && (timer_time - target_hit_time) >= sa.cfg.target_hit_reset_time; }   // :510-524
+    double CalcHitPhase() const {   // :390-401
+        if (!target_hit) return 0.0;
+        return std::min(std::max((timer_time - target_hit_time) / sa.cfg.target_hit_reset_time, 0.0), 1.0);
+    }
+    // CalcReward / CalcRewardTrain / CalcRewardTest / CalcRewardTargetNear / CalcRewardTargetFar (:9-190)
+    double CalcRewardStrike() const {
+        const double far_w = 0.3, near_w = 0.3, hit_w = 0.4;
+        if (mode == 1) return (IsEpisodeEnd() && CheckTerminate() == 2) ? timer_max - timer_time : 0.0;
+        const D3 root = SimRootPos();
+        D3 trd = target_pos - root; trd.y = 0;
+        const double dist_sq = sqnorm(trd), near_dist = sa.cfg.tar_near_dist;
+        if (target_hit) return far_w + near_w + hit_w;
+        if (dist_sq < near_dist * near_dist) {
+            // near: best strike body, 0.2 distance term + 0.8 squared normalised speed towards the target
+            const double n = std::sqrt(dist_sq);
+            D3 dir; if (n > 1e-5) dir = trd / n;
+            double r = 0.0;
+            for (int b : sa.cfg.strike_bodies) {
+                const double dr = std::exp(-sa.cfg.tar_reward_scale * sqnorm(target_pos - BodyPos(b)));
+                double vr = std::min(std::max(dot(dir, link_lin_vel[b]) / sa.cfg.hit_tar_speed, 0.0), 1.0);
+                vr *= vr;
+                r = std::max(r, 0.2 * dr + 0.8 * vr);
+            }
+            return far_w + near_w * r;
+        }
+        // far: like the target scene, but the position term measures the distance to the near radius
+        double r = 0.0;
+        if (!HasFallen()) {
+            const double tar_speed = target_speed, vel_err_scale = 4 / (tar_speed * tar_speed);
+            const double root_tar_dist = std::sqrt(dist_sq);
+            const double root_dist_err = std::max(root_tar_dist - near_dist, 0.0);
+            const double pos_reward = std::exp(-sa.cfg.pos_reward_scale * root_dist_err * root_dist_err);
+            double vel_reward = 0;
+            if (root_tar_dist < near_dist) vel_reward = 1.0;
+            else {
+                const double step_dur = ctrl_time - prev_action_time;
+                const D3 com = CalcCOM();
+                D3 ctd = target_pos - com; ctd.y = 0;
+                const double cd = norm(ctd);
+                D3 cdir; if (cd > 0.0001) cdir = ctd / cd;
+                const double avg_vel = dot(cdir, com - prev_action_com) / step_dur;
+                double vel_err = tar_speed - avg_vel;
+                if (avg_vel < 0) vel_reward = 0.0;
+                else { if (sa.cfg.enable_min_tar_vel) vel_err = std::max(vel_err, 0.0); vel_reward = std::exp(-vel_err_scale * vel_err * vel_err); }
+            }
+            r = 0.7 * pos_reward + 0.3 * vel_reward;
+        }
+        return far_w * r;
+    }
+
     // cRLSceneSimChar::CheckTerminate + cSceneImitate::CheckTerminate (RLSceneSimChar.cpp:187-197; SceneImitate.cpp:193-205)
     int CheckTerminate() const {
         bool fail = sa.cfg.enable_fall_end && HasFallen();
         // the AMP scenes use cRLSceneSimChar::CheckTerminate alone (SceneImitateAMP.cpp:185-189): no motion-over failure there
         if (!fail && scene_kind == kImitate && !Mot().loop && kin_time >= Mot().duration()) fail = true;
         if (!fail && scene_kind == kTargetAMP && CheckTarDistFail()) fail = true;   // cSceneTargetAMP::CheckTerminate (SceneTargetAMP.cpp:294-319)
+        if (!fail && scene_kind == kStrikeAMP) {   // cSceneStrikeAMP::CheckTerminateTarget (:526-546): distance, forbidden bodies at the target, then success (2)
+            if (CheckTarDistFail() || CheckTarContactFail()) fail = true;
+            else if (CheckTarHitSucc()) return 2;
+        }
         return fail ? 1 : 0;
     }
     bool IsEpisodeEnd() const { return timer_time >= timer_max || CheckTerminate() != 0; }  // RLScene.cpp:36-50
@@ -1112,6 +1218,9 @@ void dmo_get_getup_state(void* h, double* out) {
     Oracle* o = static_cast<Oracle*>(h);
     out[0] = o->getup_timer_time; out[1] = o->getup_time; out[2] = o->CheckGettingUp() ? 1 : 0; out[3] = o->ContactFall() ? 1 : 0;
 }
+// strike_amp: out[0] = target hit (0 / 1), out[1] = hit time, out[2] = hit phase, out[3] = target height
+void dmo_get_strike_state(void* h, double* out) { Oracle* o = static_cast<Oracle*>(h); out[0] = o->target_hit ? 1 : 0; out[1] = o->target_hit_time; out[2] = o->CalcHitPhase(); out[3] = o->target_pos.y; }
+void dmo_set_strike_state(void* h, int hit, double hit_time) { Oracle* o = static_cast<Oracle*>(h); o->target_hit = hit != 0; o->target_hit_time = hit_time; }
 int dmo_check_target_succ(void* h) { return static_cast<Oracle*>(h)->CheckTargetSucc() ? 1 : 0; }
 int dmo_enable_amp_task_reward(void* h) { return static_cast<Oracle*>(h)->IsTask() ? 1 : 0; }   // SceneTargetAMP.cpp:222-225
 void dmo_calc_com(void* h, double* out) { orc::D3 c = static_cast<Oracle*>(h)->CalcCOM(); out[0] = c.x; out[1] = c.y; out[2] = c.z; }

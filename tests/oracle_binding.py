@@ -119,6 +119,15 @@ class Oracle:
         self.L.dmo_get_getup_state(self.h, dp(o))
         return dict(timer=o[0], getup_time=o[1], getting_up=bool(o[2]), contact_fall=bool(o[3]))
 
+    def strike_state(self):
+        """strike_amp: dict(hit, hit_time, phase, target_height)"""
+        o = np.zeros(4)
+        self.L.dmo_get_strike_state(self.h, dp(o))
+        return dict(hit=bool(o[0]), hit_time=o[1], phase=o[2], target_height=o[3])
+
+    def set_strike_state(self, hit, hit_time):
+        self.L.dmo_set_strike_state(self.h, int(bool(hit)), C.c_double(hit_time))
+
     def check_target_succ(self):
         return bool(self.L.dmo_check_target_succ(self.h))
 

@@ -625,3 +625,104 @@ def test_pretrained_getup_policy_stands_up_and_follows_the_heading_in_the_oracle
         rew.append(o.calc_reward()); head.append(o.body_state()[0][2][1])
     assert len(rew) == 600 and not o.has_fallen()
     assert max(head) > 1.3 and head[-1] > 1.25 and np.mean(rew[300:]) > 0.85, (max(head), head[-1], np.mean(rew[300:]))
+
+
+# ------------------------------------------------------------------------------------------------ strike_amp (cSceneStrikeAMP)
+STRIKE = ["--scene", "strike_amp", "--target_hit_reset_time", "2", "--target_radius", "0.2", "--target_min", "-0.5", "1.2", "0.6", "--target_max", "0.5", "1.4", "1.1",
+          "--tar_near_dist", "1.4", "--tar_far_prob", "0.4", "--strike_bodies", "8", "--fail_tar_contact_bodies", "0", "1", "2", "--init_hit_prob", "0.1",
+          "--hit_tar_speed", "1.5", "--tar_reward_scale", "2"] + TARGET
+
+
+def test_strike_reset_draw_order_goal_and_rewards(asset_root):
+    """SceneStrikeAMP.cpp: reset draws (:300-383), goal = target in the origin frame + hit phase (:407-430), train reward in its three regimes
+    (:22-190), hit detection (:440-481), forbidden-body failure and success after the hold time (:489-546)."""
+    o = Oracle(STRIKE, asset_root)
+    assert o.goal_size == 4 and o.enable_amp_task_reward()
+    o.set_task_stream(13, 2, 0)
+    o.reset(0.3, 0.0, 20.0, clip=0)
+    s = Stream(13, 2)
+    s.uniform(1.0, 5.0)                                                          # target timer (cSceneTargetAMP defaults 1..5 s)
+    far = s.coin(0.4)
+    theta = s.uniform(-math.pi, math.pi) if far else s.uniform(-0.5, 0.5)
+    h = s.uniform(1.2, 1.4)
+    dist = s.uniform(0.6, 10.0) if far else s.uniform(0.6, 1.1)
+    hit0 = s.coin(0.1)                                                           # ResetTargetHit (train mode, init_hit_prob 0.1)
+    hit_time = s.uniform(0.0 - 2.0, 0.0) if hit0 else -1.0
+    root = o.get_pose()[0][:3]
+    ts, ss = o.task_state(), o.strike_state()
+    np.testing.assert_allclose([ts["target_pos"][0], ss["target_height"], ts["target_pos"][2]],
+                               [root[0] + dist * math.cos(theta), h, root[2] - dist * math.sin(theta)], atol=1e-7)
+    assert ss["hit"] == hit0 and ss["hit_time"] == pytest.approx(hit_time, abs=1e-12) and o.task_counter() == s.k
+    step_policy(o); step_policy(o)
+    pose = o.get_pose()[0]
+    root, hd = pose[:3], heading_of(pose)
+    pos, rot, lv, av = o.body_state()
+    com = com_of(o, asset_root)
+    ts = o.task_state()
+    c, s_ = math.cos(-hd), math.sin(-hd)
+
+    def put_target(p, hit=False, hit_time=-1.0):
+        o.set_task_state(p, 1.0, 0.0, ts["timer"], ts["timer_max"], ts["prev_action_com"])
+        o.set_strike_state(hit, hit_time)
+
+    hand = pos[8]
+    # far regime: 0.3 * (0.7 exp(-0.5 max(d - 1.4, 0)^2) + 0.3 vel term)
+    tar = np.array([root[0] + 4.0, 1.3, root[2] + 1.0])
+    put_target(tar)
+    d = math.hypot(tar[0] - root[0], tar[2] - root[2])
+    cd = np.array([tar[0] - com[0], 0.0, tar[2] - com[2]]); cd /= np.linalg.norm(cd)
+    avg = float(cd @ (com - ts["prev_action_com"])) / (19 / 600.0)
+    vel_r = 0.0 if avg < 0 else math.exp(-4.0 * max(1.0 - avg, 0.0) ** 2)
+    assert o.calc_reward() == pytest.approx(0.3 * (0.7 * math.exp(-0.5 * (d - 1.4) ** 2) + 0.3 * vel_r), abs=1e-9)
+    loc = np.array([tar[0] - root[0], tar[1], tar[2] - root[2]])
+    np.testing.assert_allclose(o.record_goal(), [c * loc[0] + s_ * loc[2], loc[1], -s_ * loc[0] + c * loc[2], 0.0], atol=1e-9)
+    # near regime: 0.3 + 0.3 * max over strike bodies of (0.2 exp(-2 |t - hand|^2) + 0.8 clamp(v.dir / 1.5)^2)
+    tar = hand + np.array([0.25, 0.05, -0.1])
+    put_target(tar)
+    dirn = np.array([tar[0] - root[0], 0.0, tar[2] - root[2]]); dirn /= np.linalg.norm(dirn)
+    near = 0.2 * math.exp(-2.0 * float(((tar - hand) ** 2).sum())) + 0.8 * min(max(float(dirn @ lv[8]) / 1.5, 0.0), 1.0) ** 2
+    assert o.calc_reward() == pytest.approx(0.3 + 0.3 * near, abs=1e-9) and o.check_terminate() == 0
+    # hit: full reward, phase grows with the hold time, success (terminate 2) once it reaches the reset time
+    t_now = o.get_time()
+    put_target(tar, hit=True, hit_time=t_now - 0.5)
+    assert o.calc_reward() == pytest.approx(1.0, abs=1e-12) and o.record_goal()[3] == pytest.approx(0.25, abs=1e-12) and o.check_terminate() == 0
+    put_target(tar, hit=True, hit_time=t_now - 2.0)
+    assert o.record_goal()[3] == 1.0 and o.check_terminate() == 2 and o.is_episode_end()
+    # a forbidden body (root / torso / head) at the target fails the episode; too far fails it as well
+    put_target(pos[1] + np.array([0.05, 0.0, 0.05]))
+    assert o.check_terminate() == 1
+    put_target(np.array([root[0] + 15.5, 1.3, root[2]]))
+    assert o.check_terminate() == 1
+    # hit detection needs both the hand inside the sphere and enough speed towards the target: standing still near it is no hit
+    put_target(hand + np.array([0.05, 0.0, 0.0]))
+    o.update(1.0 / 600.0)
+    assert not o.strike_state()["hit"]
+
+
+@needs_reference
+@pytest.mark.parametrize("seed,far", [(1, False), (7, True)])
+def test_pretrained_strike_policy_punches_the_target_in_the_oracle(seed, far):
+    """The reference's walk-and-punch policy hits the oracle-drawn target with its hand (fast enough, from the right side) and holds for the 2 s
+    that make the episode a success (terminate code 2) -- also when it first has to walk 5 m to get there."""
+    from deepmimic_b200.tf_checkpoint import load_actor
+    ref = "/root/reference"
+    a = _f64(load_actor(os.path.join(ref, "data/policies/humanoid3d_amp/humanoid3d_amp_strike_walk_punch.ckpt")))
+    o = Oracle(["--arg_file", "args/run_amp_strike_humanoid3d_walk_punch_args.txt"], ref)
+    o.L.dmo_set_mode(o.h, 1)
+    o.set_task_stream(seed, 0, 0)
+    o.reset(0.3, 0.0, 20.0, clip=0)
+    tp, root = o.task_state()["target_pos"], o.get_pose()[0]
+    assert (math.hypot(tp[0] - root[0], tp[2] - root[2]) > 3.0) == far
+    hit_step = None
+    for k in range(600):
+        if o.is_episode_end():
+            break
+        o.set_action(gated_actor_mode(a, o.record_state(), o.record_goal()))
+        for _ in range(20):
+            o.update(1.0 / 600.0)
+            if o.is_episode_end():
+                break
+        if hit_step is None and o.strike_state()["hit"]:
+            hit_step = k
+    assert hit_step is not None and o.check_terminate() == 2 and not o.has_fallen(), (hit_step, o.check_terminate())
+    assert o.get_time() == pytest.approx((hit_step + 1) / 30.0 + 2.0, abs=0.05)     # success exactly the hold time after the hit
