@@ -536,6 +536,10 @@ struct Ctx {
     bool act;
 };
 __device__ __forceinline__ const StepLayout& lay_of(const Ctx& c) { return *reinterpret_cast<const StepLayout*>(c.LYS); }
+// The phase routines are real calls (__noinline__), so the compiler cannot see that the context's pointers address shared memory and would emit
+// generic LD / ST for them; these address-space hints turn them back into LDS / STS.
+#define DM_ASSUME_SHARED_CTX(c) do { __builtin_assume(__isShared((c).E)); __builtin_assume(__isShared((c).LYS)); __builtin_assume(__isShared((c).LK)); \
+                                     __builtin_assume(__isShared((c).LVC)); } while (0)
 __device__ __forceinline__ S6 shift_m(S6 m, V3 c) { return mks(m.a, m.l + cross(m.a, c)); }   // motion vector: reference point moved by +c
 __device__ __forceinline__ S6 shift_f(S6 f, V3 c) { return mks(f.a + cross(c, f.l), f.l); }   // force vector: child pivot -> parent pivot (child = parent + c)
 __device__ __forceinline__ float cl100(float v) { return fminf(fmaxf(v, -100.f), 100.f); }   // applyDeltaVeeMultiDof clamp
@@ -556,6 +560,7 @@ __device__ __forceinline__ V3 tile_com(const float* w, const float* v, float mas
 template <int W>
 __device__ __noinline__ void kin_pass(Ctx c, float4 jp, float4 jv) {
     using T = Tl<W>;
+    DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
     float* sS = c.E + LY.oR; float* sW = c.E + LY.oW; float* sV = c.E + LY.oV; const float* sB = c.E + LY.oG + 21;
     const float* LKo = c.LK + c.li * kLkFloats;
@@ -613,6 +618,7 @@ __device__ __noinline__ void kin_pass(Ctx c, float4 jp, float4 jv) {
 template <int W>
 __device__ __noinline__ int collide(Ctx c, float* mani, int alive, float scale) {
     using T = Tl<W>;
+    DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
     const float* sW = c.E + LY.oW; const float* sV = c.E + LY.oV;
     float* sPp = c.E + LY.oPp; float* sPi = c.E + LY.oPi; int* sPr = reinterpret_cast<int*>(c.E + LY.oPr);
@@ -744,6 +750,7 @@ template <int W, bool DEBUG>
 __device__ __noinline__ float3 aba_solve(Ctx c, float g0, float g1, float g2, float kdt, int bullet, float jvx, float jvy, float jvz, float gx, float gy, float gz, float h,
                                          float* dbg_acc) {
     using T = Tl<W>;
+    DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
     float* sU = c.E + LY.oU; const float* sS = c.E + LY.oR; const float* sW = c.E + LY.oW; float* sV = c.E + LY.oV; float* sG = c.E + LY.oG; float* sB = sG + 21;
     const float* LKo = c.LK + c.li * kLkFloats;
@@ -937,6 +944,7 @@ __device__ __noinline__ float3 aba_solve(Ctx c, float g0, float g1, float g2, fl
 template <int W>
 __device__ __noinline__ float3 dv_pass(Ctx c) {
     using T = Tl<W>;
+    DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
     const float* sU = c.E + LY.oU; const float* sS = c.E + LY.oR; float* sG = c.E + LY.oG; float* sB = sG + 21; const float* sZ = c.E + LY.oZ;
     const float* q = sS + c.li * 12;
@@ -986,6 +994,7 @@ __device__ __noinline__ float3 dv_pass(Ctx c) {
 template <int W>
 __device__ __noinline__ void vel_pass(Ctx c, float jvx, float jvy, float jvz, bool want) {
     using T = Tl<W>;
+    DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
     const float* sS = c.E + LY.oR; float* sV = c.E + LY.oV; const float* sB = c.E + LY.oG + 21;
     const float* q = sS + c.li * 12;
