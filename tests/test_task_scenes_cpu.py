@@ -641,7 +641,7 @@ def test_strike_reset_draw_order_goal_and_rewards(asset_root):
     o.set_task_stream(13, 2, 0)
     o.reset(0.3, 0.0, 20.0, clip=0)
     s = Stream(13, 2)
-    s.uniform(1.0, 5.0)                                                          # target timer (cSceneTargetAMP defaults 1..5 s)
+    s.uniform(5.0, 10.0)                                                         # target timer (--rand_target_time_min/max of the target args)
     far = s.coin(0.4)
     theta = s.uniform(-math.pi, math.pi) if far else s.uniform(-0.5, 0.5)
     h = s.uniform(1.2, 1.4)
@@ -726,3 +726,153 @@ def test_pretrained_strike_policy_punches_the_target_in_the_oracle(seed, far):
             hit_step = k
     assert hit_step is not None and o.check_terminate() == 2 and not o.has_fallen(), (hit_step, o.check_terminate())
     assert o.get_time() == pytest.approx((hit_step + 1) / 30.0 + 2.0, abs=0.05)     # success exactly the hold time after the hit
+
+
+# ------------------------------------------------------------------------------------------------ dm_task_ext.cuh on the host (get-up, strike)
+def _ext_params(getup_time=0.0, root_h=0.5, head_h=0.5, recover=0.0, head_id=0, strike=(), fail=(), init_hit=0.0):
+    q = np.zeros(32)
+    q[0:4] = [getup_time, root_h, head_h, recover]
+    q[4:7] = [-0.5, 1.2, 0.6]; q[7:10] = [0.5, 1.4, 1.1]
+    q[10:17] = [0.2, 2.0, 2.0, 1.5, init_hit, 0.4, 1.4]
+    q[17] = head_id; q[18] = len(strike); q[19:19 + len(strike)] = strike; q[23] = len(fail); q[24:24 + len(fail)] = fail
+    return q
+
+
+def _task_params(kind, timer=(1.0, 5.0), max_dist=10.0, succ=0.5, fail=15.0, pos_scale=0.5, tar_speed=1.0, min_vel=1):
+    p = np.zeros(16)
+    p[0:7] = [kind, timer[0], timer[1], max_dist, succ, fail, pos_scale]
+    p[7:13] = [0.15, 0.01, 0.02, 1.0, 5.0, 0.25]
+    p[13], p[14] = tar_speed, min_vel
+    return p
+
+
+def _bodies(o, xq):
+    pos, rot, lv, av = o.body_state()
+    b = np.zeros(38)
+    b[0] = pos[int(xq[17])][1]; b[1] = float(o.getup_state()["contact_fall"])
+    for k in range(int(xq[18])):
+        b[2 + 3 * k: 5 + 3 * k] = pos[int(xq[19 + k])]; b[14 + 3 * k: 17 + 3 * k] = lv[int(xq[19 + k])]
+    for k in range(int(xq[23])):
+        b[26 + 3 * k: 29 + 3 * k] = pos[int(xq[24 + k])]
+    return b
+
+
+def _shim_ext_signatures(L):
+    import ctypes as C
+    d, dp_, u64, i = C.c_double, C.POINTER(C.c_double), C.c_uint64, C.c_int
+    L.shim_getup_reset.argtypes = [dp_, dp_, d, i]
+    L.shim_getup_try_recovery.argtypes = [dp_, dp_, u64, u64, i, i]
+    L.shim_getup_recovery_reset.argtypes = [dp_, dp_]
+    L.shim_getup_update.argtypes = [dp_, dp_, d, i, i]
+    L.shim_getup_phase.argtypes = [dp_, dp_]; L.shim_getup_phase.restype = d
+    L.shim_getup_reward.argtypes = [dp_, d, d]; L.shim_getup_reward.restype = d
+    L.shim_strike_reset.argtypes = [dp_, dp_, dp_, dp_, u64, u64, d, d, d, i]
+    L.shim_strike_update.argtypes = [dp_, dp_, dp_, dp_, u64, u64, d, d, d, d, dp_]
+    L.shim_strike_terminate.argtypes = [dp_, dp_, dp_, dp_, d, d, d]
+    L.shim_strike_goal.argtypes = [dp_, dp_, dp_, d, d, d, d, dp_]
+    L.shim_strike_reward.argtypes = [dp_, dp_, dp_, dp_, i, d, d, d, i, i, d, d]; L.shim_strike_reward.restype = d
+    return L
+
+
+def test_device_strike_logic_matches_the_oracle_on_the_host(asset_root, task_shim):
+    """dm_task_ext.cuh (host build) against the oracle's strike scene over 5 s of a random policy, with the target re-placed in front of the moving
+    hand every second so that hits, holds, successes and forbidden-body failures all occur: hit state / time, goal, reward and termination code
+    after every update."""
+    L = _shim_ext_signatures(task_shim)
+    o = Oracle(STRIKE, asset_root)
+    P, X = _task_params(1, timer=(5.0, 10.0)), _ext_params(head_id=2, strike=(8,), fail=(0, 1, 2), init_hit=0.1)   # STRIKE sits on the target args: timer 5..10 s
+    seed, env = 5, 9
+    o.set_task_stream(seed, env, 0)
+    o.reset(0.3, 0.0, 20.0, clip=0)
+    t, x = np.zeros(16), np.zeros(8)
+    root = o.get_pose()[0]
+    L.shim_strike_reset(_ptr(P), _ptr(X), _ptr(t), _ptr(x), seed, env, root[0], root[2], 0.0, 0)
+    rng = np.random.default_rng(0)
+    st = o.action_statics()
+    seen = dict(hit=0, succ=0, fail=0, near=0, far=0)
+
+    def compare(k):
+        ts, ss = o.task_state(), o.strike_state()
+        np.testing.assert_allclose([t[0], x[0], t[1]], [ts["target_pos"][0], ss["target_height"], ts["target_pos"][2]], atol=1e-7)
+        assert bool(x[1]) == ss["hit"] and x[2] == pytest.approx(ss["hit_time"], abs=1e-12), k
+        assert t[4] == pytest.approx(ts["timer"], abs=1e-12) and t[5] == pytest.approx(ts["timer_max"], rel=1e-15) and int(t[12]) == o.task_counter()
+    compare(-1)
+    for k in range(3000):
+        if k == 1:              # first second: a far target (the far regime of the reward)
+            rp = o.get_pose()[0]
+            tar = np.array([rp[0] + 5.0, 1.3, rp[2] + 1.0])
+            ts = o.task_state()
+            o.set_task_state(tar, 1.0, 0.0, ts["timer"], ts["timer_max"], ts["prev_action_com"]); o.set_strike_state(False, -1.0)
+            t[0], x[0], t[1] = tar[0], tar[1], tar[2]; x[1], x[2] = 0.0, -1.0
+        if k in (301, 2101):    # (between two action boundaries) the target goes where the hand will be -- hit, 2 s hold, success -- and later onto the chest (forbidden)
+            pos, _, lv, _ = o.body_state()
+            tar = pos[8] + 0.02 * lv[8] / (np.linalg.norm(lv[8]) + 1e-9) if k == 301 else pos[1] + np.array([0.0, 0.05, 0.0])
+            ts = o.task_state()
+            o.set_task_state(tar, 1.0, 0.0, ts["timer"], ts["timer_max"], ts["prev_action_com"]); o.set_strike_state(False, -1.0)
+            t[0], x[0], t[1] = tar[0], tar[1], tar[2]; x[1], x[2] = 0.0, -1.0
+        if o.need_new_action():
+            ts = o.task_state(); t[6:9] = ts["prev_action_com"]; t[9:12] = o.calc_com()
+            pose = o.get_pose()[0]
+            g = np.zeros(4)
+            L.shim_strike_goal(_ptr(X), _ptr(t), _ptr(x), pose[0], pose[2], heading_of(pose), o.get_time(), _ptr(g))
+            np.testing.assert_allclose(g, o.record_goal(), atol=1e-9)
+            if k > 0:
+                r = L.shim_strike_reward(_ptr(P), _ptr(X), _ptr(t), _ptr(x), int(o.has_fallen()), pose[0], pose[2], 19.0 / 600.0, 0, o.check_terminate(), 20.0, o.get_time())
+                assert r == pytest.approx(o.calc_reward(), abs=1e-9), k
+                d = math.hypot(t[0] - pose[0], t[1] - pose[2])
+                seen["near" if d < 1.4 else "far"] += 1
+            o.set_action(np.clip(-st[0] + 0.3 / st[1] * rng.standard_normal(o.action_size), st[2], st[3]))
+        o.update(1.0 / 600.0)
+        root = o.get_pose()[0]
+        L.shim_strike_update(_ptr(P), _ptr(X), _ptr(t), _ptr(x), seed, env, 1.0 / 600.0, root[0], root[2], o.get_time(), _ptr(_bodies(o, X)))
+        compare(k)
+        code = L.shim_strike_terminate(_ptr(P), _ptr(X), _ptr(t), _ptr(x), root[0], root[2], o.get_time())
+        if not o.has_fallen():
+            assert code == o.check_terminate(), k
+        seen["hit"] += int(x[1]); seen["succ"] += int(code == 2); seen["fail"] += int(code == 1)
+    assert min(seen.values()) > 0, seen
+
+
+def test_device_getup_logic_matches_the_oracle_on_the_host(asset_root, task_shim):
+    """dm_task_ext.cuh's get-up pieces against the oracle: timer / phase / reward through a reset in a get-up clip, a fall, a recovery episode
+    (train mode) and a test-mode get-up."""
+    L = _shim_ext_signatures(task_shim)
+    rng = np.random.default_rng(4)
+    for mode in (0, 1):
+        o = Oracle(["--recover_episode_prob", "1"] + GETUP, asset_root)
+        o.L.dmo_set_mode(o.h, mode)
+        dur = o.clip_table()[0]
+        X = _ext_params(getup_time=max(dur[1], dur[2]), root_h=1.2, head_h=2.0, recover=1.0, head_id=2)
+        seed, env = 6, 1
+        o.set_task_stream(seed, env, 0)
+        o.reset(0.4, 0.0, 20.0, clip=1)
+        t, x = np.zeros(16), np.zeros(8)
+        L.shim_getup_reset(_ptr(X), _ptr(x), 0.4, 1)
+        st = o.action_statics()
+        recoveries = began = 0
+        for k in range(2400):
+            if o.is_episode_end():
+                assert mode == 0                                                   # test mode never ends on a fall here: it gets up instead
+                t[12] = o.task_counter()
+                rec = L.shim_getup_try_recovery(_ptr(X), _ptr(t), seed, env, mode, o.check_terminate())
+                o.reset(0.2, 0.0, 20.0, clip=0)
+                assert int(t[12]) == o.task_counter() - (0 if rec else 4)         # a full reset also draws timer, target x2 and speed
+                if rec:
+                    L.shim_getup_recovery_reset(_ptr(t), _ptr(x)); recoveries += 1
+                else:
+                    L.shim_getup_reset(_ptr(X), _ptr(x), 0.2, 0)
+                if recoveries >= 2:
+                    break
+            if o.need_new_action():
+                g = o.getup_state()
+                assert L.shim_getup_phase(_ptr(X), _ptr(x)) == pytest.approx(o.record_goal()[3], abs=1e-12)
+                if g["getting_up"]:
+                    assert L.shim_getup_reward(_ptr(X), o.get_pose()[0][1], o.body_state()[0][2][1]) == pytest.approx(o.calc_reward(), abs=1e-12)
+                o.set_action(np.clip(-st[0] + 1.0 / st[1] * rng.standard_normal(o.action_size), st[2], st[3]))
+            before = o.getup_state()["getting_up"]
+            o.update(1.0 / 600.0)
+            g = o.getup_state()
+            up = L.shim_getup_update(_ptr(X), _ptr(x), 1.0 / 600.0, mode, int(g["contact_fall"]))
+            assert bool(up) == g["getting_up"] and x[3] == pytest.approx(g["timer"], abs=1e-12), k
+            began += int(g["getting_up"] and not before)
+        assert (recoveries >= 2) if mode == 0 else (began >= 1)
