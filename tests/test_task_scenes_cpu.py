@@ -867,7 +867,7 @@ def test_device_getup_logic_matches_the_oracle_on_the_host(asset_root, task_shim
                 g = o.getup_state()
                 assert L.shim_getup_phase(_ptr(X), _ptr(x)) == pytest.approx(o.record_goal()[3], abs=1e-12)
                 if g["getting_up"]:
-                    assert L.shim_getup_reward(_ptr(X), o.get_pose()[0][1], o.body_state()[0][2][1]) == pytest.approx(o.calc_reward(), abs=1e-12)
+                    assert L.shim_getup_reward(_ptr(X), o.get_pose()[0][1], o.body_state()[0][2][1]) == pytest.approx(o.calc_reward(), abs=1e-7)   # root height through the float link frames in the oracle
                 o.set_action(np.clip(-st[0] + 1.0 / st[1] * rng.standard_normal(o.action_size), st[2], st[3]))
             before = o.getup_state()["getting_up"]
             o.update(1.0 / 600.0)
