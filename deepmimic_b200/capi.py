@@ -144,12 +144,12 @@ class BatchedCore:
         self._chk(lib().dm_record_goal(self.h, C.c_void_p(out.data_ptr())))
 
     def goal_host(self):
-        out = np.zeros((self.num_envs, 3), dtype=np.float32)
+        out = np.zeros((self.num_envs, self.dims.goal_size), dtype=np.float32)
         self._chk(lib().dm_goal_host(self.h, C.c_void_p(out.ctypes.data)))
         return out
 
     def task_state(self, env):
-        out = np.zeros(16, dtype=np.float64)
+        out = np.zeros(24, dtype=np.float64)     # dm_task.cuh block (16) | dm_task_ext.cuh block (8)
         self._chk(lib().dm_get_task_state(self.h, env, _dptr(out)))
         return out
 
@@ -158,7 +158,7 @@ class BatchedCore:
         self._chk(lib().dm_set_task_state(self.h, env, _dptr(b)))
 
     def task_params(self):
-        out = np.zeros(16, dtype=np.float64)
+        out = np.zeros(48, dtype=np.float64)     # [0:16] dm_task.cuh constants, [16:48] dm_task_ext.cuh constants
         key = (C.c_uint64 * 2)()
         self._chk(lib().dm_get_task_params(self.h, _dptr(out), key))
         return out, int(key[0]), int(key[1])
@@ -244,7 +244,7 @@ class HostModel:
         return out
 
     def task_params(self):
-        out = np.zeros(16, dtype=np.float64)
+        out = np.zeros(48, dtype=np.float64)     # [0:16] dm_task.cuh constants, [16:48] dm_task_ext.cuh constants
         key = (C.c_uint64 * 2)()
         lib().dm_get_task_params(self.h, _dptr(out), key)
         return out, int(key[0]), int(key[1])

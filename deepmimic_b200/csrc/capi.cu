@@ -157,7 +157,32 @@ bool build_device_model(dm_handle& H) {
     M.total_mass = static_cast<float>(cm.total_mass());
     {   // AMP task scenes (dm_task.cuh)
         const dmh::SceneConfig& c = sa.cfg;
-        M.task_kind = c.scene == "target_amp" ? dmk::kTaskTarget : (c.scene == "heading_amp" ? dmk::kTaskHeading : dmk::kTaskNone);
+        M.task_kind = c.scene == "target_amp" ? dmk::kTaskTarget : c.scene == "heading_amp" ? dmk::kTaskHeading :
+                      c.scene == "heading_amp_getup" ? dmk::kTaskHeadingGetup : c.scene == "strike_amp" ? dmk::kTaskStrike : dmk::kTaskNone;
+        {   // heading_amp_getup / strike_amp (dm_task_ext.cuh)
+            dmk::TaskExtParams& X = M.taskx;
+            X.getup_time = 0.0;
+            for (int id : c.getup_motion_ids) {
+                if (id < 0 || id >= static_cast<int>(sa.clips.size())) { g_err = "--getup_motion_ids out of range"; return false; }
+                X.getup_time = std::max(X.getup_time, sa.clips[id].duration());   // cSceneHeadingAMPGetup::CalcGetupTime (:262-287)
+            }
+            X.getup_height_root = c.getup_height_root; X.getup_height_head = c.getup_height_head; X.recover_episode_prob = c.recover_episode_prob;
+            for (int k = 0; k < 3; ++k) { X.target_min[k] = c.target_min[k]; X.target_max[k] = c.target_max[k]; }
+            X.target_radius = c.target_radius; X.hit_reset_time = c.target_hit_reset_time; X.tar_reward_scale = c.tar_reward_scale; X.hit_tar_speed = c.hit_tar_speed;
+            X.init_hit_prob = c.init_hit_prob; X.tar_far_prob = c.tar_far_prob; X.tar_near_dist = c.tar_near_dist;
+            X.head_id = c.head_id;
+            if (X.head_id < 0 || X.head_id >= nl) { g_err = "--head_id out of range"; return false; }
+            if (static_cast<int>(c.strike_bodies.size()) > dmk::kMaxTaskBodies || static_cast<int>(c.fail_tar_contact_bodies.size()) > dmk::kMaxTaskBodies) {
+                g_err = "more than 4 --strike_bodies / --fail_tar_contact_bodies"; return false;
+            }
+            X.n_strike = static_cast<int>(c.strike_bodies.size()); X.n_fail = static_cast<int>(c.fail_tar_contact_bodies.size());
+            for (int k = 0; k < dmk::kMaxTaskBodies; ++k) {
+                X.strike_bodies[k] = k < X.n_strike ? c.strike_bodies[k] : 0; X.fail_bodies[k] = k < X.n_fail ? c.fail_tar_contact_bodies[k] : 0;
+                if (X.strike_bodies[k] < 0 || X.strike_bodies[k] >= nl || X.fail_bodies[k] < 0 || X.fail_bodies[k] >= nl) { g_err = "strike / fail body id out of range"; return false; }
+            }
+            if (M.task_kind == dmk::kTaskStrike && X.n_strike == 0) { g_err = "strike_amp needs --strike_bodies"; return false; }
+            if (M.task_kind == dmk::kTaskHeadingGetup && !(X.getup_time > 0.0)) { g_err = "heading_amp_getup needs --getup_motion_ids"; return false; }
+        }
         dmk::TaskParams& T = M.task;
         T.timer_min = c.rand_target_time_min; T.timer_max = c.rand_target_time_max;
         T.max_target_dist = c.max_target_dist; T.target_succ_dist = c.target_succ_dist; T.tar_fail_dist = c.tar_fail_dist; T.pos_reward_scale = c.pos_reward_scale;
@@ -379,7 +404,7 @@ static bool load_host_model(dm_handle& H, const char* asset_root, int argc, cons
         // but it has not run on hardware yet: they are accepted only with DM_EXPERIMENTAL_TASK_SCENES=1, otherwise refused like every other scene.
         const char* exp_env = std::getenv("DM_EXPERIMENTAL_TASK_SCENES");
         const bool experimental = exp_env != nullptr && exp_env[0] == '1';
-        const bool task_scene = H.sa.cfg.scene == "target_amp" || H.sa.cfg.scene == "heading_amp";   // heading_amp_getup, strike_amp: oracle only so far
+        const bool task_scene = H.sa.cfg.is_task_scene();   // target_amp, heading_amp, heading_amp_getup, strike_amp
         if (H.sa.cfg.scene != "imitate" && H.sa.cfg.scene != "imitate_amp" && !(task_scene && experimental))
             throw std::runtime_error("Unsupported scene: " + H.sa.cfg.scene + " (supported: imitate, imitate_amp)");
         if (H.sa.clips.size() != 1 && !task_scene)
@@ -461,6 +486,7 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
         const double* fb = mc.frame(0); const double* fe = mc.frame(mc.num_frames - 1);
         ci.cycle_delta[0] = static_cast<float>(fe[0] - fb[0]); ci.cycle_delta[1] = 0.f; ci.cycle_delta[2] = static_cast<float>(fe[2] - fb[2]);
         h->ctab.cdf[c] = h->sa.clip_cdf[c];
+        ci.is_getup = std::find(h->sa.cfg.getup_motion_ids.begin(), h->sa.cfg.getup_motion_ids.end(), static_cast<int>(c)) != h->sa.cfg.getup_motion_ids.end() ? 1 : 0;
         h->total_frames += mc.num_frames;
     }
     const size_t TF = static_cast<size_t>(h->total_frames);
@@ -487,7 +513,9 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
     if (M.task_kind != dmk::kTaskNone) {
         if (!(chk(cudaMalloc(&h->st.task, N * dmk::kTaskDoubles * sizeof(double)), "cudaMalloc task") &&
               chk(cudaMemset(h->st.task, 0, N * dmk::kTaskDoubles * sizeof(double)), "memset task") &&
-              chk(cudaMalloc(&h->d_goal, N * 3 * sizeof(float)), "cudaMalloc goal") && chk(cudaMallocHost(&h->p_goal, N * 3 * sizeof(float)), "cudaMallocHost goal") &&
+              chk(cudaMalloc(&h->st.taskx, N * dmk::kTaskExtDoubles * sizeof(double)), "cudaMalloc taskx") &&
+              chk(cudaMemset(h->st.taskx, 0, N * dmk::kTaskExtDoubles * sizeof(double)), "memset taskx") &&
+              chk(cudaMalloc(&h->d_goal, N * 4 * sizeof(float)), "cudaMalloc goal") && chk(cudaMallocHost(&h->p_goal, N * 4 * sizeof(float)), "cudaMallocHost goal") &&
               chk(cudaMalloc(&h->st.clip, N * sizeof(int)), "cudaMalloc clip") && chk(cudaMemset(h->st.clip, 0, N * sizeof(int)), "memset clip") &&
               chk(cudaMalloc(&h->d_clip_inj, N * sizeof(int)), "cudaMalloc clip inject") &&
               chk(cudaMalloc(&h->d_ctab, sizeof(dmk::ClipTable)), "cudaMalloc clip table") &&
@@ -530,7 +558,7 @@ void dm_destroy(dm_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->st.task); cudaFree(h->d_goal); cudaFreeHost(h->p_goal); cudaFree(h->st.clip); cudaFree(h->d_clip_inj); cudaFree(h->d_ctab);
+    cudaFree(h->st.task); cudaFree(h->st.taskx); cudaFree(h->d_goal); cudaFreeHost(h->p_goal); cudaFree(h->st.clip); cudaFree(h->d_clip_inj); cudaFree(h->d_ctab);
     cudaFree(h->d_amp); cudaFreeHost(h->p_amp); cudaFree(h->st.hist); cudaFree(h->d_model); cudaFree(h->st.sim); cudaFree(h->st.time); cudaFree(h->st.flags); cudaFree(h->st.manifold);
     cudaFree(h->d_frame_times); cudaFree(h->d_frames); cudaFree(h->d_frame_vel); cudaFree(h->d_flags4); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew);
     for (auto& p : h->d_inj) cudaFree(p);
@@ -541,7 +569,7 @@ void dm_destroy(dm_handle* h) {
 
 int dm_get_dims(dm_handle* h, dm_dims* o) {
     const auto& M = h->hm;
-    o->num_envs = h->num_envs; o->num_joints = M.nl; o->pose_dim = M.pose_dim; o->num_dofs = M.n; o->state_size = M.state_size; o->goal_size = M.task_kind != dmk::kTaskNone ? 3 : 0; o->amp_obs_size = M.amp_obs_size;
+    o->num_envs = h->num_envs; o->num_joints = M.nl; o->pose_dim = M.pose_dim; o->num_dofs = M.n; o->state_size = M.state_size; o->goal_size = M.task_kind == dmk::kTaskNone ? 0 : (M.task_kind >= dmk::kTaskHeadingGetup ? 4 : 3); o->amp_obs_size = M.amp_obs_size;
     o->action_size = M.action_size; o->snapshot_size = 29 + 59 * M.nl;
     o->num_update_substeps = h->sa.cfg.num_update_substeps;
     o->updates_per_action = 20;
@@ -560,7 +588,16 @@ int dm_get_static(dm_handle* h, int kind, double* out) {
 }
 void* dm_stream(dm_handle* h) { return h->stream; }
 int dm_sync(dm_handle* h) { DM_DEVICE(h); DM_CUDA(cudaStreamSynchronize(h->stream)); return 0; }
-int dm_set_mode(dm_handle* h, int mode) { h->mode = mode; return 0; }
+int dm_set_mode(dm_handle* h, int mode) {
+    h->mode = mode;
+    h->hm.test_mode = mode;
+    if (h->stream != nullptr && h->hm.task_kind != dmk::kTaskNone) {   // the task scenes read the mode inside the kernels (test-mode get-ups, rewards)
+        DM_CUDA(cudaSetDevice(h->device));
+        DM_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h->d_model) + offsetof(dmk::DevModel, test_mode), &h->hm.test_mode, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        DM_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
 // cRLSceneSimChar::SetSampleCount -> UpdateTimerParams (RLSceneSimChar.cpp:223-227,330-347): the episode time limits move from
 // (time_lim_min, time_lim_max) to (time_end_lim_min, time_end_lim_max) with lerp = clamp(count / anneal_samples, 0, 1)^4.
 int dm_set_sample_count(dm_handle* h, long long count) {
@@ -665,9 +702,10 @@ int dm_goal_host(dm_handle* h, float* h_out) {
     if (h->hm.task_kind == dmk::kTaskNone) return 0;
     DM_DEVICE(h);
     if (launch_task_observe(h, h->d_goal, nullptr)) return 1;
-    DM_CUDA(cudaMemcpyAsync(h->p_goal, h->d_goal, static_cast<size_t>(h->num_envs) * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    const size_t gbytes = static_cast<size_t>(h->num_envs) * (h->hm.task_kind >= dmk::kTaskHeadingGetup ? 4 : 3) * sizeof(float);
+    DM_CUDA(cudaMemcpyAsync(h->p_goal, h->d_goal, gbytes, cudaMemcpyDeviceToHost, h->stream));
     DM_CUDA(cudaStreamSynchronize(h->stream));
-    std::memcpy(h_out, h->p_goal, static_cast<size_t>(h->num_envs) * 3 * sizeof(float));
+    std::memcpy(h_out, h->p_goal, gbytes);
     return 0;
 }
 // test hooks of the task scenes: the environment's task block (dm_task.cuh: TaskSlot) and the scene constants as the device sees them
@@ -676,6 +714,7 @@ int dm_get_task_state(dm_handle* h, int env, double* h_out) {
     DM_DEVICE(h);
     DM_CUDA(cudaStreamSynchronize(h->stream));
     DM_CUDA(cudaMemcpy(h_out, h->st.task + static_cast<size_t>(env) * dmk::kTaskDoubles, dmk::kTaskDoubles * sizeof(double), cudaMemcpyDeviceToHost));
+    DM_CUDA(cudaMemcpy(h_out + dmk::kTaskDoubles, h->st.taskx + static_cast<size_t>(env) * dmk::kTaskExtDoubles, dmk::kTaskExtDoubles * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
 int dm_set_task_state(dm_handle* h, int env, const double* h_in) {
@@ -683,6 +722,7 @@ int dm_set_task_state(dm_handle* h, int env, const double* h_in) {
     DM_DEVICE(h);
     DM_CUDA(cudaStreamSynchronize(h->stream));
     DM_CUDA(cudaMemcpy(h->st.task + static_cast<size_t>(env) * dmk::kTaskDoubles, h_in, dmk::kTaskDoubles * sizeof(double), cudaMemcpyHostToDevice));
+    DM_CUDA(cudaMemcpy(h->st.taskx + static_cast<size_t>(env) * dmk::kTaskExtDoubles, h_in + dmk::kTaskDoubles, dmk::kTaskExtDoubles * sizeof(double), cudaMemcpyHostToDevice));
     return 0;
 }
 int dm_get_task_params(dm_handle* h, double* o, unsigned long long* stream) {
@@ -690,6 +730,16 @@ int dm_get_task_params(dm_handle* h, double* o, unsigned long long* stream) {
     o[0] = h->hm.task_kind; o[1] = T.timer_min; o[2] = T.timer_max; o[3] = T.max_target_dist; o[4] = T.target_succ_dist; o[5] = T.tar_fail_dist; o[6] = T.pos_reward_scale;
     o[7] = T.max_heading_turn_rate; o[8] = T.sharp_turn_prob; o[9] = T.speed_change_prob; o[10] = T.tar_speed_min; o[11] = T.tar_speed_max; o[12] = T.vel_reward_scale;
     o[13] = T.tar_speed; o[14] = T.enable_min_tar_vel; o[15] = 0;
+    {   // dm_task_ext.cuh constants, in the order tests/task_shim.cpp reads them
+        const dmk::TaskExtParams& X = h->hm.taskx;
+        double* q = o + 16;
+        q[0] = X.getup_time; q[1] = X.getup_height_root; q[2] = X.getup_height_head; q[3] = X.recover_episode_prob;
+        for (int k = 0; k < 3; ++k) { q[4 + k] = X.target_min[k]; q[7 + k] = X.target_max[k]; }
+        q[10] = X.target_radius; q[11] = X.hit_reset_time; q[12] = X.tar_reward_scale; q[13] = X.hit_tar_speed; q[14] = X.init_hit_prob; q[15] = X.tar_far_prob; q[16] = X.tar_near_dist;
+        q[17] = X.head_id; q[18] = X.n_strike; q[23] = X.n_fail;
+        for (int k = 0; k < 4; ++k) { q[19 + k] = X.strike_bodies[k]; q[24 + k] = X.fail_bodies[k]; }
+        q[28] = q[29] = q[30] = q[31] = 0;
+    }
     if (stream) { stream[0] = h->hm.task_seed; stream[1] = h->hm.env_id_base; }
     return 0;
 }

@@ -12,6 +12,7 @@
 #include "dm_math.cuh"
 
 #include "dm_task.cuh"
+#include "dm_task_ext.cuh"
 
 namespace dmk {
 
@@ -68,6 +69,8 @@ struct DevModel {
     int task_kind;
     TaskParams task;
     unsigned long long task_seed, env_id_base;   // draw stream: u01(task_seed, env_id_base + env, k)
+    TaskExtParams taskx;                          // heading_amp_getup / strike_amp (dm_task_ext.cuh)
+    int test_mode, pad_task_;                     // cRLScene::eMode, kept current by dm_set_mode in the task scenes
     DevLink link[kMaxLinks];
     uint8_t chain_dof[kMaxLinks][kMaxChain];  // dof index at chain depth d on the path base -> link (valid for d <= last depth of link)
     uint8_t dof_depth[kMaxDofs];
@@ -83,6 +86,7 @@ struct ClipInfo {
     int frame_off;            // first frame of the clip in frame_times / frames / frame_vel (frame_times restart at 0 for every clip)
     int num_frames, loop;
     float cycle_delta[3];     // cKinController::CalcCycleRootDelta
+    int is_getup;             // cSceneHeadingAMPGetup::mGetupMotionFlags
 };
 struct ClipTable {
     int num_clips, pad_;
@@ -129,6 +133,7 @@ struct DevState {
     float* hist;  // AMP history: DeepMimic pose | vel vectors (2 * pose_dim floats per env) of the simulated character at the last applied action
     float* pdbg;  // optional debug scratch (n x ...), may be null
     double* task; // AMP task scenes: kTaskDoubles per env (dm_task.cuh), null otherwise
+    double* taskx; // ... and kTaskExtDoubles per env (dm_task_ext.cuh)
     int* clip;    // --kin_ctrl clips: active clip of every env, null for single-clip scenes
     const ClipTable* ctab;
     int num_envs;

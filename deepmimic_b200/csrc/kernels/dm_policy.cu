@@ -14,6 +14,7 @@ namespace {
 template <int W>
 struct TileP {
     static __device__ __forceinline__ float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src, W); }
+    static __device__ __forceinline__ int shfli(int v, int src) { return __shfl_sync(0xffffffffu, v, src, W); }
     static __device__ __forceinline__ V3 shfl3(V3 v, int src) { return mk3(shfl(v.x, src), shfl(v.y, src), shfl(v.z, src)); }
     static __device__ __forceinline__ float sum(float v) {
 #pragma unroll
@@ -507,6 +508,7 @@ __global__ void __launch_bounds__(BLOCK) dm_reset_kernel(const DevModel* __restr
     ClipModel CM;
     double reset_time_span = M.motion_dur;
     int new_clip = 0;
+    bool recovery = false;   // TASKV, get-up scene: this reset is a recovery episode (decided below, applied at the commit)
     if constexpr (TASKV) {
         const ClipTable& CT = *st.ctab;
         const int prev_clip = st.clip[env];
@@ -524,6 +526,18 @@ __global__ void __launch_bounds__(BLOCK) dm_reset_kernel(const DevModel* __restr
     double th = rot_theta_in ? rot_theta_in[env] : (M.rand_rot_reset ? (-3.14159265358979323846 + u01(seed, gid, 3 * cnt + 2) * 6.283185307179586) : 0.0);
     if (!M.rand_rot_reset) th = 0.0;
     if (test_mode) mt = M.time_end_lim_max;
+    if constexpr (TASKV) {
+        // cSceneHeadingAMPGetup::Reset (SceneHeadingAMPGetup.cpp:111-123): after a failed episode a coin decides on a recovery episode -- the fallen
+        // character stays as it is, only the scene timer and the controller clocks restart (ResetRecoveryEpisode, :40-58)
+        if (M.task_kind == kTaskHeadingGetup) {
+            int rec = 0;
+            if (lane == 0 && doit) {
+                TaskRng rng{M.task_seed, gid, st.task + static_cast<size_t>(env) * kTaskDoubles + kKCounter};
+                rec = getup_try_recovery(M.taskx, rng, test_mode != 0, fl[kFTerminate]) ? 1 : 0;
+            }
+            recovery = T::shfli(rec, 0) != 0;
+        }
+    }
     int idx, cyc; double bld;
     frame_index(KM, frame_times, kt, idx, bld, cyc);
     bld = fmin(fmax(bld, 0.0), 1.0);
@@ -583,6 +597,16 @@ __global__ void __launch_bounds__(BLOCK) dm_reset_kernel(const DevModel* __restr
     min_h = T::minf(min_h);
     const float min_violation = fminf(min_h, 0.f);
     if (min_violation < 0.f) basePos.y += -min_violation * M.scale;
+    if constexpr (TASKV) {
+        if (recovery) {   // all of the tile's shuffles are behind us: only lane 0 writes, the simulated state is left alone
+            if (lane == 0) {
+                tm[kTTimer] = 0.0; tm[kTTimerMax] = mt; tm[kTCtrl] = 0.0; tm[kTInitOff] = 0.0; tm[kTPrevAct] = 0.0;
+                fl[kFNeedAction] = 1; fl[kFDone] = 0; fl[kFTerminate] = 0; fl[kFValid] = 1; fl[kFFallen] = 0; fl[kFUpdates] = 0; fl[7] = fl[7] + 1;
+                st.taskx[static_cast<size_t>(env) * kTaskExtDoubles + kXRecover] = 1.0;
+            }
+            return;
+        }
+    }
     if (!doit) return;
     // ---- commit
     if (lane == 0) {
@@ -635,37 +659,66 @@ __global__ void dm_task_reset_kernel(const DevModel* __restrict__ gm, DevState s
     if (env >= num_envs) return;
     const DevModel& M = *gm;
     double* tk = st.task + static_cast<size_t>(env) * kTaskDoubles;
+    double* tx = st.taskx + static_cast<size_t>(env) * kTaskExtDoubles;
     const int* fl = st.flags + static_cast<size_t>(env) * kFlagInts;
     if (static_cast<double>(fl[7]) == tk[kKResetSeen]) return;
     const float* sim = st.sim + static_cast<size_t>(env) * sim_stride(M.nl);
+    const double* tm = st.time + static_cast<size_t>(env) * kTimeDoubles;
+    const int kind = M.task_kind;
     TaskRng rng{M.task_seed, M.env_id_base + static_cast<unsigned long long>(env), tk + kKCounter};
-    task_reset(M.task_kind, M.task, tk, rng, static_cast<double>(sim[0]) / M.scale, static_cast<double>(sim[2]) / M.scale);
+    const double rx = static_cast<double>(sim[0]) / M.scale, rz = static_cast<double>(sim[2]) / M.scale;
+    if (kind == kTaskHeadingGetup && tx[kXRecover] != 0.0) {   // recovery episode: target, timers of the task and the fallen character stay
+        getup_recovery_reset(tk, tx);
+        tx[kXRecover] = 0.0;
+    } else if (kind == kTaskStrike) {   // cSceneTargetAMP::Reset with cSceneStrikeAMP::ResetTarget (SceneStrikeAMP.cpp:300-383); scene time 0
+        task_timer_reset(M.task, tk, rng);
+        strike_reset_target(M.task, M.taskx, tk, tx, rng, rx, rz, 0.0, M.test_mode != 0);
+        tk[kKSpeed] = M.task.tar_speed;
+        tk[kKPrevCom] = tk[kKPrevCom + 1] = tk[kKPrevCom + 2] = 0.0;
+    } else {
+        task_reset(task_base_kind(kind), M.task, tk, rng, rx, rz);
+        if (kind == kTaskHeadingGetup) getup_reset(M.taskx, tx, tm[kTKin], st.ctab->info[st.clip[env]].is_getup != 0);   // SyncGetupTimer (:179-199)
+    }
     tk[kKCom] = tk[kKCom + 1] = tk[kKCom + 2] = 0.0;
     tk[kKResetSeen] = static_cast<double>(fl[7]);
 }
 
-// RecordGoal ([N x 3], SceneTargetAMP.cpp:185-215 / SceneHeadingAMP.cpp:136-151) and CalcReward ([N], SceneTargetAMP.cpp:3-80 /
-// SceneHeadingAMP.cpp:3-48) from the committed base state and the task block.  Either pointer may be null.
+// RecordGoal ([N x goal_size]: 3, or 4 with the get-up / hit phase) and CalcReward ([N]) of the task scenes from the committed base state and the
+// task blocks (SceneTargetAMP.cpp:3-80,185-215; SceneHeadingAMP.cpp:3-48,136-151; SceneHeadingAMPGetup.cpp:4-38,125-133; SceneStrikeAMP.cpp:9-190,407-430).
 __global__ void dm_task_observe_kernel(const DevModel* __restrict__ gm, DevState st, float* __restrict__ goal, float* __restrict__ reward, int num_real_envs) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= num_real_envs) return;
     const DevModel& M = *gm;
     const double* tk = st.task + static_cast<size_t>(env) * kTaskDoubles;
+    const double* tx = st.taskx + static_cast<size_t>(env) * kTaskExtDoubles;
     const double* tm = st.time + static_cast<size_t>(env) * kTimeDoubles;
     const int* fl = st.flags + static_cast<size_t>(env) * kFlagInts;
     const float* sim = st.sim + static_cast<size_t>(env) * sim_stride(M.nl);
-    const double rx = static_cast<double>(sim[0]) / M.scale, rz = static_cast<double>(sim[2]) / M.scale;
+    const int kind = M.task_kind;
+    const double rx = static_cast<double>(sim[0]) / M.scale, ry = static_cast<double>(sim[1]) / M.scale, rz = static_cast<double>(sim[2]) / M.scale;
     if (goal != nullptr) {
         // heading of the root joint (cKinTree::CalcHeading): the root rotation is the inverse of the stored world->base quaternion
         const double qx = -static_cast<double>(sim[4]), qy = -static_cast<double>(sim[5]), qz = -static_cast<double>(sim[6]), qw = static_cast<double>(sim[7]);
         const double hx = 1.0 - 2.0 * (qy * qy + qz * qz), hz = 2.0 * (qx * qz - qw * qy);   // rotate (1, 0, 0)
-        double g[3];
-        task_goal(M.task_kind, tk, rx, rz, atan2(-hz, hx), g);
-        float* o = goal + static_cast<size_t>(env) * 3;
-        o[0] = static_cast<float>(g[0]); o[1] = static_cast<float>(g[1]); o[2] = static_cast<float>(g[2]);
+        const double heading = atan2(-hz, hx);
+        double g[4] = {0.0, 0.0, 0.0, 0.0};
+        int gs = 3;
+        if (kind == kTaskStrike) { strike_goal(M.taskx, tk, tx, rx, rz, heading, tm[kTTimer], g); gs = 4; }
+        else {
+            task_goal(task_base_kind(kind), tk, rx, rz, heading, g);
+            if (kind == kTaskHeadingGetup) { g[3] = getup_phase(M.taskx, tx); gs = 4; }
+        }
+        float* o = goal + static_cast<size_t>(env) * gs;
+        for (int k = 0; k < gs; ++k) o[k] = static_cast<float>(g[k]);
     }
-    if (reward != nullptr)
-        reward[env] = static_cast<float>(task_reward(M.task_kind, M.task, tk, fl[kFFallen] != 0, rx, rz, tm[kTCtrl] - tm[kTPrevAct]));
+    if (reward != nullptr) {
+        const double step_dur = tm[kTCtrl] - tm[kTPrevAct];
+        double r;
+        if (kind == kTaskStrike) r = strike_reward(M.task, M.taskx, tk, tx, fl[kFFallen] != 0, rx, rz, step_dur, M.test_mode != 0, fl[kFTerminate], tm[kTTimerMax], tm[kTTimer]);
+        else if (kind == kTaskHeadingGetup && getup_active(M.taskx, tx)) r = getup_reward(M.taskx, ry, tx[kXHeadY]);
+        else r = task_reward(task_base_kind(kind), M.task, tk, fl[kFFallen] != 0, rx, rz, step_dur);
+        reward[env] = static_cast<float>(r);
+    }
 }
 
 template __global__ void dm_observe_kernel<16, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);

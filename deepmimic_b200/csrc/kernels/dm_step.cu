@@ -1100,7 +1100,8 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     float* mani = st.manifold + static_cast<size_t>(env) * nl * kManifoldFloats;
     // AMP task scenes (TASK instantiations only): the environment's task block, advanced by lane 0 after every update (dm_task.cuh)
     double* tk = nullptr;
-    if constexpr (TASK) tk = st.task + static_cast<size_t>(env) * kTaskDoubles;
+    double* tkx = nullptr;
+    if constexpr (TASK) { tk = st.task + static_cast<size_t>(env) * kTaskDoubles; tkx = st.taskx + static_cast<size_t>(env) * kTaskExtDoubles; }
     float* sB = sG + 21;   // base state, owned by lane 0: position [0..2], quaternion (world->base) [3..6], omega_w [7..9], v_w [10..12]
     if (lane == 0) {
         float4 b0 = reinterpret_cast<const float4*>(sim)[0], b1 = reinterpret_cast<const float4*>(sim)[1], b2 = reinterpret_cast<const float4*>(sim)[2],
@@ -1168,25 +1169,58 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             float mx = fmaxf(fmaxf(fmaxf(fabsf(vw.x), fabsf(vw.y)), fabsf(vw.z)), fmaxf(fmaxf(fabsf(wa.x), fabsf(wa.y)), fabsf(wa.z)));
             const unsigned eb = __ballot_sync(0xffffffffu, act && mx > 100.f);
             const unsigned eseg = (W == 32) ? eb : ((eb >> (threadIdx.x & 16)) & 0xffffu);
-            int task_fail = 0;
+            int task_fail = 0;          // 0 none, 1 fail, 2 success (cRLScene::eTerminate)
+            int fallen_eff = fallen;    // HasFallen as the scene sees it (the get-up scene ignores contacts while getting up)
             if constexpr (TASK) {
                 // cSceneTargetAMP::Update: target timer / position / heading / speed after the scene update, then the distance failure of
-                // CheckTerminate; the COM is kept for CalcReward (SceneTargetAMP.cpp:3-80,136-145,294-319)
+                // CheckTerminate; the COM is kept for CalcReward (SceneTargetAMP.cpp:3-80,136-145,294-319).  heading_amp_getup and strike_amp
+                // (dm_task_ext.cuh) additionally need a few bodies' positions / velocities, published to lane 0 by shuffles.
                 const V3 com = tile_com<W>(E + LY.oW + li * 12, v, act ? LKo[kLM] : 0.f, 1.0f / (M.total_mass * scale));
-                int tf = 0;
+                const int kind = M.task_kind;
+                TaskBodies B;
+                if (kind >= kTaskHeadingGetup) {
+                    const float* w_ = E + LY.oW + li * 12;
+                    const V3 cpos = mk3((w_[9] + v[6]) / scale, (w_[10] + v[7]) / scale, (w_[11] + v[8]) / scale);   // this lane's body COM, unscaled
+                    const TaskExtParams& X = M.taskx;
+                    B.head_y = T::shfl(cpos.y, X.head_id);
+                    B.contact_fall = fallen;
+#pragma unroll
+                    for (int k = 0; k < kMaxTaskBodies; ++k) {
+                        const V3 sp = T::shfl3(cpos, k < X.n_strike ? X.strike_bodies[k] : 0), sv = T::shfl3(vw, k < X.n_strike ? X.strike_bodies[k] : 0);
+                        const V3 fp = T::shfl3(cpos, k < X.n_fail ? X.fail_bodies[k] : 0);
+                        B.spos[k][0] = sp.x; B.spos[k][1] = sp.y; B.spos[k][2] = sp.z; B.svel[k][0] = sv.x; B.svel[k][1] = sv.y; B.svel[k][2] = sv.z;
+                        B.fpos[k][0] = fp.x; B.fpos[k][1] = fp.y; B.fpos[k][2] = fp.z;
+                    }
+                }
+                int tf = 0, fe = fallen;
                 if (lane == 0 && alive) {
                     TaskRng rng{M.task_seed, M.env_id_base + static_cast<unsigned long long>(env), tk + kKCounter};
                     const double rx = static_cast<double>(sB[0]) / M.scale, rz = static_cast<double>(sB[2]) / M.scale;
-                    task_update(M.task_kind, M.task, tk, rng, dt, rx, rz);
                     tk[kKCom] = com.x; tk[kKCom + 1] = com.y; tk[kKCom + 2] = com.z;
-                    tf = task_dist_fail(M.task_kind, M.task, tk, rx, rz) ? 1 : 0;
+                    if (kind == kTaskStrike) {
+                        // cSceneTargetAMP::UpdateTarget without the timed re-draw (CheckTargetReset is false in this scene), hit detection,
+                        // then the target timer's own restart (SceneTargetAMP.cpp:136-145; SceneStrikeAMP.cpp:289-298,385-388)
+                        const double scene_time = tm[kTTimer];
+                        tk[kKTimer] += dt;
+                        strike_update(M.taskx, tk, tkx, rx, rz, scene_time, B);
+                        if (tk[kKTimer] >= tk[kKTimerMax]) task_timer_reset(M.task, tk, rng);
+                        tf = strike_terminate(M.task, M.taskx, tk, tkx, rx, rz, scene_time);
+                    } else {
+                        task_update(task_base_kind(kind), M.task, tk, rng, dt, rx, rz);
+                        tf = task_dist_fail(kind, M.task, tk, rx, rz) ? 1 : 0;
+                        if (kind == kTaskHeadingGetup) {
+                            tkx[kXHeadY] = B.head_y;
+                            if (getup_update(M.taskx, tkx, dt, M.test_mode != 0, fallen != 0)) fe = 0;   // HasFallenContact override while getting up
+                        }
+                    }
                 }
                 task_fail = T::shfli(tf, 0);
+                fallen_eff = T::shfli(fe, 0);
             }
             if (alive) {
-                int term = (M.enable_fall_end && fallen) ? 1 : 0;
+                int term = (M.enable_fall_end && fallen_eff) ? 1 : 0;
                 if (!term && (cbits & 4)) term = 1;
-                if (TASK && !term && task_fail) term = 1;
+                if (TASK && !term && task_fail) term = task_fail;
                 f_updates++;
                 const bool end = (cbits & 2) || term;
                 if (end || stage == total_stages) {   // commit
@@ -1195,7 +1229,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                         reinterpret_cast<float4*>(sim)[1] = make_float4(sB[3], sB[4], sB[5], sB[6]);
                         reinterpret_cast<float4*>(sim)[2] = make_float4(sB[7], sB[8], sB[9], 0.f);
                         reinterpret_cast<float4*>(sim)[3] = make_float4(sB[10], sB[11], sB[12], 0.f);
-                        fl[kFNeedAction] = need_action; fl[kFDone] = end ? 1 : 0; fl[kFTerminate] = term; fl[kFValid] = (eseg == 0) ? 1 : 0; fl[kFFallen] = fallen;
+                        fl[kFNeedAction] = need_action; fl[kFDone] = end ? 1 : 0; fl[kFTerminate] = term; fl[kFValid] = (eseg == 0) ? 1 : 0; fl[kFFallen] = fallen_eff;
                         fl[kFRowOverflow] = f_over; fl[kFUpdates] = f_updates;
                     }
                     if (act) {

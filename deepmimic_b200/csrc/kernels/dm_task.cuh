@@ -16,7 +16,9 @@
 
 namespace dmk {
 
-enum TaskKind { kTaskNone = 0, kTaskTarget = 1, kTaskHeading = 2 };
+enum TaskKind { kTaskNone = 0, kTaskTarget = 1, kTaskHeading = 2, kTaskHeadingGetup = 3, kTaskStrike = 4 };   // 3, 4: dm_task_ext.cuh on top
+// the dm_task.cuh behaviour a scene builds on: the get-up scene is a heading scene, the strike scene a target scene
+DM_HD int task_base_kind(int kind) { return kind == kTaskHeadingGetup ? kTaskHeading : (kind == kTaskStrike ? kTaskTarget : kind); }
 
 // scene constants (cSceneTargetAMP::ParseArgs SceneTargetAMP.cpp:107-120, cSceneHeadingAMP::ParseArgs SceneHeadingAMP.cpp:71-88)
 struct TaskParams {

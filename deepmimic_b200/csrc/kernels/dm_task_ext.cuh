@@ -1,6 +1,6 @@
 // Per-environment logic of two more AMP task scenes, written as host / device-shared code like dm_task.cuh and checked against the oracle on the
-// host (tests/test_task_scenes_cpu.py through tests/task_shim.cpp).  NOT yet called by any kernel: the device glue (what the tile publishes to
-// lane 0 every update, the reset / observe kernels) is the next step; dm_create refuses these scenes.
+// host (tests/test_task_scenes_cpu.py through tests/task_shim.cpp).  The device glue (what the tile publishes to lane 0 every update in
+// dm_step_kernel<.., kVarTask>, the task reset / observe kernels) is written but has not run on hardware: opt-in, DM_EXPERIMENTAL_TASK_SCENES=1.
 //   cSceneHeadingAMPGetup  R/DeepMimicCore/scenes/SceneHeadingAMPGetup.cpp  get-up timer, phase goal, get-up reward, recovery episodes
 //   cSceneStrikeAMP        R/DeepMimicCore/scenes/SceneStrikeAMP.cpp        point target, hit detection, three-regime reward, success
 // Both sit on top of the target / heading logic of dm_task.cuh (task block t, draw stream TaskRng); their own state lives in an extension block x.
@@ -28,7 +28,9 @@ enum TaskExtSlot {
     kXHitTime = 2,     // strike: mTargetHitTime (scene time of the hit, -1 = none)
     kXGetupTimer = 3,  // get-up: mGetupTimer time (its end is getup_time)
     kXNearR = 4,       // strike: near-regime reward term of the current state (max over the strike bodies)
-    kXContactFail = 5  // strike: a forbidden body is inside the target sphere
+    kXContactFail = 5, // strike: a forbidden body is inside the target sphere
+    kXHeadY = 6,       // get-up: height of body head_id after the last update (for CalcRewardGetup at the next query)
+    kXRecover = 7      // get-up: the reset kernel started a recovery episode (consumed by the task reset kernel)
 };
 
 // what the environment's tile hands to lane 0 after an update: unscaled world positions / COM velocities of a few bodies

@@ -103,7 +103,7 @@ int dm_record_amp_obs_expert_clips(dm_handle* h, const int* h_clip, const double
 int dm_get_clip_table(dm_handle* h, int* num_clips, double* h_dur, double* h_cdf);
 int dm_get_task_state(dm_handle* h, int env, double* h_out16);
 int dm_set_task_state(dm_handle* h, int env, const double* h_in16);
-int dm_get_task_params(dm_handle* h, double* h_out16, unsigned long long* h_stream2);
+int dm_get_task_params(dm_handle* h, double* h_out48, unsigned long long* h_stream2);   /* 16 dm_task.cuh + 32 dm_task_ext.cuh constants */
 int dm_calc_reward(dm_handle* h, float* d_out);              /* [num_envs] */
 /* AMP observations (RecordAMPObsAgent / RecordAMPObsExpert, DeepMimicCore.h:81-82; cSceneImitateAMP::BuildAMPObs): [num_envs x amp_obs_size].
  * Agent: simulated pose / vel now and at the last dm_set_action (call dm_set_action exactly when need_new_action is set, like the

@@ -407,8 +407,19 @@ def test_task_scenes_stay_refused_without_the_opt_in(asset_root, monkeypatch):
     dur, cdf = m.clip_table()
     o = Oracle(TARGET, asset_root)
     np.testing.assert_array_equal(dur, o.clip_table()[0]); np.testing.assert_array_equal(cdf, o.clip_table()[2])
-    with pytest.raises(RuntimeError, match="Unsupported scene"):                # the get-up variant is restated in the oracle only
-        capi.HostModel(["--scene", "heading_amp_getup", "--getup_motion_ids", "1", "2"] + HEADING, asset_root)
+    # the get-up and strike scenes load too (goal size 4) and the loader hands the device the constants the host-checked logic was tested with
+    g = capi.HostModel(GETUP, asset_root)
+    Pg, _, _ = g.task_params()
+    assert g.dims.goal_size == 4 and Pg[0] == 3
+    np.testing.assert_allclose(Pg[16:48], _ext_params(getup_time=max(dur[1], dur[2]), root_h=1.2, head_h=2.0, head_id=2), atol=0)
+    k = capi.HostModel(STRIKE, asset_root)
+    Pk, _, _ = k.task_params()
+    assert k.dims.goal_size == 4 and Pk[0] == 4
+    np.testing.assert_allclose(Pk[16:48], _ext_params(head_id=0, strike=(8,), fail=(0, 1, 2), init_hit=0.1), atol=0)
+    np.testing.assert_allclose(Pk[:7], [4, 5.0, 10.0, 10.0, 0.5, 15.0, 0.5], atol=0)   # kind, target timer, max / success / fail distance, pos reward scale
+    np.testing.assert_allclose(Pk[13:15], [1.0, 1.0], atol=0)                          # tar_speed, enable_min_tar_vel
+    with pytest.raises(RuntimeError, match="strike_amp needs --strike_bodies"):
+        capi.HostModel(["--scene", "strike_amp"] + TARGET, asset_root)
     with pytest.raises(RuntimeError, match="more than one clip"):               # ... but not in the plain AMP imitation scene
         capi.HostModel(["--scene", "imitate_amp"] + TARGET, asset_root)
 

@@ -19,10 +19,15 @@ pytestmark = [pytest.mark.gpu,
 MINI = ["--motion_file", "data/datasets/test_clips_mini.txt"]                    # 4-clip dataset of the committed asset archive (--kin_ctrl clips)
 TARGET = ["--rand_target_time_min", "1", "--rand_target_time_max", "2"] + MINI + ["--arg_file", "args/train_amp_target_humanoid3d_locomotion_args.txt"]
 HEADING = MINI + ["--arg_file", "args/train_amp_heading_humanoid3d_locomotion_args.txt"]
+# heading_amp_getup / strike_amp on the same assets (clips 1, 2 of the mini dataset stand in for the get-up motions; see tests/test_task_scenes_cpu.py)
+GETUP = ["--scene", "heading_amp_getup", "--getup_motion_ids", "1", "2", "--getup_height_root", "1.2", "--getup_height_head", "2.0", "--head_id", "2"] + HEADING
+STRIKE = ["--scene", "strike_amp", "--target_hit_reset_time", "2", "--target_radius", "0.2", "--target_min", "-0.5", "1.2", "0.6", "--target_max", "0.5", "1.4", "1.1",
+          "--tar_near_dist", "1.4", "--tar_far_prob", "0.4", "--strike_bodies", "8", "--fail_tar_contact_bodies", "0", "1", "2", "--init_hit_prob", "0.1",
+          "--hit_tar_speed", "1.5", "--tar_reward_scale", "2"] + TARGET
 N = 32
 
 
-@pytest.mark.parametrize("args", [TARGET, HEADING])
+@pytest.mark.parametrize("args", [TARGET, HEADING, GETUP, STRIKE])
 def test_task_goal_reward_and_updates_match_the_oracle(asset_root, args, monkeypatch):
     """Free-running comparison over 3 s under one random action sequence per environment: same draw stream (seed, global env id), so the
     target timers, headings and speeds must agree exactly in count and to rounding in value; goals and rewards to the fp32 state's accuracy."""
@@ -31,7 +36,8 @@ def test_task_goal_reward_and_updates_match_the_oracle(asset_root, args, monkeyp
     monkeypatch.setenv("DM_EXPERIMENTAL_TASK_SCENES", "1")
     core = capi.BatchedCore(args, N, asset_root, seed=21, global_env_offset=100)
     P, task_seed, env_base = core.task_params()
-    assert core.dims.goal_size == 3 and env_base == 100
+    G = core.dims.goal_size
+    assert G == (4 if args in (GETUP, STRIKE) else 3) and env_base == 100
     kin_time = np.linspace(0.0, 0.7, N); theta = np.linspace(-3.0, 3.0, N); max_time = np.full(N, 20.0); clip = np.arange(N) % 4
     core.reset(force_all=True, kin_time=kin_time, max_time=max_time, rot_theta=theta, clip=clip)
     oracles = []
@@ -50,8 +56,15 @@ def test_task_goal_reward_and_updates_match_the_oracle(asset_root, args, monkeyp
     for e, o in enumerate(oracles):
         np.testing.assert_allclose(st0[e].cpu().numpy(), o.record_state(), atol=2e-4)
         np.testing.assert_allclose(amp[e].cpu().numpy(), o.record_amp_obs_expert(etime[e], clip=int(eclip[e])), atol=2e-3)
-    goal = torch.zeros(N, 3, device="cuda"); rew = torch.zeros(N, device="cuda"); flags = torch.zeros(N, 4, dtype=torch.int32, device="cuda")
+    goal = torch.zeros(N, G, device="cuda"); rew = torch.zeros(N, device="cuda"); flags = torch.zeros(N, 4, dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
+    if args is STRIKE:   # every 4th environment gets its target right at the (moving) hand so that hits, holds and successes occur in the run
+        for e in range(0, N, 4):
+            o = oracles[e]
+            pos, _, lv, _ = o.body_state()
+            ts = o.task_state()
+            o.set_task_state(pos[8] + 0.02 * lv[8] / (np.linalg.norm(lv[8]) + 1e-9), 1.0, 0.0, ts["timer"], ts["timer_max"], ts["prev_action_com"])
+            o.set_strike_state(False, -1.0)
     rng = np.random.default_rng(5)
     st = oracles[0].action_statics()
     worst_goal = worst_rew = 0.0
@@ -67,6 +80,11 @@ def test_task_goal_reward_and_updates_match_the_oracle(asset_root, args, monkeyp
             tb[0], tb[1] = ts["target_pos"][0], ts["target_pos"][2]
             tb[2:6] = [ts["target_speed"], ts["target_heading"], ts["timer"], ts["timer_max"]]
             tb[6:9] = ts["prev_action_com"]; tb[12] = o.task_counter()
+            if args is GETUP:
+                tb[16 + 3] = o.getup_state()["timer"]
+            if args is STRIKE:
+                ss = o.strike_state()
+                tb[16 + 0], tb[16 + 1], tb[16 + 2] = ss["target_height"], float(ss["hit"]), ss["hit_time"]
             core.set_task_state(e, tb)
         a = np.clip(-st[0] + 0.1 / st[1] * rng.standard_normal((N, oracles[0].action_size)), st[2], st[3])
         core.set_action(torch.as_tensor(a, dtype=torch.float32, device="cuda"))
@@ -89,6 +107,13 @@ def test_task_goal_reward_and_updates_match_the_oracle(asset_root, args, monkeyp
             np.testing.assert_allclose([tb[0], tb[1]], ts["target_pos"][[0, 2]], atol=2e-3)  # target = root position (fp32 sim state) + draw
             np.testing.assert_allclose(tb[6:9], ts["prev_action_com"], atol=1e-4)           # COM at the action (fp32 link frames)
             np.testing.assert_allclose(tb[9:12], o.calc_com(), atol=2e-3)                    # COM after 20 free updates
+            if args is GETUP:
+                assert tb[16 + 3] == pytest.approx(o.getup_state()["timer"], abs=1e-9)
+            if args is STRIKE:
+                ss = o.strike_state()
+                assert bool(tb[16 + 1]) == ss["hit"] and tb[16 + 0] == pytest.approx(ss["target_height"], abs=1e-9)
+                if ss["hit"]:
+                    assert tb[16 + 2] == pytest.approx(ss["hit_time"], abs=1e-9)
             worst_goal = max(worst_goal, float(np.abs(g[e] - o.record_goal()).max()))
             if not o.has_fallen():
                 worst_rew = max(worst_rew, abs(float(r[e]) - o.calc_reward()))
