@@ -9,6 +9,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -112,8 +113,21 @@ public:
     virtual int GetNumActions(int) const { return 0; }
     virtual std::vector<double> BuildStateOffset(int) const { return Static(DM_STATE_OFFSET, mDims.state_size); }
     virtual std::vector<double> BuildStateScale(int) const { return Static(DM_STATE_SCALE, mDims.state_size); }
-    virtual std::vector<double> BuildGoalOffset(int) const { return std::vector<double>(mDims.goal_size, 0.0); }   // RLSceneSimChar.cpp:111-116
-    virtual std::vector<double> BuildGoalScale(int) const { return std::vector<double>(mDims.goal_size, 1.0); }
+    int TaskKind() const {   // dm_task.cuh: 0 none, 1 target, 2 heading, 3 heading + get-up, 4 strike
+        if (mDims.goal_size == 0) return 0;
+        double p[48]; dm_get_task_params(mHandle, p, nullptr);
+        return static_cast<int>(p[0]);
+    }
+    virtual std::vector<double> BuildGoalOffset(int) const {   // RLSceneSimChar.cpp:111-116; SceneHeadingAMPGetup.cpp:142-149
+        std::vector<double> v(mDims.goal_size, 0.0);
+        if (TaskKind() == 3) v[3] = -0.5;
+        return v;
+    }
+    virtual std::vector<double> BuildGoalScale(int) const {
+        std::vector<double> v(mDims.goal_size, 1.0);
+        if (TaskKind() == 3) v[3] = 2.0;
+        return v;
+    }
     virtual std::vector<double> BuildActionOffset(int) const { return Static(DM_ACTION_OFFSET, mDims.action_size); }
     virtual std::vector<double> BuildActionScale(int) const { return Static(DM_ACTION_SCALE, mDims.action_size); }
     virtual std::vector<double> BuildActionBoundMin(int) const { return Static(DM_ACTION_BOUND_MIN, mDims.action_size); }
@@ -122,7 +136,13 @@ public:
         std::vector<double> g = Static(DM_STATE_NORM_GROUPS, mDims.state_size);
         return std::vector<int>(g.begin(), g.end());
     }
-    virtual std::vector<int> BuildGoalNormGroups(int) const { return std::vector<int>(mDims.goal_size, 0); }
+    virtual std::vector<int> BuildGoalNormGroups(int) const {   // RLSceneSimChar.cpp:136-140; SceneHeadingAMPGetup.cpp:151-157; SceneStrikeAMP.cpp:401-405
+        std::vector<int> v(mDims.goal_size, 0);
+        const int kind = TaskKind();
+        if (kind == 3) v[3] = -1;
+        if (kind == 4) std::fill(v.begin(), v.end(), -1);
+        return v;
+    }
     virtual double CalcReward(int agent_id) { Refresh(); return mReward[Env(agent_id)]; }
     virtual double GetRewardMin(int) const { return 0; }
     virtual double GetRewardMax(int) const { return 1; }

@@ -182,11 +182,21 @@ class DeepMimicBatchEnv:
     def build_state_scale(self, agent_id=0):
         return np.array(self._core.static(DM_STATE_SCALE))
 
+    def _task_kind(self):
+        """0 none, 1 target_amp, 2 heading_amp, 3 heading_amp_getup, 4 strike_amp (dm_task.cuh: TaskKind)"""
+        return int(self._core.task_params()[0][0]) if self._core.dims.goal_size > 0 else 0
+
     def build_goal_offset(self, agent_id=0):
-        return np.zeros(self._core.dims.goal_size)          # cRLSceneSimChar::BuildGoalOffsetScale (RLSceneSimChar.cpp:111-116)
+        off = np.zeros(self._core.dims.goal_size)           # cRLSceneSimChar::BuildGoalOffsetScale (RLSceneSimChar.cpp:111-116)
+        if self._task_kind() == 3:
+            off[3] = -0.5                                   # the get-up phase (SceneHeadingAMPGetup.cpp:142-149)
+        return off
 
     def build_goal_scale(self, agent_id=0):
-        return np.ones(self._core.dims.goal_size)
+        scl = np.ones(self._core.dims.goal_size)
+        if self._task_kind() == 3:
+            scl[3] = 2.0
+        return scl
 
     def build_action_offset(self, agent_id=0):
         return np.array(self._core.static(DM_ACTION_OFFSET))
@@ -204,7 +214,13 @@ class DeepMimicBatchEnv:
         return np.array(self._core.static(DM_STATE_NORM_GROUPS), dtype=np.int32)
 
     def build_goal_norm_groups(self, agent_id=0):
-        return np.zeros(self._core.dims.goal_size, dtype=np.int32)   # gNormGroupSingle (RLSceneSimChar.cpp:136-140)
+        g = np.zeros(self._core.dims.goal_size, dtype=np.int32)      # gNormGroupSingle (RLSceneSimChar.cpp:136-140)
+        kind = self._task_kind()
+        if kind == 3:
+            g[3] = -1                                                # gNormGroupNone for the get-up phase (SceneHeadingAMPGetup.cpp:151-157)
+        elif kind == 4:
+            g[:] = -1                                                # no normalisation of the strike goal (SceneStrikeAMP.cpp:401-405)
+        return g
 
     def get_reward_min(self, agent_id=0):
         return 0.0
