@@ -205,3 +205,45 @@ def test_step_exchange_gloo_world2(total):
     for rank, g, tmax in got:
         np.testing.assert_array_equal(g[:total], expect)      # every rank sees the whole job, in global env order
         assert tmax == 2.0
+
+
+def test_malformed_assets_are_rejected_with_messages(asset_root, tmp_path):
+    """Ragged / empty / mismatching inputs: the loaders of the C-ABI library and of the oracle refuse them with the reference's messages
+    (cMotion::LoadJson Motion.cpp:104-141,303-360; cKinTree::Load KinTree.cpp:204-258; cClipsController::LoadMotions ClipsController.cpp:145-188)."""
+    import json
+    walk = json.load(open(os.path.join(asset_root, "data/motions/humanoid3d_walk.txt")))
+    char = json.load(open(os.path.join(asset_root, "data/characters/humanoid3d.txt")))
+
+    def write(name, obj):
+        p = os.path.join(str(tmp_path), name)
+        json.dump(obj, open(p, "w"))
+        return p
+
+    base = ["--arg_file", ARG_FILES[1]]
+    ragged = dict(walk); ragged["Frames"] = [f[:] for f in walk["Frames"][:5]]; ragged["Frames"][3] = ragged["Frames"][3][:-2]
+    cases = [
+        (["--motion_file", write("ragged.txt", ragged)], "ragged frame"),
+        (["--motion_file", write("empty.txt", {"Loop": "wrap", "Frames": []})], "Failed to load motion"),
+        (["--motion_file", write("noframes.txt", {"Loop": "wrap"})], "Failed to load motion"),
+        (["--motion_file", write("badloop.txt", {"Loop": "sometimes", "Frames": walk["Frames"][:4]})], "Unsupported loop mode"),
+        (["--motion_file", os.path.join(asset_root, "data/motions/dog3d_trot.txt")], "DOF mismatch"),
+    ]
+    bad_char = json.loads(json.dumps(char)); bad_char["Skeleton"]["Joints"][3]["Type"] = "ball_and_socket"
+    cases.append((["--character_files", write("badjoint.txt", bad_char)], "Unsupported joint type"))
+    bad_char = json.loads(json.dumps(char)); bad_char["BodyDefs"] = bad_char["BodyDefs"][:-1]
+    cases.append((["--character_files", write("fewbodies.txt", bad_char)], "joint / body count mismatch"))
+    bad_char = json.loads(json.dumps(char)); bad_char["Skeleton"]["Joints"][2]["Parent"] = 7
+    cases.append((["--character_files", write("badparent.txt", bad_char)], "Parent id must be"))
+    open(os.path.join(str(tmp_path), "notjson.txt"), "w").write("{ this is not json")
+    cases.append((["--character_files", os.path.join(str(tmp_path), "notjson.txt")], None))
+    for extra, msg in cases:
+        with pytest.raises(RuntimeError, match=msg):
+            capi.HostModel(extra + base, asset_root)
+        with pytest.raises(RuntimeError, match=msg):
+            Oracle(extra + base, asset_root)
+    # clip datasets (oracle; the C-ABI loader takes them in the task scenes only)
+    ds_missing = write("ds_missing.txt", {"Motions": [{"File": "data/motions/humanoid3d_walk.txt"}, {"File": "data/motions/nope.txt"}]})
+    ds_empty = write("ds_empty.txt", {"Motions": []})
+    for ds in (ds_missing, ds_empty, write("ds_nokey.txt", {"Clips": []})):
+        with pytest.raises(RuntimeError):
+            Oracle(["--kin_ctrl", "clips", "--motion_file", ds] + base, asset_root)
