@@ -538,8 +538,12 @@ struct Ctx {
 __device__ __forceinline__ const StepLayout& lay_of(const Ctx& c) { return *reinterpret_cast<const StepLayout*>(c.LYS); }
 // The phase routines are real calls (__noinline__), so the compiler cannot see that the context's pointers address shared memory and would emit
 // generic LD / ST for them; these address-space hints turn them back into LDS / STS.
+#ifndef DM_NO_SHARED_HINTS   // `make nohints` builds the A/B library without them (libdeepmimic_b200_nohints.so, select with DM_LIB)
 #define DM_ASSUME_SHARED_CTX(c) do { __builtin_assume(__isShared((c).E)); __builtin_assume(__isShared((c).LYS)); __builtin_assume(__isShared((c).LK)); \
                                      __builtin_assume(__isShared((c).LVC)); } while (0)
+#else
+#define DM_ASSUME_SHARED_CTX(c) do { } while (0)
+#endif
 __device__ __forceinline__ S6 shift_m(S6 m, V3 c) { return mks(m.a, m.l + cross(m.a, c)); }   // motion vector: reference point moved by +c
 __device__ __forceinline__ S6 shift_f(S6 f, V3 c) { return mks(f.a + cross(c, f.l), f.l); }   // force vector: child pivot -> parent pivot (child = parent + c)
 __device__ __forceinline__ float cl100(float v) { return fminf(fmaxf(v, -100.f), 100.f); }   // applyDeltaVeeMultiDof clamp
