@@ -17,6 +17,10 @@ FILES = [
     "args/run_dog3d_trot_args.txt", "args/train_dog3d_trot_args.txt", "args/train_dog3d_pace_args.txt",
     # AMP task scenes (target / heading); their 48 MB clip dataset is replaced in the tests by the authored mini dataset below
     "args/train_amp_target_humanoid3d_locomotion_args.txt", "args/train_amp_heading_humanoid3d_locomotion_args.txt",
+    # heading + get-up: its 4-clip dataset is small enough to ship whole (run and walk are above); strike: args only, run on the mini dataset
+    "args/train_amp_heading_getup_humanoid3d_locomotion_getup_args.txt", "data/datasets/humanoid3d_clips_locomotion_getup.txt",
+    "data/motions/humanoid3d_getup_facedown.txt", "data/motions/humanoid3d_getup_faceup.txt",
+    "args/train_amp_strike_humanoid3d_walk_punch_args.txt",
 ]
 
 # Authored here (not reference data): a cClipsController dataset over clips that are already in the archive, in the reference's format

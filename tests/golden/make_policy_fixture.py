@@ -22,8 +22,8 @@ for char, clip in (("humanoid3d", "spinkick"), ("dog3d", "trot")):
     print("wrote", path, os.path.getsize(path), "bytes")
 
 # Goal-conditioned AMP task policies (gated actor fc_2layers_gated_1024units; scenes target_amp / heading_amp)
-for task in ("target", "heading"):
-    a = load_actor(os.path.join(ref, "data/policies/humanoid3d_amp/humanoid3d_amp_%s_locomotion.ckpt" % task))
+for task, ckpt in (("target", "target_locomotion"), ("heading", "heading_locomotion"), ("heading_getup", "heading_getup_locomotion_getup"), ("strike", "strike_walk_punch")):
+    a = load_actor(os.path.join(ref, "data/policies/humanoid3d_amp/humanoid3d_amp_%s.ckpt" % ckpt))
     h = lambda x: np.asarray(x).astype(np.float16)
     out = dict(w0=h(a["hidden"][0][0]), b0=h(a["hidden"][0][1]), w1=h(a["hidden"][1][0]), b1=h(a["hidden"][1][1]), wm=h(a["mean"][0]), bm=h(a["mean"][1]),
                logstd=a["logstd"], gcw=h(a["gate_common"][0]), gcb=h(a["gate_common"][1]),
@@ -31,6 +31,6 @@ for task in ("target", "heading"):
     for i, g in enumerate(a["gates"]):
         for part in ("hidden", "bias", "scale"):
             out["g%d_%s_w" % (i, part)] = h(g[part][0]); out["g%d_%s_b" % (i, part)] = h(g[part][1])
-    path = os.path.join(REPO, "tests", "golden", "policy_humanoid3d_amp_%s_locomotion_fp16.npz" % task)
+    path = os.path.join(REPO, "tests", "golden", "policy_humanoid3d_amp_%s_fp16.npz" % ckpt)
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -475,7 +475,8 @@ def test_device_clip_wrap_sync_matches_the_oracle_on_the_host(asset_root, task_s
 
 def fixture_task_actor(task):
     """tests/golden/policy_humanoid3d_amp_<task>_locomotion_fp16.npz (tests/golden/make_policy_fixture.py) in load_actor's layout."""
-    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policy_humanoid3d_amp_%s_locomotion_fp16.npz" % task))
+    name = dict(target="target_locomotion", heading="heading_locomotion", heading_getup="heading_getup_locomotion_getup", strike="strike_walk_punch")[task]
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policy_humanoid3d_amp_%s_fp16.npz" % name))
     g = lambda k: f[k].astype(np.float64)
     return dict(hidden=[(g("w0"), g("b0")), (g("w1"), g("b1"))], mean=(g("wm"), g("bm")), logstd=g("logstd"), gate_common=(g("gcw"), g("gcb")),
                 gates=[dict(hidden=(g("g%d_hidden_w" % i), g("g%d_hidden_b" % i)), bias=(g("g%d_bias_w" % i), g("g%d_bias_b" % i)),
@@ -887,3 +888,43 @@ def test_device_getup_logic_matches_the_oracle_on_the_host(asset_root, task_shim
             assert bool(up) == g["getting_up"] and x[3] == pytest.approx(g["timer"], abs=1e-12), k
             began += int(g["getting_up"] and not before)
         assert (recoveries >= 2) if mode == 0 else (began >= 1)
+
+
+def test_fixture_getup_and_strike_policies_in_the_oracle_without_the_reference_tree(asset_root):
+    """Hermetic pins for the two other task scenes on the committed assets: the get-up policy (real get-up clips, shipped in the archive) stands
+    up from lying face down and then follows the heading; the strike policy, reset from the mini dataset, walks to a far target and punches it."""
+    a = fixture_task_actor("heading_getup")
+    o = Oracle(["--arg_file", "args/train_amp_heading_getup_humanoid3d_locomotion_getup_args.txt"], asset_root)
+    o.L.dmo_set_mode(o.h, 1)
+    o.set_task_stream(4, 0, 0)
+    o.reset(0.0, 0.4, 20.0, clip=2)
+    assert o.num_clips() == 4 and o.record_goal()[3] == 1.0 and o.body_state()[0][2][1] < 0.5
+    rew, head = [], []
+    for _ in range(600):
+        o.set_action(gated_actor_mode(a, o.record_state(), o.record_goal()))
+        for _ in range(20):
+            o.update(1.0 / 600.0)
+        rew.append(o.calc_reward()); head.append(o.body_state()[0][2][1])
+    assert not o.is_episode_end() or o.get_time() >= 20.0 - 1e-6
+    assert not o.has_fallen() and max(head) > 1.3 and np.mean(rew[300:]) > 0.85, (max(head), np.mean(rew[300:]))
+    a = fixture_task_actor("strike")
+    o = Oracle(MINI + ["--arg_file", "args/train_amp_strike_humanoid3d_walk_punch_args.txt"], asset_root)
+    o.L.dmo_set_mode(o.h, 1)
+    for seed in range(1, 40):                                                  # a seed whose first target is a far one
+        o.set_task_stream(seed, 0, 0)
+        o.reset(0.3, 0.0, 20.0, clip=1)
+        tp, root = o.task_state()["target_pos"], o.get_pose()[0]
+        if math.hypot(tp[0] - root[0], tp[2] - root[2]) > 3.0:
+            break
+    hit = None
+    for k in range(600):
+        if o.is_episode_end():
+            break
+        o.set_action(gated_actor_mode(a, o.record_state(), o.record_goal()))
+        for _ in range(20):
+            o.update(1.0 / 600.0)
+            if o.is_episode_end():
+                break
+        if hit is None and o.strike_state()["hit"]:
+            hit = k
+    assert hit is not None and o.check_terminate() == 2 and not o.has_fallen(), (hit, o.check_terminate())

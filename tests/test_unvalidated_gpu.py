@@ -156,10 +156,14 @@ def test_root_rotation_sync_matches_the_oracle_across_a_clip_wrap(asset_root, mo
     core.close()
 
 
-@pytest.mark.parametrize("task,args", [("target", TARGET), ("heading", HEADING)])
+GETUP_REAL = ["--arg_file", "args/train_amp_heading_getup_humanoid3d_locomotion_getup_args.txt"]      # the reference's own 4-clip get-up dataset (in the archive)
+STRIKE_REAL = MINI + ["--arg_file", "args/train_amp_strike_humanoid3d_walk_punch_args.txt"]
+
+
+@pytest.mark.parametrize("task,args", [("target", TARGET), ("heading", HEADING), ("heading_getup", GETUP_REAL), ("strike", STRIKE_REAL)])
 def test_fixture_task_policies_through_the_cuda_path(asset_root, task, args, monkeypatch):
     """The reference's pretrained task policies (fp16 fixtures) driving 64 environments for 20 s through the batched env + goal-conditioned
-    rollout: no falls to speak of, targets reached / heading followed, like in the oracle (tests/test_task_scenes_cpu.py)."""
+    rollout: targets reached / heading followed / up from the ground and walking / target punched, like in the oracle (tests/test_task_scenes_cpu.py)."""
     import torch
     from deepmimic_b200.env import DeepMimicBatchEnv
     from deepmimic_b200.rollout import BatchedRollout, build_gated_policy, load_actor_weights
@@ -169,15 +173,21 @@ def test_fixture_task_policies_through_the_cuda_path(asset_root, task, args, mon
     env = DeepMimicBatchEnv(args, num_envs=64, asset_root=asset_root, seed=9)
     env.set_mode(1)
     env.reset(True)
-    ro = BatchedRollout(env, policy=load_actor_weights(build_gated_policy(226, 3, 28), a), exp_rate=0.0)
+    G = env.get_goal_size()
+    ro = BatchedRollout(env, policy=load_actor_weights(build_gated_policy(226, G, 28), a), exp_rate=0.0)
     ro.s_norm.set_mean_std(a["s_norm_mean"], a["s_norm_std"]); ro.g_norm.set_mean_std(a["g_norm_mean"], a["g_norm_std"]); ro.a_norm.set_mean_std(a["a_norm_mean"], a["a_norm_std"])
     traj = ro.collect(600, record_stats=False)
     torch.cuda.synchronize()
     falls = int((traj["terminate"] == 1).sum())
     mean_r = float(traj["rewards"].mean())
-    assert falls <= 6, falls
     if task == "target":
         inside = (traj["goals"][:, :, 2] < 0.5).float().mean()
-        assert float(inside) > 0.08 and mean_r > 0.4, (float(inside), mean_r)
-    else:
-        assert mean_r > 0.8, mean_r
+        assert falls <= 6 and float(inside) > 0.08 and mean_r > 0.4, (falls, float(inside), mean_r)
+    elif task == "heading":
+        assert falls <= 6 and mean_r > 0.8, (falls, mean_r)
+    elif task == "heading_getup":   # test mode: a fall starts a get-up instead of ending the episode; half of the start clips lie on the ground
+        assert falls == 0 and float(traj["rewards"][300:].mean()) > 0.8, (falls, float(traj["rewards"][300:].mean()))
+        assert float(traj["goals"][0, :, 3].max()) > 0.7 and float(traj["goals"][-1, :, 3].max()) < 0.5       # get-up phase: some start near 1 (lying down), nobody is still getting up at the end
+    else:                           # strike: episodes end with the success code 2 s after the hit and restart; most environments get there at least once
+        succ = int((traj["terminate"] == 2).sum())
+        assert succ >= 32 and falls <= 16, (succ, falls)
