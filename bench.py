@@ -237,6 +237,7 @@ def main():
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "sim_updates_per_s": value * 20, "l2": "flushed between timed steps (192 MiB fill)", "updates_per_launch": upl,
                        "episodes_finished_in_timed_region": done_count, "solver_row_overflows": overflow,
+                       "e2e_host_buffers": "page-locked caller buffers, DMA'd directly by dm_step_host (pageable ones would pass through pinned staging)",
                        "collective": "nccl all_gather of [N x (%d+2)] fp32 per step" % S if world > 1 else "none (1 GPU)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "dm_step_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
