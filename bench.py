@@ -3,13 +3,14 @@
 
 One "step" = one 30 Hz policy step of every environment on this rank: set_action -> 20 x Update(1/600)
 (= 40 dynamics sub-steps) -> record_state + calc_reward + flags -> reset of finished episodes, and for N > 1 one
-NCCL all-gather of [obs | reward | done] rows.  value = policy steps of all ranks / max-over-ranks device time.
+exchange of [obs | reward | done] rows between the ranks.  value = policy steps of all ranks / max-over-ranks device time.
+Both arms run the SURVEY.md 8(d) workload: random-policy actions, 20 s episode limit, falls end episodes and reset the environment.
 
   python bench.py --gpus 1 --steps 64 --warmup 4            # this framework (CUDA path through the C ABI)
-  python bench.py --impl reference --gpus 1 --steps 3       # CPU restatement of the reference path on all host cores
+  python bench.py --impl reference --gpus 1 --steps 3       # CPU restatement of the reference path on all usable host cores
+  python bench.py --arg-file args/train_dog3d_trot_args.txt # BASELINE.json configs[3] (2048 envs, 64-dof quadruped)
 """
 import argparse
-import ctypes
 import json
 import multiprocessing as mp
 import os
@@ -24,7 +25,31 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 ALG_BYTES_PER_UPDATE = {"humanoid3d": 792, "dog3d": 1528}   # fp32 words read+written per Update(1/600) per env
-METRIC = "env-steps/sec (30 Hz policy steps; humanoid3d, 4096 envs/GPU)"
+# per policy step on top of the 20 updates: action read + observation write + reward / done
+ALG_IO_BYTES_PER_STEP = {"humanoid3d": 4 * (28 + 227 + 2), "dog3d": 4 * (58 + 347 + 2)}
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12           # 148 SMs x 128 fp32 lanes x 2 (FMA) x 1.965 GHz: CUDA-core fp32 peak of a B200
+
+
+def metric_name(char, clip, envs):
+    return "env-steps/sec (30 Hz policy steps; %s_%s, %d envs/GPU)" % (char, clip, envs)
+
+
+def usable_cores():
+    """host cores this process may use: the affinity mask capped by the cgroup cpu quota (os.cpu_count() counts the whole box and
+    oversubscribed the 1-GPU lease in round 1)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        txt = open("/sys/fs/cgroup/cpu.max").read().split()
+        if txt and txt[0] != "max":
+            n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
 
 
 def parse():
@@ -33,22 +58,26 @@ def parse():
     ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=4096)
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="default: 4096 (humanoid3d) / 2048 (dog3d), the BASELINE.json configs")
     ap.add_argument("--arg-file", default="args/train_humanoid3d_spinkick_args.txt")
+    ap.add_argument("--preroll", type=int, default=48, help="untimed policy steps before the warm-up: the timed region then sees the steady-state mix of "
+                    "stance / flight / falling characters, not 4096 freshly reset ones")
+    ap.add_argument("--episode-seconds", type=float, default=20.0, help="episode time limit of both arms (SURVEY.md 8d)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--updates-per-launch", type=int, default=20)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p"], help="N > 1: how the [obs | reward | done] rows reach the other ranks")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle = port of the reference path)
-def _oracle_worker(arg_file, root, seconds, seed, q):
+def _oracle_worker(arg_file, root, seconds, seed, max_time, q):
     from tests.oracle_binding import Oracle
     from tests.parity_util import random_policy_action
     o = Oracle(["--arg_file", arg_file], root)
     off, scl, lo, hi = o.action_statics()
     rng = np.random.default_rng(seed)
-    o.reset(float(rng.uniform(0, o.motion_duration)), 0.0, 20.0)
+    o.reset(float(rng.uniform(0, o.motion_duration)), 0.0, max_time)
     steps = 0
     t0 = time.perf_counter()
     while time.perf_counter() - t0 < seconds:
@@ -56,23 +85,24 @@ def _oracle_worker(arg_file, root, seconds, seed, q):
         for _ in range(20):
             o.update(1.0 / 600.0)
             if o.is_episode_end():
-                o.reset(float(rng.uniform(0, o.motion_duration)), 0.0, 20.0)
+                o.reset(float(rng.uniform(0, o.motion_duration)), 0.0, max_time)
                 break
         o.record_state(); o.calc_reward()
         steps += 1
     q.put((steps, time.perf_counter() - t0))
 
 
-def cpu_policy_steps_per_sec(arg_file, root, seconds, procs):
+def cpu_policy_steps_per_sec(arg_file, root, seconds, procs, max_time):
     ctx = mp.get_context("fork")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_oracle_worker, args=(arg_file, root, seconds, 100 + i, q)) for i in range(procs)]
+    ps = [ctx.Process(target=_oracle_worker, args=(arg_file, root, seconds, 100 + i, max_time, q)) for i in range(procs)]
     for p in ps:
         p.start()
     res = [q.get() for _ in ps]
     for p in ps:
         p.join()
-    return sum(s / t for s, t in res), res
+    rates = np.array([s / t for s, t in res])
+    return float(rates.sum()), rates
 
 
 class ClockSampler(threading.Thread):
@@ -101,31 +131,51 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def _profile_facts(char):
+    """ncu-derived facts about the dominant kernel (written by tools/ncu_summary.py from the round's `ncu --set full` capture of this same
+    command; static between captures -- the file names the capture it came from)"""
+    try:
+        d = json.load(open(os.path.join(REPO, "profiles", "step_metrics_%s.json" % char)))
+        return d
+    except Exception:
+        return {}
+
+
 def main():
     a = parse()
     from deepmimic_b200.assets import asset_root
     root = asset_root()
     char = "dog3d" if "dog" in a.arg_file else "humanoid3d"
-    workload = "%s / %s, %d envs/GPU, random-policy actions, 20 x Update(1/600) per step" % (os.path.basename(a.arg_file), char, a.envs_per_gpu)
+    base = os.path.basename(a.arg_file)
+    clip = base.replace("train_", "").replace("run_", "").replace("_args.txt", "").replace(char + "_", "").replace("amp_", "amp-")
+    if a.envs_per_gpu <= 0:
+        a.envs_per_gpu = 2048 if char == "dog3d" else 4096
+    N = a.envs_per_gpu
+    METRIC = metric_name(char, clip, N)
+    workload = "%s / %s, %d envs/GPU, random-policy actions, 20 x Update(1/600) per step, %.0f s episode limit, falls reset the environment" % (base, char, N, a.episode_seconds)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if a.impl == "reference":
         if rank != 0:
             return 0
-        cores = os.cpu_count() or 1
-        # each "step" is a bounded sample: all host cores run independent single-env episodes for a fixed wall time
+        cores = usable_cores()
+        # each "step" is a bounded sample: all usable host cores run independent single-env episodes for a fixed wall time
         per_step_seconds = max(0.3, min(20.0, 90.0 / max(1, a.steps + a.warmup)))   # whole run ~90 s whatever K and W are
-        vals = []
+        vals, per_proc = [], []
         for s in range(a.warmup + a.steps):
-            v, _ = cpu_policy_steps_per_sec(a.arg_file, root, per_step_seconds, cores)
+            v, rates = cpu_policy_steps_per_sec(a.arg_file, root, per_step_seconds, cores, a.episode_seconds)
             if s >= a.warmup:
-                vals.append(v)
+                vals.append(v); per_proc.append(rates)
         value = float(np.mean(vals))
+        pp = np.concatenate(per_proc)
         line = {"metric": METRIC, "value": value, "unit": "policy_steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1000.0 * per_step_seconds, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
-                "impl": "reference", "config": {"workload": workload, "note": "CPU restatement of the reference path (oracle port, not Bullet): the reference itself needs Bullet 2.88 + Eigen, absent here"},
+                "impl": "reference", "config": {"workload": workload, "note": "CPU restatement of the reference path (oracle port, not Bullet): the reference itself needs Bullet 2.88 + Eigen, absent here",
+                                                "host_cpu_count": os.cpu_count(), "usable_cores": cores,
+                                                "per_process_policy_steps_per_s": {"min": float(pp.min()), "median": float(np.median(pp)), "max": float(pp.max())}},
                 "cpu_baseline": {"value": value, "unit": "policy_steps/s", "cores": cores, "kind": "port",
-                                 "sample": "%d processes x %.1f s of single-env episodes per step (process replication = the reference's only parallelism, mpi_run.py)" % (cores, per_step_seconds)},
+                                 "sample": "%d processes (affinity / cgroup core count; the box has %d) x %.1f s of single-env episodes per step (process replication = the reference's only parallelism, mpi_run.py)"
+                                           % (cores, os.cpu_count() or 0, per_step_seconds)},
                 "e2e": {"value": value, "unit": "policy_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return 0
@@ -133,12 +183,11 @@ def main():
     import torch
     import torch.distributed as dist
     from deepmimic_b200.capi import BatchedCore
-    from deepmimic_b200.sharding import StepExchange, pack_rows
+    from deepmimic_b200.sharding import make_exchange
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    N = a.envs_per_gpu
     core = BatchedCore(["--arg_file", a.arg_file], N, root, device=local_rank, seed=1000 + rank, global_env_offset=rank * N)
     S, A = core.dims.state_size, core.dims.action_size
     stream = torch.cuda.ExternalStream(core.stream(), device=local_rank)
@@ -151,11 +200,15 @@ def main():
         lo = torch.tensor(core.static(4), dtype=torch.float32, device="cuda"); hi = torch.tensor(core.static(5), dtype=torch.float32, device="cuda")
         bank = 16
         actions = torch.clamp(-off + 0.25 / scl * torch.randn(bank, N, A, device="cuda", generator=g), lo, hi).contiguous()
-        out = torch.zeros(N, S + 2, device="cuda")           # [obs | reward | done] rows of this rank
-        obs = torch.zeros(N, S, device="cuda"); rew = torch.zeros(N, device="cuda"); flags = torch.zeros(N, 4, dtype=torch.int32, device="cuda")
-        xchg = StepExchange(world * N, S + 2, rank, world, torch.device("cuda", local_rank))
+        flags = torch.zeros(N, 4, dtype=torch.int32, device="cuda")
+        xchg = make_exchange(a.exchange, core, N, S, rank, world, torch.device("cuda", local_rank))   # owns the [obs | reward | done] rows of every rank
         flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
         done_total = torch.zeros((), dtype=torch.int64, device="cuda")
+        fell_total = torch.zeros((), dtype=torch.int64, device="cuda")
+        # episodes: fixed 20 s limit in both arms (the train args anneal 0.5 s -> 20 s over 32 M samples; the end of the schedule is the workload)
+        big = np.full(N, a.episode_seconds)
+        core.reset(True, max_time=big)
+        core.set_episode_limit(a.episode_seconds)
 
         def step(i, ev=None):
             core.set_action(actions[i % bank])
@@ -163,17 +216,20 @@ def main():
             for _ in range(20 // upl):
                 core.update(dt, upl)
             if ev: ev[1].record(stream)
-            core.observe(obs, rew); core.flags(flags)
-            xchg.gather(pack_rows(out, obs, rew, flags[:, 1]))    # N > 1: one NCCL all-gather of every rank's [obs | reward | done] rows
-            done_total.add_(flags[:, 1].sum())
+            xchg.publish(i)               # record_state + calc_reward + done; N > 1: the rows reach all ranks (P2P stores over NVLink, or one NCCL all-gather)
+            core.flags(flags)
+            done_total.add_(flags[:, 1].sum()); fell_total.add_(flags[:, 2].sum())
+            if i > 0:
+                xchg.consume(i - 1)       # the learner's side of the exchange: all ranks' rows of the previous step have arrived, slot released
             core.reset(False)
 
-        for i in range(a.warmup):
+        for i in range(a.preroll + a.warmup):
             step(i)
         stream.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        done_total.zero_(); fell_total.zero_()
         sampler = ClockSampler(local_rank); sampler.start()
         l0 = core.counters()[0]
         step_ms, upd_ms = [], []
@@ -181,43 +237,56 @@ def main():
             flush.fill_(float(i))            # L2 flush between timed iterations (outside the event pairs)
             e0, e1, ek0, ek1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
             e0.record(stream)
-            step(a.warmup + i, (ek0, ek1))
+            step(a.preroll + a.warmup + i, (ek0, ek1))
             e1.record(stream)
             step_ms.append((e0, e1)); upd_ms.append((ek0, ek1))
+        xchg.consume(a.preroll + a.warmup + a.steps - 1)
         stream.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         sampler.stop_flag = True; sampler.join(timeout=2)
-        launches = core.counters()[0] - l0
-        total_ms = sum(x.elapsed_time(y) for x, y in step_ms)
-        kern_ms = sum(x.elapsed_time(y) for x, y in upd_ms) / (a.steps * (20 // upl))
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        launches = core.counters()[0] - l0 + a.steps * xchg.launches_per_step
+        per_step = np.array([x.elapsed_time(y) for x, y in step_ms])
+        per_kern = np.array([x.elapsed_time(y) for x, y in upd_ms]) / (20 // upl)
+        total_ms = float(per_step.sum())
+        kern_ms = float(per_kern.mean())
+        t = torch.tensor([total_ms, -kern_ms, kern_ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        total_ms = float(t[0].item()); kern_min_rank, kern_max_rank = -float(t[1].item()), float(t[2].item())
         overflow = core.counters()[1]
-        done_count = int(done_total.item())
+        done_count, fell_count = int(done_total.item()), int(fell_total.item())
 
-        # ---- end-to-end through the host-buffer C-ABI call (pinned staging, H2D actions + D2H obs/reward/flags every step)
-        # host buffers are page-locked (the contract's "from pinned host memory"); the tensors own the memory, the numpy arrays are views
-        t_act = actions[0].cpu().pin_memory(); t_obs = torch.zeros(N, S, dtype=torch.float32).pin_memory()
+        # ---- end-to-end through the host-buffer C-ABI call (page-locked caller buffers, H2D actions + D2H obs/reward/flags every step)
+        nb = 4
+        t_acts = [actions[k].cpu().pin_memory() for k in range(nb)]
+        t_obs = torch.zeros(N, S, dtype=torch.float32).pin_memory()
         t_rew = torch.zeros(N, dtype=torch.float32).pin_memory(); t_fl = torch.zeros(N, 4, dtype=torch.int32).pin_memory()
-        h_act, h_obs, h_rew, h_fl = t_act.numpy(), t_obs.numpy(), t_rew.numpy(), t_fl.numpy()
-        for _ in range(2):
-            core.step_host(h_act, dt, 20, h_obs, h_rew, h_fl); core.reset(False)
+        h_acts, h_obs, h_rew, h_fl = [x.numpy() for x in t_acts], t_obs.numpy(), t_rew.numpy(), t_fl.numpy()
+        for k in range(3):
+            core.step_host(h_acts[k % nb], dt, 20, h_obs, h_rew, h_fl, reset_done=True)
         core.sync()
         ke = max(8, a.steps // 4)
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         for i in range(ke):
-            core.step_host(h_act, dt, 20, h_obs, h_rew, h_fl)
-            core.reset(False)
+            core.step_host(h_acts[i % nb], dt, 20, h_obs, h_rew, h_fl, reset_done=True)
         core.sync()
         e2e_s = time.perf_counter() - t0
         te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_value = world * N * ke / float(te.item())
+        # phase breakdown of the same call (separate short pass with the library's event hooks on; not part of the timed e2e figure)
+        core.set_timing(True)
+        br = []
+        for i in range(8):
+            core.step_host(h_acts[i % nb], dt, 20, h_obs, h_rew, h_fl, reset_done=True)
+            br.append(core.step_host_timing())
+        core.set_timing(False)
+        e2e_break = {k: float(np.median([b[k] for b in br])) for k in br[0]}
 
     value = world * N * a.steps / (total_ms / 1000.0)
     peaks = {}
@@ -226,32 +295,43 @@ def main():
     except Exception:
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
-    alg_bytes = N * upl * ALG_BYTES_PER_UPDATE[char]
+    alg_bytes = N * (upl * ALG_BYTES_PER_UPDATE[char] + ALG_IO_BYTES_PER_STEP[char] * upl // 20)
     achieved = alg_bytes / (kern_ms / 1000.0) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(REPO, "profiles", "traffic_r01.json"))).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    pf = _profile_facts(char)
+    flop_per_update = pf.get("fp32_flop_per_update_per_env")
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": pf.get("dram_bytes_per_launch"),
+            "kernel": "dm_step_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
+            "algorithmic_bytes_note": "%d envs x (%d updates x %d B + %d B action/obs/reward I/O of the policy step)" % (N, upl, ALG_BYTES_PER_UPDATE[char], ALG_IO_BYTES_PER_STEP[char] * upl // 20),
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+            "note": "latency/issue-bound path: state stays on chip for the whole launch, HBM fraction is small by construction (SURVEY 8d); the issue / fp32 figures below are the informative ones",
+            "issue_slot_pct_of_peak": pf.get("issue_slot_pct_of_peak"), "sm_active_pct": pf.get("sm_active_pct"),
+            "profile_source": pf.get("source")}
+    if flop_per_update:
+        tf = flop_per_update * N * upl / (kern_ms / 1000.0) / 1e12
+        roof.update({"fp32_flop_per_update_per_env": flop_per_update, "fp32_tflops": tf, "fp32_peak_tflops": FP32_PEAK_TFLOPS, "fp32_frac": tf / FP32_PEAK_TFLOPS,
+                     "fp32_flop_source": pf.get("flop_source")})
     line = {"metric": METRIC, "value": value, "unit": "policy_steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "sim_updates_per_s": value * 20, "l2": "flushed between timed steps (192 MiB fill)", "updates_per_launch": upl,
-                       "episodes_finished_in_timed_region": done_count, "solver_row_overflows": overflow,
-                       "e2e_host_buffers": "page-locked caller buffers, DMA'd directly by dm_step_host (pageable ones would pass through pinned staging)",
-                       "collective": "nccl all_gather of [N x (%d+2)] fp32 per step" % S if world > 1 else "none (1 GPU)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "dm_step_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                         "note": "latency/issue-bound path: state stays on chip for the whole launch, HBM fraction is small by construction (SURVEY 8d)"},
+                       "preroll_steps": a.preroll, "episode_limit_s": a.episode_seconds,
+                       "episodes_finished_in_timed_region": done_count, "of_which_falls": fell_count, "solver_row_overflows": overflow,
+                       "step_ms": {"min": float(per_step.min()), "median": float(np.median(per_step)), "max": float(per_step.max())},
+                       "kernel_ms_over_ranks": {"min": kern_min_rank, "max": kern_max_rank},
+                       "e2e_host_buffers": "page-locked caller buffers, DMA'd directly by dm_step_host (pageable ones would pass through pinned staging); %d action buffers in rotation; finished episodes reset inside the call" % nb,
+                       "e2e_breakdown_ms": e2e_break,
+                       "collective": xchg.describe() if world > 1 else "none (1 GPU)"},
+            "roofline": roof,
             "e2e": {"value": e2e_value, "unit": "policy_steps/s", "h2d_bytes_per_step": int(N * A * 4), "d2h_bytes_per_step": int(N * (S + 1 + 4) * 4)},
             "gpu_launches": int(launches), "clocks": sampler.summary()}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        v, res = cpu_policy_steps_per_sec(a.arg_file, root, a.cpu_baseline_seconds, 1)
+        v, _ = cpu_policy_steps_per_sec(a.arg_file, root, a.cpu_baseline_seconds, 1, a.episode_seconds)
         line["cpu_baseline"] = {"value": v, "unit": "policy_steps/s", "cores": 1, "kind": "port",
-                                "sample": "1 process x %.0f s of single-env episodes with the same action distribution (CPU restatement, not Bullet)" % a.cpu_baseline_seconds}
+                                "sample": "1 process x %.0f s of single-env episodes with the same action distribution and episode limit (CPU restatement, not Bullet)" % a.cpu_baseline_seconds}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
+        xchg.close()
         dist.destroy_process_group()
     return 0
 

@@ -17,8 +17,8 @@ class DmDims(C.Structure):
 
 DM_STATE_OFFSET, DM_STATE_SCALE, DM_ACTION_OFFSET, DM_ACTION_SCALE, DM_ACTION_BOUND_MIN, DM_ACTION_BOUND_MAX, DM_STATE_NORM_GROUPS = range(7)
 
-EXPORTS = ["dm_create", "dm_load_host", "dm_get_model_info", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_stream", "dm_sync", "dm_set_mode", "dm_set_sample_count", "dm_get_time_limits", "dm_reset", "dm_set_action",
-           "dm_update", "dm_record_state", "dm_record_goal", "dm_goal_host", "dm_reset_clips", "dm_record_amp_obs_expert_clips", "dm_get_clip_table", "dm_get_task_state", "dm_set_task_state", "dm_get_task_params", "dm_calc_reward", "dm_record_amp_obs_agent", "dm_record_amp_obs_expert", "dm_amp_obs_host", "dm_observe", "dm_get_flags", "dm_step_host", "dm_get_snapshot",
+EXPORTS = ["dm_create", "dm_load_host", "dm_get_model_info", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_get_scene_name", "dm_stream", "dm_sync", "dm_set_mode", "dm_set_sample_count", "dm_get_time_limits", "dm_reset", "dm_set_action",
+           "dm_update", "dm_record_state", "dm_record_goal", "dm_goal_host", "dm_reset_clips", "dm_record_amp_obs_expert_clips", "dm_get_clip_table", "dm_get_task_state", "dm_set_task_state", "dm_get_task_params", "dm_calc_reward", "dm_record_amp_obs_agent", "dm_record_amp_obs_expert", "dm_amp_obs_host", "dm_observe", "dm_get_flags", "dm_step_host", "dm_step_host_reset", "dm_set_time_limits", "dm_exchange_create", "dm_exchange_connect", "dm_exchange_publish", "dm_exchange_acquire", "dm_exchange_release", "dm_exchange_status", "dm_exchange_destroy", "dm_set_timing", "dm_step_host_timing", "dm_get_snapshot",
            "dm_set_snapshot", "dm_get_counters", "dm_debug_enable", "dm_get_debug"]
 
 
@@ -39,6 +39,7 @@ def lib():
         L.dm_last_error.restype = C.c_char_p
         L.dm_get_dims.argtypes = [vp, C.POINTER(DmDims)]
         L.dm_get_static.argtypes = [vp, C.c_int, dp]
+        L.dm_get_scene_name.argtypes = [vp, C.c_char_p, C.c_int]
         L.dm_stream.restype = vp
         L.dm_stream.argtypes = [vp]
         L.dm_sync.argtypes = [vp]
@@ -64,6 +65,17 @@ def lib():
         L.dm_observe.argtypes = [vp, fp, fp]
         L.dm_get_flags.argtypes = [vp, ip]
         L.dm_step_host.argtypes = [vp, fp, C.c_double, C.c_int, fp, fp, ip]
+        L.dm_step_host_reset.argtypes = [vp, fp, C.c_double, C.c_int, fp, fp, ip, C.c_int]
+        L.dm_set_time_limits.argtypes = [vp, C.c_double, C.c_double]
+        L.dm_exchange_create.argtypes = [vp, C.c_int, C.c_int, C.c_void_p]
+        L.dm_exchange_connect.argtypes = [vp, C.c_void_p]
+        L.dm_exchange_publish.argtypes = [vp, C.c_longlong]
+        L.dm_exchange_acquire.argtypes = [vp, C.c_longlong, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.dm_exchange_release.argtypes = [vp, C.c_longlong]
+        L.dm_exchange_status.argtypes = [vp, C.POINTER(C.c_int)]
+        L.dm_exchange_destroy.argtypes = [vp]
+        L.dm_set_timing.argtypes = [vp, C.c_int]
+        L.dm_step_host_timing.argtypes = [vp, dp]
         L.dm_get_snapshot.argtypes = [vp, C.c_int, dp]
         L.dm_set_snapshot.argtypes = [vp, C.c_int, dp]
         L.dm_get_counters.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -113,6 +125,11 @@ class BatchedCore:
         out = np.zeros(n, dtype=np.float64)
         self._chk(lib().dm_get_static(self.h, kind, _dptr(out)))
         return out
+
+    def scene_name(self):
+        buf = C.create_string_buffer(64)
+        self._chk(lib().dm_get_scene_name(self.h, buf, 64))
+        return buf.value.decode()
 
     def reset(self, force_all=True, kin_time=None, max_time=None, rot_theta=None, clip=None):
         f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
@@ -191,9 +208,47 @@ class BatchedCore:
         self._chk(lib().dm_get_time_limits(self.h, _dptr(out)))
         return out
 
-    def step_host(self, actions, dt, n_updates, state, reward, flags):  # numpy host arrays
+    def step_host(self, actions, dt, n_updates, state, reward, flags, reset_done=False):  # numpy host arrays
         p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
-        self._chk(lib().dm_step_host(self.h, p(actions), dt, n_updates, p(state), p(reward), p(flags)))
+        self._chk(lib().dm_step_host_reset(self.h, p(actions), dt, n_updates, p(state), p(reward), p(flags), 1 if reset_done else 0))
+
+    def set_episode_limit(self, seconds_min, seconds_max=None):
+        self._chk(lib().dm_set_time_limits(self.h, float(seconds_min), float(seconds_min if seconds_max is None else seconds_max)))
+
+    # ---- multi-GPU exchange over NVLink peer memory (dm_exchange_*)
+    def exchange_create(self, rank, world):
+        buf = C.create_string_buffer(64)
+        self._chk(lib().dm_exchange_create(self.h, rank, world, buf))
+        return bytes(buf.raw)
+
+    def exchange_connect(self, handles):   # world x 64 bytes, rank order
+        blob = b"".join(handles)
+        self._chk(lib().dm_exchange_connect(self.h, C.c_char_p(blob)))
+
+    def exchange_publish(self, step):
+        self._chk(lib().dm_exchange_publish(self.h, int(step)))
+
+    def exchange_acquire(self, step):
+        o, r, d = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._chk(lib().dm_exchange_acquire(self.h, int(step), C.byref(o), C.byref(r), C.byref(d)))
+        return o.value, r.value, d.value
+
+    def exchange_release(self, step):
+        self._chk(lib().dm_exchange_release(self.h, int(step)))
+
+    def exchange_status(self):
+        s = C.c_int(0)
+        self._chk(lib().dm_exchange_status(self.h, C.byref(s)))
+        return s.value
+
+    def set_timing(self, on=True):
+        self._chk(lib().dm_set_timing(self.h, 1 if on else 0))
+
+    def step_host_timing(self):
+        """last dm_step_host: dict of device ms per phase and host wall ms (enqueue / wait / staging copies)"""
+        o = np.zeros(8, dtype=np.float64)
+        self._chk(lib().dm_step_host_timing(self.h, _dptr(o)))
+        return dict(h2d_set_action_ms=o[0], update_ms=o[1], observe_flags_ms=o[2], d2h_ms=o[3], host_enqueue_ms=o[4], host_wait_ms=o[5], host_copy_ms=o[6])
 
     def get_snapshot(self, env):
         out = np.zeros(self.dims.snapshot_size, dtype=np.float64)

@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <numeric>
 #include <cstring>
+#include <ctime>
+#include <utility>
 #include <memory>
 #include <string>
 #include <vector>
@@ -22,7 +24,7 @@
 
 namespace dmk {
 template <int W, int BLOCK>
-__global__ void dm_observe_kernel(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
+__global__ void dm_observe_kernel(const DevModel*, DevState, const double*, const float*, const float*, ObsFan, int);
 template <int W, int BLOCK, bool TASKV>
 __global__ void dm_reset_kernel(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*,
                                 unsigned long long, unsigned long long, int, const int*);
@@ -41,6 +43,41 @@ __global__ void dm_flags_kernel(DevState st, int32_t* out, int num_real_envs) {
     if (e >= num_real_envs) return;
     const int* f = st.flags + static_cast<size_t>(e) * kFlagInts;
     out[e * 4 + 0] = f[kFNeedAction]; out[e * 4 + 1] = f[kFDone]; out[e * 4 + 2] = f[kFTerminate]; out[e * 4 + 3] = f[kFValid];
+}
+
+// ---- multi-GPU exchange flags (dm_exchange_*): every rank owns one block {epoch[8], ack[8], status} that its peers write through P2P.
+// epoch[r] = s + 1: rank r's rows of policy step s have arrived here; ack[r] = s + 1: rank r has finished reading the rows of step s there.
+struct XchgFlags { unsigned long long epoch[8]; unsigned long long ack[8]; unsigned int status; unsigned int pad[31]; };
+struct XchgPeers { int n; XchgFlags* f[8]; };
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// lane r publishes `value` into slot `me` of peer r's epoch (which = 0) or ack (which = 1) array.  The rows were stored by the preceding
+// kernel of this stream; the system-scope fence + release store order them before the flag for the remote acquire load.
+__global__ void dm_xchg_signal_kernel(XchgPeers P, int me, int which, unsigned long long value) {
+    const int r = threadIdx.x;
+    if (r >= P.n) return;
+    __threadfence_system();
+    st_release_sys(which == 0 ? &P.f[r]->epoch[me] : &P.f[r]->ack[me], value);
+}
+// lane r spins until this rank's own epoch[r] (which = 0) / ack[r] (which = 1) reaches `value`; gives up after `timeout_ns` and raises status
+__global__ void dm_xchg_wait_kernel(XchgFlags* mine, int n, int which, unsigned long long value, unsigned long long timeout_ns) {
+    const int r = threadIdx.x;
+    if (r >= n) return;
+    const unsigned long long* p = which == 0 ? &mine->epoch[r] : &mine->ack[r];
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(p) < value) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) { atomicOr(&mine->status, 1u << which); return; }
+        __nanosleep(200);
+    }
 }
 }  // namespace dmk
 
@@ -81,6 +118,17 @@ struct dm_handle {
     int64_t launches = 0;
     uint64_t amp_calls = 0;
     std::vector<double> st_off, st_scale, act_off, act_scale, act_min, act_max, st_groups;
+    // dm_step_host: page-locked-ness of the caller's buffers, looked up once per pointer (cudaPointerGetAttributes is a driver call)
+    std::vector<std::pair<const void*, bool>> pin_cache;
+    // dm_step_host_timing: phase events of the last dm_step_host call (created by dm_set_timing)
+    // dm_exchange_*: one allocation {XchgFlags | 2 x [obs world*N*S | rew world*N | done world*N]}, mapped into the peers through CUDA IPC
+    int x_rank = 0, x_world = 0;
+    char* x_base = nullptr;                       // this rank's allocation
+    char* x_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // every rank's allocation as seen from here ([x_rank] = x_base)
+    size_t x_data_off = 0, x_parity_bytes = 0;
+    bool timing = false;
+    cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double host_ms[3] = {0, 0, 0};   // enqueue, wait (stream synchronize), staging copies
 };
 
 namespace {
@@ -344,13 +392,20 @@ int launch_update(dm_handle* h, double dt, int n_updates) {
     return launch_step<W, DEBUG, 0>(h, dt, n_updates);
 }
 template <int W>
-int launch_observe(dm_handle* h, float* d_state, float* d_reward) {
+int launch_observe_fan(dm_handle* h, const dmk::ObsFan& fan) {
     constexpr int BLOCK = 64;
     const int grid = h->padded_envs / (BLOCK / W);
-    dmk::dm_observe_kernel<W, BLOCK><<<grid, BLOCK, 0, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, d_state, d_reward, h->num_envs);
+    const size_t smem = static_cast<size_t>(BLOCK / W) * h->hm.state_size * sizeof(float);   // the block's observation rows, staged for 16-byte stores
+    dmk::dm_observe_kernel<W, BLOCK><<<grid, BLOCK, smem, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, fan, h->num_envs);
     DM_CUDA(cudaGetLastError());
     h->launches++;
     return 0;
+}
+template <int W>
+int launch_observe(dm_handle* h, float* d_state, float* d_reward) {
+    dmk::ObsFan fan{};
+    fan.n = 1; fan.obs[0] = d_state; fan.rew[0] = d_reward; fan.done[0] = nullptr;
+    return launch_observe_fan<W>(h, fan);
 }
 template <int W>
 int launch_reset(dm_handle* h, int force, const double* kt, const double* mt, const double* th, const int* clip) {
@@ -463,11 +518,16 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
         const int per_env = h->lay.env_floats * 4;
         const int hot = h->lay.hot_floats * 4 + 1024;
         int max_tiles = std::min(dmk::kStepMaxThreads / h->W, (static_cast<int>(prop.sharedMemPerBlockOptin) - hot) / per_env);
-        if (const char* t = std::getenv("DM_TILES_PER_BLOCK")) max_tiles = std::max(1, std::min(max_tiles, std::atoi(t)));
+        if (const char* t = std::getenv("DM_TILES_PER_BLOCK")) max_tiles = std::min(max_tiles, std::max(h->W == 16 ? 2 : 1, std::atoi(t)));
+        const int min_tiles = (h->W == 16) ? 2 : 1;   // W = 16: two environments share a warp
+        if (max_tiles < min_tiles) {
+            g_err = "not enough shared memory per block for one environment tile (need " + std::to_string(hot + min_tiles * per_env) + " bytes, the device offers " +
+                    std::to_string(static_cast<long long>(prop.sharedMemPerBlockOptin)) + ")";
+            fail(); return nullptr;
+        }
         const int sms = prop.multiProcessorCount;
-        int tiles = std::min(max_tiles, std::max(1, (num_envs + sms - 1) / sms));
-        if (h->W == 16 && (tiles & 1)) tiles = std::min(max_tiles - (max_tiles & 1), tiles + 1);   // whole warps
-        if (h->W == 16 && (tiles & 1)) tiles = std::max(2, tiles - 1);
+        int tiles = std::min(max_tiles, std::max(min_tiles, (num_envs + sms - 1) / sms));
+        if (h->W == 16 && (tiles & 1)) tiles = (tiles + 1 <= max_tiles) ? tiles + 1 : tiles - 1;   // whole warps; tiles >= 2 here, so tiles - 1 >= 2 when odd
         h->tiles = tiles;
         const int quantum = (tiles * (64 / h->W)) / std::__gcd(tiles, 64 / h->W);   // multiple of both the update block and the 64-thread policy blocks
         h->padded_envs = ((num_envs + quantum - 1) / quantum) * quantum;
@@ -554,15 +614,18 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
     return h.release();
 }
 
+int dm_exchange_destroy(dm_handle* h);
 void dm_destroy(dm_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    dm_exchange_destroy(h);
     cudaFree(h->st.task); cudaFree(h->st.taskx); cudaFree(h->d_goal); cudaFreeHost(h->p_goal); cudaFree(h->st.clip); cudaFree(h->d_clip_inj); cudaFree(h->d_ctab);
     cudaFree(h->d_amp); cudaFreeHost(h->p_amp); cudaFree(h->st.hist); cudaFree(h->d_model); cudaFree(h->st.sim); cudaFree(h->st.time); cudaFree(h->st.flags); cudaFree(h->st.manifold);
     cudaFree(h->d_frame_times); cudaFree(h->d_frames); cudaFree(h->d_frame_vel); cudaFree(h->d_flags4); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew);
     for (auto& p : h->d_inj) cudaFree(p);
     cudaFreeHost(h->p_act); cudaFreeHost(h->p_obs); cudaFreeHost(h->p_rew); cudaFreeHost(h->p_flags);
+    for (auto& e : h->tev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -574,6 +637,15 @@ int dm_get_dims(dm_handle* h, dm_dims* o) {
     o->num_update_substeps = h->sa.cfg.num_update_substeps;
     o->updates_per_action = 20;
     o->motion_duration = M.motion_dur;
+    return 0;
+}
+// cScene::GetName of the configured scene (SceneImitate.cpp:209, SceneImitateAMP.cpp:211, SceneTargetAMP.cpp:233, SceneHeadingAMP.cpp:153, ...)
+int dm_get_scene_name(dm_handle* h, char* out, int cap) {
+    const std::string& sc = h->sa.cfg.scene;
+    const char* name = sc == "imitate_amp" ? "Imitate AMP" : sc == "target_amp" ? "Target AMP" : sc == "heading_amp" ? "Heading AMP" :
+                       sc == "heading_amp_getup" ? "Heading AMP Getup" : sc == "strike_amp" ? "Strike AMP" : "Imitate";
+    if (cap <= 0) { g_err = "dm_get_scene_name: empty buffer"; return fail(); }
+    std::snprintf(out, static_cast<size_t>(cap), "%s", name);
     return 0;
 }
 int dm_get_static(dm_handle* h, int kind, double* out) {
@@ -612,6 +684,18 @@ int dm_set_sample_count(dm_handle* h, long long count) {
     if (h->stream != nullptr) {   // device handle: the reset kernel reads the limits from the model blob, stream-ordered
         DM_CUDA(cudaSetDevice(h->device));
         static_assert(offsetof(dmk::DevModel, time_lim_max) == offsetof(dmk::DevModel, time_lim_min) + sizeof(double), "time limits must be adjacent");
+        DM_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h->d_model) + offsetof(dmk::DevModel, time_lim_min), &h->hm.time_lim_min, 2 * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+        DM_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+// Episode time limits set directly (both train-mode bounds): bench.py and tests that want a fixed limit without the annealing schedule.
+int dm_set_time_limits(dm_handle* h, double tmin, double tmax) {
+    if (!(tmin > 0.0) || !(tmax >= tmin)) { g_err = "dm_set_time_limits: need 0 < min <= max"; return fail(); }
+    h->hm.time_lim_min = tmin; h->hm.time_lim_max = tmax;
+    if (h->stream != nullptr) {
+        DM_CUDA(cudaSetDevice(h->device));
         DM_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h->d_model) + offsetof(dmk::DevModel, time_lim_min), &h->hm.time_lim_min, 2 * sizeof(double),
                                 cudaMemcpyHostToDevice, h->stream));
         DM_CUDA(cudaStreamSynchronize(h->stream));
@@ -807,32 +891,186 @@ int dm_get_flags(dm_handle* h, int32_t* d_flags) {
     return 0;
 }
 // true when the host pointer is page-locked (cudaMallocHost / cudaHostRegister): the copy engines can address it directly
-static bool is_pinned_host(const void* p) {
+static bool is_pinned_host(dm_handle* h, const void* p) {
+    for (const auto& e : h->pin_cache) if (e.first == p) return e.second;
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) cudaGetLastError();
+    else pinned = at.type == cudaMemoryTypeHost;
+    // a stale entry (buffer freed and the address reused with the other kind) costs performance only: cudaMemcpyAsync accepts pageable memory
+    if (h->pin_cache.size() >= 32) h->pin_cache.clear();
+    h->pin_cache.emplace_back(p, pinned);
+    return pinned;
+}
+static inline double now_ms() {
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * static_cast<double>(ts.tv_sec) + 1e-6 * static_cast<double>(ts.tv_nsec);
+}
+int dm_set_timing(dm_handle* h, int on) {
+    DM_DEVICE(h);
+    if (on && !h->tev[0]) for (auto& e : h->tev) DM_CUDA(cudaEventCreate(&e));
+    h->timing = on != 0;
+    return 0;
+}
+int dm_step_host_timing(dm_handle* h, double* o) {
+    DM_DEVICE(h);
+    if (!h->timing || !h->tev[0]) { g_err = "dm_step_host_timing: call dm_set_timing(h, 1) before the dm_step_host to be measured"; return fail(); }
+    float ms[4] = {0, 0, 0, 0};
+    for (int k = 0; k < 4; ++k) DM_CUDA(cudaEventElapsedTime(&ms[k], h->tev[k], h->tev[k + 1]));
+    for (int k = 0; k < 4; ++k) o[k] = ms[k];
+    o[4] = h->host_ms[0]; o[5] = h->host_ms[1]; o[6] = h->host_ms[2]; o[7] = 0.0;
+    return 0;
 }
 int dm_step_host(dm_handle* h, const float* h_actions, double dt, int n_updates, float* h_state, float* h_reward, int32_t* h_flags) {
+    return dm_step_host_reset(h, h_actions, dt, n_updates, h_state, h_reward, h_flags, 0);
+}
+int dm_step_host_reset(dm_handle* h, const float* h_actions, double dt, int n_updates, float* h_state, float* h_reward, int32_t* h_flags, int reset_done) {
     DM_DEVICE(h);
     const size_t N = h->num_envs, A = h->hm.action_size, S = h->hm.state_size;
     // page-locked caller buffers are used as they are; pageable ones go through the handle's pinned staging buffers (one extra host copy)
-    const bool pa = h_actions && is_pinned_host(h_actions), ps = h_state && is_pinned_host(h_state), pr = h_reward && is_pinned_host(h_reward),
-               pf = h_flags && is_pinned_host(h_flags);
+    const bool pa = h_actions && is_pinned_host(h, h_actions), ps = h_state && is_pinned_host(h, h_state), pr = h_reward && is_pinned_host(h, h_reward),
+               pf = h_flags && is_pinned_host(h, h_flags);
+    const bool tm = h->timing;
+    const double t0 = tm ? now_ms() : 0.0;
+    double t_copy = 0.0;
+    if (tm) DM_CUDA(cudaEventRecord(h->tev[0], h->stream));
     if (h_actions) {
-        if (!pa) std::memcpy(h->p_act, h_actions, N * A * sizeof(float));
+        if (!pa) { const double c0 = tm ? now_ms() : 0.0; std::memcpy(h->p_act, h_actions, N * A * sizeof(float)); if (tm) t_copy += now_ms() - c0; }
         DM_CUDA(cudaMemcpyAsync(h->d_act, pa ? h_actions : h->p_act, N * A * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         if (dm_set_action(h, h->d_act)) return 1;
     }
+    if (tm) DM_CUDA(cudaEventRecord(h->tev[1], h->stream));
     if (n_updates > 0 && dm_update(h, dt, n_updates)) return 1;
+    if (tm) DM_CUDA(cudaEventRecord(h->tev[2], h->stream));
     if (dm_observe(h, h_state ? h->d_obs : nullptr, h_reward ? h->d_rew : nullptr)) return 1;
     if (h_flags && dm_get_flags(h, h->d_flags4)) return 1;
+    if (tm) DM_CUDA(cudaEventRecord(h->tev[3], h->stream));
     if (h_state) DM_CUDA(cudaMemcpyAsync(ps ? h_state : h->p_obs, h->d_obs, N * S * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     if (h_reward) DM_CUDA(cudaMemcpyAsync(pr ? h_reward : h->p_rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     if (h_flags) DM_CUDA(cudaMemcpyAsync(pf ? h_flags : h->p_flags, h->d_flags4, N * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (tm) DM_CUDA(cudaEventRecord(h->tev[4], h->stream));
+    const double t1 = tm ? now_ms() : 0.0;
     DM_CUDA(cudaStreamSynchronize(h->stream));
+    const double t2 = tm ? now_ms() : 0.0;
     if (h_state && !ps) std::memcpy(h_state, h->p_obs, N * S * sizeof(float));
     if (h_reward && !pr) std::memcpy(h_reward, h->p_rew, N * sizeof(float));
     if (h_flags && !pf) std::memcpy(h_flags, h->p_flags, N * 4 * sizeof(int32_t));
+    if (tm) { h->host_ms[0] = t1 - t0 - t_copy; h->host_ms[1] = t2 - t1; h->host_ms[2] = t_copy + (now_ms() - t2); }
+    // the caller has the finished episodes' last state / reward / flags: restart them now, after the wait, so that the reset kernel runs
+    // under the caller's own work and the next call finds the stream idle (the reference's caller resets right after IsEpisodeEnd)
+    if (reset_done) return dm_reset(h, 0, nullptr, nullptr, nullptr);
+    return 0;
+}
+
+// ---------------------------------------------------------------- multi-GPU exchange over NVLink peer memory (include/deepmimic_b200.h)
+static size_t xchg_parity_floats(const dm_handle* h) { return static_cast<size_t>(h->x_world) * h->num_envs * (h->hm.state_size + 2); }
+static float* xchg_plane(const dm_handle* h, const char* base, int parity, int plane /*0 obs 1 rew 2 done*/) {
+    const size_t WN = static_cast<size_t>(h->x_world) * h->num_envs, S = h->hm.state_size;
+    float* p = reinterpret_cast<float*>(const_cast<char*>(base) + h->x_data_off + static_cast<size_t>(parity) * h->x_parity_bytes);
+    return plane == 0 ? p : (plane == 1 ? p + WN * S : p + WN * S + WN);
+}
+int dm_exchange_create(dm_handle* h, int rank, int world, void* h_ipc_out64) {
+    DM_DEVICE(h);
+    if (h->x_base) { g_err = "dm_exchange_create: the handle already has an exchange"; return fail(); }
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) { g_err = "dm_exchange_create: world must be 1..8 (one node) and 0 <= rank < world"; return fail(); }
+    h->x_rank = rank; h->x_world = world;
+    h->x_data_off = 1024;
+    h->x_parity_bytes = ((xchg_parity_floats(h) * sizeof(float) + 255) / 256) * 256;
+    const size_t bytes = h->x_data_off + 2 * h->x_parity_bytes;
+    DM_CUDA(cudaMalloc(&h->x_base, bytes));
+    DM_CUDA(cudaMemset(h->x_base, 0, bytes));
+    DM_CUDA(cudaDeviceSynchronize());
+    h->x_peer[rank] = h->x_base;
+    cudaIpcMemHandle_t ipc;
+    DM_CUDA(cudaIpcGetMemHandle(&ipc, h->x_base));
+    static_assert(sizeof(ipc) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(h_ipc_out64, &ipc, 64);
+    return 0;
+}
+int dm_exchange_connect(dm_handle* h, const void* h_ipc_all) {
+    DM_DEVICE(h);
+    if (!h->x_base) { g_err = "dm_exchange_connect: call dm_exchange_create first"; return fail(); }
+    for (int r = 0; r < h->x_world; ++r) {
+        if (r == h->x_rank) continue;
+        cudaIpcMemHandle_t ipc;
+        std::memcpy(&ipc, static_cast<const char*>(h_ipc_all) + 64 * r, 64);
+        void* p = nullptr;
+        DM_CUDA(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+        h->x_peer[r] = static_cast<char*>(p);
+    }
+    return 0;
+}
+static dmk::XchgPeers xchg_peers(const dm_handle* h) {
+    dmk::XchgPeers P{};
+    P.n = h->x_world;
+    for (int r = 0; r < h->x_world; ++r) P.f[r] = reinterpret_cast<dmk::XchgFlags*>(h->x_peer[r]);
+    return P;
+}
+static const unsigned long long kXchgTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+int dm_exchange_publish(dm_handle* h, long long step) {
+    DM_DEVICE(h);
+    if (!h->x_base) { g_err = "dm_exchange_publish: no exchange (dm_exchange_create / dm_exchange_connect)"; return fail(); }
+    for (int r = 0; r < h->x_world; ++r) if (!h->x_peer[r]) { g_err = "dm_exchange_publish: peers are not connected"; return fail(); }
+    const int par = static_cast<int>(step & 1);
+    if (step >= 2 && h->x_world > 1) {   // the slot still holds step - 2: every rank must have released it
+        dmk::dm_xchg_wait_kernel<<<1, 32, 0, h->stream>>>(reinterpret_cast<dmk::XchgFlags*>(h->x_base), h->x_world, 1, static_cast<unsigned long long>(step - 1), kXchgTimeoutNs);
+        DM_CUDA(cudaGetLastError()); h->launches++;
+    }
+    dmk::ObsFan fan{};
+    fan.n = h->x_world;
+    const size_t N = h->num_envs, S = h->hm.state_size;
+    int d = 0;
+    for (int k = 0; k < h->x_world; ++k) {   // destination 0 = local, then the peers starting after this rank (spreads the first stores over the links)
+        const int r = (h->x_rank + k) % h->x_world;
+        fan.obs[d] = xchg_plane(h, h->x_peer[r], par, 0) + h->x_rank * N * S;
+        fan.rew[d] = xchg_plane(h, h->x_peer[r], par, 1) + h->x_rank * N;
+        fan.done[d] = xchg_plane(h, h->x_peer[r], par, 2) + h->x_rank * N;
+        ++d;
+    }
+    if (h->hm.task_kind != dmk::kTaskNone) { g_err = "dm_exchange_publish: the AMP task scenes are not wired to the exchange"; return fail(); }
+    if (h->W == 16 ? launch_observe_fan<16>(h, fan) : launch_observe_fan<32>(h, fan)) return 1;
+    dmk::dm_xchg_signal_kernel<<<1, 32, 0, h->stream>>>(xchg_peers(h), h->x_rank, 0, static_cast<unsigned long long>(step + 1));
+    DM_CUDA(cudaGetLastError()); h->launches++;
+    return 0;
+}
+int dm_exchange_acquire(dm_handle* h, long long step, float** d_obs, float** d_rew, float** d_done) {
+    DM_DEVICE(h);
+    if (!h->x_base) { g_err = "dm_exchange_acquire: no exchange"; return fail(); }
+    if (h->x_world > 1) {
+        dmk::dm_xchg_wait_kernel<<<1, 32, 0, h->stream>>>(reinterpret_cast<dmk::XchgFlags*>(h->x_base), h->x_world, 0, static_cast<unsigned long long>(step + 1), kXchgTimeoutNs);
+        DM_CUDA(cudaGetLastError()); h->launches++;
+    }
+    const int par = static_cast<int>(step & 1);
+    if (d_obs) *d_obs = xchg_plane(h, h->x_base, par, 0);
+    if (d_rew) *d_rew = xchg_plane(h, h->x_base, par, 1);
+    if (d_done) *d_done = xchg_plane(h, h->x_base, par, 2);
+    return 0;
+}
+int dm_exchange_release(dm_handle* h, long long step) {
+    DM_DEVICE(h);
+    if (!h->x_base) { g_err = "dm_exchange_release: no exchange"; return fail(); }
+    if (h->x_world > 1) {
+        dmk::dm_xchg_signal_kernel<<<1, 32, 0, h->stream>>>(xchg_peers(h), h->x_rank, 1, static_cast<unsigned long long>(step + 1));
+        DM_CUDA(cudaGetLastError()); h->launches++;
+    }
+    return 0;
+}
+int dm_exchange_status(dm_handle* h, int* status) {
+    DM_DEVICE(h);
+    if (!h->x_base) { g_err = "dm_exchange_status: no exchange"; return fail(); }
+    DM_CUDA(cudaStreamSynchronize(h->stream));
+    unsigned int s = 0;
+    DM_CUDA(cudaMemcpy(&s, h->x_base + offsetof(dmk::XchgFlags, status), sizeof(s), cudaMemcpyDeviceToHost));
+    *status = static_cast<int>(s);
+    return 0;
+}
+int dm_exchange_destroy(dm_handle* h) {
+    if (!h->x_base) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < h->x_world; ++r) if (r != h->x_rank && h->x_peer[r]) { cudaIpcCloseMemHandle(h->x_peer[r]); }
+    for (auto& p : h->x_peer) p = nullptr;
+    cudaFree(h->x_base); h->x_base = nullptr; h->x_world = 0;
     return 0;
 }
 

@@ -67,7 +67,7 @@ public:
         mFresh = false;
     }
     virtual double GetTime() const { return mTime; }
-    virtual std::string GetName() const { return "Imitate"; }
+    virtual std::string GetName() const { char b[64] = "Imitate"; if (mHandle) dm_get_scene_name(mHandle, b, 64); return b; }
     virtual bool EnableDraw() const { return mEnableDraw; }
 
     virtual void Draw() {}

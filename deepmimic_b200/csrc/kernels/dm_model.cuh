@@ -139,6 +139,16 @@ struct DevState {
     int num_envs;
 };
 
+// Output destinations of dm_observe_kernel: [0] is local, [1..n) the same slots of the peers' exchange buffers (NVLink P2P stores).
+// obs: [num_envs x state_size], rew / done: [num_envs] floats; rew[0] / done[0] null = not wanted.
+constexpr int kMaxFan = 8;
+struct ObsFan {
+    int n;
+    float* obs[kMaxFan];
+    float* rew[kMaxFan];
+    float* done[kMaxFan];
+};
+
 // shared-memory layout of dm_step_kernel (float offsets inside one environment's block), filled by dm_step_layout on the host and
 // passed by value as a kernel parameter (constant bank)
 struct StepLayout {

@@ -167,11 +167,16 @@ template <> struct ClipPick<true> { static __device__ __forceinline__ const Clip
 }  // namespace
 
 // obs: [N x state_size] floats, reward: [N] floats.  Either pointer may be null.
+// Outputs go to `fan.n` destinations with identical layout (ObsFan, dm_model.cuh): destination 0 is this GPU's buffer, the others are the
+// same slots of the peers' exchange buffers, mapped through CUDA IPC -- the observation rows are staged in shared memory and leave the SM as
+// 16-byte stores, so the multi-GPU "all-gather" of the policy step is the store phase of this kernel (NVLink P2P writes), not a collective.
 template <int W, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) dm_observe_kernel(const DevModel* __restrict__ gm, DevState st, const double* __restrict__ frame_times,
                                                             const float* __restrict__ frames, const float* __restrict__ frame_vel,
-                                                            float* __restrict__ obs, float* __restrict__ reward, int num_real_envs) {
+                                                            ObsFan fan, int num_real_envs) {
     using T = TileP<W>;
+    extern __shared__ __align__(16) float srow[];   // [tiles x state_size] observation rows of this block
+    const bool want_obs = fan.obs[0] != nullptr, want_reward = fan.rew[0] != nullptr;
     const int tiles = BLOCK / W, tile = threadIdx.x / W, lane = threadIdx.x % W;
     const int env = blockIdx.x * tiles + tile;
     const DevModel& M = *gm;
@@ -228,8 +233,8 @@ __global__ void __launch_bounds__(BLOCK) dm_observe_kernel(const DevModel* __res
     float sh, ch; sincosf(-heading, &sh, &ch);
     auto rotH = [&](V3 v) { return mk3(ch * v.x + sh * v.z, v.y, -sh * v.x + ch * v.z); };   // rotation about y by -heading
 
-    if (obs != nullptr && env < num_real_envs && act) {
-        float* o = obs + static_cast<size_t>(env) * M.state_size;
+    if (want_obs && env < num_real_envs && act) {
+        float* o = srow + tile * M.state_size;
         const int ph = M.phase_input ? 1 : 0;
         if (lane == 0) {
             if (ph) { double p = fmod(tm[kTCtrl] / M.cycle_period, 1.0); o[0] = static_cast<float>(p < 0 ? 1 + p : p); }
@@ -246,7 +251,32 @@ __global__ void __launch_bounds__(BLOCK) dm_observe_kernel(const DevModel* __res
         float* ov = o + ph + 1 + 9 * nl + 6 * lane;
         ov[0] = lv_.x; ov[1] = lv_.y; ov[2] = lv_.z; ov[3] = av_.x; ov[4] = av_.y; ov[5] = av_.z;
     }
-    if (reward == nullptr) return;
+    if (want_obs) {
+        // flush the block's rows (consecutive environments = one contiguous range of every destination): scalar head up to the first
+        // 16-byte boundary, float4 body, scalar tail; every value is read once from shared memory and stored to all destinations
+        __syncthreads();
+        const int S = M.state_size;
+        const int nreal = min(tiles, num_real_envs - static_cast<int>(blockIdx.x) * tiles);
+        const size_t base = static_cast<size_t>(blockIdx.x) * tiles * S;
+        const int total = nreal > 0 ? nreal * S : 0;
+        const int head = min(total, static_cast<int>((4 - (base & 3)) & 3));
+        const int nvec = (total - head) >> 2;
+        for (int i = threadIdx.x; i < nvec; i += BLOCK) {
+            const float* q = srow + head + 4 * i;
+            const float4 v = make_float4(q[0], q[1], q[2], q[3]);
+            for (int d = 0; d < fan.n; ++d) reinterpret_cast<float4*>(fan.obs[d] + base + head)[i] = v;
+        }
+        for (int i = threadIdx.x; i < total; i += BLOCK) {
+            if (i >= head && i < head + 4 * nvec) continue;
+            const float v = srow[i];
+            for (int d = 0; d < fan.n; ++d) fan.obs[d][base + i] = v;
+        }
+    }
+    if (fan.done[0] != nullptr && lane == 0 && env < num_real_envs) {
+        const float dn = fl[kFDone] ? 1.f : 0.f;
+        for (int d = 0; d < fan.n; ++d) fan.done[d][env] = dn;
+    }
+    if (!want_reward) return;
 
     // ---- mocap frame at kin_time
     int idx, cyc; double bld;
@@ -342,7 +372,7 @@ __global__ void __launch_bounds__(BLOCK) dm_observe_kernel(const DevModel* __res
         float rwd = 0.5f * expf(-pose_scale * pose_err) + 0.05f * expf(-vel_scale * vel_err) + 0.15f * expf(-10.f * end_eff_err) +
                     0.2f * expf(-5.f * root_err) + 0.1f * expf(-10.f * com_err);
         if (fl[kFFallen]) rwd = 0.f;
-        reward[env] = rwd;
+        for (int d = 0; d < fan.n; ++d) fan.rew[d][env] = rwd;
     }
 }
 
@@ -721,8 +751,8 @@ __global__ void dm_task_observe_kernel(const DevModel* __restrict__ gm, DevState
     }
 }
 
-template __global__ void dm_observe_kernel<16, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
-template __global__ void dm_observe_kernel<32, 64>(const DevModel*, DevState, const double*, const float*, const float*, float*, float*, int);
+template __global__ void dm_observe_kernel<16, 64>(const DevModel*, DevState, const double*, const float*, const float*, ObsFan, int);
+template __global__ void dm_observe_kernel<32, 64>(const DevModel*, DevState, const double*, const float*, const float*, ObsFan, int);
 template __global__ void dm_amp_obs_kernel<16, 64, false>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int, const int*);
 template __global__ void dm_amp_obs_kernel<32, 64, false>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int, const int*);
 template __global__ void dm_amp_obs_kernel<16, 64, true>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int, const int*);

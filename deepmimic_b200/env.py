@@ -50,7 +50,8 @@ class DeepMimicBatchEnv:
         return self._time
 
     def get_name(self):
-        return "Imitate"
+        """cScene::GetName of the configured scene (SceneImitate.cpp:209, SceneImitateAMP.cpp:211, SceneTargetAMP.cpp:233, ...)"""
+        return self._core.scene_name()
 
     def is_rl_scene(self):
         return True
@@ -129,18 +130,23 @@ class DeepMimicBatchEnv:
     def get_amp_obs_norm_group(self):
         return np.zeros(self.get_amp_obs_size(), dtype=np.int32)
 
-    def _amp_buf(self):
-        if not hasattr(self, "_amp"):
-            self._amp = self.torch.zeros(self.num_envs, self.get_amp_obs_size(), device=self.device)
-        return self._amp
+    def _amp_buf(self, which):
+        # two buffers: the AMP agent fetches the agent's and the expert's observations of a step and stores both (R/learning/amp_agent.py:244-285)
+        name = "_amp_" + which
+        if not hasattr(self, name):
+            with self.torch.cuda.stream(self.stream):
+                setattr(self, name, self.torch.zeros(self.num_envs, self.get_amp_obs_size(), device=self.device))
+        return getattr(self, name)
 
     def record_amp_obs_agent(self, agent_id=0):
-        self._pre(); self._core.amp_obs_agent(self._amp_buf()); self._post()
-        return self._amp
+        buf = self._amp_buf("agent")
+        self._pre(); self._core.amp_obs_agent(buf); self._post()
+        return buf
 
     def record_amp_obs_expert(self, agent_id=0, kin_time=None):
-        self._pre(); self._core.amp_obs_expert(self._amp_buf(), kin_time); self._post()
-        return self._amp
+        buf = self._amp_buf("expert")
+        self._pre(); self._core.amp_obs_expert(buf, kin_time); self._post()
+        return buf
 
     def is_episode_end(self):
         return self._refresh_flags()[:, 1].bool()
@@ -237,10 +243,28 @@ class DeepMimicBatchEnv:
     def sync(self):
         self._core.sync()
 
+    def counters(self):
+        """(kernel launches so far, environments whose constraint solver ran out of row capacity).  The second number must stay 0: a
+        truncated contact set is a silent deviation from the reference physics."""
+        return self._core.counters()
+
+    def check_solver_capacity(self, raise_on_overflow=True):
+        """Call at reset / collect boundaries (host synchronisation).  Raises (or warns) when any environment exceeded the solver's row
+        capacity since the handle was created: raise DM_MAX_ROWS or treat the affected episodes as invalid."""
+        over = self._core.counters()[1]
+        if over:
+            msg = "deepmimic_b200: %d environment(s) exceeded the contact-solver row capacity; contacts were truncated (set DM_MAX_ROWS higher)" % over
+            if raise_on_overflow:
+                raise RuntimeError(msg)
+            import warnings
+            warnings.warn(msg)
+        return over
+
 
 class ShardedDeepMimicEnv(DeepMimicBatchEnv):
-    """One process per GPU: this rank owns shard_range(total_envs, rank, world) of the job's environments; `step`
-    additionally all-gathers every rank's [obs | reward | done] rows (NCCL) so each rank returns the whole job's."""
+    """One process per GPU: this rank owns shard_range(total_envs, rank, world) of the job's environments.  `step` keeps the base
+    class's contract (the LOCAL rows: obs, reward, done, terminate -- what a replicated policy acts on); `step_gathered` additionally
+    all-gathers every rank's [obs | reward | done] rows so that each rank (the learner) sees the whole job's transitions."""
 
     def __init__(self, args, total_envs, asset_root, seed=0):
         rank, world, local_rank = rank_world()
@@ -252,8 +276,13 @@ class ShardedDeepMimicEnv(DeepMimicBatchEnv):
             self._rows = self.torch.zeros(cnt, S + 2, device=self.device)
             self._xchg = StepExchange(total_envs, S + 2, rank, world, self.device)
 
-    def step(self, actions, timestep=1.0 / 600.0):
-        obs, rew, done, _ = super().step(actions, timestep)
+    def gather_rows(self, obs, rew, done):
+        """local [cnt, .] rows -> the job's [total_envs, .] rows in global environment order (same on every rank)"""
         allrows = self._xchg.gather(pack_rows(self._rows, obs, rew, done))    # on the caller's stream, after _post()
         S = self.get_state_size()
         return allrows[:, :S], allrows[:, S], allrows[:, S + 1] > 0.5
+
+    def step_gathered(self, actions, timestep=1.0 / 600.0):
+        """step() for this rank's environments, then the all-gather: returns (local 4-tuple, (all_obs, all_reward, all_done))."""
+        local = self.step(actions, timestep)
+        return local, self.gather_rows(local[0], local[1], local[2])

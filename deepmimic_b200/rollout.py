@@ -8,8 +8,9 @@ N environments of a rank at once with observations, actions and rewards staying 
   BatchedRollout     record_state -> normalise -> actor -> un-normalise -> set_action -> 20 x update -> reward / flags -> masked reset,
                      collecting [T, N, .] trajectory tensors for a learner
 
-The MLP runs as plain torch matmuls (cuBLAS): a library GEMM, not part of the hand-written hot path.  Loading the reference's TF1
-checkpoints is not implemented (weights are random-initialised the way the reference initialises them)."""
+The MLP runs as plain torch matmuls (cuBLAS): a library GEMM, not part of the hand-written hot path.  The reference's TF1 checkpoints
+are read by deepmimic_b200/tf_checkpoint.py (TensorBundle reader, no TensorFlow) and loaded with load_actor_weights; without a
+checkpoint the weights are random-initialised the way the reference initialises them."""
 import math
 
 import numpy as np

@@ -65,3 +65,131 @@ class StepExchange:
         for r in range(self.world):
             self.out[self.offsets[r]: self.offsets[r] + self.counts[r]] = self.buf[r * self.maxc: r * self.maxc + self.counts[r]]
         return self.out
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Exchange of the policy step's rows between the ranks of one node.  Layout on every rank (planes, so that the local observe kernel
+# writes its rows in place and no packing copy is needed):  obs [world, N, S] | reward [world, N] | done [world, N]  (fp32).
+class _DevMem:
+    """raw device memory owned by the C library, exposed to torch through __cuda_array_interface__ (no copy)"""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+class LocalRows:
+    """world == 1: the rows stay where dm_observe writes them."""
+    launches_per_step = 0
+
+    def __init__(self, core, N, S, device):
+        import torch
+        self.core = core
+        self.obs = torch.zeros(1, N, S, device=device); self.rew = torch.zeros(1, N, device=device); self.done = torch.zeros(1, N, device=device)
+        self.flags = torch.zeros(N, 4, dtype=torch.int32, device=device)
+
+    def publish(self, step):
+        self.core.observe(self.obs[0], self.rew[0]); self.core.flags(self.flags)
+        self.done[0].copy_(self.flags[:, 1])
+
+    def rows(self, step):
+        return self.obs, self.rew, self.done
+
+    def consume(self, step):
+        pass
+
+    def describe(self):
+        return "none (1 GPU)"
+
+    def close(self):
+        pass
+
+
+class NcclRows:
+    """One in-place NCCL all-gather per step of the rank's contiguous chunk [N*S obs | N reward | N done]; blocking per step (every rank
+    waits for the slowest one).  Kept as the portable path and as the A/B for P2PRows; CPU tests drive it with gloo."""
+    launches_per_step = 1
+
+    def __init__(self, core, N, S, rank, world, device):
+        import torch
+        self.torch, self.core, self.N, self.S, self.rank, self.world = torch, core, N, S, rank, world
+        self.chunk = N * (S + 2)
+        self.buf = torch.zeros(world, self.chunk, device=device)
+        self.flags = torch.zeros(N, 4, dtype=torch.int32, device=device)
+        mine = self.buf[rank]
+        self.l_obs = mine[: N * S].view(N, S); self.l_rew = mine[N * S: N * S + N]; self.l_done = mine[N * S + N:]
+
+    def publish(self, step):
+        import torch.distributed as dist
+        self.core.observe(self.l_obs, self.l_rew); self.core.flags(self.flags)
+        self.l_done.copy_(self.flags[:, 1])
+        dist.all_gather_into_tensor(self.buf.view(-1), self.buf[self.rank])   # in place: the input is this rank's slice of the output
+
+    def rows(self, step):
+        N, S = self.N, self.S
+        b = self.buf
+        return b[:, : N * S].view(self.world, N, S), b[:, N * S: N * S + N], b[:, N * S + N:]
+
+    def consume(self, step):
+        pass
+
+    def describe(self):
+        return "nccl all_gather (in place) of [N x (%d+2)] fp32 per rank and step; a per-step barrier" % self.S
+
+    def close(self):
+        pass
+
+
+class P2PRows:
+    """No collective: dm_observe_kernel stores this rank's rows into every peer's buffer over NVLink (CUDA IPC peer memory) and raises a
+    per-rank epoch flag; rows are consumed one step late, two buffers by step parity (include/deepmimic_b200.h, dm_exchange_*)."""
+    launches_per_step = 0   # the launches are the library's own and are counted by dm_get_counters
+
+    def __init__(self, core, N, S, rank, world, device):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.core, self.N, self.S, self.rank, self.world, self.device = torch, core, N, S, rank, world, device
+        mine = core.exchange_create(rank, world)
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, mine)
+        else:
+            handles[0] = mine
+        core.exchange_connect(handles)
+        if world > 1:
+            dist.barrier()
+        self._views = {}
+
+    def publish(self, step):
+        self.core.exchange_publish(step)
+
+    def rows(self, step):
+        """stream-orders the arrival of every rank's rows of `step` and returns (obs [world, N, S], reward [world, N], done [world, N])"""
+        o, r, d = self.core.exchange_acquire(step)
+        key = step & 1
+        if key not in self._views:
+            t = self.torch
+            self._views[key] = (t.as_tensor(_DevMem(o, (self.world, self.N, self.S)), device=self.device),
+                                t.as_tensor(_DevMem(r, (self.world, self.N)), device=self.device),
+                                t.as_tensor(_DevMem(d, (self.world, self.N)), device=self.device))
+        return self._views[key]
+
+    def consume(self, step):
+        self.core.exchange_acquire(step)
+        self.core.exchange_release(step)
+
+    def describe(self):
+        return ("no collective: dm_observe_kernel stores the rank's [N x %d] obs + reward + done rows into all %d ranks' buffers (NVLink P2P stores, CUDA IPC), "
+                "epoch flag per rank, consumed one step late (2 steps of slack between ranks)" % (self.S, self.world))
+
+    def close(self):
+        st = self.core.exchange_status()
+        if st:
+            raise RuntimeError("exchange wait timed out (status %d): a peer rank stopped publishing" % st)
+
+
+def make_exchange(kind, core, N, S, rank, world, device):
+    if world == 1 and kind in ("auto", "nccl"):
+        return LocalRows(core, N, S, device)
+    if kind == "nccl":
+        return NcclRows(core, N, S, rank, world, device)
+    return P2PRows(core, N, S, rank, world, device)

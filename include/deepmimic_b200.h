@@ -69,6 +69,7 @@ int dm_get_model_info(dm_handle* h, int kind, int* out);
 void dm_destroy(dm_handle* h);
 const char* dm_last_error(void);
 int dm_get_dims(dm_handle* h, dm_dims* out);
+int dm_get_scene_name(dm_handle* h, char* h_out, int capacity);   /* cDeepMimicCore::GetName (DeepMimicCore.cpp:141-150): "Imitate", "Imitate AMP", "Target AMP", ... */
 int dm_get_static(dm_handle* h, int kind, double* h_out);   /* h_out: state_size or action_size doubles (norm groups as doubles) */
 void* dm_stream(dm_handle* h);                               /* cudaStream_t */
 int dm_sync(dm_handle* h);
@@ -77,6 +78,7 @@ int dm_set_mode(dm_handle* h, int mode);                     /* 0 train, 1 test 
  * (--time_end_lim_min/max) with clamp(count / --anneal_samples, 0, 1)^4 (cRLSceneSimChar::UpdateTimerParams, RLSceneSimChar.cpp:330-347).
  * No-op without --anneal_samples.  Host logic: also valid on dm_load_host handles. */
 int dm_set_sample_count(dm_handle* h, long long count);
+int dm_set_time_limits(dm_handle* h, double t_min, double t_max);   /* both train-mode bounds directly, bypassing the annealing (measurement / tests) */
 int dm_get_time_limits(dm_handle* h, double* h_out3);        /* current train-mode min, max and the test-mode limit (seconds) */
 
 /* Resets the envs whose done flag is set (force_all = 0) or every env (force_all != 0).  Optional host arrays
@@ -119,6 +121,34 @@ int dm_get_flags(dm_handle* h, int32_t* d_flags);
 /* ---- host-buffer convenience wrappers (the reference-facing plugin path: host in, host out, copies inside).  Page-locked caller buffers
  * (cudaMallocHost / cudaHostRegister) are DMA'd directly; pageable ones pass through the handle's pinned staging buffers. */
 int dm_step_host(dm_handle* h, const float* h_actions, double dt, int n_updates, float* h_state, float* h_reward, int32_t* h_flags);
+/* Same, and with reset_done != 0 the episodes that ended in this step are restarted (masked dm_reset) after the results have been
+ * delivered -- the batched form of the reference caller's "if IsEpisodeEnd(): Reset()" (R/learning/rl_world.py:94-132). */
+int dm_step_host_reset(dm_handle* h, const float* h_actions, double dt, int n_updates, float* h_state, float* h_reward, int32_t* h_flags, int reset_done);
+/* Measurement hook (bench.py's e2e breakdown): with timing on, every dm_step_host records CUDA events between its phases;
+ * dm_step_host_timing returns the last call's {H2D + set_action, update launches, observe + flags, D2H} device ms, then the host's
+ * {enqueue, stream-synchronize wait, staging memcpy} wall ms, one spare: 8 doubles. */
+int dm_set_timing(dm_handle* h, int on);
+int dm_step_host_timing(dm_handle* h, double* h_out8);
+
+/* ---- multi-GPU exchange of the policy step's rows (the reference has no multi-GPU path; north_star asks for the step's
+ * observations / rewards of all ranks on every rank).  One process per GPU on ONE node, <= 8 ranks.  No collective kernel: every rank's
+ * dm_observe_kernel stores its [obs | reward | done] rows straight into the same slots of every peer's buffer (CUDA IPC mapped, NVLink P2P
+ * stores from the producing kernel), then raises a per-rank epoch flag in every peer; a consumer waits (on the handle's stream) only when it
+ * reads.  Two buffers by step parity: rows of step s may be overwritten by step s + 2 only after every rank released step s, which gives the
+ * ranks two steps of slack against each other instead of a barrier per step.
+ *   create : allocates the local buffer, returns its 64-byte cudaIpcMemHandle_t; exchange the handles of all ranks (e.g. all_gather_object)
+ *   connect: maps the peers (h_ipc_all = world x 64 bytes, own slot ignored)
+ *   publish(step): record_state + calc_reward + done of this rank for `step`, stored into every rank's buffer; needs release(step - 2) of all
+ *   acquire(step): stream-orders the arrival of every rank's rows of `step`; returns device pointers to [world x N x state], [world x N], [world x N]
+ *   release(step): the rows of `step` may be overwritten
+ *   status : bit 0 / 1 set if a wait for rows / for a release gave up after 20 s (a peer died) */
+int dm_exchange_create(dm_handle* h, int rank, int world, void* h_ipc_out64);
+int dm_exchange_connect(dm_handle* h, const void* h_ipc_all);
+int dm_exchange_publish(dm_handle* h, long long step);
+int dm_exchange_acquire(dm_handle* h, long long step, float** d_obs, float** d_reward, float** d_done);
+int dm_exchange_release(dm_handle* h, long long step);
+int dm_exchange_status(dm_handle* h, int* status);
+int dm_exchange_destroy(dm_handle* h);
 
 /* ---- test hooks: raw per-env simulator state, layout shared with the CPU oracle (doubles):
  *  [0..2] basePos(scaled) [3..6] baseQuat world->base (x,y,z,w) [7..9] baseOmega [10..12] baseVel(scaled)

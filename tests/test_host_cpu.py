@@ -207,6 +207,68 @@ def test_step_exchange_gloo_world2(total):
         assert tmax == 2.0
 
 
+class _MockCore:
+    """stands in for BatchedCore in the CPU tests of the exchange classes: observe / flags fill rows that are functions of the GLOBAL env id"""
+
+    def __init__(self, off, cnt, S):
+        self.off, self.cnt, self.S, self.step = off, cnt, S, 0
+
+    def observe(self, obs, rew):
+        import torch
+        ids = torch.arange(self.off, self.off + self.cnt, dtype=torch.float32)
+        obs.copy_(ids[:, None] * 10 + torch.arange(self.S, dtype=torch.float32)[None, :] + 1000.0 * self.step)
+        rew.copy_(ids * 0.5 + self.step)
+
+    def flags(self, out):
+        import torch
+        ids = torch.arange(self.off, self.off + self.cnt)
+        out.zero_()
+        out[:, 1] = ((ids + self.step) % 3 == 0).to(out.dtype)
+
+
+def _rows_worker(rank, world, port, N, S, q):
+    import torch
+    import torch.distributed as dist
+    from deepmimic_b200.sharding import make_exchange
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        core = _MockCore(rank * N, N, S)
+        x = make_exchange("nccl", core, N, S, rank, world, "cpu")      # NcclRows; the backend of the process group decides the transport
+        out = []
+        for step in range(3):
+            core.step = step
+            x.publish(step)
+            if step > 0:
+                x.consume(step - 1)
+            o, r, d = x.rows(step)
+            out.append((o.clone().numpy(), r.clone().numpy(), d.clone().numpy()))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rows_exchange_in_place_all_gather_gloo_world2():
+    """NcclRows (the collective variant of the policy-step exchange, bench.py --exchange nccl): planes layout, the local observe output is
+    this rank's slice of the gathered buffer, one in-place all-gather per step.  Every rank must see every rank's rows of the step."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port, world, N, S = _free_port(), 2, 5, 4
+    procs = [ctx.Process(target=_rows_worker, args=(r, world, port, N, S, q)) for r in range(world)]
+    [p.start() for p in procs]
+    got = [q.get(timeout=120) for _ in range(world)]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    ids = np.arange(world * N, dtype=np.float32)
+    for rank, out in got:
+        for step, (o, r, d) in enumerate(out):
+            assert o.shape == (world, N, S) and r.shape == (world, N) and d.shape == (world, N)
+            np.testing.assert_array_equal(o.reshape(world * N, S), ids[:, None] * 10 + np.arange(S)[None, :] + 1000.0 * step)
+            np.testing.assert_array_equal(r.reshape(-1), ids * 0.5 + step)
+            np.testing.assert_array_equal(d.reshape(-1), ((ids.astype(int) + step) % 3 == 0).astype(np.float32))
+
+
 def test_malformed_assets_are_rejected_with_messages(asset_root, tmp_path):
     """Ragged / empty / mismatching inputs: the loaders of the C-ABI library and of the oracle refuse them with the reference's messages
     (cMotion::LoadJson Motion.cpp:104-141,303-360; cKinTree::Load KinTree.cpp:204-258; cClipsController::LoadMotions ClipsController.cpp:145-188)."""
