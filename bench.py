@@ -71,10 +71,18 @@ def parse():
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle = port of the reference path)
+def scene_args(arg_file):
+    """arg list of a bench workload.  The AMP task scenes name a 56-clip, 48 MB dataset that is not in the committed asset archive: they run on
+    the authored 56-entry dataset of the same shape (tests/golden/make_assets.py) -- synthetic data, said so in the JSON line."""
+    extra = ["--motion_file", "data/datasets/synthetic_locomotion_56.txt"] if "_amp_" in arg_file else []
+    return extra + ["--arg_file", arg_file]
+
+
 def _oracle_worker(arg_file, root, seconds, seed, max_time, q):
     from tests.oracle_binding import Oracle
     from tests.parity_util import random_policy_action
-    o = Oracle(["--arg_file", arg_file], root)
+    o = Oracle(scene_args(arg_file), root)
+    amp = "_amp_" in arg_file
     off, scl, lo, hi = o.action_statics()
     rng = np.random.default_rng(seed)
     o.reset(float(rng.uniform(0, o.motion_duration)), 0.0, max_time)
@@ -88,6 +96,8 @@ def _oracle_worker(arg_file, root, seconds, seed, max_time, q):
                 o.reset(float(rng.uniform(0, o.motion_duration)), 0.0, max_time)
                 break
         o.record_state(); o.calc_reward()
+        if amp:      # config 5: goal, AMP agent observation and the imitation reward next to the task reward
+            o.record_goal(); o.record_amp_obs_agent(); o.calc_reward_imitate()
         steps += 1
     q.put((steps, time.perf_counter() - t0))
 
@@ -144,8 +154,9 @@ def _profile_facts(char):
 def main():
     a = parse()
     from deepmimic_b200.assets import asset_root
-    root = asset_root()
+    root = asset_root(prefer_archive=True)   # the committed archive: the same inputs here and on the GPU box
     char = "dog3d" if "dog" in a.arg_file else "humanoid3d"
+    amp = "_amp_" in a.arg_file
     base = os.path.basename(a.arg_file)
     clip = base.replace("train_", "").replace("run_", "").replace("_args.txt", "").replace(char + "_", "").replace("amp_", "amp-")
     if a.envs_per_gpu <= 0:
@@ -188,7 +199,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    core = BatchedCore(["--arg_file", a.arg_file], N, root, device=local_rank, seed=1000 + rank, global_env_offset=rank * N)
+    core = BatchedCore(scene_args(a.arg_file), N, root, device=local_rank, seed=1000 + rank, global_env_offset=rank * N)
     S, A = core.dims.state_size, core.dims.action_size
     stream = torch.cuda.ExternalStream(core.stream(), device=local_rank)
     dt = 1.0 / 600.0
@@ -201,6 +212,8 @@ def main():
         bank = 16
         actions = torch.clamp(-off + 0.25 / scl * torch.randn(bank, N, A, device="cuda", generator=g), lo, hi).contiguous()
         flags = torch.zeros(N, 4, dtype=torch.int32, device="cuda")
+        if amp:
+            goal_buf = torch.zeros(N, max(1, core.dims.goal_size), device="cuda"); amp_buf = torch.zeros(N, core.dims.amp_obs_size, device="cuda"); rim_buf = torch.zeros(N, device="cuda")
         xchg = make_exchange(a.exchange, core, N, S, rank, world, torch.device("cuda", local_rank))   # owns the [obs | reward | done] rows of every rank
         flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
         done_total = torch.zeros((), dtype=torch.int64, device="cuda")
@@ -218,7 +231,9 @@ def main():
             if ev: ev[1].record(stream)
             xchg.publish(i)               # record_state + calc_reward + done; N > 1: the rows reach all ranks (P2P stores over NVLink, or one NCCL all-gather)
             core.flags(flags)
-            done_total.add_(flags[:, 1].sum()); fell_total.add_(flags[:, 2].sum())
+            if amp:                       # config 5: goal + AMP agent observation + imitation reward (active clip) recorded alongside
+                core.record_goal(goal_buf); core.amp_obs_agent(amp_buf); core.reward_imitate(rim_buf)
+            done_total.add_(flags[:, 1].sum()); fell_total.add_((flags[:, 2] == 1).sum())
             if i > 0:
                 xchg.consume(i - 1)       # the learner's side of the exchange: all ranks' rows of the previous step have arrived, slot released
             core.reset(False)
@@ -295,13 +310,14 @@ def main():
     except Exception:
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
-    alg_bytes = N * (upl * ALG_BYTES_PER_UPDATE[char] + ALG_IO_BYTES_PER_STEP[char] * upl // 20)
+    io_bytes = ALG_IO_BYTES_PER_STEP[char] + (4 * (core.dims.amp_obs_size + core.dims.goal_size + 1) if amp else 0)
+    alg_bytes = N * (upl * ALG_BYTES_PER_UPDATE[char] + io_bytes * upl // 20)
     achieved = alg_bytes / (kern_ms / 1000.0) / 1e9
     pf = _profile_facts(char)
     flop_per_update = pf.get("fp32_flop_per_update_per_env")
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": pf.get("dram_bytes_per_launch"),
             "kernel": "dm_step_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
-            "algorithmic_bytes_note": "%d envs x (%d updates x %d B + %d B action/obs/reward I/O of the policy step)" % (N, upl, ALG_BYTES_PER_UPDATE[char], ALG_IO_BYTES_PER_STEP[char] * upl // 20),
+            "algorithmic_bytes_note": "%d envs x (%d updates x %d B + %d B action/obs/reward I/O of the policy step)" % (N, upl, ALG_BYTES_PER_UPDATE[char], io_bytes * upl // 20),
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
             "note": "latency/issue-bound path: state stays on chip for the whole launch, HBM fraction is small by construction (SURVEY 8d); the issue / fp32 figures below are the informative ones",
             "issue_slot_pct_of_peak": pf.get("issue_slot_pct_of_peak"), "sm_active_pct": pf.get("sm_active_pct"),
@@ -311,7 +327,8 @@ def main():
         roof.update({"fp32_flop_per_update_per_env": flop_per_update, "fp32_tflops": tf, "fp32_peak_tflops": FP32_PEAK_TFLOPS, "fp32_frac": tf / FP32_PEAK_TFLOPS,
                      "fp32_flop_source": pf.get("flop_source")})
     line = {"metric": METRIC, "value": value, "unit": "policy_steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic" + (" (56-entry clip dataset of the reference's shape over the archive's locomotion clips)" if amp else ""),
             "config": {"workload": workload, "sim_updates_per_s": value * 20, "l2": "flushed between timed steps (192 MiB fill)", "updates_per_launch": upl,
                        "preroll_steps": a.preroll, "episode_limit_s": a.episode_seconds,
                        "episodes_finished_in_timed_region": done_count, "of_which_falls": fell_count, "solver_row_overflows": overflow,

@@ -17,8 +17,8 @@ class DmDims(C.Structure):
 
 DM_STATE_OFFSET, DM_STATE_SCALE, DM_ACTION_OFFSET, DM_ACTION_SCALE, DM_ACTION_BOUND_MIN, DM_ACTION_BOUND_MAX, DM_STATE_NORM_GROUPS = range(7)
 
-EXPORTS = ["dm_create", "dm_load_host", "dm_get_model_info", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_get_scene_name", "dm_stream", "dm_sync", "dm_set_mode", "dm_set_sample_count", "dm_get_time_limits", "dm_reset", "dm_set_action",
-           "dm_update", "dm_record_state", "dm_record_goal", "dm_goal_host", "dm_reset_clips", "dm_record_amp_obs_expert_clips", "dm_get_clip_table", "dm_get_task_state", "dm_set_task_state", "dm_get_task_params", "dm_calc_reward", "dm_record_amp_obs_agent", "dm_record_amp_obs_expert", "dm_amp_obs_host", "dm_observe", "dm_get_flags", "dm_step_host", "dm_step_host_reset", "dm_set_time_limits", "dm_exchange_create", "dm_exchange_connect", "dm_exchange_publish", "dm_exchange_acquire", "dm_exchange_release", "dm_exchange_status", "dm_exchange_destroy", "dm_set_timing", "dm_step_host_timing", "dm_get_snapshot",
+EXPORTS = ["dm_create", "dm_load_host", "dm_get_model_info", "dm_get_link_table", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_get_scene_name", "dm_stream", "dm_sync", "dm_set_mode", "dm_set_sample_count", "dm_get_time_limits", "dm_reset", "dm_set_action",
+           "dm_update", "dm_record_state", "dm_record_goal", "dm_goal_host", "dm_reset_clips", "dm_record_amp_obs_expert_clips", "dm_get_clip_table", "dm_get_task_state", "dm_set_task_state", "dm_get_task_params", "dm_calc_reward", "dm_calc_reward_imitate", "dm_record_amp_obs_agent", "dm_record_amp_obs_expert", "dm_amp_obs_host", "dm_observe", "dm_get_flags", "dm_step_host", "dm_step_host_reset", "dm_set_time_limits", "dm_exchange_create", "dm_exchange_connect", "dm_exchange_publish", "dm_exchange_acquire", "dm_exchange_release", "dm_exchange_status", "dm_exchange_destroy", "dm_set_timing", "dm_step_host_timing", "dm_get_snapshot",
            "dm_set_snapshot", "dm_get_counters", "dm_debug_enable", "dm_get_debug"]
 
 
@@ -36,6 +36,7 @@ def lib():
         L.dm_load_host.restype = vp
         L.dm_load_host.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p)]
         L.dm_get_model_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
+        L.dm_get_link_table.argtypes = [vp, dp]
         L.dm_last_error.restype = C.c_char_p
         L.dm_get_dims.argtypes = [vp, C.POINTER(DmDims)]
         L.dm_get_static.argtypes = [vp, C.c_int, dp]
@@ -52,6 +53,7 @@ def lib():
         L.dm_record_state.argtypes = [vp, fp]
         L.dm_record_goal.argtypes = [vp, fp]
         L.dm_calc_reward.argtypes = [vp, fp]
+        L.dm_calc_reward_imitate.argtypes = [vp, fp]
         L.dm_goal_host.argtypes = [vp, fp]
         L.dm_reset_clips.argtypes = [vp, C.c_int, C.POINTER(C.c_int), dp, dp, dp]
         L.dm_record_amp_obs_expert_clips.argtypes = [vp, C.POINTER(C.c_int), dp, fp]
@@ -156,6 +158,9 @@ class BatchedCore:
     def observe(self, state=None, reward=None):
         self._chk(lib().dm_observe(self.h, C.c_void_p(state.data_ptr()) if state is not None else None,
                                    C.c_void_p(reward.data_ptr()) if reward is not None else None))
+
+    def reward_imitate(self, out):  # torch float32 cuda tensor [N]: CalcRewardImitate also in the task scenes (active clip of the dataset)
+        self._chk(lib().dm_calc_reward_imitate(self.h, C.c_void_p(out.data_ptr())))
 
     def record_goal(self, out):  # torch float32 cuda tensor [N, goal_size]; task scenes only
         self._chk(lib().dm_record_goal(self.h, C.c_void_p(out.data_ptr())))
@@ -325,6 +330,12 @@ class HostModel:
         if lib().dm_get_model_info(self.h, self.INFO[name], out) != 0:
             raise RuntimeError(lib().dm_last_error().decode())
         return np.array(out[:], dtype=np.int64)
+
+    def link_table(self):
+        """[num_joints, 24]: mass, inertiaB[3], inertiaD[3], dvec[3], evec[3], zrot xyzw, axis[3], half extents[3], breaking threshold"""
+        out = np.zeros((self.dims.num_joints, 24), dtype=np.float64)
+        lib().dm_get_link_table(self.h, _dptr(out))
+        return out
 
     def layout(self):
         out = (C.c_int * 6)()

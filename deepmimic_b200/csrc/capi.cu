@@ -23,7 +23,7 @@
 #include "kernels/dm_model.cuh"
 
 namespace dmk {
-template <int W, int BLOCK>
+template <int W, int BLOCK, bool CLIPS>
 __global__ void dm_observe_kernel(const DevModel*, DevState, const double*, const float*, const float*, ObsFan, int);
 template <int W, int BLOCK, bool TASKV>
 __global__ void dm_reset_kernel(const DevModel*, DevState, const double*, const float*, const float*, int, const double*, const double*, const double*,
@@ -178,11 +178,6 @@ bool build_device_model(dm_handle& H) {
     const int nl = cm.num_joints();
     if (nl > dmk::kMaxLinks) { g_err = "character has more links than lanes (32)"; return false; }
     if (cm.joints[0].type != dmh::kNone) { g_err = "only floating-base characters (root joint type 'none') are supported"; return false; }
-    if (sa.cfg.sync_char_root_rot) {
-        // device code written (dm_step_kernel<.., kVarRootRot>) but not yet run on hardware: opt-in like the task scenes
-        const char* e = std::getenv("DM_EXPERIMENTAL_ROOT_ROT_SYNC");
-        if (!(e && e[0] == '1')) { g_err = "--sync_char_root_rot true is not supported by the batched path"; return false; }
-    }
     const double sc = sa.cfg.world_scale;
     M.nl = nl; M.scale = static_cast<float>(sc);
     M.gravity[0] = static_cast<float>(sa.cfg.gravity.x * sc); M.gravity[1] = static_cast<float>(sa.cfg.gravity.y * sc); M.gravity[2] = static_cast<float>(sa.cfg.gravity.z * sc);
@@ -396,7 +391,10 @@ int launch_observe_fan(dm_handle* h, const dmk::ObsFan& fan) {
     constexpr int BLOCK = 64;
     const int grid = h->padded_envs / (BLOCK / W);
     const size_t smem = static_cast<size_t>(BLOCK / W) * h->hm.state_size * sizeof(float);   // the block's observation rows, staged for 16-byte stores
-    dmk::dm_observe_kernel<W, BLOCK><<<grid, BLOCK, smem, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, fan, h->num_envs);
+    if (h->hm.task_kind != dmk::kTaskNone)   // clip dataset: every environment's own active clip
+        dmk::dm_observe_kernel<W, BLOCK, true><<<grid, BLOCK, smem, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, fan, h->num_envs);
+    else
+        dmk::dm_observe_kernel<W, BLOCK, false><<<grid, BLOCK, smem, h->stream>>>(h->d_model, h->st, h->d_frame_times, h->d_frames, h->d_frame_vel, fan, h->num_envs);
     DM_CUDA(cudaGetLastError());
     h->launches++;
     return 0;
@@ -455,13 +453,17 @@ static bool load_host_model(dm_handle& H, const char* asset_root, int argc, cons
                 if (t["Type"].asString("") != "plane") throw std::runtime_error("Unsupported terrain type: " + t["Type"].asString("") + " (supported: plane)");
             }
         }
-        // The AMP task scenes target_amp / heading_amp have their device code written (dm_task.cuh, dm_step_kernel<.., TASK>, dm_task_*_kernel)
-        // but it has not run on hardware yet: they are accepted only with DM_EXPERIMENTAL_TASK_SCENES=1, otherwise refused like every other scene.
+        // Scenes on the accelerated path: imitate, imitate_amp, and the AMP task scenes target_amp / heading_amp (goals, task rewards, clip
+        // datasets; validated on hardware against the oracle in round 2: tests/test_task_scenes_gpu.py).  heading_amp_getup / strike_amp have
+        // their device code written and host-checked but are not validated on hardware: opt-in with DM_EXPERIMENTAL_TASK_SCENES=1.  Every other
+        // scene name is refused.
         const char* exp_env = std::getenv("DM_EXPERIMENTAL_TASK_SCENES");
         const bool experimental = exp_env != nullptr && exp_env[0] == '1';
         const bool task_scene = H.sa.cfg.is_task_scene();   // target_amp, heading_amp, heading_amp_getup, strike_amp
-        if (H.sa.cfg.scene != "imitate" && H.sa.cfg.scene != "imitate_amp" && !(task_scene && experimental))
-            throw std::runtime_error("Unsupported scene: " + H.sa.cfg.scene + " (supported: imitate, imitate_amp)");
+        const std::string& scn = H.sa.cfg.scene;
+        const bool validated = scn == "imitate" || scn == "imitate_amp" || scn == "target_amp" || scn == "heading_amp";
+        if (!validated && !(task_scene && experimental))
+            throw std::runtime_error("Unsupported scene: " + scn + " (supported: imitate, imitate_amp, target_amp, heading_amp)");
         if (H.sa.clips.size() != 1 && !task_scene)
             throw std::runtime_error("Unsupported kinematic controller: clips with more than one clip outside the AMP task scenes (supported: motion)");
         if (static_cast<int>(H.sa.clips.size()) > dmk::kMaxClips) throw std::runtime_error("clip dataset larger than the device clip table (" + std::to_string(dmk::kMaxClips) + ")");
@@ -488,6 +490,21 @@ int dm_get_model_info(dm_handle* h, int kind, int* out) {
         case DM_INFO_END_EFFECTORS: for (int j = 0; j < M.nl; ++j) out[j] = M.link[j].end_eff; break;
         case DM_INFO_LAYOUT: out[0] = M.nl; out[1] = M.n; out[2] = M.cs; out[3] = M.maxlevel; out[4] = M.num_frames; out[5] = M.loop_motion; break;
         default: g_err = "dm_get_model_info: bad kind"; return fail();
+    }
+    return 0;
+}
+
+// Per-link model constants as the kernels use them (24 doubles per link): mass, Bullet inertia[3], DeepMimic inertia[3], dvec[3], evec[3],
+// zrot (x,y,z,w), axis[3], half extents[3], breaking threshold.  Scaled units.  For the independent known-answer tests of the loader.
+int dm_get_link_table(dm_handle* h, double* out) {
+    const auto& M = h->hm;
+    for (int j = 0; j < M.nl; ++j) {
+        const dmk::DevLink& L = M.link[j];
+        double* o = out + 24 * j;
+        o[0] = L.mass;
+        for (int k = 0; k < 3; ++k) { o[1 + k] = L.inertiaB[k]; o[4 + k] = L.inertiaD[k]; o[7 + k] = L.dvec[k]; o[10 + k] = L.evec[k]; o[17 + k] = L.axis[k]; o[20 + k] = L.he[k]; }
+        for (int k = 0; k < 4; ++k) o[13 + k] = L.zrot[k];
+        o[23] = L.break_thr;
     }
     return 0;
 }
@@ -569,7 +586,7 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
               chk(cudaMallocHost(&h->p_flags, N * 4 * sizeof(int32_t)), "cudaMallocHost");
     for (int k = 0; k < 3 && ok; ++k) ok = chk(cudaMalloc(&h->d_inj[k], N * sizeof(double)), "cudaMalloc inject");
     if (!ok) { fail(); dm_destroy(h.release()); return nullptr; }
-    h->st.pdbg = nullptr; h->st.num_envs = h->padded_envs;
+    h->st.pdbg = nullptr; h->st.num_envs = h->padded_envs; h->st.num_real = h->num_envs;
     if (M.task_kind != dmk::kTaskNone) {
         if (!(chk(cudaMalloc(&h->st.task, N * dmk::kTaskDoubles * sizeof(double)), "cudaMalloc task") &&
               chk(cudaMemset(h->st.task, 0, N * dmk::kTaskDoubles * sizeof(double)), "memset task") &&
@@ -599,6 +616,14 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
          chk(cudaMemcpy(h->d_frame_vel, fvel.data(), sizeof(float) * fvel.size(), cudaMemcpyHostToDevice), "memcpy fvel") &&
          chk(cudaMemset(h->st.sim, 0, N * ss * sizeof(float)), "memset") && chk(cudaMemset(h->st.time, 0, N * dmk::kTimeDoubles * sizeof(double)), "memset") &&
          chk(cudaMemset(h->st.flags, 0, N * dmk::kFlagInts * sizeof(int)), "memset") && chk(cudaMemset(h->st.manifold, 0, N * M.nl * dmk::kManifoldFloats * sizeof(float)), "memset");
+    if (ok && h->padded_envs > h->num_envs) {
+        // padding environments (the step kernel works on whole blocks): marked done once and for all, so that every kernel skips them.  Left
+        // alive they would stand on both feet without ever receiving an action -- 26 constraint rows each, the slowest block of the launch
+        // (found with tools/section_profile.py in round 2: the last block set the kernel time).
+        std::vector<int> fl(static_cast<size_t>(h->padded_envs - h->num_envs) * dmk::kFlagInts, 0);
+        for (int e = 0; e < h->padded_envs - h->num_envs; ++e) { fl[static_cast<size_t>(e) * dmk::kFlagInts + dmk::kFDone] = 1; fl[static_cast<size_t>(e) * dmk::kFlagInts + dmk::kFValid] = 1; }
+        ok = chk(cudaMemcpy(h->st.flags + static_cast<size_t>(h->num_envs) * dmk::kFlagInts, fl.data(), fl.size() * sizeof(int), cudaMemcpyHostToDevice), "memcpy padding flags");
+    }
     if (ok) {
         // initial PD targets: identity / TargetTheta0 (cPDController::Init, PDController.cpp:99-112)
         std::vector<float> sim(N * ss, 0.f);
@@ -777,6 +802,12 @@ int dm_observe(dm_handle* h, float* d_state, float* d_reward) {
     return 0;
 }
 int dm_record_state(dm_handle* h, float* d_out) { return dm_observe(h, d_out, nullptr); }
+// cSceneImitate::CalcRewardImitate in every scene: in the AMP task scenes (where CalcReward is the task reward) against the environment's
+// active clip of the dataset -- BASELINE.json config 5 records it beside the AMP observations.
+int dm_calc_reward_imitate(dm_handle* h, float* d_out) {
+    DM_DEVICE(h);
+    return h->W == 16 ? launch_observe<16>(h, nullptr, d_out) : launch_observe<32>(h, nullptr, d_out);
+}
 int dm_record_goal(dm_handle* h, float* d_out) {
     if (h->hm.task_kind == dmk::kTaskNone) return 0;
     DM_DEVICE(h);

@@ -136,7 +136,8 @@ struct DevState {
     double* taskx; // ... and kTaskExtDoubles per env (dm_task_ext.cuh)
     int* clip;    // --kin_ctrl clips: active clip of every env, null for single-clip scenes
     const ClipTable* ctab;
-    int num_envs;
+    int num_envs;   // padded to a multiple of the step kernel's environments per block
+    int num_real;   // environments the caller asked for; [num_real, num_envs) are padding: permanently "done", never reset, never simulated
 };
 
 // Output destinations of dm_observe_kernel: [0] is local, [1..n) the same slots of the peers' exchange buffers (NVLink P2P stores).

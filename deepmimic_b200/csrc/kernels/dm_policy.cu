@@ -170,7 +170,9 @@ template <> struct ClipPick<true> { static __device__ __forceinline__ const Clip
 // Outputs go to `fan.n` destinations with identical layout (ObsFan, dm_model.cuh): destination 0 is this GPU's buffer, the others are the
 // same slots of the peers' exchange buffers, mapped through CUDA IPC -- the observation rows are staged in shared memory and leave the SM as
 // 16-byte stores, so the multi-GPU "all-gather" of the policy step is the store phase of this kernel (NVLink P2P writes), not a collective.
-template <int W, int BLOCK>
+// CLIPS (--kin_ctrl clips, AMP task scenes): the imitation reward is taken against the environment's own active clip of the dataset
+// (st.clip / st.ctab) -- BASELINE.json config 5 records it next to the AMP observations and the task reward.
+template <int W, int BLOCK, bool CLIPS>
 __global__ void __launch_bounds__(BLOCK) dm_observe_kernel(const DevModel* __restrict__ gm, DevState st, const double* __restrict__ frame_times,
                                                             const float* __restrict__ frames, const float* __restrict__ frame_vel,
                                                             ObsFan fan, int num_real_envs) {
@@ -279,20 +281,27 @@ __global__ void __launch_bounds__(BLOCK) dm_observe_kernel(const DevModel* __res
     if (!want_reward) return;
 
     // ---- mocap frame at kin_time
+    ClipModel CM;
+    if constexpr (CLIPS) {
+        const ClipInfo& ci = st.ctab->info[st.clip[env < num_real_envs ? env : 0]];
+        CM = clip_model(ci, M.pose_dim, M.query_dt);
+        frame_times += ci.frame_off; frames += static_cast<size_t>(ci.frame_off) * M.pose_dim; frame_vel += static_cast<size_t>(ci.frame_off) * M.pose_dim;
+    }
+    const auto& KM = ClipPick<CLIPS>::get(M, CM);
     int idx, cyc; double bld;
-    frame_index(M, frame_times, tm[kTKin], idx, bld, cyc);
+    frame_index(KM, frame_times, tm[kTKin], idx, bld, cyc);
     bld = fmin(fmax(bld, 0.0), 1.0);
     const float bl = static_cast<float>(bld);
     const float* f0 = frames + static_cast<size_t>(idx) * M.pose_dim; const float* f1 = f0 + M.pose_dim;
     const float* v0 = frame_vel + static_cast<size_t>(idx) * M.pose_dim; const float* v1 = v0 + M.pose_dim;
-    const bool clip_over = !M.loop_motion && tm[kTKin] >= M.motion_dur;
+    const bool clip_over = !KM.loop_motion && tm[kTKin] >= KM.motion_dur;
     KinJoint kj = sample_joint(L, f0, f1, v0, v1, bl, lane == 0);
     if (clip_over) { kj.w = mk3(0, 0, 0); kj.angvel = 0; }
     const Q4 orot = mkq(static_cast<float>(tm[kTOriginRot + 1]), static_cast<float>(tm[kTOriginRot + 2]), static_cast<float>(tm[kTOriginRot + 3]), static_cast<float>(tm[kTOriginRot]));
     const V3 org = mk3(static_cast<float>(tm[kTOrigin]), static_cast<float>(tm[kTOrigin + 1]), static_cast<float>(tm[kTOrigin + 2]));
     // kinematic root in the world
-    V3 kroot = mk3((1 - bl) * f0[0] + bl * f1[0] + (M.loop_motion ? cyc * M.cycle_delta[0] : 0.f), (1 - bl) * f0[1] + bl * f1[1],
-                   (1 - bl) * f0[2] + bl * f1[2] + (M.loop_motion ? cyc * M.cycle_delta[2] : 0.f));
+    V3 kroot = mk3((1 - bl) * f0[0] + bl * f1[0] + (KM.loop_motion ? cyc * KM.cycle_delta[0] : 0.f), (1 - bl) * f0[1] + bl * f1[1],
+                   (1 - bl) * f0[2] + bl * f1[2] + (KM.loop_motion ? cyc * KM.cycle_delta[2] : 0.f));
     kroot = qrot(orot, kroot) + org;
     V3 kroot_v = mk3((1 - bl) * v0[0] + bl * v1[0], (1 - bl) * v0[1] + bl * v1[1], (1 - bl) * v0[2] + bl * v1[2]);
     if (clip_over) kroot_v = mk3(0, 0, 0);
@@ -532,7 +541,7 @@ __global__ void __launch_bounds__(BLOCK) dm_reset_kernel(const DevModel* __restr
     float* sim = st.sim + static_cast<size_t>(env) * ss;
     double* tm = st.time + static_cast<size_t>(env) * kTimeDoubles;
     int* fl = st.flags + static_cast<size_t>(env) * kFlagInts;
-    const bool doit = force || fl[kFDone] != 0;
+    const bool doit = (force || fl[kFDone] != 0) && env < st.num_real;   // padding environments stay frozen (done) for the life of the handle
     // draws
     const unsigned long long gid = env_id_base + env, cnt = static_cast<unsigned long long>(fl[7]);
     ClipModel CM;
@@ -751,8 +760,10 @@ __global__ void dm_task_observe_kernel(const DevModel* __restrict__ gm, DevState
     }
 }
 
-template __global__ void dm_observe_kernel<16, 64>(const DevModel*, DevState, const double*, const float*, const float*, ObsFan, int);
-template __global__ void dm_observe_kernel<32, 64>(const DevModel*, DevState, const double*, const float*, const float*, ObsFan, int);
+template __global__ void dm_observe_kernel<16, 64, false>(const DevModel*, DevState, const double*, const float*, const float*, ObsFan, int);
+template __global__ void dm_observe_kernel<32, 64, false>(const DevModel*, DevState, const double*, const float*, const float*, ObsFan, int);
+template __global__ void dm_observe_kernel<16, 64, true>(const DevModel*, DevState, const double*, const float*, const float*, ObsFan, int);
+template __global__ void dm_observe_kernel<32, 64, true>(const DevModel*, DevState, const double*, const float*, const float*, ObsFan, int);
 template __global__ void dm_amp_obs_kernel<16, 64, false>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int, const int*);
 template __global__ void dm_amp_obs_kernel<32, 64, false>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int, const int*);
 template __global__ void dm_amp_obs_kernel<16, 64, true>(const DevModel*, DevState, const double*, const float*, const float*, float*, int, const double*, int, const int*);

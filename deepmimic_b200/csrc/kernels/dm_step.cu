@@ -122,6 +122,100 @@ int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L) {
 }
 int dm_step_smem_bytes(const StepLayout& L, int tiles) { return (L.hot_floats + L.env_floats * tiles) * static_cast<int>(sizeof(float)); }
 
+// Projected Gauss-Seidel in impulse space, 10 sweeps in btMultiBodyConstraintSolver::solveSingleIteration's row order (joint limits in
+// alternating order, contact normals, friction pairs), lanes = rows: every lane keeps its rows' right-hand side, 1 / A_ii, impulse, bounds
+// and w = (A lambda)_row in registers (S rows per lane: row = lane + s W).  One sequential row update is
+//     every lane evaluates the update of ITS OWN rows from its own w (no data from other lanes),
+//     the update of the row whose turn it is is broadcast by one shuffle, its owner commits its impulse,
+//     every lane adds A(row, i) * delta to its w's (A: symmetric W x W square when S == 1, packed lower triangle otherwise).
+// Same arithmetic in the same order as Bullet's row-by-row sweep (resolveSingleConstraintRowGeneric: delta = rhs - w * jacDiagABInv, clamped sum,
+// delta replaced only when the sum was clamped; friction bounds +-mu * the point's current normal impulse, row skipped while that is <= 0),
+// but the dependent chain of a row is ~6 ALU operations + one shuffle + one FMA.  The two environments of a W = 16 warp run in lockstep, each
+// with its own row numbering (the shuffles are tile-wide).  tj: per-slot triangle offsets rid (rid + 1) / 2 of the packed storage (S > 1).
+template <int W, int S, bool SQUARE>
+__device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const float* sRhs, const float* sInv, const int* tj, int lane, int NL, int P, int NR,
+                                           int NLmax, int Pmax, float mu) {
+    using T = Tl<W>;
+    float w[S], lam[S], rhs[S], inv[S], lo[S], hi[S];
+    int nrow[S];       // friction rows: solver row of the point's normal; -1 otherwise
+    bool live[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int rid = lane + s * W;
+        live[s] = rid < NR;
+        const int r = live[s] ? rid : 0;
+        w[s] = 0.f; lam[s] = live[s] ? sLam[r] : 0.f; rhs[s] = sRhs[r]; inv[s] = sInv[r];
+        nrow[s] = -1; lo[s] = 0.f; hi[s] = 1e10f;                       // contact normals: [0, inf)
+        if (rid < NL) hi[s] = 100.f;                                     // joint limits: [0, 100] (m_maxAppliedImpulse of the limit constraint)
+        else if (rid >= NL + P && live[s]) { nrow[s] = NL + ((rid - NL - P) >> 1); hi[s] = -1.f; lo[s] = 1.f; }   // friction: bounds set per sweep; hi < 0 = skipped
+    }
+    auto a_of = [&](int s, int i) -> float {   // A(lane + s W, i)
+        if (SQUARE) return sA[i * W + lane];
+        const int rid = lane + s * W;
+        return sA[(rid >= i) ? (tj[s] + i) : (i * (i + 1) / 2 + rid)];
+    };
+    // one sequential row update; i: this tile's row (tile-uniform), valid: the row exists in this tile
+    auto row_step = [&](int i, bool valid) {
+        float c[S], sc[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const float d = rhs[s] - w[s] * inv[s];
+            const float sum = lam[s] + d;
+            sc[s] = fminf(fmaxf(sum, lo[s]), hi[s]);
+            c[s] = (sc[s] == sum) ? d : sc[s] - lam[s];
+            if (hi[s] < lo[s]) { c[s] = 0.f; sc[s] = lam[s]; }        // skipped friction row (its normal impulse is not positive)
+        }
+        float sel = c[0];
+#pragma unroll
+        for (int s = 1; s < S; ++s) if (i >= s * W) sel = c[s];
+        float dI = T::shfl(sel, i & (W - 1));
+        dI = valid ? dI : 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            if (valid && lane + s * W == i) lam[s] = sc[s];
+            if (live[s]) w[s] += a_of(s, valid ? i : 0) * dI;
+        }
+    };
+    // warm start: w = A lambda0 (normals carry 0.85 x the cached impulse, everything else starts at 0), in point order
+#pragma unroll 1
+    for (int p = 0; p < Pmax; ++p) {
+        const int i = NL + ((p < P) ? p : 0);
+        float sel = lam[0];
+#pragma unroll
+        for (int s = 1; s < S; ++s) if (i >= s * W) sel = lam[s];
+        float l0 = T::shfl(sel, i & (W - 1));
+        if (!(p < P)) l0 = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) if (live[s] && l0 != 0.f) w[s] += a_of(s, i) * l0;
+    }
+#pragma unroll 1
+    for (int it = 0; it < 10; ++it) {
+#pragma unroll 1
+        for (int u = 0; u < NLmax; ++u) { const bool valid = u < NL; row_step(valid ? ((it & 1) ? u : NL - 1 - u) : 0, valid); }
+#pragma unroll 1
+        for (int p = 0; p < Pmax; ++p) row_step(NL + ((p < P) ? p : 0), p < P);
+        // friction bounds from the normal impulses of this sweep
+        {
+            float tot[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const int n = nrow[s] >= 0 ? nrow[s] : 0;
+                float v = T::shfl(lam[0], n & (W - 1));
+#pragma unroll
+                for (int q = 1; q < S; ++q) { const float vq = T::shfl(lam[q], n & (W - 1)); if (n >= q * W) v = vq; }
+                tot[s] = v;
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) if (nrow[s] >= 0) { if (tot[s] > 0.f) { hi[s] = mu * tot[s]; lo[s] = -hi[s]; } else { hi[s] = -1.f; lo[s] = 1.f; } }
+        }
+#pragma unroll 1
+        for (int f = 0; f < 2 * Pmax; ++f) row_step(NL + P + ((f < 2 * P) ? f : 0), f < 2 * P);
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) if (live[s]) sLam[lane + s * W] = lam[s];
+    __syncwarp();
+}
+
 // Constraint rows of one Bullet sub-step for the environment owned by this tile (warp-collective; both environments of a W = 16 warp
 // run it in lockstep).  Input (shared memory): per-link factors U / 1/D, joint axes, pivots, link velocities, contact points, limit
 // rows, base Cholesky factor.  Output: impulses in sLam (also written to the persistent manifold), z = Y^T lambda in sZ.
@@ -149,10 +243,8 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
     const int NRmax = (W == 32) ? NR : wmax(NR);
     const int nslots = (NRmax + W - 1) / W;
     constexpr int kSlots = (W == 16) ? 3 : 2;
-    float r_w[kSlots];
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
-        r_w[s] = 0.f;
         const int rid = lane + s * W;
         if (s < nslots) {
             const bool rv_ = rid < NR;
@@ -283,77 +375,7 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
         }
         __syncwarp();
         SPROF(8);
-        const float* Ac = sA + lane;                       // column `lane` of A (= row, A is symmetric): Ac[i * W] = A(lane, i)
-        const bool myrow = lane < NR;
-        float w = 0.f;                                     // (A lambda)_lane
-        // warm start: w = A lambda0
-#pragma unroll 1
-        for (int p = 0; p < Pmax; ++p) {
-            const float l0 = (p < P) ? sLam[NL + p] : 0.f;
-            if (myrow && l0 != 0.f) w += Ac[(NL + p) * W] * l0;
-        }
-        // ---- projected Gauss-Seidel, 10 sweeps, rows in blocks of KB consecutive solver rows (see the general path below for the scheme)
-        constexpr int KB = 4;
-        auto block1 = [&](int i0, int nvalid, bool friction) {
-            float wi[KB], lam[KB], rhs[KB], inv[KB], lo[KB], hi[KB], dI[KB], ab[KB * (KB - 1) / 2], av[KB];
-            const float* Ar = sA + i0 * W + i0;            // A(i0 + a, i0 + c) = Ar[a * W + c]
-            const float* Ai = Ac + i0 * W;                 // A(lane, i0 + a) = Ai[a * W]
-#pragma unroll
-            for (int a = 0; a < KB; ++a) {
-                wi[a] = T::shfl(w, i0 + a);
-                av[a] = (a < nvalid) ? Ai[a * W] : 0.f;
-                lam[a] = sLam[i0 + a]; rhs[a] = sRhs[i0 + a]; inv[a] = sInv[i0 + a];
-                lo[a] = 0.f; hi[a] = 1e10f;
-                if (friction) { const float tot = sLam[NL + ((i0 + a - NL - P) >> 1)]; hi[a] = (tot > 0.f) ? mu * tot : -1.f; lo[a] = -hi[a]; }   // hi < 0: skipped row
-#pragma unroll
-                for (int c = 0; c < a; ++c) ab[a * (a - 1) / 2 + c] = Ar[a * W + c];
-            }
-#pragma unroll
-            for (int a = 0; a < KB; ++a) {
-                float wa = wi[a];
-#pragma unroll
-                for (int c = 0; c < a; ++c) wa += ab[a * (a - 1) / 2 + c] * dI[c];
-                float d = rhs[a] - wa * inv[a];
-                const float sum = lam[a] + d;
-                const float sc = fminf(fmaxf(sum, lo[a]), hi[a]);   // same result as the reference's two-sided if: d is only replaced when the sum was clamped
-                d = (sc == sum) ? d : sc - lam[a];
-                const bool ok = a < nvalid && !(friction && hi[a] < 0.f);
-                d = ok ? d : 0.f;
-                dI[a] = d;
-                if (ok && lane == 0) sLam[i0 + a] = sc;
-            }
-            if (myrow) {
-#pragma unroll
-                for (int a = 0; a < KB; ++a) w += av[a] * dI[a];
-            }
-        };
-        auto limit1 = [&](int i, bool valid) {   // one joint-limit row: impulse in [0, 100]
-            const float wi = T::shfl(w, i);
-            const float av = Ac[i * W];
-            const float lam = sLam[i];
-            float d = sRhs[i] - wi * sInv[i];
-            const float sum = lam + d;
-            const float sc = fminf(fmaxf(sum, 0.f), 100.f);
-            d = (sc == sum) ? d : sc - lam;
-            d = valid ? d : 0.f;
-            if (valid && lane == 0) sLam[i] = sc;
-            if (myrow) w += av * d;
-        };
-#pragma unroll 1
-        for (int it = 0; it < 10; ++it) {
-#pragma unroll 1
-            for (int u = 0; u < NLmax; ++u) {
-                const bool valid = u < NL;
-                limit1(valid ? ((it & 1) ? u : NL - 1 - u) : 0, valid);
-                __syncwarp();
-            }
-#pragma unroll 1
-            for (int p = 0; p < Pmax; p += KB) block1(NL + ((p < P) ? p : 0), min(KB, max(0, P - p)), false);
-            __syncwarp();
-#pragma unroll 1
-            for (int f = 0; f < 2 * Pmax; f += KB) block1(NL + P + ((f < 2 * P) ? f : 0), min(KB, max(0, 2 * P - f)), true);
-            __syncwarp();
-        }
+        pgs_sweeps<W, 1, true>(sA, sLam, sRhs, sInv, nullptr, lane, NL, P, NR, NLmax, Pmax, mu);
     } else {
         // ================= general path: up to kSlots rows per lane, A as a packed lower triangle
         // ---- A = J M^-1 J^T, packed lower triangle (overwrites the world-frame / velocity scratch, no longer needed this sub-step)
@@ -391,101 +413,7 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
         }
         __syncwarp();
         SPROF(8);
-        // warm start: w = A lambda0
-    #pragma unroll 1
-        for (int p = 0; p < Pmax; ++p) {
-            const int i = NL + p;
-            const float l0 = (p < P) ? sLam[i] : 0.f;
-            const int ti = i * (i + 1) / 2;
-    #pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                const int rid = lane + s * W;
-                if (s < nslots && rid < NR && l0 != 0.f) r_w[s] += sA[(rid >= i) ? (tj[s] + i) : (ti + rid)] * l0;
-            }
-        }
-        // ---- projected Gauss-Seidel, 10 sweeps (btMultiBodyConstraintSolver::solveSingleIteration ordering: limits (alternating), normals,
-        // frictions).  w = A lambda lives in registers, lanes = rows.  Rows are processed in blocks of KB consecutive solver rows: the
-        // block's w values are fetched with independent shuffles, the KB sequential Gauss-Seidel updates are evaluated by every lane from
-        // broadcast data (with the in-block corrections A(b,a) dI_a), then each lane applies the KB impulses to its rows -- the same
-        // arithmetic, in the same order, as row-by-row Gauss-Seidel, but one shuffle round trip per block instead of per row.
-        constexpr int KB = 4;
-        auto tri = [](int r, int c) { return r * (r + 1) / 2 + c; };   // r >= c
-        auto block_update = [&](int i0, int nvalid, bool friction) {
-            float wi[KB], lam[KB], rhs[KB], inv[KB], lo[KB], hi[KB], dI[KB], ab[KB * (KB - 1) / 2];
-            int ii[KB];
-    #pragma unroll
-            for (int a = 0; a < KB; ++a) {
-                const int i = (a < nvalid) ? i0 + a : i0;
-                ii[a] = i;
-                const int owner = i & (W - 1), oslot = i / W;
-                float wsel = r_w[0];
-    #pragma unroll
-                for (int s = 1; s < kSlots; ++s) if (oslot == s) wsel = r_w[s];
-                wi[a] = T::shfl(wsel, owner);
-                lam[a] = sLam[i]; rhs[a] = sRhs[i]; inv[a] = sInv[i];
-                lo[a] = 0.f; hi[a] = 1e10f;
-                if (friction) { const float tot = sLam[NL + ((i - NL - P) >> 1)]; hi[a] = (tot > 0.f) ? mu * tot : -1.f; lo[a] = -hi[a]; }   // hi < 0 marks a skipped row
-    #pragma unroll
-                for (int c = 0; c < a; ++c) ab[a * (a - 1) / 2 + c] = sA[tri(i, ii[c])];
-            }
-    #pragma unroll
-            for (int a = 0; a < KB; ++a) {
-                float w = wi[a];
-    #pragma unroll
-                for (int c = 0; c < a; ++c) if (a < nvalid) w += ab[a * (a - 1) / 2 + c] * dI[c];
-                float d = rhs[a] - w * inv[a];
-                float sum = lam[a] + d;
-                if (sum < lo[a]) { d = lo[a] - lam[a]; sum = lo[a]; } else if (sum > hi[a]) { d = hi[a] - lam[a]; sum = hi[a]; }
-                const bool ok = a < nvalid && !(friction && hi[a] < 0.f);
-                if (!ok) d = 0.f;
-                dI[a] = d;
-                if (ok && lane == 0) sLam[ii[a]] = sum;
-            }
-    #pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                const int rid = lane + s * W;
-                if (s < nslots && rid < NR) {
-                    float w = r_w[s];
-    #pragma unroll
-                    for (int a = 0; a < KB; ++a) if (a < nvalid) w += sA[(rid >= ii[a]) ? (tj[s] + ii[a]) : (tri(ii[a], rid))] * dI[a];
-                    r_w[s] = w;
-                }
-            }
-        };
-        auto row_update = [&](int i, bool valid) {   // single limit row: lo = 0, hi = 100
-            const int owner = i & (W - 1), oslot = i / W;
-            float wsel = r_w[0];
-    #pragma unroll
-            for (int s = 1; s < kSlots; ++s) if (oslot == s) wsel = r_w[s];
-            const float wi = T::shfl(wsel, owner);
-            const float lam = sLam[i];
-            float dI = sRhs[i] - wi * sInv[i];
-            float sum = lam + dI;
-            if (sum < 0.f) { dI = -lam; sum = 0.f; } else if (sum > 100.f) { dI = 100.f - lam; sum = 100.f; }
-            if (!valid) dI = 0.f;
-            if (valid && lane == 0) sLam[i] = sum;
-            const int ti = i * (i + 1) / 2;
-    #pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                const int rid = lane + s * W;
-                if (s < nslots && rid < NR) r_w[s] += sA[(rid >= i) ? (tj[s] + i) : (ti + rid)] * dI;
-            }
-        };
-    #pragma unroll 1
-        for (int it = 0; it < 10; ++it) {
-    #pragma unroll 1
-            for (int u = 0; u < NLmax; ++u) {
-                const bool valid = u < NL;
-                row_update(valid ? ((it & 1) ? u : NL - 1 - u) : 0, valid);
-                __syncwarp();
-            }
-    #pragma unroll 1
-            for (int p = 0; p < Pmax; p += KB) block_update(NL + ((p < P) ? p : 0), min(KB, max(0, P - p)), false);
-            __syncwarp();
-    #pragma unroll 1
-            for (int f = 0; f < 2 * Pmax; f += KB) block_update(NL + P + ((f < 2 * P) ? f : 0), min(KB, max(0, 2 * P - f)), true);
-            __syncwarp();
-        }
+        pgs_sweeps<W, kSlots, false>(sA, sLam, sRhs, sInv, tj, lane, NL, P, NR, NLmax, Pmax, mu);
     }
     SPROF(9);
     // write impulses back to the manifold (warm start of the next sub-step)
@@ -1410,7 +1338,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             __syncwarp();
             PROF(5);
 #ifdef DM_PROFILE
-            { const int nrm = wmax(NR); if ((threadIdx.x & 31) == 0) { PRF[13] += nrm; PRF[14] += 1; } }
+            { const int nrm = wmax(NR); if ((threadIdx.x & 31) == 0) { PRF[13] += nrm; PRF[14] += 1; if (nrm > W) PRF[15] += 1; } }
 #endif
             solve_rows<W>(E, LYS, LK, CD, CH, lane, NL, P, h, mu, mani, alive ? 1 : 0, PRFP);
             PROF(10);

@@ -66,6 +66,10 @@ enum dm_model_info_kind {
 };
 /* out: num_joints ints (DM_INFO_LAYOUT: 6 ints).  cKinTree joint-table columns as the kernels see them (anim/KinTree.cpp:25-60). */
 int dm_get_model_info(dm_handle* h, int kind, int* out);
+/* test hook: 24 doubles per link -- mass, Bullet shape inertia[3], DeepMimic exact inertia[3], pivot->COM[3], parent COM->pivot[3],
+ * parent->this rotation (x,y,z,w), revolute axis[3], shape half extents[3], manifold breaking threshold (cSimCharacter::BuildMultiBody,
+ * SimCharacter.cpp:789-946, at world scale).  Valid on dm_load_host handles. */
+int dm_get_link_table(dm_handle* h, double* h_out);
 void dm_destroy(dm_handle* h);
 const char* dm_last_error(void);
 int dm_get_dims(dm_handle* h, dm_dims* out);
@@ -92,8 +96,8 @@ int dm_update(dm_handle* h, double dt, int n_updates);
 int dm_record_state(dm_handle* h, float* d_out);             /* [num_envs x state_size] */
 int dm_record_goal(dm_handle* h, float* d_out);              /* [num_envs x goal_size] (no-op when goal_size == 0) */
 /* AMP task scenes target_amp / heading_amp (cSceneTargetAMP / cSceneHeadingAMP: RecordGoal, CalcReward, target updates; goal_size 3).
- * EXPERIMENTAL: the device code is written but has not run on hardware; dm_create accepts these scenes only with
- * DM_EXPERIMENTAL_TASK_SCENES=1 in the environment.  dm_goal_host is RecordGoal into a host buffer [num_envs x 3]; the task-state hooks
+ * heading_amp_getup / strike_amp are EXPERIMENTAL (device code written and host-checked, not validated on hardware): dm_create accepts
+ * them only with DM_EXPERIMENTAL_TASK_SCENES=1 in the environment.  dm_goal_host is RecordGoal into a host buffer [num_envs x 3]; the task-state hooks
  * expose one environment's task block (16 doubles: target x, z, speed, heading, timer, timer max, previous-action COM[3], COM[3], draw
  * counter, reset counter) and the scene constants + draw-stream key for the parity tests. */
 int dm_goal_host(dm_handle* h, float* h_out);
@@ -107,6 +111,9 @@ int dm_get_task_state(dm_handle* h, int env, double* h_out16);
 int dm_set_task_state(dm_handle* h, int env, const double* h_in16);
 int dm_get_task_params(dm_handle* h, double* h_out48, unsigned long long* h_stream2);   /* 16 dm_task.cuh + 32 dm_task_ext.cuh constants */
 int dm_calc_reward(dm_handle* h, float* d_out);              /* [num_envs] */
+/* cSceneImitate::CalcRewardImitate (SceneImitate.cpp:7-127) whatever the scene's own CalcReward is: in the AMP task scenes it is evaluated
+ * against each environment's active clip of the dataset (BASELINE.json config 5: "AMP obs recorded alongside imitate reward"). */
+int dm_calc_reward_imitate(dm_handle* h, float* d_out);
 /* AMP observations (RecordAMPObsAgent / RecordAMPObsExpert, DeepMimicCore.h:81-82; cSceneImitateAMP::BuildAMPObs): [num_envs x amp_obs_size].
  * Agent: simulated pose / vel now and at the last dm_set_action (call dm_set_action exactly when need_new_action is set, like the
  * reference's agent).  Expert: the clip at h_kin_time[env] (NULL: random U(0, duration) per env and call) and one query period earlier. */

@@ -766,15 +766,17 @@ struct Oracle {
         return fallen;
     }
     // cSceneImitate::CalcReward / CalcRewardImitate (SceneImitate.cpp:7-127,163-175)
-    double CalcReward(double* dbg = nullptr) const {
-        if (scene_kind == kTargetAMP) return CalcRewardTarget();
-        if (scene_kind == kStrikeAMP) return CalcRewardStrike();
-        if (scene_kind == kHeadingGetup && CheckGettingUp()) {   // cSceneHeadingAMPGetup::CalcRewardGetup (:18-38), flat ground at 0
+    // force_imitate: cSceneImitate::CalcRewardImitate whatever the scene (the task scenes inherit it; BASELINE.json config 5 records it next to
+    // the AMP observations) -- against the kinematic character, i.e. the active clip of the dataset
+    double CalcReward(double* dbg = nullptr, bool force_imitate = false) const {
+        if (!force_imitate && scene_kind == kTargetAMP) return CalcRewardTarget();
+        if (!force_imitate && scene_kind == kStrikeAMP) return CalcRewardStrike();
+        if (!force_imitate && scene_kind == kHeadingGetup && CheckGettingUp()) {   // cSceneHeadingAMPGetup::CalcRewardGetup (:18-38), flat ground at 0
             const double root_h = std::min(std::max(SimRootPos().y / sa.cfg.getup_height_root, 0.0), 1.0);
             const double head_h = std::min(std::max(BodyPos(sa.cfg.head_id).y / sa.cfg.getup_height_head, 0.0), 1.0);
             return 0.2 * root_h + 0.8 * head_h;
         }
-        if (IsHeading()) return CalcRewardHeading();
+        if (!force_imitate && IsHeading()) return CalcRewardHeading();
         if (HasFallen()) return 0;
         double pose_w = 0.5, vel_w = 0.05, end_eff_w = 0.15, root_w = 0.2, com_w = 0.1;
         double total_w = pose_w + vel_w + end_eff_w + root_w + com_w;
@@ -1185,6 +1187,24 @@ void dmo_get_dims(void* h, int* out) {
     Oracle* o = static_cast<Oracle*>(h);
     out[0] = o->nj; out[1] = o->ndof; out[2] = 6 + o->mb.numDofs; out[3] = o->StateSize(); out[4] = o->action_size; out[5] = o->GoalSize(); out[6] = o->SnapshotSize(); out[7] = o->sa.motion.num_frames;
 }
+// test hook mirroring dm_get_link_table (same 24-double rows) from the oracle's own multibody: mass, Bullet inertia, cRBDUtil moment of inertia
+// (diagonal of BuildMomentInertia), dVector, eVector, zeroRotParentToThis (x,y,z,w), axis, half extents, breaking threshold
+void dmo_link_table(void* h, double* out) {
+    Oracle* o = static_cast<Oracle*>(h);
+    for (int j = 0; j < o->nj; ++j) {
+        const orc::BtLink& L = o->mb.links[j];
+        double* q = out + 24 * j;
+        q[0] = L.mass;
+        q[1] = L.inertia.x; q[2] = L.inertia.y; q[3] = L.inertia.z;
+        const orc::SpMat I = orc::BuildMomentInertia(*o->cm, j);
+        q[4] = I.m[0][0]; q[5] = I.m[1][1]; q[6] = I.m[2][2];
+        q[7] = L.dVector.x; q[8] = L.dVector.y; q[9] = L.dVector.z; q[10] = L.eVector.x; q[11] = L.eVector.y; q[12] = L.eVector.z;
+        q[13] = L.zeroRotParentToThis.x; q[14] = L.zeroRotParentToThis.y; q[15] = L.zeroRotParentToThis.z; q[16] = L.zeroRotParentToThis.w;
+        q[17] = L.axisTop[0].x; q[18] = L.axisTop[0].y; q[19] = L.axisTop[0].z;
+        q[20] = L.halfExtents.x; q[21] = L.halfExtents.y; q[22] = L.halfExtents.z;
+        q[23] = L.manifold.breakingThreshold;
+    }
+}
 double dmo_motion_duration(void* h) { return static_cast<Oracle*>(h)->Mot().duration(); }
 void dmo_set_mode(void* h, int mode) { static_cast<Oracle*>(h)->mode = mode; }
 void dmo_reset(void* h, double kin_time, double rand_theta, double max_time) { static_cast<Oracle*>(h)->Reset(kin_time, rand_theta, max_time); }
@@ -1232,6 +1252,7 @@ void dmo_record_amp_obs_agent(void* h, double* out) { static_cast<Oracle*>(h)->R
 void dmo_record_amp_obs_expert(void* h, double kin_time, double* out) { static_cast<Oracle*>(h)->RecordAMPObsExpert(-1, kin_time, out); }
 void dmo_record_amp_obs_expert_clip(void* h, int clip, double kin_time, double* out) { static_cast<Oracle*>(h)->RecordAMPObsExpert(clip, kin_time, out); }
 double dmo_calc_reward(void* h) { return static_cast<Oracle*>(h)->CalcReward(); }
+double dmo_calc_reward_imitate(void* h) { return static_cast<Oracle*>(h)->CalcReward(nullptr, true); }
 double dmo_calc_reward_terms(void* h, double* errs) { return static_cast<Oracle*>(h)->CalcReward(errs); }
 int dmo_need_new_action(void* h) { return static_cast<Oracle*>(h)->need_new_action ? 1 : 0; }
 int dmo_is_episode_end(void* h) { return static_cast<Oracle*>(h)->IsEpisodeEnd() ? 1 : 0; }

@@ -37,6 +37,14 @@ MINI_DATASET_TEXT = """{
 }
 """
 
+# Authored as well: a 56-entry dataset with the SHAPE of R/data/datasets/humanoid3d_clips_locomotion.txt (56 clips, 48 MB -- too large to
+# ship) over the two locomotion clips of the archive, with varying weights: BASELINE.json config 5 ("AMP target humanoid3d_locomotion, 4096
+# envs") runs on it in bench.py and in the GPU tests (synthetic data of the reference's shape; every entry is loaded as a clip of its own).
+SYN56_DATASET = "data/datasets/synthetic_locomotion_56.txt"
+SYN56_DATASET_TEXT = "{\n\t\"Motions\":\n\t[\n" + ",\n".join(
+    "\t\t{\"Weight\": %d, \"File\": \"data/motions/humanoid3d_%s.txt\"}" % (1 + (7 * k) % 5, "walk" if k % 3 else "run") for k in range(56)) + "\n\t]\n}\n"
+
+
 def main():
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets.tar.gz")
     with tarfile.open(out, "w:gz", compresslevel=9) as tf:
@@ -47,10 +55,11 @@ def main():
             with open(p, "rb") as fh:
                 tf.addfile(ti, fh)
         import io
-        data = MINI_DATASET_TEXT.encode()
-        ti = tarfile.TarInfo(MINI_DATASET)
-        ti.size = len(data); ti.mtime = 0; ti.mode = 0o644
-        tf.addfile(ti, io.BytesIO(data))
+        for name, text in ((MINI_DATASET, MINI_DATASET_TEXT), (SYN56_DATASET, SYN56_DATASET_TEXT)):
+            data = text.encode()
+            ti = tarfile.TarInfo(name)
+            ti.size = len(data); ti.mtime = 0; ti.mode = 0o644
+            tf.addfile(ti, io.BytesIO(data))
     print("wrote", out, os.path.getsize(out), "bytes")
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@ def load_oracle():
     L.dmo_create.restype = C.c_void_p
     L.dmo_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p)]
     L.dmo_last_error.restype = C.c_char_p
-    for f in ("dmo_calc_reward", "dmo_motion_duration", "dmo_get_time", "dmo_calc_reward_terms", "dmo_u01"):
+    for f in ("dmo_calc_reward", "dmo_calc_reward_imitate", "dmo_motion_duration", "dmo_get_time", "dmo_calc_reward_terms", "dmo_u01"):
         getattr(L, f).restype = C.c_double
     L.dmo_u01.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
     L.dmo_set_task_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
@@ -154,6 +154,9 @@ class Oracle:
     def calc_reward(self):
         return self.L.dmo_calc_reward(self.h)
 
+    def calc_reward_imitate(self):
+        return self.L.dmo_calc_reward_imitate(self.h)
+
     def amp_obs_size(self):
         return int(self.L.dmo_amp_obs_size(self.h))
 
@@ -218,6 +221,11 @@ class Oracle:
         pos, rot, lv, av = np.zeros((n, 3)), np.zeros((n, 4)), np.zeros((n, 3)), np.zeros((n, 3))
         self.L.dmo_body_state(self.h, dp(pos), dp(rot), dp(lv), dp(av))
         return pos, rot, lv, av
+
+    def link_table(self):
+        out = np.zeros((self.num_joints, 24))
+        self.L.dmo_link_table(self.h, dp(out))
+        return out
 
     def get_snapshot(self):
         s = np.zeros(self.snapshot_size)

@@ -75,7 +75,7 @@ def test_loader_errors_are_reported(asset_root):
     with pytest.raises(RuntimeError):
         capi.HostModel(["--scene", "imitate", "--character_files", "data/characters/nope.txt"], asset_root)
     with pytest.raises(RuntimeError, match="Unsupported scene"):
-        capi.HostModel(["--scene", "heading_amp", "--arg_file", ARG_FILES[0]], asset_root)     # first key wins: the scene is overridden
+        capi.HostModel(["--scene", "dribble_amp", "--arg_file", ARG_FILES[0]], asset_root)     # first key wins: the scene is overridden
     for extra, msg in ((["--char_ctrls", "ct_vel"], "Unsupported character controller"), (["--enable_char_soft_contact", "true"], "enable_char_soft_contact"),
                        (["--enable_root_rot_fail", "true"], "enable_root_rot_fail"), (["--char_types", "biped3d"], "Unsupported character type"),
                        (["--character_files", "data/characters/humanoid3d.txt", "data/characters/dog3d.txt"], "more than one character")):

@@ -15,6 +15,7 @@ import pytest
 
 from tests.oracle_binding import Oracle
 from tests.parity_util import SnapLayout, compare_sim_state, joint_types_from_assets, random_policy_action
+from tests.test_parity_gpu import _explained_by_branch_flip
 
 pytestmark = pytest.mark.gpu
 
@@ -161,17 +162,20 @@ def test_set_action_pd_targets_match_oracle(asset_root, arg_file, char_file):
 
 
 def _contact_state(orc, lay, rng, t0, min_updates, min_points=2):
-    """oracle state after at least `min_updates` updates of a random-policy episode, at the first update with >= min_points manifold points"""
+    """oracle state of a gently perturbed episode (small random actions around the clip's mean pose) after at least `min_updates` updates,
+    at the first update with >= min_points manifold points; retried with other draws when the character falls first"""
     off, scl, lo, hi = orc.action_statics()
-    orc.reset(float(t0), 0.0, 20.0)
-    for upd in range(1200):
-        if orc.need_new_action():
-            orc.set_action(random_policy_action(rng, off, scl, lo, hi))
-        orc.update(1.0 / 600.0)
-        assert not orc.is_episode_end()
-        s = orc.get_snapshot()
-        if upd >= min_updates and sum(lay.contact_counts(s)) >= min_points:
-            return s
+    for attempt in range(20):
+        orc.reset(float(t0), 0.0, 20.0)
+        for upd in range(600):
+            if orc.need_new_action():
+                orc.set_action(random_policy_action(rng, off, scl, lo, hi, sigma=0.1))
+            orc.update(1.0 / 600.0)
+            if orc.is_episode_end():
+                break
+            s = orc.get_snapshot()
+            if upd >= min_updates and sum(lay.contact_counts(s)) >= min_points:
+                return s
     raise AssertionError("no contact state found")
 
 
@@ -239,6 +243,9 @@ def test_config2_4096_walk_envs_reward_parity_on_a_64_env_subset(asset_root):
         states[e] = orc.get_snapshot()
     eqs, eqds, r_pure, r_own, s_pure = [], [], 0.0, 0.0, 0.0
     ended = set()
+    flips = 0
+    orc2 = Oracle(["--arg_file", arg_file], asset_root)
+    rng3 = np.random.default_rng(17)
     for step in range(STEPS):
         acts = np.clip(-off + 0.25 / scl * rng.standard_normal((N, off.shape[0])), lo, hi)
         core.set_action(torch.tensor(acts, dtype=torch.float32, device="cuda"))
@@ -255,7 +262,12 @@ def test_config2_4096_walk_envs_reward_parity_on_a_64_env_subset(asset_root):
                 orc.set_snapshot(states[e]); orc.update(1.0 / 600.0)
                 so, sg = orc.get_snapshot(), core.get_snapshot(int(e))
                 eq, eqd = compare_sim_state(lay, so, sg, jt)
-                if lay.contact_counts(so) == lay.contact_counts(sg):   # discrete contact branches are covered by test_parity_gpu
+                if eq > 1e-3 or eqd > 0.5 or lay.contact_counts(so) != lay.contact_counts(sg):
+                    # a discrete contact branch (cached point kept / dropped at the breaking threshold, support vertex of a flat foot): the
+                    # oracle itself must land on the device's result under fp32-rounding noise of the same start state
+                    assert _explained_by_branch_flip(orc2, lay, jt, states[e], sg, rng3), ("c2", step, upd, int(e), eq, eqd)
+                    flips += 1
+                else:
                     eqs.append(eq); eqds.append(eqd)
                 _assert_time_block(lay, so, sg, ("c2", step, upd, int(e)))
                 states[e] = so
@@ -283,20 +295,20 @@ def test_config2_4096_walk_envs_reward_parity_on_a_64_env_subset(asset_root):
     print("C2 walk 4096 envs, %d-env subset, %d updates compared (%d episodes of the subset ended): |dq| max %.2e ; |dqd| median %.2e p99 %.2e max %.2e ; "
           "reward own-state %.2e, pure %.2e ; observation pure %.2e" % (len(sub), len(eqs), len(ended), eqs.max(), np.median(eqds), np.percentile(eqds, 99), eqds.max(),
                                                                         r_own, r_pure, s_pure))
-    assert len(eqs) > 0.9 * len(sub) * 20 * STEPS * 0.5
-    assert eqs.max() <= 1e-3
+    print("C2: %d updates went through a contact branch flip that the oracle reproduces under rounding noise" % flips)
+    assert len(eqs) > 0.9 * len(sub) * 20 * STEPS * 0.5 and flips <= max(2, len(eqs) // 200)
+    assert eqs.max() <= 1e-3 and eqds.max() <= 0.5
     assert np.median(eqds) <= 2e-3 and np.percentile(eqds, 99) <= 5e-2
     assert r_pure < 2e-5 and s_pure < 2e-4 and r_own < 1e-3
     assert core.counters()[1] == 0
 
 
-def test_root_rot_sync_time_block_matches_oracle_across_clip_wrap(asset_root, monkeypatch):
+def test_root_rot_sync_time_block_matches_oracle_across_clip_wrap(asset_root):
     """--sync_char_root_rot true (dog3d_spin and 3 more shipped arg files; cSceneImitate::SyncKinCharNewCycle, SceneImitate.cpp:420-444):
     the simulated root is turned by 0.7 rad before the clip wraps; the kinematic origin must pick up the same heading correction
     (rotation AND the re-centred position) as the oracle's at the wrap and keep it.  Teacher-forced like the test above."""
     import torch
     from deepmimic_b200.capi import BatchedCore
-    monkeypatch.setenv("DM_EXPERIMENTAL_ROOT_ROT_SYNC", "1")
     args = ["--sync_char_root_rot", "true", "--arg_file", "args/train_humanoid3d_walk_args.txt"]
     core = BatchedCore(args, 4, asset_root, device=0, seed=3)
     orc = Oracle(args, asset_root)

@@ -396,13 +396,17 @@ def test_device_task_logic_matches_the_oracle_on_the_host(asset_root, task_shim,
     assert n_goal == 180 and o.task_counter() > (3 if args is TARGET else 50) and (n_far > 0) == (args is TARGET)
 
 
-def test_task_scenes_stay_refused_without_the_opt_in(asset_root, monkeypatch):
+def test_unvalidated_task_scenes_stay_refused_without_the_opt_in(asset_root, monkeypatch):
+    """target_amp / heading_amp are on the default path since round 2 (validated on hardware); heading_amp_getup / strike_amp and every other
+    scene name are still refused unless DM_EXPERIMENTAL_TASK_SCENES=1."""
     from deepmimic_b200 import capi
     monkeypatch.delenv("DM_EXPERIMENTAL_TASK_SCENES", raising=False)
-    with pytest.raises(RuntimeError, match="Unsupported scene"):
-        capi.HostModel(["--kin_ctrl", "motion", "--motion_file", "data/motions/humanoid3d_run.txt"] + TARGET[2:], asset_root)
-    monkeypatch.setenv("DM_EXPERIMENTAL_TASK_SCENES", "1")
+    for bad in (GETUP, STRIKE, ["--scene", "dribble_amp"] + TARGET, ["--scene", "kin_char"] + TARGET):
+        with pytest.raises(RuntimeError, match="Unsupported scene"):
+            capi.HostModel(bad, asset_root)
+    assert capi.HostModel(HEADING, asset_root).dims.goal_size == 3
     m = capi.HostModel(TARGET, asset_root)                                      # the mini dataset (4 clips) loads in a task scene ...
+    monkeypatch.setenv("DM_EXPERIMENTAL_TASK_SCENES", "1")
     assert m.dims.goal_size == 3
     dur, cdf = m.clip_table()
     o = Oracle(TARGET, asset_root)
