@@ -149,6 +149,8 @@ struct Oracle {
     void BuildSimCharacter() {
         mb = BtMultiBody();
         mb.links.resize(nj);
+        // CONVEX_DISTANCE_MARGIN; DMO_CAPSULE_MARGIN=0 reproduces round 1's margin-free capsule inertia for A/B runs of the behavioural pins
+        const float capsule_inertia_margin = std::getenv("DMO_CAPSULE_MARGIN") ? static_cast<float>(std::atof(std::getenv("DMO_CAPSULE_MARGIN"))) : 0.04f;
         float fs = static_cast<float>(scale);
         mb.gravity = F3(static_cast<float>(sa.cfg.gravity.x * scale), static_cast<float>(sa.cfg.gravity.y * scale), static_cast<float>(sa.cfg.gravity.z * scale));  // cWorld::SetGravity (World.cpp:229-235)
         child_rot.resize(nj); child_pos.resize(nj);
@@ -172,8 +174,9 @@ struct Oracle {
                 float r = static_cast<float>(scale * 0.5 * bd.param[0]);
                 float hh = 0.5f * static_cast<float>(scale * bd.param[1]);  // btCapsuleShape(radius, height): halfHeight = 0.5*height
                 L.halfExtents = F3(r, hh, 0);
-                F3 he(r, r + hh, r);  // btCapsuleShape::calculateLocalInertia: bounding box of the capsule
-                float lx = 2 * he.x, ly = 2 * he.y, lz = 2 * he.z;
+                F3 he(r, r + hh, r);  // btCapsuleShape::calculateLocalInertia: bounding box of the capsule ...
+                const float margin = capsule_inertia_margin;   // ... with CONVEX_DISTANCE_MARGIN (0.04) added to every half extent (Bullet 2.88)
+                float lx = 2 * (he.x + margin), ly = 2 * (he.y + margin), lz = 2 * (he.z + margin);
                 float sm = mass * 0.08333333f;
                 L.inertia = F3(sm * (ly * ly + lz * lz), sm * (lx * lx + lz * lz), sm * (lx * lx + ly * ly));
                 L.manifold.breakingThreshold = 0.02f * length(he);
