@@ -136,7 +136,11 @@ template <int W, int S, bool SQUARE>
 __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const float* sRhs, const float* sInv, const int* tj, int lane, int NL, int P, int NR,
                                            int NLmax, int Pmax, float mu) {
     using T = Tl<W>;
-    float w[S], lam[S], rhs[S], inv[S], lo[S], hi[S];
+    // per row (S rows per lane): w = (A lambda)_row, impulse, rhs, -1 / A_ii, bounds, and the bounds expressed on the UPDATE: dlo = lo - lambda,
+    // dhi = hi - lambda.  Clamping the update to [dlo, dhi] is Bullet's "clamp the sum, then delta = limit - applied" (the two produce the same
+    // delta in every branch: unclamped -> d itself, clamped -> limit - applied) with a dependent chain of FFMA, FMNMX, FMNMX per row instead
+    // of seven operations; dlo / dhi are refreshed off the chain by the row's owner.  A skipped friction row has dlo = dhi = 0.
+    float w[S], lam[S], rhs[S], ninv[S], lo[S], hi[S], dlo[S], dhi[S];
     int nrow[S];       // friction rows: solver row of the point's normal; -1 otherwise
     bool live[S];
 #pragma unroll
@@ -144,10 +148,12 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
         const int rid = lane + s * W;
         live[s] = rid < NR;
         const int r = live[s] ? rid : 0;
-        w[s] = 0.f; lam[s] = live[s] ? sLam[r] : 0.f; rhs[s] = sRhs[r]; inv[s] = sInv[r];
+        w[s] = 0.f; lam[s] = live[s] ? sLam[r] : 0.f; rhs[s] = live[s] ? sRhs[r] : 0.f; ninv[s] = live[s] ? -sInv[r] : 0.f;
         nrow[s] = -1; lo[s] = 0.f; hi[s] = 1e10f;                       // contact normals: [0, inf)
-        if (rid < NL) hi[s] = 100.f;                                     // joint limits: [0, 100] (m_maxAppliedImpulse of the limit constraint)
-        else if (rid >= NL + P && live[s]) { nrow[s] = NL + ((rid - NL - P) >> 1); hi[s] = -1.f; lo[s] = 1.f; }   // friction: bounds set per sweep; hi < 0 = skipped
+        if (rid < NL) hi[s] = 100.f;                                     // joint limits: [0, 100]
+        dlo[s] = lo[s] - lam[s]; dhi[s] = hi[s] - lam[s];
+        if (rid >= NL + P && live[s]) { nrow[s] = NL + ((rid - NL - P) >> 1); dlo[s] = dhi[s] = 0.f; }   // friction: bounds set per sweep
+        if (!live[s]) dlo[s] = dhi[s] = 0.f;
     }
     auto a_of = [&](int s, int i) -> float {   // A(lane + s W, i)
         if (SQUARE) return sA[i * W + lane];
@@ -156,15 +162,11 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
     };
     // one sequential row update; i: this tile's row (tile-uniform), valid: the row exists in this tile
     auto row_step = [&](int i, bool valid) {
-        float c[S], sc[S];
+        float a[S], c[S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const float d = rhs[s] - w[s] * inv[s];
-            const float sum = lam[s] + d;
-            sc[s] = fminf(fmaxf(sum, lo[s]), hi[s]);
-            c[s] = (sc[s] == sum) ? d : sc[s] - lam[s];
-            if (hi[s] < lo[s]) { c[s] = 0.f; sc[s] = lam[s]; }        // skipped friction row (its normal impulse is not positive)
-        }
+        for (int s = 0; s < S; ++s) a[s] = live[s] ? a_of(s, i) : 0.f;           // independent of the chain: issued first
+#pragma unroll
+        for (int s = 0; s < S; ++s) c[s] = fminf(fmaxf(fmaf(ninv[s], w[s], rhs[s]), dlo[s]), dhi[s]);
         float sel = c[0];
 #pragma unroll
         for (int s = 1; s < S; ++s) if (i >= s * W) sel = c[s];
@@ -172,8 +174,11 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
         dI = valid ? dI : 0.f;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            if (valid && lane + s * W == i) lam[s] = sc[s];
-            if (live[s]) w[s] += a_of(s, valid ? i : 0) * dI;
+            w[s] = fmaf(a[s], dI, w[s]);
+            if (valid && lane + s * W == i) {      // the owner commits: applied impulse = the limit itself when clamped (Bullet), else applied + delta
+                lam[s] = (c[s] == dlo[s] && c[s] != dhi[s]) ? lo[s] : ((c[s] == dhi[s] && c[s] != dlo[s]) ? hi[s] : lam[s] + c[s]);
+                if (nrow[s] < 0 || dlo[s] != dhi[s]) { dlo[s] = lo[s] - lam[s]; dhi[s] = hi[s] - lam[s]; }
+            }
         }
     };
     // warm start: w = A lambda0 (normals carry 0.85 x the cached impulse, everything else starts at 0), in point order
@@ -194,7 +199,7 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
         for (int u = 0; u < NLmax; ++u) { const bool valid = u < NL; row_step(valid ? ((it & 1) ? u : NL - 1 - u) : 0, valid); }
 #pragma unroll 1
         for (int p = 0; p < Pmax; ++p) row_step(NL + ((p < P) ? p : 0), p < P);
-        // friction bounds from the normal impulses of this sweep
+        // friction bounds from the normal impulses of this sweep: +-mu * lambda_n; a point whose normal impulse is not positive skips its friction rows
         {
             float tot[S];
 #pragma unroll
@@ -206,7 +211,10 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
                 tot[s] = v;
             }
 #pragma unroll
-            for (int s = 0; s < S; ++s) if (nrow[s] >= 0) { if (tot[s] > 0.f) { hi[s] = mu * tot[s]; lo[s] = -hi[s]; } else { hi[s] = -1.f; lo[s] = 1.f; } }
+            for (int s = 0; s < S; ++s) if (nrow[s] >= 0) {
+                if (tot[s] > 0.f) { hi[s] = mu * tot[s]; lo[s] = -hi[s]; dlo[s] = lo[s] - lam[s]; dhi[s] = hi[s] - lam[s]; }
+                else dlo[s] = dhi[s] = 0.f;
+            }
         }
 #pragma unroll 1
         for (int f = 0; f < 2 * Pmax; ++f) row_step(NL + P + ((f < 2 * P) ? f : 0), f < 2 * P);
@@ -242,7 +250,7 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
     const int NR = NL + 3 * P;
     const int NRmax = (W == 32) ? NR : wmax(NR);
     const int nslots = (NRmax + W - 1) / W;
-    constexpr int kSlots = (W == 16) ? 3 : 2;
+    constexpr int kSlots = 2;   // rows per lane in the general path: the host caps the row capacity at 2 W (32 humanoid3d, 60 dog3d)
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
         const int rid = lane + s * W;

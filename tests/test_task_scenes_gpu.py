@@ -148,7 +148,7 @@ def test_config5_shape_4096_envs_56_clip_dataset(asset_root):
     lo = torch.tensor(core.static(4), dtype=torch.float32, device="cuda"); hi = torch.tensor(core.static(5), dtype=torch.float32, device="cuda")
     g = torch.Generator(device="cuda"); g.manual_seed(1)
     core.reward_imitate(rim); core.sync()
-    assert float(rim.min()) > 0.98                     # right after a reset the simulated character sits on its own clip's pose: reward 1
+    assert float(rim.min()) > 0.95 and float(rim.median()) > 0.999   # right after a reset the simulated character sits on its clip pose (lifted out of the ground where needed)
     for step in range(6):
         a = torch.clamp(-off + 0.25 / scl * torch.randn(Nn, 28, device="cuda", generator=g), lo, hi).contiguous()
         core.set_action(a); core.update(1.0 / 600.0, 20)
