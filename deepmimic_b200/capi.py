@@ -19,7 +19,7 @@ DM_STATE_OFFSET, DM_STATE_SCALE, DM_ACTION_OFFSET, DM_ACTION_SCALE, DM_ACTION_BO
 
 EXPORTS = ["dm_create", "dm_load_host", "dm_get_model_info", "dm_get_link_table", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_get_scene_name", "dm_stream", "dm_sync", "dm_set_mode", "dm_set_sample_count", "dm_get_time_limits", "dm_reset", "dm_set_action",
            "dm_update", "dm_record_state", "dm_record_goal", "dm_goal_host", "dm_reset_clips", "dm_record_amp_obs_expert_clips", "dm_get_clip_table", "dm_get_task_state", "dm_set_task_state", "dm_get_task_params", "dm_calc_reward", "dm_calc_reward_imitate", "dm_record_amp_obs_agent", "dm_record_amp_obs_expert", "dm_amp_obs_host", "dm_observe", "dm_get_flags", "dm_step_host", "dm_step_host_reset", "dm_set_time_limits", "dm_exchange_create", "dm_exchange_connect", "dm_exchange_publish", "dm_exchange_acquire", "dm_exchange_release", "dm_exchange_status", "dm_exchange_destroy", "dm_set_timing", "dm_step_host_timing", "dm_get_snapshot",
-           "dm_set_snapshot", "dm_get_counters", "dm_debug_enable", "dm_get_debug"]
+           "dm_set_snapshot", "dm_get_counters", "dm_debug_enable", "dm_get_debug", "dm_mlp_create", "dm_mlp_forward", "dm_mlp_launches", "dm_mlp_destroy"]
 
 
 def lib():
@@ -83,6 +83,13 @@ def lib():
         L.dm_get_counters.argtypes = [vp, C.POINTER(C.c_int64)]
         L.dm_debug_enable.argtypes = [vp, C.c_int]
         L.dm_get_debug.argtypes = [vp, C.c_int, C.c_void_p]
+        fpp = C.POINTER(C.c_float)
+        L.dm_mlp_create.restype = vp
+        L.dm_mlp_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fpp, fpp, fpp, fpp, fpp, fpp, fpp, fpp, C.c_float, fpp, fpp, C.c_int]
+        L.dm_mlp_forward.argtypes = [vp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.dm_mlp_launches.restype = C.c_longlong
+        L.dm_mlp_launches.argtypes = [vp]
+        L.dm_mlp_destroy.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -345,6 +352,49 @@ class HostModel:
     def close(self):
         if self.h:
             lib().dm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TensorCoreMLP:
+    """dm_mlp_* handle: the actor network (normalise -> 2 hidden ReLU layers -> linear -> un-normalise) on the tcgen05 tensor cores.
+    weights: the reference's dense kernels, [inputs x units] float arrays (deepmimic_b200.tf_checkpoint.load_actor / the fixture files)."""
+
+    def __init__(self, w0, b0, w1, b1, w2, b2, in_mean=None, in_std=None, in_clip=float("inf"), out_mean=None, out_std=None, max_rows=4096, device=0):
+        L = lib()
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+        w0, b0, w1, b1, w2, b2, in_mean, in_std, out_mean, out_std = (f(x) for x in (w0, b0, w1, b1, w2, b2, in_mean, in_std, out_mean, out_std))
+        self.in_dim, self.h0 = w0.shape
+        self.h1, self.out_dim = w2.shape
+        assert w1.shape == (self.h0, self.h1) and b0.shape == (self.h0,) and b1.shape == (self.h1,) and b2.shape == (self.out_dim,)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+        clip = 0.0 if not np.isfinite(in_clip) else float(in_clip)
+        self.h = L.dm_mlp_create(device, self.in_dim, self.h0, self.h1, self.out_dim, p(w0), p(b0), p(w1), p(b1), p(w2), p(b2), p(in_mean), p(in_std), clip, p(out_mean), p(out_std), max_rows)
+        if not self.h:
+            raise RuntimeError("dm_mlp_create failed: %s" % L.dm_last_error().decode())
+        self.h = C.c_void_p(self.h)
+        self.max_rows = max_rows
+
+    def forward(self, obs, actions, noise=None, stream=None):
+        """obs [rows, in_dim], actions [rows, out_dim] (written), noise [rows, out_dim] or None: contiguous float32 CUDA tensors; stream: cudaStream_t handle (int) or None"""
+        rows = obs.shape[0]
+        rc = lib().dm_mlp_forward(self.h, C.c_void_p(obs.data_ptr()), C.c_void_p(noise.data_ptr()) if noise is not None else None, C.c_void_p(actions.data_ptr()), rows,
+                                  C.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise RuntimeError("dm_mlp_forward: %s" % lib().dm_last_error().decode())
+        return actions
+
+    def launches(self):
+        return int(lib().dm_mlp_launches(self.h))
+
+    def close(self):
+        if self.h:
+            lib().dm_mlp_destroy(self.h)
             self.h = None
 
     def __del__(self):

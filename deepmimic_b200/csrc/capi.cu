@@ -424,6 +424,7 @@ int launch_reset(dm_handle* h, int force, const double* kt, const double* mt, co
 extern "C" {
 
 const char* dm_last_error(void) { return g_err.c_str(); }
+void dm_set_last_error(const char* msg) { g_err = msg ? msg : ""; }   // other translation units of the library (mlp_capi.cu) report through the same string
 
 // host half of dm_create: argument / asset loading and the flat model (no device work)
 static bool load_host_model(dm_handle& H, const char* asset_root, int argc, const char** argv) {

@@ -95,7 +95,11 @@ __device__ __forceinline__ Q4 quat_integrate3(V3 omega, Q4 quat, bool base_body,
 
 // ---- block-shared model table, floats per link (LK)
 enum LkSlot { kLC = 0 /*3*/, kLD = 3 /*3*/, kLM = 6, kLWd = 7 /*6*/, kLWb = 13 /*6*/, kLAx = 19 /*3*/, kLInt = 22 /* parent|jtype|ndof|depth0 */, kLInt2 = 23 /* dof0|lastd|nchild */,
-              kLZr = 24 /*4*/, kLHe = 28 /*3*/, kLThr = 31, kLKp = 32, kLKd = 33, kLTl = 34, kLLo = 35, kLHi = 36, kLFlg = 37 /* shape | fall<<8 | has_limit<<16 */, kLkFloats = 40 };
+              kLZr = 24 /*4*/, kLHe = 28 /*3*/, kLThr = 31, kLKp = 32, kLKd = 33, kLTl = 34, kLLo = 35, kLHi = 36, kLFlg = 37 /* shape | fall<<8 | has_limit<<16 */, kLTree = 38 /* level | maxlevel<<8 | nchild<<16 */, kLChild = 39 /* child lanes, 8 bits each */,
+              kLkFloats = 40 };
+// ---- block-shared header in front of the link table (floats): the launch's StepLayout (24 ints), children per tree level (8 ints), constants
+enum HdrSlot { kHLayout = 0, kHLvc = 24, kHGrav = 32 /*3*/, kHh = 35, kHScale = 36, kHMu = 37, kHFdt = 38, kHdrFloats = 40 };
+__device__ __forceinline__ float* step_smem() { extern __shared__ __align__(16) float dm_step_sm[]; return dm_step_sm; }
 
 }  // namespace
 
@@ -117,7 +121,7 @@ int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L) {
     L->oG = o; o += 21 + 13 + 2;                   // base Cholesky factor (21), base state: position 3, quaternion 4, omega 3, velocity 3
     L->oZ = o; o += ((n + 3) / 4) * 4;
     L->env_floats = ((o + 15) / 32) * 32 + 16;     // stride == 16 (mod 32 banks): the two environments of a warp (W = 16) hit disjoint bank halves
-    L->hot_floats = ((nl * kLkFloats + (nl * nl + nl * chain_len + 3) / 4 + 8 + 24 + 3) / 4) * 4;
+    L->hot_floats = kHdrFloats + ((nl * kLkFloats + (nl * nl + nl * chain_len + 3) / 4 + 3) / 4) * 4;
     return L->hot_floats * 4 + 0;
 }
 int dm_step_smem_bytes(const StepLayout& L, int tiles) { return (L.hot_floats + L.env_floats * tiles) * static_cast<int>(sizeof(float)); }
@@ -229,9 +233,14 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
 // rows, base Cholesky factor.  Output: impulses in sLam (also written to the persistent manifold), z = Y^T lambda in sZ.
 // Row ids in solver order: limits [0,NL) | normals [NL, NL+P) | friction pairs NL+P+2p+{0,1} (t1 = -x, t2 = +z).
 template <int W>
-__device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* LK, const unsigned char* CD, const unsigned char* CH, int lane, int NL, int P, float h,
-                                        float mu, float* mani, int alive, unsigned int* prf) {
+__device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, unsigned int* prf) {
     using T = Tl<W>;
+    // context from threadIdx and the block-shared header (nothing but scalars crosses the call, see Ctx below)
+    float* const sm_ = step_smem();
+    const int* LYS = reinterpret_cast<const int*>(sm_ + kHLayout);
+    const float* LK = sm_ + kHdrFloats;
+    const int lane = threadIdx.x % W;
+    const float h = sm_[kHh], mu = sm_[kHMu];
 #ifdef DM_PROFILE
     unsigned int pt = static_cast<unsigned int>(clock64());
 #define SPROF(sec) do { if ((threadIdx.x & 31) == 0) { unsigned int t_ = static_cast<unsigned int>(clock64()); prf[sec] += t_ - pt; pt = t_; } } while (0)
@@ -240,6 +249,9 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
 #endif
     const StepLayout& LY = *reinterpret_cast<const StepLayout*>(LYS);
     const int nl = LY.nl, CL = LY.chain_len, MR = LY.maxrows;
+    float* const E = sm_ + LY.hot_floats + (threadIdx.x / W) * LY.env_floats;
+    const unsigned char* CD = reinterpret_cast<const unsigned char*>(LK + nl * kLkFloats);
+    const unsigned char* CH = CD + nl * nl;
     float* sU = E + LY.oU; float* sS = E + LY.oR; float* sW = E + LY.oW; float* sV = E + LY.oV; float* sA = E + LY.oA; float* sY = E + LY.oY;
     float* sLam = E + LY.oLam; float* sRhs = E + LY.oRhs; float* sInv = E + LY.oInv; int* sRl = reinterpret_cast<int*>(E + LY.oRl);
     float* sPp = E + LY.oPp; float* sPi = E + LY.oPi; int* sPr = reinterpret_cast<int*>(E + LY.oPr);
@@ -461,7 +473,10 @@ __device__ __noinline__ void solve_rows(float* E, const int* LYS, const float* L
 }
 
 
-// ---- per-lane context handed to the phase routines (all in registers)
+// ---- per-lane context of the phase routines.  The routines are real calls (__noinline__: each gets the whole register budget), and a struct
+// passed by value to a real call travels through the caller's local-memory stack: every field access in the callee was a local load (the
+// ncu capture of round 2 showed 28 % of the stall samples on those).  So nothing is passed: a routine rebuilds its context from threadIdx and
+// the block-shared tables (two LDS), and the launch constants (layout, gravity, h, ...) sit in a header in front of the link table.
 struct Ctx {
     float* E;              // this environment's shared-memory block
     const int* LYS;        // layout (shared copy of StepLayout)
@@ -472,14 +487,26 @@ struct Ctx {
     bool act;
 };
 __device__ __forceinline__ const StepLayout& lay_of(const Ctx& c) { return *reinterpret_cast<const StepLayout*>(c.LYS); }
-// The phase routines are real calls (__noinline__), so the compiler cannot see that the context's pointers address shared memory and would emit
-// generic LD / ST for them; these address-space hints turn them back into LDS / STS.
-#ifndef DM_NO_SHARED_HINTS   // `make nohints` builds the A/B library without them (libdeepmimic_b200_nohints.so, select with DM_LIB)
-#define DM_ASSUME_SHARED_CTX(c) do { __builtin_assume(__isShared((c).E)); __builtin_assume(__isShared((c).LYS)); __builtin_assume(__isShared((c).LK)); \
-                                     __builtin_assume(__isShared((c).LVC)); } while (0)
-#else
+template <int W>
+__device__ __forceinline__ Ctx make_ctx() {
+    Ctx c;
+    float* sm = step_smem();
+    c.LYS = reinterpret_cast<const int*>(sm + kHLayout); c.LVC = reinterpret_cast<const int*>(sm + kHLvc); c.LK = sm + kHdrFloats;
+    const StepLayout& LY = *reinterpret_cast<const StepLayout*>(c.LYS);
+    const int tile = threadIdx.x / W;
+    c.lane = threadIdx.x % W;
+    c.act = c.lane < LY.nl;
+    c.li = c.act ? c.lane : LY.nl - 1;
+    c.E = sm + LY.hot_floats + tile * LY.env_floats;
+    const int* q = reinterpret_cast<const int*>(c.LK + c.li * kLkFloats);
+    const int info = q[kLInt], tree = q[kLTree];
+    const int par = static_cast<int>(static_cast<signed char>(info & 0xff));
+    c.plane = par >= 0 ? par : 0; c.jtype = (info >> 8) & 0xff; c.ndof = c.act ? ((info >> 16) & 0xff) : 0;
+    c.level = c.act ? (tree & 0xff) : 1000; c.maxlevel = (tree >> 8) & 0xff; c.nchild = c.act ? ((tree >> 16) & 0xff) : 0;
+    c.child_pack = q[kLChild];
+    return c;
+}
 #define DM_ASSUME_SHARED_CTX(c) do { } while (0)
-#endif
 __device__ __forceinline__ S6 shift_m(S6 m, V3 c) { return mks(m.a, m.l + cross(m.a, c)); }   // motion vector: reference point moved by +c
 __device__ __forceinline__ S6 shift_f(S6 f, V3 c) { return mks(f.a + cross(c, f.l), f.l); }   // force vector: child pivot -> parent pivot (child = parent + c)
 __device__ __forceinline__ float cl100(float v) { return fminf(fmaxf(v, -100.f), 100.f); }   // applyDeltaVeeMultiDof clamp
@@ -498,7 +525,8 @@ __device__ __forceinline__ V3 tile_com(const float* w, const float* v, float mas
 // Forward kinematics and link velocities, root -> leaves.  Writes per link: world->link rotation + pivot (sW), joint axes in world axes +
 // parent pivot -> pivot (sS), spatial velocity at the pivot + pivot -> COM (sV).  Base state is read from sB by lane 0.
 template <int W>
-__device__ __noinline__ void kin_pass(Ctx c, float4 jp, float4 jv) {
+__device__ __noinline__ void kin_pass(float4 jp, float4 jv) {
+    const Ctx c = make_ctx<W>();
     using T = Tl<W>;
     DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
@@ -556,7 +584,9 @@ __device__ __noinline__ void kin_pass(Ctx c, float4 jp, float4 jv) {
 // memory; the points of the environment are published to shared memory for the row builder.
 // Returns P | in_contact_tol << 8 | overflow << 9.
 template <int W>
-__device__ __noinline__ int collide(Ctx c, float* mani, int alive, float scale) {
+__device__ __noinline__ int collide(float* mani, int alive) {
+    const Ctx c = make_ctx<W>();
+    const float scale = step_smem()[kHScale];
     using T = Tl<W>;
     DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
@@ -687,8 +717,9 @@ __device__ __noinline__ int collide(Ctx c, float* mani, int alive, float scale) 
 //   root -> leaves: accelerations.  Bullet sub-steps (bullet != 0) also publish the factors (sU, sG), advance the link velocities in sV
 //   and the base velocity in sB by h * acceleration.  Returns this link's joint accelerations.
 template <int W, bool DEBUG>
-__device__ __noinline__ float3 aba_solve(Ctx c, float g0, float g1, float g2, float kdt, int bullet, float jvx, float jvy, float jvz, float gx, float gy, float gz, float h,
-                                         float* dbg_acc) {
+__device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt, int bullet, float jvx, float jvy, float jvz, float* dbg_acc) {
+    const Ctx c = make_ctx<W>();
+    const float gx = step_smem()[kHGrav], gy = step_smem()[kHGrav + 1], gz = step_smem()[kHGrav + 2], h = step_smem()[kHh];
     using T = Tl<W>;
     DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
@@ -725,7 +756,7 @@ __device__ __noinline__ float3 aba_solve(Ctx c, float g0, float g1, float g2, fl
     }
     // ---- leaves -> root
     Art IA; S6 pA;
-    S6 U0, U1, U2; float inv0 = 0.f, inv1 = 0.f, inv2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;
+    float inv0 = 0.f, inv1 = 0.f, inv2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;
     {
         const float* wsel = LKo + (bullet ? kLWb : kLWd);
         float wl[6];
@@ -745,9 +776,11 @@ __device__ __noinline__ float3 aba_solve(Ctx c, float g0, float g1, float g2, fl
         const V3 hn = sym_mul(IA.ww, vel.a) + cross(md, vel.l), hf = mass * vel.l + cross(vel.a, md);
         const V3 an = sym_mul(IA.ww, ab.a) + cross(md, ab.l), af = mass * ab.l + cross(ab.a, md);
         pA = mks(an + cross(vel.a, hn) + cross(vel.l, hf), af + cross(vel.a, hf));
-        U0 = U1 = U2 = mks(mk3(0, 0, 0), mk3(0, 0, 0));
     }
-    auto eliminate = [&](V3 dir, float g, S6& Uo, float& invo, float& uo) {
+    // U_d = IA s_d goes straight to the environment's factor table (sU: read back by the acceleration pass below and, in the Bullet sub-steps,
+    // by the constraint rows and the velocity correction) instead of living in 18 registers across the leaves -> root loop
+    float* const uown = sU + c.lane * 24;
+    auto eliminate = [&](V3 dir, float g, int d, float& invo, float& uo) {
         const V3 Ua = sym_mul(IA.ww, dir), Ul = wvT_mul(IA.wv, dir);
         const float D = dot(dir, Ua) + kdt;
         const float inv = 1.0f / D;
@@ -758,29 +791,28 @@ __device__ __noinline__ float3 aba_solve(Ctx c, float g0, float g1, float g2, fl
         IA.wv[6] -= sa.z * Ul.x; IA.wv[7] -= sa.z * Ul.y; IA.wv[8] -= sa.z * Ul.z;
         IA.vv[0] -= sl.x * Ul.x; IA.vv[1] -= sl.x * Ul.y; IA.vv[2] -= sl.x * Ul.z; IA.vv[3] -= sl.y * Ul.y; IA.vv[4] -= sl.y * Ul.z; IA.vv[5] -= sl.z * Ul.z;
         pA.a += u * sa; pA.l += u * sl;
-        Uo = mks(Ua, Ul); invo = inv; uo = u;
+        float* uo_ = uown + 6 * d;
+        uo_[0] = Ua.x; uo_[1] = Ua.y; uo_[2] = Ua.z; uo_[3] = Ul.x; uo_[4] = Ul.y; uo_[5] = Ul.z;
+        invo = inv; uo = u;
     };
-    Art sd; S6 sf;
+    // (IA, pA) of a link are shifted to the parent's pivot IN PLACE once the link's own dofs are eliminated (the link no longer needs them about
+    // its own pivot), so that the parent reads them straight out of the child's registers: no second copy of the 21 + 6 values is alive.
 #pragma unroll 1
     for (int lv = c.maxlevel; lv >= 0; --lv) {
         if (c.level == lv) {
-            if (c.ndof == 3) { eliminate(S2, g2, U2, inv2, u2); eliminate(S1, g1, U1, inv1, u1); }
-            if (c.ndof >= 1) eliminate(S0, g0, U0, inv0, u0);
-        }
-        // express (IA, pA) about the parent's pivot: shift by c = cw:  B' = B + C V ; A' = A - B C + C B'^T   (C = [c]x)
-        {
+            if (c.ndof == 3) { eliminate(S2, g2, 2, inv2, u2); eliminate(S1, g1, 1, inv1, u1); }
+            if (c.ndof >= 1) eliminate(S0, g0, 0, inv0, u0);
+            // express (IA, pA) about the parent's pivot: shift by c = cw:  B' = B + C V ; A' = A - B C + C B'^T   (C = [c]x)
             const V3 v0 = mk3(IA.vv[0], IA.vv[1], IA.vv[2]), v1 = mk3(IA.vv[1], IA.vv[3], IA.vv[4]), v2 = mk3(IA.vv[2], IA.vv[4], IA.vv[5]);   // columns (= rows) of V
             const V3 b0 = mk3(IA.wv[0], IA.wv[1], IA.wv[2]), b1 = mk3(IA.wv[3], IA.wv[4], IA.wv[5]), b2 = mk3(IA.wv[6], IA.wv[7], IA.wv[8]);   // rows of B
             const V3 k0 = cross(cw, v0), k1 = cross(cw, v1), k2 = cross(cw, v2);   // columns of C V
             const V3 n0 = mk3(b0.x + k0.x, b0.y + k1.x, b0.z + k2.x), n1 = mk3(b1.x + k0.y, b1.y + k1.y, b1.z + k2.y), n2 = mk3(b2.x + k0.z, b2.y + k1.z, b2.z + k2.z);   // rows of B'
             const V3 p0 = cross(b0, cw), p1 = cross(b1, cw), p2 = cross(b2, cw);   // rows of B C
             const V3 q0 = cross(cw, n0), q1 = cross(cw, n1), q2 = cross(cw, n2);   // columns of C B'^T
-            sd.ww[0] = IA.ww[0] - p0.x + q0.x; sd.ww[1] = IA.ww[1] - p0.y + q1.x; sd.ww[2] = IA.ww[2] - p0.z + q2.x;
-            sd.ww[3] = IA.ww[3] - p1.y + q1.y; sd.ww[4] = IA.ww[4] - p1.z + q2.y; sd.ww[5] = IA.ww[5] - p2.z + q2.z;
-            sd.wv[0] = n0.x; sd.wv[1] = n0.y; sd.wv[2] = n0.z; sd.wv[3] = n1.x; sd.wv[4] = n1.y; sd.wv[5] = n1.z; sd.wv[6] = n2.x; sd.wv[7] = n2.y; sd.wv[8] = n2.z;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) sd.vv[k] = IA.vv[k];
-            sf = shift_f(pA, cw);
+            IA.ww[0] += q0.x - p0.x; IA.ww[1] += q1.x - p0.y; IA.ww[2] += q2.x - p0.z;
+            IA.ww[3] += q1.y - p1.y; IA.ww[4] += q2.y - p1.z; IA.ww[5] += q2.z - p2.z;
+            IA.wv[0] = n0.x; IA.wv[1] = n0.y; IA.wv[2] = n0.z; IA.wv[3] = n1.x; IA.wv[4] = n1.y; IA.wv[5] = n1.z; IA.wv[6] = n2.x; IA.wv[7] = n2.y; IA.wv[8] = n2.z;
+            pA = shift_f(pA, cw);
         }
         if (lv == 0) break;
         const int nslot = c.LVC[lv - 1];
@@ -790,12 +822,12 @@ __device__ __noinline__ float3 aba_solve(Ctx c, float g0, float g1, float g2, fl
             const int src = chl >= 0 ? chl : c.lane;
             const bool take = chl >= 0 && c.level == lv - 1;
 #pragma unroll
-            for (int j = 0; j < 6; ++j) { float g = T::shfl(sd.ww[j], src); if (take) IA.ww[j] += g; }
+            for (int j = 0; j < 6; ++j) { float g = T::shfl(IA.ww[j], src); if (take) IA.ww[j] += g; }
 #pragma unroll
-            for (int j = 0; j < 9; ++j) { float g = T::shfl(sd.wv[j], src); if (take) IA.wv[j] += g; }
+            for (int j = 0; j < 9; ++j) { float g = T::shfl(IA.wv[j], src); if (take) IA.wv[j] += g; }
 #pragma unroll
-            for (int j = 0; j < 6; ++j) { float g = T::shfl(sd.vv[j], src); if (take) IA.vv[j] += g; }
-            const S6 gf = T::shfl6(sf, src);
+            for (int j = 0; j < 6; ++j) { float g = T::shfl(IA.vv[j], src); if (take) IA.vv[j] += g; }
+            const S6 gf = T::shfl6(pA, src);
             if (take) { pA.a += gf.a; pA.l += gf.l; }
         }
     }
@@ -804,9 +836,9 @@ __device__ __noinline__ float3 aba_solve(Ctx c, float g0, float g1, float g2, fl
     S6 aB = mks(mk3(0, 0, 0), mk3(0, 0, 0));
     if (c.lane == 0) {
         float a[6][6];   // lower triangle a[i][j], j <= i ; coordinates [w(3); v(3)]
-        a[0][0] = sd.ww[0]; a[1][0] = sd.ww[1]; a[1][1] = sd.ww[3]; a[2][0] = sd.ww[2]; a[2][1] = sd.ww[4]; a[2][2] = sd.ww[5];
-        a[3][0] = sd.wv[0]; a[3][1] = sd.wv[3]; a[3][2] = sd.wv[6]; a[4][0] = sd.wv[1]; a[4][1] = sd.wv[4]; a[4][2] = sd.wv[7]; a[5][0] = sd.wv[2]; a[5][1] = sd.wv[5]; a[5][2] = sd.wv[8];   // B'^T
-        a[3][3] = sd.vv[0]; a[4][3] = sd.vv[1]; a[4][4] = sd.vv[3]; a[5][3] = sd.vv[2]; a[5][4] = sd.vv[4]; a[5][5] = sd.vv[5];
+        a[0][0] = IA.ww[0]; a[1][0] = IA.ww[1]; a[1][1] = IA.ww[3]; a[2][0] = IA.ww[2]; a[2][1] = IA.ww[4]; a[2][2] = IA.ww[5];
+        a[3][0] = IA.wv[0]; a[3][1] = IA.wv[3]; a[3][2] = IA.wv[6]; a[4][0] = IA.wv[1]; a[4][1] = IA.wv[4]; a[4][2] = IA.wv[7]; a[5][0] = IA.wv[2]; a[5][1] = IA.wv[5]; a[5][2] = IA.wv[8];   // B'^T
+        a[3][3] = IA.vv[0]; a[4][3] = IA.vv[1]; a[4][4] = IA.vv[3]; a[5][3] = IA.vv[2]; a[5][4] = IA.vv[4]; a[5][5] = IA.vv[5];
         float gi[6];   // 1 / G_ii
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
@@ -824,7 +856,7 @@ __device__ __noinline__ float3 aba_solve(Ctx c, float g0, float g1, float g2, fl
             }
         }
         // x = -(G G^T)^-1 p
-        float x[6] = {-sf.a.x, -sf.a.y, -sf.a.z, -sf.l.x, -sf.l.y, -sf.l.z};
+        float x[6] = {-pA.a.x, -pA.a.y, -pA.a.z, -pA.l.x, -pA.l.y, -pA.l.z};
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
 #pragma unroll
@@ -854,9 +886,10 @@ __device__ __noinline__ float3 aba_solve(Ctx c, float g0, float g1, float g2, fl
     // ---- accelerations (root -> leaves): qdd_d = (u_d - U_d . a') / D_d
     float qd0 = 0.f, qd1 = 0.f, qd2 = 0.f;
     S6 al = mks(mk3(0, 0, 0), mk3(0, 0, 0));   // link acceleration (deviation from the bias acceleration)
+    auto udot = [&](S6 a, int d) { const float* q_ = uown + 6 * d; return a.a.x * q_[0] + a.a.y * q_[1] + a.a.z * q_[2] + a.l.x * q_[3] + a.l.y * q_[4] + a.l.z * q_[5]; };
     auto descend = [&](S6 a) {
-        if (c.ndof >= 1) { qd0 = inv0 * (u0 - sdot(a, U0)); a.a += qd0 * S0; }
-        if (c.ndof == 3) { qd1 = inv1 * (u1 - sdot(a, U1)); a.a += qd1 * S1; qd2 = inv2 * (u2 - sdot(a, U2)); a.a += qd2 * S2; }
+        if (c.ndof >= 1) { qd0 = inv0 * (u0 - udot(a, 0)); a.a += qd0 * S0; }
+        if (c.ndof == 3) { qd1 = inv1 * (u1 - udot(a, 1)); a.a += qd1 * S1; qd2 = inv2 * (u2 - udot(a, 2)); a.a += qd2 * S2; }
         return a;
     };
     if (c.lane == 0) al = descend(shift_m(aB, cw));
@@ -866,10 +899,7 @@ __device__ __noinline__ float3 aba_solve(Ctx c, float g0, float g1, float g2, fl
         if (c.level == lv) al = descend(shift_m(pa, cw));
     }
     if (bullet && c.act) {   // publish the factors and the advanced link velocity (linear in the generalised velocities; the clamp only acts on exploding states)
-        float* u = sU + c.lane * 24;
-        u[0] = U0.a.x; u[1] = U0.a.y; u[2] = U0.a.z; u[3] = U0.l.x; u[4] = U0.l.y; u[5] = U0.l.z;
-        u[6] = U1.a.x; u[7] = U1.a.y; u[8] = U1.a.z; u[9] = U1.l.x; u[10] = U1.l.y; u[11] = U1.l.z;
-        u[12] = U2.a.x; u[13] = U2.a.y; u[14] = U2.a.z; u[15] = U2.l.x; u[16] = U2.l.y; u[17] = U2.l.z;
+        float* u = sU + c.lane * 24;   // U0 U1 U2 are already there (eliminate)
         u[18] = inv0; u[19] = inv1; u[20] = inv2; u[21] = sqrtf(inv0); u[22] = sqrtf(inv1); u[23] = sqrtf(inv2);
         float* v = sV + c.lane * 12;
         v[0] = vel.a.x + h * al.a.x; v[1] = vel.a.y + h * al.a.y; v[2] = vel.a.z + h * al.a.z;
@@ -882,7 +912,8 @@ __device__ __noinline__ float3 aba_solve(Ctx c, float g0, float g1, float g2, fl
 // Velocity correction of the constraint impulses: dv = L^-1 D^-1/2 z with z = Y^T lambda (sZ), by the root -> leaves pass over the factors
 // published by aba_solve.  Lane 0 also corrects the base velocity in sB.  Returns this link's joint-rate corrections.
 template <int W>
-__device__ __noinline__ float3 dv_pass(Ctx c) {
+__device__ __noinline__ float3 dv_pass() {
+    const Ctx c = make_ctx<W>();
     using T = Tl<W>;
     DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
@@ -932,7 +963,8 @@ __device__ __noinline__ float3 dv_pass(Ctx c) {
 // Link velocities from the generalised velocities (root -> leaves), for the environments flagged by `want`.  Only needed when Bullet's
 // per-coordinate velocity clamp (maxCoordinateVelocity = 100) fired in the velocity update: otherwise aba_solve's v + h a is the same thing.
 template <int W>
-__device__ __noinline__ void vel_pass(Ctx c, float jvx, float jvy, float jvz, bool want) {
+__device__ __noinline__ void vel_pass(float jvx, float jvy, float jvz, bool want) {
+    const Ctx c = make_ctx<W>();
     using T = Tl<W>;
     DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
@@ -973,12 +1005,13 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     const bool act = lane < nl;
     const int li = act ? lane : nl - 1;
 
-    // ---- block-shared tables: per-link constants (LK), common chain depth of two links (CD), chain depth -> dof (CH), children per level
-    float* LK = sm;
-    unsigned char* CD = reinterpret_cast<unsigned char*>(sm + nl * kLkFloats);
+    // ---- block-shared header (layout, children per level, launch constants) and tables: per-link constants (LK), common chain depth of two
+    // links (CD), chain depth -> dof (CH)
+    float* LK = sm + kHdrFloats;
+    unsigned char* CD = reinterpret_cast<unsigned char*>(LK + nl * kLkFloats);
     unsigned char* CH = CD + nl * nl;
-    int* LVC = reinterpret_cast<int*>(sm + LY.hot_floats - 8);
-    int* LYS = reinterpret_cast<int*>(sm + LY.hot_floats - 8 - 24);   // shared copy of the layout for the phase routines
+    int* LVC = reinterpret_cast<int*>(sm + kHLvc);
+    int* LYS = reinterpret_cast<int*>(sm + kHLayout);   // shared copy of the layout for the phase routines
     for (int j = threadIdx.x; j < nl; j += blockDim.x) {
         const DevLink& K = M.link[j];
         float* q = LK + j * kLkFloats;
@@ -996,6 +1029,8 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         for (int k = 0; k < 3; ++k) q[kLHe + k] = K.he[k];
         q[kLThr] = K.break_thr; q[kLKp] = K.kp; q[kLKd] = K.kd; q[kLTl] = K.tlim; q[kLLo] = K.lim_lo; q[kLHi] = K.lim_hi;
         reinterpret_cast<int*>(q)[kLFlg] = (K.shape & 0xff) | ((K.fall_contact & 0xff) << 8) | ((K.has_limit & 0xff) << 16);
+        reinterpret_cast<int*>(q)[kLTree] = (K.level & 0xff) | ((M.maxlevel & 0xff) << 8) | ((K.nchild & 0xff) << 16);
+        reinterpret_cast<int*>(q)[kLChild] = (K.child[0] & 0xff) | ((K.child[1] & 0xff) << 8) | ((K.child[2] & 0xff) << 16) | ((K.child[3] & 0xff) << 24);
         for (int d = 0; d < CL; ++d) CH[j * CL + d] = M.chain_dof[j][d];
         for (int b = 0; b < nl; ++b) {
             int cnt = 0;
@@ -1005,8 +1040,11 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         }
     }
     if (threadIdx.x == blockDim.x - 1) {
+        static_assert(sizeof(StepLayout) / sizeof(int) <= kHLvc, "StepLayout must fit the header slot");
         const int* src = reinterpret_cast<const int*>(&LY);
         for (int k = 0; k < static_cast<int>(sizeof(StepLayout) / sizeof(int)); ++k) LYS[k] = src[k];
+        sm[kHGrav] = M.gravity[0]; sm[kHGrav + 1] = M.gravity[1]; sm[kHGrav + 2] = M.gravity[2];
+        sm[kHh] = static_cast<float>(dt) / static_cast<float>(sim_substeps); sm[kHScale] = M.scale; sm[kHMu] = M.friction; sm[kHFdt] = static_cast<float>(dt);
     }
     if (threadIdx.x < 8) {
         int mx = 0;
@@ -1015,19 +1053,10 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     }
     __syncthreads();
 
-    Ctx C;
-    {
-        const DevLink& L = M.link[li];
-        C.E = sm + LY.hot_floats + tile * LY.env_floats; C.LYS = LYS; C.LK = LK; C.LVC = LVC;
-        C.lane = lane; C.li = li; C.plane = L.parent >= 0 ? L.parent : 0; C.level = act ? L.level : 1000; C.ndof = act ? L.ndof : 0; C.jtype = L.jtype;
-        C.nchild = act ? L.nchild : 0;
-        C.child_pack = (L.child[0] & 0xff) | ((L.child[1] & 0xff) << 8) | ((L.child[2] & 0xff) << 16) | ((L.child[3] & 0xff) << 24);
-        C.maxlevel = M.maxlevel; C.act = act;
-    }
-    float* E = C.E;
+    float* E = sm + LY.hot_floats + tile * LY.env_floats;
     float* sV = E + LY.oV; float* sG = E + LY.oG; float* sQ = E + LY.oQ; float* sLam = E + LY.oLam;
     const float* LKo = LK + li * kLkFloats;
-    const int ndof = C.ndof, jtype = C.jtype;
+    const int jtype = (reinterpret_cast<const int*>(LKo)[kLInt] >> 8) & 0xff, ndof = act ? ((reinterpret_cast<const int*>(LKo)[kLInt] >> 16) & 0xff) : 0;
     const int dof0 = reinterpret_cast<const int*>(LKo)[kLInt2] & 0xff;
     const int lflags = reinterpret_cast<const int*>(LKo)[kLFlg];
     const bool fall_contact = ((lflags >> 8) & 0xff) != 0, has_limit = ((lflags >> 16) & 0xff) != 0;
@@ -1092,7 +1121,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             asm volatile("prefetch.global.L1 [%0];" ::"l"(mp_ + 32));
         }
         // =================================================================== forward kinematics + link velocities
-        if (need_kin) { need_kin = false; kin_pass<W>(C, jp, jv); }
+        if (need_kin) { need_kin = false; kin_pass<W>(jp, jv); }
         PROF(0);
         // =================================================================== post-update flags of the update that just finished
         if (pending_flags) {
@@ -1279,7 +1308,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             }
             const float kp = LKo[kLKp], kd = LKo[kLKd];
             const float pe0 = kp * e0, pe1 = kp * e1, pe2 = kp * e2;
-            const float3 qdd = aba_solve<W, DEBUG>(C, pe0 - kd * jv.x, pe1 - kd * jv.y, pe2 - kd * jv.z, fdt * kd, 0, jv.x, jv.y, jv.z, gx, gy, gz, h, nullptr);
+            const float3 qdd = aba_solve<W, DEBUG>(pe0 - kd * jv.x, pe1 - kd * jv.y, pe2 - kd * jv.z, fdt * kd, 0, jv.x, jv.y, jv.z, nullptr);
             // ---------------- torques: tau = Kp e + Kd (edot - dt a), clamped by norm (cSimBodyJoint::ClampTotalTorque, SimBodyJoint.cpp:299-307)
             float t0 = 0, t1 = 0, t2 = 0;
             if (ndof >= 1) t0 = pe0 + kd * (-jv.x - fdt * qdd.x);
@@ -1299,13 +1328,13 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         const int sub = ph - 1;
         int P;
         {
-            const int r = collide<W>(C, mani, alive ? 1 : 0, scale);
+            const int r = collide<W>(mani, alive ? 1 : 0);
             P = r & 0xff; in_contact_tol = ((r >> 8) & 1) != 0; if (r >> 9) f_over = 1;
         }
         PROF(3);
         {   // unconstrained accelerations, v += a h (the base and the link velocities are advanced inside)
             float* dacc = (DEBUG && dbg && first_upd) ? dbg + (sub == 0 ? 4 * kMaxDofs : 8 * kMaxDofs + 1024) : nullptr;
-            const float3 qdd = aba_solve<W, DEBUG>(C, tau0, tau1, tau2, 0.f, 1, jv.x, jv.y, jv.z, gx, gy, gz, h, dacc);
+            const float3 qdd = aba_solve<W, DEBUG>(tau0, tau1, tau2, 0.f, 1, jv.x, jv.y, jv.z, dacc);
             if (DEBUG && dacc) { if (ndof >= 1) dacc[dof0] = qdd.x; if (ndof == 3) { dacc[dof0 + 1] = qdd.y; dacc[dof0 + 2] = qdd.z; } }
             bool hit = false;   // a generalised velocity reached Bullet's clamp: the link velocities must be rebuilt from the clamped values
             if (ndof >= 1) { const float v = jv.x + h * qdd.x; jv.x = cl100(v); hit |= fabsf(v) > 100.f; }
@@ -1314,7 +1343,7 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
             const unsigned hb = __ballot_sync(0xffffffffu, hit);
             if (hb != 0u) {
                 const unsigned hseg = (W == 32) ? hb : ((hb >> (threadIdx.x & 16)) & 0xffffu);
-                vel_pass<W>(C, jv.x, jv.y, jv.z, hseg != 0u);
+                vel_pass<W>(jv.x, jv.y, jv.z, hseg != 0u);
             }
             if (DEBUG && dbg && first_upd) {
                 const int o = (sub == 0 ? 5 * kMaxDofs : 9 * kMaxDofs + 1024);
@@ -1348,9 +1377,9 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
 #ifdef DM_PROFILE
             { const int nrm = wmax(NR); if ((threadIdx.x & 31) == 0) { PRF[13] += nrm; PRF[14] += 1; if (nrm > W) PRF[15] += 1; } }
 #endif
-            solve_rows<W>(E, LYS, LK, CD, CH, lane, NL, P, h, mu, mani, alive ? 1 : 0, PRFP);
+            solve_rows<W>(NL, P, mani, alive ? 1 : 0, PRFP);
             PROF(10);
-            const float3 dq = dv_pass<W>(C);
+            const float3 dq = dv_pass<W>();
             if (NR > 0) {
                 if (ndof >= 1) jv.x = cl100(jv.x + dq.x);
                 if (ndof == 3) { jv.y = cl100(jv.y + dq.y); jv.z = cl100(jv.z + dq.z); }

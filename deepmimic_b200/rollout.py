@@ -185,7 +185,12 @@ def load_actor_weights(policy, actor):
 
 
 class BatchedRollout:
-    def __init__(self, env, policy=None, exp_rate=1.0, noise=0.05, seed=0):
+    """backend "torch": the policy is a torch module (cuBLAS GEMMs, eager normalisers) -- needed for training and for the gated task actor.
+    backend "tcgen05": inference of the plain 2-layer actor on the library's own tensor-core kernels (dm_mlp_*, kernels/dm_mlp.cu): normaliser,
+    three GEMMs, bias / ReLU and the action un-normalisation in three launches on the environment's stream; the weights and the normaliser
+    statistics are snapshotted by refresh_tensor_core_policy() (call it again after a learner update)."""
+
+    def __init__(self, env, policy=None, exp_rate=1.0, noise=0.05, seed=0, backend="torch"):
         import torch
         self.torch, self.env = torch, env
         dev = env.device
@@ -202,6 +207,39 @@ class BatchedRollout:
         self.a_norm.set_mean_std(-env.build_action_offset(), 1.0 / env.build_action_scale())
         self.exp_rate = exp_rate
         self.gen = torch.Generator(device=dev); self.gen.manual_seed(seed)
+        self.backend, self._tc = backend, None
+        if backend not in ("torch", "tcgen05"):
+            raise ValueError("backend must be 'torch' or 'tcgen05'")
+        if backend == "tcgen05" and G > 0:
+            raise ValueError("the tcgen05 backend implements the plain 2-layer actor; goal-conditioned (gated) actors run on the torch backend")
+
+    def refresh_tensor_core_policy(self):
+        """(re)builds the dm_mlp handle from the current torch policy and normalisers"""
+        from .capi import TensorCoreMLP
+        pol, env = self.policy, self.env
+        if len(pol.hidden) != 2:
+            raise ValueError("the tcgen05 backend implements exactly two hidden layers")
+        g = lambda t: t.detach().float().cpu().numpy()
+        if self._tc is not None:
+            self._tc.close()
+        self._tc = TensorCoreMLP(g(pol.hidden[0].weight).T, g(pol.hidden[0].bias), g(pol.hidden[1].weight).T, g(pol.hidden[1].bias), g(pol.mean.weight).T, g(pol.mean.bias),
+                                 in_mean=g(self.s_norm.mean), in_std=g(self.s_norm.std), in_clip=self.s_norm.clip, out_mean=g(self.a_norm.mean), out_std=g(self.a_norm.std),
+                                 max_rows=env.num_envs, device=env.device.index or 0)
+        self._tc_act = self.torch.empty(env.num_envs, env.get_action_size(), device=env.device)
+        return self._tc
+
+    def _act_tensor_core(self, s, explore):
+        """un-normalised actions and log-probabilities from the tensor-core actor (exploration noise is drawn in torch, added in the kernel's epilogue)"""
+        t = self.torch
+        if self._tc is None:
+            self.refresh_tensor_core_policy()
+        std = self.policy.logstd.detach().exp()
+        eps = t.randn(s.shape[0], std.shape[0], device=s.device, generator=self.gen) * explore[:, None].to(s.dtype)
+        noise = (std * eps).contiguous()
+        cur = t.cuda.current_stream(s.device)
+        self._tc.forward(s.contiguous(), self._tc_act, noise=noise, stream=cur.cuda_stream)
+        logp = (-0.5 * eps * eps - self.policy.logstd.detach() - 0.5 * math.log(2 * math.pi)).sum(dim=-1)
+        return self._tc_act, logp
 
     @property
     def stream(self):
@@ -230,9 +268,12 @@ class BatchedRollout:
                     if record_stats:
                         self.g_norm.record(g)
                     na, logp = self.policy.sample(self.s_norm.normalize(s), self.g_norm.normalize(g), explore, self.gen)
+                elif self.backend == "tcgen05":
+                    a, logp = self._act_tensor_core(s, explore)
                 else:
                     na, logp = self.policy.sample(self.s_norm.normalize(s), explore, self.gen)
-                a = self.a_norm.unnormalize(na).contiguous()
+                if not (G == 0 and self.backend == "tcgen05"):
+                    a = self.a_norm.unnormalize(na).contiguous()
                 s, r, done, term = env.step(a)
                 out["actions"][k] = a; out["logps"][k] = logp; out["rewards"][k] = r; out["dones"][k] = done; out["terminate"][k] = term
                 env.reset()                # restarts exactly the finished episodes

@@ -157,6 +157,19 @@ int dm_exchange_release(dm_handle* h, long long step);
 int dm_exchange_status(dm_handle* h, int* status);
 int dm_exchange_destroy(dm_handle* h);
 
+/* ---- policy network of the batched rollout on the Blackwell tensor cores (R/learning/nets/fc_2layers_1024units.py,
+ * R/learning/pg_agent.py:140-160, R/learning/normalizer.py): actions = a_mean + a_std * (W2^T relu(W1^T relu(W0^T clip((s - s_mean) / s_std)
+ * + b0) + b1) + b2 [+ noise]).  Weights are the reference's dense kernels, [inputs x units] row major, fp32 on the host; they are tiled once
+ * into the tcgen05 operand layout as fp16 hi + lo pairs (exact to fp32 level).  d_obs [rows x in_dim], d_noise [rows x out_dim] or NULL,
+ * d_actions [rows x out_dim], all fp32 device pointers; `stream` is a cudaStream_t (e.g. dm_stream(h)); out_dim <= 64. */
+typedef struct dm_mlp dm_mlp;
+dm_mlp* dm_mlp_create(int device, int in_dim, int h0, int h1, int out_dim, const float* h_w0, const float* h_b0, const float* h_w1, const float* h_b1,
+                      const float* h_w2, const float* h_b2, const float* h_in_mean, const float* h_in_std, float in_clip, const float* h_out_mean,
+                      const float* h_out_std, int max_rows);
+int dm_mlp_forward(dm_mlp* m, const float* d_obs, const float* d_noise, float* d_actions, int rows, void* stream);
+long long dm_mlp_launches(dm_mlp* m);
+void dm_mlp_destroy(dm_mlp* m);
+
 /* ---- test hooks: raw per-env simulator state, layout shared with the CPU oracle (doubles):
  *  [0..2] basePos(scaled) [3..6] baseQuat world->base (x,y,z,w) [7..9] baseOmega [10..12] baseVel(scaled)
  *  [13 + 4j ..] jointPos(j)  [13 + 4nl + 3j ..] jointVel(j)
