@@ -21,6 +21,7 @@
 // register budget and the main loop only carries the joint state of its link.
 // No tensor cores: there is no dense contraction here (34 or 70 dofs, tree-sparse); the path is latency-bound.
 #include "dm_model.cuh"
+#include <type_traits>
 
 namespace dmk {
 
@@ -114,7 +115,7 @@ int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L) {
     L->oW = o; L->oV = o + nl * 12;
     o += (world > tri ? world : tri);
     L->oY = o; o += chain_len * maxrows;           // Yt[depth][row]
-    L->oLam = o; o += maxrows; L->oRhs = o; o += maxrows; L->oInv = o; o += maxrows;
+    L->oLam = o; o += maxrows; o += (o & 1); L->oRhs = o; o += maxrows; L->oInv = o; o += maxrows;   // oRhs .. : interleaved (rhs, 1 / A_ii) pairs, 8-byte aligned
     L->oRl = o; o += maxrows;                      // row -> link (int)
     L->oPp = o; o += maxpts * 4; L->oPi = o; o += maxpts; L->oPr = o; o += maxpts;
     L->oQ = o; o += 4 * 8;                         // limit rows: link, dir, penetration, joint rate (<= 8)
@@ -126,106 +127,114 @@ int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L) {
 }
 int dm_step_smem_bytes(const StepLayout& L, int tiles) { return (L.hot_floats + L.env_floats * tiles) * static_cast<int>(sizeof(float)); }
 
+#ifndef DM_PGS_BLOCK
+#define DM_PGS_BLOCK 2   // solver steps evaluated per block of the projected Gauss-Seidel sweeps (measured on a B200: 1 -> 1.22 M, 2 -> 1.49 M, 4 -> 1.32 M, 8 -> 0.95 M policy steps/s)
+#endif
 // Projected Gauss-Seidel in impulse space, 10 sweeps in btMultiBodyConstraintSolver::solveSingleIteration's row order (joint limits in
-// alternating order, contact normals, friction pairs), lanes = rows: every lane keeps its rows' right-hand side, 1 / A_ii, impulse, bounds
-// and w = (A lambda)_row in registers (S rows per lane: row = lane + s W).  One sequential row update is
-//     every lane evaluates the update of ITS OWN rows from its own w (no data from other lanes),
-//     the update of the row whose turn it is is broadcast by one shuffle, its owner commits its impulse,
-//     every lane adds A(row, i) * delta to its w's (A: symmetric W x W square when S == 1, packed lower triangle otherwise).
-// Same arithmetic in the same order as Bullet's row-by-row sweep (resolveSingleConstraintRowGeneric: delta = rhs - w * jacDiagABInv, clamped sum,
-// delta replaced only when the sum was clamped; friction bounds +-mu * the point's current normal impulse, row skipped while that is <= 0),
-// but the dependent chain of a row is ~6 ALU operations + one shuffle + one FMA.  The two environments of a W = 16 warp run in lockstep, each
-// with its own row numbering (the shuffles are tile-wide).  tj: per-slot triangle offsets rid (rid + 1) / 2 of the packed storage (S > 1).
-template <int W, int S, bool SQUARE>
-__device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const float* sRhs, const float* sInv, const int* tj, int lane, int NL, int P, int NR,
-                                           int NLmax, int Pmax, float mu) {
+// alternating order, contact normals, friction pairs).  Lanes = rows for the state that is wide: every lane keeps w = (A lambda)_row of ITS rows in
+// registers (S rows per lane: row = lane + s W).  The sequential part is evaluated in blocks of B consecutive solver steps of one section:
+//     B independent shuffles fetch the block's w values from their owners; the rows' right-hand side, 1 / A_ii and impulse are broadcast loads,
+//     EVERY lane then evaluates the B sequential Gauss-Seidel updates redundantly (row k+1 sees row k's update through A(k+1, k), B (B-1) / 2
+//     broadcast entries of A), one lane per row commits the new impulse to shared memory,
+//     and every lane adds A(own row, row_k) * delta_k, k = 0..B-1 in order, to its own w's.
+// During the sweeps the warps of a block are issue-bound (3.5 warps per scheduler all inside this loop), so the figure of merit is warp
+// instructions per solver step: ~40 with one shuffle per step (the owner computed and broadcast its update), ~20 here.  Every floating-point
+// operation on w and the update, and their order, are those of the row-by-row sweep (resolveSingleConstraintRowGeneric: delta = rhs - w *
+// jacDiagABInv, clamped sum; friction bounds +-mu * the point's current normal impulse, row skipped while that is <= 0).  Bounds are applied to
+// the UPDATE: clamp(delta, lo - lambda, hi - lambda) equals Bullet's "clamp the sum, then delta = limit - applied" in every branch; the stored
+// impulse is clamp(lambda + delta, lo, hi) (Bullet stores the limit itself when clamped: equal up to one rounding of lambda + (limit - lambda)).
+// The two environments of a W = 16 warp run in lockstep, each with its own row numbering (shuffles are tile-wide).
+// A: symmetric W x W square when S == 1, packed lower triangle otherwise.  sRI: (rhs, 1 / A_ii) pairs.  NLmax / Pmax: warp-wide maxima of NL / P
+// (block loops are warp-uniform).
+enum PgsSection { kSecLimit = 0, kSecNormal = 1, kSecFriction = 2 };
+template <int W, int S, bool SQUARE, int B>
+__device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const float2* sRI, int lane, int NL, int P, int NLmax, int Pmax, float mu) {
     using T = Tl<W>;
-    // per row (S rows per lane): w = (A lambda)_row, impulse, rhs, -1 / A_ii, bounds, and the bounds expressed on the UPDATE: dlo = lo - lambda,
-    // dhi = hi - lambda.  Clamping the update to [dlo, dhi] is Bullet's "clamp the sum, then delta = limit - applied" (the two produce the same
-    // delta in every branch: unclamped -> d itself, clamped -> limit - applied) with a dependent chain of FFMA, FMNMX, FMNMX per row instead
-    // of seven operations; dlo / dhi are refreshed off the chain by the row's owner.  A skipped friction row has dlo = dhi = 0.
-    float w[S], lam[S], rhs[S], ninv[S], lo[S], hi[S], dlo[S], dhi[S];
-    int nrow[S];       // friction rows: solver row of the point's normal; -1 otherwise
-    bool live[S];
+    float w[S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-        const int rid = lane + s * W;
-        live[s] = rid < NR;
-        const int r = live[s] ? rid : 0;
-        w[s] = 0.f; lam[s] = live[s] ? sLam[r] : 0.f; rhs[s] = live[s] ? sRhs[r] : 0.f; ninv[s] = live[s] ? -sInv[r] : 0.f;
-        nrow[s] = -1; lo[s] = 0.f; hi[s] = 1e10f;                       // contact normals: [0, inf)
-        if (rid < NL) hi[s] = 100.f;                                     // joint limits: [0, 100]
-        dlo[s] = lo[s] - lam[s]; dhi[s] = hi[s] - lam[s];
-        if (rid >= NL + P && live[s]) { nrow[s] = NL + ((rid - NL - P) >> 1); dlo[s] = dhi[s] = 0.f; }   // friction: bounds set per sweep
-        if (!live[s]) dlo[s] = dhi[s] = 0.f;
-    }
-    auto a_of = [&](int s, int i) -> float {   // A(lane + s W, i)
+    for (int s = 0; s < S; ++s) w[s] = 0.f;
+    // A(lane + s W, i).  Lanes without a row read finite leftovers of the scratch region: their w is never fetched.
+    auto a_own = [&](int s, int i) -> float {
         if (SQUARE) return sA[i * W + lane];
         const int rid = lane + s * W;
-        return sA[(rid >= i) ? (tj[s] + i) : (i * (i + 1) / 2 + rid)];
+        return sA[(rid >= i) ? (rid * (rid + 1) / 2 + i) : (i * (i + 1) / 2 + rid)];
     };
-    // one sequential row update; i: this tile's row (tile-uniform), valid: the row exists in this tile
-    auto row_step = [&](int i, bool valid) {
-        float a[S], c[S];
-#pragma unroll
-        for (int s = 0; s < S; ++s) a[s] = live[s] ? a_of(s, i) : 0.f;           // independent of the chain: issued first
-#pragma unroll
-        for (int s = 0; s < S; ++s) c[s] = fminf(fmaxf(fmaf(ninv[s], w[s], rhs[s]), dlo[s]), dhi[s]);
-        float sel = c[0];
-#pragma unroll
-        for (int s = 1; s < S; ++s) if (i >= s * W) sel = c[s];
-        float dI = T::shfl(sel, i & (W - 1));
-        dI = valid ? dI : 0.f;
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            w[s] = fmaf(a[s], dI, w[s]);
-            if (valid && lane + s * W == i) {      // the owner commits: applied impulse = the limit itself when clamped (Bullet), else applied + delta
-                lam[s] = (c[s] == dlo[s] && c[s] != dhi[s]) ? lo[s] : ((c[s] == dhi[s] && c[s] != dlo[s]) ? hi[s] : lam[s] + c[s]);
-                if (nrow[s] < 0 || dlo[s] != dhi[s]) { dlo[s] = lo[s] - lam[s]; dhi[s] = hi[s] - lam[s]; }
-            }
-        }
+    auto a_pair = [&](int i, int j) -> float {   // A(i, j), tile-uniform indices
+        if (SQUARE) return sA[i * W + j];
+        const int hi_ = max(i, j), lo_ = min(i, j);
+        return sA[hi_ * (hi_ + 1) / 2 + lo_];
     };
     // warm start: w = A lambda0 (normals carry 0.85 x the cached impulse, everything else starts at 0), in point order
 #pragma unroll 1
     for (int p = 0; p < Pmax; ++p) {
         const int i = NL + ((p < P) ? p : 0);
-        float sel = lam[0];
+        const float l0 = (p < P) ? sLam[i] : 0.f;
 #pragma unroll
-        for (int s = 1; s < S; ++s) if (i >= s * W) sel = lam[s];
-        float l0 = T::shfl(sel, i & (W - 1));
-        if (!(p < P)) l0 = 0.f;
-#pragma unroll
-        for (int s = 0; s < S; ++s) if (live[s] && l0 != 0.f) w[s] += a_of(s, i) * l0;
+        for (int s = 0; s < S; ++s) w[s] = fmaf(a_own(s, i), l0, w[s]);
     }
+    // one block of B consecutive solver steps of section SEC, starting at position pos0 of the section
+    auto block = [&](int pos0, int it, auto sec_tag) {
+        constexpr int SEC = decltype(sec_tag)::value;
+        int ik[B]; bool vk[B];
+        float tot = 0.f;
+        float wk[B], rhs[B], inv[B], lam[B], lo[B], hi[B], ain[B * (B - 1) / 2 > 0 ? B * (B - 1) / 2 : 1], ao[S][B];
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const int pos = pos0 + k;
+            if (SEC == kSecLimit) { vk[k] = pos < NL; ik[k] = vk[k] ? ((it & 1) ? pos : NL - 1 - pos) : 0; }
+            else if (SEC == kSecNormal) { vk[k] = pos < P; ik[k] = vk[k] ? NL + pos : 0; }
+            else { vk[k] = pos < 2 * P; ik[k] = vk[k] ? NL + P + pos : 0; }
+        }
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const float2 ri = sRI[ik[k]];
+            rhs[k] = ri.x; inv[k] = ri.y; lam[k] = sLam[ik[k]];
+            if (SEC == kSecFriction) {
+                // the point's normal impulse of this sweep; the two friction rows of a point are consecutive: one load per pair when B is even
+                if ((B & 1) != 0 || (k & 1) == 0) tot = sLam[vk[k] ? NL + ((pos0 + k) >> 1) : 0];
+                const bool on = tot > 0.f;
+                hi[k] = on ? mu * tot : lam[k]; lo[k] = on ? -hi[k] : lam[k];   // normal impulse not positive: the row is skipped
+            } else { lo[k] = 0.f; hi[k] = (SEC == kSecLimit) ? 100.f : 1e10f; }     // joint limits [0, 100], contact normals [0, inf)
+        }
+        {
+            int o = 0;
+#pragma unroll
+            for (int k = 1; k < B; ++k)
+#pragma unroll
+                for (int j = 0; j < k; ++j) ain[o++] = a_pair(ik[k], ik[j]);
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int k = 0; k < B; ++k) ao[s][k] = a_own(s, ik[k]);
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            float sel = w[0];
+#pragma unroll
+            for (int s = 1; s < S; ++s) if (ik[k] >= s * W) sel = w[s];
+            wk[k] = T::shfl(sel, ik[k] & (W - 1));
+        }
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            float c = fminf(fmaxf(fmaf(-inv[k], wk[k], rhs[k]), lo[k] - lam[k]), hi[k] - lam[k]);
+            c = vk[k] ? c : 0.f;
+#pragma unroll
+            for (int j = k + 1; j < B; ++j) wk[j] = fmaf(ain[j * (j - 1) / 2 + k], c, wk[j]);
+            if (vk[k] && lane == k) sLam[ik[k]] = fminf(fmaxf(lam[k] + c, lo[k]), hi[k]);
+#pragma unroll
+            for (int s = 0; s < S; ++s) w[s] = fmaf(ao[s][k], c, w[s]);
+        }
+        __syncwarp();
+    };
 #pragma unroll 1
     for (int it = 0; it < 10; ++it) {
 #pragma unroll 1
-        for (int u = 0; u < NLmax; ++u) { const bool valid = u < NL; row_step(valid ? ((it & 1) ? u : NL - 1 - u) : 0, valid); }
+        for (int p0 = 0; p0 < NLmax; p0 += B) block(p0, it, std::integral_constant<int, kSecLimit>{});
 #pragma unroll 1
-        for (int p = 0; p < Pmax; ++p) row_step(NL + ((p < P) ? p : 0), p < P);
-        // friction bounds from the normal impulses of this sweep: +-mu * lambda_n; a point whose normal impulse is not positive skips its friction rows
-        {
-            float tot[S];
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-                const int n = nrow[s] >= 0 ? nrow[s] : 0;
-                float v = T::shfl(lam[0], n & (W - 1));
-#pragma unroll
-                for (int q = 1; q < S; ++q) { const float vq = T::shfl(lam[q], n & (W - 1)); if (n >= q * W) v = vq; }
-                tot[s] = v;
-            }
-#pragma unroll
-            for (int s = 0; s < S; ++s) if (nrow[s] >= 0) {
-                if (tot[s] > 0.f) { hi[s] = mu * tot[s]; lo[s] = -hi[s]; dlo[s] = lo[s] - lam[s]; dhi[s] = hi[s] - lam[s]; }
-                else dlo[s] = dhi[s] = 0.f;
-            }
-        }
+        for (int p0 = 0; p0 < Pmax; p0 += B) block(p0, it, std::integral_constant<int, kSecNormal>{});
 #pragma unroll 1
-        for (int f = 0; f < 2 * Pmax; ++f) row_step(NL + P + ((f < 2 * P) ? f : 0), f < 2 * P);
+        for (int p0 = 0; p0 < 2 * Pmax; p0 += B) block(p0, it, std::integral_constant<int, kSecFriction>{});
     }
-#pragma unroll
-    for (int s = 0; s < S; ++s) if (live[s]) sLam[lane + s * W] = lam[s];
-    __syncwarp();
 }
 
 // Constraint rows of one Bullet sub-step for the environment owned by this tile (warp-collective; both environments of a W = 16 warp
@@ -253,7 +262,7 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
     const unsigned char* CD = reinterpret_cast<const unsigned char*>(LK + nl * kLkFloats);
     const unsigned char* CH = CD + nl * nl;
     float* sU = E + LY.oU; float* sS = E + LY.oR; float* sW = E + LY.oW; float* sV = E + LY.oV; float* sA = E + LY.oA; float* sY = E + LY.oY;
-    float* sLam = E + LY.oLam; float* sRhs = E + LY.oRhs; float* sInv = E + LY.oInv; int* sRl = reinterpret_cast<int*>(E + LY.oRl);
+    float* sLam = E + LY.oLam; float2* sRI = reinterpret_cast<float2*>(E + LY.oRhs); int* sRl = reinterpret_cast<int*>(E + LY.oRl);
     float* sPp = E + LY.oPp; float* sPi = E + LY.oPi; int* sPr = reinterpret_cast<int*>(E + LY.oPr);
     float* sQ = E + LY.oQ; float* sG = E + LY.oG; float* sZ = E + LY.oZ;
     auto lk_i = [&](int j) { return reinterpret_cast<const int*>(LK + j * kLkFloats)[kLInt]; };
@@ -262,6 +271,7 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
     const int NR = NL + 3 * P;
     const int NRmax = (W == 32) ? NR : wmax(NR);
     const int nslots = (NRmax + W - 1) / W;
+    constexpr int kPgsBlock = DM_PGS_BLOCK;
     constexpr int kSlots = 2;   // rows per lane in the general path: the host caps the row capacity at 2 W (32 humanoid3d, 60 dog3d)
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
@@ -359,7 +369,7 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
                     if (lpen > 0.f) verr = -lpen / h; else perr = -lpen * 0.2f / h;
                     rhs = combine ? (perr * inv + verr * inv) : (verr * inv);
                 }
-                sRhs[rid] = rhs; sInv[rid] = inv; sLam[rid] = lam0;
+                sRI[rid] = make_float2(rhs, inv); sLam[rid] = lam0;
             }
         }
     }
@@ -367,9 +377,11 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
     SPROF(7);
     const int Pmax = (W == 32) ? P : wmax(P);
     const int NLmax = (W == 32) ? NL : wmax(NL);
-    if (nslots == 1) {
-        // ================= common case: at most W rows -> one row per lane, A stored as a full symmetric W x W square (stride W)
-        // lanes = (i, j <= i) pairs of the lower triangle, W pairs per pass
+    {
+        // ---- A = J M^-1 J^T = Y Y^T: lanes = (i, j <= i) pairs of the lower triangle, W pairs per pass.  At most W rows (the common case): full
+        // symmetric W x W square (stride W); more: packed lower triangle (pair index = storage index).  Overwrites the world-frame / velocity
+        // scratch, no longer needed this sub-step.
+        const bool sq = nslots == 1;
         const int npair = NR * (NR + 1) / 2, npmax = NRmax * (NRmax + 1) / 2;
 #pragma unroll 1
         for (int q0 = 0; q0 < npmax; q0 += W) {
@@ -391,49 +403,12 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
                 if (k + 2 < cd) acc += a2 * b2;
                 if (k + 3 < cd) acc += a3 * b3;
             }
-            if (pv) { sA[i * W + j] = acc; sA[j * W + i] = acc; }
+            if (pv) { if (sq) { sA[i * W + j] = acc; sA[j * W + i] = acc; } else sA[q] = acc; }
         }
         __syncwarp();
         SPROF(8);
-        pgs_sweeps<W, 1, true>(sA, sLam, sRhs, sInv, nullptr, lane, NL, P, NR, NLmax, Pmax, mu);
-    } else {
-        // ================= general path: up to kSlots rows per lane, A as a packed lower triangle
-        // ---- A = J M^-1 J^T, packed lower triangle (overwrites the world-frame / velocity scratch, no longer needed this sub-step)
-        int bj[kSlots], tj[kSlots];
-    #pragma unroll
-        for (int s = 0; s < kSlots; ++s) { const int rid = lane + s * W; bj[s] = (rid < NR) ? sRl[rid] : 0; tj[s] = rid * (rid + 1) / 2; }
-        __syncwarp();
-    #pragma unroll 1
-        for (int i = 0; i < NRmax; ++i) {
-            const bool iv = i < NR;
-            const int bi = iv ? sRl[i] : 0;
-            const unsigned char* cdr = CD + bi * nl;
-            const int ti = i * (i + 1) / 2;
-            const int cdi = iv ? ((lk_i2(bi) >> 8) & 0xff) + 1 : 0;          // chain length of row i
-            const int cdm = (W == 32) ? cdi : wmax(cdi);
-    #pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                const int rid = lane + s * W;
-                if (s * W <= i) {   // only rows j <= i are stored
-                    const int cd = (iv && rid <= i) ? cdr[bj[s]] : 0;       // common chain depth of rows i and rid
-                    const float* yi = sY + i; const float* yr = sY + ((rid < MR) ? rid : 0);
-                    float acc = 0.f;
-    #pragma unroll 1
-                    for (int k = 0; k < cdm; k += 4) {
-                        const float a0 = yi[k * MR], a1 = yi[(k + 1) * MR], a2 = yi[(k + 2) * MR], a3 = yi[(k + 3) * MR];
-                        const float b0 = yr[k * MR], b1 = yr[(k + 1) * MR], b2 = yr[(k + 2) * MR], b3 = yr[(k + 3) * MR];
-                        if (k < cd) acc += a0 * b0;
-                        if (k + 1 < cd) acc += a1 * b1;
-                        if (k + 2 < cd) acc += a2 * b2;
-                        if (k + 3 < cd) acc += a3 * b3;
-                    }
-                    if (iv && rid <= i) sA[ti + rid] = acc;
-                }
-            }
-        }
-        __syncwarp();
-        SPROF(8);
-        pgs_sweeps<W, kSlots, false>(sA, sLam, sRhs, sInv, tj, lane, NL, P, NR, NLmax, Pmax, mu);
+        if (sq) pgs_sweeps<W, 1, true, kPgsBlock>(sA, sLam, sRI, lane, NL, P, NLmax, Pmax, mu);
+        else pgs_sweeps<W, kSlots, false, kPgsBlock>(sA, sLam, sRI, lane, NL, P, NLmax, Pmax, mu);
     }
     SPROF(9);
     // write impulses back to the manifold (warm start of the next sub-step)
@@ -1385,8 +1360,8 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
                 if (ndof == 3) { jv.y = cl100(jv.y + dq.y); jv.z = cl100(jv.z + dq.z); }
             }
             if (DEBUG && dbg && first_upd) {   // solver rows in solver order: right-hand side, 1 / A_ii, impulse (test hook)
-                const float* sRhs_ = E + LY.oRhs; const float* sInv_ = E + LY.oInv;
-                for (int k = lane; k < NR && k < 64; k += W) { float* o = dbg + 8 * kMaxDofs + sub * 256; o[k] = sRhs_[k]; o[64 + k] = sInv_[k]; o[128 + k] = sLam[k]; }
+                const float2* sRI_ = reinterpret_cast<const float2*>(E + LY.oRhs);
+                for (int k = lane; k < NR && k < 64; k += W) { float* o = dbg + 8 * kMaxDofs + sub * 256; o[k] = sRI_[k].x; o[64 + k] = sRI_[k].y; o[128 + k] = sLam[k]; }
             }
             if (DEBUG && dbg && first_upd) {   // impulses in the order [normals | friction pairs | limits]
                 const int lo_ = (sub == 0 ? 7 * kMaxDofs : 11 * kMaxDofs + 1024) + 1;

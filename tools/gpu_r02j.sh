@@ -1,0 +1,8 @@
+# round 2, call j: blocked PGS (B = 4 default, 2 and 8 as A/B libraries): parity tests, bench, section profile
+set -x
+timeout 900 python -m pytest tests -m gpu -q --tb=short -x --deselect tests/test_mlp_gpu.py 2>&1 | tail -12
+B() { python -c "import sys,json; d=json.loads(sys.stdin.read()); print('BENCH $1', round(d['value']), d['roofline']['kernel_ms'], round(d['e2e']['value']), d['config']['step_ms'])"; }
+timeout 300 python bench.py --steps 128 --no-cpu-baseline 2>gpurun_out/bench_r02j.err | B b4
+DM_LIB=$PWD/deepmimic_b200/libdeepmimic_b200_b8.so timeout 300 python bench.py --steps 128 --no-cpu-baseline 2>>gpurun_out/bench_r02j.err | B b8
+DM_LIB=$PWD/deepmimic_b200/libdeepmimic_b200_b2.so timeout 300 python bench.py --steps 128 --no-cpu-baseline 2>>gpurun_out/bench_r02j.err | B b2
+DM_LIB=$PWD/deepmimic_b200/libdeepmimic_b200_prof.so timeout 300 python tools/section_profile.py 2>&1 | tail -40
