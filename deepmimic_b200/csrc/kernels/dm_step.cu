@@ -114,7 +114,8 @@ int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L) {
     const int world = nl * 24, tri = maxrows * (maxrows + 1) / 2;   // world: Rwl 9 + pivot 3 | link velocity 6 + pivot->COM 3 (+3 pad)
     L->oW = o; L->oV = o + nl * 12;
     o += (world > tri ? world : tri);
-    L->oY = o; o += chain_len * maxrows;           // Yt[depth][row]
+    o = (o + 3) & ~3;                              // 16-byte aligned: the articulated-body pass borrows the block as float4 scratch (28 floats per lane)
+    L->oY = o; o += (chain_len * maxrows > 28 * (nl <= 16 ? 16 : 32)) ? chain_len * maxrows : 28 * (nl <= 16 ? 16 : 32);   // Yt[depth][row]
     L->oLam = o; o += maxrows; o += (o & 1); L->oRhs = o; o += maxrows; L->oInv = o; o += maxrows;   // oRhs .. : interleaved (rhs, 1 / A_ii) pairs, 8-byte aligned
     L->oRl = o; o += maxrows;                      // row -> link (int)
     L->oPp = o; o += maxpts * 4; L->oPi = o; o += maxpts; L->oPr = o; o += maxpts;
@@ -153,16 +154,20 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
     float w[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) w[s] = 0.f;
-    // A(lane + s W, i).  Lanes without a row read finite leftovers of the scratch region: their w is never fetched.
-    auto a_own = [&](int s, int i) -> float {
+    // A(lane + s W, i).  Lanes without a row read finite leftovers of the scratch region: their w is never fetched.  Packed storage: tri(r) = r (r + 1) / 2
+    // of the lane's own rows is computed once, tri(i) once per solver step.
+    int tjs[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { const int rid = lane + s * W; tjs[s] = rid * (rid + 1) / 2; }
+    auto tri = [](int i) { return (i * (i + 1)) >> 1; };
+    auto a_own = [&](int s, int i, int ti) -> float {
         if (SQUARE) return sA[i * W + lane];
         const int rid = lane + s * W;
-        return sA[(rid >= i) ? (rid * (rid + 1) / 2 + i) : (i * (i + 1) / 2 + rid)];
+        return sA[(rid >= i) ? (tjs[s] + i) : (ti + rid)];
     };
-    auto a_pair = [&](int i, int j) -> float {   // A(i, j), tile-uniform indices
+    auto a_pair = [&](int i, int j, int ti, int tj_) -> float {   // A(i, j), tile-uniform indices
         if (SQUARE) return sA[i * W + j];
-        const int hi_ = max(i, j), lo_ = min(i, j);
-        return sA[hi_ * (hi_ + 1) / 2 + lo_];
+        return sA[(i >= j) ? (ti + j) : (tj_ + i)];
     };
     // warm start: w = A lambda0 (normals carry 0.85 x the cached impulse, everything else starts at 0), in point order
 #pragma unroll 1
@@ -170,12 +175,12 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
         const int i = NL + ((p < P) ? p : 0);
         const float l0 = (p < P) ? sLam[i] : 0.f;
 #pragma unroll
-        for (int s = 0; s < S; ++s) w[s] = fmaf(a_own(s, i), l0, w[s]);
+        for (int s = 0; s < S; ++s) w[s] = fmaf(a_own(s, i, tri(i)), l0, w[s]);
     }
     // one block of B consecutive solver steps of section SEC, starting at position pos0 of the section
     auto block = [&](int pos0, int it, auto sec_tag) {
         constexpr int SEC = decltype(sec_tag)::value;
-        int ik[B]; bool vk[B];
+        int ik[B], tk[B]; bool vk[B];
         float tot = 0.f;
         float wk[B], rhs[B], inv[B], lam[B], lo[B], hi[B], ain[B * (B - 1) / 2 > 0 ? B * (B - 1) / 2 : 1], ao[S][B];
 #pragma unroll
@@ -184,6 +189,7 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
             if (SEC == kSecLimit) { vk[k] = pos < NL; ik[k] = vk[k] ? ((it & 1) ? pos : NL - 1 - pos) : 0; }
             else if (SEC == kSecNormal) { vk[k] = pos < P; ik[k] = vk[k] ? NL + pos : 0; }
             else { vk[k] = pos < 2 * P; ik[k] = vk[k] ? NL + P + pos : 0; }
+            tk[k] = SQUARE ? 0 : tri(ik[k]);
         }
 #pragma unroll
         for (int k = 0; k < B; ++k) {
@@ -201,12 +207,12 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
 #pragma unroll
             for (int k = 1; k < B; ++k)
 #pragma unroll
-                for (int j = 0; j < k; ++j) ain[o++] = a_pair(ik[k], ik[j]);
+                for (int j = 0; j < k; ++j) ain[o++] = a_pair(ik[k], ik[j], tk[k], tk[j]);
         }
 #pragma unroll
         for (int s = 0; s < S; ++s)
 #pragma unroll
-            for (int k = 0; k < B; ++k) ao[s][k] = a_own(s, ik[k]);
+            for (int k = 0; k < B; ++k) ao[s][k] = a_own(s, ik[k], tk[k]);
 #pragma unroll
         for (int k = 0; k < B; ++k) {
             float sel = w[0];
@@ -755,6 +761,7 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
     // U_d = IA s_d goes straight to the environment's factor table (sU: read back by the acceleration pass below and, in the Bullet sub-steps,
     // by the constraint rows and the velocity correction) instead of living in 18 registers across the leaves -> root loop
     float* const uown = sU + c.lane * 24;
+    float* const scr = c.E + LY.oY;   // 28 floats per lane (dm_step_layout guarantees the room and the 16-byte alignment)
     auto eliminate = [&](V3 dir, float g, int d, float& invo, float& uo) {
         const V3 Ua = sym_mul(IA.ww, dir), Ul = wvT_mul(IA.wv, dir);
         const float D = dot(dir, Ua) + kdt;
@@ -790,20 +797,27 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
             pA = shift_f(pA, cw);
         }
         if (lv == 0) break;
-        const int nslot = c.LVC[lv - 1];
+        // children -> parent through the environment's scratch (the Y block of the constraint rows, not live during this routine): a link of
+        // level lv publishes its shifted (IA, pA) as 7 float4, its parent adds its children's in child order.  (Was 33 shuffles + 33 predicated
+        // adds per child slot of the level: 8 slots per solve for humanoid3d.)
+        if (c.level == lv) {
+            float4* o4 = reinterpret_cast<float4*>(scr + c.lane * 28);
+            o4[0] = make_float4(IA.ww[0], IA.ww[1], IA.ww[2], IA.ww[3]); o4[1] = make_float4(IA.ww[4], IA.ww[5], IA.wv[0], IA.wv[1]);
+            o4[2] = make_float4(IA.wv[2], IA.wv[3], IA.wv[4], IA.wv[5]); o4[3] = make_float4(IA.wv[6], IA.wv[7], IA.wv[8], IA.vv[0]);
+            o4[4] = make_float4(IA.vv[1], IA.vv[2], IA.vv[3], IA.vv[4]); o4[5] = make_float4(IA.vv[5], pA.a.x, pA.a.y, pA.a.z);
+            o4[6] = make_float4(pA.l.x, pA.l.y, pA.l.z, 0.f);
+        }
+        __syncwarp();
+        if (c.level == lv - 1) {
 #pragma unroll 1
-        for (int k = 0; k < nslot; ++k) {
-            const int chl = (k < c.nchild) ? ((c.child_pack >> (8 * k)) & 0xff) : -1;
-            const int src = chl >= 0 ? chl : c.lane;
-            const bool take = chl >= 0 && c.level == lv - 1;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) { float g = T::shfl(IA.ww[j], src); if (take) IA.ww[j] += g; }
-#pragma unroll
-            for (int j = 0; j < 9; ++j) { float g = T::shfl(IA.wv[j], src); if (take) IA.wv[j] += g; }
-#pragma unroll
-            for (int j = 0; j < 6; ++j) { float g = T::shfl(IA.vv[j], src); if (take) IA.vv[j] += g; }
-            const S6 gf = T::shfl6(pA, src);
-            if (take) { pA.a += gf.a; pA.l += gf.l; }
+            for (int k = 0; k < c.nchild; ++k) {
+                const float4* i4 = reinterpret_cast<const float4*>(scr + ((c.child_pack >> (8 * k)) & 0xff) * 28);
+                const float4 g0 = i4[0], g1 = i4[1], g2 = i4[2], g3 = i4[3], g4 = i4[4], g5 = i4[5], g6 = i4[6];
+                IA.ww[0] += g0.x; IA.ww[1] += g0.y; IA.ww[2] += g0.z; IA.ww[3] += g0.w; IA.ww[4] += g1.x; IA.ww[5] += g1.y;
+                IA.wv[0] += g1.z; IA.wv[1] += g1.w; IA.wv[2] += g2.x; IA.wv[3] += g2.y; IA.wv[4] += g2.z; IA.wv[5] += g2.w; IA.wv[6] += g3.x; IA.wv[7] += g3.y; IA.wv[8] += g3.z;
+                IA.vv[0] += g3.w; IA.vv[1] += g4.x; IA.vv[2] += g4.y; IA.vv[3] += g4.z; IA.vv[4] += g4.w; IA.vv[5] += g5.x;
+                pA.a.x += g5.y; pA.a.y += g5.z; pA.a.z += g5.w; pA.l.x += g6.x; pA.l.y += g6.y; pA.l.z += g6.z;
+            }
         }
     }
     // ---- base: the (massless) floating base carries the root link's articulated inertia; Cholesky of the 6x6 in world axes at the base
@@ -861,7 +875,16 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
     // ---- accelerations (root -> leaves): qdd_d = (u_d - U_d . a') / D_d
     float qd0 = 0.f, qd1 = 0.f, qd2 = 0.f;
     S6 al = mks(mk3(0, 0, 0), mk3(0, 0, 0));   // link acceleration (deviation from the bias acceleration)
-    auto udot = [&](S6 a, int d) { const float* q_ = uown + 6 * d; return a.a.x * q_[0] + a.a.y * q_[1] + a.a.z * q_[2] + a.l.x * q_[3] + a.l.y * q_[4] + a.l.z * q_[5]; };
+    // U of this link's dofs back into registers (the articulated inertia is dead by now): the recursion below then has no shared-memory load on its chain
+    float ur[18];
+    {
+        const float4* u4 = reinterpret_cast<const float4*>(uown);
+        const float4 a0 = u4[0], a1 = u4[1], a2 = u4[2], a3 = u4[3];
+        const float2 a4 = *reinterpret_cast<const float2*>(uown + 16);
+        ur[0] = a0.x; ur[1] = a0.y; ur[2] = a0.z; ur[3] = a0.w; ur[4] = a1.x; ur[5] = a1.y; ur[6] = a1.z; ur[7] = a1.w; ur[8] = a2.x; ur[9] = a2.y; ur[10] = a2.z; ur[11] = a2.w;
+        ur[12] = a3.x; ur[13] = a3.y; ur[14] = a3.z; ur[15] = a3.w; ur[16] = a4.x; ur[17] = a4.y;
+    }
+    auto udot = [&](S6 a, int d) { const float* q_ = ur + 6 * d; return a.a.x * q_[0] + a.a.y * q_[1] + a.a.z * q_[2] + a.l.x * q_[3] + a.l.y * q_[4] + a.l.z * q_[5]; };
     auto descend = [&](S6 a) {
         if (c.ndof >= 1) { qd0 = inv0 * (u0 - udot(a, 0)); a.a += qd0 * S0; }
         if (c.ndof == 3) { qd1 = inv1 * (u1 - udot(a, 1)); a.a += qd1 * S1; qd2 = inv2 * (u2 - udot(a, 2)); a.a += qd2 * S2; }

@@ -5,7 +5,7 @@ the reference and files produced by the reference load here.  Pure host code, no
   state snapshot cCharacter::WriteState / ReadState   R/DeepMimicCore/anim/Character.cpp:320-385,434-443
   training log   Logger.log_tabular / dump_tabular    R/util/logger.py:63-127 (fixed-width 25-character columns)
 
-The BVH importer (R/DeepMimicCore/util/BVHReader.cpp) is not rebuilt: it feeds an offline retargeting tool, not the simulation."""
+The BVH importer (R/DeepMimicCore/util/BVHReader.cpp) is deepmimic_b200/bvh.py."""
 import json
 import re
 

@@ -187,7 +187,7 @@ def load_actor_weights(policy, actor):
 class BatchedRollout:
     """backend "torch": the policy is a torch module (cuBLAS GEMMs, eager normalisers) -- needed for training and for the gated task actor.
     backend "tcgen05": inference of the plain 2-layer actor on the library's own tensor-core kernels (dm_mlp_*, kernels/dm_mlp.cu): normaliser,
-    three GEMMs, bias / ReLU and the action un-normalisation in three launches on the environment's stream; the weights and the normaliser
+    three GEMMs, bias / ReLU and the action un-normalisation in four launches (operand preparation + one per layer) on the environment's stream; the weights and the normaliser
     statistics are snapshotted by refresh_tensor_core_policy() (call it again after a learner update)."""
 
     def __init__(self, env, policy=None, exp_rate=1.0, noise=0.05, seed=0, backend="torch"):

@@ -22,7 +22,7 @@ def main():
     for r in rows[1:]:
         v = float(r[val_i].replace(",", ""))
         u = r[unit_i]
-        scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}.get(u, 1.0)
+        scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0, "ns": 1e-9, "us": 1e-6, "ms": 1e-3}.get(u, 1.0)
         per.setdefault(r[name_i], []).append(v * scale)
     avg = {k: sum(v) / len(v) for k, v in per.items()}
     n = len(next(iter(per.values())))
