@@ -35,7 +35,7 @@ template <int W, bool DEBUG, int VAR>
 __global__ void dm_step_kernel(const DevModel*, DevState, const double*, const float*, double, int, int, StepLayout, int);
 __global__ void dm_task_reset_kernel(const DevModel*, DevState, int);
 __global__ void dm_task_observe_kernel(const DevModel*, DevState, float*, float*, int);
-int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L);
+int dm_step_layout(int nl, int n, int chain_len, int maxrows, int W, StepLayout* L);
 int dm_step_smem_bytes(const StepLayout& L, int tiles);
 
 __global__ void dm_flags_kernel(DevState st, int32_t* out, int num_real_envs) {
@@ -533,7 +533,7 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
         if (!chk(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { fail(); return nullptr; }
         int chain_len = 0;
         for (int j = 0; j < M.nl; ++j) chain_len = std::max(chain_len, M.link[j].last_depth + 1);
-        dmk::dm_step_layout(M.nl, M.n, chain_len, h->maxrows, &h->lay);
+        dmk::dm_step_layout(M.nl, M.n, chain_len, h->maxrows, h->W, &h->lay);
         const int per_env = h->lay.env_floats * 4;
         const int hot = h->lay.hot_floats * 4 + 1024;
         int max_tiles = std::min(dmk::kStepMaxThreads / h->W, (static_cast<int>(prop.sharedMemPerBlockOptin) - hot) / per_env);

@@ -34,6 +34,7 @@ struct Tl {
     static __device__ __forceinline__ V3 shfl3(V3 v, int src) { return mk3(shfl(v.x, src), shfl(v.y, src), shfl(v.z, src)); }
     static __device__ __forceinline__ S6 shfl6(S6 v, int src) { return mks(shfl3(v.a, src), shfl3(v.l, src)); }
 };
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ int wmax(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -104,7 +105,7 @@ __device__ __forceinline__ float* step_smem() { extern __shared__ __align__(16) 
 
 }  // namespace
 
-int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L) {
+int dm_step_layout(int nl, int n, int chain_len, int maxrows, int W, StepLayout* L) {
     const int maxpts = maxrows / 3;
     int o = 0;
     L->nl = nl; L->n = n; L->chain_len = chain_len; L->maxrows = maxrows; L->maxpts = maxpts;
@@ -115,7 +116,7 @@ int dm_step_layout(int nl, int n, int chain_len, int maxrows, StepLayout* L) {
     L->oW = o; L->oV = o + nl * 12;
     o += (world > tri ? world : tri);
     o = (o + 3) & ~3;                              // 16-byte aligned: the articulated-body pass borrows the block as float4 scratch (28 floats per lane)
-    L->oY = o; o += (chain_len * maxrows > 28 * (nl <= 16 ? 16 : 32)) ? chain_len * maxrows : 28 * (nl <= 16 ? 16 : 32);   // Yt[depth][row]
+    L->oY = o; o += (chain_len * 2 * W > 28 * W) ? chain_len * 2 * W : 28 * W;   // Yt[depth][row], row stride 2 W (a compile-time constant of the kernel: immediate offsets)
     L->oLam = o; o += maxrows; o += (o & 1); L->oRhs = o; o += maxrows; L->oInv = o; o += maxrows;   // oRhs .. : interleaved (rhs, 1 / A_ii) pairs, 8-byte aligned
     L->oRl = o; o += maxrows;                      // row -> link (int)
     L->oPp = o; o += maxpts * 4; L->oPi = o; o += maxpts; L->oPr = o; o += maxpts;
@@ -145,10 +146,10 @@ int dm_step_smem_bytes(const StepLayout& L, int tiles) { return (L.hot_floats + 
 // the UPDATE: clamp(delta, lo - lambda, hi - lambda) equals Bullet's "clamp the sum, then delta = limit - applied" in every branch; the stored
 // impulse is clamp(lambda + delta, lo, hi) (Bullet stores the limit itself when clamped: equal up to one rounding of lambda + (limit - lambda)).
 // The two environments of a W = 16 warp run in lockstep, each with its own row numbering (shuffles are tile-wide).
-// A: symmetric W x W square when S == 1, packed lower triangle otherwise.  sRI: (rhs, 1 / A_ii) pairs.  NLmax / Pmax: warp-wide maxima of NL / P
+// A: symmetric square of stride ST (W when the environment has at most W rows, kSq2 for up to kSq2 rows on two slots), packed lower triangle beyond.  sRI: (rhs, 1 / A_ii) pairs.  NLmax / Pmax: warp-wide maxima of NL / P
 // (block loops are warp-uniform).
 enum PgsSection { kSecLimit = 0, kSecNormal = 1, kSecFriction = 2 };
-template <int W, int S, bool SQUARE, int B>
+template <int W, int S, int ST, int B>   // ST > 0: A is a full symmetric square of stride ST; ST == 0: packed lower triangle
 __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const float2* sRI, int lane, int NL, int P, int NLmax, int Pmax, float mu) {
     using T = Tl<W>;
     float w[S];
@@ -161,12 +162,12 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
     for (int s = 0; s < S; ++s) { const int rid = lane + s * W; tjs[s] = rid * (rid + 1) / 2; }
     auto tri = [](int i) { return (i * (i + 1)) >> 1; };
     auto a_own = [&](int s, int i, int ti) -> float {
-        if (SQUARE) return sA[i * W + lane];
+        if (ST > 0) return sA[i * ST + lane + s * W];
         const int rid = lane + s * W;
         return sA[(rid >= i) ? (tjs[s] + i) : (ti + rid)];
     };
     auto a_pair = [&](int i, int j, int ti, int tj_) -> float {   // A(i, j), tile-uniform indices
-        if (SQUARE) return sA[i * W + j];
+        if (ST > 0) return sA[i * ST + j];
         return sA[(i >= j) ? (ti + j) : (tj_ + i)];
     };
     // warm start: w = A lambda0 (normals carry 0.85 x the cached impulse, everything else starts at 0), in point order
@@ -183,21 +184,26 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
         int ik[B], tk[B]; bool vk[B];
         float tot = 0.f;
         float wk[B], rhs[B], inv[B], lam[B], lo[B], hi[B], ain[B * (B - 1) / 2 > 0 ? B * (B - 1) / 2 : 1], ao[S][B];
+        if (SEC == kSecLimit) {
 #pragma unroll
-        for (int k = 0; k < B; ++k) {
-            const int pos = pos0 + k;
-            if (SEC == kSecLimit) { vk[k] = pos < NL; ik[k] = vk[k] ? ((it & 1) ? pos : NL - 1 - pos) : 0; }
-            else if (SEC == kSecNormal) { vk[k] = pos < P; ik[k] = vk[k] ? NL + pos : 0; }
-            else { vk[k] = pos < 2 * P; ik[k] = vk[k] ? NL + P + pos : 0; }
-            tk[k] = SQUARE ? 0 : tri(ik[k]);
+            for (int k = 0; k < B; ++k) { const int pos = pos0 + k; vk[k] = pos < NL; ik[k] = vk[k] ? ((it & 1) ? pos : NL - 1 - pos) : 0; }
+        } else {
+            // normals / friction rows are consecutive: one base index, immediate offsets.  Steps past the section's end (the other environment of
+            // the warp has more rows, or an odd count) keep their natural index: they read initialised words of the environment block (zeroed
+            // at kernel start, see dm_step_kernel) and their update is forced to 0 below.
+            const int i0 = ((SEC == kSecNormal) ? NL : NL + P) + pos0, cnt = (SEC == kSecNormal) ? P : 2 * P;
+#pragma unroll
+            for (int k = 0; k < B; ++k) { ik[k] = i0 + k; vk[k] = pos0 + k < cnt; }
         }
+#pragma unroll
+        for (int k = 0; k < B; ++k) tk[k] = (ST > 0) ? 0 : tri(ik[k]);
 #pragma unroll
         for (int k = 0; k < B; ++k) {
             const float2 ri = sRI[ik[k]];
             rhs[k] = ri.x; inv[k] = ri.y; lam[k] = sLam[ik[k]];
             if (SEC == kSecFriction) {
                 // the point's normal impulse of this sweep; the two friction rows of a point are consecutive: one load per pair when B is even
-                if ((B & 1) != 0 || (k & 1) == 0) tot = sLam[vk[k] ? NL + ((pos0 + k) >> 1) : 0];
+                if ((B & 1) != 0 || (k & 1) == 0) tot = sLam[NL + ((pos0 + k) >> 1)];
                 const bool on = tot > 0.f;
                 hi[k] = on ? mu * tot : lam[k]; lo[k] = on ? -hi[k] : lam[k];   // normal impulse not positive: the row is skipped
             } else { lo[k] = 0.f; hi[k] = (SEC == kSecLimit) ? 100.f : 1e10f; }     // joint limits [0, 100], contact normals [0, inf)
@@ -222,11 +228,12 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
         }
 #pragma unroll
         for (int k = 0; k < B; ++k) {
-            float c = fminf(fmaxf(fmaf(-inv[k], wk[k], rhs[k]), lo[k] - lam[k]), hi[k] - lam[k]);
+            float c = fmaxf(fmaf(-inv[k], wk[k], rhs[k]), lo[k] - lam[k]);
+            if (SEC != kSecNormal) c = fminf(c, hi[k] - lam[k]);     // contact normals have no upper bound (Bullet: 1e10)
             c = vk[k] ? c : 0.f;
 #pragma unroll
             for (int j = k + 1; j < B; ++j) wk[j] = fmaf(ain[j * (j - 1) / 2 + k], c, wk[j]);
-            if (vk[k] && lane == k) sLam[ik[k]] = fminf(fmaxf(lam[k] + c, lo[k]), hi[k]);
+            if (vk[k] && lane == k) sLam[ik[k]] = (SEC == kSecNormal) ? fmaxf(lam[k] + c, 0.f) : fminf(fmaxf(lam[k] + c, lo[k]), hi[k]);
 #pragma unroll
             for (int s = 0; s < S; ++s) w[s] = fmaf(ao[s][k], c, w[s]);
         }
@@ -264,6 +271,7 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
 #endif
     const StepLayout& LY = *reinterpret_cast<const StepLayout*>(LYS);
     const int nl = LY.nl, CL = LY.chain_len, MR = LY.maxrows;
+    constexpr int YS = 2 * W;   // row stride of Yt (>= maxrows: the host caps the row capacity at 2 W)
     float* const E = sm_ + LY.hot_floats + (threadIdx.x / W) * LY.env_floats;
     const unsigned char* CD = reinterpret_cast<const unsigned char*>(LK + nl * kLkFloats);
     const unsigned char* CH = CD + nl * nl;
@@ -320,7 +328,7 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
                     {   // dof 2
                         const float t = qb.z * f.a.x + qb.w * f.a.y + qc.x * f.a.z;
                         const float y = t * uf.w;
-                        if (rv_) sY[(dp0 + 2) * MR + rid] = y;
+                        if (rv_) sY[(dp0 + 2) * YS + rid] = y;
                         acc += y * y;
                         const float ti = t * uf.x;
                         f.a.x -= ti * ud.x; f.a.y -= ti * ud.y; f.a.z -= ti * ud.z; f.l.x -= ti * ud.w; f.l.y -= ti * ue.x; f.l.z -= ti * ue.y;
@@ -328,7 +336,7 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
                     {   // dof 1
                         const float t = qa.w * f.a.x + qb.x * f.a.y + qb.y * f.a.z;
                         const float y = t * uf.z;
-                        if (rv_) sY[(dp0 + 1) * MR + rid] = y;
+                        if (rv_) sY[(dp0 + 1) * YS + rid] = y;
                         acc += y * y;
                         const float ti = t * ue.w;
                         f.a.x -= ti * ub.z; f.a.y -= ti * ub.w; f.a.z -= ti * uc.x; f.l.x -= ti * uc.y; f.l.y -= ti * uc.z; f.l.z -= ti * uc.w;
@@ -338,7 +346,7 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
                     float t = qa.x * f.a.x + qa.y * f.a.y + qa.z * f.a.z;
                     if (first && kind == 0) { t = lsign; rvel = lsign * sQ[24 + rid]; }
                     const float y = t * uf.y;
-                    if (rv_) sY[dp0 * MR + rid] = y;
+                    if (rv_) sY[dp0 * YS + rid] = y;
                     acc += y * y;
                     const float ti = t * ue.z;
                     f.a.x -= ti * ua.x; f.a.y -= ti * ua.y; f.a.z -= ti * ua.z; f.l.x -= ti * ua.w; f.l.y -= ti * ub.x; f.l.z -= ti * ub.y;
@@ -356,7 +364,7 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
 #pragma unroll
                     for (int k = 0; k < i; ++k) x[i] -= sG[o++] * x[k];
                     x[i] *= sG[15 + i];
-                    if (rv_) sY[i * MR + rid] = x[i];
+                    if (rv_) sY[i * YS + rid] = x[i];
                     acc += x[i] * x[i];
                 }
             }
@@ -387,7 +395,13 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
         // ---- A = J M^-1 J^T = Y Y^T: lanes = (i, j <= i) pairs of the lower triangle, W pairs per pass.  At most W rows (the common case): full
         // symmetric W x W square (stride W); more: packed lower triangle (pair index = storage index).  Overwrites the world-frame / velocity
         // scratch, no longer needed this sub-step.
-        const bool sq = nslots == 1;
+        // storage: 0 = W x W square (one row per lane), 1 = kSq2 x kSq2 square on two rows per lane (most "more than W rows" cases are just above
+        // W; its sweep blocks are ~75 instructions against ~95 with packed indexing), 2 = packed triangle (pair index = storage index).
+        // Warp-uniform (NRmax).
+        constexpr int kSq2 = (W == 16) ? 22 : 42;             // kSq2^2 floats fit the scratch block (dm_step_layout: max(24 nl, maxrows (maxrows + 1) / 2))
+        const int region = max(nl * 24, MR * (MR + 1) / 2);   // floats of the scratch block
+        const int mode = (nslots == 1) ? 0 : ((NRmax <= kSq2 && kSq2 * kSq2 + W <= region) ? 1 : 2);
+        const int st = (mode == 0) ? W : kSq2;
         const int npair = NR * (NR + 1) / 2, npmax = NRmax * (NRmax + 1) / 2;
 #pragma unroll 1
         for (int q0 = 0; q0 < npmax; q0 += W) {
@@ -401,20 +415,21 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
             const float* yi = sY + (pv ? i : 0); const float* yj = sY + (pv ? j : 0);
             float acc = 0.f;
 #pragma unroll 1
-            for (int k = 0; k < CL; k += 4) {   // entries past the common depth are masked (reads past the chain length stay inside the block)
-                const float a0 = yi[k * MR], a1 = yi[(k + 1) * MR], a2 = yi[(k + 2) * MR], a3 = yi[(k + 3) * MR];
-                const float b0 = yj[k * MR], b1 = yj[(k + 1) * MR], b2 = yj[(k + 2) * MR], b3 = yj[(k + 3) * MR];
+            for (int k = 0; k < CL; k += 4, yi += 4 * YS, yj += 4 * YS) {   // entries past the common depth are masked (reads past the chain length stay inside the block)
+                const float a0 = yi[0], a1 = yi[YS], a2 = yi[2 * YS], a3 = yi[3 * YS];
+                const float b0 = yj[0], b1 = yj[YS], b2 = yj[2 * YS], b3 = yj[3 * YS];
                 if (k < cd) acc += a0 * b0;
                 if (k + 1 < cd) acc += a1 * b1;
                 if (k + 2 < cd) acc += a2 * b2;
                 if (k + 3 < cd) acc += a3 * b3;
             }
-            if (pv) { if (sq) { sA[i * W + j] = acc; sA[j * W + i] = acc; } else sA[q] = acc; }
+            if (pv) { if (mode != 2) { sA[i * st + j] = acc; sA[j * st + i] = acc; } else sA[q] = acc; }
         }
         __syncwarp();
         SPROF(8);
-        if (sq) pgs_sweeps<W, 1, true, kPgsBlock>(sA, sLam, sRI, lane, NL, P, NLmax, Pmax, mu);
-        else pgs_sweeps<W, kSlots, false, kPgsBlock>(sA, sLam, sRI, lane, NL, P, NLmax, Pmax, mu);
+        if (mode == 0) pgs_sweeps<W, 1, W, kPgsBlock>(sA, sLam, sRI, lane, NL, P, NLmax, Pmax, mu);
+        else if (mode == 1) pgs_sweeps<W, kSlots, kSq2, kPgsBlock>(sA, sLam, sRI, lane, NL, P, NLmax, Pmax, mu);
+        else pgs_sweeps<W, kSlots, 0, kPgsBlock>(sA, sLam, sRI, lane, NL, P, NLmax, Pmax, mu);
     }
     SPROF(9);
     // write impulses back to the manifold (warm start of the next sub-step)
@@ -439,10 +454,10 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
             if (i < NR) {
                 const int b = sRl[i];
                 const float l = sLam[i];
-                zb += sY[kb * MR + i] * l;
+                zb += sY[kb * YS + i] * l;
                 if (lane < nl && nd > 0 && CD[b * nl + lane] > dp0 + nd - 1) {   // the row's chain contains this link's dofs
-                    z0 += sY[dp0 * MR + i] * l;
-                    if (nd == 3) { z1 += sY[(dp0 + 1) * MR + i] * l; z2 += sY[(dp0 + 2) * MR + i] * l; }
+                    z0 += sY[dp0 * YS + i] * l;
+                    if (nd == 3) { z1 += sY[(dp0 + 1) * YS + i] * l; z2 += sY[(dp0 + 2) * YS + i] * l; }
                 }
             }
         }
@@ -765,7 +780,7 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
     auto eliminate = [&](V3 dir, float g, int d, float& invo, float& uo) {
         const V3 Ua = sym_mul(IA.ww, dir), Ul = wvT_mul(IA.wv, dir);
         const float D = dot(dir, Ua) + kdt;
-        const float inv = 1.0f / D;
+        const float inv = rcp_fast(D);   // MUFU.RCP (1 ulp); D = s . IA s + kdt is a positive, well-scaled inertia
         const float u = g - dot(dir, pA.a);
         const V3 sa = inv * Ua, sl = inv * Ul;
         IA.ww[0] -= sa.x * Ua.x; IA.ww[1] -= sa.x * Ua.y; IA.ww[2] -= sa.x * Ua.z; IA.ww[3] -= sa.y * Ua.y; IA.ww[4] -= sa.y * Ua.z; IA.ww[5] -= sa.z * Ua.z;
@@ -773,8 +788,8 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
         IA.wv[6] -= sa.z * Ul.x; IA.wv[7] -= sa.z * Ul.y; IA.wv[8] -= sa.z * Ul.z;
         IA.vv[0] -= sl.x * Ul.x; IA.vv[1] -= sl.x * Ul.y; IA.vv[2] -= sl.x * Ul.z; IA.vv[3] -= sl.y * Ul.y; IA.vv[4] -= sl.y * Ul.z; IA.vv[5] -= sl.z * Ul.z;
         pA.a += u * sa; pA.l += u * sl;
-        float* uo_ = uown + 6 * d;
-        uo_[0] = Ua.x; uo_[1] = Ua.y; uo_[2] = Ua.z; uo_[3] = Ul.x; uo_[4] = Ul.y; uo_[5] = Ul.z;
+        float2* uo_ = reinterpret_cast<float2*>(uown + 6 * d);   // 8-byte aligned: 24-float records
+        uo_[0] = make_float2(Ua.x, Ua.y); uo_[1] = make_float2(Ua.z, Ul.x); uo_[2] = make_float2(Ul.y, Ul.z);
         invo = inv; uo = u;
     };
     // (IA, pA) of a link are shifted to the parent's pivot IN PLACE once the link's own dofs are eliminated (the link no longer needs them about
@@ -1052,6 +1067,10 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     __syncthreads();
 
     float* E = sm + LY.hot_floats + tile * LY.env_floats;
+    // every word of the environment's block is initialised once per launch: the constraint sweeps read (and discard) words past the live rows
+    // of a section, which must hold finite numbers (a NaN pattern left by an earlier kernel would survive the multiplication by a zero update)
+    for (int k = lane * 4; k < LY.env_floats; k += W * 4) *reinterpret_cast<float4*>(E + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
     float* sV = E + LY.oV; float* sG = E + LY.oG; float* sQ = E + LY.oQ; float* sLam = E + LY.oLam;
     const float* LKo = LK + li * kLkFloats;
     const int jtype = (reinterpret_cast<const int*>(LKo)[kLInt] >> 8) & 0xff, ndof = act ? ((reinterpret_cast<const int*>(LKo)[kLInt] >> 16) & 0xff) : 0;

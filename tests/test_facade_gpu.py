@@ -140,3 +140,22 @@ def test_pretrained_reference_policy_tracks_the_clip_on_the_gpu(asset_root, char
     print("pretrained %s %s policy on the GPU: %d falls in %d episodes, mean reward %.3f" % (char, clip, falls, N, mean_r))
     assert falls <= 4, falls
     assert mean_r > 0.8, mean_r
+
+
+def test_sharded_env_keeps_the_step_contract_and_gathers_rows(asset_root, monkeypatch):
+    """ShardedDeepMimicEnv at world size 1 (the N > 1 exchange itself is covered by the gloo tests and by bench.py --gpus N): step() returns the
+    local 4-tuple that BatchedRollout.collect unpacks, step_gathered() additionally returns the job's rows in global environment order."""
+    import torch
+    from deepmimic_b200.env import ShardedDeepMimicEnv
+    from deepmimic_b200.rollout import BatchedRollout
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    env = ShardedDeepMimicEnv(["--arg_file", "args/run_humanoid3d_spinkick_args.txt"], 32, asset_root, seed=3)
+    env.reset(True)
+    traj = BatchedRollout(env, exp_rate=1.0).collect(3, record_stats=False)
+    assert traj["states"].shape == (3, 32, env.get_state_size()) and torch.isfinite(traj["rewards"]).all()
+    a = traj["actions"][-1].contiguous()
+    (s, r, done, term), (all_s, all_r, all_done) = env.step_gathered(a)
+    torch.cuda.synchronize()
+    assert s.shape == (32, env.get_state_size()) and term.shape == (32,)
+    assert torch.equal(all_s, s) and torch.equal(all_r, r) and torch.equal(all_done, done)
