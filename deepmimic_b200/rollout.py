@@ -277,6 +277,8 @@ class BatchedRollout:
                 s, r, done, term = env.step(a)
                 out["actions"][k] = a; out["logps"][k] = logp; out["rewards"][k] = r; out["dones"][k] = done; out["terminate"][k] = term
                 env.reset()                # restarts exactly the finished episodes
-                if bool(done.any()):
-                    s = env.record_state()
+                # the restarted environments need the observation of their new state.  Unconditional (one more ~10 us observation kernel) instead of
+                # `if done.any()`: that test is a host synchronisation per policy step, which leaves the GPU idle while the host launches the
+                # next step's small kernels (measured: 1.52 M -> see tests/test_mlp_gpu.py for the current rates)
+                s = env.record_state()
         return out
