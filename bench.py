@@ -282,9 +282,11 @@ def main():
         for k in range(3):
             core.step_host(h_acts[k % nb], dt, 20, h_obs, h_rew, h_fl, reset_done=True)
         core.sync()
-        ke = max(8, a.steps // 4)
+        ke = max(32, a.steps // 4)     # at least 32 calls (~70 ms): the wall-clock figure must not be dominated by start-up skew between ranks
         if world > 1:
-            dist.barrier()
+            torch.cuda.synchronize()
+            dist.barrier()             # NCCL's barrier is stream-ordered: synchronise again so that it has completed before the clock starts
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(ke):
             core.step_host(h_acts[i % nb], dt, 20, h_obs, h_rew, h_fl, reset_done=True)
