@@ -524,9 +524,9 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
     const auto& M = h->hm;
     h->W = (M.nl <= 16) ? 16 : 32;   // lanes per environment: one lane per link
     if (const char* w = std::getenv("DM_TILE_WIDTH")) { int v = std::atoi(w); if (v == 32 || (v == 16 && M.nl <= 16)) h->W = v; }
-    h->maxrows = (h->W == 16) ? 32 : 60;   // <= 2 rows per lane; humanoid3d: 8 foot points x 3 + limit rows <= 28, dog3d: 4 feet x 4 x 3 + limits <= 56
+    h->maxrows = dmk::dm_step_y_stride(h->W);   // humanoid3d: 8 foot points x 3 + limit rows <= 28 of 32; dog3d: 4 feet x 4 points x 3 + 4 limit rows = 52
     if (const char* sv = std::getenv("DM_SYNC_EVERY_STAGE")) h->sync_every_stage = std::atoi(sv);
-    if (const char* r = std::getenv("DM_MAX_ROWS")) { int v = std::atoi(r); if (v >= 12 && v <= 2 * h->W) h->maxrows = v; }
+    if (const char* r = std::getenv("DM_MAX_ROWS")) { int v = std::atoi(r); if (v >= 12 && v <= dmk::dm_step_y_stride(h->W)) h->maxrows = v; }
     {
         // one block per SM: as many environments per block as shared memory (227 KB) and 512 threads allow, balanced over the SMs
         cudaDeviceProp prop;

@@ -150,6 +150,11 @@ struct ObsFan {
     float* done[kMaxFan];
 };
 
+// Row capacity of the constraint solver per tile width = row stride of the Y block.  W = 16 (humanoid3d): 2 rows per lane (8 foot points x 3 + limits
+// <= 28).  W = 32: 52 = 16 points x 3 + 4 limit rows (dog3d: four feet flat + its four revolute joints at a limit), which is what lets 14
+// dog environments share a block: 2048 environments then run as ONE wave of 147 blocks instead of 171 blocks in two waves.
+__host__ __device__ constexpr int dm_step_y_stride(int W) { return W == 16 ? 32 : 52; }
+
 // shared-memory layout of dm_step_kernel (float offsets inside one environment's block), filled by dm_step_layout on the host and
 // passed by value as a kernel parameter (constant bank)
 struct StepLayout {

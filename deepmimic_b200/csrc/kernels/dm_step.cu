@@ -116,7 +116,8 @@ int dm_step_layout(int nl, int n, int chain_len, int maxrows, int W, StepLayout*
     L->oW = o; L->oV = o + nl * 12;
     o += (world > tri ? world : tri);
     o = (o + 3) & ~3;                              // 16-byte aligned: the articulated-body pass borrows the block as float4 scratch (28 floats per lane)
-    L->oY = o; o += (chain_len * 2 * W > 28 * W) ? chain_len * 2 * W : 28 * W;   // Yt[depth][row], row stride 2 W (a compile-time constant of the kernel: immediate offsets)
+    const int ys = dm_step_y_stride(W);
+    L->oY = o; o += (chain_len * ys > 28 * W) ? chain_len * ys : 28 * W;   // Yt[depth][row], row stride = the tile width's row capacity (a compile-time constant of the kernel: immediate offsets)
     L->oLam = o; o += maxrows; o += (o & 1); L->oRhs = o; o += maxrows; L->oInv = o; o += maxrows;   // oRhs .. : interleaved (rhs, 1 / A_ii) pairs, 8-byte aligned
     L->oRl = o; o += maxrows;                      // row -> link (int)
     L->oPp = o; o += maxpts * 4; L->oPi = o; o += maxpts; L->oPr = o; o += maxpts;
@@ -271,7 +272,7 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
 #endif
     const StepLayout& LY = *reinterpret_cast<const StepLayout*>(LYS);
     const int nl = LY.nl, CL = LY.chain_len, MR = LY.maxrows;
-    constexpr int YS = 2 * W;   // row stride of Yt (>= maxrows: the host caps the row capacity at 2 W)
+    constexpr int YS = dm_step_y_stride(W);   // row stride of Yt (>= maxrows: the host caps the row capacity there)
     float* const E = sm_ + LY.hot_floats + (threadIdx.x / W) * LY.env_floats;
     const unsigned char* CD = reinterpret_cast<const unsigned char*>(LK + nl * kLkFloats);
     const unsigned char* CH = CD + nl * nl;
@@ -286,7 +287,7 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
     const int NRmax = (W == 32) ? NR : wmax(NR);
     const int nslots = (NRmax + W - 1) / W;
     constexpr int kPgsBlock = DM_PGS_BLOCK;
-    constexpr int kSlots = 2;   // rows per lane in the general path: the host caps the row capacity at 2 W (32 humanoid3d, 60 dog3d)
+    constexpr int kSlots = 2;   // rows per lane in the general path: the host caps the row capacity at dm_step_y_stride(W) (32 humanoid3d, 52 dog3d)
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
         const int rid = lane + s * W;
@@ -398,7 +399,7 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
         // storage: 0 = W x W square (one row per lane), 1 = kSq2 x kSq2 square on two rows per lane (most "more than W rows" cases are just above
         // W; its sweep blocks are ~75 instructions against ~95 with packed indexing), 2 = packed triangle (pair index = storage index).
         // Warp-uniform (NRmax).
-        constexpr int kSq2 = (W == 16) ? 22 : 42;             // kSq2^2 floats fit the scratch block (dm_step_layout: max(24 nl, maxrows (maxrows + 1) / 2))
+        constexpr int kSq2 = (W == 16) ? 22 : 36;             // kSq2^2 floats fit the scratch block (dm_step_layout: max(24 nl, maxrows (maxrows + 1) / 2))
         const int region = max(nl * 24, MR * (MR + 1) / 2);   // floats of the scratch block
         const int mode = (nslots == 1) ? 0 : ((NRmax <= kSq2 && kSq2 * kSq2 + W <= region) ? 1 : 2);
         const int st = (mode == 0) ? W : kSq2;

@@ -184,6 +184,14 @@ def load_actor_weights(policy, actor):
     return policy
 
 
+class _nullcontext:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class BatchedRollout:
     """backend "torch": the policy is a torch module (cuBLAS GEMMs, eager normalisers) -- needed for training and for the gated task actor.
     backend "tcgen05": inference of the plain 2-layer actor on the library's own tensor-core kernels (dm_mlp_*, kernels/dm_mlp.cu): normaliser,
@@ -255,7 +263,12 @@ class BatchedRollout:
         G = self.goal_size
         if G > 0:
             out["goals"] = t.empty(num_steps, N, G, device=env.device)
-        with t.no_grad():
+        # the whole loop runs on the environment's stream: with the actor and the bookkeeping on another stream every env call is a pair of
+        # cross-stream event waits (measured: 0.4 ms of bubbles per policy step); the caller's stream waits for the trajectory at the end
+        caller = t.cuda.current_stream(env.device) if env.device.type == "cuda" else None
+        if caller is not None:
+            env.stream.wait_stream(caller)
+        with t.no_grad(), (t.cuda.stream(env.stream) if caller is not None else _nullcontext()):
             s = env.record_state()
             for k in range(num_steps):
                 out["states"][k] = s
@@ -281,4 +294,6 @@ class BatchedRollout:
                 # `if done.any()`: that test is a host synchronisation per policy step, which leaves the GPU idle while the host launches the
                 # next step's small kernels (measured: 1.52 M -> see tests/test_mlp_gpu.py for the current rates)
                 s = env.record_state()
+        if caller is not None:
+            caller.wait_stream(env.stream)
         return out
