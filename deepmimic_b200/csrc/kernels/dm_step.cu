@@ -403,28 +403,87 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
         const int region = max(nl * 24, MR * (MR + 1) / 2);   // floats of the scratch block
         const int mode = (nslots == 1) ? 0 : ((NRmax <= kSq2 && kSq2 * kSq2 + W <= region) ? 1 : 2);
         const int st = (mode == 0) ? W : kSq2;
-        const int npair = NR * (NR + 1) / 2, npmax = NRmax * (NRmax + 1) / 2;
+        auto put = [&](int i, int j, float v) {   // A(i, j) = A(j, i) = v
+            if (mode != 2) { sA[i * st + j] = v; sA[j * st + i] = v; }
+            else { const int hi_ = max(i, j), lo_ = min(i, j); sA[hi_ * (hi_ + 1) / 2 + lo_] = v; }
+        };
+        // (1) pairs with a joint-limit row (rows [0, NL): the smaller index of such a pair is a limit row): lanes = the other row
 #pragma unroll 1
-        for (int q0 = 0; q0 < npmax; q0 += W) {
-            const int q = q0 + lane;
-            const bool pv = q < npair;
-            int i = static_cast<int>((sqrtf(8.0f * static_cast<float>(q) + 1.0f) - 1.0f) * 0.5f);
-            if (i * (i + 1) / 2 > q) --i;
-            if ((i + 1) * (i + 2) / 2 <= q) ++i;
-            const int j = q - i * (i + 1) / 2;
-            const int cd = pv ? CD[sRl[i] * nl + sRl[j]] : 0;          // common chain depth of rows i and j
-            const float* yi = sY + (pv ? i : 0); const float* yj = sY + (pv ? j : 0);
-            float acc = 0.f;
+        for (int j = 0; j < NLmax; ++j) {
+            const bool jv = j < NL;
+            const int bj = jv ? sRl[j] : 0;
 #pragma unroll 1
-            for (int k = 0; k < CL; k += 4, yi += 4 * YS, yj += 4 * YS) {   // entries past the common depth are masked (reads past the chain length stay inside the block)
-                const float a0 = yi[0], a1 = yi[YS], a2 = yi[2 * YS], a3 = yi[3 * YS];
-                const float b0 = yj[0], b1 = yj[YS], b2 = yj[2 * YS], b3 = yj[3 * YS];
-                if (k < cd) acc += a0 * b0;
-                if (k + 1 < cd) acc += a1 * b1;
-                if (k + 2 < cd) acc += a2 * b2;
-                if (k + 3 < cd) acc += a3 * b3;
+            for (int i0 = 0; i0 < NRmax; i0 += W) {
+                const int i = i0 + lane;
+                const bool pv = jv && i < NR && i >= j;
+                const int cd = pv ? CD[sRl[i] * nl + bj] : 0;          // common chain depth of rows i and j
+                const float* yi = sY + (pv ? i : 0); const float* yj = sY + (jv ? j : 0);
+                float acc = 0.f;
+#pragma unroll 1
+                for (int k = 0; k < CL; k += 4, yi += 4 * YS, yj += 4 * YS) {   // entries past the common depth are masked (reads past the chain length stay inside the block)
+                    const float a0 = yi[0], a1 = yi[YS], a2 = yi[2 * YS], a3 = yi[3 * YS];
+                    const float b0 = yj[0], b1 = yj[YS], b2 = yj[2 * YS], b3 = yj[3 * YS];
+                    if (k < cd) acc += a0 * b0;
+                    if (k + 1 < cd) acc += a1 * b1;
+                    if (k + 2 < cd) acc += a2 * b2;
+                    if (k + 3 < cd) acc += a3 * b3;
+                }
+                if (pv) put(i, j, acc);
             }
-            if (pv) { if (mode != 2) { sA[i * st + j] = acc; sA[j * st + i] = acc; } else sA[q] = acc; }
+        }
+        // (2) contact rows: lanes = (p, r <= p) pairs of contact POINTS, each lane forms the 3 x 3 block between the rows {normal, t1, t2} of the
+        // two points (rows NL + p, NL + P + 2 p, NL + P + 2 p + 1: they act on the same link, so one common depth serves all nine products, and
+        // six Y rows are loaded for nine dot products instead of two per product).  Same products, same summation order as pair by pair.
+        const int npp = P * (P + 1) / 2, nppmax = Pmax * (Pmax + 1) / 2;
+#pragma unroll 1
+        for (int q0 = 0; q0 < nppmax; q0 += W) {
+            const int q = q0 + lane;
+            const bool pv = q < npp;
+            int pp = static_cast<int>((sqrtf(8.0f * static_cast<float>(q) + 1.0f) - 1.0f) * 0.5f);
+            if (pp * (pp + 1) / 2 > q) --pp;
+            if ((pp + 1) * (pp + 2) / 2 <= q) ++pp;
+            const int pr = q - pp * (pp + 1) / 2;
+            const int in_p = pv ? NL + pp : 0, it_p = pv ? NL + P + 2 * pp : 0, in_r = pv ? NL + pr : 0, it_r = pv ? NL + P + 2 * pr : 0;
+            const int cd = pv ? CD[sRl[in_p] * nl + sRl[in_r]] : 0;
+            const float* ypn = sY + in_p; const float* ypt = sY + it_p; const float* yrn = sY + in_r; const float* yrt = sY + it_r;
+            float acc[3][3];
+#pragma unroll
+            for (int x = 0; x < 3; ++x)
+#pragma unroll
+                for (int y = 0; y < 3; ++y) acc[x][y] = 0.f;
+#pragma unroll 1
+            for (int k = 0; k < CL; k += 4, ypn += 4 * YS, ypt += 4 * YS, yrn += 4 * YS, yrt += 4 * YS) {
+                float av[3][4], bv[3][4];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    av[0][d] = ypn[d * YS]; av[1][d] = ypt[d * YS]; av[2][d] = ypt[d * YS + 1];
+                    bv[0][d] = yrn[d * YS]; bv[1][d] = yrt[d * YS]; bv[2][d] = yrt[d * YS + 1];
+                }
+#pragma unroll
+                for (int d = 0; d < 4; ++d)
+                    if (k + d < cd) {
+#pragma unroll
+                        for (int x = 0; x < 3; ++x)
+#pragma unroll
+                            for (int y = 0; y < 3; ++y) acc[x][y] += av[x][d] * bv[y][d];
+                    }
+            }
+            if (pv) {
+                if (mode != 2) {   // square: rows of p at stride st, columns of r, and the transposed entries
+                    float* rp[3] = {sA + in_p * st, sA + it_p * st, sA + it_p * st + st};
+                    float* rr[3] = {sA + in_r * st, sA + it_r * st, sA + it_r * st + st};
+                    const int cp[3] = {in_p, it_p, it_p + 1}, cr[3] = {in_r, it_r, it_r + 1};
+#pragma unroll
+                    for (int x = 0; x < 3; ++x)
+#pragma unroll
+                        for (int y = 0; y < 3; ++y) { rp[x][cr[y]] = acc[x][y]; rr[y][cp[x]] = acc[x][y]; }
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 3; ++x)
+#pragma unroll
+                        for (int y = 0; y < 3; ++y) put(x == 0 ? in_p : it_p + x - 1, y == 0 ? in_r : it_r + y - 1, acc[x][y]);
+                }
+            }
         }
         __syncwarp();
         SPROF(8);
