@@ -509,17 +509,19 @@ __device__ __noinline__ void solve_rows(int NL, int P, float* mani, int alive, u
         const int d0 = (lane < nl) ? (lk_i2(lane) & 0xff) : 0;
         float z0 = 0.f, z1 = 0.f, z2 = 0.f, zb = 0.f;
         const int kb = (lane < 6) ? lane : 0;
-#pragma unroll 1
+        // branch-free body, loads independent of the accumulators (two rows in flight): rows past NR contribute lambda = 0 (their Y entries are
+        // initialised words of the block), links outside the row's chain are masked
+        const bool mine = lane < nl && nd > 0;
+        const int need = dp0 + nd - 1;
+        const unsigned char* cdl = CD + lane;
+#pragma unroll 2
         for (int i = 0; i < NRmax; ++i) {
-            if (i < NR) {
-                const int b = sRl[i];
-                const float l = sLam[i];
-                zb += sY[kb * YS + i] * l;
-                if (lane < nl && nd > 0 && CD[b * nl + lane] > dp0 + nd - 1) {   // the row's chain contains this link's dofs
-                    z0 += sY[dp0 * YS + i] * l;
-                    if (nd == 3) { z1 += sY[(dp0 + 1) * YS + i] * l; z2 += sY[(dp0 + 2) * YS + i] * l; }
-                }
-            }
+            const int b = sRl[i];
+            const float l = (i < NR) ? sLam[i] : 0.f;
+            const float yb = sY[kb * YS + i], y0 = sY[dp0 * YS + i], y1 = sY[(dp0 + 1) * YS + i], y2 = sY[(dp0 + 2) * YS + i];
+            const bool in = mine && cdl[b * nl] > need;   // the row's chain contains this link's dofs
+            zb = fmaf(yb, l, zb);
+            if (in) { z0 = fmaf(y0, l, z0); if (nd == 3) { z1 = fmaf(y1, l, z1); z2 = fmaf(y2, l, z2); } }
         }
         if (lane < 6) sZ[lane] = zb;
         if (lane < nl && nd >= 1) sZ[d0] = z0;
