@@ -282,7 +282,7 @@ def main():
         for k in range(3):
             core.step_host(h_acts[k % nb], dt, 20, h_obs, h_rew, h_fl, reset_done=True)
         core.sync()
-        ke = max(32, a.steps // 4)     # at least 32 calls (~70 ms): the wall-clock figure must not be dominated by start-up skew between ranks
+        ke = max(64, a.steps // 2)     # at least 64 calls (~0.13 s): the wall-clock figure must not be dominated by start-up skew between ranks
         if world > 1:
             torch.cuda.synchronize()
             dist.barrier()             # NCCL's barrier is stream-ordered: synchronise again so that it has completed before the clock starts

@@ -179,6 +179,9 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
 #pragma unroll
         for (int s = 0; s < S; ++s) w[s] = fmaf(a_own(s, i, tri(i)), l0, w[s]);
     }
+    bool writer[B];   // lane k of the tile commits the impulse of the block's k-th step
+#pragma unroll
+    for (int k = 0; k < B; ++k) writer[k] = lane == k;
     // one block of B consecutive solver steps of section SEC, starting at position pos0 of the section
     auto block = [&](int pos0, int it, auto sec_tag) {
         constexpr int SEC = decltype(sec_tag)::value;
@@ -225,7 +228,7 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
             float sel = w[0];
 #pragma unroll
             for (int s = 1; s < S; ++s) if (ik[k] >= s * W) sel = w[s];
-            wk[k] = T::shfl(sel, ik[k] & (W - 1));
+            wk[k] = T::shfl(sel, (S == 1) ? ik[k] : (ik[k] & (W - 1)));   // one row per lane: the row index is the owner's lane (the shuffle wraps indices past W itself)
         }
 #pragma unroll
         for (int k = 0; k < B; ++k) {
@@ -234,7 +237,7 @@ __device__ __forceinline__ void pgs_sweeps(const float* sA, float* sLam, const f
             c = vk[k] ? c : 0.f;
 #pragma unroll
             for (int j = k + 1; j < B; ++j) wk[j] = fmaf(ain[j * (j - 1) / 2 + k], c, wk[j]);
-            if (vk[k] && lane == k) sLam[ik[k]] = (SEC == kSecNormal) ? fmaxf(lam[k] + c, 0.f) : fminf(fmaxf(lam[k] + c, lo[k]), hi[k]);
+            if (vk[k] && writer[k]) sLam[ik[k]] = (SEC == kSecNormal) ? fmaxf(lam[k] + c, 0.f) : fminf(fmaxf(lam[k] + c, lo[k]), hi[k]);
 #pragma unroll
             for (int s = 0; s < S; ++s) w[s] = fmaf(ao[s][k], c, w[s]);
         }
