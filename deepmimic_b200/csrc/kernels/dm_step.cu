@@ -98,9 +98,11 @@ __device__ __forceinline__ Q4 quat_integrate3(V3 omega, Q4 quat, bool base_body,
 // ---- block-shared model table, floats per link (LK)
 enum LkSlot { kLC = 0 /*3*/, kLD = 3 /*3*/, kLM = 6, kLWd = 7 /*6*/, kLWb = 13 /*6*/, kLAx = 19 /*3*/, kLInt = 22 /* parent|jtype|ndof|depth0 */, kLInt2 = 23 /* dof0|lastd|nchild */,
               kLZr = 24 /*4*/, kLHe = 28 /*3*/, kLThr = 31, kLKp = 32, kLKd = 33, kLTl = 34, kLLo = 35, kLHi = 36, kLFlg = 37 /* shape | fall<<8 | has_limit<<16 */, kLTree = 38 /* level | maxlevel<<8 | nchild<<16 */, kLChild = 39 /* child lanes, 8 bits each */,
-              kLkFloats = 40 };
+              kLDyn = 40 /* dynamics tree: parent | level<<8 (signed: root -1, lumped 100) | bypassed kinematic parent<<16 (0xff none) | children<<24 */, kLDChild = 41 /* dynamics children, 8 bits each */,
+              kLMc = 42 /* composite mass */, kLDc = 43 /*3: reference point -> composite COM, link axes */,
+              kLkFloats = 48 };
 // ---- block-shared header in front of the link table (floats): the launch's StepLayout (24 ints), children per tree level (8 ints), constants
-enum HdrSlot { kHLayout = 0, kHLvc = 24, kHGrav = 32 /*3*/, kHh = 35, kHScale = 36, kHMu = 37, kHFdt = 38, kHdrFloats = 40 };
+enum HdrSlot { kHLayout = 0, kHLvc = 24, kHGrav = 32 /*3*/, kHh = 35, kHScale = 36, kHMu = 37, kHFdt = 38, kHDmax = 39 /* int: deepest level of the dynamics tree */, kHdrFloats = 40 };
 __device__ __forceinline__ float* step_smem() { extern __shared__ __align__(16) float dm_step_sm[]; return dm_step_sm; }
 
 }  // namespace
@@ -786,20 +788,31 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
     const StepLayout& LY = lay_of(c);
     float* sU = c.E + LY.oU; const float* sS = c.E + LY.oR; const float* sW = c.E + LY.oW; float* sV = c.E + LY.oV; float* sG = c.E + LY.oG; float* sB = sG + 21;
     const float* LKo = c.LK + c.li * kLkFloats;
-    const float mass = c.act ? LKo[kLM] : 0.f;
+    // dynamics tree (see the table build in dm_step_kernel): parent lane, level (root -1: its lane accumulates the base; lumped fixed leaves 100:
+    // they take no part), the bypassed root whose pivot offset is added to this link's shift, children
+    const int dyn = c.act ? reinterpret_cast<const int*>(LKo)[kLDyn] : (100 << 8);
+    const int dpar = dyn & 0xff, dlev = static_cast<int>(static_cast<signed char>((dyn >> 8) & 0xff)), byp = (dyn >> 16) & 0xff, dnch = (dyn >> 24) & 0xff;
+    const int dchild = reinterpret_cast<const int*>(LKo)[kLDChild];
+    const int dmax = reinterpret_cast<const int*>(step_smem())[kHDmax];
+    const bool isroot = c.lane == 0;
+    const float mass = c.act ? LKo[kLMc] : 0.f;   // composite mass (own + lumped leaves; 0 for a lumped leaf itself)
     const float* q = sS + c.li * 12;
-    const V3 S0 = mk3(q[0], q[1], q[2]), S1 = mk3(q[3], q[4], q[5]), S2 = mk3(q[6], q[7], q[8]), cw = mk3(q[9], q[10], q[11]);
+    const V3 S0 = mk3(q[0], q[1], q[2]), S1 = mk3(q[3], q[4], q[5]), S2 = mk3(q[6], q[7], q[8]), cwk = mk3(q[9], q[10], q[11]);   // cwk: kinematic parent's pivot -> pivot
+    V3 cw = cwk;                                    // dynamics parent's reference point -> this link's reference point
+    if (byp != 0xff) { const float* qb = sS + byp * 12; cw = cw + mk3(qb[9], qb[10], qb[11]); }
+    if (isroot) cw = mk3(0, 0, 0);
     const float* vv = sV + c.li * 12;
-    const S6 vel = mks(mk3(vv[0], vv[1], vv[2]), mk3(vv[3], vv[4], vv[5]));
-    const V3 dw = mk3(vv[6], vv[7], vv[8]);
+    const S6 velk = mks(mk3(vv[0], vv[1], vv[2]), mk3(vv[3], vv[4], vv[5]));   // velocity at the link's own pivot
+    S6 vel = velk;                                                               // velocity at the reference point of the dynamics (root: base origin)
+    if (isroot) vel = mks(mk3(sB[7], sB[8], sB[9]), mk3(sB[10], sB[11], sB[12]));
     V3 jww = mk3(0, 0, 0);   // joint angular velocity, world axes
     if (c.jtype == kJSpherical) jww = jvx * S0 + jvy * S1 + jvz * S2; else if (c.jtype == kJRevolute) jww = jvx * S0;
     // ---- bias accelerations (root -> leaves)
     S6 ab;
     {
         const S6 cj = mks(cross(vel.a, jww), cross(vel.l, jww));
-        if (c.lane == 0) {
-            const V3 bo = mk3(sB[7], sB[8], sB[9]), bv = mk3(sB[10], sB[11], sB[12]);
+        if (isroot) {
+            const V3 bo = vel.a, bv = vel.l;
             V3 wxv;
             if (bullet) wxv = cross(bo, bv);
             else {   // cRBDUtil::BuildCjRoot differentiates the root quaternion with the body-frame formula applied to the world-frame
@@ -807,12 +820,12 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
                 const M3 Rwb = qmat(mkq(sB[3], sB[4], sB[5], sB[6]));
                 wxv = mulT(Rwb, cross(bo, mul(Rwb, bv)));
             }
-            ab = shift_m(mks(mk3(0, 0, 0), mk3(-gx, -gy, -gz) - wxv), cw) + cj;
+            ab = mks(mk3(0, 0, 0), mk3(-gx, -gy, -gz) - wxv);   // at the base origin (the root link has no joint velocity: no cj)
         }
 #pragma unroll 1
-        for (int lv = 1; lv <= c.maxlevel; ++lv) {
-            S6 pa = T::shfl6(ab, c.plane);
-            if (c.level == lv) ab = shift_m(pa, cw) + cj;
+        for (int lv = 0; lv <= dmax; ++lv) {
+            S6 pa = T::shfl6(ab, dpar);
+            if (dlev == lv) ab = shift_m(pa, cw) + cj;
         }
     }
     // ---- leaves -> root
@@ -830,7 +843,7 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
             for (int k = 0; k < 9; ++k) Rwl.m[k] = w[k];
         }
         rot_sym(Rwl, wl, IA.ww);     // link axes -> world axes
-        const V3 md = mass * dw;
+        const V3 md = mass * mulT(Rwl, mk3(LKo[kLDc], LKo[kLDc + 1], LKo[kLDc + 2]));   // first moment about the reference point, world axes
         IA.wv[0] = 0.f; IA.wv[1] = -md.z; IA.wv[2] = md.y; IA.wv[3] = md.z; IA.wv[4] = 0.f; IA.wv[5] = -md.x; IA.wv[6] = -md.y; IA.wv[7] = md.x; IA.wv[8] = 0.f;
         IA.vv[0] = mass; IA.vv[1] = 0.f; IA.vv[2] = 0.f; IA.vv[3] = mass; IA.vv[4] = 0.f; IA.vv[5] = mass;
         // h = I v ; pA = I ab + v x* h
@@ -860,11 +873,11 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
     // (IA, pA) of a link are shifted to the parent's pivot IN PLACE once the link's own dofs are eliminated (the link no longer needs them about
     // its own pivot), so that the parent reads them straight out of the child's registers: no second copy of the 21 + 6 values is alive.
 #pragma unroll 1
-    for (int lv = c.maxlevel; lv >= 0; --lv) {
-        if (c.level == lv) {
+    for (int lv = dmax; lv >= 0; --lv) {
+        if (dlev == lv) {
             if (c.ndof == 3) { eliminate(S2, g2, 2, inv2, u2); eliminate(S1, g1, 1, inv1, u1); }
             if (c.ndof >= 1) eliminate(S0, g0, 0, inv0, u0);
-            // express (IA, pA) about the parent's pivot: shift by c = cw:  B' = B + C V ; A' = A - B C + C B'^T   (C = [c]x)
+            // express (IA, pA) about the parent's reference point: shift by c = cw:  B' = B + C V ; A' = A - B C + C B'^T   (C = [c]x)
             const V3 v0 = mk3(IA.vv[0], IA.vv[1], IA.vv[2]), v1 = mk3(IA.vv[1], IA.vv[3], IA.vv[4]), v2 = mk3(IA.vv[2], IA.vv[4], IA.vv[5]);   // columns (= rows) of V
             const V3 b0 = mk3(IA.wv[0], IA.wv[1], IA.wv[2]), b1 = mk3(IA.wv[3], IA.wv[4], IA.wv[5]), b2 = mk3(IA.wv[6], IA.wv[7], IA.wv[8]);   // rows of B
             const V3 k0 = cross(cw, v0), k1 = cross(cw, v1), k2 = cross(cw, v2);   // columns of C V
@@ -875,12 +888,9 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
             IA.ww[3] += q1.y - p1.y; IA.ww[4] += q2.y - p1.z; IA.ww[5] += q2.z - p2.z;
             IA.wv[0] = n0.x; IA.wv[1] = n0.y; IA.wv[2] = n0.z; IA.wv[3] = n1.x; IA.wv[4] = n1.y; IA.wv[5] = n1.z; IA.wv[6] = n2.x; IA.wv[7] = n2.y; IA.wv[8] = n2.z;
             pA = shift_f(pA, cw);
-        }
-        if (lv == 0) break;
-        // children -> parent through the environment's scratch (the Y block of the constraint rows, not live during this routine): a link of
-        // level lv publishes its shifted (IA, pA) as 7 float4, its parent adds its children's in child order.  (Was 33 shuffles + 33 predicated
-        // adds per child slot of the level: 8 slots per solve for humanoid3d.)
-        if (c.level == lv) {
+            // children -> parent through the environment's scratch (the Y block of the constraint rows, not live during this routine): the link
+            // publishes its shifted (IA, pA) as 7 float4, its parent adds its children's in child order.  (Was 33 shuffles + 33 predicated
+            // adds per child slot of the level.)
             float4* o4 = reinterpret_cast<float4*>(scr + c.lane * 28);
             o4[0] = make_float4(IA.ww[0], IA.ww[1], IA.ww[2], IA.ww[3]); o4[1] = make_float4(IA.ww[4], IA.ww[5], IA.wv[0], IA.wv[1]);
             o4[2] = make_float4(IA.wv[2], IA.wv[3], IA.wv[4], IA.wv[5]); o4[3] = make_float4(IA.wv[6], IA.wv[7], IA.wv[8], IA.vv[0]);
@@ -888,10 +898,10 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
             o4[6] = make_float4(pA.l.x, pA.l.y, pA.l.z, 0.f);
         }
         __syncwarp();
-        if (c.level == lv - 1) {
+        if (dlev == lv - 1) {   // lv == 0: the root's lane gathers the base's children
 #pragma unroll 1
-            for (int k = 0; k < c.nchild; ++k) {
-                const float4* i4 = reinterpret_cast<const float4*>(scr + ((c.child_pack >> (8 * k)) & 0xff) * 28);
+            for (int k = 0; k < dnch; ++k) {
+                const float4* i4 = reinterpret_cast<const float4*>(scr + ((dchild >> (8 * k)) & 0xff) * 28);
                 const float4 g0 = i4[0], g1 = i4[1], g2 = i4[2], g3 = i4[3], g4 = i4[4], g5 = i4[5], g6 = i4[6];
                 IA.ww[0] += g0.x; IA.ww[1] += g0.y; IA.ww[2] += g0.z; IA.ww[3] += g0.w; IA.ww[4] += g1.x; IA.ww[5] += g1.y;
                 IA.wv[0] += g1.z; IA.wv[1] += g1.w; IA.wv[2] += g2.x; IA.wv[3] += g2.y; IA.wv[4] += g2.z; IA.wv[5] += g2.w; IA.wv[6] += g3.x; IA.wv[7] += g3.y; IA.wv[8] += g3.z;
@@ -900,8 +910,8 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
             }
         }
     }
-    // ---- base: the (massless) floating base carries the root link's articulated inertia; Cholesky of the 6x6 in world axes at the base
-    // origin, i.e. directly in the generalised base coordinates [omega_w, v_w]
+    // ---- base: the (massless) floating base carries the root link's inertia and everything gathered on the root's lane, about the base origin in
+    // world axes: Cholesky of the 6x6 directly in the generalised base coordinates [omega_w, v_w]
     S6 aB = mks(mk3(0, 0, 0), mk3(0, 0, 0));
     if (c.lane == 0) {
         float a[6][6];   // lower triangle a[i][j], j <= i ; coordinates [w(3); v(3)]
@@ -970,18 +980,24 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
         if (c.ndof == 3) { qd1 = inv1 * (u1 - udot(a, 1)); a.a += qd1 * S1; qd2 = inv2 * (u2 - udot(a, 2)); a.a += qd2 * S2; }
         return a;
     };
-    if (c.lane == 0) al = descend(shift_m(aB, cw));
+    if (isroot) al = aB;   // at the base origin; the root link has no dofs
 #pragma unroll 1
-    for (int lv = 1; lv <= c.maxlevel; ++lv) {
-        S6 pa = T::shfl6(al, c.plane);
-        if (c.level == lv) al = descend(shift_m(pa, cw));
+    for (int lv = 0; lv <= dmax; ++lv) {
+        S6 pa = T::shfl6(al, dpar);
+        if (dlev == lv) al = descend(shift_m(pa, cw));
     }
-    if (bullet && c.act) {   // publish the factors and the advanced link velocity (linear in the generalised velocities; the clamp only acts on exploding states)
-        float* u = sU + c.lane * 24;   // U0 U1 U2 are already there (eliminate)
-        u[18] = inv0; u[19] = inv1; u[20] = inv2; u[21] = sqrtf(inv0); u[22] = sqrtf(inv1); u[23] = sqrtf(inv2);
-        float* v = sV + c.lane * 12;
-        v[0] = vel.a.x + h * al.a.x; v[1] = vel.a.y + h * al.a.y; v[2] = vel.a.z + h * al.a.z;
-        v[3] = vel.l.x + h * al.l.x; v[4] = vel.l.y + h * al.l.y; v[5] = vel.l.z + h * al.l.z;
+    if (bullet) {
+        // links without a level of their own move with their kinematic parent: the root link (its pivot is offset from the base origin) and the
+        // lumped leaves get the parent's acceleration at their own pivot
+        const S6 pk = T::shfl6(al, c.plane);
+        if (isroot || dlev == 100) al = shift_m(pk, cwk);
+        if (c.act) {   // publish the factors and the advanced link velocity (linear in the generalised velocities; the clamp only acts on exploding states)
+            float* u = sU + c.lane * 24;   // U0 U1 U2 are already there (eliminate)
+            u[18] = inv0; u[19] = inv1; u[20] = inv2; u[21] = sqrtf(inv0); u[22] = sqrtf(inv1); u[23] = sqrtf(inv2);
+            float* v = sV + c.lane * 12;
+            v[0] = velk.a.x + h * al.a.x; v[1] = velk.a.y + h * al.a.y; v[2] = velk.a.z + h * al.a.z;
+            v[3] = velk.l.x + h * al.l.x; v[4] = velk.l.y + h * al.l.y; v[5] = velk.l.z + h * al.l.z;
+        }
     }
     __syncwarp();
     return make_float3(qd0, qd1, qd2);
@@ -997,9 +1013,15 @@ __device__ __noinline__ float3 dv_pass() {
     const StepLayout& LY = lay_of(c);
     const float* sU = c.E + LY.oU; const float* sS = c.E + LY.oR; float* sG = c.E + LY.oG; float* sB = sG + 21; const float* sZ = c.E + LY.oZ;
     const float* q = sS + c.li * 12;
-    const V3 S0 = mk3(q[0], q[1], q[2]), S1 = mk3(q[3], q[4], q[5]), S2 = mk3(q[6], q[7], q[8]), cw = mk3(q[9], q[10], q[11]);
+    const V3 S0 = mk3(q[0], q[1], q[2]), S1 = mk3(q[3], q[4], q[5]), S2 = mk3(q[6], q[7], q[8]);
+    V3 cw = mk3(q[9], q[10], q[11]);
     const float* u = sU + c.li * 24;
     const int dof0 = reinterpret_cast<const int*>(c.LK + c.li * kLkFloats)[kLInt2] & 0xff;
+    // dynamics tree (as in aba_solve): the root's lane carries the base's correction at the base origin, its children shift by both pivot offsets
+    const int dyn = c.act ? reinterpret_cast<const int*>(c.LK + c.li * kLkFloats)[kLDyn] : (100 << 8);
+    const int dpar = dyn & 0xff, dlev = static_cast<int>(static_cast<signed char>((dyn >> 8) & 0xff)), byp = (dyn >> 16) & 0xff;
+    const int dmax = reinterpret_cast<const int*>(step_smem())[kHDmax];
+    if (byp != 0xff) { const float* qb = sS + byp * 12; cw = cw + mk3(qb[9], qb[10], qb[11]); }
     S6 dB = mks(mk3(0, 0, 0), mk3(0, 0, 0));
     if (c.lane == 0) {   // base: dB = G^-T z
         float x[6] = {sZ[0], sZ[1], sZ[2], sZ[3], sZ[4], sZ[5]};
@@ -1028,11 +1050,11 @@ __device__ __noinline__ float3 dv_pass() {
         return a;
     };
     S6 al = mks(mk3(0, 0, 0), mk3(0, 0, 0));
-    if (c.lane == 0) al = descend(shift_m(dB, cw));
+    if (c.lane == 0) al = dB;
 #pragma unroll 1
-    for (int lv = 1; lv <= c.maxlevel; ++lv) {
-        S6 pa = T::shfl6(al, c.plane);
-        if (c.level == lv) al = descend(shift_m(pa, cw));
+    for (int lv = 0; lv <= dmax; ++lv) {
+        S6 pa = T::shfl6(al, dpar);
+        if (dlev == lv) al = descend(shift_m(pa, cw));
     }
     __syncwarp();
     return make_float3(qd0, qd1, qd2);
@@ -1096,11 +1118,52 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         const int p = K.parent;
         for (int k = 0; k < 3; ++k) { q[kLC + k] = K.evec[k] + (p >= 0 ? M.link[p].dvec[k] : 0.f); q[kLD + k] = K.dvec[k]; q[kLAx + k] = K.axis[k]; }
         q[kLM] = K.mass;
-        // rigid-body inertia about the joint pivot (COM at d): ww = Icom + m (|d|^2 1 - d d^T)
-        const float m = K.mass, dx = K.dvec[0], dy = K.dvec[1], dz = K.dvec[2], dd = dx * dx + dy * dy + dz * dz;
-        const float sh[6] = {m * (dd - dx * dx), -m * dx * dy, -m * dx * dz, m * (dd - dy * dy), -m * dy * dz, m * (dd - dz * dz)};
-        q[kLWd + 0] = K.inertiaD[0] + sh[0]; q[kLWd + 1] = sh[1]; q[kLWd + 2] = sh[2]; q[kLWd + 3] = K.inertiaD[1] + sh[3]; q[kLWd + 4] = sh[4]; q[kLWd + 5] = K.inertiaD[2] + sh[5];
-        q[kLWb + 0] = K.inertiaB[0] + sh[0]; q[kLWb + 1] = sh[1]; q[kLWb + 2] = sh[2]; q[kLWb + 3] = K.inertiaB[1] + sh[3]; q[kLWb + 4] = sh[4]; q[kLWb + 5] = K.inertiaB[2] + sh[5];
+        // ---- dynamics tree of the articulated-body passes (aba_solve, dv_pass).  Links without dofs need no level of their own there:
+        //   * the root link is fixed to the floating base: its rigid inertia is referred to the BASE ORIGIN (constant in link axes), its lane
+        //     accumulates the base's 6 x 6, and its children hang off the base directly (their shift is the sum of the two pivot offsets),
+        //   * a fixed leaf (humanoid3d: the wrists) is lumped into its parent: mass, first moment and inertia of the pair about the parent's
+        //     pivot are constants in the parent's axes.
+        // Same rigid-body system, two tree levels fewer (humanoid3d: 5 -> 3) in every pass of those routines.  The kinematic tree (kin_pass,
+        // the constraint rows' chain walks, vel_pass) is unchanged.
+        auto lumped = [&](int c_) { const DevLink& C_ = M.link[c_]; return C_.ndof == 0 && C_.nchild == 0 && C_.parent >= 0 && M.link[C_.parent].ndof > 0; };
+        const bool isroot = p < 0, self_lumped = lumped(j);
+        {
+            // composite rigid body about the reference point (COM of part i at r_i): ww = sum Icom_i + m_i (|r_i|^2 1 - r_i r_i^T), first moment sum m_i r_i
+            float cm = 0.f, mdx = 0.f, mdy = 0.f, mdz = 0.f, wD[6] = {0, 0, 0, 0, 0, 0}, wB[6] = {0, 0, 0, 0, 0, 0};
+            auto add_part = [&](float m_, V3 r, const float* iD, const float* iB) {   // iD / iB: symmetric 3 x 3 about the part's COM, this link's axes
+                const float rr = dot(r, r);
+                const float sh[6] = {m_ * (rr - r.x * r.x), -m_ * r.x * r.y, -m_ * r.x * r.z, m_ * (rr - r.y * r.y), -m_ * r.y * r.z, m_ * (rr - r.z * r.z)};
+                for (int k = 0; k < 6; ++k) { wD[k] += iD[k] + sh[k]; wB[k] += iB[k] + sh[k]; }
+                cm += m_; mdx += m_ * r.x; mdy += m_ * r.y; mdz += m_ * r.z;
+            };
+            if (!self_lumped) {
+                V3 r = mk3(K.dvec[0], K.dvec[1], K.dvec[2]);
+                if (isroot) r = r + mul(qmat(mkq(K.zrot[0], K.zrot[1], K.zrot[2], K.zrot[3])), mk3(K.evec[0], K.evec[1], K.evec[2]));   // base origin -> pivot, link axes
+                const float iD[6] = {K.inertiaD[0], 0.f, 0.f, K.inertiaD[1], 0.f, K.inertiaD[2]}, iB[6] = {K.inertiaB[0], 0.f, 0.f, K.inertiaB[1], 0.f, K.inertiaB[2]};
+                add_part(K.mass, r, iD, iB);
+                for (int k = 0; k < K.nchild; ++k) {
+                    const int c_ = K.child[k];
+                    if (!lumped(c_)) continue;
+                    const DevLink& C_ = M.link[c_];
+                    const M3 Rc = qmat(mkq(C_.zrot[0], C_.zrot[1], C_.zrot[2], C_.zrot[3]));   // this link's axes -> the child's axes (fixed joint)
+                    const V3 rc = mk3(C_.evec[0] + K.dvec[0], C_.evec[1] + K.dvec[1], C_.evec[2] + K.dvec[2]) + mulT(Rc, mk3(C_.dvec[0], C_.dvec[1], C_.dvec[2]));
+                    const float cD[6] = {C_.inertiaD[0], 0.f, 0.f, C_.inertiaD[1], 0.f, C_.inertiaD[2]}, cB[6] = {C_.inertiaB[0], 0.f, 0.f, C_.inertiaB[1], 0.f, C_.inertiaB[2]};
+                    float rD[6], rB[6];
+                    rot_sym(Rc, cD, rD); rot_sym(Rc, cB, rB);
+                    add_part(C_.mass, rc, rD, rB);
+                }
+            }
+            for (int k = 0; k < 6; ++k) { q[kLWd + k] = wD[k]; q[kLWb + k] = wB[k]; }
+            q[kLMc] = cm;
+            const float icm = cm > 0.f ? 1.0f / cm : 0.f;
+            q[kLDc] = mdx * icm; q[kLDc + 1] = mdy * icm; q[kLDc + 2] = mdz * icm;
+            int dch = 0, dn = 0;
+            for (int k = 0; k < K.nchild; ++k) if (!lumped(K.child[k])) { dch |= (K.child[k] & 0xff) << (8 * dn); ++dn; }
+            const int dlev = isroot ? -1 : (self_lumped ? 100 : K.level - 1);
+            const int dpar = isroot ? 0 : p, byp = (!isroot && p >= 0 && M.link[p].parent < 0) ? p : 0xff;
+            reinterpret_cast<int*>(q)[kLDyn] = (dpar & 0xff) | ((dlev & 0xff) << 8) | ((byp & 0xff) << 16) | ((dn & 0xff) << 24);
+            reinterpret_cast<int*>(q)[kLDChild] = dch;
+        }
         reinterpret_cast<int*>(q)[kLInt] = (K.parent & 0xff) | ((K.jtype & 0xff) << 8) | ((K.ndof & 0xff) << 16) | ((K.depth0 & 0xff) << 24);
         reinterpret_cast<int*>(q)[kLInt2] = (K.dof0 & 0xff) | ((K.last_depth & 0xff) << 8) | ((K.nchild & 0xff) << 16);
         for (int k = 0; k < 4; ++k) q[kLZr + k] = K.zrot[k];
@@ -1128,6 +1191,11 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         int mx = 0;
         for (int j = 0; j < nl; ++j) if (M.link[j].level == static_cast<int>(threadIdx.x)) mx = max(mx, M.link[j].nchild);
         LVC[threadIdx.x] = mx;
+    }
+    if (threadIdx.x == 8) {   // deepest level of the dynamics tree (levels of the links with dofs, the root's children being level 0)
+        int mx = 0;
+        for (int j = 0; j < nl; ++j) { const DevLink& K = M.link[j]; if (K.parent >= 0 && !(K.ndof == 0 && K.nchild == 0 && M.link[K.parent].ndof > 0)) mx = max(mx, K.level - 1); }
+        reinterpret_cast<int*>(sm)[kHDmax] = mx;
     }
     __syncthreads();
 
