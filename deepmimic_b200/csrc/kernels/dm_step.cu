@@ -645,9 +645,9 @@ __device__ __noinline__ void kin_pass(float4 jp, float4 jv) {
 // Collision of this lane's link with the plane y = 0: persistent manifold of <= 4 points (btPersistentManifold), one new point per
 // sub-step from the support vertex (btConvexPlaneCollisionAlgorithm), refresh with the breaking threshold.  The manifold lives in global
 // memory; the points of the environment are published to shared memory for the row builder.
-// Returns P | in_contact_tol << 8 | overflow << 9.
+// Returns P | in_contact_tol << 8 | overflow << 9 | this lane's point count << 10.
 template <int W>
-__device__ __noinline__ int collide(float* mani, int alive) {
+__device__ __noinline__ int collide(float* mani, int alive, int mcnt) {
     const Ctx c = make_ctx<W>();
     const float scale = step_smem()[kHScale];
     using T = Tl<W>;
@@ -665,13 +665,6 @@ __device__ __noinline__ int collide(float* mani, int alive) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) Rwl.m[k] = w[k];
     }
-    {
-        const float4* mg = reinterpret_cast<const float4*>(mani + c.li * kManifoldFloats);
-#pragma unroll
-        for (int k = 0; k < 12; ++k) { float4 v = mg[k]; mp[4 * k] = v.x; mp[4 * k + 1] = v.y; mp[4 * k + 2] = v.z; mp[4 * k + 3] = v.w; }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) if (mp[k * 12] != 0.f && cnt == k) cnt = k + 1;
     const float thr = LKo[kLThr];
     const V3 he = mk3(LKo[kLHe], LKo[kLHe + 1], LKo[kLHe + 2]);
     const V3 pos = mk3(sW[c.li * 12 + 9] + sV[c.li * 12 + 6], sW[c.li * 12 + 10] + sV[c.li * 12 + 7], sW[c.li * 12 + 11] + sV[c.li * 12 + 8]);   // COM, world (Bullet's link collider frame)
@@ -686,6 +679,18 @@ __device__ __noinline__ int collide(float* mani, int alive) {
     }
     const V3 vw = pos + mulT(Rwl, vtx);
     const float dist = vw.y;
+    // The manifold of a link is read (and written back) only if it can matter: the link held points after the previous sub-step (mcnt, carried
+    // by the caller; "unknown" = 4 at the start of a launch) or its support vertex is inside the contact threshold now.  For all other links --
+    // 13 of 15 for a standing humanoid -- the twelve 16-byte loads and stores per lane are predicated off: with the warps of a block in lockstep
+    // they all arrive here together, and the unconditional version throttled the memory pipe (14.6 % of the stall samples in capture r02y).
+    const bool need = c.act && alive && (mcnt > 0 || dist < thr);
+    {
+        const float4* mg = reinterpret_cast<const float4*>(mani + c.li * kManifoldFloats);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) { float4 v = need ? mg[k] : make_float4(0.f, 0.f, 0.f, 0.f); mp[4 * k] = v.x; mp[4 * k + 1] = v.y; mp[4 * k + 2] = v.z; mp[4 * k + 3] = v.w; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (mp[k * 12] != 0.f && cnt == k) cnt = k + 1;
     if (c.act && dist < thr) {
         float best = thr * thr; int nearest = -1;
 #pragma unroll
@@ -749,7 +754,7 @@ __device__ __noinline__ int collide(float* mani, int alive) {
     int tol = 0;                     // cContactManager::Update: distance <= 0.001 * scale
 #pragma unroll
     for (int k = 0; k < 4; ++k) if (k < cnt && mp[k * 12 + 10] <= 0.001f * scale) tol = 1;
-    if (c.act && alive) {
+    if (need) {
         float4* mo = reinterpret_cast<float4*>(mani + c.li * kManifoldFloats);
 #pragma unroll
         for (int k = 0; k < 12; ++k) mo[k] = make_float4(mp[4 * k], mp[4 * k + 1], mp[4 * k + 2], mp[4 * k + 3]);
@@ -771,7 +776,7 @@ __device__ __noinline__ int collide(float* mani, int alive) {
     }
     const int P = min(T::shfli(incl, W - 1), LY.maxpts);
     __syncwarp();
-    return P | (tol << 8) | (over << 9);
+    return P | (tol << 8) | (over << 9) | (cnt << 10);
 }
 
 // Articulated-body solve of  H qdd = g - C  for this environment (H: joint-space inertia, + kdt on the joint diagonal for Stable-PD).
@@ -1259,13 +1264,14 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     unsigned int* PRFP = nullptr;
 #endif
     bool need_kin = true, pending_flags = false;
+    int mcnt = 4;   // cached points of this lane's link after the last collision pass; unknown at the start of a launch: forces the first read
     const int stages_per_upd = sim_substeps + 1;
     const int total_stages = n_updates * stages_per_upd;
     const int sync_period = sync_mode > 0 ? 1 : (sync_mode == 0 ? stages_per_upd : (sync_mode <= -1000 ? 0 : -sync_mode * stages_per_upd));
 #pragma unroll 1
     for (int stage = 0; stage <= total_stages; ++stage) {
         // the manifold of this lane's link is read by the collision pass of a Bullet sub-step: start pulling its two cache lines in now
-        if ((stage % stages_per_upd) != 0 && act && alive) {
+        if ((stage % stages_per_upd) != 0 && act && alive && mcnt > 0) {
             const float* mp_ = mani + li * kManifoldFloats;
             asm volatile("prefetch.global.L1 [%0];" ::"l"(mp_));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(mp_ + 32));
@@ -1478,8 +1484,8 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         const int sub = ph - 1;
         int P;
         {
-            const int r = collide<W>(mani, alive ? 1 : 0);
-            P = r & 0xff; in_contact_tol = ((r >> 8) & 1) != 0; if (r >> 9) f_over = 1;
+            const int r = collide<W>(mani, alive ? 1 : 0, mcnt);
+            P = r & 0xff; in_contact_tol = ((r >> 8) & 1) != 0; if ((r >> 9) & 1) f_over = 1; mcnt = (r >> 10) & 7;
         }
         PROF(3);
         {   // unconstrained accelerations, v += a h (the base and the link velocities are advanced inside)
