@@ -34,6 +34,15 @@ struct Tl {
     static __device__ __forceinline__ V3 shfl3(V3 v, int src) { return mk3(shfl(v.x, src), shfl(v.y, src), shfl(v.z, src)); }
     static __device__ __forceinline__ S6 shfl6(S6 v, int src) { return mks(shfl3(v.a, src), shfl3(v.l, src)); }
 };
+// 12-float shared-memory records (48 bytes, 16-byte aligned: every offset of the environment block is a multiple of 4 floats) move as three 128-bit accesses
+__device__ __forceinline__ void ld12(const float* p, float* o) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1], c_ = reinterpret_cast<const float4*>(p)[2];
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w; o[8] = c_.x; o[9] = c_.y; o[10] = c_.z; o[11] = c_.w;
+}
+__device__ __forceinline__ void st12(float* p, const float* o) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(o[0], o[1], o[2], o[3]); reinterpret_cast<float4*>(p)[1] = make_float4(o[4], o[5], o[6], o[7]);
+    reinterpret_cast<float4*>(p)[2] = make_float4(o[8], o[9], o[10], o[11]);
+}
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ int wmax(int v) {
 #pragma unroll
@@ -631,13 +640,10 @@ __device__ __noinline__ void kin_pass(float4 jp, float4 jv) {
         const V3 dw = mulT(Rwl, mk3(LKo[kLD], LKo[kLD + 1], LKo[kLD + 2]));
         V3 S0 = mk3(Rwl.m[0], Rwl.m[1], Rwl.m[2]);
         if (c.jtype != kJSpherical) S0 = mulT(Rwl, axis);
-        float* w = sW + c.lane * 12; float* q = sS + c.lane * 12; float* v = sV + c.lane * 12;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) w[k] = Rwl.m[k];
-        w[9] = Pw.x; w[10] = Pw.y; w[11] = Pw.z;
-        q[0] = S0.x; q[1] = S0.y; q[2] = S0.z; q[3] = Rwl.m[3]; q[4] = Rwl.m[4]; q[5] = Rwl.m[5]; q[6] = Rwl.m[6]; q[7] = Rwl.m[7]; q[8] = Rwl.m[8];
-        q[9] = cw.x; q[10] = cw.y; q[11] = cw.z;
-        v[0] = vel.a.x; v[1] = vel.a.y; v[2] = vel.a.z; v[3] = vel.l.x; v[4] = vel.l.y; v[5] = vel.l.z; v[6] = dw.x; v[7] = dw.y; v[8] = dw.z;
+        const float wr[12] = {Rwl.m[0], Rwl.m[1], Rwl.m[2], Rwl.m[3], Rwl.m[4], Rwl.m[5], Rwl.m[6], Rwl.m[7], Rwl.m[8], Pw.x, Pw.y, Pw.z};
+        const float qr[12] = {S0.x, S0.y, S0.z, Rwl.m[3], Rwl.m[4], Rwl.m[5], Rwl.m[6], Rwl.m[7], Rwl.m[8], cw.x, cw.y, cw.z};
+        const float vr[12] = {vel.a.x, vel.a.y, vel.a.z, vel.l.x, vel.l.y, vel.l.z, dw.x, dw.y, dw.z, 0.f, 0.f, 0.f};
+        st12(sW + c.lane * 12, wr); st12(sS + c.lane * 12, qr); st12(sV + c.lane * 12, vr);
     }
     __syncwarp();
 }
@@ -660,14 +666,13 @@ __device__ __noinline__ int collide(float* mani, int alive, int mcnt) {
     int cnt = 0;
     float mp[48];
     M3 Rwl;
-    {
-        const float* w = sW + c.li * 12;
+    float wrec[12], vrec[12];
+    ld12(sW + c.li * 12, wrec); ld12(sV + c.li * 12, vrec);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) Rwl.m[k] = w[k];
-    }
+    for (int k = 0; k < 9; ++k) Rwl.m[k] = wrec[k];
     const float thr = LKo[kLThr];
     const V3 he = mk3(LKo[kLHe], LKo[kLHe + 1], LKo[kLHe + 2]);
-    const V3 pos = mk3(sW[c.li * 12 + 9] + sV[c.li * 12 + 6], sW[c.li * 12 + 10] + sV[c.li * 12 + 7], sW[c.li * 12 + 11] + sV[c.li * 12 + 8]);   // COM, world (Bullet's link collider frame)
+    const V3 pos = mk3(wrec[9] + vrec[6], wrec[10] + vrec[7], wrec[11] + vrec[8]);   // COM, world (Bullet's link collider frame)
     V3 dl = mul(Rwl, mk3(0.f, -1.f, 0.f));   // support direction -n in link coordinates
     V3 vtx;
     if (shape == kSBox) vtx = mk3(dl.x >= 0 ? he.x : -he.x, dl.y >= 0 ? he.y : -he.y, dl.z >= 0 ? he.z : -he.z);
@@ -801,12 +806,17 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
     const int dmax = reinterpret_cast<const int*>(step_smem())[kHDmax];
     const bool isroot = c.lane == 0;
     const float mass = c.act ? LKo[kLMc] : 0.f;   // composite mass (own + lumped leaves; 0 for a lumped leaf itself)
-    const float* q = sS + c.li * 12;
+    float q[12];
+    ld12(sS + c.li * 12, q);
     const V3 S0 = mk3(q[0], q[1], q[2]), S1 = mk3(q[3], q[4], q[5]), S2 = mk3(q[6], q[7], q[8]), cwk = mk3(q[9], q[10], q[11]);   // cwk: kinematic parent's pivot -> pivot
     V3 cw = cwk;                                    // dynamics parent's reference point -> this link's reference point
     if (byp != 0xff) { const float* qb = sS + byp * 12; cw = cw + mk3(qb[9], qb[10], qb[11]); }
     if (isroot) cw = mk3(0, 0, 0);
-    const float* vv = sV + c.li * 12;
+    float vv[8];
+    {
+        const float4 a = reinterpret_cast<const float4*>(sV + c.li * 12)[0], b = reinterpret_cast<const float4*>(sV + c.li * 12)[1];
+        vv[0] = a.x; vv[1] = a.y; vv[2] = a.z; vv[3] = a.w; vv[4] = b.x; vv[5] = b.y;
+    }
     const S6 velk = mks(mk3(vv[0], vv[1], vv[2]), mk3(vv[3], vv[4], vv[5]));   // velocity at the link's own pivot
     S6 vel = velk;                                                               // velocity at the reference point of the dynamics (root: base origin)
     if (isroot) vel = mks(mk3(sB[7], sB[8], sB[9]), mk3(sB[10], sB[11], sB[12]));
@@ -843,7 +853,8 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
         for (int k = 0; k < 6; ++k) wl[k] = c.act ? wsel[k] : 0.f;
         M3 Rwl;
         {
-            const float* w = sW + c.li * 12;
+            float w[12];
+            ld12(sW + c.li * 12, w);
 #pragma unroll
             for (int k = 0; k < 9; ++k) Rwl.m[k] = w[k];
         }
@@ -1017,10 +1028,10 @@ __device__ __noinline__ float3 dv_pass() {
     DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
     const float* sU = c.E + LY.oU; const float* sS = c.E + LY.oR; float* sG = c.E + LY.oG; float* sB = sG + 21; const float* sZ = c.E + LY.oZ;
-    const float* q = sS + c.li * 12;
+    float q[12], u[24];
+    ld12(sS + c.li * 12, q); ld12(sU + c.li * 24, u); ld12(sU + c.li * 24 + 12, u + 12);
     const V3 S0 = mk3(q[0], q[1], q[2]), S1 = mk3(q[3], q[4], q[5]), S2 = mk3(q[6], q[7], q[8]);
     V3 cw = mk3(q[9], q[10], q[11]);
-    const float* u = sU + c.li * 24;
     const int dof0 = reinterpret_cast<const int*>(c.LK + c.li * kLkFloats)[kLInt2] & 0xff;
     // dynamics tree (as in aba_solve): the root's lane carries the base's correction at the base origin, its children shift by both pivot offsets
     const int dyn = c.act ? reinterpret_cast<const int*>(c.LK + c.li * kLkFloats)[kLDyn] : (100 << 8);
@@ -1074,7 +1085,8 @@ __device__ __noinline__ void vel_pass(float jvx, float jvy, float jvz, bool want
     DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
     const float* sS = c.E + LY.oR; float* sV = c.E + LY.oV; const float* sB = c.E + LY.oG + 21;
-    const float* q = sS + c.li * 12;
+    float q[12];
+    ld12(sS + c.li * 12, q);
     const V3 S0 = mk3(q[0], q[1], q[2]), S1 = mk3(q[3], q[4], q[5]), S2 = mk3(q[6], q[7], q[8]), cw = mk3(q[9], q[10], q[11]);
     V3 jww = mk3(0, 0, 0);
     if (c.jtype == kJSpherical) jww = jvx * S0 + jvy * S1 + jvz * S2; else if (c.jtype == kJRevolute) jww = jvx * S0;
