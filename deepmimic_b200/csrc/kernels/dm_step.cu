@@ -105,11 +105,19 @@ __device__ __forceinline__ Q4 quat_integrate3(V3 omega, Q4 quat, bool base_body,
 }
 
 // ---- block-shared model table, floats per link (LK)
-enum LkSlot { kLC = 0 /*3*/, kLD = 3 /*3*/, kLM = 6, kLWd = 7 /*6*/, kLWb = 13 /*6*/, kLAx = 19 /*3*/, kLInt = 22 /* parent|jtype|ndof|depth0 */, kLInt2 = 23 /* dof0|lastd|nchild */,
-              kLZr = 24 /*4*/, kLHe = 28 /*3*/, kLThr = 31, kLKp = 32, kLKd = 33, kLTl = 34, kLLo = 35, kLHi = 36, kLFlg = 37 /* shape | fall<<8 | has_limit<<16 */, kLTree = 38 /* level | maxlevel<<8 | nchild<<16 */, kLChild = 39 /* child lanes, 8 bits each */,
-              kLDyn = 40 /* dynamics tree: parent | level<<8 (signed: root -1, lumped 100) | bypassed kinematic parent<<16 (0xff none) | children<<24 */, kLDChild = 41 /* dynamics children, 8 bits each */,
-              kLMc = 42 /* composite mass */, kLDc = 43 /*3: reference point -> composite COM, link axes */,
+// (groups of four: the hot routines read a group with one 128-bit load)
+enum LkSlot { kLC = 0 /*3*/, kLM = 3,                 // parent pivot -> pivot (parent axes) | own mass
+              kLD = 4 /*3*/, kLThr = 7,               // pivot -> COM (link axes) | contact breaking threshold
+              kLWd = 8 /*6*/, kLInt = 14 /* parent|jtype|ndof|depth0 */, kLInt2 = 15 /* dof0|lastd|nchild */,
+              kLWb = 16 /*6*/, kLFlg = 22 /* shape | fall<<8 | has_limit<<16 */, kLTree = 23 /* level | maxlevel<<8 | nchild<<16 */,
+              kLAx = 24 /*3*/, kLTl = 27,
+              kLZr = 28 /*4*/,
+              kLHe = 32 /*3*/, kLKp = 35,
+              kLKd = 36, kLLo = 37, kLHi = 38, kLChild = 39 /* child lanes, 8 bits each */,
+              kLDc = 40 /*3: reference point -> composite COM, link axes */, kLMc = 43 /* composite mass */,
+              kLDyn = 44 /* dynamics tree: parent | level<<8 (signed: root -1, lumped 100) | bypassed kinematic parent<<16 (0xff none) | children<<24 */, kLDChild = 45 /* dynamics children, 8 bits each */,
               kLkFloats = 48 };
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 // ---- block-shared header in front of the link table (floats): the launch's StepLayout (24 ints), children per tree level (8 ints), constants
 enum HdrSlot { kHLayout = 0, kHLvc = 24, kHGrav = 32 /*3*/, kHh = 35, kHScale = 36, kHMu = 37, kHFdt = 38, kHDmax = 39 /* int: deepest level of the dynamics tree */, kHdrFloats = 40 };
 __device__ __forceinline__ float* step_smem() { extern __shared__ __align__(16) float dm_step_sm[]; return dm_step_sm; }
@@ -604,9 +612,10 @@ __device__ __noinline__ void kin_pass(float4 jp, float4 jv) {
     const StepLayout& LY = lay_of(c);
     float* sS = c.E + LY.oR; float* sW = c.E + LY.oW; float* sV = c.E + LY.oV; const float* sB = c.E + LY.oG + 21;
     const float* LKo = c.LK + c.li * kLkFloats;
-    const V3 axis = mk3(LKo[kLAx], LKo[kLAx + 1], LKo[kLAx + 2]);
-    const Q4 zrot = mkq(LKo[kLZr], LKo[kLZr + 1], LKo[kLZr + 2], LKo[kLZr + 3]);
-    const V3 cvec = mk3(LKo[kLC], LKo[kLC + 1], LKo[kLC + 2]);
+    const float4 ax4 = ld4(LKo + kLAx), zr4 = ld4(LKo + kLZr), c4 = ld4(LKo + kLC);
+    const V3 axis = mk3(ax4.x, ax4.y, ax4.z);
+    const Q4 zrot = mkq(zr4.x, zr4.y, zr4.z, zr4.w);
+    const V3 cvec = mk3(c4.x, c4.y, c4.z);
     Q4 cached;
     if (c.jtype == kJSpherical) cached = qmul(mkq(jp.x, jp.y, jp.z, -jp.w), zrot);
     else if (c.jtype == kJRevolute) {
@@ -637,7 +646,8 @@ __device__ __noinline__ void kin_pass(float4 jp, float4 jv) {
         }
     }
     if (c.act) {
-        const V3 dw = mulT(Rwl, mk3(LKo[kLD], LKo[kLD + 1], LKo[kLD + 2]));
+        const float4 d4 = ld4(LKo + kLD);
+        const V3 dw = mulT(Rwl, mk3(d4.x, d4.y, d4.z));
         V3 S0 = mk3(Rwl.m[0], Rwl.m[1], Rwl.m[2]);
         if (c.jtype != kJSpherical) S0 = mulT(Rwl, axis);
         const float wr[12] = {Rwl.m[0], Rwl.m[1], Rwl.m[2], Rwl.m[3], Rwl.m[4], Rwl.m[5], Rwl.m[6], Rwl.m[7], Rwl.m[8], Pw.x, Pw.y, Pw.z};
@@ -671,7 +681,8 @@ __device__ __noinline__ int collide(float* mani, int alive, int mcnt) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) Rwl.m[k] = wrec[k];
     const float thr = LKo[kLThr];
-    const V3 he = mk3(LKo[kLHe], LKo[kLHe + 1], LKo[kLHe + 2]);
+    const float4 he4 = ld4(LKo + kLHe);
+    const V3 he = mk3(he4.x, he4.y, he4.z);
     const V3 pos = mk3(wrec[9] + vrec[6], wrec[10] + vrec[7], wrec[11] + vrec[8]);   // COM, world (Bullet's link collider frame)
     V3 dl = mul(Rwl, mk3(0.f, -1.f, 0.f));   // support direction -n in link coordinates
     V3 vtx;
@@ -805,7 +816,8 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
     const int dchild = reinterpret_cast<const int*>(LKo)[kLDChild];
     const int dmax = reinterpret_cast<const int*>(step_smem())[kHDmax];
     const bool isroot = c.lane == 0;
-    const float mass = c.act ? LKo[kLMc] : 0.f;   // composite mass (own + lumped leaves; 0 for a lumped leaf itself)
+    const float4 dc4 = ld4(LKo + kLDc);           // reference point -> composite COM (link axes) | composite mass
+    const float mass = c.act ? dc4.w : 0.f;       // composite mass (own + lumped leaves; 0 for a lumped leaf itself)
     float q[12];
     ld12(sS + c.li * 12, q);
     const V3 S0 = mk3(q[0], q[1], q[2]), S1 = mk3(q[3], q[4], q[5]), S2 = mk3(q[6], q[7], q[8]), cwk = mk3(q[9], q[10], q[11]);   // cwk: kinematic parent's pivot -> pivot
@@ -848,9 +860,10 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
     float inv0 = 0.f, inv1 = 0.f, inv2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;
     {
         const float* wsel = LKo + (bullet ? kLWb : kLWd);
-        float wl[6];
+        const float4 w4 = ld4(wsel); const float2 w2 = *reinterpret_cast<const float2*>(wsel + 4);
+        float wl[6] = {w4.x, w4.y, w4.z, w4.w, w2.x, w2.y};
 #pragma unroll
-        for (int k = 0; k < 6; ++k) wl[k] = c.act ? wsel[k] : 0.f;
+        for (int k = 0; k < 6; ++k) wl[k] = c.act ? wl[k] : 0.f;
         M3 Rwl;
         {
             float w[12];
@@ -859,7 +872,7 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
             for (int k = 0; k < 9; ++k) Rwl.m[k] = w[k];
         }
         rot_sym(Rwl, wl, IA.ww);     // link axes -> world axes
-        const V3 md = mass * mulT(Rwl, mk3(LKo[kLDc], LKo[kLDc + 1], LKo[kLDc + 2]));   // first moment about the reference point, world axes
+        const V3 md = mass * mulT(Rwl, mk3(dc4.x, dc4.y, dc4.z));   // first moment about the reference point, world axes
         IA.wv[0] = 0.f; IA.wv[1] = -md.z; IA.wv[2] = md.y; IA.wv[3] = md.z; IA.wv[4] = 0.f; IA.wv[5] = -md.x; IA.wv[6] = -md.y; IA.wv[7] = md.x; IA.wv[8] = 0.f;
         IA.vv[0] = mass; IA.vv[1] = 0.f; IA.vv[2] = 0.f; IA.vv[3] = mass; IA.vv[4] = 0.f; IA.vv[5] = mass;
         // h = I v ; pA = I ab + v x* h
@@ -1009,10 +1022,11 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
         if (isroot || dlev == 100) al = shift_m(pk, cwk);
         if (c.act) {   // publish the factors and the advanced link velocity (linear in the generalised velocities; the clamp only acts on exploding states)
             float* u = sU + c.lane * 24;   // U0 U1 U2 are already there (eliminate)
-            u[18] = inv0; u[19] = inv1; u[20] = inv2; u[21] = sqrtf(inv0); u[22] = sqrtf(inv1); u[23] = sqrtf(inv2);
+            *reinterpret_cast<float2*>(u + 18) = make_float2(inv0, inv1);
+            *reinterpret_cast<float4*>(u + 20) = make_float4(inv2, sqrtf(inv0), sqrtf(inv1), sqrtf(inv2));
             float* v = sV + c.lane * 12;
-            v[0] = velk.a.x + h * al.a.x; v[1] = velk.a.y + h * al.a.y; v[2] = velk.a.z + h * al.a.z;
-            v[3] = velk.l.x + h * al.l.x; v[4] = velk.l.y + h * al.l.y; v[5] = velk.l.z + h * al.l.z;
+            *reinterpret_cast<float4*>(v) = make_float4(velk.a.x + h * al.a.x, velk.a.y + h * al.a.y, velk.a.z + h * al.a.z, velk.l.x + h * al.l.x);
+            *reinterpret_cast<float2*>(v + 4) = make_float2(velk.l.y + h * al.l.y, velk.l.z + h * al.l.z);
         }
     }
     __syncwarp();
