@@ -2,7 +2,7 @@
 set -x
 N=${1:-2}
 nvidia-smi topo -m 2>&1 | head -12
-for x in auto nccl; do
+for x in ${3:-auto nccl}; do
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps ${2:-128} --warmup 4 --exchange $x > gpurun_out/bench_n${N}_${x}_r02o.json 2> gpurun_out/bench_n${N}_${x}_r02o.err
 python - <<PY
 import json
