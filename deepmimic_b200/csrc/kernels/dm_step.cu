@@ -8,17 +8,22 @@
 //
 // B200 mapping: one tile of W lanes (16 or 32) per environment, lane = link.  Every linear solve with the joint-space mass
 // matrix is done by the articulated-body recursion (the tree-structured L^T D L factorisation in its O(depth) form): one
-// leaves->root pass builds articulated inertias in registers (parent <- child by warp shuffles), one root->leaves pass
-// propagates accelerations.  The Stable-PD system is the same recursion with dt*Kd added to the joint-space diagonal and
-// DeepMimic's exact-shape inertias; the Bullet sub-steps use Bullet's collision-shape inertias (their unconstrained
-// accelerations are btMultiBody::computeAccelerationsArticulatedBodyAlgorithmMultiDof's).  Constraint rows are built with
-// lanes = rows (each lane walks its row's link chain once), the row coupling matrix J M^-1 J^T is formed explicitly in shared
-// memory and PGS runs in impulse space with lanes = rows (one shuffle + one FMA per row update instead of a reduction).
+// leaves->root pass builds articulated inertias in registers (a link publishes its shifted inertia in shared scratch, its parent
+// adds its children's), one root->leaves pass propagates accelerations; both run on a dynamics tree without the dof-less links
+// (root referred to the base origin, fixed leaves lumped into their parents).  The Stable-PD system is the same recursion with
+// dt*Kd added to the joint-space diagonal and DeepMimic's exact-shape inertias; the Bullet sub-steps use Bullet's collision-shape
+// inertias (their unconstrained accelerations are btMultiBody::computeAccelerationsArticulatedBodyAlgorithmMultiDof's).
+// Constraint rows are built with lanes = rows (each lane walks its row's link chain once), the row coupling matrix
+// J M^-1 J^T is formed explicitly in shared memory with lanes = pairs of contact points (3 x 3 blocks), and PGS runs in impulse
+// space: w = A lambda lives in registers (lane = row), the sequential sweep is evaluated in blocks of two solver steps by every lane
+// redundantly from broadcast row data (the figure of merit is warp instructions per step: the sweeps are issue-bound).
 // All spatial quantities of a link are expressed in WORLD axes about the link's own joint pivot, so passing them between
 // parent and child is a pure shift (no rotation of 6x6 blocks).
 // The update is split into phase routines (kinematics, collision, articulated-body solve, constraint rows + PGS, velocity correction)
 // that are deliberately NOT inlined: they exchange state through the environment's shared-memory block, so each phase gets the full
-// register budget and the main loop only carries the joint state of its link.
+// register budget and the main loop only carries the joint state of its link.  The warps of a block run in lockstep (a barrier after
+// every stage: the ~9 k-instruction loop does not fit the instruction cache otherwise), which makes every unconditional memory burst a
+// contention point: the collision routine touches a link's persistent manifold only when it can matter.
 // No tensor cores: there is no dense contraction here (34 or 70 dofs, tree-sparse); the path is latency-bound.
 #include "dm_model.cuh"
 #include <type_traits>
@@ -561,9 +566,8 @@ struct Ctx {
     float* E;              // this environment's shared-memory block
     const int* LYS;        // layout (shared copy of StepLayout)
     const float* LK;       // block-shared link constants
-    const int* LVC;        // children per tree level
     int lane, li;          // lane in the tile, link index (clamped for idle lanes)
-    int plane, level, ndof, jtype, nchild, child_pack, maxlevel;
+    int plane, level, ndof, jtype, maxlevel;   // kinematic tree (the articulated-body passes read their dynamics tree themselves)
     bool act;
 };
 __device__ __forceinline__ const StepLayout& lay_of(const Ctx& c) { return *reinterpret_cast<const StepLayout*>(c.LYS); }
@@ -571,7 +575,7 @@ template <int W>
 __device__ __forceinline__ Ctx make_ctx() {
     Ctx c;
     float* sm = step_smem();
-    c.LYS = reinterpret_cast<const int*>(sm + kHLayout); c.LVC = reinterpret_cast<const int*>(sm + kHLvc); c.LK = sm + kHdrFloats;
+    c.LYS = reinterpret_cast<const int*>(sm + kHLayout); c.LK = sm + kHdrFloats;
     const StepLayout& LY = *reinterpret_cast<const StepLayout*>(c.LYS);
     const int tile = threadIdx.x / W;
     c.lane = threadIdx.x % W;
@@ -582,8 +586,7 @@ __device__ __forceinline__ Ctx make_ctx() {
     const int info = q[kLInt], tree = q[kLTree];
     const int par = static_cast<int>(static_cast<signed char>(info & 0xff));
     c.plane = par >= 0 ? par : 0; c.jtype = (info >> 8) & 0xff; c.ndof = c.act ? ((info >> 16) & 0xff) : 0;
-    c.level = c.act ? (tree & 0xff) : 1000; c.maxlevel = (tree >> 8) & 0xff; c.nchild = c.act ? ((tree >> 16) & 0xff) : 0;
-    c.child_pack = q[kLChild];
+    c.level = c.act ? (tree & 0xff) : 1000; c.maxlevel = (tree >> 8) & 0xff;
     return c;
 }
 #define DM_ASSUME_SHARED_CTX(c) do { } while (0)
@@ -1141,7 +1144,6 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
     float* LK = sm + kHdrFloats;
     unsigned char* CD = reinterpret_cast<unsigned char*>(LK + nl * kLkFloats);
     unsigned char* CH = CD + nl * nl;
-    int* LVC = reinterpret_cast<int*>(sm + kHLvc);
     int* LYS = reinterpret_cast<int*>(sm + kHLayout);   // shared copy of the layout for the phase routines
     for (int j = threadIdx.x; j < nl; j += blockDim.x) {
         const DevLink& K = M.link[j];
@@ -1217,11 +1219,6 @@ __global__ void __launch_bounds__(kStepMaxThreads, 1) dm_step_kernel(const DevMo
         for (int k = 0; k < static_cast<int>(sizeof(StepLayout) / sizeof(int)); ++k) LYS[k] = src[k];
         sm[kHGrav] = M.gravity[0]; sm[kHGrav + 1] = M.gravity[1]; sm[kHGrav + 2] = M.gravity[2];
         sm[kHh] = static_cast<float>(dt) / static_cast<float>(sim_substeps); sm[kHScale] = M.scale; sm[kHMu] = M.friction; sm[kHFdt] = static_cast<float>(dt);
-    }
-    if (threadIdx.x < 8) {
-        int mx = 0;
-        for (int j = 0; j < nl; ++j) if (M.link[j].level == static_cast<int>(threadIdx.x)) mx = max(mx, M.link[j].nchild);
-        LVC[threadIdx.x] = mx;
     }
     if (threadIdx.x == 8) {   // deepest level of the dynamics tree (levels of the links with dofs, the root's children being level 0)
         int mx = 0;
