@@ -17,7 +17,7 @@ class DmDims(C.Structure):
 
 DM_STATE_OFFSET, DM_STATE_SCALE, DM_ACTION_OFFSET, DM_ACTION_SCALE, DM_ACTION_BOUND_MIN, DM_ACTION_BOUND_MAX, DM_STATE_NORM_GROUPS = range(7)
 
-EXPORTS = ["dm_create", "dm_load_host", "dm_get_model_info", "dm_get_link_table", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_get_scene_name", "dm_stream", "dm_sync", "dm_set_mode", "dm_set_sample_count", "dm_get_time_limits", "dm_reset", "dm_set_action",
+EXPORTS = ["dm_create", "dm_load_host", "dm_plan_launch", "dm_get_model_info", "dm_get_link_table", "dm_destroy", "dm_last_error", "dm_get_dims", "dm_get_static", "dm_get_scene_name", "dm_stream", "dm_sync", "dm_set_mode", "dm_set_sample_count", "dm_get_time_limits", "dm_reset", "dm_set_action",
            "dm_update", "dm_record_state", "dm_record_goal", "dm_goal_host", "dm_reset_clips", "dm_record_amp_obs_expert_clips", "dm_get_clip_table", "dm_get_task_state", "dm_set_task_state", "dm_get_task_params", "dm_calc_reward", "dm_calc_reward_imitate", "dm_record_amp_obs_agent", "dm_record_amp_obs_expert", "dm_amp_obs_host", "dm_observe", "dm_get_flags", "dm_step_host", "dm_step_host_reset", "dm_set_time_limits", "dm_exchange_create", "dm_exchange_connect", "dm_exchange_publish", "dm_exchange_acquire", "dm_exchange_release", "dm_exchange_status", "dm_exchange_destroy", "dm_set_timing", "dm_step_host_timing", "dm_get_snapshot",
            "dm_set_snapshot", "dm_get_counters", "dm_debug_enable", "dm_get_debug", "dm_mlp_create", "dm_mlp_forward", "dm_mlp_launches", "dm_mlp_destroy"]
 
@@ -36,6 +36,7 @@ def lib():
         L.dm_load_host.restype = vp
         L.dm_load_host.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p)]
         L.dm_get_model_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
+        L.dm_plan_launch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.dm_get_link_table.argtypes = [vp, dp]
         L.dm_last_error.restype = C.c_char_p
         L.dm_get_dims.argtypes = [vp, C.POINTER(DmDims)]
@@ -186,6 +187,14 @@ class BatchedCore:
         b = np.ascontiguousarray(block, dtype=np.float64)
         self._chk(lib().dm_set_task_state(self.h, env, _dptr(b)))
 
+    def plan_launch(self, num_envs, smem_bytes_per_block=232448, num_sms=148):
+        """dm_plan_launch: launch plan of the step kernel on a device with that much opt-in shared memory per block and that many SMs (B200 defaults)"""
+        out = (C.c_int * 9)()
+        if lib().dm_plan_launch(self.h, int(num_envs), int(smem_bytes_per_block), int(num_sms), out) != 0:
+            raise RuntimeError(lib().dm_last_error().decode())
+        keys = ("tile_width", "envs_per_block", "blocks", "smem_bytes", "max_rows", "env_floats", "hot_floats", "y_offset", "padded_envs")
+        return dict(zip(keys, [int(v) for v in out]))
+
     def task_params(self):
         out = np.zeros(48, dtype=np.float64)     # [0:16] dm_task.cuh constants, [16:48] dm_task_ext.cuh constants
         key = (C.c_uint64 * 2)()
@@ -309,6 +318,14 @@ class HostModel:
         if lib().dm_get_static(self.h, kind, _dptr(out)) != 0:
             raise RuntimeError(lib().dm_last_error().decode())
         return out
+
+    def plan_launch(self, num_envs, smem_bytes_per_block=232448, num_sms=148):
+        """dm_plan_launch: launch plan of the step kernel on a device with that much opt-in shared memory per block and that many SMs (B200 defaults)"""
+        out = (C.c_int * 9)()
+        if lib().dm_plan_launch(self.h, int(num_envs), int(smem_bytes_per_block), int(num_sms), out) != 0:
+            raise RuntimeError(lib().dm_last_error().decode())
+        keys = ("tile_width", "envs_per_block", "blocks", "smem_bytes", "max_rows", "env_floats", "hot_floats", "y_offset", "padded_envs")
+        return dict(zip(keys, [int(v) for v in out]))
 
     def task_params(self):
         out = np.zeros(48, dtype=np.float64)     # [0:16] dm_task.cuh constants, [16:48] dm_task_ext.cuh constants

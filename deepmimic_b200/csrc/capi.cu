@@ -421,6 +421,37 @@ int launch_reset(dm_handle* h, int force, const double* kt, const double* mt, co
 
 }  // namespace
 
+// Launch plan of dm_step_kernel: tile width, row capacity, shared-memory layout, environments per block (one block per SM: as many
+// environments per block as shared memory and kStepMaxThreads allow, balanced over the SMs), padded environment count.  Pure host arithmetic
+// (also reachable without a device through dm_plan_launch, for the CPU tests of the one-wave property).
+static bool plan_launch(dm_handle& H, int num_envs, int smem_optin, int sms, int max_tiles_env) {
+    const auto& M = H.hm;
+    H.W = (M.nl <= 16) ? 16 : 32;   // lanes per environment: one lane per link
+    if (const char* w = std::getenv("DM_TILE_WIDTH")) { int v = std::atoi(w); if (v == 32 || (v == 16 && M.nl <= 16)) H.W = v; }
+    H.maxrows = dmk::dm_step_y_stride(H.W);   // humanoid3d: 8 foot points x 3 + limit rows <= 28 of 32; dog3d: 4 feet x 4 points x 3 + 4 limit rows = 52
+    if (const char* r = std::getenv("DM_MAX_ROWS")) { int v = std::atoi(r); if (v >= 12 && v <= dmk::dm_step_y_stride(H.W)) H.maxrows = v; }
+    int chain_len = 0;
+    for (int j = 0; j < M.nl; ++j) chain_len = std::max(chain_len, M.link[j].last_depth + 1);
+    dmk::dm_step_layout(M.nl, M.n, chain_len, H.maxrows, H.W, &H.lay);
+    const int per_env = H.lay.env_floats * 4;
+    const int hot = H.lay.hot_floats * 4 + 1024;
+    int max_tiles = std::min(dmk::kStepMaxThreads / H.W, (smem_optin - hot) / per_env);
+    if (max_tiles_env > 0) max_tiles = std::min(max_tiles, std::max(H.W == 16 ? 2 : 1, max_tiles_env));
+    const int min_tiles = (H.W == 16) ? 2 : 1;   // W = 16: two environments share a warp
+    if (max_tiles < min_tiles) {
+        g_err = "not enough shared memory per block for one environment tile (need " + std::to_string(hot + min_tiles * per_env) + " bytes, the device offers " +
+                std::to_string(static_cast<long long>(smem_optin)) + ")";
+        return false;
+    }
+    int tiles = std::min(max_tiles, std::max(min_tiles, (num_envs + sms - 1) / sms));
+    if (H.W == 16 && (tiles & 1)) tiles = (tiles + 1 <= max_tiles) ? tiles + 1 : tiles - 1;   // whole warps; tiles >= 2 here, so tiles - 1 >= 2 when odd
+    H.tiles = tiles;
+    const int quantum = (tiles * (64 / H.W)) / std::__gcd(tiles, 64 / H.W);   // multiple of both the update block and the 64-thread policy blocks
+    H.padded_envs = ((num_envs + quantum - 1) / quantum) * quantum;
+    H.smem_bytes = dmk::dm_step_smem_bytes(H.lay, H.tiles) + 1024;
+    return true;
+}
+
 extern "C" {
 
 const char* dm_last_error(void) { return g_err.c_str(); }
@@ -481,6 +512,16 @@ dm_handle* dm_load_host(const char* asset_root, int argc, const char** argv) {
     return h.release();
 }
 
+int dm_plan_launch(dm_handle* h, int num_envs, int smem_bytes_per_block, int num_sms, int* out) {
+    if (!h || num_envs <= 0 || num_sms <= 0) { g_err = "dm_plan_launch: bad arguments"; return fail(); }
+    dm_handle tmp;
+    tmp.hm = h->hm;
+    if (!plan_launch(tmp, num_envs, smem_bytes_per_block, num_sms, 0)) return fail();
+    out[0] = tmp.W; out[1] = tmp.tiles; out[2] = tmp.padded_envs / tmp.tiles; out[3] = tmp.smem_bytes; out[4] = tmp.maxrows; out[5] = tmp.lay.env_floats;
+    out[6] = tmp.lay.hot_floats; out[7] = tmp.lay.oY; out[8] = tmp.padded_envs;
+    return 0;
+}
+
 int dm_get_model_info(dm_handle* h, int kind, int* out) {
     const auto& M = h->hm;
     switch (kind) {
@@ -522,35 +563,13 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
     h->device = device; h->seed = seed; h->env_offset = global_env_offset; h->num_envs = num_envs;
     h->hm.task_seed = seed ^ 0x7461736b73ull; h->hm.env_id_base = global_env_offset;   // the model blob is uploaded below
     const auto& M = h->hm;
-    h->W = (M.nl <= 16) ? 16 : 32;   // lanes per environment: one lane per link
-    if (const char* w = std::getenv("DM_TILE_WIDTH")) { int v = std::atoi(w); if (v == 32 || (v == 16 && M.nl <= 16)) h->W = v; }
-    h->maxrows = dmk::dm_step_y_stride(h->W);   // humanoid3d: 8 foot points x 3 + limit rows <= 28 of 32; dog3d: 4 feet x 4 points x 3 + 4 limit rows = 52
     if (const char* sv = std::getenv("DM_SYNC_EVERY_STAGE")) h->sync_every_stage = std::atoi(sv);
-    if (const char* r = std::getenv("DM_MAX_ROWS")) { int v = std::atoi(r); if (v >= 12 && v <= dmk::dm_step_y_stride(h->W)) h->maxrows = v; }
     {
-        // one block per SM: as many environments per block as shared memory (227 KB) and 512 threads allow, balanced over the SMs
         cudaDeviceProp prop;
         if (!chk(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { fail(); return nullptr; }
-        int chain_len = 0;
-        for (int j = 0; j < M.nl; ++j) chain_len = std::max(chain_len, M.link[j].last_depth + 1);
-        dmk::dm_step_layout(M.nl, M.n, chain_len, h->maxrows, h->W, &h->lay);
-        const int per_env = h->lay.env_floats * 4;
-        const int hot = h->lay.hot_floats * 4 + 1024;
-        int max_tiles = std::min(dmk::kStepMaxThreads / h->W, (static_cast<int>(prop.sharedMemPerBlockOptin) - hot) / per_env);
-        if (const char* t = std::getenv("DM_TILES_PER_BLOCK")) max_tiles = std::min(max_tiles, std::max(h->W == 16 ? 2 : 1, std::atoi(t)));
-        const int min_tiles = (h->W == 16) ? 2 : 1;   // W = 16: two environments share a warp
-        if (max_tiles < min_tiles) {
-            g_err = "not enough shared memory per block for one environment tile (need " + std::to_string(hot + min_tiles * per_env) + " bytes, the device offers " +
-                    std::to_string(static_cast<long long>(prop.sharedMemPerBlockOptin)) + ")";
-            fail(); return nullptr;
-        }
-        const int sms = prop.multiProcessorCount;
-        int tiles = std::min(max_tiles, std::max(min_tiles, (num_envs + sms - 1) / sms));
-        if (h->W == 16 && (tiles & 1)) tiles = (tiles + 1 <= max_tiles) ? tiles + 1 : tiles - 1;   // whole warps; tiles >= 2 here, so tiles - 1 >= 2 when odd
-        h->tiles = tiles;
-        const int quantum = (tiles * (64 / h->W)) / std::__gcd(tiles, 64 / h->W);   // multiple of both the update block and the 64-thread policy blocks
-        h->padded_envs = ((num_envs + quantum - 1) / quantum) * quantum;
-        h->smem_bytes = dmk::dm_step_smem_bytes(h->lay, h->tiles) + 1024;
+        int max_tiles_env = 0;
+        if (const char* t = std::getenv("DM_TILES_PER_BLOCK")) max_tiles_env = std::atoi(t);
+        if (!plan_launch(*h, num_envs, static_cast<int>(prop.sharedMemPerBlockOptin), prop.multiProcessorCount, max_tiles_env)) { fail(); return nullptr; }
     }
     const size_t N = static_cast<size_t>(h->padded_envs);
     const int ss = dmk::sim_stride(M.nl);

@@ -60,6 +60,11 @@ dm_handle* dm_create(const char* asset_root, int argc, const char** argv, int nu
  * cDeepMimicCore::ParseArgs + SetupScene's loaders, DeepMimicCore.cpp:40-86): needs no CUDA device.  The handle answers
  * dm_get_dims / dm_get_static / dm_get_model_info; every compute entry point returns an error on it (no CPU fallback). */
 dm_handle* dm_load_host(const char* asset_root, int argc, const char** argv);
+/* Launch plan of the step kernel for `num_envs` environments on a device with `smem_bytes_per_block` opt-in shared memory per block and `num_sms`
+ * multiprocessors (host arithmetic, valid on dm_load_host handles; B200: 232448 bytes, 148 SMs).  out[9] = {tile width (lanes per environment),
+ * environments per block, blocks, dynamic shared memory per block, solver row capacity, floats per environment block, floats of the block-shared
+ * tables, offset of the Y block, padded environment count}.  The default configurations are planned as ONE wave (blocks <= SMs). */
+int dm_plan_launch(dm_handle* h, int num_envs, int smem_bytes_per_block, int num_sms, int* out9);
 enum dm_model_info_kind {
     DM_INFO_PARENTS = 0, DM_INFO_JOINT_TYPES = 1 /* 0 revolute 1 spherical 2 fixed */, DM_INFO_DOF_OFFSETS = 2, DM_INFO_POSE_OFFSETS = 3,
     DM_INFO_FALL_BODIES = 4, DM_INFO_END_EFFECTORS = 5, DM_INFO_LAYOUT = 6 /* {links, 6+dofs, chain stride, tree depth, frames, loop} */

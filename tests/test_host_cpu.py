@@ -309,3 +309,25 @@ def test_malformed_assets_are_rejected_with_messages(asset_root, tmp_path):
     for ds in (ds_missing, ds_empty, write("ds_nokey.txt", {"Clips": []})):
         with pytest.raises(RuntimeError):
             Oracle(["--kin_ctrl", "clips", "--motion_file", ds] + base, asset_root)
+
+
+@pytest.mark.parametrize("arg_file,envs,width,per_block,rows", [("args/train_humanoid3d_spinkick_args.txt", 4096, 16, 28, 32),
+                                                                 ("args/train_dog3d_trot_args.txt", 2048, 32, 14, 52),
+                                                                 ("args/train_amp_target_humanoid3d_locomotion_args.txt", 4096, 16, 28, 32)])
+def test_launch_plan_of_the_baseline_configurations_is_one_wave_on_a_b200(asset_root, arg_file, envs, width, per_block, rows):
+    """dm_plan_launch (host arithmetic of dm_create): the BASELINE.json configurations run dm_step_kernel as ONE wave of blocks on the 148 SMs of a
+    B200 with 227 KB of shared memory per block -- dog3d only since its row capacity went from 60 to 52 (171 blocks in two waves before) -- the
+    16-byte alignment the kernels' 128-bit accesses rely on holds, and a device with too little shared memory is refused with an error."""
+    from deepmimic_b200.capi import HostModel
+    extra = ["--motion_file", "data/datasets/synthetic_locomotion_56.txt"] if "_amp_" in arg_file else []
+    hm = HostModel(extra + ["--arg_file", arg_file], asset_root)
+    p = hm.plan_launch(envs)
+    assert p["tile_width"] == width and p["envs_per_block"] == per_block and p["max_rows"] == rows
+    assert p["blocks"] <= 148 and p["blocks"] * p["envs_per_block"] == p["padded_envs"] >= envs
+    assert p["smem_bytes"] <= 232448
+    assert p["env_floats"] % 16 == 0 and p["hot_floats"] % 4 == 0 and p["y_offset"] % 4 == 0
+    assert p["smem_bytes"] == 4 * (p["hot_floats"] + p["envs_per_block"] * p["env_floats"]) + 1024
+    half = hm.plan_launch(envs // 8)                     # fewer environments: fewer per block, still whole warps for the 16-lane tiles
+    assert half["envs_per_block"] <= per_block and (width == 32 or half["envs_per_block"] % 2 == 0)
+    with pytest.raises(RuntimeError):
+        hm.plan_launch(envs, smem_bytes_per_block=8 * 1024)
