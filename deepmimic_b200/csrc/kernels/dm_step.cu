@@ -589,7 +589,6 @@ __device__ __forceinline__ Ctx make_ctx() {
     c.level = c.act ? (tree & 0xff) : 1000; c.maxlevel = (tree >> 8) & 0xff;
     return c;
 }
-#define DM_ASSUME_SHARED_CTX(c) do { } while (0)
 __device__ __forceinline__ S6 shift_m(S6 m, V3 c) { return mks(m.a, m.l + cross(m.a, c)); }   // motion vector: reference point moved by +c
 __device__ __forceinline__ S6 shift_f(S6 f, V3 c) { return mks(f.a + cross(c, f.l), f.l); }   // force vector: child pivot -> parent pivot (child = parent + c)
 __device__ __forceinline__ float cl100(float v) { return fminf(fmaxf(v, -100.f), 100.f); }   // applyDeltaVeeMultiDof clamp
@@ -611,7 +610,6 @@ template <int W>
 __device__ __noinline__ void kin_pass(float4 jp, float4 jv) {
     const Ctx c = make_ctx<W>();
     using T = Tl<W>;
-    DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
     float* sS = c.E + LY.oR; float* sW = c.E + LY.oW; float* sV = c.E + LY.oV; const float* sB = c.E + LY.oG + 21;
     const float* LKo = c.LK + c.li * kLkFloats;
@@ -670,7 +668,6 @@ __device__ __noinline__ int collide(float* mani, int alive, int mcnt) {
     const Ctx c = make_ctx<W>();
     const float scale = step_smem()[kHScale];
     using T = Tl<W>;
-    DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
     const float* sW = c.E + LY.oW; const float* sV = c.E + LY.oV;
     float* sPp = c.E + LY.oPp; float* sPi = c.E + LY.oPi; int* sPr = reinterpret_cast<int*>(c.E + LY.oPr);
@@ -808,7 +805,6 @@ __device__ __noinline__ float3 aba_solve(float g0, float g1, float g2, float kdt
     const Ctx c = make_ctx<W>();
     const float gx = step_smem()[kHGrav], gy = step_smem()[kHGrav + 1], gz = step_smem()[kHGrav + 2], h = step_smem()[kHh];
     using T = Tl<W>;
-    DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
     float* sU = c.E + LY.oU; const float* sS = c.E + LY.oR; const float* sW = c.E + LY.oW; float* sV = c.E + LY.oV; float* sG = c.E + LY.oG; float* sB = sG + 21;
     const float* LKo = c.LK + c.li * kLkFloats;
@@ -1042,7 +1038,6 @@ template <int W>
 __device__ __noinline__ float3 dv_pass() {
     const Ctx c = make_ctx<W>();
     using T = Tl<W>;
-    DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
     const float* sU = c.E + LY.oU; const float* sS = c.E + LY.oR; float* sG = c.E + LY.oG; float* sB = sG + 21; const float* sZ = c.E + LY.oZ;
     float q[12], u[24];
@@ -1099,7 +1094,6 @@ template <int W>
 __device__ __noinline__ void vel_pass(float jvx, float jvy, float jvz, bool want) {
     const Ctx c = make_ctx<W>();
     using T = Tl<W>;
-    DM_ASSUME_SHARED_CTX(c);
     const StepLayout& LY = lay_of(c);
     const float* sS = c.E + LY.oR; float* sV = c.E + LY.oV; const float* sB = c.E + LY.oG + 21;
     float q[12];

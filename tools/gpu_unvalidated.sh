@@ -9,5 +9,3 @@ timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
 timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -3
 timeout 300 python bench.py 2>&1 | tail -2
 # A/B of the address-space hints: same bench through the library built without them
-(cd deepmimic_b200/csrc && make nohints >/dev/null 2>&1)
-DM_LIB=$PWD/deepmimic_b200/libdeepmimic_b200_nohints.so timeout 300 python bench.py --no-cpu-baseline 2>&1 | tail -1
